@@ -1,0 +1,149 @@
+/* xped_b200 -- C ABI of the B200-native backend for the Xped block-sparse symmetric-tensor hot path.
+ *
+ * Drop-in boundary: Xped selects its dense backend at compile time through the
+ * `PlainInterface` policy struct (include/Xped/Interfaces/PlainInterface.hpp:102-110, CMake
+ * XPED_{MATRIX,TENSOR,VECTOR}_LIB + XPED_STORAGE, CMakeLists.txt:35-70).  That per-block interface is too
+ * fine grained for a device (one launch per tree pair) and is not sealed (Core reaches into Eigen directly,
+ * src/Core/Tensor.cpp:661-676,768-772), so this library sits one level higher: each entry point replaces one
+ * public method of `Xped::Tensor<double,Rank,CoRank,Symmetry>` / `TensorBase` as cited below.  A new
+ * `XPED_MATRIX_LIB=B200` + `XPED_STORAGE=DeviceArena` choice binds these symbols.
+ *
+ * Conventions: every function returns 0 on success or an xb_status; xb_last_error() gives the message.
+ * Handles own device memory; functions never free their inputs; outputs are fresh handles released with
+ * xb_*_free.  Plain pointers and sizes only.  All work is enqueued on the context's CUDA stream; functions
+ * that return host values (download, norms, tSVD truncation) synchronise that stream.
+ * There is NO CPU fallback: xb_ctx_create fails with XB_ERR_NO_DEVICE when no CUDA device is visible.
+ */
+#ifndef XPED_B200_H_
+#define XPED_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xb_ctx xb_ctx;
+typedef struct xb_basis xb_basis;   /* Qbasis<Symmetry,1>  (include/Xped/Core/Qbasis.hpp:37-268) */
+typedef struct xb_tensor xb_tensor; /* Tensor<double,Rank,CoRank,Symmetry> (include/Xped/Core/Tensor.hpp:59-444) */
+typedef struct xb_ctm xb_ctm;       /* CTM<double,Symmetry,2> (include/Xped/PEPS/CTM.hpp:60-312) */
+
+enum xb_status {
+    XB_OK = 0,
+    XB_ERR_INVALID = 1,   /* bad argument / basis or shape mismatch (reference: assert / DEBUG_ASSERT) */
+    XB_ERR_NO_DEVICE = 2, /* no CUDA device: the product path never falls back to the CPU */
+    XB_ERR_CUDA = 3,
+    XB_ERR_NOMEM = 4,     /* reference: std::bad_alloc rethrow, StorageType_contiguous.hpp:91-96 */
+    XB_ERR_INTERNAL = 5
+};
+
+/* Symmetry factors: Sym::U0, Sym::U1<Kind>, Sym::ZN<Kind,N>, Sym::SU2<Kind>; products (Sym::S1xS2 / Combined)
+ * are given as a list.  `fermionic` selects the FChargeU1 / FChargeSU2 style kinds. */
+enum xb_sym_kind { XB_SYM_U0 = 0, XB_SYM_U1 = 1, XB_SYM_ZN = 2, XB_SYM_SU2 = 3 };
+typedef struct xb_sym_factor { int kind; int N; int fermionic; } xb_sym_factor;
+
+const char* xb_last_error(void);
+const char* xb_version(void);
+
+/* ---- context: one per GPU / host thread (replaces mpi::XpedWorld threading, include/Xped/Util/Mpi.hpp:17-47) */
+int xb_ctx_create(xb_ctx** ctx, int device, const xb_sym_factor* factors, int n_factors);
+int xb_ctx_free(xb_ctx* ctx);
+int xb_ctx_sync(xb_ctx* ctx);
+int xb_ctx_nq(const xb_ctx* ctx);
+/* counters: [0] kernel launches, [1] permute-plan cache hits, [2] plan cache misses */
+int xb_ctx_stats(const xb_ctx* ctx, int64_t out[3]);
+
+/* ---- Qbasis<Symmetry,1> ------------------------------------------------------------------------------
+ * q: n * Nq ints (qarray<Nq> per sector, include/Xped/Symmetry/qarray.hpp:29-80), dims: n inner dims.
+ * Sectors are push_back()ed in the given order (src/Core/Qbasis.cpp:34-74); equal q merge. */
+int xb_basis_create(xb_ctx* ctx, const int* q, const int64_t* dims, int n, xb_basis** out);
+int xb_basis_free(xb_basis* b);
+int xb_basis_conj(const xb_basis* b, xb_basis** out);                  /* Qbasis::conj, Qbasis.cpp:418-439 */
+int xb_basis_sorted(const xb_basis* b, xb_basis** out);                /* copy + Qbasis::sort, Qbasis.cpp:306-331 */
+int xb_basis_combine(const xb_basis* a, const xb_basis* b, xb_basis** out); /* combine().forgetHistory(), :441-495,:410-416 */
+int xb_basis_size(const xb_basis* b, int* n_sectors, int64_t* dim, int64_t* full_dim, int* is_conj);
+int xb_basis_get(const xb_basis* b, int* q /* n*Nq */, int64_t* dims /* n */);
+
+/* ---- Tensor construction / storage ---------------------------------------------------------------------
+ * xb_tensor_create: Tensor(basis_domain, basis_codomain) + setZero()  (Tensor.hpp:106-110, Tensor.cpp:46-55) */
+int xb_tensor_create(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, xb_tensor** out);
+int xb_tensor_free(xb_tensor* t);
+int xb_tensor_clone(const xb_tensor* t, xb_tensor** out);
+int xb_tensor_rank(const xb_tensor* t, int* rank, int* corank);
+int xb_tensor_leg_basis(const xb_tensor* t, int leg, xb_basis** out);  /* uncoupledDomain()/uncoupledCodomain() */
+int64_t xb_tensor_plain_size(const xb_tensor* t);                      /* plainSize(), StorageType_contiguous.hpp:149 */
+int xb_tensor_num_sectors(const xb_tensor* t);
+/* sector(i), block(i).rows()/cols(), m_offsets[i]: the data the bit-exact structure tests compare */
+int xb_tensor_structure(const xb_tensor* t, int* q /* nsec*Nq */, int64_t* rows, int64_t* cols, int64_t* offsets);
+/* number of (tree, cotree) pairs and, per pair: sector index, row offset (leftOffset), col offset, rows, cols */
+int64_t xb_tensor_num_tree_pairs(const xb_tensor* t);
+int xb_tensor_tree_pairs(const xb_tensor* t, int64_t* out5 /* npairs*5 */);
+/* raw `m_data` image, host <-> device (Tensor::data()/set_data(), Tensor.hpp:137-152) */
+int xb_tensor_upload(xb_tensor* t, const double* host, int64_t n);
+int xb_tensor_download(const xb_tensor* t, double* host, int64_t n);
+int xb_tensor_set_zero(xb_tensor* t);
+int xb_tensor_set_identity(xb_tensor* t);                              /* Tensor.cpp:57-68 */
+int xb_tensor_set_constant(xb_tensor* t, double v);                    /* Tensor.cpp:70-81 */
+/* counter-based uniform[-1,1] fill keyed by (seed, element index): same values as the oracle's helper */
+int xb_tensor_set_random(xb_tensor* t, uint64_t seed);
+
+/* ---- hot path --------------------------------------------------------------------------------------------*/
+/* Tensor::permute<shift,p...>()  src/Core/Tensor.cpp:335-355 (-> permute_impl :83-146 / :148-214) */
+int xb_permute(xb_ctx* ctx, const xb_tensor* t, int shift, const int* p, int n, xb_tensor** out);
+/* Tensor::permute_adj<shift,p...>()  src/Core/Tensor.cpp:258-333 (AD reverse rule, ADTensor.hpp:171-185) */
+int xb_permute_adj(xb_ctx* ctx, const xb_tensor* t, int shift, const int* p, int n, xb_tensor** out);
+/* TensorBase::operator*  src/Core/TensorBase.cpp:243-288; adj_a/adj_b read an operand as its lazy AdjointOp
+ * (include/Xped/Core/AdjointOp.hpp:26-69), which is also what the GEMM reverse rules need (ADTensor.hpp:749-758) */
+int xb_multiply(xb_ctx* ctx, const xb_tensor* a, int adj_a, const xb_tensor* b, int adj_b, xb_tensor** out);
+/* Tensor::contract<a1,a2,ResRank>()  include/Xped/Core/Tensor.hpp:328-351 (labels as in NCON: >0 contracted, <0 open) */
+int xb_contract(xb_ctx* ctx, const xb_tensor* a, const int* labels_a, int na, const xb_tensor* b, const int* labels_b, int nb,
+                int res_rank, xb_tensor** out);
+/* TensorBase::adjoint().eval()  TensorBase.cpp:82-86, AdjointOp.hpp:44-65 */
+int xb_adjoint(xb_ctx* ctx, const xb_tensor* t, xb_tensor** out);
+/* Tensor::twist(leg)  src/Core/Tensor.cpp:357-377 */
+int xb_twist(xb_ctx* ctx, const xb_tensor* t, int leg, xb_tensor** out);
+/* alpha*x (+ beta*y): operator*(scalar), operator+/-  (TensorBase.hpp:197-209, CoeffBinaryOp.hpp:44-64); y may be NULL */
+int xb_axpby(xb_ctx* ctx, double alpha, const xb_tensor* x, double beta, const xb_tensor* y, xb_tensor** out);
+/* diag_sqrt / diag_inv  TensorBase.cpp:191-202; op: 0 = sqrt, 1 = inv, 2 = inv(sqrt) */
+int xb_diag_map(xb_ctx* ctx, const xb_tensor* t, int op, xb_tensor** out);
+int xb_max_norm(xb_ctx* ctx, const xb_tensor* t, double* out);        /* TensorBase.cpp:48-56 */
+int xb_trace(xb_ctx* ctx, const xb_tensor* t, double* out);           /* TensorBase.cpp:27-37 */
+int xb_squared_norm(xb_ctx* ctx, const xb_tensor* t, double* out);    /* TensorBase.cpp:58-64 */
+/* Tensor::tSVD(maxKeep, eps_svd, truncWeight, entropy, ..., PRESERVE_MULTIPLETS)  src/Core/Tensor.cpp:478-633.
+ * trunc_weight / entropy are in-out accumulators like the reference's reference parameters. */
+int xb_tsvd(xb_ctx* ctx, const xb_tensor* t, int64_t max_keep, double eps_svd, int preserve_multiplets, xb_tensor** U, xb_tensor** S,
+            xb_tensor** Vdag, double* trunc_weight, double* entropy);
+/* reverse rule of the full SVD + truncation  include/Xped/AD/ADTensor.hpp:253-325,356-371 */
+int xb_tsvd_backward(xb_ctx* ctx, const xb_tensor* A, const xb_tensor* U, const xb_tensor* S, const xb_tensor* Vdag, const xb_tensor* dU,
+                     const xb_tensor* dS, const xb_tensor* dVdag, xb_tensor** dA);
+/* Tensor::tQR()  src/Core/Tensor.cpp:757-780 (tall blocks) ; Tensor::teigh()  :782-803 */
+int xb_tqr(xb_ctx* ctx, const xb_tensor* t, xb_tensor** Q, xb_tensor** R);
+int xb_teigh(xb_ctx* ctx, const xb_tensor* t, xb_tensor** D, xb_tensor** V);
+/* decompose(T1,T2,chi)  src/PEPS/PEPSContractions.cpp:18-43: CTM projectors P1 = S^-1/2 U^+ T1, P2 = T2 V S^-1/2 */
+int xb_decompose(xb_ctx* ctx, const xb_tensor* T1, const xb_tensor* T2, int64_t chi, xb_tensor** P1, xb_tensor** P2);
+/* contract_L / contract_R  src/MPS/MpsContractions.cpp:11-51 / :54-105 */
+int xb_contract_L(xb_ctx* ctx, const xb_tensor* Bold, const xb_tensor* Bra, const xb_tensor* Ket, xb_tensor** Bnew);
+int xb_contract_R(xb_ctx* ctx, const xb_tensor* Bold, const xb_tensor* Bra, const xb_tensor* Ket, xb_tensor** Bnew);
+
+/* ---- CTM driver (1x1 unit cell, TRank = 2, corner projectors)  src/PEPS/CTM.cpp:45-244,385-420,924-1760 ------
+ * A: iPEPS site tensor Tensor<double,2,3> (left, top | right, bottom, phys), include/Xped/PEPS/iPEPS.hpp. */
+int xb_ctm_create(xb_ctx* ctx, const xb_tensor* A, int64_t chi, xb_ctm** out);   /* CTM(A, chi, FROM_A) + init() */
+int xb_ctm_free(xb_ctm* c);
+int xb_ctm_step(xb_ctm* c);                                                      /* grow_all(): left, right, top, bottom move */
+/* which: 0..3 = C1..C4, 4..7 = T1..T4, 8 = A, 9 = Adag. Returns a clone. */
+int xb_ctm_get(const xb_ctm* c, int which, xb_tensor** out);
+int xb_ctm_set(xb_ctm* c, int which, const xb_tensor* t);
+/* single directional pieces, for parity tests: corner 0..3 = UL, UR, LR, LL (Opts::CORNER) */
+int xb_ctm_corner(xb_ctm* c, int corner, xb_tensor** Q);                         /* contractCorner  CTM.cpp:1643-1760 */
+int xb_ctm_move(xb_ctm* c, int direction);                                       /* 0 left, 1 right, 2 top, 3 bottom  :924-1183 */
+
+/* ---- micro-benchmark hooks (device-resident, timed with CUDA events on the context stream) -------------- */
+/* runs `reps` launches of the cached plan of permute<shift,p>(t); returns avg ms per launch and algorithmic bytes */
+int xb_bench_permute(xb_ctx* ctx, const xb_tensor* t, int shift, const int* p, int n, int reps, double* ms_per_launch, int64_t* bytes);
+int xb_bench_multiply(xb_ctx* ctx, const xb_tensor* a, const xb_tensor* b, int reps, double* ms_per_launch, double* flops);
+int xb_flush_l2(xb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XPED_B200_H_ */

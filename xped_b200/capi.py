@@ -1,0 +1,115 @@
+"""ctypes binding of include/xped_b200.h -- the one and only way Python reaches the product.
+
+The shared library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a). Loading it does not need a
+GPU (symbol checks run on CPU); creating a context does, and fails loudly without one: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libxped_b200.so")
+
+
+class XbError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"xped_b200 status {status}: {msg}")
+        self.status = status
+
+
+class SymFactor(C.Structure):
+    _fields_ = [("kind", C.c_int), ("N", C.c_int), ("fermionic", C.c_int)]
+
+
+P = C.c_void_p
+PP = C.POINTER(C.c_void_p)
+IP = C.POINTER(C.c_int)
+LP = C.POINTER(C.c_int64)
+DP = C.POINTER(C.c_double)
+
+# name -> (restype, argtypes); mirrors include/xped_b200.h declaration by declaration
+SIGNATURES = {
+    "xb_last_error": (C.c_char_p, []),
+    "xb_version": (C.c_char_p, []),
+    "xb_ctx_create": (C.c_int, [PP, C.c_int, C.POINTER(SymFactor), C.c_int]),
+    "xb_ctx_free": (C.c_int, [P]),
+    "xb_ctx_sync": (C.c_int, [P]),
+    "xb_ctx_nq": (C.c_int, [P]),
+    "xb_ctx_stats": (C.c_int, [P, LP]),
+    "xb_basis_create": (C.c_int, [P, IP, LP, C.c_int, PP]),
+    "xb_basis_free": (C.c_int, [P]),
+    "xb_basis_conj": (C.c_int, [P, PP]),
+    "xb_basis_sorted": (C.c_int, [P, PP]),
+    "xb_basis_combine": (C.c_int, [P, P, PP]),
+    "xb_basis_size": (C.c_int, [P, IP, LP, LP, IP]),
+    "xb_basis_get": (C.c_int, [P, IP, LP]),
+    "xb_tensor_create": (C.c_int, [P, PP, C.c_int, PP, C.c_int, PP]),
+    "xb_tensor_free": (C.c_int, [P]),
+    "xb_tensor_clone": (C.c_int, [P, PP]),
+    "xb_tensor_rank": (C.c_int, [P, IP, IP]),
+    "xb_tensor_leg_basis": (C.c_int, [P, C.c_int, PP]),
+    "xb_tensor_plain_size": (C.c_int64, [P]),
+    "xb_tensor_num_sectors": (C.c_int, [P]),
+    "xb_tensor_structure": (C.c_int, [P, IP, LP, LP, LP]),
+    "xb_tensor_num_tree_pairs": (C.c_int64, [P]),
+    "xb_tensor_tree_pairs": (C.c_int, [P, LP]),
+    "xb_tensor_upload": (C.c_int, [P, DP, C.c_int64]),
+    "xb_tensor_download": (C.c_int, [P, DP, C.c_int64]),
+    "xb_tensor_set_zero": (C.c_int, [P]),
+    "xb_tensor_set_identity": (C.c_int, [P]),
+    "xb_tensor_set_constant": (C.c_int, [P, C.c_double]),
+    "xb_tensor_set_random": (C.c_int, [P, C.c_uint64]),
+    "xb_permute": (C.c_int, [P, P, C.c_int, IP, C.c_int, PP]),
+    "xb_permute_adj": (C.c_int, [P, P, C.c_int, IP, C.c_int, PP]),
+    "xb_multiply": (C.c_int, [P, P, C.c_int, P, C.c_int, PP]),
+    "xb_contract": (C.c_int, [P, P, IP, C.c_int, P, IP, C.c_int, C.c_int, PP]),
+    "xb_adjoint": (C.c_int, [P, P, PP]),
+    "xb_twist": (C.c_int, [P, P, C.c_int, PP]),
+    "xb_axpby": (C.c_int, [P, C.c_double, P, C.c_double, P, PP]),
+    "xb_diag_map": (C.c_int, [P, P, C.c_int, PP]),
+    "xb_max_norm": (C.c_int, [P, P, DP]),
+    "xb_trace": (C.c_int, [P, P, DP]),
+    "xb_squared_norm": (C.c_int, [P, P, DP]),
+    "xb_tsvd": (C.c_int, [P, P, C.c_int64, C.c_double, C.c_int, PP, PP, PP, DP, DP]),
+    "xb_tsvd_backward": (C.c_int, [P, P, P, P, P, P, P, P, PP]),
+    "xb_tqr": (C.c_int, [P, P, PP, PP]),
+    "xb_teigh": (C.c_int, [P, P, PP, PP]),
+    "xb_decompose": (C.c_int, [P, P, P, C.c_int64, PP, PP]),
+    "xb_contract_L": (C.c_int, [P, P, P, P, PP]),
+    "xb_contract_R": (C.c_int, [P, P, P, P, PP]),
+    "xb_ctm_create": (C.c_int, [P, P, C.c_int64, PP]),
+    "xb_ctm_free": (C.c_int, [P]),
+    "xb_ctm_step": (C.c_int, [P]),
+    "xb_ctm_get": (C.c_int, [P, C.c_int, PP]),
+    "xb_ctm_set": (C.c_int, [P, C.c_int, P]),
+    "xb_ctm_corner": (C.c_int, [P, C.c_int, PP]),
+    "xb_ctm_move": (C.c_int, [P, C.c_int]),
+    "xb_bench_permute": (C.c_int, [P, P, C.c_int, IP, C.c_int, C.c_int, DP, LP]),
+    "xb_bench_multiply": (C.c_int, [P, P, P, C.c_int, DP, DP]),
+    "xb_flush_l2": (C.c_int, [P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libxped_b200.so (no GPU needed). Raises if the extension has not been built: the product never
+    substitutes another implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                              "xped_b200 has no CPU or PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise XbError(status, load().xb_last_error().decode())

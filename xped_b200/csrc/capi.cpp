@@ -1,0 +1,649 @@
+// extern "C" boundary: include/xped_b200.h.  Exceptions are mapped to status codes + xb_last_error().
+#include "../../include/xped_b200.h"
+
+#include <cstring>
+#include <memory>
+#include <new>
+#include <stdexcept>
+#include <string>
+
+#include "ctm.hpp"
+#include "engine.hpp"
+
+using namespace xb;
+
+struct xb_ctx { Context impl; xb_ctx(int dev, const std::vector<Factor>& f) : impl(dev, f) {} };
+struct xb_basis { xb_ctx* ctx; BasisPtr b; };
+struct xb_tensor { xb_ctx* ctx; std::unique_ptr<Tensor> t; };
+struct xb_ctm { xb_ctx* ctx; std::unique_ptr<Ctm> c; };
+
+namespace {
+thread_local std::string g_err;
+
+template <typename F>
+int guard(F&& f)
+{
+    try {
+        f();
+        return XB_OK;
+    } catch(const std::bad_alloc& e) {
+        g_err = std::string("out of memory: ") + e.what();
+        return XB_ERR_NOMEM;
+    } catch(const std::invalid_argument& e) {
+        g_err = e.what();
+        return XB_ERR_INVALID;
+    } catch(const std::out_of_range& e) {
+        g_err = e.what();
+        return XB_ERR_INVALID;
+    } catch(const std::runtime_error& e) {
+        g_err = e.what();
+        if(g_err.find("no CUDA device") != std::string::npos) return XB_ERR_NO_DEVICE;
+        if(g_err.find("out of memory") != std::string::npos) return XB_ERR_NOMEM;
+        return XB_ERR_CUDA;
+    } catch(const std::exception& e) {
+        g_err = e.what();
+        return XB_ERR_INTERNAL;
+    }
+}
+
+xb_tensor* wrap(xb_ctx* ctx, Tensor* t) { return new xb_tensor{ctx, std::unique_ptr<Tensor>(t)}; }
+
+void need(const void* p, const char* what)
+{
+    if(!p) throw std::invalid_argument(std::string("null argument: ") + what);
+}
+
+Q make_q(const Symmetry& s, const int* q)
+{
+    Q out{};
+    for(int i = 0; i < s.Nq(); ++i) out[i] = q[i];
+    return out;
+}
+}   // namespace
+
+extern "C" {
+
+const char* xb_last_error(void) { return g_err.c_str(); }
+const char* xb_version(void) { return "xped_b200 0.1 (sm_100a)"; }
+
+int xb_ctx_create(xb_ctx** ctx, int device, const xb_sym_factor* factors, int n_factors)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        std::vector<Factor> f;
+        for(int i = 0; i < n_factors; ++i) {
+            if(factors[i].kind < 0 || factors[i].kind > 3) throw std::invalid_argument("unknown symmetry kind");
+            if(factors[i].kind == XB_SYM_ZN && factors[i].N < 2) throw std::invalid_argument("ZN needs N >= 2");
+            f.push_back({static_cast<Kind>(factors[i].kind), factors[i].N, factors[i].fermionic != 0});
+        }
+        if(f.empty()) f.push_back({Kind::U0, 0, false});
+        *ctx = new xb_ctx(device, f);
+    });
+}
+
+int xb_ctx_free(xb_ctx* ctx)
+{
+    return guard([&] { delete ctx; });
+}
+
+int xb_ctx_sync(xb_ctx* ctx)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        ctx->impl.sync();
+    });
+}
+
+int xb_ctx_nq(const xb_ctx* ctx) { return ctx ? ctx->impl.sym->Nq() : -1; }
+
+int xb_ctx_stats(const xb_ctx* ctx, int64_t out[3])
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        out[0] = ctx->impl.launches;
+        out[1] = ctx->impl.plan_hits;
+        out[2] = ctx->impl.plan_misses;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------- bases
+int xb_basis_create(xb_ctx* ctx, const int* q, const int64_t* dims, int n, xb_basis** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(out, "out");
+        auto b = std::make_shared<Qbasis>(ctx->impl.sym, 1);
+        const int nq = ctx->impl.sym->Nq();
+        for(int i = 0; i < n; ++i) {
+            if(dims[i] < 0) throw std::invalid_argument("negative sector dimension");
+            b->push_back(make_q(*ctx->impl.sym, q + static_cast<size_t>(i) * nq), dims[i]);
+        }
+        *out = new xb_basis{ctx, b};
+    });
+}
+
+int xb_basis_free(xb_basis* b)
+{
+    return guard([&] { delete b; });
+}
+
+int xb_basis_conj(const xb_basis* b, xb_basis** out)
+{
+    return guard([&] {
+        need(b, "basis");
+        *out = new xb_basis{b->ctx, b->b->conj()};
+    });
+}
+
+int xb_basis_sorted(const xb_basis* b, xb_basis** out)
+{
+    return guard([&] {
+        need(b, "basis");
+        auto c = std::make_shared<Qbasis>(*b->b);
+        c->sort();
+        *out = new xb_basis{b->ctx, c};
+    });
+}
+
+int xb_basis_combine(const xb_basis* a, const xb_basis* b, xb_basis** out)
+{
+    return guard([&] {
+        need(a, "a");
+        need(b, "b");
+        *out = new xb_basis{a->ctx, a->b->combine(*b->b)->forget_history()};
+    });
+}
+
+int xb_basis_size(const xb_basis* b, int* n_sectors, int64_t* dim, int64_t* full_dim, int* is_conj)
+{
+    return guard([&] {
+        need(b, "basis");
+        if(n_sectors) *n_sectors = static_cast<int>(b->b->entries().size());
+        if(dim) *dim = b->b->dim();
+        if(full_dim) *full_dim = b->b->full_dim();
+        if(is_conj) *is_conj = b->b->is_conj();
+    });
+}
+
+int xb_basis_get(const xb_basis* b, int* q, int64_t* dims)
+{
+    return guard([&] {
+        need(b, "basis");
+        const int nq = b->b->sym()->Nq();
+        size_t i = 0;
+        for(const auto& e : b->b->entries()) {
+            for(int k = 0; k < nq; ++k) q[i * nq + k] = e.q[k];
+            dims[i] = e.dim;
+            ++i;
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------- tensors
+int xb_tensor_create(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, xb_tensor** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(out, "out");
+        if(rank < 0 || corank < 0 || rank > MAXR || corank > MAXR) throw std::invalid_argument("rank/corank out of range");
+        std::vector<BasisPtr> d, c;
+        for(int i = 0; i < rank; ++i) {
+            need(domain[i], "domain basis");
+            d.push_back(domain[i]->b);
+        }
+        for(int i = 0; i < corank; ++i) {
+            need(codomain[i], "codomain basis");
+            c.push_back(codomain[i]->b);
+        }
+        *out = wrap(ctx, new Tensor(&ctx->impl, ctx->impl.layout(d, c), true));
+    });
+}
+
+int xb_tensor_free(xb_tensor* t)
+{
+    return guard([&] { delete t; });
+}
+
+int xb_tensor_clone(const xb_tensor* t, xb_tensor** out)
+{
+    return guard([&] {
+        need(t, "tensor");
+        *out = wrap(t->ctx, t->ctx->impl.copy(*t->t));
+    });
+}
+
+int xb_tensor_rank(const xb_tensor* t, int* rank, int* corank)
+{
+    return guard([&] {
+        need(t, "tensor");
+        *rank = t->t->layout->rank();
+        *corank = t->t->layout->corank();
+    });
+}
+
+int xb_tensor_leg_basis(const xb_tensor* t, int leg, xb_basis** out)
+{
+    return guard([&] {
+        need(t, "tensor");
+        const Layout& L = *t->t->layout;
+        if(leg < 0 || leg >= L.rank() + L.corank()) throw std::invalid_argument("leg out of range");
+        *out = new xb_basis{t->ctx, leg < L.rank() ? L.dom[leg] : L.cod[leg - L.rank()]};
+    });
+}
+
+int64_t xb_tensor_plain_size(const xb_tensor* t) { return t ? t->t->layout->size : -1; }
+int xb_tensor_num_sectors(const xb_tensor* t) { return t ? static_cast<int>(t->t->layout->sector.size()) : -1; }
+
+int xb_tensor_structure(const xb_tensor* t, int* q, int64_t* rows, int64_t* cols, int64_t* offsets)
+{
+    return guard([&] {
+        need(t, "tensor");
+        const Layout& L = *t->t->layout;
+        const int nq = t->ctx->impl.sym->Nq();
+        for(size_t i = 0; i < L.sector.size(); ++i) {
+            for(int k = 0; k < nq; ++k) q[i * nq + k] = L.sector[i][k];
+            rows[i] = L.rows[i];
+            cols[i] = L.cols[i];
+            offsets[i] = L.off[i];
+        }
+    });
+}
+
+int64_t xb_tensor_num_tree_pairs(const xb_tensor* t)
+{
+    if(!t) return -1;
+    const Layout& L = *t->t->layout;
+    int64_t n = 0;
+    for(const Q& q : L.sector) n += static_cast<int64_t>(L.cdom->trees(q).size()) * static_cast<int64_t>(L.ccod->trees(q).size());
+    return n;
+}
+
+int xb_tensor_tree_pairs(const xb_tensor* t, int64_t* out5)
+{
+    return guard([&] {
+        need(t, "tensor");
+        const Layout& L = *t->t->layout;
+        size_t n = 0;
+        for(size_t i = 0; i < L.sector.size(); ++i) {
+            int64_t ro = 0;
+            for(const Tree& dt : L.cdom->trees(L.sector[i])) {
+                int64_t co = 0;
+                for(const Tree& ct : L.ccod->trees(L.sector[i])) {
+                    int64_t* o = out5 + 5 * n++;
+                    o[0] = static_cast<int64_t>(i);
+                    o[1] = ro;
+                    o[2] = co;
+                    o[3] = dt.dim;
+                    o[4] = ct.dim;
+                    co += ct.dim;
+                }
+                ro += dt.dim;
+            }
+        }
+    });
+}
+
+int xb_tensor_upload(xb_tensor* t, const double* host, int64_t n)
+{
+    return guard([&] {
+        need(t, "tensor");
+        if(n != t->t->layout->size) throw std::invalid_argument("upload: size != plainSize()");
+        Context& c = t->ctx->impl;
+        check_cuda(cudaMemcpyAsync(t->t->d, host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream), "upload");
+        c.sync();
+    });
+}
+
+int xb_tensor_download(const xb_tensor* t, double* host, int64_t n)
+{
+    return guard([&] {
+        need(t, "tensor");
+        if(n != t->t->layout->size) throw std::invalid_argument("download: size != plainSize()");
+        Context& c = t->ctx->impl;
+        check_cuda(cudaMemcpyAsync(host, t->t->d, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream), "download");
+        c.sync();
+    });
+}
+
+int xb_tensor_set_zero(xb_tensor* t)
+{
+    return guard([&] {
+        need(t, "tensor");
+        check_cuda(cudaMemsetAsync(t->t->d, 0, sizeof(double) * t->t->layout->size, t->ctx->impl.stream), "set_zero");
+    });
+}
+
+int xb_tensor_set_identity(xb_tensor* t)
+{
+    return guard([&] {
+        need(t, "tensor");
+        t->ctx->impl.fill(*t->t, 1, 0.0, 0);
+    });
+}
+
+int xb_tensor_set_constant(xb_tensor* t, double v)
+{
+    return guard([&] {
+        need(t, "tensor");
+        t->ctx->impl.fill(*t->t, 0, v, 0);
+    });
+}
+
+int xb_tensor_set_random(xb_tensor* t, uint64_t seed)
+{
+    return guard([&] {
+        need(t, "tensor");
+        t->ctx->impl.fill(*t->t, 2, 0.0, seed);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------- hot path
+int xb_permute(xb_ctx* ctx, const xb_tensor* t, int shift, const int* p, int n, xb_tensor** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(t, "tensor");
+        *out = wrap(ctx, ctx->impl.permute(*t->t, shift, std::vector<int>(p, p + n)));
+    });
+}
+
+int xb_permute_adj(xb_ctx* ctx, const xb_tensor* t, int shift, const int* p, int n, xb_tensor** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(t, "tensor");
+        *out = wrap(ctx, ctx->impl.permute_adj(*t->t, shift, std::vector<int>(p, p + n)));
+    });
+}
+
+int xb_multiply(xb_ctx* ctx, const xb_tensor* a, int adj_a, const xb_tensor* b, int adj_b, xb_tensor** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(a, "a");
+        need(b, "b");
+        *out = wrap(ctx, ctx->impl.multiply(*a->t, adj_a != 0, *b->t, adj_b != 0));
+    });
+}
+
+int xb_contract(xb_ctx* ctx, const xb_tensor* a, const int* la, int na, const xb_tensor* b, const int* lb, int nb, int res_rank, xb_tensor** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(a, "a");
+        need(b, "b");
+        *out = wrap(ctx, ctx->impl.contract(*a->t, std::vector<int>(la, la + na), *b->t, std::vector<int>(lb, lb + nb), res_rank));
+    });
+}
+
+int xb_adjoint(xb_ctx* ctx, const xb_tensor* t, xb_tensor** out)
+{
+    return guard([&] {
+        need(t, "tensor");
+        *out = wrap(ctx, ctx->impl.adjoint(*t->t));
+    });
+}
+
+int xb_twist(xb_ctx* ctx, const xb_tensor* t, int leg, xb_tensor** out)
+{
+    return guard([&] {
+        need(t, "tensor");
+        *out = wrap(ctx, ctx->impl.twist(*t->t, leg));
+    });
+}
+
+int xb_axpby(xb_ctx* ctx, double alpha, const xb_tensor* x, double beta, const xb_tensor* y, xb_tensor** out)
+{
+    return guard([&] {
+        need(x, "x");
+        *out = wrap(ctx, ctx->impl.axpby(alpha, *x->t, beta, y ? y->t.get() : nullptr));
+    });
+}
+
+int xb_diag_map(xb_ctx* ctx, const xb_tensor* t, int op, xb_tensor** out)
+{
+    return guard([&] {
+        need(t, "tensor");
+        if(op < 0 || op > 2) throw std::invalid_argument("diag_map: op must be 0, 1 or 2");
+        *out = wrap(ctx, ctx->impl.diag_map(*t->t, op));
+    });
+}
+
+int xb_max_norm(xb_ctx* ctx, const xb_tensor* t, double* out)
+{
+    return guard([&] {
+        need(t, "tensor");
+        *out = ctx->impl.max_norm(*t->t);
+    });
+}
+
+int xb_trace(xb_ctx* ctx, const xb_tensor* t, double* out)
+{
+    return guard([&] {
+        need(t, "tensor");
+        *out = ctx->impl.trace(*t->t);
+    });
+}
+
+int xb_squared_norm(xb_ctx* ctx, const xb_tensor* t, double* out)
+{
+    return guard([&] {
+        need(t, "tensor");
+        *out = ctx->impl.squared_norm(*t->t);
+    });
+}
+
+int xb_tsvd(xb_ctx* ctx, const xb_tensor* t, int64_t max_keep, double eps_svd, int preserve_multiplets, xb_tensor** U, xb_tensor** S, xb_tensor** Vdag,
+            double* trunc_weight, double* entropy)
+{
+    return guard([&] {
+        need(t, "tensor");
+        SvdResult r = ctx->impl.tsvd(*t->t, max_keep, eps_svd, preserve_multiplets != 0);
+        *U = wrap(ctx, r.U);
+        *S = wrap(ctx, r.S);
+        *Vdag = wrap(ctx, r.Vd);
+        if(trunc_weight) *trunc_weight += r.trunc_weight;
+        if(entropy) *entropy += r.entropy;
+    });
+}
+
+int xb_tsvd_backward(xb_ctx* ctx, const xb_tensor* A, const xb_tensor* U, const xb_tensor* S, const xb_tensor* Vdag, const xb_tensor* dU,
+                     const xb_tensor* dS, const xb_tensor* dVdag, xb_tensor** dA)
+{
+    return guard([&] {
+        need(A, "A");
+        need(U, "U");
+        need(S, "S");
+        need(Vdag, "Vdag");
+        *dA = wrap(ctx, ctx->impl.tsvd_backward(*A->t, *U->t, *S->t, *Vdag->t, dU ? dU->t.get() : nullptr, dS ? dS->t.get() : nullptr,
+                                                dVdag ? dVdag->t.get() : nullptr));
+    });
+}
+
+int xb_tqr(xb_ctx* ctx, const xb_tensor* t, xb_tensor** Qo, xb_tensor** Ro)
+{
+    return guard([&] {
+        need(t, "tensor");
+        Tensor *q = nullptr, *r = nullptr;
+        ctx->impl.tqr(*t->t, &q, &r);
+        *Qo = wrap(ctx, q);
+        *Ro = wrap(ctx, r);
+    });
+}
+
+int xb_teigh(xb_ctx* ctx, const xb_tensor* t, xb_tensor** D, xb_tensor** V)
+{
+    return guard([&] {
+        need(t, "tensor");
+        Tensor *d = nullptr, *v = nullptr;
+        ctx->impl.teigh(*t->t, &d, &v);
+        *D = wrap(ctx, d);
+        *V = wrap(ctx, v);
+    });
+}
+
+int xb_decompose(xb_ctx* ctx, const xb_tensor* T1, const xb_tensor* T2, int64_t chi, xb_tensor** P1, xb_tensor** P2)
+{
+    return guard([&] {
+        need(T1, "T1");
+        need(T2, "T2");
+        Tensor *p1 = nullptr, *p2 = nullptr;
+        decompose_projectors(ctx->impl, *T1->t, *T2->t, chi, &p1, &p2);
+        *P1 = wrap(ctx, p1);
+        *P2 = wrap(ctx, p2);
+    });
+}
+
+int xb_contract_L(xb_ctx* ctx, const xb_tensor* Bold, const xb_tensor* Bra, const xb_tensor* Ket, xb_tensor** Bnew)
+{
+    return guard([&] {
+        need(Bold, "Bold");
+        need(Bra, "Bra");
+        need(Ket, "Ket");
+        Tensor* o = nullptr;
+        ctx->impl.contract_L(*Bold->t, *Bra->t, *Ket->t, &o);
+        *Bnew = wrap(ctx, o);
+    });
+}
+
+int xb_contract_R(xb_ctx* ctx, const xb_tensor* Bold, const xb_tensor* Bra, const xb_tensor* Ket, xb_tensor** Bnew)
+{
+    return guard([&] {
+        need(Bold, "Bold");
+        need(Bra, "Bra");
+        need(Ket, "Ket");
+        Tensor* o = nullptr;
+        ctx->impl.contract_R(*Bold->t, *Bra->t, *Ket->t, &o);
+        *Bnew = wrap(ctx, o);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------- CTM
+int xb_ctm_create(xb_ctx* ctx, const xb_tensor* A, int64_t chi, xb_ctm** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(A, "A");
+        *out = new xb_ctm{ctx, std::make_unique<Ctm>(ctx->impl, *A->t, chi)};
+    });
+}
+
+int xb_ctm_free(xb_ctm* c)
+{
+    return guard([&] { delete c; });
+}
+
+int xb_ctm_step(xb_ctm* c)
+{
+    return guard([&] {
+        need(c, "ctm");
+        c->c->grow_all();
+    });
+}
+
+int xb_ctm_get(const xb_ctm* c, int which, xb_tensor** out)
+{
+    return guard([&] {
+        need(c, "ctm");
+        *out = wrap(c->ctx, c->ctx->impl.copy(c->c->get(which)));
+    });
+}
+
+int xb_ctm_set(xb_ctm* c, int which, const xb_tensor* t)
+{
+    return guard([&] {
+        need(c, "ctm");
+        need(t, "tensor");
+        c->c->set(which, c->ctx->impl.copy(*t->t));
+    });
+}
+
+int xb_ctm_corner(xb_ctm* c, int corner, xb_tensor** Qo)
+{
+    return guard([&] {
+        need(c, "ctm");
+        *Qo = wrap(c->ctx, c->c->contract_corner(corner));
+    });
+}
+
+int xb_ctm_move(xb_ctm* c, int direction)
+{
+    return guard([&] {
+        need(c, "ctm");
+        c->c->move(direction);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------- bench hooks
+int xb_bench_permute(xb_ctx* ctx, const xb_tensor* t, int shift, const int* p, int n, int reps, double* ms_per_launch, int64_t* bytes)
+{
+    return guard([&] {
+        need(t, "tensor");
+        Context& c = ctx->impl;
+        auto plan = c.permute_plan(t->t->layout, shift, std::vector<int>(p, p + n), false);
+        Tensor out(&c, plan->out, false);
+        cudaEvent_t e0, e1;
+        check_cuda(cudaEventCreate(&e0), "event");
+        check_cuda(cudaEventCreate(&e1), "event");
+        check_cuda(cudaEventRecord(e0, c.stream), "record");
+        for(int r = 0; r < reps; ++r) {
+            if(plan->identity_copy)
+                check_cuda(cudaMemcpyAsync(out.d, t->t->d, sizeof(double) * t->t->size(), cudaMemcpyDeviceToDevice, c.stream), "copy");
+            else
+                launch_permute(t->t->d, out.d, *plan, c.stream);
+        }
+        c.launches += reps;
+        check_cuda(cudaEventRecord(e1, c.stream), "record");
+        check_cuda(cudaEventSynchronize(e1), "event sync");
+        float ms = 0.f;
+        check_cuda(cudaEventElapsedTime(&ms, e0, e1), "elapsed");
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *ms_per_launch = static_cast<double>(ms) / reps;
+        *bytes = plan->bytes;
+    });
+}
+
+int xb_bench_multiply(xb_ctx* ctx, const xb_tensor* a, const xb_tensor* b, int reps, double* ms_per_launch, double* flops)
+{
+    return guard([&] {
+        need(a, "a");
+        need(b, "b");
+        Context& c = ctx->impl;
+        const Layout& LA = *a->t->layout;
+        const Layout& LB = *b->t->layout;
+        double fl = 0.0;
+        for(size_t i = 0; i < LA.sector.size(); ++i) {
+            const int j = LB.find(LA.sector[i]);
+            if(j >= 0) fl += 2.0 * static_cast<double>(LA.rows[i]) * static_cast<double>(LA.cols[i]) * static_cast<double>(LB.cols[j]);
+        }
+        std::unique_ptr<Tensor> warm(c.multiply(*a->t, false, *b->t, false));
+        cudaEvent_t e0, e1;
+        check_cuda(cudaEventCreate(&e0), "event");
+        check_cuda(cudaEventCreate(&e1), "event");
+        check_cuda(cudaEventRecord(e0, c.stream), "record");
+        for(int r = 0; r < reps; ++r) std::unique_ptr<Tensor> o(c.multiply(*a->t, false, *b->t, false));
+        check_cuda(cudaEventRecord(e1, c.stream), "record");
+        check_cuda(cudaEventSynchronize(e1), "event sync");
+        float ms = 0.f;
+        check_cuda(cudaEventElapsedTime(&ms, e0, e1), "elapsed");
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        c.sync();
+        *ms_per_launch = static_cast<double>(ms) / reps;
+        *flops = fl;
+    });
+}
+
+int xb_flush_l2(xb_ctx* ctx)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        Context& c = ctx->impl;
+        const size_t bytes = size_t(256) << 20;   // > 126 MB L2
+        void* p = c.scratch(bytes);
+        check_cuda(cudaMemsetAsync(p, 0, bytes, c.stream), "flush_l2");
+    });
+}
+
+}   // extern "C"

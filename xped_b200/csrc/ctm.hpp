@@ -1,0 +1,40 @@
+// Directional CTMRG driver re-hosted on the device backend (1x1 unit cell, TRank = 2, corner projectors).
+// Mirrors Xped::CTM<double,Symmetry,2> (include/Xped/PEPS/CTM.hpp:60-312, src/PEPS/CTM.cpp).
+#pragma once
+#include <memory>
+
+#include "engine.hpp"
+
+namespace xb {
+
+using TP = std::shared_ptr<Tensor>;
+
+// decompose(T1, T2, chi): src/PEPS/PEPSContractions.cpp:18-43
+void decompose_projectors(Context& ctx, const Tensor& T1, const Tensor& T2, int64_t chi, Tensor** P1, Tensor** P2);
+
+class Ctm
+{
+public:
+    Ctm(Context& ctx, const Tensor& A, int64_t chi);   // CTM(A, chi, FROM_A) + init()  (CTM.cpp:45-244)
+
+    void grow_all();                    // CTM.cpp:385-420
+    void move(int direction);           // 0 left, 1 right, 2 top, 3 bottom  (CTM.cpp:924-1183)
+    Tensor* contract_corner(int corner);   // 0 UL, 1 UR, 2 LR, 3 LL  (CTM.cpp:1643-1760)
+    const Tensor& get(int which) const;
+    void set(int which, Tensor* t);     // takes ownership
+
+private:
+    Context& ctx_;
+    int64_t chi_;
+    TP A_, Adag_;
+    TP C1_, C2_, C3_, C4_, T1_, T2_, T3_, T4_;
+
+    TP con(const TP& a, std::initializer_list<int> la, const TP& b, std::initializer_list<int> lb, int res_rank) const;
+    TP tw(const TP& t, std::initializer_list<int> legs) const;   // chained twists; no-op (shared) for bosonic symmetries
+    TP normalized(const TP& t) const;                            // t * (1 / t.maxNorm()) without a host round trip
+    TP corner(int c) const;
+    void projectors(int direction, TP& P1, TP& P2) const;        // get_projectors  CTM.cpp:1185-1337
+    void init_from_A();
+};
+
+}   // namespace xb

@@ -1,0 +1,196 @@
+// xped_b200 engine: device-resident block arenas, cached layouts and cached permute plans.
+//
+// A Tensor is (shared immutable Layout, one contiguous device buffer).  The buffer holds exactly the
+// reference's contiguous storage image: per-sector column-major matrices concatenated at
+// Layout::off[i] (include/Xped/Core/storage/StorageType_contiguous.hpp:79-97,112-122), so upload /
+// download are plain memcpys of `m_data` and structure checks are bit-exact by construction.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "core.hpp"
+
+namespace xb {
+
+struct Layout
+{
+    std::vector<BasisPtr> dom, cod;   // uncoupled leg bases
+    BasisPtr cdom, ccod;              // coupled bases with fusion trees
+    std::vector<Q> sector;
+    std::unordered_map<Q, int, QHash> dict;
+    std::vector<int64_t> off, rows, cols;
+    int64_t size = 0;
+    std::string sig;   // leg-basis signature (+ explicit sector order for push_back-built tensors)
+    int rank() const { return static_cast<int>(dom.size()); }
+    int corank() const { return static_cast<int>(cod.size()); }
+    int find(const Q& q) const
+    {
+        auto it = dict.find(q);
+        return it == dict.end() ? -1 : it->second;
+    }
+};
+using LayoutPtr = std::shared_ptr<const Layout>;
+
+// ---- device-side plan records (plain structs shared with the kernels) -------------------------------
+constexpr int PERM_MAXLEG = 8;
+constexpr int PERM_TILE_ELEMS = 2048;   // doubles per tile (16 KiB of payload)
+constexpr int PERM_BUF_ELEMS = 3072;    // shared buffer incl. bank-conflict padding
+constexpr int PERM_THREADS = 256;
+constexpr int PERM_ITER = PERM_TILE_ELEMS / PERM_THREADS;
+
+struct PermTask   // one destination sub-block (target tree pair) = sum_k coeff_k * transpose(src_k)
+{
+    long long dst_off;
+    int nleg;        // merged legs, dst order (leg 0 fastest in dst)
+    int ntl;         // legs with tile extent > 1
+    int src_begin;   // first PermSrc
+    int src_count;   // fan-in K (0 => zero fill)
+    int vol;         // tile volume prod(w)
+    int pad_;
+    int dims[PERM_MAXLEG];
+    int w[PERM_MAXLEG];
+    int ntile[PERM_MAXLEG];
+    int dstride[PERM_MAXLEG];
+    int smstride[PERM_MAXLEG];       // shared-memory stride of each leg (src-order packing, padded)
+    int tl_d[PERM_MAXLEG];           // tile legs in dst order
+    int tl_s[PERM_MAXLEG];           // tile legs in src order
+    unsigned magic[PERM_MAXLEG];     // ceil(2^32 / w[leg]) for fast division by the tile extent
+};
+
+struct PermSrc
+{
+    long long off;
+    double coeff;
+    int sstride[PERM_MAXLEG];   // source stride of each (dst-ordered) leg
+};
+
+struct PermTile { int task; int tile; };
+
+struct PermutePlan
+{
+    LayoutPtr out;
+    int n_tasks = 0, n_srcs = 0, n_tiles = 0;
+    PermTask* d_tasks = nullptr;
+    PermSrc* d_srcs = nullptr;
+    PermTile* d_tiles = nullptr;
+    bool identity_copy = false;   // permute<0, identity>: plain copy (Tensor.cpp:344)
+    int64_t bytes = 0;            // algorithmic bytes: 8*(N_src + N_dst)
+    int max_fan_in = 0;
+    ~PermutePlan();
+};
+
+struct GemmItem   // one (sector, tile) of a grouped product
+{
+    long long a_off, b_off, c_off;
+    int m, n, k;
+    int lda, ldb, ldc;
+    int tm, tn;   // tile origin
+    int ta, tb;   // operand stored transposed (adjoint block)?
+};
+
+class Context;
+
+struct Tensor
+{
+    Context* ctx = nullptr;
+    LayoutPtr layout;
+    double* d = nullptr;
+    Tensor(Context* c, LayoutPtr l, bool zero);
+    ~Tensor();
+    Tensor(const Tensor&) = delete;
+    Tensor& operator=(const Tensor&) = delete;
+    int64_t size() const { return layout->size; }
+};
+
+struct SvdResult
+{
+    Tensor *U = nullptr, *S = nullptr, *Vd = nullptr;
+    double trunc_weight = 0.0, entropy = 0.0;
+};
+
+class Context
+{
+public:
+    Context(int device, const std::vector<Factor>& factors);
+    ~Context();
+
+    SymPtr sym;
+    int device;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+
+    // ---- host metadata (cached) ----
+    BasisPtr coupled(const std::vector<BasisPtr>& uncoupled);
+    LayoutPtr layout(const std::vector<BasisPtr>& dom, const std::vector<BasisPtr>& cod);
+    LayoutPtr layout_custom(const std::vector<BasisPtr>& dom, const std::vector<BasisPtr>& cod, const std::vector<Q>& sectors);
+    std::shared_ptr<PermutePlan> permute_plan(const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan);
+
+    // ---- ops (all asynchronous on `stream` unless they return host values) ----
+    Tensor* permute(const Tensor& t, int shift, const std::vector<int>& pi);
+    Tensor* permute_adj(const Tensor& t, int shift, const std::vector<int>& pi);
+    Tensor* multiply(const Tensor& a, bool adj_a, const Tensor& b, bool adj_b);   // operator* with lazy AdjointOp operands
+    Tensor* contract(const Tensor& a, const std::vector<int>& l1, const Tensor& b, const std::vector<int>& l2, int res_rank);
+    Tensor* adjoint(const Tensor& t);
+    Tensor* twist(const Tensor& t, int leg);
+    Tensor* copy(const Tensor& t);
+    Tensor* axpby(double alpha, const Tensor& x, double beta, const Tensor* y);   // alpha*x + beta*y
+    Tensor* diag_map(const Tensor& t, int op);                                    // 0 sqrt, 1 inv, 2 inv-sqrt
+    double max_norm(const Tensor& t);
+    Tensor* scale_by_inv_maxnorm(const Tensor& t);   // t * (1 / t.maxNorm()), scalar stays on the device
+    double trace(const Tensor& t);
+    double squared_norm(const Tensor& t);
+    void fill(Tensor& t, int mode, double value, uint64_t seed);                 // 0 constant, 1 identity, 2 counter-based uniform[-1,1]
+    SvdResult tsvd(const Tensor& t, int64_t max_keep, double eps_svd, bool preserve_multiplets);
+    Tensor* tsvd_backward(const Tensor& A, const Tensor& U, const Tensor& S, const Tensor& Vd, const Tensor* dU, const Tensor* dS, const Tensor* dVd);
+    void tqr(const Tensor& t, Tensor** Qo, Tensor** Ro);
+    void teigh(const Tensor& t, Tensor** D, Tensor** V);
+    void contract_L(const Tensor& Bold, const Tensor& Bra, const Tensor& Ket, Tensor** Bnew);
+    void contract_R(const Tensor& Bold, const Tensor& Bra, const Tensor& Ket, Tensor** Bnew);
+    void sync();
+
+    // statistics for bench / gpu_launches
+    int64_t launches = 0;
+    int64_t plan_hits = 0, plan_misses = 0;
+
+    // scratch device buffer for reductions / work lists
+    void* scratch(size_t bytes);
+    void* pinned(size_t bytes);
+    void upload_async(void* dst, const void* src, size_t bytes);   // via a growing pinned staging ring
+
+private:
+    std::unordered_map<std::string, BasisPtr> coupled_cache_;
+    std::unordered_map<std::string, LayoutPtr> layout_cache_;
+    std::unordered_map<std::string, std::shared_ptr<PermutePlan>> plan_cache_;
+    void* scratch_ = nullptr;
+    size_t scratch_bytes_ = 0;
+    void* pinned_ = nullptr;
+    size_t pinned_bytes_ = 0;
+    std::vector<std::pair<void*, size_t>> staging_;   // pinned blocks kept alive until the next sync
+};
+
+void check_cuda(cudaError_t e, const char* what);
+
+// ---- kernel launchers (kernels.cu) ----
+void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s);
+void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, cudaStream_t s);
+void launch_scale_copy(const double* x, double* y, double alpha, int64_t n, cudaStream_t s);
+void launch_axpby(const double* x, const double* y, double* z, double alpha, double beta, int64_t n, cudaStream_t s);
+void launch_absmax(const double* x, int64_t n, double* d_out, cudaStream_t s);
+void launch_scale_by_inv(const double* x, double* y, const double* d_scalar, int64_t n, cudaStream_t s);
+void launch_fill_constant(double* x, double v, int64_t n, cudaStream_t s);
+void launch_fill_random(double* x, uint64_t seed, int64_t n, cudaStream_t s);
+struct BlockDesc { long long off; int rows, cols; double weight; };
+void launch_transpose_blocks(const double* src, double* dst, const BlockDesc* d_src_blocks, const long long* d_dst_off, int nblocks, cudaStream_t s);
+void launch_set_identity(double* x, const BlockDesc* d_blocks, int nblocks, cudaStream_t s);
+void launch_diag_map(const double* src, double* dst, const BlockDesc* d_blocks, int nblocks, int op, cudaStream_t s);
+struct SubScale { long long off; int rows, cols, ld; double scale; };
+void launch_scale_subblocks(double* data, const SubScale* d_subs, int n, cudaStream_t s);
+void launch_trace(const double* src, const BlockDesc* d_blocks, int nblocks, double* d_out, cudaStream_t s);
+
+}   // namespace xb

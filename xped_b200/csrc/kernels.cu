@@ -1,0 +1,462 @@
+// Hand-written sm_100a kernels for the Xped hot path.
+//
+//  permute_kernel      batched strided scaled-accumulate tensor transpose: the whole of
+//                      Tensor::permute / permute_adj (src/Core/Tensor.cpp:83-214,258-333) in ONE launch.
+//                      HBM-bound: every source element is read once per consumer tile through a
+//                      coalesced, shared-memory staged tile; every destination element is written once.
+//                      (TMA is not usable here: sub-block origins and leading dimensions are arbitrary
+//                      multiples of 8 bytes, cp.async.bulk[.tensor] needs 16-byte aligned boxes/strides.)
+//  gemm_grouped_kernel ragged per-sector C_q += op(A_q) * op(B_q) (src/Core/TensorBase.cpp:262-279) on the
+//                      FP64 tensor cores (mma.sync m8n8k4 DMMA; tcgen05 has no FP64 kind).
+//  small fused elementwise / reduction kernels for AdjointOp, DiagCoeffUnaryOp, maxNorm, trace.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "engine.hpp"
+
+namespace xb {
+
+// ================================================================================================ permute
+__global__ void __launch_bounds__(PERM_THREADS)
+permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const PermTask* __restrict__ tasks,
+               const PermSrc* __restrict__ srcs, const PermTile* __restrict__ tiles)
+{
+    __shared__ PermTask T;
+    __shared__ PermSrc S;
+    __shared__ double buf[PERM_BUF_ELEMS];
+    __shared__ int s_base[PERM_MAXLEG];
+    __shared__ int s_lim[PERM_MAXLEG];
+
+    const int tid = threadIdx.x;
+    const PermTile tile = tiles[blockIdx.x];
+    {   // stage the task record
+        const int* g = reinterpret_cast<const int*>(tasks + tile.task);
+        int* s = reinterpret_cast<int*>(&T);
+        for(int i = tid; i < static_cast<int>(sizeof(PermTask) / sizeof(int)); i += PERM_THREADS) s[i] = g[i];
+    }
+    __syncthreads();
+    if(tid == 0) {
+        int r = tile.tile;
+        for(int l = 0; l < T.nleg; ++l) {
+            const int c = r % T.ntile[l];
+            r /= T.ntile[l];
+            const int b = c * T.w[l];
+            s_base[l] = b;
+            s_lim[l] = min(T.w[l], T.dims[l] - b);
+        }
+    }
+    __syncthreads();
+
+    const int ntl = T.ntl;
+    const int vol = T.vol;
+    long long dbase = T.dst_off;
+    for(int l = 0; l < T.nleg; ++l) dbase += static_cast<long long>(s_base[l]) * T.dstride[l];
+
+    // write-out coordinates of this thread's elements (fixed for all sources)
+    int d_off[PERM_ITER];
+    int d_pos[PERM_ITER];   // shared-memory position, -1 if outside the tile / tensor
+    double acc[PERM_ITER];
+#pragma unroll
+    for(int it = 0; it < PERM_ITER; ++it) {
+        int e = tid + it * PERM_THREADS;
+        int off = 0, pos = 0;
+        bool ok = e < vol;
+        for(int j = 0; j < ntl; ++j) {
+            const int l = T.tl_d[j];
+            const int q = __umulhi(static_cast<unsigned>(e), T.magic[l]);
+            const int c = e - q * T.w[l];
+            e = q;
+            ok = ok && (c < s_lim[l]);
+            off += c * T.dstride[l];
+            pos += c * T.smstride[l];
+        }
+        d_off[it] = off;
+        d_pos[it] = ok ? pos : -1;
+        acc[it] = 0.0;
+    }
+
+    for(int k = 0; k < T.src_count; ++k) {
+        if(tid < static_cast<int>(sizeof(PermSrc) / sizeof(int))) {
+            reinterpret_cast<int*>(&S)[tid] = reinterpret_cast<const int*>(srcs + T.src_begin + k)[tid];
+        }
+        __syncthreads();   // S visible; also: previous round's reads of buf are complete
+        long long sbase = S.off;
+        for(int l = 0; l < T.nleg; ++l) sbase += static_cast<long long>(s_base[l]) * S.sstride[l];
+        const double* __restrict__ sp = src + sbase;
+#pragma unroll
+        for(int it = 0; it < PERM_ITER; ++it) {
+            int e = tid + it * PERM_THREADS;
+            if(e < vol) {
+                int off = 0, pos = 0;
+                bool ok = true;
+                for(int j = 0; j < ntl; ++j) {
+                    const int l = T.tl_s[j];
+                    const int q = __umulhi(static_cast<unsigned>(e), T.magic[l]);
+                    const int c = e - q * T.w[l];
+                    e = q;
+                    ok = ok && (c < s_lim[l]);
+                    off += c * S.sstride[l];
+                    pos += c * T.smstride[l];
+                }
+                if(ok) buf[pos] = __ldg(sp + off);
+            }
+        }
+        __syncthreads();
+        const double coeff = S.coeff;
+#pragma unroll
+        for(int it = 0; it < PERM_ITER; ++it)
+            if(d_pos[it] >= 0) acc[it] = fma(coeff, buf[d_pos[it]], acc[it]);
+    }
+    double* __restrict__ dp = dst + dbase;
+#pragma unroll
+    for(int it = 0; it < PERM_ITER; ++it)
+        if(d_pos[it] >= 0) dp[d_off[it]] = acc[it];
+}
+
+void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s)
+{
+    if(plan.n_tiles == 0) return;
+    permute_kernel<<<plan.n_tiles, PERM_THREADS, 0, s>>>(src, dst, plan.d_tasks, plan.d_srcs, plan.d_tiles);
+    check_cuda(cudaGetLastError(), "permute_kernel launch");
+}
+
+// ================================================================================================ grouped DGEMM
+// CTA tile 64x64, K step 16, 4 warps in a 2x2 grid, each warp 32x32 = 4x4 DMMA m8n8k4 tiles.
+constexpr int GM = 64, GN = 64, GK = 16, GEMM_THREADS = 128;
+constexpr int GPAD = 4;   // keeps fragment loads spread over banks
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_grouped_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, const GemmItem* __restrict__ items)
+{
+    // As[k][m], Bs[k][n]: k-major so that the m8n8k4 fragments (A: row=lane/4, k=lane%4; B: k=lane%4, col=lane/4)
+    // are read with lane-varying m/n (conflict-free) for a fixed k.
+    __shared__ double As[2][GK][GM + GPAD];
+    __shared__ double Bs[2][GK][GN + GPAD];
+
+    const GemmItem it = items[blockIdx.x];
+    const double* __restrict__ Ap = A + it.a_off;
+    const double* __restrict__ Bp = B + it.b_off;
+    double* __restrict__ Cp = C + it.c_off;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+    const int m0 = it.tm, n0 = it.tn;
+
+    double acc[4][4][2];
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+#pragma unroll
+        for(int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // global -> shared loaders: A tile is 64(m) x 16(k), B tile is 16(k) x 64(n); 1024 elements each, 8 per thread
+    auto load_tiles = [&](int buf, int k0) {
+#pragma unroll
+        for(int r = 0; r < (GM * GK) / GEMM_THREADS; ++r) {
+            const int e = tid + r * GEMM_THREADS;
+            // A: op(A)[m][k]; stored column-major (m fastest) unless transposed
+            int mm, kk;
+            if(!it.ta) { mm = e % GM; kk = e / GM; } else { kk = e % GK; mm = e / GK; }
+            const int gm = m0 + mm, gk = k0 + kk;
+            double v = 0.0;
+            if(gm < it.m && gk < it.k) v = it.ta ? Ap[gk + static_cast<long long>(gm) * it.lda] : Ap[gm + static_cast<long long>(gk) * it.lda];
+            As[buf][kk][mm] = v;
+        }
+#pragma unroll
+        for(int r = 0; r < (GN * GK) / GEMM_THREADS; ++r) {
+            const int e = tid + r * GEMM_THREADS;
+            int nn, kk;
+            if(!it.tb) { kk = e % GK; nn = e / GK; } else { nn = e % GN; kk = e / GN; }
+            const int gn = n0 + nn, gk = k0 + kk;
+            double v = 0.0;
+            if(gn < it.n && gk < it.k) v = it.tb ? Bp[gn + static_cast<long long>(gk) * it.ldb] : Bp[gk + static_cast<long long>(gn) * it.ldb];
+            Bs[buf][kk][nn] = v;
+        }
+    };
+
+    const int nk = (it.k + GK - 1) / GK;
+    if(nk > 0) load_tiles(0, 0);
+    __syncthreads();
+    const int fr = lane >> 2, fk = lane & 3;
+    for(int kt = 0; kt < nk; ++kt) {
+        const int cur = kt & 1;
+        if(kt + 1 < nk) load_tiles(cur ^ 1, (kt + 1) * GK);
+#pragma unroll
+        for(int ks = 0; ks < GK; ks += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for(int i = 0; i < 4; ++i) a[i] = As[cur][ks + fk][wm + i * 8 + fr];
+#pragma unroll
+            for(int j = 0; j < 4; ++j) b[j] = Bs[cur][ks + fk][wn + j * 8 + fr];
+#pragma unroll
+            for(int i = 0; i < 4; ++i)
+#pragma unroll
+                for(int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+    // C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+#pragma unroll
+        for(int j = 0; j < 4; ++j) {
+            const int gm = m0 + wm + i * 8 + fr;
+            const int gn = n0 + wn + j * 8 + 2 * fk;
+            if(gm < it.m) {
+                if(gn < it.n) Cp[gm + static_cast<long long>(gn) * it.ldc] = acc[i][j][0];
+                if(gn + 1 < it.n) Cp[gm + static_cast<long long>(gn + 1) * it.ldc] = acc[i][j][1];
+            }
+        }
+}
+
+void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, cudaStream_t s)
+{
+    if(n_items == 0) return;
+    gemm_grouped_kernel<<<n_items, GEMM_THREADS, 0, s>>>(A, B, C, d_items);
+    check_cuda(cudaGetLastError(), "gemm_grouped_kernel launch");
+}
+
+// ================================================================================================ elementwise
+__global__ void scale_copy_kernel(const double* __restrict__ x, double* __restrict__ y, double alpha, long long n)
+{
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for(long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = alpha * x[i];
+}
+
+__global__ void axpby_kernel(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ z, double alpha, double beta, long long n)
+{
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for(long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) z[i] = alpha * x[i] + beta * y[i];
+}
+
+static int grid_for(long long n, int threads, int sms = 148)
+{
+    long long g = (n + threads - 1) / threads;
+    const long long cap = static_cast<long long>(sms) * 8;
+    return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+void launch_scale_copy(const double* x, double* y, double alpha, int64_t n, cudaStream_t s)
+{
+    if(n == 0) return;
+    scale_copy_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, y, alpha, n);
+    check_cuda(cudaGetLastError(), "scale_copy_kernel launch");
+}
+
+void launch_axpby(const double* x, const double* y, double* z, double alpha, double beta, int64_t n, cudaStream_t s)
+{
+    if(n == 0) return;
+    axpby_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, y, z, alpha, beta, n);
+    check_cuda(cudaGetLastError(), "axpby_kernel launch");
+}
+
+__global__ void fill_constant_kernel(double* __restrict__ x, double v, long long n)
+{
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for(long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;
+}
+
+// Counter-based uniform[-1,1): splitmix64 of (seed, element index) -> 53 random mantissa bits. The oracle's
+// helper (oracle/xped_oracle/rng.py) computes the same integers with numpy, so fills are bit-identical.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void fill_random_kernel(double* __restrict__ x, unsigned long long seed, long long n)
+{
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const unsigned long long key = splitmix64(seed);
+    for(long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long r = splitmix64(key ^ (static_cast<unsigned long long>(i) * 0xD1342543DE82EF95ull));
+        x[i] = static_cast<double>(r >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    }
+}
+
+static int grid_for(long long n, int threads, int sms);
+
+void launch_fill_constant(double* x, double v, int64_t n, cudaStream_t s)
+{
+    if(n == 0) return;
+    fill_constant_kernel<<<grid_for(n, 256, 148), 256, 0, s>>>(x, v, n);
+    check_cuda(cudaGetLastError(), "fill_constant_kernel launch");
+}
+
+void launch_fill_random(double* x, uint64_t seed, int64_t n, cudaStream_t s)
+{
+    if(n == 0) return;
+    fill_random_kernel<<<grid_for(n, 256, 148), 256, 0, s>>>(x, seed, n);
+    check_cuda(cudaGetLastError(), "fill_random_kernel launch");
+}
+
+// max |x| : order-independent, so a plain atomic max on the bit pattern of a non-negative double is exact.
+__global__ void absmax_kernel(const double* __restrict__ x, long long n, unsigned long long* out)
+{
+    double m = 0.0;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for(long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) m = fmax(m, fabs(x[i]));
+    for(int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ double sm[8];
+    if((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        for(int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) m = fmax(m, sm[w]);
+        atomicMax(out, static_cast<unsigned long long>(__double_as_longlong(m)));
+    }
+}
+
+void launch_absmax(const double* x, int64_t n, double* d_out, cudaStream_t s)
+{
+    check_cuda(cudaMemsetAsync(d_out, 0, sizeof(double), s), "absmax memset");
+    if(n == 0) return;
+    absmax_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, n, reinterpret_cast<unsigned long long*>(d_out));
+    check_cuda(cudaGetLastError(), "absmax_kernel launch");
+}
+
+// per-block transpose through a 32x33 shared tile: AdjointOp::eval() (include/Xped/Core/AdjointOp.hpp:44-65)
+__global__ void transpose_blocks_kernel(const double* __restrict__ src, double* __restrict__ dst, const BlockDesc* __restrict__ blocks,
+                                        const long long* __restrict__ dst_off, int nblocks)
+{
+    __shared__ double tile[32][33];
+    for(int b = blockIdx.y; b < nblocks; b += gridDim.y) {
+        const BlockDesc d = blocks[b];
+        const int tr = (d.rows + 31) / 32, tc = (d.cols + 31) / 32;
+        for(int t = blockIdx.x; t < tr * tc; t += gridDim.x) {
+            const int r0 = (t % tr) * 32, c0 = (t / tr) * 32;
+            for(int j = threadIdx.y; j < 32; j += blockDim.y) {
+                const int r = r0 + threadIdx.x, c = c0 + j;
+                if(r < d.rows && c < d.cols) tile[j][threadIdx.x] = src[d.off + r + static_cast<long long>(c) * d.rows];
+            }
+            __syncthreads();
+            for(int j = threadIdx.y; j < 32; j += blockDim.y) {
+                const int c = c0 + threadIdx.x, r = r0 + j;   // output is cols x rows, column-major
+                if(r < d.rows && c < d.cols) dst[dst_off[b] + c + static_cast<long long>(r) * d.cols] = tile[threadIdx.x][j];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+void launch_transpose_blocks(const double* src, double* dst, const BlockDesc* d_src_blocks, const long long* d_dst_off, int nblocks, cudaStream_t s)
+{
+    if(nblocks == 0) return;
+    dim3 grid(148, static_cast<unsigned>(nblocks < 64 ? nblocks : 64)), block(32, 8);
+    transpose_blocks_kernel<<<grid, block, 0, s>>>(src, dst, d_src_blocks, d_dst_off, nblocks);
+    check_cuda(cudaGetLastError(), "transpose_blocks_kernel launch");
+}
+
+// DiagCoeffUnaryOp (include/Xped/Core/DiagCoeffUnaryOp.hpp:48-51): out = diag(f(diag(in))), off-diagonals zero.
+__global__ void diag_map_kernel(const double* __restrict__ src, double* __restrict__ dst, const BlockDesc* __restrict__ blocks, int nblocks, int op)
+{
+    for(int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const BlockDesc d = blocks[b];
+        const long long n = static_cast<long long>(d.rows) * d.cols;
+        for(long long e = threadIdx.x; e < n; e += blockDim.x) {
+            const int r = static_cast<int>(e % d.rows), c = static_cast<int>(e / d.rows);
+            double v = 0.0;
+            if(r == c) {
+                const double x = src[d.off + e];
+                v = op == 0 ? sqrt(x) : (op == 1 ? 1.0 / x : 1.0 / sqrt(x));
+            }
+            dst[d.off + e] = v;
+        }
+    }
+}
+
+void launch_diag_map(const double* src, double* dst, const BlockDesc* d_blocks, int nblocks, int op, cudaStream_t s)
+{
+    if(nblocks == 0) return;
+    diag_map_kernel<<<nblocks < 296 ? nblocks : 296, 256, 0, s>>>(src, dst, d_blocks, nblocks, op);
+    check_cuda(cudaGetLastError(), "diag_map_kernel launch");
+}
+
+// Tensor::twist for fermionic symmetries (src/Core/Tensor.cpp:365-375): scale tree-pair sub-blocks by +-1.
+__global__ void scale_subblocks_kernel(double* __restrict__ data, const SubScale* __restrict__ subs, int n)
+{
+    for(int b = blockIdx.x; b < n; b += gridDim.x) {
+        const SubScale d = subs[b];
+        const long long cnt = static_cast<long long>(d.rows) * d.cols;
+        for(long long e = threadIdx.x; e < cnt; e += blockDim.x) {
+            const long long idx = d.off + (e % d.rows) + (e / d.rows) * d.ld;
+            data[idx] *= d.scale;
+        }
+    }
+}
+
+void launch_scale_subblocks(double* data, const SubScale* d_subs, int n, cudaStream_t s)
+{
+    if(n == 0) return;
+    scale_subblocks_kernel<<<n < 1184 ? n : 1184, 256, 0, s>>>(data, d_subs, n);
+    check_cuda(cudaGetLastError(), "scale_subblocks_kernel launch");
+}
+
+// trace = sum_q weight_q * tr(block_q) (src/Core/TensorBase.cpp:27-37). One block, fixed summation order => deterministic.
+__global__ void trace_kernel(const double* __restrict__ src, const BlockDesc* __restrict__ blocks, int nblocks, double* out)
+{
+    __shared__ double sm[256];
+    double acc = 0.0;
+    for(int b = 0; b < nblocks; ++b) {
+        const BlockDesc d = blocks[b];
+        const int n = d.rows < d.cols ? d.rows : d.cols;
+        double part = 0.0;
+        for(int i = threadIdx.x; i < n; i += blockDim.x) part += src[d.off + i + static_cast<long long>(i) * d.rows];
+        acc += d.weight * part;
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for(int o = 128; o > 0; o >>= 1) {
+        if(threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) *out = sm[0];
+}
+
+void launch_trace(const double* src, const BlockDesc* d_blocks, int nblocks, double* d_out, cudaStream_t s)
+{
+    trace_kernel<<<1, 256, 0, s>>>(src, d_blocks, nblocks, d_out);
+    check_cuda(cudaGetLastError(), "trace_kernel launch");
+}
+
+}   // namespace xb
+
+namespace xb {
+// y = x / (*d_scalar): the max-norm normalisation of renormalize_* (src/PEPS/CTM.cpp:1369,1381,1409) without a host sync.
+__global__ void scale_by_inv_kernel(const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ d_scalar, long long n)
+{
+    const double inv = 1. / *d_scalar;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for(long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = x[i] * inv;
+}
+
+void launch_scale_by_inv(const double* x, double* y, const double* d_scalar, int64_t n, cudaStream_t s)
+{
+    if(n == 0) return;
+    long long g = (n + 255) / 256;
+    if(g > 1184) g = 1184;
+    scale_by_inv_kernel<<<static_cast<int>(g), 256, 0, s>>>(x, y, d_scalar, n);
+    check_cuda(cudaGetLastError(), "scale_by_inv_kernel launch");
+}
+
+__global__ void set_identity_kernel(double* __restrict__ x, const BlockDesc* __restrict__ blocks, int nblocks)
+{
+    for(int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const BlockDesc d = blocks[b];
+        const int n = d.rows < d.cols ? d.rows : d.cols;
+        for(int i = threadIdx.x; i < n; i += blockDim.x) x[d.off + i + static_cast<long long>(i) * d.rows] = 1.0;
+    }
+}
+
+void launch_set_identity(double* x, const BlockDesc* d_blocks, int nblocks, cudaStream_t s)
+{
+    if(nblocks == 0) return;
+    set_identity_kernel<<<nblocks < 296 ? nblocks : 296, 256, 0, s>>>(x, d_blocks, nblocks);
+    check_cuda(cudaGetLastError(), "set_identity_kernel launch");
+}
+}   // namespace xb

@@ -1,0 +1,552 @@
+// Context plumbing, cached layouts and the permute plan builder (host side of Tensor::permute).
+//
+// Reference path being replaced: src/Core/Tensor.cpp:83-214 (permute_impl x2) and :258-333 (permute_adj)
+// recompute the fusion-tree recoupling for every tree pair on every call and move the data in three
+// passes per target.  Here the recoupling is evaluated once per (leg bases, shift, permutation), turned
+// into a gather plan (each destination sub-block = sum_k coeff_k * transpose(src_k)), tiled, uploaded and
+// cached; the data then moves in one kernel launch (kernels.cu: permute_kernel).
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+
+#include "engine.hpp"
+
+namespace xb {
+
+void check_cuda(cudaError_t e, const char* what)
+{
+    if(e != cudaSuccess) throw std::runtime_error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+
+// ------------------------------------------------------------------------------------------------ Context
+Context::Context(int dev, const std::vector<Factor>& factors) : sym(std::make_shared<Symmetry>(factors)), device(dev)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if(e != cudaSuccess || count == 0) {
+        throw std::runtime_error("xped_b200: no CUDA device visible -- this backend has no CPU fallback (" +
+                                 std::string(e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + ")");
+    }
+    check_cuda(cudaSetDevice(device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    check_cuda(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    sm_count = prop.multiProcessorCount;
+    check_cuda(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    cudaMemPool_t pool;
+    check_cuda(cudaDeviceGetDefaultMemPool(&pool, device), "cudaDeviceGetDefaultMemPool");
+    uint64_t threshold = UINT64_MAX;   // keep freed blocks in the pool: block arenas are recycled every CTM move
+    check_cuda(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold), "cudaMemPoolSetAttribute");
+}
+
+Context::~Context()
+{
+    cudaSetDevice(device);
+    if(stream) cudaStreamSynchronize(stream);
+    plan_cache_.clear();
+    for(auto& p : staging_) cudaFreeHost(p.first);
+    if(scratch_) cudaFree(scratch_);
+    if(pinned_) cudaFreeHost(pinned_);
+    if(stream) cudaStreamDestroy(stream);
+}
+
+void Context::sync()
+{
+    check_cuda(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    for(auto& p : staging_) cudaFreeHost(p.first);
+    staging_.clear();
+}
+
+void* Context::scratch(size_t bytes)
+{
+    if(bytes > scratch_bytes_) {
+        check_cuda(cudaStreamSynchronize(stream), "scratch sync");
+        if(scratch_) cudaFree(scratch_);
+        scratch_bytes_ = std::max(bytes, size_t(1) << 20);
+        check_cuda(cudaMalloc(&scratch_, scratch_bytes_), "cudaMalloc scratch");
+    }
+    return scratch_;
+}
+
+void* Context::pinned(size_t bytes)
+{
+    if(bytes > pinned_bytes_) {
+        check_cuda(cudaStreamSynchronize(stream), "pinned sync");
+        if(pinned_) cudaFreeHost(pinned_);
+        pinned_bytes_ = std::max(bytes, size_t(1) << 16);
+        check_cuda(cudaMallocHost(&pinned_, pinned_bytes_), "cudaMallocHost");
+    }
+    return pinned_;
+}
+
+void Context::upload_async(void* dst, const void* src, size_t bytes)
+{
+    if(bytes == 0) return;
+    void* h = nullptr;
+    check_cuda(cudaMallocHost(&h, bytes), "cudaMallocHost staging");
+    std::memcpy(h, src, bytes);
+    staging_.emplace_back(h, bytes);
+    check_cuda(cudaMemcpyAsync(dst, h, bytes, cudaMemcpyHostToDevice, stream), "upload_async");
+}
+
+Tensor::Tensor(Context* c, LayoutPtr l, bool zero) : ctx(c), layout(std::move(l))
+{
+    const size_t bytes = static_cast<size_t>(std::max<int64_t>(layout->size, 1)) * sizeof(double);
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d), bytes, ctx->stream), "cudaMallocAsync(block arena)");
+    if(zero) check_cuda(cudaMemsetAsync(d, 0, bytes, ctx->stream), "cudaMemsetAsync");
+}
+
+Tensor::~Tensor()
+{
+    if(d) cudaFreeAsync(d, ctx->stream);
+}
+
+PermutePlan::~PermutePlan()
+{
+    if(d_tasks) cudaFree(d_tasks);
+    if(d_srcs) cudaFree(d_srcs);
+    if(d_tiles) cudaFree(d_tiles);
+}
+
+// ------------------------------------------------------------------------------------------------ layouts
+namespace {
+std::string bases_sig(const std::vector<BasisPtr>& v)
+{
+    std::string s;
+    for(const auto& b : v) s += b->signature() + "|";
+    return s;
+}
+}   // namespace
+
+BasisPtr Context::coupled(const std::vector<BasisPtr>& uncoupled)
+{
+    std::string key = bases_sig(uncoupled);
+    auto it = coupled_cache_.find(key);
+    if(it != coupled_cache_.end()) return it->second;
+    BasisPtr b = build_fusion_tree(sym, uncoupled);
+    coupled_cache_.emplace(key, b);
+    return b;
+}
+
+static void fill_sectors(Layout& L, const std::vector<Q>* custom)
+{
+    int64_t curr = 0;
+    auto add = [&](const Q& q) {
+        L.dict.emplace(q, static_cast<int>(L.sector.size()));
+        L.sector.push_back(q);
+        L.off.push_back(curr);
+        const int64_t r = L.cdom->inner_dim(q), c = L.ccod->inner_dim(q);
+        L.rows.push_back(r);
+        L.cols.push_back(c);
+        curr += r * c;
+    };
+    if(custom) {
+        for(const Q& q : *custom) add(q);   // push_back order (StorageType_contiguous.hpp:161-171)
+    } else {
+        for(const auto& e : L.cdom->entries())   // resize() (StorageType_contiguous.hpp:79-97)
+            if(L.ccod->find(e.q) >= 0) add(e.q);
+    }
+    L.size = curr;
+}
+
+LayoutPtr Context::layout(const std::vector<BasisPtr>& dom, const std::vector<BasisPtr>& cod)
+{
+    std::string key = bases_sig(dom) + "->" + bases_sig(cod);
+    auto it = layout_cache_.find(key);
+    if(it != layout_cache_.end()) return it->second;
+    auto L = std::make_shared<Layout>();
+    L->dom = dom;
+    L->cod = cod;
+    L->cdom = coupled(dom);
+    L->ccod = coupled(cod);
+    fill_sectors(*L, nullptr);
+    L->sig = key;
+    layout_cache_.emplace(key, L);
+    return L;
+}
+
+LayoutPtr Context::layout_custom(const std::vector<BasisPtr>& dom, const std::vector<BasisPtr>& cod, const std::vector<Q>& sectors)
+{
+    LayoutPtr canon = layout(dom, cod);
+    if(canon->sector == sectors) return canon;
+    std::string key = canon->sig + "#";
+    for(const Q& q : sectors) {
+        for(int i = 0; i < sym->Nq(); ++i) key += std::to_string(q[i]) + ",";
+        key += ";";
+    }
+    auto it = layout_cache_.find(key);
+    if(it != layout_cache_.end()) return it->second;
+    auto L = std::make_shared<Layout>();
+    L->dom = dom;
+    L->cod = cod;
+    L->cdom = canon->cdom;
+    L->ccod = canon->ccod;
+    for(const Q& q : sectors)
+        if(L->cdom->find(q) < 0 || L->ccod->find(q) < 0) throw std::invalid_argument("layout_custom: sector not in both coupled bases");
+    fill_sectors(*L, &sectors);
+    L->sig = key;
+    layout_cache_.emplace(key, L);
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------ permute plans
+namespace {
+
+struct SubBlock   // geometry of one (tree, cotree) sub-block inside its sector matrix
+{
+    int64_t base;
+    int nlegs;
+    int64_t dims[MAXR * 2];
+    int64_t stride[MAXR * 2];
+};
+
+SubBlock geometry(const Layout& L, int sector, const Tree& dt, const Tree& ct)
+{
+    SubBlock g;
+    const int64_t ro = L.cdom->left_offset(dt), co = L.ccod->left_offset(ct);
+    const int64_t ld = L.rows[sector];
+    g.base = L.off[sector] + ro + co * ld;
+    g.nlegs = dt.rank + ct.rank;
+    int64_t s = 1;
+    for(int k = 0; k < dt.rank; ++k) {
+        g.dims[k] = dt.dims[k];
+        g.stride[k] = s;
+        s *= dt.dims[k];
+    }
+    s = ld;
+    for(int k = 0; k < ct.rank; ++k) {
+        g.dims[dt.rank + k] = ct.dims[k];
+        g.stride[dt.rank + k] = s;
+        s *= ct.dims[k];
+    }
+    return g;
+}
+
+struct Contribution
+{
+    SubBlock src;
+    double coeff;
+};
+
+struct DstTask
+{
+    SubBlock dst;
+    std::vector<Contribution> srcs;
+};
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Choose tile extents so that both the source-contiguous and the destination-contiguous runs of a tile
+// are >= `target` elements (coalesced 128-256 B segments on both sides), then grow to ~PERM_TILE_ELEMS.
+void choose_tiles(PermTask& T, const int* sstride0, int target)
+{
+    const int n = T.nleg;
+    int order_s[PERM_MAXLEG];
+    std::iota(order_s, order_s + n, 0);
+    std::stable_sort(order_s, order_s + n, [&](int a, int b) { return sstride0[a] < sstride0[b]; });
+    for(int i = 0; i < n; ++i) T.w[i] = 1;
+    int run = 1;
+    for(int i = 0; i < n && run < target; ++i) {   // destination-contiguous run: legs in dst order
+        T.w[i] = std::min(T.dims[i], ceil_div(target, run));
+        run *= T.w[i];
+        if(T.w[i] < T.dims[i]) break;
+    }
+    run = 1;
+    for(int j = 0; j < n && run < target; ++j) {   // source-contiguous run: legs in src order
+        const int l = order_s[j];
+        T.w[l] = std::max(T.w[l], std::min(T.dims[l], ceil_div(target, run)));
+        run *= T.w[l];
+        if(T.w[l] < T.dims[l]) break;
+    }
+    long long vol = 1;
+    for(int i = 0; i < n; ++i) vol *= T.w[i];
+    // grow: alternate between the two orders so that both runs get longer
+    bool grew = true;
+    while(grew && vol < PERM_TILE_ELEMS) {
+        grew = false;
+        for(int pass = 0; pass < 2 && vol < PERM_TILE_ELEMS; ++pass) {
+            for(int j = 0; j < n; ++j) {
+                const int l = pass == 0 ? j : order_s[j];
+                if(T.w[l] >= T.dims[l]) continue;
+                long long rest = vol / T.w[l];
+                int nw = static_cast<int>(std::min<long long>(T.dims[l], PERM_TILE_ELEMS / rest));
+                // split the leg evenly so that the last tile is not nearly empty
+                if(nw < T.dims[l]) nw = ceil_div(T.dims[l], ceil_div(T.dims[l], nw));
+                if(nw > T.w[l] && rest * nw <= PERM_TILE_ELEMS) {
+                    vol = rest * nw;
+                    T.w[l] = nw;
+                    grew = true;
+                }
+                break;   // only the first incomplete leg of each order extends a contiguous run
+            }
+        }
+    }
+    T.vol = static_cast<int>(vol);
+    // shared-memory packing: src order, with one padding element where the dst-fastest tile leg starts
+    // so that its stride is odd (conflict-free 8-byte accesses in the write-out phase).
+    T.ntl = 0;
+    for(int i = 0; i < n; ++i)
+        if(T.w[i] > 1) T.tl_d[T.ntl++] = i;
+    int k = 0;
+    for(int j = 0; j < n; ++j)
+        if(T.w[order_s[j]] > 1) T.tl_s[k++] = order_s[j];
+    int m = 1;
+    const int lead_d = T.ntl > 0 ? T.tl_d[0] : -1;
+    for(int j = 0; j < T.ntl; ++j) {
+        const int l = T.tl_s[j];
+        if(l == lead_d && m > 1 && (m % 2 == 0)) m += 1;
+        T.smstride[l] = m;
+        m *= T.w[l];
+    }
+    for(int i = 0; i < n; ++i) {
+        if(T.w[i] <= 1) T.smstride[i] = 0;
+        T.ntile[i] = ceil_div(T.dims[i], T.w[i]);
+        T.magic[i] = T.w[i] > 1 ? static_cast<unsigned>(((1ull << 32) + T.w[i] - 1) / T.w[i]) : 0u;
+    }
+}
+
+int smem_extent(const PermTask& T)
+{
+    int ext = 1;
+    for(int j = 0; j < T.ntl; ++j) {
+        const int l = T.tl_s[j];
+        ext = std::max(ext, T.smstride[l] * (T.w[l] - 1) + 1 + (ext - 1));
+    }
+    // exact upper bound: sum over legs of stride*(w-1) + 1
+    int e = 1;
+    for(int j = 0; j < T.ntl; ++j) e += T.smstride[T.tl_s[j]] * (T.w[T.tl_s[j]] - 1);
+    return e;
+}
+
+}   // namespace
+
+std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan)
+{
+    std::string key = in->sig + (adjoint_plan ? "@adj" : "@fwd") + std::to_string(shift) + ":";
+    for(int p : pi) key += std::to_string(p) + ",";
+    auto hit = plan_cache_.find(key);
+    if(hit != plan_cache_.end()) {
+        ++plan_hits;
+        return hit->second;
+    }
+    ++plan_misses;
+
+    const int R = in->rank(), C = in->corank(), N = R + C;
+    if(static_cast<int>(pi.size()) != N) throw std::invalid_argument("permute: permutation has wrong length");
+    {
+        std::vector<int> chk(pi);
+        std::sort(chk.begin(), chk.end());
+        for(int i = 0; i < N; ++i)
+            if(chk[i] != i) throw std::invalid_argument("permute: not a permutation");
+    }
+    std::vector<int> pinv(N);
+    for(int i = 0; i < N; ++i) pinv[pi[i]] = i;
+    const Symmetry& S = *sym;
+
+    auto plan = std::make_shared<PermutePlan>();
+    bool is_identity = (shift == 0);
+    for(int i = 0; i < N && is_identity; ++i) is_identity = (pi[i] == i);
+    if(is_identity) {   // Tensor.cpp:344 / :263
+        plan->out = in;
+        plan->identity_copy = true;
+        plan->bytes = 16 * in->size;
+        plan_cache_.emplace(key, plan);
+        return plan;
+    }
+
+    // ---- output bases: Tensor.cpp:157-174 (forward) / :273-287 (adjoint; pi_inv and the opposite shift)
+    const std::vector<int>& leg_of = adjoint_plan ? pinv : pi;
+    const int newR = adjoint_plan ? R + shift : R - shift;
+    if(newR < 0 || newR > N) throw std::invalid_argument("permute: shift out of range");
+    std::vector<BasisPtr> nd, nc;
+    for(int i = 0; i < N; ++i) {
+        const int s = leg_of[i];
+        const bool to_domain = i < newR;
+        BasisPtr b;
+        if(s > R - 1 || R == 0) {
+            b = in->cod[s - R];
+            if(to_domain) b = b->conj();
+        } else {
+            b = in->dom[s];
+            if(!to_domain) b = b->conj();
+        }
+        (to_domain ? nd : nc).push_back(b);
+    }
+    LayoutPtr out = layout(nd, nc);
+    plan->out = out;
+    plan->bytes = 8 * (in->size + out->size);
+
+    // ---- destination tasks, one per (sector, tree, cotree) of the output, in storage order
+    std::vector<DstTask> tasks;
+    std::vector<std::vector<int>> task_index(out->sector.size());   // [sector][a * ncod + b]
+    std::vector<int> ncod(out->sector.size());
+    for(size_t j = 0; j < out->sector.size(); ++j) {
+        const auto& dts = out->cdom->trees(out->sector[j]);
+        const auto& cts = out->ccod->trees(out->sector[j]);
+        ncod[j] = static_cast<int>(cts.size());
+        task_index[j].resize(dts.size() * cts.size());
+        for(size_t a = 0; a < dts.size(); ++a)
+            for(size_t b = 0; b < cts.size(); ++b) {
+                task_index[j][a * cts.size() + b] = static_cast<int>(tasks.size());
+                DstTask t;
+                t.dst = geometry(*out, static_cast<int>(j), dts[a], cts[b]);
+                tasks.push_back(std::move(t));
+            }
+    }
+    auto dst_task = [&](const Tree& dt, const Tree& ct) -> int {
+        const int j = out->find(dt.coupled);
+        if(j < 0) throw std::logic_error("permute plan: target sector missing in output layout");
+        int a = -1, b = -1;
+        out->cdom->left_offset(dt, &a);
+        out->ccod->left_offset(ct, &b);
+        return task_index[j][a * ncod[j] + b];
+    };
+
+    if(!adjoint_plan) {
+        const bool intra = [&] {   // Tensor.cpp:346-351
+            if(shift != 0) return false;
+            for(int i = 0; i < R; ++i)
+                if(pi[i] >= R) return false;
+            for(int i = R; i < N; ++i)
+                if(pi[i] < R) return false;
+            return true;
+        }();
+        std::vector<int> pd(pi.begin(), pi.begin() + (intra ? R : 0)), pc;
+        if(intra)
+            for(int i = R; i < N; ++i) pc.push_back(pi[i] - R);
+        for(size_t i = 0; i < in->sector.size(); ++i) {
+            const auto& dts = in->cdom->trees(in->sector[i]);
+            const auto& cts = in->ccod->trees(in->sector[i]);
+            std::vector<TreeMap> pcts;
+            if(intra)
+                for(const Tree& ct : cts) pcts.push_back(tree_permute(S, ct, pc));
+            for(const Tree& dt : dts) {
+                TreeMap pdt;
+                if(intra) pdt = tree_permute(S, dt, pd);
+                for(size_t b = 0; b < cts.size(); ++b) {
+                    const Tree& ct = cts[b];
+                    SubBlock g = geometry(*in, static_cast<int>(i), dt, ct);
+                    if(intra) {   // Tensor.cpp:109-143
+                        for(const auto& [ndt, cd] : pdt)
+                            for(const auto& [nct, cc] : pcts[b]) {
+                                if(std::abs(cd * cc) < 1.e-10) continue;
+                                tasks[dst_task(ndt, nct)].srcs.push_back({g, cd * cc});
+                            }
+                    } else {   // Tensor.cpp:179-210
+                        for(const auto& [pr, coeff] : treepair_permute(S, shift, dt, ct, pi)) {
+                            if(std::abs(coeff) < 1.e-10) continue;
+                            tasks[dst_task(pr.d, pr.c)].srcs.push_back({g, coeff});
+                        }
+                    }
+                }
+            }
+        }
+    } else {   // Tensor.cpp:292-330: gather form over the result's tree pairs
+        for(size_t j = 0; j < out->sector.size(); ++j) {
+            const auto& dts = out->cdom->trees(out->sector[j]);
+            const auto& cts = out->ccod->trees(out->sector[j]);
+            for(size_t a = 0; a < dts.size(); ++a)
+                for(size_t b = 0; b < cts.size(); ++b) {
+                    DstTask& t = tasks[task_index[j][a * cts.size() + b]];
+                    for(const auto& [pr, coeff] : treepair_permute(S, shift, dts[a], cts[b], pi)) {
+                        if(std::abs(coeff) < 1.e-10) continue;
+                        const int i = in->find(pr.d.coupled);
+                        if(i < 0) throw std::logic_error("permute_adj plan: source sector missing");
+                        t.srcs.push_back({geometry(*in, i, pr.d, pr.c), coeff});
+                    }
+                }
+        }
+    }
+
+    // ---- lower to device records
+    std::vector<PermTask> h_tasks;
+    std::vector<PermSrc> h_srcs;
+    std::vector<PermTile> h_tiles;
+    h_tasks.reserve(tasks.size());
+    for(const DstTask& t : tasks) {
+        if(t.dst.nlegs != N) throw std::logic_error("permute plan: leg count mismatch");
+        // legs in dst order with their per-source strides; drop extent-1 legs
+        int n = 0;
+        int64_t d[MAXR * 2], ds[MAXR * 2];
+        std::vector<std::array<int64_t, MAXR * 2>> ss(t.srcs.size());
+        int64_t count = 1;
+        for(int j = 0; j < N; ++j) {
+            count *= t.dst.dims[j];
+            if(t.dst.dims[j] == 1) continue;
+            d[n] = t.dst.dims[j];
+            ds[n] = t.dst.stride[j];
+            for(size_t k = 0; k < t.srcs.size(); ++k) {
+                if(t.srcs[k].src.dims[leg_of[j]] != t.dst.dims[j]) throw std::logic_error("permute plan: extent mismatch between source and target leg");
+                ss[k][n] = t.srcs[k].src.stride[leg_of[j]];
+            }
+            ++n;
+        }
+        if(count == 0) continue;
+        // fuse neighbouring legs that are contiguous in the destination and in every source
+        int m = 0;
+        for(int j = 0; j < n; ++j) {
+            bool fuse = m > 0 && ds[j] == ds[m - 1] * d[m - 1];
+            for(size_t k = 0; fuse && k < ss.size(); ++k) fuse = ss[k][j] == ss[k][m - 1] * d[m - 1];
+            if(fuse) {
+                d[m - 1] *= d[j];
+            } else {
+                d[m] = d[j];
+                ds[m] = ds[j];
+                for(auto& s : ss) s[m] = s[j];
+                ++m;
+            }
+        }
+        n = m;
+        if(n > PERM_MAXLEG) throw std::length_error("permute plan: more than 8 non-fusable legs");
+        PermTask T;
+        std::memset(&T, 0, sizeof(T));
+        T.dst_off = t.dst.base;
+        T.nleg = n;
+        T.src_begin = static_cast<int>(h_srcs.size());
+        T.src_count = static_cast<int>(t.srcs.size());
+        for(int j = 0; j < n; ++j) {
+            if(d[j] > INT32_MAX || ds[j] > INT32_MAX) throw std::length_error("permute plan: extent exceeds 32-bit index range");
+            T.dims[j] = static_cast<int>(d[j]);
+            T.dstride[j] = static_cast<int>(ds[j]);
+        }
+        for(size_t k = 0; k < t.srcs.size(); ++k) {
+            PermSrc s;
+            std::memset(&s, 0, sizeof(s));
+            s.off = t.srcs[k].src.base;
+            s.coeff = t.srcs[k].coeff;
+            for(int j = 0; j < n; ++j) {
+                if(ss[k][j] > INT32_MAX) throw std::length_error("permute plan: stride exceeds 32-bit index range");
+                s.sstride[j] = static_cast<int>(ss[k][j]);
+            }
+            h_srcs.push_back(s);
+        }
+        int s0[PERM_MAXLEG];
+        for(int j = 0; j < n; ++j) s0[j] = t.srcs.empty() ? T.dstride[j] : h_srcs[T.src_begin].sstride[j];
+        choose_tiles(T, s0, 32);
+        if(T.vol > PERM_TILE_ELEMS || smem_extent(T) > PERM_BUF_ELEMS) choose_tiles(T, s0, 16);
+        if(T.vol > PERM_TILE_ELEMS || smem_extent(T) > PERM_BUF_ELEMS) throw std::logic_error("permute plan: tile does not fit shared memory");
+        long long nt = 1;
+        for(int j = 0; j < n; ++j) nt *= T.ntile[j];
+        const int tid = static_cast<int>(h_tasks.size());
+        for(long long x = 0; x < nt; ++x) h_tiles.push_back({tid, static_cast<int>(x)});
+        plan->max_fan_in = std::max(plan->max_fan_in, T.src_count);
+        h_tasks.push_back(T);
+    }
+    plan->n_tasks = static_cast<int>(h_tasks.size());
+    plan->n_srcs = static_cast<int>(h_srcs.size());
+    plan->n_tiles = static_cast<int>(h_tiles.size());
+    if(plan->n_tasks) {
+        check_cuda(cudaMalloc(&plan->d_tasks, h_tasks.size() * sizeof(PermTask)), "cudaMalloc plan tasks");
+        check_cuda(cudaMemcpy(plan->d_tasks, h_tasks.data(), h_tasks.size() * sizeof(PermTask), cudaMemcpyHostToDevice), "upload plan tasks");
+        check_cuda(cudaMalloc(&plan->d_tiles, h_tiles.size() * sizeof(PermTile)), "cudaMalloc plan tiles");
+        check_cuda(cudaMemcpy(plan->d_tiles, h_tiles.data(), h_tiles.size() * sizeof(PermTile), cudaMemcpyHostToDevice), "upload plan tiles");
+    }
+    if(plan->n_srcs) {
+        check_cuda(cudaMalloc(&plan->d_srcs, h_srcs.size() * sizeof(PermSrc)), "cudaMalloc plan sources");
+        check_cuda(cudaMemcpy(plan->d_srcs, h_srcs.data(), h_srcs.size() * sizeof(PermSrc), cudaMemcpyHostToDevice), "upload plan sources");
+    }
+    plan_cache_.emplace(key, plan);
+    return plan;
+}
+
+}   // namespace xb

@@ -1,0 +1,495 @@
+// Batched per-sector decompositions: tSVD (+ global truncation), teigh, tQR.
+//
+// Reference: Tensor::tSVD / full_svd_impl / cutoff_matrices (src/Core/Tensor.cpp:478-633) loops over sectors and
+// calls LAPACK/Eigen per block (src/Interfaces/PlainInterface_Eigen_impl.cpp:114-127); here ALL sector blocks are
+// decomposed together by a block one-sided Jacobi (Hestenes) method:
+//   work matrix W_q (tall side first) and accumulator V_q = I; one kernel launch per round-robin round handles
+//   every (column-block pair, sector) in parallel: Gram matrix of the 2x16 columns -> cyclic Jacobi
+//   eigen-rotation in shared memory -> panel update of W_q and V_q.  Converged columns of W_q are sigma_j * u_j.
+// The singular values of all sectors are then sorted globally on the host (<= ~1e4 numbers) for the truncation
+// decision (Tensor.cpp:543-557) and one gather kernel writes the truncated U, Sigma, V^dagger.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <stdexcept>
+
+#include "engine.hpp"
+
+namespace xb {
+
+namespace {
+
+constexpr int SB = 16;    // column-block width
+constexpr int SP = 32;    // panel = two column blocks
+constexpr int SCH = 64;   // rows per staged chunk
+constexpr int SVD_THREADS = 256;
+
+struct SvdBlock
+{
+    long long w_off;   // work matrix, rows x cols, column-major, ld = rows
+    long long v_off;   // accumulator, cols x cols
+    long long s_off;   // singular values (cols)
+    int rows, cols;
+    double tol;
+};
+
+struct SvdTask { int block, bi, bj; };
+
+__global__ void svd_init_kernel(const double* __restrict__ A, double* __restrict__ W, double* __restrict__ V, const SvdBlock* __restrict__ blocks,
+                                const long long* __restrict__ a_off, const int* __restrict__ a_rows, const int* __restrict__ transposed, int nblocks)
+{
+    for(int b = blockIdx.y; b < nblocks; b += gridDim.y) {
+        const SvdBlock d = blocks[b];
+        const long long cnt = static_cast<long long>(d.rows) * d.cols;
+        const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+        const int lda = a_rows[b];
+        for(long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < cnt; e += stride) {
+            const int r = static_cast<int>(e % d.rows), c = static_cast<int>(e / d.rows);
+            W[d.w_off + e] = transposed[b] ? A[a_off[b] + c + static_cast<long long>(r) * lda] : A[a_off[b] + r + static_cast<long long>(c) * lda];
+        }
+        const long long vc = static_cast<long long>(d.cols) * d.cols;
+        for(long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < vc; e += stride)
+            V[d.v_off + e] = (e % d.cols == e / d.cols) ? 1.0 : 0.0;
+    }
+}
+
+__device__ __forceinline__ void panel_pair(int step, int g, int& p, int& q)
+{
+    // round-robin tournament on SP = 32 players: 31 steps x 16 disjoint pairs
+    int a, b;
+    if(g == 0) {
+        a = SP - 1;
+        b = step;
+    } else {
+        a = (step + g) % (SP - 1);
+        b = (step - g + (SP - 1)) % (SP - 1);
+    }
+    p = a < b ? a : b;
+    q = a < b ? b : a;
+}
+
+__global__ void __launch_bounds__(SVD_THREADS)
+svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock* __restrict__ blocks, const SvdTask* __restrict__ tasks, int* __restrict__ rotated)
+{
+    __shared__ double G[SP][SP + 1];
+    __shared__ double Vl[SP][SP + 1];
+    __shared__ double Xs[SP][SCH + 1];
+    __shared__ int colidx[SP];
+    __shared__ int s_any, s_total;
+
+    const int tid = threadIdx.x;
+    const SvdTask task = tasks[blockIdx.x];
+    const SvdBlock blk = blocks[task.block];
+    if(tid < SP) {
+        int c = tid < SB ? task.bi * SB + tid : (task.bj >= 0 ? task.bj * SB + (tid - SB) : -1);
+        if(c >= blk.cols) c = -1;
+        colidx[tid] = c;
+    }
+    if(tid == 0) s_total = 0;
+    __syncthreads();
+
+    // ---- Gram matrix of the panel
+    {
+        const int i = tid & 31, j0 = (tid >> 5) * 4;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for(int r0 = 0; r0 < blk.rows; r0 += SCH) {
+            for(int e = tid; e < SP * SCH; e += SVD_THREADS) {
+                const int col = e / SCH, row = e % SCH;
+                const int gr = r0 + row, gc = colidx[col];
+                Xs[col][row] = (gc >= 0 && gr < blk.rows) ? W[blk.w_off + gr + static_cast<long long>(gc) * blk.rows] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for(int row = 0; row < SCH; ++row) {
+                const double xi = Xs[i][row];
+#pragma unroll
+                for(int k = 0; k < 4; ++k) acc[k] = fma(xi, Xs[j0 + k][row], acc[k]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for(int k = 0; k < 4; ++k) G[i][j0 + k] = acc[k];
+        for(int e = tid; e < SP * SP; e += SVD_THREADS) Vl[e / SP][e % SP] = (e / SP == e % SP) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+
+    // ---- cyclic Jacobi on G (two-sided), rotations accumulated in Vl
+    const int grp = tid >> 4, l = tid & 15;
+    for(int sweep = 0; sweep < 10; ++sweep) {
+        if(tid == 0) s_any = 0;
+        __syncthreads();
+        for(int step = 0; step < SP - 1; ++step) {
+            int p, q;
+            panel_pair(step, grp, p, q);
+            const double a = G[p][p], b = G[q][q], c = G[p][q];
+            double cs = 1.0, sn = 0.0;
+            const bool rot = (a > 0.0 && b > 0.0 && fabs(c) > blk.tol * sqrt(a * b));
+            if(rot) {
+                const double zeta = (b - a) / (2.0 * c);
+                const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                cs = 1.0 / sqrt(1.0 + t * t);
+                sn = cs * t;
+            }
+            __syncthreads();   // everybody has read its pivots
+            if(rot) {
+                if(l == 0) s_any = 1;
+#pragma unroll
+                for(int h = 0; h < 2; ++h) {   // columns p, q of G and Vl
+                    const int r = l + 16 * h;
+                    const double gp = G[r][p], gq = G[r][q];
+                    G[r][p] = cs * gp - sn * gq;
+                    G[r][q] = sn * gp + cs * gq;
+                    const double vp = Vl[r][p], vq = Vl[r][q];
+                    Vl[r][p] = cs * vp - sn * vq;
+                    Vl[r][q] = sn * vp + cs * vq;
+                }
+            }
+            __syncthreads();
+            if(rot) {
+#pragma unroll
+                for(int h = 0; h < 2; ++h) {   // rows p, q of G
+                    const int r = l + 16 * h;
+                    const double gp = G[p][r], gq = G[q][r];
+                    G[p][r] = cs * gp - sn * gq;
+                    G[q][r] = sn * gp + cs * gq;
+                }
+            }
+            __syncthreads();
+        }
+        if(tid == 0 && s_any) s_total = 1;
+        const int any = s_any;
+        __syncthreads();
+        if(!any) break;
+    }
+    if(!s_total) return;   // panel already orthogonal: nothing to update
+    if(tid == 0) atomicExch(rotated, 1);
+
+    // ---- panel updates  X <- X * Vl  for W (rows) and V (cols)
+    for(int which = 0; which < 2; ++which) {
+        double* __restrict__ M = which == 0 ? W + blk.w_off : V + blk.v_off;
+        const int nrows = which == 0 ? blk.rows : blk.cols;
+        const int row = tid & (SCH - 1), c0 = (tid >> 6) * 8;
+        for(int r0 = 0; r0 < nrows; r0 += SCH) {
+            for(int e = tid; e < SP * SCH; e += SVD_THREADS) {
+                const int col = e / SCH, rr = e % SCH;
+                const int gr = r0 + rr, gc = colidx[col];
+                Xs[col][rr] = (gc >= 0 && gr < nrows) ? M[gr + static_cast<long long>(gc) * nrows] : 0.0;
+            }
+            __syncthreads();
+            double out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+            for(int k = 0; k < SP; ++k) {
+                const double x = Xs[k][row];
+#pragma unroll
+                for(int c = 0; c < 8; ++c) out[c] = fma(x, Vl[k][c0 + c], out[c]);
+            }
+            const int gr = r0 + row;
+            if(gr < nrows) {
+#pragma unroll
+                for(int c = 0; c < 8; ++c) {
+                    const int gc = colidx[c0 + c];
+                    if(gc >= 0) M[gr + static_cast<long long>(gc) * nrows] = out[c];
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// column norms -> singular values; one warp per column
+__global__ void svd_norms_kernel(const double* __restrict__ W, const SvdBlock* __restrict__ blocks, int nblocks, double* __restrict__ sigma)
+{
+    const int warps_per_block = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for(int b = blockIdx.y; b < nblocks; b += gridDim.y) {
+        const SvdBlock d = blocks[b];
+        for(int c = blockIdx.x * warps_per_block + warp; c < d.cols; c += gridDim.x * warps_per_block) {
+            const double* col = W + d.w_off + static_cast<long long>(c) * d.rows;
+            // scaled two-pass norm is unnecessary here: entries are O(sigma_max) at most, squares stay in range
+            double s = 0.0;
+            for(int r = lane; r < d.rows; r += 32) s = fma(col[r], col[r], s);
+            for(int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if(lane == 0) sigma[d.s_off + c] = sqrt(s);
+        }
+    }
+}
+
+struct GatherCol
+{
+    long long w_src;   // start of the work-matrix column (length wl)
+    long long v_src;   // start of the accumulator column (length vl)
+    long long u_dst, vd_dst, s_dst;
+    int wl, vl;
+    int vd_ld;         // leading dimension (= kept count) of the V^dagger block
+    int w_is_u;        // 1: W column -> U column, V column -> V^dagger row; 0: the transposed case
+    double sigma;
+};
+
+__global__ void svd_gather_kernel(const double* __restrict__ W, const double* __restrict__ V, double* __restrict__ U, double* __restrict__ S,
+                                  double* __restrict__ Vd, const GatherCol* __restrict__ cols, int n)
+{
+    for(int i = blockIdx.x; i < n; i += gridDim.x) {
+        const GatherCol g = cols[i];
+        const double inv = g.sigma > 0.0 ? 1.0 / g.sigma : 0.0;
+        if(g.w_is_u) {
+            for(int r = threadIdx.x; r < g.wl; r += blockDim.x) U[g.u_dst + r] = W[g.w_src + r] * inv;
+            for(int r = threadIdx.x; r < g.vl; r += blockDim.x) Vd[g.vd_dst + static_cast<long long>(r) * g.vd_ld] = V[g.v_src + r];
+        } else {
+            for(int r = threadIdx.x; r < g.vl; r += blockDim.x) U[g.u_dst + r] = V[g.v_src + r];
+            for(int r = threadIdx.x; r < g.wl; r += blockDim.x) Vd[g.vd_dst + static_cast<long long>(r) * g.vd_ld] = W[g.w_src + r] * inv;
+        }
+        if(threadIdx.x == 0) S[g.s_dst] = g.sigma;
+    }
+}
+
+// Round-robin schedule over `nb` column blocks: rounds x pairs; a bye (odd nb / nb == 1) becomes a single-block task.
+void schedule(int block, int nb, std::vector<std::vector<SvdTask>>& rounds)
+{
+    if(nb <= 0) return;
+    if(nb == 1) {
+        if(rounds.empty()) rounds.resize(1);
+        rounds[0].push_back({block, 0, -1});
+        return;
+    }
+    const int n = nb + (nb & 1);   // even number of players, player n-1 may be the dummy
+    if(static_cast<int>(rounds.size()) < n - 1) rounds.resize(n - 1);
+    for(int r = 0; r < n - 1; ++r) {
+        for(int g = 0; g < n / 2; ++g) {
+            int a, b;
+            if(g == 0) {
+                a = n - 1;
+                b = r;
+            } else {
+                a = (r + g) % (n - 1);
+                b = (r - g + (n - 1)) % (n - 1);
+            }
+            if(a > b) std::swap(a, b);
+            if(b >= nb) {
+                // bye: orthogonalise inside the lone block only in the first round (it meets every other block later)
+                if(r == 0) rounds[r].push_back({block, a, -1});
+            } else {
+                rounds[r].push_back({block, a, b});
+            }
+        }
+    }
+}
+
+struct JacobiResult
+{
+    std::vector<SvdBlock> blocks;
+    std::vector<int> transposed;
+    std::vector<double> sigma;   // host copy, per block at s_off
+    double* d_W = nullptr;
+    double* d_V = nullptr;
+    int sweeps = 0;
+};
+
+// One-sided block Jacobi on every sector block of `t`. Leaves W (= sigma_j u_j columns) and V on the device.
+JacobiResult jacobi_all(Context& ctx, const Tensor& t, const std::vector<double>* shift)
+{
+    const Layout& L = *t.layout;
+    const int nb = static_cast<int>(L.sector.size());
+    JacobiResult R;
+    R.blocks.resize(nb);
+    R.transposed.resize(nb);
+    long long woff = 0, voff = 0, soff = 0;
+    std::vector<long long> a_off(nb);
+    std::vector<int> a_rows(nb);
+    for(int i = 0; i < nb; ++i) {
+        const int m = static_cast<int>(L.rows[i]), n = static_cast<int>(L.cols[i]);
+        const bool tr = m < n;
+        R.transposed[i] = tr;
+        SvdBlock& b = R.blocks[i];
+        b.rows = tr ? n : m;
+        b.cols = tr ? m : n;
+        b.w_off = woff;
+        b.v_off = voff;
+        b.s_off = soff;
+        b.tol = 4.0 * 2.220446049250313e-16 * std::sqrt(static_cast<double>(std::max(b.rows, 1)));
+        woff += static_cast<long long>(b.rows) * b.cols;
+        voff += static_cast<long long>(b.cols) * b.cols;
+        soff += b.cols;
+        a_off[i] = L.off[i];
+        a_rows[i] = m;
+    }
+    R.sigma.assign(static_cast<size_t>(soff), 0.0);
+    if(nb == 0 || woff == 0) return R;
+    cudaStream_t s = ctx.stream;
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&R.d_W), sizeof(double) * std::max<long long>(woff, 1), s), "svd W");
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&R.d_V), sizeof(double) * std::max<long long>(voff, 1), s), "svd V");
+
+    // schedule
+    std::vector<std::vector<SvdTask>> rounds;
+    for(int i = 0; i < nb; ++i) schedule(i, (R.blocks[i].cols + SB - 1) / SB, rounds);
+    std::vector<SvdTask> flat;
+    std::vector<int> round_begin;
+    for(const auto& r : rounds) {
+        round_begin.push_back(static_cast<int>(flat.size()));
+        flat.insert(flat.end(), r.begin(), r.end());
+    }
+    round_begin.push_back(static_cast<int>(flat.size()));
+
+    // device metadata: blocks | a_off | a_rows | transposed | tasks | sigma | flag
+    const size_t o_blocks = 0, o_aoff = o_blocks + sizeof(SvdBlock) * nb, o_arows = o_aoff + sizeof(long long) * nb, o_tr = o_arows + sizeof(int) * nb;
+    size_t o_tasks = o_tr + sizeof(int) * nb;
+    o_tasks = (o_tasks + 15) & ~size_t(15);
+    size_t o_sigma = o_tasks + sizeof(SvdTask) * flat.size();
+    o_sigma = (o_sigma + 15) & ~size_t(15);
+    const size_t o_flag = o_sigma + sizeof(double) * soff;
+    const size_t meta_bytes = o_flag + 16;
+    char* d_meta = nullptr;
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_meta), meta_bytes, s), "svd meta");
+    std::vector<char> h_meta(o_sigma, 0);
+    std::memcpy(h_meta.data() + o_blocks, R.blocks.data(), sizeof(SvdBlock) * nb);
+    std::memcpy(h_meta.data() + o_aoff, a_off.data(), sizeof(long long) * nb);
+    std::memcpy(h_meta.data() + o_arows, a_rows.data(), sizeof(int) * nb);
+    std::memcpy(h_meta.data() + o_tr, R.transposed.data(), sizeof(int) * nb);
+    if(!flat.empty()) std::memcpy(h_meta.data() + o_tasks, flat.data(), sizeof(SvdTask) * flat.size());
+    ctx.upload_async(d_meta, h_meta.data(), h_meta.size());
+    auto* d_blocks = reinterpret_cast<SvdBlock*>(d_meta + o_blocks);
+    auto* d_tasks = reinterpret_cast<SvdTask*>(d_meta + o_tasks);
+    auto* d_sigma = reinterpret_cast<double*>(d_meta + o_sigma);
+    auto* d_flag = reinterpret_cast<int*>(d_meta + o_flag);
+
+    {
+        dim3 grid(64, static_cast<unsigned>(std::min(nb, 64)));
+        svd_init_kernel<<<grid, 256, 0, s>>>(t.d, R.d_W, R.d_V, d_blocks, reinterpret_cast<long long*>(d_meta + o_aoff),
+                                            reinterpret_cast<int*>(d_meta + o_arows), reinterpret_cast<int*>(d_meta + o_tr), nb);
+        check_cuda(cudaGetLastError(), "svd_init_kernel launch");
+        ++ctx.launches;
+    }
+    (void)shift;
+    int* h_flag = static_cast<int*>(ctx.pinned(sizeof(int)));
+    const int max_sweeps = 40;
+    for(R.sweeps = 0; R.sweeps < max_sweeps; ++R.sweeps) {
+        check_cuda(cudaMemsetAsync(d_flag, 0, sizeof(int), s), "svd flag reset");
+        for(size_t r = 0; r + 1 < round_begin.size(); ++r) {
+            const int cnt = round_begin[r + 1] - round_begin[r];
+            if(cnt == 0) continue;
+            svd_round_kernel<<<cnt, SVD_THREADS, 0, s>>>(R.d_W, R.d_V, d_blocks, d_tasks + round_begin[r], d_flag);
+            ++ctx.launches;
+        }
+        check_cuda(cudaGetLastError(), "svd_round_kernel launch");
+        check_cuda(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s), "svd flag readback");
+        check_cuda(cudaStreamSynchronize(s), "svd sweep sync");
+        if(*h_flag == 0) break;
+    }
+    if(R.sweeps >= max_sweeps) {
+        cudaFreeAsync(d_meta, s);
+        cudaFreeAsync(R.d_W, s);
+        cudaFreeAsync(R.d_V, s);
+        throw std::runtime_error("tSVD: block Jacobi did not converge in 40 sweeps");
+    }
+    {
+        dim3 grid(32, static_cast<unsigned>(std::min(nb, 64)));
+        svd_norms_kernel<<<grid, 256, 0, s>>>(R.d_W, d_blocks, nb, d_sigma);
+        check_cuda(cudaGetLastError(), "svd_norms_kernel launch");
+        ++ctx.launches;
+    }
+    check_cuda(cudaMemcpyAsync(R.sigma.data(), d_sigma, sizeof(double) * soff, cudaMemcpyDeviceToHost, s), "sigma readback");
+    check_cuda(cudaStreamSynchronize(s), "svd sync");
+    check_cuda(cudaFreeAsync(d_meta, s), "svd meta free");
+    return R;
+}
+
+void free_jacobi(Context& ctx, JacobiResult& R)
+{
+    if(R.d_W) cudaFreeAsync(R.d_W, ctx.stream);
+    if(R.d_V) cudaFreeAsync(R.d_V, ctx.stream);
+    R.d_W = R.d_V = nullptr;
+}
+
+}   // namespace
+
+// ------------------------------------------------------------------------------------------------ tSVD
+SvdResult Context::tsvd(const Tensor& t, int64_t max_keep, double eps_svd, bool preserve_multiplets)
+{
+    const Layout& L = *t.layout;
+    if(L.sector.empty()) throw std::invalid_argument("tSVD: tensor has no blocks");
+    JacobiResult J = jacobi_all(*this, t, nullptr);
+    struct SV { int sector; int col; double s; };
+    std::vector<SV> all;
+    for(size_t i = 0; i < L.sector.size(); ++i) {
+        const SvdBlock& b = J.blocks[i];
+        // per-block descending order first (what LAPACK returns), ties by column index
+        std::vector<int> idx(b.cols);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return J.sigma[b.s_off + x] > J.sigma[b.s_off + y]; });
+        for(int c : idx) all.push_back({static_cast<int>(i), c, J.sigma[b.s_off + c]});
+    }
+    if(all.empty()) throw std::invalid_argument("tSVD: tensor has no singular values");
+    const SV first_entry = all[0];
+    // Tensor.cpp:543-547; the reference's std::sort is unstable for ties -- here ties keep (sector, k) order.
+    std::stable_sort(all.begin(), all.end(), [](const SV& a, const SV& b) { return a.s > b.s; });
+    SvdResult res;
+    for(size_t i = static_cast<size_t>(std::max<int64_t>(max_keep, 0)); i < all.size(); ++i)   // :548
+        res.trunc_weight += sym->degeneracy(L.sector[all[i].sector]) * all[i].s * all[i].s;
+    if(static_cast<int64_t>(all.size()) > max_keep) all.resize(static_cast<size_t>(std::max<int64_t>(max_keep, 0)));
+    if(eps_svd > 0.0) all.erase(std::remove_if(all.begin(), all.end(), [eps_svd](const SV& x) { return x.s < eps_svd; }), all.end());   // :551-557
+    if(preserve_multiplets) {   // :569-584
+        int end_of_multiplet = -1;
+        for(int i = static_cast<int>(all.size()) - 1; i > 0; --i) {
+            const double rel = 2 * (all[i - 1].s - all[i].s) / (all[i - 1].s + all[i].s);
+            if(rel > 0.1) {
+                end_of_multiplet = i;
+                break;
+            }
+        }
+        if(end_of_multiplet != -1) all.resize(end_of_multiplet);
+    }
+    if(all.empty()) all.push_back(first_entry);   // :586-590
+    std::map<Q, std::vector<SV>> ordered;         // std::map => ascending qarray order (:592-598)
+    for(const SV& x : all) {
+        ordered[L.sector[x.sector]].push_back(x);
+        res.entropy += -sym->degeneracy(L.sector[x.sector]) * x.s * x.s * std::log(x.s * x.s);
+    }
+    auto trunc = std::make_shared<Qbasis>(sym, 1);
+    std::vector<Q> qs;
+    for(const auto& [q, v] : ordered) {
+        trunc->push_back(q, static_cast<int64_t>(v.size()));
+        qs.push_back(q);
+    }
+    BasisPtr tb = trunc;
+    LayoutPtr LU = layout_custom(L.dom, {tb}, qs), LS = layout_custom({tb}, {tb}, qs), LV = layout_custom({tb}, L.cod, qs);
+    res.U = new Tensor(this, LU, false);
+    res.S = new Tensor(this, LS, true);
+    res.Vd = new Tensor(this, LV, false);
+    std::vector<GatherCol> cols;
+    for(size_t k = 0; k < qs.size(); ++k) {
+        const auto& v = ordered[qs[k]];
+        const int i = v[0].sector;
+        const SvdBlock& b = J.blocks[i];
+        const int nret = static_cast<int>(v.size());
+        const int m = static_cast<int>(L.rows[i]), n = static_cast<int>(L.cols[i]);
+        for(int r = 0; r < nret; ++r) {
+            GatherCol g;
+            g.w_src = b.w_off + static_cast<long long>(v[r].col) * b.rows;
+            g.v_src = b.v_off + static_cast<long long>(v[r].col) * b.cols;
+            g.wl = b.rows;
+            g.vl = b.cols;
+            g.u_dst = LU->off[k] + static_cast<long long>(r) * m;
+            g.vd_dst = LV->off[k] + r;
+            g.vd_ld = nret;
+            g.s_dst = LS->off[k] + r + static_cast<long long>(r) * nret;
+            g.w_is_u = J.transposed[i] ? 0 : 1;
+            g.sigma = v[r].s;
+            (void)n;
+            cols.push_back(g);
+        }
+    }
+    GatherCol* d_cols = nullptr;
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_cols), sizeof(GatherCol) * cols.size(), stream), "svd gather meta");
+    upload_async(d_cols, cols.data(), sizeof(GatherCol) * cols.size());
+    svd_gather_kernel<<<static_cast<unsigned>(std::min<size_t>(cols.size(), 2368)), 128, 0, stream>>>(J.d_W, J.d_V, res.U->d, res.S->d, res.Vd->d, d_cols,
+                                                                                                      static_cast<int>(cols.size()));
+    check_cuda(cudaGetLastError(), "svd_gather_kernel launch");
+    ++launches;
+    check_cuda(cudaFreeAsync(d_cols, stream), "svd gather free");
+    free_jacobi(*this, J);
+    return res;
+}
+
+}   // namespace xb

@@ -1,0 +1,315 @@
+// Whole-tensor operations of the B200 backend (the methods of Xped::Tensor that sit on the hot path).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <stdexcept>
+
+#include "engine.hpp"
+
+namespace xb {
+
+// ------------------------------------------------------------------------------------------------ permute
+Tensor* Context::permute(const Tensor& t, int shift, const std::vector<int>& pi)
+{
+    auto plan = permute_plan(t.layout, shift, pi, false);
+    auto* out = new Tensor(this, plan->out, false);
+    if(plan->identity_copy) {
+        check_cuda(cudaMemcpyAsync(out->d, t.d, sizeof(double) * t.size(), cudaMemcpyDeviceToDevice, stream), "permute identity copy");
+    } else {
+        launch_permute(t.d, out->d, *plan, stream);
+    }
+    ++launches;
+    return out;
+}
+
+Tensor* Context::permute_adj(const Tensor& t, int shift, const std::vector<int>& pi)
+{
+    auto plan = permute_plan(t.layout, shift, pi, true);
+    auto* out = new Tensor(this, plan->out, false);
+    if(plan->identity_copy) {
+        check_cuda(cudaMemcpyAsync(out->d, t.d, sizeof(double) * t.size(), cudaMemcpyDeviceToDevice, stream), "permute_adj identity copy");
+    } else {
+        launch_permute(t.d, out->d, *plan, stream);
+    }
+    ++launches;
+    return out;
+}
+
+Tensor* Context::copy(const Tensor& t)
+{
+    auto* out = new Tensor(this, t.layout, false);
+    check_cuda(cudaMemcpyAsync(out->d, t.d, sizeof(double) * t.size(), cudaMemcpyDeviceToDevice, stream), "copy");
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------ operator*
+// TensorBase::operator* (src/Core/TensorBase.cpp:243-288). Operands may be lazy adjoints (AdjointOp.hpp:26-69):
+// the block is then read transposed, domain/codomain swap roles, the sector list stays the operand's.
+Tensor* Context::multiply(const Tensor& a, bool adj_a, const Tensor& b, bool adj_b)
+{
+    const Layout& LA = *a.layout;
+    const Layout& LB = *b.layout;
+    const auto& a_dom = adj_a ? LA.cod : LA.dom;
+    const auto& a_cod = adj_a ? LA.dom : LA.cod;
+    const auto& b_dom = adj_b ? LB.cod : LB.dom;
+    const auto& b_cod = adj_b ? LB.dom : LB.cod;
+    if(a_cod.size() != b_dom.size()) throw std::invalid_argument("operator*: CoRank of left operand != Rank of right operand");
+    for(size_t i = 0; i < a_cod.size(); ++i)   // DEBUG_ASSERT(coupledCodomain == coupledDomain), TensorBase.cpp:254
+        if(!a_cod[i]->same_sectors(*b_dom[i])) throw std::invalid_argument("operator*: coupledCodomain(left) != coupledDomain(right)");
+    LayoutPtr LO = layout(a_dom, b_cod);
+    auto* out = new Tensor(this, LO, true);   // Tout.setZero(); sectors missing in an operand stay zero blocks
+
+    std::vector<GemmItem> items;
+    for(size_t i = 0; i < LA.sector.size(); ++i) {
+        const int j = LB.find(LA.sector[i]);
+        if(j < 0) continue;
+        const int o = LO->find(LA.sector[i]);
+        if(o < 0) continue;
+        GemmItem g;
+        std::memset(&g, 0, sizeof(g));
+        g.a_off = LA.off[i];
+        g.b_off = LB.off[j];
+        g.c_off = LO->off[o];
+        g.lda = static_cast<int>(LA.rows[i]);
+        g.ldb = static_cast<int>(LB.rows[j]);
+        g.ldc = static_cast<int>(LO->rows[o]);
+        g.ta = adj_a;
+        g.tb = adj_b;
+        g.m = static_cast<int>(adj_a ? LA.cols[i] : LA.rows[i]);
+        g.k = static_cast<int>(adj_a ? LA.rows[i] : LA.cols[i]);
+        const int kb = static_cast<int>(adj_b ? LB.cols[j] : LB.rows[j]);
+        g.n = static_cast<int>(adj_b ? LB.rows[j] : LB.cols[j]);
+        if(kb != g.k || g.m != LO->rows[o] || g.n != LO->cols[o]) throw std::logic_error("operator*: block shape mismatch");
+        if(g.m == 0 || g.n == 0) continue;
+        for(int tn = 0; tn < g.n; tn += 64)
+            for(int tm = 0; tm < g.m; tm += 64) {
+                g.tm = tm;
+                g.tn = tn;
+                items.push_back(g);
+            }
+    }
+    if(!items.empty()) {
+        // heavy tiles first: k is the per-tile cost
+        std::stable_sort(items.begin(), items.end(), [](const GemmItem& x, const GemmItem& y) { return x.k > y.k; });
+        GemmItem* d_items = nullptr;
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_items), items.size() * sizeof(GemmItem), stream), "cudaMallocAsync gemm items");
+        upload_async(d_items, items.data(), items.size() * sizeof(GemmItem));
+        launch_gemm_grouped(a.d, b.d, out->d, d_items, static_cast<int>(items.size()), stream);
+        check_cuda(cudaFreeAsync(d_items, stream), "cudaFreeAsync gemm items");
+        ++launches;
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------ contract
+// Tensor::contract (include/Xped/Core/Tensor.hpp:328-351) with get_permutations (Util/Constfct.hpp:55-109).
+Tensor* Context::contract(const Tensor& a, const std::vector<int>& l1, const Tensor& b, const std::vector<int>& l2, int res_rank)
+{
+    const int r1 = static_cast<int>(l1.size()), r2 = static_cast<int>(l2.size());
+    if(r1 != a.layout->rank() + a.layout->corank() || r2 != b.layout->rank() + b.layout->corank())
+        throw std::invalid_argument("contract: label array length != number of legs");
+    const int max1 = std::max(0, r1 ? *std::max_element(l1.begin(), l1.end()) : 0);
+    const int max2 = std::max(0, r2 ? *std::max_element(l2.begin(), l2.end()) : 0);
+    if(max1 != max2) throw std::invalid_argument("contract: contracted labels do not match");
+    auto pos = [](const std::vector<int>& v, int label) {
+        auto it = std::find(v.begin(), v.end(), label);
+        if(it == v.end()) throw std::invalid_argument("contract: missing contraction label");
+        return static_cast<int>(it - v.begin());
+    };
+    std::vector<int> p1, p2, con1;
+    for(int k = 1; k <= max2; ++k) p2.push_back(pos(l2, k));
+    for(int i = 0; i < r2; ++i)
+        if(std::find(p2.begin(), p2.begin() + max2, i) == p2.begin() + max2) p2.push_back(i);
+    for(int k = 1; k <= max1; ++k) con1.push_back(pos(l1, k));
+    for(int i = 0; i < r1; ++i)
+        if(std::find(con1.begin(), con1.end(), i) == con1.end()) p1.push_back(i);
+    p1.insert(p1.end(), con1.begin(), con1.end());
+    std::vector<int> open;
+    for(int x : l1)
+        if(x < 0) open.push_back(x);
+    for(int x : l2)
+        if(x < 0) open.push_back(x);
+    std::vector<int> pres(open.size());
+    std::iota(pres.begin(), pres.end(), 0);
+    std::sort(pres.begin(), pres.end(), [&](int i, int j) { return open[i] > open[j]; });
+    const int shift1 = a.layout->rank() - r1 + max1;
+    const int shift2 = b.layout->rank() - max2;
+    const int shiftres = r1 - max1 - res_rank;
+
+    std::unique_ptr<Tensor> ap(permute(a, shift1, p1));
+    std::unique_ptr<Tensor> bp(permute(b, shift2, p2));
+    std::unique_ptr<Tensor> prod(multiply(*ap, false, *bp, false));
+    return permute(*prod, shiftres, pres);
+}
+
+// ------------------------------------------------------------------------------------------------ adjoint / twist / elementwise
+namespace {
+std::vector<BlockDesc> block_descs(const Layout& L, const Symmetry* weight_sym)
+{
+    std::vector<BlockDesc> v(L.sector.size());
+    for(size_t i = 0; i < L.sector.size(); ++i)
+        v[i] = {L.off[i], static_cast<int>(L.rows[i]), static_cast<int>(L.cols[i]), weight_sym ? static_cast<double>(weight_sym->degeneracy(L.sector[i])) : 1.0};
+    return v;
+}
+}   // namespace
+
+Tensor* Context::adjoint(const Tensor& t)
+{
+    // AdjointOp::eval(): domain <-> codomain, blocks pushed in the operand's sector order (Tensor.hpp:448-453)
+    const Layout& L = *t.layout;
+    LayoutPtr LO = layout_custom(L.cod, L.dom, L.sector);
+    auto* out = new Tensor(this, LO, false);
+    const int nb = static_cast<int>(L.sector.size());
+    if(nb == 0) return out;
+    auto descs = block_descs(L, nullptr);
+    std::vector<long long> doff(LO->off.begin(), LO->off.end());
+    const size_t b1 = descs.size() * sizeof(BlockDesc), b2 = doff.size() * sizeof(long long);
+    char* d_meta = nullptr;
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_meta), b1 + b2, stream), "cudaMallocAsync adjoint meta");
+    upload_async(d_meta, descs.data(), b1);
+    upload_async(d_meta + b1, doff.data(), b2);
+    launch_transpose_blocks(t.d, out->d, reinterpret_cast<BlockDesc*>(d_meta), reinterpret_cast<long long*>(d_meta + b1), nb, stream);
+    check_cuda(cudaFreeAsync(d_meta, stream), "cudaFreeAsync adjoint meta");
+    ++launches;
+    return out;
+}
+
+Tensor* Context::twist(const Tensor& t, int leg)
+{
+    // Tensor::twist (src/Core/Tensor.cpp:357-377): early-out copy for bosonic symmetries (:362).
+    if(!sym->fermionic()) return copy(t);
+    const Layout& L = *t.layout;
+    // Fermionic: scale every tree-pair sub-block by coeff_twist of the leg's sector label, on the device.
+    const int R = L.rank(), N = R + L.corank();
+    if(leg < 0 || leg >= N) throw std::invalid_argument("twist: leg out of range");
+    auto* out = copy(t);
+    std::vector<SubScale> subs;
+    for(size_t i = 0; i < L.sector.size(); ++i) {
+        const auto& dts = L.cdom->trees(L.sector[i]);
+        const auto& cts = L.ccod->trees(L.sector[i]);
+        int64_t ro = 0;
+        for(const Tree& dt : dts) {
+            int64_t co = 0;
+            for(const Tree& ct : cts) {
+                const double c = leg < R ? sym->coeff_twist(dt.unc[leg]) : sym->coeff_twist(ct.unc[leg - R]);
+                if(c != 1.0) subs.push_back({L.off[i] + ro + co * L.rows[i], static_cast<int>(dt.dim), static_cast<int>(ct.dim), static_cast<int>(L.rows[i]), c});
+                co += ct.dim;
+            }
+            ro += dt.dim;
+        }
+    }
+    if(!subs.empty()) {
+        SubScale* d_subs = nullptr;
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_subs), subs.size() * sizeof(SubScale), stream), "cudaMallocAsync twist");
+        upload_async(d_subs, subs.data(), subs.size() * sizeof(SubScale));
+        launch_scale_subblocks(out->d, d_subs, static_cast<int>(subs.size()), stream);
+        check_cuda(cudaFreeAsync(d_subs, stream), "cudaFreeAsync twist");
+        ++launches;
+    }
+    return out;
+}
+
+Tensor* Context::axpby(double alpha, const Tensor& x, double beta, const Tensor* y)
+{
+    auto* out = new Tensor(this, x.layout, false);
+    if(y == nullptr) {
+        launch_scale_copy(x.d, out->d, alpha, x.size(), stream);   // CoeffUnaryOp (CoeffUnaryOp.hpp:48-49)
+    } else {
+        // CoeffBinaryOp pairs the i-th blocks and requires identical sector lists (CoeffBinaryOp.hpp:44-64)
+        if(y->layout->sector != x.layout->sector || y->layout->size != x.layout->size) throw std::invalid_argument("axpby: operands have different block structure");
+        launch_axpby(x.d, y->d, out->d, alpha, beta, x.size(), stream);
+    }
+    ++launches;
+    return out;
+}
+
+Tensor* Context::diag_map(const Tensor& t, int op)
+{
+    const Layout& L = *t.layout;
+    auto* out = new Tensor(this, t.layout, false);
+    const int nb = static_cast<int>(L.sector.size());
+    if(nb == 0) return out;
+    auto descs = block_descs(L, nullptr);
+    BlockDesc* d_meta = nullptr;
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_meta), descs.size() * sizeof(BlockDesc), stream), "cudaMallocAsync diag meta");
+    upload_async(d_meta, descs.data(), descs.size() * sizeof(BlockDesc));
+    launch_diag_map(t.d, out->d, d_meta, nb, op, stream);
+    check_cuda(cudaFreeAsync(d_meta, stream), "cudaFreeAsync diag meta");
+    ++launches;
+    return out;
+}
+
+double Context::max_norm(const Tensor& t)
+{
+    double* d_out = static_cast<double*>(scratch(sizeof(double)));
+    launch_absmax(t.d, t.size(), d_out, stream);
+    ++launches;
+    double h = 0.0;
+    check_cuda(cudaMemcpyAsync(&h, d_out, sizeof(double), cudaMemcpyDeviceToHost, stream), "max_norm readback");
+    sync();
+    return h;
+}
+
+double Context::trace(const Tensor& t)
+{
+    const Layout& L = *t.layout;
+    auto descs = block_descs(L, sym.get());
+    const size_t bytes = descs.size() * sizeof(BlockDesc);
+    char* d_meta = static_cast<char*>(scratch(bytes + 64));
+    upload_async(d_meta + 64, descs.data(), bytes);
+    launch_trace(t.d, reinterpret_cast<BlockDesc*>(d_meta + 64), static_cast<int>(descs.size()), reinterpret_cast<double*>(d_meta), stream);
+    ++launches;
+    double h = 0.0;
+    check_cuda(cudaMemcpyAsync(&h, d_meta, sizeof(double), cudaMemcpyDeviceToHost, stream), "trace readback");
+    sync();
+    return h;
+}
+
+double Context::squared_norm(const Tensor& t)
+{
+    // squaredNorm = (T * T^dagger).trace() (src/Core/TensorBase.cpp:58-64)
+    std::unique_ptr<Tensor> p(multiply(t, false, t, true));
+    return trace(*p);
+}
+
+}   // namespace xb
+
+namespace xb {
+
+Tensor* Context::scale_by_inv_maxnorm(const Tensor& t)
+{
+    auto* out = new Tensor(this, t.layout, false);
+    double* d_scalar = nullptr;
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_scalar), sizeof(double), stream), "cudaMallocAsync maxnorm scalar");
+    launch_absmax(t.d, t.size(), d_scalar, stream);
+    launch_scale_by_inv(t.d, out->d, d_scalar, t.size(), stream);
+    check_cuda(cudaFreeAsync(d_scalar, stream), "cudaFreeAsync maxnorm scalar");
+    launches += 2;
+    return out;
+}
+
+void Context::fill(Tensor& t, int mode, double value, uint64_t seed)
+{
+    const Layout& L = *t.layout;
+    if(mode == 0) {
+        launch_fill_constant(t.d, value, L.size, stream);
+    } else if(mode == 2) {
+        launch_fill_random(t.d, seed, L.size, stream);
+    } else {
+        check_cuda(cudaMemsetAsync(t.d, 0, sizeof(double) * static_cast<size_t>(L.size), stream), "fill identity memset");
+        std::vector<BlockDesc> descs(L.sector.size());
+        for(size_t i = 0; i < L.sector.size(); ++i) descs[i] = {L.off[i], static_cast<int>(L.rows[i]), static_cast<int>(L.cols[i]), 1.0};
+        if(!descs.empty()) {
+            BlockDesc* d_meta = nullptr;
+            check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_meta), descs.size() * sizeof(BlockDesc), stream), "cudaMallocAsync identity meta");
+            upload_async(d_meta, descs.data(), descs.size() * sizeof(BlockDesc));
+            launch_set_identity(t.d, d_meta, static_cast<int>(descs.size()), stream);
+            check_cuda(cudaFreeAsync(d_meta, stream), "cudaFreeAsync identity meta");
+        }
+    }
+    ++launches;
+}
+
+}   // namespace xb

@@ -1,0 +1,332 @@
+"""Host-side mirror of the reference interface above the C ABI (Python flavour, used by tests and bench).
+
+Names and argument meaning follow Xped: `Qbasis.push_back/conj/combine`, `Tensor.permute(shift, p)`,
+`A * B` / `A @ B` (TensorBase::operator*), `contract(a1, other, a2, res_rank)`, `adjoint()`, `tSVD(maxKeep, eps,
+PRESERVE_MULTIPLETS)`, `twist(leg)`, `maxNorm()`, `trace()`, `squaredNorm()` (include/Xped/Core/Tensor.hpp:59-444,
+TensorBase.hpp:34-148).  Everything numeric happens in libxped_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import check
+
+KINDS = {"U0": 0, "U1": 1, "ZN": 2, "SU2": 3}
+
+
+def _ints(seq):
+    arr = (C.c_int * max(len(seq), 1))(*[int(x) for x in seq])
+    return arr
+
+
+class Context:
+    """One per GPU; carries the symmetry (spec: list of (kind, N, fermionic), e.g. [("SU2", 0, 0)])."""
+
+    def __init__(self, spec, device=0):
+        self.lib = capi.load()
+        self.spec = [(k, int(n), int(f)) for k, n, f in spec]
+        facs = (capi.SymFactor * max(len(self.spec), 1))()
+        for i, (k, n, f) in enumerate(self.spec):
+            facs[i].kind, facs[i].N, facs[i].fermionic = KINDS[k], n, f
+        h = C.c_void_p()
+        check(self.lib.xb_ctx_create(C.byref(h), device, facs, len(self.spec)))
+        self.h = h
+        self.Nq = self.lib.xb_ctx_nq(h)
+
+    def sync(self):
+        check(self.lib.xb_ctx_sync(self.h))
+
+    def stats(self):
+        out = (C.c_int64 * 3)()
+        check(self.lib.xb_ctx_stats(self.h, out))
+        return {"launches": out[0], "plan_hits": out[1], "plan_misses": out[2]}
+
+    def flush_l2(self):
+        check(self.lib.xb_flush_l2(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.xb_ctx_free(self.h)
+            self.h = None
+
+    # -- factories
+    def basis(self, entries):
+        """entries: [(q, dim)], q an int (Nq == 1) or a tuple of Nq ints; push_back order is kept."""
+        return Qbasis.from_entries(self, entries)
+
+    def tensor(self, domain, codomain):
+        return Tensor.zeros(self, domain, codomain)
+
+
+class Qbasis:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.xb_basis_free(self.h)
+        except Exception:
+            pass
+
+    @staticmethod
+    def from_entries(ctx, entries):
+        qs, dims = [], []
+        for q, d in entries:
+            q = (q,) if isinstance(q, (int, np.integer)) else tuple(q)
+            assert len(q) == ctx.Nq
+            qs += list(q)
+            dims.append(int(d))
+        h = C.c_void_p()
+        check(ctx.lib.xb_basis_create(ctx.h, _ints(qs), (C.c_int64 * max(len(dims), 1))(*dims), len(dims), C.byref(h)))
+        return Qbasis(ctx, h)
+
+    def _unary(self, fn):
+        h = C.c_void_p()
+        check(fn(self.h, C.byref(h)))
+        return Qbasis(self.ctx, h)
+
+    def conj(self): return self._unary(self.ctx.lib.xb_basis_conj)
+    def sorted(self): return self._unary(self.ctx.lib.xb_basis_sorted)
+
+    def combine(self, other):
+        """combine(other).forgetHistory()"""
+        h = C.c_void_p()
+        check(self.ctx.lib.xb_basis_combine(self.h, other.h, C.byref(h)))
+        return Qbasis(self.ctx, h)
+
+    def info(self):
+        n, d, fd, cj = C.c_int(), C.c_int64(), C.c_int64(), C.c_int()
+        check(self.ctx.lib.xb_basis_size(self.h, C.byref(n), C.byref(d), C.byref(fd), C.byref(cj)))
+        return n.value, d.value, fd.value, bool(cj.value)
+
+    def entries(self):
+        n = self.info()[0]
+        q = (C.c_int * max(n * self.ctx.Nq, 1))()
+        d = (C.c_int64 * max(n, 1))()
+        check(self.ctx.lib.xb_basis_get(self.h, q, d))
+        nq = self.ctx.Nq
+        return [(tuple(q[i * nq + k] for k in range(nq)), d[i]) for i in range(n)]
+
+    def dim(self): return self.info()[1]
+    def fullDim(self): return self.info()[2]
+    def IS_CONJ(self): return self.info()[3]
+
+
+class Tensor:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.xb_tensor_free(self.h)
+        except Exception:
+            pass
+
+    # -- construction / storage
+    @staticmethod
+    def zeros(ctx, domain, codomain):
+        d = (C.c_void_p * max(len(domain), 1))(*[b.h for b in domain])
+        c = (C.c_void_p * max(len(codomain), 1))(*[b.h for b in codomain])
+        h = C.c_void_p()
+        check(ctx.lib.xb_tensor_create(ctx.h, d, len(domain), c, len(codomain), C.byref(h)))
+        return Tensor(ctx, h)
+
+    def _out(self, fn, *args):
+        h = C.c_void_p()
+        check(fn(*args, C.byref(h)))
+        return Tensor(self.ctx, h)
+
+    @property
+    def rank(self):
+        r, c = C.c_int(), C.c_int()
+        check(self.ctx.lib.xb_tensor_rank(self.h, C.byref(r), C.byref(c)))
+        return r.value
+
+    @property
+    def corank(self):
+        r, c = C.c_int(), C.c_int()
+        check(self.ctx.lib.xb_tensor_rank(self.h, C.byref(r), C.byref(c)))
+        return c.value
+
+    def leg_basis(self, leg):
+        h = C.c_void_p()
+        check(self.ctx.lib.xb_tensor_leg_basis(self.h, leg, C.byref(h)))
+        return Qbasis(self.ctx, h)
+
+    def uncoupledDomain(self): return [self.leg_basis(i) for i in range(self.rank)]
+    def uncoupledCodomain(self): return [self.leg_basis(self.rank + i) for i in range(self.corank)]
+    def plainSize(self): return self.ctx.lib.xb_tensor_plain_size(self.h)
+
+    def structure(self):
+        """([sector q], rows, cols, offsets) -- compared bit-exactly against the oracle."""
+        n = self.ctx.lib.xb_tensor_num_sectors(self.h)
+        nq = self.ctx.Nq
+        q = (C.c_int * max(n * nq, 1))()
+        r, c, o = ((C.c_int64 * max(n, 1))() for _ in range(3))
+        check(self.ctx.lib.xb_tensor_structure(self.h, q, r, c, o))
+        return ([tuple(q[i * nq + k] for k in range(nq)) for i in range(n)], list(r[:n]), list(c[:n]), list(o[:n]))
+
+    def tree_pairs(self):
+        n = self.ctx.lib.xb_tensor_num_tree_pairs(self.h)
+        buf = (C.c_int64 * max(5 * n, 1))()
+        check(self.ctx.lib.xb_tensor_tree_pairs(self.h, buf))
+        return np.frombuffer(buf, dtype=np.int64, count=5 * n).reshape(n, 5).copy()
+
+    def upload(self, data):
+        a = np.ascontiguousarray(data, dtype=np.float64)
+        check(self.ctx.lib.xb_tensor_upload(self.h, a.ctypes.data_as(capi.DP), a.size))
+        return self
+
+    def download(self):
+        out = np.empty(self.plainSize(), dtype=np.float64)
+        check(self.ctx.lib.xb_tensor_download(self.h, out.ctypes.data_as(capi.DP), out.size))
+        return out
+
+    def setZero(self):
+        check(self.ctx.lib.xb_tensor_set_zero(self.h)); return self
+
+    def setIdentity(self):
+        check(self.ctx.lib.xb_tensor_set_identity(self.h)); return self
+
+    def setConstant(self, v):
+        check(self.ctx.lib.xb_tensor_set_constant(self.h, float(v))); return self
+
+    def setRandom(self, seed):
+        check(self.ctx.lib.xb_tensor_set_random(self.h, int(seed))); return self
+
+    def clone(self): return self._out(self.ctx.lib.xb_tensor_clone, self.h)
+
+    # -- hot path
+    def permute(self, shift, p):
+        return self._out(self.ctx.lib.xb_permute, self.ctx.h, self.h, int(shift), _ints(p), len(p))
+
+    def permute_adj(self, shift, p):
+        return self._out(self.ctx.lib.xb_permute_adj, self.ctx.h, self.h, int(shift), _ints(p), len(p))
+
+    def multiply(self, other, adj_self=False, adj_other=False):
+        return self._out(self.ctx.lib.xb_multiply, self.ctx.h, self.h, int(adj_self), other.h, int(adj_other))
+
+    def __matmul__(self, other): return self.multiply(other)
+
+    def __mul__(self, other):
+        if isinstance(other, Tensor):
+            return self.multiply(other)
+        return self.scale(other)
+
+    __rmul__ = __mul__
+
+    def contract(self, a1, other, a2, res_rank):
+        return self._out(self.ctx.lib.xb_contract, self.ctx.h, self.h, _ints(a1), len(a1), other.h, _ints(a2), len(a2), int(res_rank))
+
+    def adjoint(self): return self._out(self.ctx.lib.xb_adjoint, self.ctx.h, self.h)
+    def twist(self, leg): return self._out(self.ctx.lib.xb_twist, self.ctx.h, self.h, int(leg))
+    def scale(self, s): return self._out(self.ctx.lib.xb_axpby, self.ctx.h, float(s), self.h, 0.0, None)
+    def axpby(self, alpha, beta, y): return self._out(self.ctx.lib.xb_axpby, self.ctx.h, float(alpha), self.h, float(beta), y.h)
+    def __add__(self, other): return self.axpby(1.0, 1.0, other)
+    def __sub__(self, other): return self.axpby(1.0, -1.0, other)
+    def diag_sqrt(self): return self._out(self.ctx.lib.xb_diag_map, self.ctx.h, self.h, 0)
+    def diag_inv(self): return self._out(self.ctx.lib.xb_diag_map, self.ctx.h, self.h, 1)
+
+    def _scalar(self, fn):
+        v = C.c_double()
+        check(fn(self.ctx.h, self.h, C.byref(v)))
+        return v.value
+
+    def maxNorm(self): return self._scalar(self.ctx.lib.xb_max_norm)
+    def trace(self): return self._scalar(self.ctx.lib.xb_trace)
+    def squaredNorm(self): return self._scalar(self.ctx.lib.xb_squared_norm)
+    def norm(self): return float(np.sqrt(self.squaredNorm()))
+
+    def tSVD(self, maxKeep, eps_svd, PRESERVE_MULTIPLETS=True, return_info=False):
+        u, s, v = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        tw, ent = C.c_double(0.0), C.c_double(0.0)
+        check(self.ctx.lib.xb_tsvd(self.ctx.h, self.h, int(maxKeep), float(eps_svd), int(PRESERVE_MULTIPLETS), C.byref(u), C.byref(s), C.byref(v),
+                                   C.byref(tw), C.byref(ent)))
+        out = (Tensor(self.ctx, u), Tensor(self.ctx, s), Tensor(self.ctx, v))
+        if return_info:
+            return out + (dict(truncWeight=tw.value, entropy=ent.value),)
+        return out
+
+    def tSVD_backward(self, U, S, Vdag, dU=None, dS=None, dVdag=None):
+        return self._out(self.ctx.lib.xb_tsvd_backward, self.ctx.h, self.h, U.h, S.h, Vdag.h, dU.h if dU else None, dS.h if dS else None,
+                         dVdag.h if dVdag else None)
+
+    def _pair(self, fn, *args):
+        a, b = C.c_void_p(), C.c_void_p()
+        check(fn(*args, C.byref(a), C.byref(b)))
+        return Tensor(self.ctx, a), Tensor(self.ctx, b)
+
+    def tQR(self): return self._pair(self.ctx.lib.xb_tqr, self.ctx.h, self.h)
+    def teigh(self): return self._pair(self.ctx.lib.xb_teigh, self.ctx.h, self.h)
+
+    # -- measurement hooks
+    def bench_permute(self, shift, p, reps=10):
+        ms, nbytes = C.c_double(), C.c_int64()
+        check(self.ctx.lib.xb_bench_permute(self.ctx.h, self.h, int(shift), _ints(p), len(p), int(reps), C.byref(ms), C.byref(nbytes)))
+        return ms.value, nbytes.value
+
+    def bench_multiply(self, other, reps=5):
+        ms, fl = C.c_double(), C.c_double()
+        check(self.ctx.lib.xb_bench_multiply(self.ctx.h, self.h, other.h, int(reps), C.byref(ms), C.byref(fl)))
+        return ms.value, fl.value
+
+
+def decompose(T1, T2, chi):
+    """PEPSContractions.cpp:18-43"""
+    ctx = T1.ctx
+    a, b = C.c_void_p(), C.c_void_p()
+    check(ctx.lib.xb_decompose(ctx.h, T1.h, T2.h, int(chi), C.byref(a), C.byref(b)))
+    return Tensor(ctx, a), Tensor(ctx, b)
+
+
+def contract_L(Bold, Bra, Ket):
+    ctx = Bold.ctx
+    h = C.c_void_p()
+    check(ctx.lib.xb_contract_L(ctx.h, Bold.h, Bra.h, Ket.h, C.byref(h)))
+    return Tensor(ctx, h)
+
+
+def contract_R(Bold, Bra, Ket):
+    ctx = Bold.ctx
+    h = C.c_void_p()
+    check(ctx.lib.xb_contract_R(ctx.h, Bold.h, Bra.h, Ket.h, C.byref(h)))
+    return Tensor(ctx, h)
+
+
+class CTM:
+    """CTM<double,Symmetry,2> on a 1x1 unit cell (include/Xped/PEPS/CTM.hpp:60-312)."""
+    NAMES = ["C1", "C2", "C3", "C4", "T1", "T2", "T3", "T4", "A", "Adag"]
+
+    def __init__(self, A: Tensor, chi: int):
+        self.ctx = A.ctx
+        h = C.c_void_p()
+        check(self.ctx.lib.xb_ctm_create(self.ctx.h, A.h, int(chi), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.xb_ctm_free(self.h)
+        except Exception:
+            pass
+
+    def grow_all(self): check(self.ctx.lib.xb_ctm_step(self.h))
+    def move(self, direction): check(self.ctx.lib.xb_ctm_move(self.h, int(direction)))
+
+    def get(self, name):
+        h = C.c_void_p()
+        check(self.ctx.lib.xb_ctm_get(self.h, self.NAMES.index(name), C.byref(h)))
+        return Tensor(self.ctx, h)
+
+    def set(self, name, t):
+        check(self.ctx.lib.xb_ctm_set(self.h, self.NAMES.index(name), t.h))
+
+    def contractCorner(self, corner):
+        h = C.c_void_p()
+        check(self.ctx.lib.xb_ctm_corner(self.h, int(corner), C.byref(h)))
+        return Tensor(self.ctx, h)

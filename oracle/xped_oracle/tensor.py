@@ -353,6 +353,14 @@ class Tensor:
         assert allSV
         first_entry = allSV[0]
         allSV.sort(key=lambda e: (-e[1], e[2], e[3]))
+        i = 0   # numerically tied values (<= 1e-12 relative) are ordered by (sector index, k), see DESIGN.md
+        while i < len(allSV):
+            j = i + 1
+            while j < len(allSV) and allSV[j - 1][1] - allSV[j][1] <= 1.0e-12 * allSV[i][1]:
+                j += 1
+            if j - i > 1:
+                allSV[i:j] = sorted(allSV[i:j], key=lambda e: (e[2], e[3]))
+            i = j
         for e in allSV[maxKeep:]:
             truncWeight += sym.degeneracy(e[0]) * abs(e[1]) ** 2
         allSV = allSV[:min(maxKeep, len(allSV))]

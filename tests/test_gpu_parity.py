@@ -93,17 +93,23 @@ def test_multiply_adjoint_contract(ctxs, name):
     assert_same(ga.adjoint(), oa.adjoint(), TOL, "adjoint")
     assert_same(ga.multiply(ga, False, True), oa @ oa.adjoint(), TOL, "A * A^dagger (lazy adjoint operand)")
     assert_same(gb.multiply(ga, True, True), ob.adjoint() @ oa.adjoint(), TOL, "B^dagger * A^dagger")
-    assert_same(ga.contract([-1, 1, 2, -2], gb, [2, -3, -4, 1], 1), oa.contract([-1, 1, 2, -2], ob, [2, -3, -4, 1], 1), TOL, "contract<2 legs>")
-    assert_same(ga.contract([1, -2, -1, 2], gb, [-3, 2, 1, -4], 3), oa.contract([1, -2, -1, 2], ob, [-3, 2, 1, -4], 3), TOL, "contract<crossed>")
+    assert_same(ga.contract([-1, -2, 2, 1], gb, [2, 1, -3, -4], 1), oa.contract([-1, -2, 2, 1], ob, [2, 1, -3, -4], 1), TOL, "contract<2 legs>")
+    assert_same(ga.contract([1, -1, 2, -2], gb, [2, -3, -4, 1], 1), oa.contract([1, -1, 2, -2], ob, [2, -3, -4, 1], 1), TOL, "contract<crossed>")
+    assert_same(ga.contract([-3, -1, -4, 1], gb, [-2, 1, -5, -6], 4), oa.contract([-3, -1, -4, 1], ob, [-2, 1, -5, -6], 4), TOL, "contract<1 leg>")
     assert_same(ga.scale(-0.37), oa.scale(-0.37), TOL, "scale")
     g2, o2 = pair(ctx, osym, [B, C], [C, D], 5)
     assert_same(ga + g2, oa + o2, TOL, "operator+")
     assert_same(ga - g2, oa - o2, TOL, "operator-")
     assert abs(ga.maxNorm() - oa.maxNorm()) == 0.0
     gsq, osq = ga.multiply(ga, False, True), oa @ oa.adjoint()
-    assert abs(gsq.trace() - osq.trace()) < 1e-12 * abs(osq.trace())
-    assert abs(ga.squaredNorm() - oa.squaredNorm()) < 1e-12 * oa.squaredNorm()
-    assert_same(gsq.diag_sqrt().diag_inv(), osq.diag_sqrt().diag_inv(), TOL, "diag_sqrt().diag_inv()")
+    assert abs(gsq.trace() - osq.trace()) <= 1e-12 * abs(osq.trace())
+    assert abs(ga.squaredNorm() - oa.squaredNorm()) <= 1e-12 * oa.squaredNorm()
+    gd, od = gsq.diag_sqrt().diag_inv(), osq.diag_sqrt().diag_inv()      # zero blocks give inf on both sides
+    assert gd.structure() == od.structure()
+    a, b = gd.download(), od.data
+    assert np.array_equal(np.isfinite(a), np.isfinite(b))
+    fin = np.isfinite(b)
+    assert np.linalg.norm(a[fin] - b[fin]) <= TOL * max(np.linalg.norm(b[fin]), 1e-300)
 
 
 def test_error_codes(ctxs):
@@ -149,7 +155,8 @@ def test_tsvd(ctxs, name):
     g, o = pair(ctx, osym, [B, C], [B, C], 21)          # square blocks
     _svd_checks(g, o, 1000, 1e-10, False)                # no truncation
     _svd_checks(g, o, 7, 1e-10, False)                   # CTM-style truncation
-    g2, o2 = pair(ctx, osym, [B, C], [B], 22)           # tall / wide blocks (MPS-like A(2,1))
+    out = [(q, d) for q, _, d in obasis(osym, B).combine(obasis(osym, C)).forgetHistory().data][::2]
+    g2, o2 = pair(ctx, osym, [B, C], [out], 22)         # tall / wide blocks (MPS-like A(2,1), cf. tests/mps_tests.hpp:13-16)
     _svd_checks(g2, o2, 1000, 0.0, False)
     _svd_checks(g2.adjoint(), o2.adjoint(), 5, 1e-10, False)
 
@@ -164,7 +171,7 @@ def test_tsvd_graded_spectrum_and_multiplets(ctxs):
         n = o.block(i).shape[0]
         q1, _ = np.linalg.qr(rng.standard_normal((n, n)))
         q2, _ = np.linalg.qr(rng.standard_normal((n, n)))
-        o.block(i)[...] = q1 @ np.diag(10.0 ** (-np.arange(n) * (3.0 + i))) @ q2.T
+        o.block(i)[...] = q1 @ np.diag(10.0 ** (-np.arange(n) * (2.9 + i))) @ q2.T
     g.upload(o.data)
     for keep, eps, pm in [(100, 1e-10, False), (9, 1e-10, False), (9, 1e-10, True), (4, 0.0, True)]:
         gU, gS, gV = g.tSVD(keep, eps, pm)
@@ -196,25 +203,55 @@ def _ctm_pair(ctx, osym, spec, D, chi, seed):
     return xb.CTM(gA, chi), OCTM(oA, chi)
 
 
-@pytest.mark.parametrize("name,D,chi", [("SU2", 3, 10), ("U1", 2, 8)])
+def _spectrum(t):
+    """per-sector singular values of an environment tensor: invariant under the orthogonal gauge freedom on the chi legs"""
+    if t.rank == 0:
+        t = t.permute(-1, list(range(t.corank)))
+    elif t.corank == 0:
+        t = t.permute(1, list(range(t.rank)))
+    S = t.tSVD(10 ** 6, 0.0, False)[1]
+    return S.structure(), (S.download() if hasattr(S, "download") else S.data)
+
+
+@pytest.mark.parametrize("name,D,chi", [("SU2", 3, 10), ("U1", 2, 8), ("U1", 3, 9)])
 def test_ctm_init_corner_and_step(ctxs, name, D, chi):
-    """CTM.cpp init (FROM_A) and contractCorner are sign-gauge free -> strict parity; a full grow_all() is compared
-    up to the per-index sign gauge of the SVD (absolute values) and through the corner spectra."""
+    """CTM.cpp init (FROM_A) and contractCorner involve no SVD -> strict parity. After grow_all() the environment is
+    defined up to an orthogonal gauge on the chi legs (sign flips, rotations inside degenerate singular subspaces --
+    the bra/ket double layer has such degeneracies), so steps are compared through gauge-invariant per-sector spectra."""
     ctx, osym = ctxs(name)
     g, o = _ctm_pair(ctx, osym, SPECS[name], D, chi, 51)
     for nm, ot in o.tensors().items():
         assert_same(g.get(nm), ot, TOL, f"init {nm}")
     for corner in range(4):
         assert_same(g.contractCorner(corner), o.contractCorner(corner), TOL, f"contractCorner {corner}")
-    for step in range(2):
+    for step in range(3):
         g.grow_all()
         o.grow_all()
         for nm, ot in o.tensors().items():
             gt = g.get(nm)
             assert gt.structure() == ot.structure(), f"step {step} {nm}"
+            (gs_struct, gs), (os_struct, os_) = _spectrum(gt), _spectrum(ot)
+            assert gs_struct == os_struct
+            assert np.abs(gs - os_).max() < 1e-9 * np.abs(os_).max(), f"step {step} {nm}: spectrum differs by {np.abs(gs - os_).max():.2e}"
+
+
+@pytest.mark.parametrize("name,D,chi", [("SU2", 3, 9), ("U1", 3, 8)])
+def test_ctm_single_moves_generic_environment(ctxs, name, D, chi):
+    """With a generic (random) environment the projector SVD has no degeneracies, so each directional move must agree
+    with the oracle element-wise up to the sign of each new chi index: compare |values| (CTM.cpp:924-1641)."""
+    ctx, osym = ctxs(name)
+    g, o = _ctm_pair(ctx, osym, SPECS[name], D, chi, 61)
+    from xped_oracle.rng import uniform_fill
+    for direction in range(4):
+        for k, nm in enumerate(["C1", "C2", "C3", "C4", "T1", "T2", "T3", "T4"]):
+            seed = 100 + 10 * direction + k
+            g.set(nm, g.get(nm).setRandom(seed))
+            ot = getattr(o, nm)
+            ot.data = uniform_fill(seed, ot.plainSize())
+        g.move(direction)
+        o.move(direction)
+        for nm, ot in o.tensors().items():
+            gt = g.get(nm)
+            assert gt.structure() == ot.structure(), f"move {direction} {nm}"
             a, b = np.abs(gt.download()), np.abs(ot.data)
-            assert np.abs(a - b).max() < 1e-8 * b.max(), f"step {step} {nm}: {np.abs(a - b).max():.2e}"
-    gc, oc = g.get("C2"), o.C2
-    gs = gc.tSVD(1000, 0.0, False)[1].download()
-    os_ = oc.tSVD(1000, 0.0, False)[1].data
-    assert np.abs(gs - os_).max() < 1e-9
+            assert np.abs(a - b).max() < 1e-10 * b.max(), f"move {direction} {nm}: {np.abs(a - b).max():.2e}"

@@ -468,9 +468,11 @@ std::shared_ptr<Qbasis> Qbasis::combine(const Qbasis& other) const
 
 bool Qbasis::same_sectors(const Qbasis& o) const
 {
+    // Order-insensitive: the reference compares the *coupled* bases, which combine() has sorted, so two legs
+    // that carry the same (q, dim) set in a different push_back order (e.g. X vs X.conj().conj()) are compatible.
     if(data_.size() != o.data_.size()) return false;
-    for(size_t i = 0; i < data_.size(); ++i)
-        if(!(data_[i].q == o.data_[i].q) || data_[i].dim != o.data_[i].dim) return false;
+    for(const auto& e : data_)
+        if(o.inner_dim(e.q) != e.dim) return false;
     return true;
 }
 

@@ -410,7 +410,7 @@ SvdResult Context::tsvd(const Tensor& t, int64_t max_keep, double eps_svd, bool 
     const Layout& L = *t.layout;
     if(L.sector.empty()) throw std::invalid_argument("tSVD: tensor has no blocks");
     JacobiResult J = jacobi_all(*this, t, nullptr);
-    struct SV { int sector; int col; double s; };
+    struct SV { int sector; int col; int k; double s; };
     std::vector<SV> all;
     for(size_t i = 0; i < L.sector.size(); ++i) {
         const SvdBlock& b = J.blocks[i];
@@ -418,12 +418,22 @@ SvdResult Context::tsvd(const Tensor& t, int64_t max_keep, double eps_svd, bool 
         std::vector<int> idx(b.cols);
         std::iota(idx.begin(), idx.end(), 0);
         std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return J.sigma[b.s_off + x] > J.sigma[b.s_off + y]; });
-        for(int c : idx) all.push_back({static_cast<int>(i), c, J.sigma[b.s_off + c]});
+        int k = 0;
+        for(int c : idx) all.push_back({static_cast<int>(i), c, k++, J.sigma[b.s_off + c]});
     }
     if(all.empty()) throw std::invalid_argument("tSVD: tensor has no singular values");
     const SV first_entry = all[0];
     // Tensor.cpp:543-547; the reference's std::sort is unstable for ties -- here ties keep (sector, k) order.
     std::stable_sort(all.begin(), all.end(), [](const SV& a, const SV& b) { return a.s > b.s; });
+    // Numerically tied values (|diff| <= 1e-12 relative; e.g. the q <-> -q partner sectors of a U(1) double layer) are
+    // ordered by (sector index, k) so that the truncation decision does not depend on rounding noise.
+    for(size_t i = 0; i < all.size();) {
+        size_t j = i + 1;
+        while(j < all.size() && all[j - 1].s - all[j].s <= 1.e-12 * all[i].s) ++j;
+        if(j - i > 1)
+            std::stable_sort(all.begin() + i, all.begin() + j, [](const SV& a, const SV& b) { return a.sector != b.sector ? a.sector < b.sector : a.k < b.k; });
+        i = j;
+    }
     SvdResult res;
     for(size_t i = static_cast<size_t>(std::max<int64_t>(max_keep, 0)); i < all.size(); ++i)   // :548
         res.trunc_weight += sym->degeneracy(L.sector[all[i].sector]) * all[i].s * all[i].s;

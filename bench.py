@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the xped_b200 hot path (contract: task statement, section 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--no-extras]
+
+Headline metric (BASELINE.json `metric`, configs[1]): CTMRG steps/s of the SU(2) iPEPS environment at D=4, chi=64,
+1x1 unit cell, CTM_INIT::FROM_A, one "step" = CTM::grow_all() = left, right, top, bottom move
+(src/PEPS/CTM.cpp:385-420), RDM/energy evaluation excluded.  The other two parts of the metric -- permute HBM GB/s and
+contract FP64 TFLOP/s -- are measured in the same run on the W4 / W3 tensors of BASELINE.md section 4 and reported under
+"kernels"; the `roofline` object is that of the permute kernel (HBM-bound), `roofline_contract` that of the grouped DGEMM.
+
+  value  : steps/s with the environment resident in HBM, CUDA events on the context stream, L2 flushed between steps.
+  e2e    : the same step through the C ABI with HOST buffers: every step uploads C1..C4, T1..T4 and A from pinned host
+           memory (xb_tensor_upload), calls xb_ctm_step and downloads the new environment (xb_tensor_download).
+  --impl reference : the CPU oracle (oracle/xped_oracle, a numpy restatement of the reference's algorithm; the reference
+           itself cannot be built here) on the host cores, same config / metric / unit.
+N > 1: sectors of one D=4 CTM are too small to shard (9 sectors, < 6 MB): every rank advances its own independent
+environment (different seed) -- "replicas", weak scaling, no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D_AUX, CHI = 4, 64
+ENV = ["C1", "C2", "C3", "C4", "T1", "T2", "T3", "T4"]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the W3/W4 kernel sections (headline only)")
+    ap.add_argument("--cpu-steps", type=int, default=3, help="oracle steps timed for cpu_baseline")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ----------------------------------------------------------------------------------------------- oracle (CPU) arm
+def oracle_ctm(seed):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import xped_oracle as xo
+    from xped_oracle.ctm import CTM, init_basis
+    from xped_oracle.rng import uniform_fill
+    sym = xo.Symmetry.SU2()
+    phys = xo.Qbasis.from_list(sym, [((2,), 1)])
+    aux = init_basis(sym, D_AUX, phys)
+    A = xo.Tensor(sym, [aux, aux], [aux, aux, phys])
+    A.data = uniform_fill(seed, A.plainSize())
+    return CTM(A, CHI)
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def time_oracle(warmup, steps):
+    import numpy as np  # noqa: F401  (loads the BLAS the oracle's GEMM / SVD calls use)
+    ctm = oracle_ctm(0)
+    for _ in range(warmup):
+        ctm.grow_all()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ctm.grow_all()
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps * 1e3
+
+
+def config_dict(n_gpus, extra=None):
+    cfg = {"workload": "configs[1]: SU(2) iPEPS CTMRG, D=4 (aux {q=1:2,q=2:2}), chi=64, 1x1 cell, FROM_A init, step = grow_all() (4 moves)",
+           "symmetry": "SU2", "D": D_AUX, "chi": CHI, "unit_cell": "1x1",
+           "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} replicas (one independent environment per GPU, no data-path collective)",
+           "l2": "flushed between timed steps (256 MiB memset outside the event pairs)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sps, ms = time_oracle(args.warmup, args.steps)
+    cores = blas_threads()
+    line = {"impl": "reference", "metric": "ctmrg_steps_per_s", "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (counter-based uniform[-1,1] site tensor, seed 0)", "config": config_dict(1),
+            "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} grow_all() steps after {args.warmup} warm-up steps, oracle/xped_oracle (numpy restatement; "
+                                       "python loops over tree pairs on 1 core, per-block GEMM/SVD in OpenBLAS/LAPACK threads)"},
+            "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def u1_basis(ctx, qmax, dim):
+    return ctx.basis([(q, dim) for q in range(-qmax, qmax + 1)])
+
+
+def su2_corner_pair(ctx, aux, env, seeds):
+    """two random corner-shaped tensors Q(3,3) on (env, aux, aux | env, aux, aux)"""
+    a, e = ctx.basis(aux), ctx.basis(env)
+    return [ctx.tensor([e, a, a], [e, a, a]).setRandom(s) for s in seeds]
+
+
+def kernel_sections(xb, device, torch):
+    """permute HBM GB/s and contract FP64 TFLOP/s on the large tensors (W4, W3)"""
+    out = {}
+    # ---- FP64 tensor peak: cuBLAS DGEMM 8192^3 measured here (MEASURED_PEAKS.json has no FP64 entry)
+    n = 8192
+    a = torch.rand(n, n, dtype=torch.float64, device="cuda")
+    b = torch.rand(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    dgemm_peak = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    out["fp64_peak_tflops_cublas_dgemm_8192"] = dgemm_peak
+
+    # ---- W4: U(1) Tensor<2,2>, legs q in -4..4, 24 states per charge
+    ctx = xb.Context([("U1", 0, 0)], device=device)
+    B = u1_basis(ctx, 4, 24)
+    T = ctx.tensor([B, B], [B, B]).setRandom(0)
+    nelem = T.plainSize()
+    perms = [(1, 0, 2, 3), (0, 1, 3, 2), (2, 3, 0, 1), (0, 2, 1, 3), (3, 2, 1, 0)]
+    rows = []
+    for p in perms:
+        for shift in (0, 1, -1, 2, -2):
+            T.bench_permute(shift, p, reps=2)            # plan build + warm-up
+            ctx.flush_l2()
+            ms, nbytes = T.bench_permute(shift, p, reps=5)  # 2.6 GB per launch >> L2
+            rows.append({"p": list(p), "shift": shift, "ms": ms, "GBps": nbytes / ms / 1e6})
+    gbs = sorted(r["GBps"] for r in rows)
+    tot_bytes = sum(2 * 8 * nelem for _ in rows)
+    tot_ms = sum(r["ms"] for r in rows)
+    out["permute_w4"] = {"tensor": f"U(1) Tensor<2,2>, leg q=-4..4 x 24, {nelem} elements", "cases": len(rows), "GBps_min": gbs[0],
+                         "GBps_median": gbs[len(gbs) // 2], "GBps_max": gbs[-1], "GBps_aggregate": tot_bytes / tot_ms / 1e6,
+                         "worst": min(rows, key=lambda r: r["GBps"]), "best": max(rows, key=lambda r: r["GBps"])}
+    ms, fl = T.bench_multiply(T, reps=3)
+    out["contract_w4"] = {"op": "T*T (17 sectors, block side (9-|Q|)*576)", "flops": fl, "ms": ms, "TFLOPs": fl / ms / 1e9,
+                          "frac_of_cublas_dgemm": fl / ms / 1e9 / dgemm_peak}
+    del T
+    ctx.close()
+    # ---- W3: SU(2) D=6 chi=144 corners, M = Q4*Q1
+    aux3 = [(1, 3), (2, 3)]
+    env3 = [(1, 16), (2, 32), (3, 36), (4, 30), (5, 18), (6, 8), (7, 4)]
+    ctx3 = xb.Context([("SU2", 0, 0)], device=device)
+    Q4, Q1 = su2_corner_pair(ctx3, aux3, env3, (1, 2))
+    ms, fl = Q4.bench_multiply(Q1, reps=5)
+    out["contract_w3"] = {"op": "Q4*Q1, SU(2) D=6 chi=144 corners (9 sectors, block side 36..2394)", "flops": fl, "ms": ms, "TFLOPs": fl / ms / 1e9,
+                          "frac_of_cublas_dgemm": fl / ms / 1e9 / dgemm_peak}
+    prow = []
+    for shift, p in [(-1, (0, 2, 3, 5, 1, 4)), (1, (0, 3, 5, 1, 2, 4)), (0, (1, 0, 2, 4, 3, 5))]:
+        Q4.bench_permute(shift, p, reps=2)
+        ctx3.flush_l2()
+        ms, nbytes = Q4.bench_permute(shift, p, reps=5)
+        prow.append({"p": list(p), "shift": shift, "ms": ms, "GBps": nbytes / ms / 1e6})
+    out["permute_w3"] = {"tensor": f"SU(2) corner Q(3,3), {Q4.plainSize()} elements (fan-in > 1: recoupling sums)", "cases": prow}
+    M = Q4 @ Q1
+    ctx3.sync()
+    ctx3.timer_start()
+    U, S, Vd = M.tSVD(144, 1e-10, False)
+    out["tsvd_w3"] = {"op": "tSVD(144, 1e-10) of M = Q4*Q1 (blocks 36..2394, 10800 singular values)", "ms": ctx3.timer_stop()}
+    del U, S, Vd, M, Q4, Q1
+    ctx3.close()
+    return out, dgemm_peak
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import xped_b200 as xb
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- xped_b200 has no CPU fallback (use --impl reference for the CPU oracle arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+
+    ctx = xb.Context([("SU2", 0, 0)], device=local)
+    lib = ctx.lib
+    aux = [(1, 2), (2, 2)]           # iPEPS::init_basis rule for D=4, spin-1/2 (src/PEPS/iPEPS.cpp:82-116)
+    a, phys = ctx.basis(aux), ctx.basis([(2, 1)])
+    A = ctx.tensor([a, a], [a, a, phys]).setRandom(rank)
+    ctm = xb.CTM(A, CHI)
+
+    def step_timed():
+        ctx.timer_start()
+        ctm.grow_all()
+        return ctx.timer_stop()
+
+    for _ in range(args.warmup):
+        ctm.grow_all()
+    ctx.sync()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident timing
+    l0 = ctx.stats()["launches"]
+    barrier()
+    total_ms = 0.0
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        total_ms += step_timed()
+    barrier()
+    launches = ctx.stats()["launches"] - l0
+    # ---- the same steps with per-category event pairs (live kernel durations for the roofline)
+    ctx.profile(True)
+    ctx.profile_read()
+    prof_ms = 0.0
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        prof_ms += step_timed()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+
+    # ---- end to end through the C ABI with host buffers
+    host = {}
+    def host_buf(name, n):
+        if name not in host or host[name].numel() < n:
+            host[name] = torch.empty(max(n, 1), dtype=torch.float64).pin_memory()
+        return host[name]
+    sizes = {}
+    for nm in ENV + ["A"]:
+        t = ctm.get(nm)
+        sizes[nm] = t.plainSize()
+        xb.capi.check(lib.xb_tensor_download(t.h, C.cast(host_buf(nm, sizes[nm]).data_ptr(), xb.capi.DP), sizes[nm]))
+    barrier()
+    e2e_ms, h2d, d2h = 0.0, 0, 0
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        ctx.timer_start()
+        for nm in ENV + ["A"]:
+            t = ctm.get(nm)          # handle with the current layout; its contents are overwritten from the host image
+            xb.capi.check(lib.xb_tensor_upload(t.h, C.cast(host[nm].data_ptr(), xb.capi.DP), sizes[nm]))
+            ctm.set(nm, t)
+            h2d += 8 * sizes[nm]
+        ctm.grow_all()
+        for nm in ENV:
+            t = ctm.get(nm)
+            sizes[nm] = t.plainSize()
+            xb.capi.check(lib.xb_tensor_download(t.h, C.cast(host_buf(nm, sizes[nm]).data_ptr(), xb.capi.DP), sizes[nm]))
+            d2h += 8 * sizes[nm]
+        e2e_ms += ctx.timer_stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        tt = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = tt.tolist()
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    extras, dgemm_peak = ({}, None)
+    if rank == 0 and not args.no_extras:
+        extras, dgemm_peak = kernel_sections(xb, local, torch)
+
+    if rank == 0:
+        ms_step = total_ms / args.steps
+        value = world * args.steps / (total_ms * 1e-3)
+        p_ms, p_cnt, p_bytes = prof["permute"]
+        g_ms, g_cnt, g_fl = prof["gemm"]
+        s_ms, s_cnt, _ = prof["tsvd"]
+        shares = {k: (v[0] / prof_ms if prof_ms > 0 else None) for k, v in prof.items()}
+        # roofline of the HBM-bound kernel on the tensor that is large enough to be bandwidth-bound (W4); the CTM-step
+        # permutes (<= 11 MB each at D=4) are launch/latency-bound and are reported beside it.
+        roofline = None
+        if extras:
+            w4 = extras["permute_w4"]
+            roofline = {"kernel": "permute_kernel", "bound": "hbm", "achieved": w4["GBps_aggregate"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": w4["GBps_aggregate"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "on": "W4 (25 permute<shift,p> cases of the 1.30 GB U(1) tensor), algorithmic bytes 8*(N_src+N_dst) per launch",
+                        "in_ctm_step": {"launches_per_step": p_cnt / args.steps, "avg_us_per_launch": 1e3 * p_ms / max(p_cnt, 1),
+                                        "GBps": p_bytes / max(p_ms, 1e-9) / 1e6, "share_of_step": shares["permute"]}}
+            roofline_contract = {"kernel": "gemm_grouped_kernel", "bound": "tensor", "achieved": extras["contract_w4"]["TFLOPs"], "peak": dgemm_peak,
+                                 "unit": "TFLOP/s", "frac": extras["contract_w4"]["TFLOPs"] / dgemm_peak, "traffic": None,
+                                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                                 "on": "W4 T*T (1.27e12 flop)",
+                                 "in_ctm_step": {"launches_per_step": g_cnt / args.steps, "avg_us_per_launch": 1e3 * g_ms / max(g_cnt, 1),
+                                                 "TFLOPs": g_fl / max(g_ms, 1e-9) / 1e9, "share_of_step": shares["gemm"]}}
+        else:
+            roofline = {"kernel": "permute_kernel", "bound": "hbm", "achieved": p_bytes / max(p_ms, 1e-9) / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": p_bytes / max(p_ms, 1e-9) / 1e6 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "on": "permutes inside the CTM step (latency-bound sizes)"}
+            roofline_contract = None
+        cpu_sps, cpu_ms = time_oracle(3, args.cpu_steps) if (world == 1 and args.cpu_steps > 0) else (None, None)
+        line = {"metric": "ctmrg_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (counter-based uniform[-1,1] site tensor, seed = rank)", "config": config_dict(world),
+                "clocks": clocks,
+                "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d // args.steps,
+                        "d2h_bytes_per_step": d2h // args.steps},
+                "gpu_launches": int(launches),
+                "roofline": roofline, "roofline_contract": roofline_contract,
+                "step_breakdown": {"ms_per_step_with_event_pairs": prof_ms / args.steps,
+                                   "per_step": {k: {"ms": v[0] / args.steps, "launch_groups": v[1] / args.steps, "share": shares[k]} for k, v in prof.items()}},
+                "kernels": extras}
+        if cpu_sps is not None:
+            line["cpu_baseline"] = {"value": cpu_sps, "unit": "steps/s", "cores": blas_threads(), "kind": "port",
+                                    "sample": f"{args.cpu_steps} grow_all() steps of the same D=4 chi=64 workload after 3 warm-up steps, oracle/xped_oracle "
+                                              "(numpy restatement of the reference algorithm)", "ms_per_step": cpu_ms}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

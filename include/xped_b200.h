@@ -142,6 +142,17 @@ int xb_ctm_move(xb_ctm* c, int direction);                                      
 int xb_bench_permute(xb_ctx* ctx, const xb_tensor* t, int shift, const int* p, int n, int reps, double* ms_per_launch, int64_t* bytes);
 int xb_bench_multiply(xb_ctx* ctx, const xb_tensor* a, const xb_tensor* b, int reps, double* ms_per_launch, double* flops);
 int xb_flush_l2(xb_ctx* ctx);
+/* the context's CUDA stream (cudaStream_t) so that a host framework can order its own work after ours */
+void* xb_ctx_stream(xb_ctx* ctx);
+/* CUDA-event stopwatch on the context stream: start records an event, stop records a second one, synchronises on
+ * it and returns the elapsed device time in ms (covers host gaps between enqueued work, like a wall clock) */
+int xb_timer_start(xb_ctx* ctx);
+int xb_timer_stop(xb_ctx* ctx, double* ms);
+/* live per-category device timing: while enabled every launch group is bracketed by a CUDA event pair.
+ * xb_profile_read synchronises, returns {ms, launches, work} summed per category and resets; categories:
+ * 0 permute (work = algorithmic bytes), 1 grouped DGEMM (work = flops), 2 tSVD (work = 0), 3 other */
+int xb_profile_enable(xb_ctx* ctx, int on);
+int xb_profile_read(xb_ctx* ctx, double ms[4], int64_t count[4], double work[4]);
 
 #ifdef __cplusplus
 }

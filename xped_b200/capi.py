@@ -88,6 +88,11 @@ SIGNATURES = {
     "xb_bench_permute": (C.c_int, [P, P, C.c_int, IP, C.c_int, C.c_int, DP, LP]),
     "xb_bench_multiply": (C.c_int, [P, P, P, C.c_int, DP, DP]),
     "xb_flush_l2": (C.c_int, [P]),
+    "xb_ctx_stream": (C.c_void_p, [P]),
+    "xb_timer_start": (C.c_int, [P]),
+    "xb_timer_stop": (C.c_int, [P, DP]),
+    "xb_profile_enable": (C.c_int, [P, C.c_int]),
+    "xb_profile_read": (C.c_int, [P, DP, LP, DP]),
 }
 
 _lib = None

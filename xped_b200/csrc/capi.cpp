@@ -646,4 +646,39 @@ int xb_flush_l2(xb_ctx* ctx)
     });
 }
 
+void* xb_ctx_stream(xb_ctx* ctx) { return ctx ? static_cast<void*>(ctx->impl.stream) : nullptr; }
+
+int xb_timer_start(xb_ctx* ctx)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        ctx->impl.timer_start();
+    });
+}
+
+int xb_timer_stop(xb_ctx* ctx, double* ms)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(ms, "ms");
+        *ms = ctx->impl.timer_stop();
+    });
+}
+
+int xb_profile_enable(xb_ctx* ctx, int on)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        ctx->impl.profiling = on != 0;
+    });
+}
+
+int xb_profile_read(xb_ctx* ctx, double ms[4], int64_t count[4], double work[4])
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        ctx->impl.prof_read(ms, count, work);
+    });
+}
+
 }   // extern "C"

@@ -158,6 +158,19 @@ public:
     int64_t launches = 0;
     int64_t plan_hits = 0, plan_misses = 0;
 
+    // ---- live per-category device timing (bench.py roofline): CUDA event pairs on `stream` around each
+    // launch group while profiling is enabled; prof_read() synchronises, sums and resets.
+    enum Cat { CAT_PERMUTE = 0, CAT_GEMM = 1, CAT_SVD = 2, CAT_OTHER = 3, CAT_N = 4 };
+    bool profiling = false;
+    struct ProfRec { cudaEvent_t e0, e1; int cat; double work; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t get_event();
+    void prof_read(double ms[CAT_N], int64_t count[CAT_N], double work[CAT_N]);
+    cudaEvent_t timer_e0 = nullptr, timer_e1 = nullptr;
+    void timer_start();
+    double timer_stop();   // ms between timer_start() and now on `stream` (synchronises)
+
     // scratch device buffer for reductions / work lists
     void* scratch(size_t bytes);
     void* pinned(size_t bytes);
@@ -175,6 +188,30 @@ private:
 };
 
 void check_cuda(cudaError_t e, const char* what);
+
+// RAII event pair around a launch group; `work` = algorithmic bytes (permute) or flops (GEMM).
+struct ProfScope
+{
+    Context& c;
+    cudaEvent_t e0 = nullptr;
+    int cat;
+    double work;
+    ProfScope(Context& ctx, int category, double w) : c(ctx), cat(category), work(w)
+    {
+        if(c.profiling) {
+            e0 = c.get_event();
+            cudaEventRecord(e0, c.stream);
+        }
+    }
+    ~ProfScope()
+    {
+        if(e0) {
+            cudaEvent_t e1 = c.get_event();
+            cudaEventRecord(e1, c.stream);
+            c.prof_recs.push_back({e0, e1, cat, work});
+        }
+    }
+};
 
 // ---- kernel launchers (kernels.cu) ----
 void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s);

@@ -44,6 +44,13 @@ Context::~Context()
     cudaSetDevice(device);
     if(stream) cudaStreamSynchronize(stream);
     plan_cache_.clear();
+    for(const ProfRec& r : prof_recs) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    for(cudaEvent_t e : event_pool) cudaEventDestroy(e);
+    if(timer_e0) cudaEventDestroy(timer_e0);
+    if(timer_e1) cudaEventDestroy(timer_e1);
     for(auto& p : staging_) cudaFreeHost(p.first);
     if(scratch_) cudaFree(scratch_);
     if(pinned_) cudaFreeHost(pinned_);
@@ -55,6 +62,57 @@ void Context::sync()
     check_cuda(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
     for(auto& p : staging_) cudaFreeHost(p.first);
     staging_.clear();
+}
+
+cudaEvent_t Context::get_event()
+{
+    if(!event_pool.empty()) {
+        cudaEvent_t e = event_pool.back();
+        event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    check_cuda(cudaEventCreate(&e), "cudaEventCreate");
+    return e;
+}
+
+void Context::prof_read(double ms[CAT_N], int64_t count[CAT_N], double work[CAT_N])
+{
+    check_cuda(cudaStreamSynchronize(stream), "prof_read sync");
+    for(int i = 0; i < CAT_N; ++i) {
+        ms[i] = 0.0;
+        count[i] = 0;
+        work[i] = 0.0;
+    }
+    for(const ProfRec& r : prof_recs) {
+        float t = 0.f;
+        check_cuda(cudaEventElapsedTime(&t, r.e0, r.e1), "cudaEventElapsedTime");
+        ms[r.cat] += t;
+        count[r.cat] += 1;
+        work[r.cat] += r.work;
+        event_pool.push_back(r.e0);
+        event_pool.push_back(r.e1);
+    }
+    prof_recs.clear();
+}
+
+void Context::timer_start()
+{
+    if(!timer_e0) {
+        check_cuda(cudaEventCreate(&timer_e0), "cudaEventCreate");
+        check_cuda(cudaEventCreate(&timer_e1), "cudaEventCreate");
+    }
+    check_cuda(cudaEventRecord(timer_e0, stream), "timer_start");
+}
+
+double Context::timer_stop()
+{
+    if(!timer_e0) throw std::invalid_argument("timer_stop without timer_start");
+    check_cuda(cudaEventRecord(timer_e1, stream), "timer_stop");
+    check_cuda(cudaEventSynchronize(timer_e1), "timer_stop sync");
+    float t = 0.f;
+    check_cuda(cudaEventElapsedTime(&t, timer_e0, timer_e1), "timer elapsed");
+    return static_cast<double>(t);
 }
 
 void* Context::scratch(size_t bytes)

@@ -409,6 +409,7 @@ SvdResult Context::tsvd(const Tensor& t, int64_t max_keep, double eps_svd, bool 
 {
     const Layout& L = *t.layout;
     if(L.sector.empty()) throw std::invalid_argument("tSVD: tensor has no blocks");
+    ProfScope prof(*this, CAT_SVD, 0.0);
     JacobiResult J = jacobi_all(*this, t, nullptr);
     struct SV { int sector; int col; int k; double s; };
     std::vector<SV> all;

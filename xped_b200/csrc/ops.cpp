@@ -15,6 +15,7 @@ Tensor* Context::permute(const Tensor& t, int shift, const std::vector<int>& pi)
 {
     auto plan = permute_plan(t.layout, shift, pi, false);
     auto* out = new Tensor(this, plan->out, false);
+    ProfScope prof(*this, CAT_PERMUTE, static_cast<double>(plan->bytes));
     if(plan->identity_copy) {
         check_cuda(cudaMemcpyAsync(out->d, t.d, sizeof(double) * t.size(), cudaMemcpyDeviceToDevice, stream), "permute identity copy");
     } else {
@@ -28,6 +29,7 @@ Tensor* Context::permute_adj(const Tensor& t, int shift, const std::vector<int>&
 {
     auto plan = permute_plan(t.layout, shift, pi, true);
     auto* out = new Tensor(this, plan->out, false);
+    ProfScope prof(*this, CAT_PERMUTE, static_cast<double>(plan->bytes));
     if(plan->identity_copy) {
         check_cuda(cudaMemcpyAsync(out->d, t.d, sizeof(double) * t.size(), cudaMemcpyDeviceToDevice, stream), "permute_adj identity copy");
     } else {
@@ -91,6 +93,9 @@ Tensor* Context::multiply(const Tensor& a, bool adj_a, const Tensor& b, bool adj
             }
     }
     if(!items.empty()) {
+        double flops = 0.0;
+        for(const GemmItem& g : items) flops += 2.0 * std::min(64, g.m - g.tm) * std::min(64, g.n - g.tn) * static_cast<double>(g.k);
+        ProfScope prof(*this, CAT_GEMM, flops);
         // heavy tiles first: k is the per-tile cost
         std::stable_sort(items.begin(), items.end(), [](const GemmItem& x, const GemmItem& y) { return x.k > y.k; });
         GemmItem* d_items = nullptr;

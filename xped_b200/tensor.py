@@ -27,6 +27,7 @@ class Context:
 
     def __init__(self, spec, device=0):
         self.lib = capi.load()
+        self.device = int(device)
         self.spec = [(k, int(n), int(f)) for k, n, f in spec]
         facs = (capi.SymFactor * max(len(self.spec), 1))()
         for i, (k, n, f) in enumerate(self.spec):
@@ -46,6 +47,23 @@ class Context:
 
     def flush_l2(self):
         check(self.lib.xb_flush_l2(self.h))
+
+    def timer_start(self):
+        check(self.lib.xb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        check(self.lib.xb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile(self, on):
+        check(self.lib.xb_profile_enable(self.h, int(bool(on))))
+
+    def profile_read(self):
+        """{category: (ms, launches, work)} since the last read; work = bytes (permute) / flops (gemm)."""
+        ms, cnt, work = (C.c_double * 4)(), (C.c_int64 * 4)(), (C.c_double * 4)()
+        check(self.lib.xb_profile_read(self.h, ms, cnt, work))
+        return {n: (ms[i], cnt[i], work[i]) for i, n in enumerate(["permute", "gemm", "tsvd", "other"])}
 
     def close(self):
         if self.h:

@@ -255,3 +255,26 @@ def test_ctm_single_moves_generic_environment(ctxs, name, D, chi):
             assert gt.structure() == ot.structure(), f"move {direction} {nm}"
             a, b = np.abs(gt.download()), np.abs(ot.data)
             assert np.abs(a - b).max() < 1e-10 * b.max(), f"move {direction} {nm}: {np.abs(a - b).max():.2e}"
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1", "U1xU1", "fU1xSU2"])
+def test_mps_transfer_contractions(ctxs, name):
+    """contract_L / contract_R (src/MPS/MpsContractions.cpp:11-105) vs the oracle, and the reference's own identity
+    tests/mps_tests.hpp:19-33 (== permute + operator* formulation) evaluated on the device."""
+    from xped_oracle.mps import contract_L as ocontract_L
+    from xped_oracle.mps import contract_R as ocontract_R
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(29)
+    inb, loc = rand_entries(SPECS[name], 12, rng), rand_entries(SPECS[name], 4, rng, 2)
+    out = [(q, d) for q, _, d in obasis(osym, inb).combine(obasis(osym, loc)).forgetHistory().data]
+    g1, o1 = pair(ctx, osym, [inb, loc], [out], 71)
+    g2, o2 = pair(ctx, osym, [inb, loc], [out], 72)
+    gR, oR = pair(ctx, osym, [out], [out], 73)
+    gL, oL = pair(ctx, osym, [inb], [inb], 74)
+    gBr, gBl = xb.contract_R(gR, g1, g2), xb.contract_L(gL, g1, g2)
+    assert_same(gBr, ocontract_R(oR, o1, o2), TOL, "contract_R")
+    assert_same(gBl, ocontract_L(oL, o1, o2), TOL, "contract_L")
+    chk = (g2 @ gR).permute(1, (0, 1, 2)).multiply(g1.permute(1, (0, 1, 2)), False, True)
+    assert np.linalg.norm(gBr.download() - chk.download()) <= 1e-12 * np.linalg.norm(chk.download())
+    chk = g1.permute(1, (0, 1, 2)).multiply(gL, True, False).permute(1, (1, 2, 0)) @ g2
+    assert np.linalg.norm(gBl.download() - chk.download()) <= 1e-12 * np.linalg.norm(chk.download())

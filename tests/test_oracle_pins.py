@@ -217,3 +217,29 @@ def test_su2_spin_operator_known_answers(twoS1):
             assert outer.block(i).size == 1
             Stot = 0.5 * (q[0] - 1.0)
             assert abs(outer.block(i)[0, 0] - 0.5 * (Stot * (Stot + 1) - S1 * (S1 + 1.0) - S2 * (S2 + 1.0))) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1", "U0", "fU1xSU2"])
+def test_mps_contractions_equal_permute_formulation(name):
+    """tests/mps_tests.hpp:19-33: contract_R / contract_L == the permute + operator* formulation."""
+    from xped_oracle.mps import contract_L, contract_R
+    make, size = SYMS[name]
+    sym = make()
+    rng = np.random.default_rng(23)
+    inb, loc = rand_basis(sym, size + 4, rng), rand_basis(sym, 4, rng, 2)
+    out = inb.combine(loc).forgetHistory()
+    T1, T2 = Tensor(sym, [inb, loc], [out]), Tensor(sym, [inb, loc], [out])
+    T1.setRandom(rng)
+    T2.setRandom(rng)
+    Bright = Tensor(sym, [out], [out])
+    Bright.setRandom(rng)
+    Bcheck = (T2 @ Bright).permute(1, (0, 1, 2)) @ T1.permute(1, (0, 1, 2)).adjoint()
+    Bn = contract_R(Bright, T1, T2)
+    assert Bn.structure() == Bcheck.structure()
+    assert np.linalg.norm(Bn.data - Bcheck.data) <= 1e-12 * max(np.linalg.norm(Bcheck.data), 1.0)
+    Bleft = Tensor(sym, [inb], [inb])
+    Bleft.setRandom(rng)
+    Bcheck = (T1.permute(1, (0, 1, 2)).adjoint() @ Bleft).permute(1, (1, 2, 0)) @ T2
+    Bn = contract_L(Bleft, T1, T2)
+    assert Bn.structure() == Bcheck.structure()
+    assert np.linalg.norm(Bn.data - Bcheck.data) <= 1e-12 * max(np.linalg.norm(Bcheck.data), 1.0)

@@ -84,6 +84,8 @@ struct PermutePlan
     ~PermutePlan();
 };
 
+constexpr int GEMM_TILE_M = 64, GEMM_TILE_N = 64;   // CTA tile of gemm_grouped_kernel
+
 struct GemmItem   // one (sector, tile) of a grouped product
 {
     long long a_off, b_off, c_off;
@@ -91,6 +93,9 @@ struct GemmItem   // one (sector, tile) of a grouped product
     int lda, ldb, ldc;
     int tm, tn;   // tile origin
     int ta, tb;   // operand stored transposed (adjoint block)?
+    int acc;      // 1: C += alpha * op(A) op(B)   0: C = alpha * op(A) op(B)
+    int pad_;
+    double alpha;
 };
 
 class Context;
@@ -153,6 +158,8 @@ public:
     void contract_L(const Tensor& Bold, const Tensor& Bra, const Tensor& Ket, Tensor** Bnew);
     void contract_R(const Tensor& Bold, const Tensor& Bra, const Tensor& Ket, Tensor** Bnew);
     void sync();
+    // grouped product launcher: one GemmItem per problem (tm = tn = 0); tiles, sorts, uploads and launches
+    void run_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems);
 
     // statistics for bench / gpu_launches
     int64_t launches = 0;

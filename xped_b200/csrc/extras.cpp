@@ -1,5 +1,9 @@
 // teigh / tQR / SVD reverse rule / MPS transfer contractions. (Filled in after the first GPU bring-up.)
+#include <cstring>
+#include <memory>
 #include <stdexcept>
+#include <string>
+#include <vector>
 
 #include "engine.hpp"
 
@@ -11,7 +15,145 @@ Tensor* Context::tsvd_backward(const Tensor&, const Tensor&, const Tensor&, cons
 {
     throw std::logic_error("tsvd_backward: not implemented yet");
 }
-void Context::contract_L(const Tensor&, const Tensor&, const Tensor&, Tensor**) { throw std::logic_error("contract_L: not implemented yet"); }
-void Context::contract_R(const Tensor&, const Tensor&, const Tensor&, Tensor**) { throw std::logic_error("contract_R: not implemented yet"); }
+// ------------------------------------------------------------------------------------------------ MPS transfer contractions
+// contract_L (src/MPS/MpsContractions.cpp:11-51):  Bnew[Q] = sum_{tree (Qin,sigma)->Q} sum_s Bra_sub(s)^T * Bold[Qin] * Ket_sub(s).
+// Device form: two grouped launches instead of one small GEMM pair per (Q, tree, s):
+//   X = "Bold applied to the left leg of Ket" (same layout as Ket; rows whose Qin is absent from Bold stay zero),
+//   Bnew[Q] = Bra[Q]^T * X[Q]   (one full-K product per sector).
+namespace {
+void check_mps_args(const Tensor& Bold, const Tensor& Bra, const Tensor& Ket, const char* who)
+{
+    if(Bold.layout->rank() != 1 || Bold.layout->corank() != 1 || Bra.layout->rank() != 2 || Bra.layout->corank() != 1 || Ket.layout->rank() != 2 ||
+       Ket.layout->corank() != 1)
+        throw std::invalid_argument(std::string(who) + ": expects Bold(1,1), Bra(2,1), Ket(2,1)");
+}
+GemmItem blank_item()
+{
+    GemmItem g;
+    std::memset(&g, 0, sizeof(g));
+    g.alpha = 1.0;
+    return g;
+}
+}   // namespace
+
+void Context::contract_L(const Tensor& Bold, const Tensor& Bra, const Tensor& Ket, Tensor** Bnew)
+{
+    check_mps_args(Bold, Bra, Ket, "contract_L");
+    const Layout &LB = *Bold.layout, &LBra = *Bra.layout, &LK = *Ket.layout;
+    LayoutPtr LO = layout({LBra.cod[0]}, {LK.cod[0]});
+    std::unique_ptr<Tensor> out(new Tensor(this, LO, true));
+    std::unique_ptr<Tensor> X(new Tensor(this, Ket.layout, true));
+    std::vector<GemmItem> s1, s2;
+    for(size_t i = 0; i < LBra.sector.size(); ++i) {
+        const Q& q = LBra.sector[i];
+        const int k = LK.find(q);
+        if(k < 0) continue;
+        const int o = LO->find(q);
+        if(o < 0) continue;
+        const int dimQ = static_cast<int>(LBra.cols[i]);
+        if(LK.cols[k] != dimQ && false) throw std::invalid_argument("contract_L: Bra / Ket blocks differ");
+        bool any = false;
+        for(const Tree& t : LBra.cdom->trees(q)) {
+            const int ib = LB.find(t.unc[0]);
+            if(ib < 0) continue;
+            const int64_t ro_k = LK.cdom->left_offset(t);
+            const int d0 = static_cast<int>(t.dims[0]), d1 = static_cast<int>(t.dims[1]);
+            if(LB.rows[ib] != d0 || LB.cols[ib] != d0) throw std::invalid_argument("contract_L: Bold block does not match the left leg of Bra/Ket");
+            for(int s = 0; s < d1; ++s) {
+                GemmItem g = blank_item();   // X_sub(s) = Bold[Qin] * Ket_sub(s)
+                g.a_off = LB.off[ib];
+                g.lda = d0;
+                g.b_off = LK.off[k] + ro_k + static_cast<int64_t>(s) * d0;
+                g.ldb = static_cast<int>(LK.rows[k]);
+                g.c_off = g.b_off;
+                g.ldc = g.ldb;
+                g.m = d0;
+                g.k = d0;
+                g.n = static_cast<int>(LK.cols[k]);
+                s1.push_back(g);
+                any = true;
+            }
+        }
+        if(!any) continue;
+        GemmItem g = blank_item();   // Bnew[Q] = Bra[Q]^T * X[Q]
+        g.a_off = LBra.off[i];
+        g.lda = static_cast<int>(LBra.rows[i]);
+        g.ta = 1;
+        g.b_off = LK.off[k];
+        g.ldb = static_cast<int>(LK.rows[k]);
+        g.c_off = LO->off[o];
+        g.ldc = static_cast<int>(LO->rows[o]);
+        g.m = dimQ;
+        g.k = static_cast<int>(LBra.rows[i]);
+        g.n = static_cast<int>(LK.cols[k]);
+        if(LK.rows[k] != LBra.rows[i] || LO->rows[o] != g.m || LO->cols[o] != g.n) throw std::invalid_argument("contract_L: Bra / Ket block shapes differ");
+        s2.push_back(g);
+    }
+    run_gemm(Bold.d, Ket.d, X->d, s1);
+    run_gemm(Bra.d, X->d, out->d, s2);
+    *Bnew = out.release();
+}
+
+// contract_R (MpsContractions.cpp:54-105): Bnew[Qin] += coeff_rightOrtho(Q,Qin) * sum_s Ket_sub(s) * Bold[Q] * Bra_sub(s)^T.
+//   Y[Q] = Ket[Q] * Bold[Q] (one product per sector), then the (Q, tree, s) terms are accumulated into Bnew[Qin] in
+//   "waves" holding at most one term per destination block, so the summation order is fixed (deterministic).
+void Context::contract_R(const Tensor& Bold, const Tensor& Bra, const Tensor& Ket, Tensor** Bnew)
+{
+    check_mps_args(Bold, Bra, Ket, "contract_R");
+    const Layout &LB = *Bold.layout, &LBra = *Bra.layout, &LK = *Ket.layout;
+    LayoutPtr LO = layout({LK.dom[0]}, {LBra.dom[0]});
+    std::unique_ptr<Tensor> out(new Tensor(this, LO, true));
+    std::unique_ptr<Tensor> Y(new Tensor(this, Ket.layout, true));
+    std::vector<GemmItem> s1;
+    std::vector<std::vector<GemmItem>> waves;
+    std::vector<int> used(LO->sector.size(), 0);
+    for(size_t i = 0; i < LK.sector.size(); ++i) {
+        const Q& q = LK.sector[i];
+        const int ib = LB.find(q), ibra = LBra.find(q);
+        if(ib < 0 || ibra < 0) continue;
+        const int dimQ = static_cast<int>(LK.cols[i]);
+        if(LB.rows[ib] != dimQ || LB.cols[ib] != dimQ || LBra.cols[ibra] != dimQ) throw std::invalid_argument("contract_R: Bold block does not match the right leg of Bra/Ket");
+        GemmItem g = blank_item();
+        g.a_off = LK.off[i];
+        g.lda = static_cast<int>(LK.rows[i]);
+        g.b_off = LB.off[ib];
+        g.ldb = dimQ;
+        g.c_off = LK.off[i];
+        g.ldc = g.lda;
+        g.m = g.lda;
+        g.k = dimQ;
+        g.n = dimQ;
+        s1.push_back(g);
+        for(const Tree& t : LK.cdom->trees(q)) {
+            const int o = LO->find(t.unc[0]);
+            if(o < 0) continue;
+            const int64_t ro_k = LK.cdom->left_offset(t), ro_b = LBra.cdom->left_offset(t);
+            const int d0 = static_cast<int>(t.dims[0]), d1 = static_cast<int>(t.dims[1]);
+            const double coeff = sym->coeff_rightOrtho(q, t.unc[0]);
+            for(int s = 0; s < d1; ++s) {
+                GemmItem h = blank_item();   // Bnew[Qin] += coeff * Y_sub(s) * Bra_sub(s)^T
+                h.a_off = LK.off[i] + ro_k + static_cast<int64_t>(s) * d0;
+                h.lda = static_cast<int>(LK.rows[i]);
+                h.b_off = LBra.off[ibra] + ro_b + static_cast<int64_t>(s) * d0;
+                h.ldb = static_cast<int>(LBra.rows[ibra]);
+                h.tb = 1;
+                h.c_off = LO->off[o];
+                h.ldc = static_cast<int>(LO->rows[o]);
+                h.m = d0;
+                h.k = dimQ;
+                h.n = d0;
+                h.acc = 1;
+                h.alpha = coeff;
+                if(LO->rows[o] != d0 || LO->cols[o] != d0) throw std::invalid_argument("contract_R: result block shape mismatch");
+                const int w = used[o]++;
+                if(static_cast<int>(waves.size()) <= w) waves.resize(w + 1);
+                waves[w].push_back(h);
+            }
+        }
+    }
+    run_gemm(Ket.d, Bold.d, Y->d, s1);
+    for(const auto& w : waves) run_gemm(Y->d, Bra.d, out->d, w);
+    *Bnew = out.release();
+}
 
 }   // namespace xb

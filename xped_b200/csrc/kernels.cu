@@ -207,8 +207,13 @@ gemm_grouped_kernel(const double* __restrict__ A, const double* __restrict__ B, 
             const int gm = m0 + wm + i * 8 + fr;
             const int gn = n0 + wn + j * 8 + 2 * fk;
             if(gm < it.m) {
-                if(gn < it.n) Cp[gm + static_cast<long long>(gn) * it.ldc] = acc[i][j][0];
-                if(gn + 1 < it.n) Cp[gm + static_cast<long long>(gn + 1) * it.ldc] = acc[i][j][1];
+#pragma unroll
+                for(int h = 0; h < 2; ++h)
+                    if(gn + h < it.n) {
+                        double* p = Cp + gm + static_cast<long long>(gn + h) * it.ldc;
+                        const double v = it.alpha * acc[i][j][h];
+                        *p = it.acc ? *p + v : v;
+                    }
             }
         }
 }

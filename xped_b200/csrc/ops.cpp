@@ -46,6 +46,33 @@ Tensor* Context::copy(const Tensor& t)
     return out;
 }
 
+// ------------------------------------------------------------------------------------------------ grouped GEMM launcher
+void Context::run_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems)
+{
+    std::vector<GemmItem> items;
+    double flops = 0.0;
+    for(GemmItem g : problems) {
+        if(g.m <= 0 || g.n <= 0) continue;
+        flops += 2.0 * g.m * static_cast<double>(g.n) * g.k;
+        for(int tn = 0; tn < g.n; tn += GEMM_TILE_N)
+            for(int tm = 0; tm < g.m; tm += GEMM_TILE_M) {
+                g.tm = tm;
+                g.tn = tn;
+                items.push_back(g);
+            }
+    }
+    if(items.empty()) return;
+    ProfScope prof(*this, CAT_GEMM, flops);
+    // heavy tiles first: k is the per-tile cost
+    std::stable_sort(items.begin(), items.end(), [](const GemmItem& x, const GemmItem& y) { return x.k > y.k; });
+    GemmItem* d_items = nullptr;
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_items), items.size() * sizeof(GemmItem), stream), "cudaMallocAsync gemm items");
+    upload_async(d_items, items.data(), items.size() * sizeof(GemmItem));
+    launch_gemm_grouped(A, B, C, d_items, static_cast<int>(items.size()), stream);
+    check_cuda(cudaFreeAsync(d_items, stream), "cudaFreeAsync gemm items");
+    ++launches;
+}
+
 // ------------------------------------------------------------------------------------------------ operator*
 // TensorBase::operator* (src/Core/TensorBase.cpp:243-288). Operands may be lazy adjoints (AdjointOp.hpp:26-69):
 // the block is then read transposed, domain/codomain swap roles, the sector list stays the operand's.
@@ -85,26 +112,10 @@ Tensor* Context::multiply(const Tensor& a, bool adj_a, const Tensor& b, bool adj
         g.n = static_cast<int>(adj_b ? LB.rows[j] : LB.cols[j]);
         if(kb != g.k || g.m != LO->rows[o] || g.n != LO->cols[o]) throw std::logic_error("operator*: block shape mismatch");
         if(g.m == 0 || g.n == 0) continue;
-        for(int tn = 0; tn < g.n; tn += 64)
-            for(int tm = 0; tm < g.m; tm += 64) {
-                g.tm = tm;
-                g.tn = tn;
-                items.push_back(g);
-            }
+        g.alpha = 1.0;
+        items.push_back(g);
     }
-    if(!items.empty()) {
-        double flops = 0.0;
-        for(const GemmItem& g : items) flops += 2.0 * std::min(64, g.m - g.tm) * std::min(64, g.n - g.tn) * static_cast<double>(g.k);
-        ProfScope prof(*this, CAT_GEMM, flops);
-        // heavy tiles first: k is the per-tile cost
-        std::stable_sort(items.begin(), items.end(), [](const GemmItem& x, const GemmItem& y) { return x.k > y.k; });
-        GemmItem* d_items = nullptr;
-        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_items), items.size() * sizeof(GemmItem), stream), "cudaMallocAsync gemm items");
-        upload_async(d_items, items.data(), items.size() * sizeof(GemmItem));
-        launch_gemm_grouped(a.d, b.d, out->d, d_items, static_cast<int>(items.size()), stream);
-        check_cuda(cudaFreeAsync(d_items, stream), "cudaFreeAsync gemm items");
-        ++launches;
-    }
+    run_gemm(a.d, b.d, out->d, items);
     return out;
 }
 

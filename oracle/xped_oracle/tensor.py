@@ -397,6 +397,42 @@ class Tensor:
             return U, S, Vd, dict(truncWeight=truncWeight, entropy=entropy, kept={q: len(v) for q, v in ordered.items()})
         return U, S, Vd
 
+    def tSVD_backward(self, dU=None, dS=None, dVd=None):
+        """Reverse rule of tSVD = full_svd_impl + cutoff_matrices (include/Xped/AD/ADTensor.hpp:253-325 and :356-371).
+        dU / dS / dVd are the adjoints of the TRUNCATED factors (or None): cutoff_matrices' reverse pass adds them into
+        the left columns / top-left corner / top rows of the full factors' adjoints, then the full-SVD rule gives dA."""
+        out = self.like()
+        out.data[...] = 0.0
+        for i, q in enumerate(self.sector):
+            u, s, vh = np.linalg.svd(self.block(i), full_matrices=False)
+            r = s.size
+            dUf, dSf, dVf = np.zeros_like(u), np.zeros((r, r)), np.zeros_like(vh)
+            touched = False
+            for src, dst, sl in ((dU, dUf, lambda b: (slice(None), slice(0, b.shape[1]))), (dS, dSf, lambda b: (slice(0, b.shape[0]), slice(0, b.shape[1]))),
+                                 (dVd, dVf, lambda b: (slice(0, b.shape[0]), slice(None)))):
+                if src is not None and q in src.dict:
+                    b = src.block(src.dict[q])
+                    dst[sl(b)] += b
+                    touched = True
+            if not touched:
+                continue   # :259-260: sectors absent from the (truncated) S contribute nothing
+            s2 = s * s
+            Finv = s2[None, :] - s2[:, None]                         # vec_diff: res(i,j) = v(j) - v(i)
+            small = np.abs(Finv) < 1.0e-12
+            with np.errstate(divide="ignore", invalid="ignore"):
+                F = np.where(small, Finv / (Finv * Finv + 1.0e-12), 1.0 / np.where(small, 1.0, Finv))
+            S = np.diag(s)
+            Vdag_dV = vh @ dVf.conj().T
+            J = F * (u.conj().T @ dUf)
+            K = F * Vdag_dV
+            dA = u @ (dSf + (J + J.conj().T) @ S + S @ (K + K.conj().T)) @ vh
+            with np.errstate(divide="ignore"):
+                Sinv = np.diag(1.0 / s)
+            dA += (np.eye(u.shape[0]) - u @ u.conj().T) @ dUf @ Sinv @ vh
+            dA += u @ Sinv @ dVf @ (np.eye(vh.shape[1]) - vh.conj().T @ vh)
+            out.block(i)[...] += dA
+        return out
+
     def tQR(self, RETURN_LQ=False):
         """Tensor.cpp:757-780."""
         sym = self.sym

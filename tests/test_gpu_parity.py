@@ -278,3 +278,68 @@ def test_mps_transfer_contractions(ctxs, name):
     assert np.linalg.norm(gBr.download() - chk.download()) <= 1e-12 * np.linalg.norm(chk.download())
     chk = g1.permute(1, (0, 1, 2)).multiply(gL, True, False).permute(1, (1, 2, 0)) @ g2
     assert np.linalg.norm(gBl.download() - chk.download()) <= 1e-12 * np.linalg.norm(chk.download())
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1", "U1xU1"])
+def test_tqr(ctxs, name):
+    """Tensor::tQR (src/Core/Tensor.cpp:757-780) on MPS-shaped A(2,1) tensors (tall blocks) and a square (2,2) tensor.
+    The reference has no tQR test ("parity unpinned"): compared with the oracle's LAPACK Householder factors (same sign
+    convention) and through Q*R = A, Q^dagger Q = 1, R upper triangular."""
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(37)
+    inb, loc = rand_entries(SPECS[name], 12, rng), rand_entries(SPECS[name], 4, rng, 2)
+    out = [(q, d) for q, _, d in obasis(osym, inb).combine(obasis(osym, loc)).forgetHistory().data][::2]
+    cases = [pair(ctx, osym, [inb, loc], [out], 81), pair(ctx, osym, [inb, loc], [inb, loc], 82)]
+    for g, o in cases:
+        gQ, gR = g.tQR()
+        oQ, oR = o.tQR()
+        assert gQ.structure() == oQ.structure() and gR.structure() == oR.structure()
+        assert_same(gQ @ gR, o, 1e-12, "Q*R")
+        one = gQ.multiply(gQ, True, False)
+        assert np.abs(one.download() - one.clone().setIdentity().download()).max() < 1e-12
+        assert_same(gR, oR, 1e-11, "R (Householder sign convention)")
+        assert_same(gQ, oQ, 1e-11, "Q")
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1", "U0"])
+def test_teigh(ctxs, name):
+    """Tensor::teigh (src/Core/Tensor.cpp:782-803): eigenvalues ascending per block (bit-exact structure, values 1e-12),
+    eigenvectors through V D V^dagger = H and V^dagger V = 1 (their signs are a gauge freedom)."""
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(41)
+    B, Cb = rand_entries(SPECS[name], 13, rng, 5), rand_entries(SPECS[name], 9, rng, 4)
+    g, o = pair(ctx, osym, [B, Cb], [B, Cb], 91)
+    gH, oH = g + g.adjoint(), o + o.adjoint()
+    gD, gV = gH.teigh()
+    oD, oV = oH.teigh()
+    assert gD.structure() == oD.structure() and gV.structure() == oV.structure()
+    lam = np.abs(oD.data).max()
+    assert np.abs(gD.download() - oD.data).max() < 1e-12 * lam * 10
+    rec = (gV @ gD).multiply(gV, False, True)
+    assert_same(rec, oH, 1e-11, "V D V^dagger")
+    one = gV.multiply(gV, True, False)
+    assert np.abs(one.download() - one.clone().setIdentity().download()).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1"])
+def test_tsvd_backward(ctxs, name):
+    """SVD reverse rule (include/Xped/AD/ADTensor.hpp:253-325,356-371) vs the oracle (which is pinned against finite
+    differences, tests/test_oracle_pins.py).  Adjoints are built from each side's own factors out of the same B, so the
+    comparison is independent of the sign gauge of the singular vectors."""
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(43)
+    b1, b2 = rand_entries(SPECS[name], 11, rng), rand_entries(SPECS[name], 8, rng)
+    out = [(q, d) for q, _, d in obasis(osym, b1).combine(obasis(osym, b2)).forgetHistory().data]
+    for dom, cod, seed, keep in [([b1, b2], [out], 101, 9), ([b1, b2], [b1, b2], 103, 12)]:
+        g, o = pair(ctx, osym, dom, cod, seed)
+        gB, oB = pair(ctx, osym, dom, cod, seed + 1)
+        gU, gS, gV = g.tSVD(keep, 0.0, False)
+        oU, oS, oV = o.tSVD(keep, 0.0, False)
+        assert gS.structure() == oS.structure()
+        g_dU, o_dU = gB.multiply(gV, False, True) @ gS, (oB @ oV.adjoint()) @ oS
+        g_dS, o_dS = gU.multiply(gB, True, False).multiply(gV, False, True), (oU.adjoint() @ oB) @ oV.adjoint()
+        g_dV, o_dV = gS @ gU.multiply(gB, True, False), oS @ (oU.adjoint() @ oB)
+        ggrad = g.tSVD_backward(gU, gS, gV, g_dU, g_dS, g_dV)
+        ograd = o.tSVD_backward(o_dU, o_dS, o_dV)
+        assert_same(ggrad, ograd, 1e-9, f"{name} tSVD_backward")
+        assert_same(g.tSVD_backward(gU, gS, gV, g_dU, None, None), o.tSVD_backward(o_dU, None, None), 1e-9, f"{name} tSVD_backward (dU only)")

@@ -243,3 +243,43 @@ def test_mps_contractions_equal_permute_formulation(name):
     Bn = contract_L(Bleft, T1, T2)
     assert Bn.structure() == Bcheck.structure()
     assert np.linalg.norm(Bn.data - Bcheck.data) <= 1e-12 * max(np.linalg.norm(Bcheck.data), 1.0)
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1"])
+def test_tsvd_backward_matches_finite_differences(name):
+    """tests/ad.cpp:421-590 shape: the SVD reverse rule against central finite differences of a gauge-invariant
+    function of the truncated factors, L(A) = <B, U_k S_k Vdag_k>_weighted (trace with sector degeneracies)."""
+    make, size = SYMS[name]
+    sym = make()
+    rng = np.random.default_rng(5)
+    b1, b2 = rand_basis(sym, size + 3, rng), rand_basis(sym, size, rng)
+    out = b1.combine(b2).forgetHistory()
+    A = Tensor(sym, [b1, b2], [out])                       # tall blocks: exercises the (1 - U U^dagger) correction
+    A.setRandom(rng)
+    B = A.like()
+    B.setRandom(rng)
+    keep = max(2, sum(min(A.block(i).shape) for i in range(len(A.sector))) // 2)
+
+    def loss(T):
+        U, S, Vd = T.tSVD(keep, 0.0, False)
+        return ((U @ S) @ Vd @ B.adjoint()).trace()
+
+    U, S, Vd = A.tSVD(keep, 0.0, False)
+    # dL/dX of L = sum_q deg(q) tr(B_q^T U S Vd): dU = deg B Vd^T S, dS = deg diag(U^T B Vd^T), dVd = deg S U^T B
+    dU, dS, dVd = U.like(), S.like(), Vd.like()
+    for j, q in enumerate(S.sector):
+        i = A.dict[q]
+        d = sym.degeneracy(q)
+        u, sm, vd, b = U.block(j), S.block(j), Vd.block(j), B.block(i)
+        dU.block(j)[...] = d * b @ vd.T @ sm
+        dS.block(j)[...] = d * np.diag(np.diag(u.T @ b @ vd.T))
+        dVd.block(j)[...] = d * sm @ u.T @ b
+    grad = A.tSVD_backward(dU, dS, dVd)
+    eps = 1e-6
+    idx = rng.choice(A.plainSize(), size=min(25, A.plainSize()), replace=False)
+    for e in idx:
+        Ap, Am = A.copy(), A.copy()
+        Ap.data[e] += eps
+        Am.data[e] -= eps
+        fd = (loss(Ap) - loss(Am)) / (2 * eps)
+        assert abs(fd - grad.data[e]) < 1e-6 * max(1.0, abs(fd)), (e, fd, grad.data[e])

@@ -235,6 +235,13 @@ void launch_set_identity(double* x, const BlockDesc* d_blocks, int nblocks, cuda
 void launch_diag_map(const double* src, double* dst, const BlockDesc* d_blocks, int nblocks, int op, cudaStream_t s);
 struct SubScale { long long off; int rows, cols, ld; double scale; };
 void launch_scale_subblocks(double* data, const SubScale* d_subs, int n, cudaStream_t s);
+// SVD reverse rule helpers (include/Xped/AD/ADTensor.hpp:253-325)
+struct DiagScaleDesc { long long off, s_off; int rows, cols, s_ld, by_cols; };
+// dst = (accumulate ? dst : 0) + src / s  with s taken per column (by_cols) or per row from the diagonal of an S block
+void launch_scale_by_diag(const double* src, double* dst, const double* S, const DiagScaleDesc* d_desc, int n, int accumulate, cudaStream_t s);
+// M = dS + (J + J^T) S + S (K + K^T) - G1 S^-1 - S^-1 G2^T,  J = F o G1, K = F o G2, F_ij = 1 / (s_j^2 - s_i^2) (regularised)
+void launch_svd_adjoint_core(const double* G1, const double* G2, const double* dS, const double* S, double* M, const BlockDesc* d_blocks, int nblocks,
+                             cudaStream_t s);
 void launch_trace(const double* src, const BlockDesc* d_blocks, int nblocks, double* d_out, cudaStream_t s);
 
 }   // namespace xb

@@ -9,11 +9,78 @@
 
 namespace xb {
 
-void Context::tqr(const Tensor&, Tensor**, Tensor**) { throw std::logic_error("tQR: not implemented yet"); }
-void Context::teigh(const Tensor&, Tensor**, Tensor**) { throw std::logic_error("teigh: not implemented yet"); }
-Tensor* Context::tsvd_backward(const Tensor&, const Tensor&, const Tensor&, const Tensor&, const Tensor*, const Tensor*, const Tensor*)
+// ------------------------------------------------------------------------------------------------ SVD reverse rule
+// Reverse pass of tSVD = full_svd_impl + cutoff_matrices (include/Xped/AD/ADTensor.hpp:253-325, 356-371).  The adjoints of
+// the truncated factors are padded into the full factors' adjoints (left columns / top-left corner / top rows) and
+//   dA = U (dS + (J+J^T) S + S (K+K^T)) V^+  +  (1 - U U^+) dU S^-1 V^+  +  U S^-1 dV^+ (1 - V V^+),   J = F o U^+dU, K = F o V^+dV
+// is evaluated as   dA = [U (M - G1 S^-1 - S^-1 G2^T) + dU S^-1] V^+ + U (S^-1 dV^+)   with G1 = U^+ dU, G2 = V^+ dV:
+// five grouped products and three elementwise kernels over all sectors at once.  The full factors are recomputed here
+// (the forward pass keeps only the truncated ones), like the reference's checkpointed replay does.
+Tensor* Context::tsvd_backward(const Tensor& A, const Tensor& U, const Tensor& S, const Tensor& Vd, const Tensor* dU, const Tensor* dS, const Tensor* dVd)
 {
-    throw std::logic_error("tsvd_backward: not implemented yet");
+    (void)U;
+    (void)S;
+    (void)Vd;
+    const Layout& LA = *A.layout;
+    SvdResult F = tsvd(A, INT64_MAX / 4, 0.0, false);
+    std::unique_ptr<Tensor> FU(F.U), FS(F.S), FV(F.Vd);
+    const Layout &LU = *FU->layout, &LS = *FS->layout, &LV = *FV->layout;
+    std::unique_ptr<Tensor> dFU(new Tensor(this, FU->layout, true)), dFS(new Tensor(this, FS->layout, true)), dFV(new Tensor(this, FV->layout, true));
+    auto pad = [&](const Tensor* src, Tensor& dst, const char* what) {
+        if(!src) return;
+        const Layout &Ls = *src->layout, &Ld = *dst.layout;
+        for(size_t j = 0; j < Ls.sector.size(); ++j) {
+            const int i = Ld.find(Ls.sector[j]);
+            if(i < 0) throw std::invalid_argument(std::string("tsvd_backward: sector of ") + what + " not present in the decomposition");
+            if(Ls.rows[j] > Ld.rows[i] || Ls.cols[j] > Ld.cols[i]) throw std::invalid_argument(std::string("tsvd_backward: block of ") + what + " too large");
+            if(Ls.rows[j] == 0 || Ls.cols[j] == 0) continue;
+            check_cuda(cudaMemcpy2DAsync(dst.d + Ld.off[i], sizeof(double) * Ld.rows[i], src->d + Ls.off[j], sizeof(double) * Ls.rows[j],
+                                         sizeof(double) * Ls.rows[j], static_cast<size_t>(Ls.cols[j]), cudaMemcpyDeviceToDevice, stream),
+                       "tsvd_backward pad");
+        }
+    };
+    pad(dU, *dFU, "dU");
+    pad(dS, *dFS, "dS");
+    pad(dVd, *dFV, "dVdag");
+    std::unique_ptr<Tensor> G1(multiply(*FU, true, *dFU, false)), G2(multiply(*FV, false, *dFV, true));
+    if(G1->layout->sector != LS.sector || G2->layout->sector != LS.sector || G1->layout->size != LS.size || G2->layout->size != LS.size)
+        throw std::logic_error("tsvd_backward: layout of U^+ dU differs from Sigma's");
+    const int nb = static_cast<int>(LS.sector.size());
+    std::vector<BlockDesc> bs(nb);
+    std::vector<DiagScaleDesc> du(nb), dv(nb);
+    for(int i = 0; i < nb; ++i) {
+        bs[i] = {LS.off[i], static_cast<int>(LS.rows[i]), static_cast<int>(LS.cols[i]), 1.0};
+        du[i] = {LU.off[i], LS.off[i], static_cast<int>(LU.rows[i]), static_cast<int>(LU.cols[i]), static_cast<int>(LS.rows[i]), 1};
+        dv[i] = {LV.off[i], LS.off[i], static_cast<int>(LV.rows[i]), static_cast<int>(LV.cols[i]), static_cast<int>(LS.rows[i]), 0};
+    }
+    const size_t b0 = sizeof(BlockDesc) * nb, b1 = sizeof(DiagScaleDesc) * nb;
+    char* d_meta = nullptr;
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_meta), b0 + 2 * b1, stream), "tsvd_backward meta");
+    upload_async(d_meta, bs.data(), b0);
+    upload_async(d_meta + b0, du.data(), b1);
+    upload_async(d_meta + b0 + b1, dv.data(), b1);
+    std::unique_ptr<Tensor> M(new Tensor(this, FS->layout, false));
+    launch_svd_adjoint_core(G1->d, G2->d, dFS->d, FS->d, M->d, reinterpret_cast<BlockDesc*>(d_meta), nb, stream);
+    std::unique_ptr<Tensor> X1(multiply(*FU, false, *M, false));
+    if(X1->layout->sector != LU.sector || X1->layout->size != LU.size) throw std::logic_error("tsvd_backward: layout of U*M differs from U's");
+    launch_scale_by_diag(dFU->d, X1->d, FS->d, reinterpret_cast<DiagScaleDesc*>(d_meta + b0), nb, 1, stream);   // X1 += dU S^-1
+    std::unique_ptr<Tensor> Z(new Tensor(this, FV->layout, false));
+    launch_scale_by_diag(dFV->d, Z->d, FS->d, reinterpret_cast<DiagScaleDesc*>(d_meta + b0 + b1), nb, 0, stream);   // Z = S^-1 dV^+
+    launches += 3;
+    check_cuda(cudaFreeAsync(d_meta, stream), "tsvd_backward meta free");
+    std::unique_ptr<Tensor> d1(multiply(*X1, false, *FV, false)), d2(multiply(*FU, false, *Z, false));
+    std::unique_ptr<Tensor> sum(axpby(1.0, *d1, 1.0, d2.get()));
+    if(sum->layout.get() == A.layout.get()) return sum.release();
+    // A was built with an explicit sector order (push_back): move the blocks into A's storage order
+    std::unique_ptr<Tensor> out(new Tensor(this, A.layout, true));
+    const Layout& Lsum = *sum->layout;
+    for(size_t i = 0; i < LA.sector.size(); ++i) {
+        const int j = Lsum.find(LA.sector[i]);
+        if(j < 0) continue;
+        check_cuda(cudaMemcpyAsync(out->d + LA.off[i], sum->d + Lsum.off[j], sizeof(double) * LA.rows[i] * LA.cols[i], cudaMemcpyDeviceToDevice, stream),
+                   "tsvd_backward relayout");
+    }
+    return out.release();
 }
 // ------------------------------------------------------------------------------------------------ MPS transfer contractions
 // contract_L (src/MPS/MpsContractions.cpp:11-51):  Bnew[Q] = sum_{tree (Qin,sigma)->Q} sum_s Bra_sub(s)^T * Bold[Qin] * Ket_sub(s).

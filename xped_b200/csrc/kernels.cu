@@ -465,3 +465,64 @@ void launch_set_identity(double* x, const BlockDesc* d_blocks, int nblocks, cuda
     check_cuda(cudaGetLastError(), "set_identity_kernel launch");
 }
 }   // namespace xb
+
+namespace xb {
+// ---- SVD reverse rule (include/Xped/AD/ADTensor.hpp:253-325), elementwise parts ------------------------------------
+__global__ void scale_by_diag_kernel(const double* __restrict__ src, double* __restrict__ dst, const double* __restrict__ S,
+                                     const DiagScaleDesc* __restrict__ descs, int n, int accumulate)
+{
+    for(int b = blockIdx.y; b < n; b += gridDim.y) {
+        const DiagScaleDesc d = descs[b];
+        const long long cnt = static_cast<long long>(d.rows) * d.cols;
+        const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+        for(long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < cnt; e += stride) {
+            const int r = static_cast<int>(e % d.rows), c = static_cast<int>(e / d.rows);
+            const int k = d.by_cols ? c : r;
+            const double v = src[d.off + e];
+            const double q = v == 0.0 ? 0.0 : v / S[d.s_off + k + static_cast<long long>(k) * d.s_ld];   // padded (zero) adjoints stay zero
+            dst[d.off + e] = accumulate ? dst[d.off + e] + q : q;
+        }
+    }
+}
+
+void launch_scale_by_diag(const double* src, double* dst, const double* S, const DiagScaleDesc* d_desc, int n, int accumulate, cudaStream_t s)
+{
+    if(n == 0) return;
+    dim3 grid(148, static_cast<unsigned>(n < 64 ? n : 64));
+    scale_by_diag_kernel<<<grid, 256, 0, s>>>(src, dst, S, d_desc, n, accumulate);
+    check_cuda(cudaGetLastError(), "scale_by_diag_kernel launch");
+}
+
+__global__ void svd_adjoint_core_kernel(const double* __restrict__ G1, const double* __restrict__ G2, const double* __restrict__ dS,
+                                        const double* __restrict__ S, double* __restrict__ M, const BlockDesc* __restrict__ blocks, int nblocks)
+{
+    for(int b = blockIdx.y; b < nblocks; b += gridDim.y) {
+        const BlockDesc d = blocks[b];
+        const int r = d.rows;
+        const long long cnt = static_cast<long long>(r) * r;
+        const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+        for(long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < cnt; e += stride) {
+            const int i = static_cast<int>(e % r), j = static_cast<int>(e / r);
+            const long long ij = d.off + e, ji = d.off + j + static_cast<long long>(i) * r;
+            const double si = S[d.off + i + static_cast<long long>(i) * r], sj = S[d.off + j + static_cast<long long>(j) * r];
+            const double dij = sj * sj - si * si;   // vec_diff: F_inv(i,j) = v(j) - v(i)
+            const double fij = fabs(dij) < 1.e-12 ? dij / (dij * dij + 1.e-12) : 1.0 / dij;
+            const double fji = -fij;                // F is antisymmetric (also in its regularised form)
+            const double g1ij = G1[ij], g1ji = G1[ji], g2ij = G2[ij], g2ji = G2[ji];
+            double m = dS[ij] + (fij * g1ij + fji * g1ji) * sj + si * (fij * g2ij + fji * g2ji);
+            if(g1ij != 0.0) m -= g1ij / sj;
+            if(g2ji != 0.0) m -= g2ji / si;
+            M[ij] = m;
+        }
+    }
+}
+
+void launch_svd_adjoint_core(const double* G1, const double* G2, const double* dS, const double* S, double* M, const BlockDesc* d_blocks, int nblocks,
+                             cudaStream_t s)
+{
+    if(nblocks == 0) return;
+    dim3 grid(148, static_cast<unsigned>(nblocks < 64 ? nblocks : 64));
+    svd_adjoint_core_kernel<<<grid, 256, 0, s>>>(G1, G2, dS, S, M, d_blocks, nblocks);
+    check_cuda(cudaGetLastError(), "svd_adjoint_core_kernel launch");
+}
+}   // namespace xb

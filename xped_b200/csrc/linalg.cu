@@ -39,17 +39,39 @@ struct SvdBlock
 
 struct SvdTask { int block, bi, bj; };
 
+// per-block diagonal shift 1.5 * ||A_q||_F for teigh: A_q + c_q 1 is positive definite with condition number <= 5
+__global__ void block_shift_kernel(const double* __restrict__ A, const long long* __restrict__ a_off, const SvdBlock* __restrict__ blocks, int nblocks,
+                                   double* __restrict__ shift)
+{
+    __shared__ double sm[256];
+    const int b = blockIdx.x;
+    const SvdBlock d = blocks[b];
+    const long long cnt = static_cast<long long>(d.rows) * d.cols;
+    double s = 0.0;
+    for(long long e = threadIdx.x; e < cnt; e += blockDim.x) s = fma(A[a_off[b] + e], A[a_off[b] + e], s);
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for(int o = 128; o > 0; o >>= 1) {
+        if(threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) shift[b] = 1.5 * sqrt(sm[0]);
+}
+
 __global__ void svd_init_kernel(const double* __restrict__ A, double* __restrict__ W, double* __restrict__ V, const SvdBlock* __restrict__ blocks,
-                                const long long* __restrict__ a_off, const int* __restrict__ a_rows, const int* __restrict__ transposed, int nblocks)
+                                const long long* __restrict__ a_off, const int* __restrict__ a_rows, const int* __restrict__ transposed, int nblocks,
+                                const double* __restrict__ shift)
 {
     for(int b = blockIdx.y; b < nblocks; b += gridDim.y) {
         const SvdBlock d = blocks[b];
         const long long cnt = static_cast<long long>(d.rows) * d.cols;
         const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
         const int lda = a_rows[b];
+        const double sh = shift ? shift[b] : 0.0;
         for(long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < cnt; e += stride) {
             const int r = static_cast<int>(e % d.rows), c = static_cast<int>(e / d.rows);
-            W[d.w_off + e] = transposed[b] ? A[a_off[b] + c + static_cast<long long>(r) * lda] : A[a_off[b] + r + static_cast<long long>(c) * lda];
+            const double a = transposed[b] ? A[a_off[b] + c + static_cast<long long>(r) * lda] : A[a_off[b] + r + static_cast<long long>(c) * lda];
+            W[d.w_off + e] = r == c ? a + sh : a;
         }
         const long long vc = static_cast<long long>(d.cols) * d.cols;
         for(long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < vc; e += stride)
@@ -282,13 +304,14 @@ struct JacobiResult
     std::vector<SvdBlock> blocks;
     std::vector<int> transposed;
     std::vector<double> sigma;   // host copy, per block at s_off
+    std::vector<double> shift;   // host copy of the per-block diagonal shift (teigh only)
     double* d_W = nullptr;
     double* d_V = nullptr;
     int sweeps = 0;
 };
 
 // One-sided block Jacobi on every sector block of `t`. Leaves W (= sigma_j u_j columns) and V on the device.
-JacobiResult jacobi_all(Context& ctx, const Tensor& t, const std::vector<double>* shift)
+JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
 {
     const Layout& L = *t.layout;
     const int nb = static_cast<int>(L.sector.size());
@@ -338,7 +361,8 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, const std::vector<double>
     o_tasks = (o_tasks + 15) & ~size_t(15);
     size_t o_sigma = o_tasks + sizeof(SvdTask) * flat.size();
     o_sigma = (o_sigma + 15) & ~size_t(15);
-    const size_t o_flag = o_sigma + sizeof(double) * soff;
+    const size_t o_shift = o_sigma + sizeof(double) * soff;
+    const size_t o_flag = o_shift + sizeof(double) * nb;
     const size_t meta_bytes = o_flag + 16;
     char* d_meta = nullptr;
     check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_meta), meta_bytes, s), "svd meta");
@@ -353,15 +377,20 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, const std::vector<double>
     auto* d_tasks = reinterpret_cast<SvdTask*>(d_meta + o_tasks);
     auto* d_sigma = reinterpret_cast<double*>(d_meta + o_sigma);
     auto* d_flag = reinterpret_cast<int*>(d_meta + o_flag);
+    auto* d_shift = reinterpret_cast<double*>(d_meta + o_shift);
 
     {
+        if(shifted) {
+            block_shift_kernel<<<nb, 256, 0, s>>>(t.d, reinterpret_cast<long long*>(d_meta + o_aoff), d_blocks, nb, d_shift);
+            check_cuda(cudaGetLastError(), "block_shift_kernel launch");
+            ++ctx.launches;
+        }
         dim3 grid(64, static_cast<unsigned>(std::min(nb, 64)));
         svd_init_kernel<<<grid, 256, 0, s>>>(t.d, R.d_W, R.d_V, d_blocks, reinterpret_cast<long long*>(d_meta + o_aoff),
-                                            reinterpret_cast<int*>(d_meta + o_arows), reinterpret_cast<int*>(d_meta + o_tr), nb);
+                                            reinterpret_cast<int*>(d_meta + o_arows), reinterpret_cast<int*>(d_meta + o_tr), nb, shifted ? d_shift : nullptr);
         check_cuda(cudaGetLastError(), "svd_init_kernel launch");
         ++ctx.launches;
     }
-    (void)shift;
     int* h_flag = static_cast<int*>(ctx.pinned(sizeof(int)));
     const int max_sweeps = 40;
     for(R.sweeps = 0; R.sweeps < max_sweeps; ++R.sweeps) {
@@ -390,6 +419,10 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, const std::vector<double>
         ++ctx.launches;
     }
     check_cuda(cudaMemcpyAsync(R.sigma.data(), d_sigma, sizeof(double) * soff, cudaMemcpyDeviceToHost, s), "sigma readback");
+    if(shifted) {
+        R.shift.resize(nb);
+        check_cuda(cudaMemcpyAsync(R.shift.data(), d_shift, sizeof(double) * nb, cudaMemcpyDeviceToHost, s), "shift readback");
+    }
     check_cuda(cudaStreamSynchronize(s), "svd sync");
     check_cuda(cudaFreeAsync(d_meta, s), "svd meta free");
     return R;
@@ -410,7 +443,7 @@ SvdResult Context::tsvd(const Tensor& t, int64_t max_keep, double eps_svd, bool 
     const Layout& L = *t.layout;
     if(L.sector.empty()) throw std::invalid_argument("tSVD: tensor has no blocks");
     ProfScope prof(*this, CAT_SVD, 0.0);
-    JacobiResult J = jacobi_all(*this, t, nullptr);
+    JacobiResult J = jacobi_all(*this, t, false);
     struct SV { int sector; int col; int k; double s; };
     std::vector<SV> all;
     for(size_t i = 0; i < L.sector.size(); ++i) {
@@ -501,6 +534,215 @@ SvdResult Context::tsvd(const Tensor& t, int64_t max_keep, double eps_svd, bool 
     check_cuda(cudaFreeAsync(d_cols, stream), "svd gather free");
     free_jacobi(*this, J);
     return res;
+}
+
+// ------------------------------------------------------------------------------------------------ teigh
+// Tensor::teigh (src/Core/Tensor.cpp:782-803; per block SelfAdjointEigenSolver, MatrixInterface_Eigen_impl.hpp).
+// Device form: every symmetric block is shifted to A_q + c_q 1 (c_q = 1.5 ||A_q||_F, positive definite), for which the
+// one-sided Jacobi SVD *is* the eigen-decomposition: W = (A + c) V, ||w_j|| = lambda_j + c.  Eigenvalues ascending
+// like LAPACK/Eigen; eigenvector signs are a gauge freedom.
+namespace {
+struct EighCol { long long v_src, v_dst, d_dst; int n; double lambda; };
+
+__global__ void eigh_gather_kernel(const double* __restrict__ V, double* __restrict__ Vout, double* __restrict__ D, const EighCol* __restrict__ cols, int n)
+{
+    for(int i = blockIdx.x; i < n; i += gridDim.x) {
+        const EighCol g = cols[i];
+        for(int r = threadIdx.x; r < g.n; r += blockDim.x) Vout[g.v_dst + r] = V[g.v_src + r];
+        if(threadIdx.x == 0) D[g.d_dst] = g.lambda;
+    }
+}
+}   // namespace
+
+void Context::teigh(const Tensor& t, Tensor** Do, Tensor** Vo)
+{
+    const Layout& L = *t.layout;
+    if(L.rank() != L.corank()) throw std::invalid_argument("teigh: Rank != CoRank");
+    for(size_t i = 0; i < L.sector.size(); ++i)
+        if(L.rows[i] != L.cols[i]) throw std::invalid_argument("teigh: blocks must be square (coupledDomain == coupledCodomain)");
+    BasisPtr md = L.cdom->forget_history(), mc = L.ccod->forget_history();
+    LayoutPtr LD = layout_custom({md}, {mc}, L.sector), LV = layout_custom(L.dom, {mc}, L.sector);
+    std::unique_ptr<Tensor> D(new Tensor(this, LD, true)), V(new Tensor(this, LV, false));
+    if(L.sector.empty() || L.size == 0) {
+        *Do = D.release();
+        *Vo = V.release();
+        return;
+    }
+    ProfScope prof(*this, CAT_SVD, 0.0);
+    JacobiResult J = jacobi_all(*this, t, true);
+    std::vector<EighCol> cols;
+    for(size_t i = 0; i < L.sector.size(); ++i) {
+        const SvdBlock& b = J.blocks[i];
+        const int n = b.cols;
+        std::vector<int> idx(n);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return J.sigma[b.s_off + x] < J.sigma[b.s_off + y]; });
+        for(int r = 0; r < n; ++r) {
+            EighCol g;
+            g.v_src = b.v_off + static_cast<long long>(idx[r]) * n;
+            g.v_dst = LV->off[i] + static_cast<long long>(r) * n;
+            g.d_dst = LD->off[i] + r + static_cast<long long>(r) * n;
+            g.n = n;
+            g.lambda = J.sigma[b.s_off + idx[r]] - J.shift[i];
+            cols.push_back(g);
+        }
+    }
+    if(!cols.empty()) {
+        EighCol* d_cols = nullptr;
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_cols), sizeof(EighCol) * cols.size(), stream), "eigh gather meta");
+        upload_async(d_cols, cols.data(), sizeof(EighCol) * cols.size());
+        eigh_gather_kernel<<<static_cast<unsigned>(std::min<size_t>(cols.size(), 2368)), 128, 0, stream>>>(J.d_V, V->d, D->d, d_cols, static_cast<int>(cols.size()));
+        check_cuda(cudaGetLastError(), "eigh_gather_kernel launch");
+        ++launches;
+        check_cuda(cudaFreeAsync(d_cols, stream), "eigh gather free");
+    }
+    free_jacobi(*this, J);
+    *Do = D.release();
+    *Vo = V.release();
+}
+
+// ------------------------------------------------------------------------------------------------ tQR
+// Tensor::tQR (src/Core/Tensor.cpp:757-780): per block HouseholderQR (MatrixInterface_Eigen_impl.hpp qr), thin factors
+// Q = Q_full * 1(m x n), R = 1(n x m) * R_full.  Device form: one CTA per sector block runs the unblocked Householder
+// recurrence with LAPACK's dlarfg sign convention (beta = -sign(alpha) ||x||, the one Eigen's makeHouseholder uses too), so
+// R's diagonal signs equal the reference's; the trailing update is spread over the CTA's warps (one column per warp,
+// lanes along the contiguous rows).  All blocks of a tensor run concurrently in one launch.
+namespace {
+struct QrBlock { long long a_off, q_off, r_off, w_off; int m, n; };
+
+__device__ double block_sum(double v, double* sm)
+{
+    for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for(int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) s += sm[w];   // fixed order: deterministic
+    return s;
+}
+
+__global__ void __launch_bounds__(256)
+qr_householder_kernel(const double* __restrict__ A, double* __restrict__ W, double* __restrict__ Qo, double* __restrict__ Ro, double* __restrict__ taus,
+                      const QrBlock* __restrict__ blocks)
+{
+    __shared__ double sm[8];
+    const QrBlock d = blocks[blockIdx.x];
+    const int m = d.m, n = d.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    double* __restrict__ w = W + d.w_off;       // m x n work copy, column-major
+    double* __restrict__ tau = taus + d.r_off;   // scratch slotted like R (n*n >= min(m, n) scalars per block)
+    const long long cnt = static_cast<long long>(m) * n;
+    for(long long e = tid; e < cnt; e += blockDim.x) w[e] = A[d.a_off + e];
+    __syncthreads();
+    const int kmax = m < n ? m : n;
+    for(int j = 0; j < kmax; ++j) {
+        double* __restrict__ x = w + j + static_cast<long long>(j) * m;
+        const int len = m - j;
+        double part = 0.0;
+        for(int r = 1 + tid; r < len; r += blockDim.x) part = fma(x[r], x[r], part);
+        const double tail = block_sum(part, sm);
+        const double alpha = x[0];
+        double beta = alpha, tj = 0.0, scale = 0.0;
+        if(tail > 0.0) {   // dlarfg; tail == 0  =>  H = 1
+            beta = -copysign(sqrt(alpha * alpha + tail), alpha);
+            tj = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        __syncthreads();
+        for(int r = 1 + tid; r < len; r += blockDim.x) x[r] *= scale;
+        if(tid == 0) {
+            x[0] = beta;
+            tau[j] = tj;
+        }
+        __syncthreads();
+        if(tj != 0.0) {
+            for(int k = j + 1 + warp; k < n; k += nwarp) {   // A[j:, k] -= tau v (v^T A[j:, k]),  v = (1, x[1:])
+                double* __restrict__ c = w + j + static_cast<long long>(k) * m;
+                double dot = lane == 0 ? c[0] : 0.0;
+                for(int r = 1 + lane; r < len; r += 32) dot = fma(x[r], c[r], dot);
+                for(int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                const double f = tj * dot;
+                if(lane == 0) c[0] -= f;
+                for(int r = 1 + lane; r < len; r += 32) c[r] = fma(-f, x[r], c[r]);
+            }
+        }
+        __syncthreads();
+    }
+    // R = 1(n x m) * R_full : n x n, rows >= min(m, n) are zero
+    double* __restrict__ R = Ro + d.r_off;
+    double* __restrict__ Q = Qo + d.q_off;
+    // Q = H_1 ... H_k * 1(m x n)  (dorg2r recurrence, backwards), built directly in the output block
+    for(long long e = tid; e < cnt; e += blockDim.x) {
+        const int r = static_cast<int>(e % m), c = static_cast<int>(e / m);
+        Q[e] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for(int j = kmax - 1; j >= 0; --j) {
+        const double tj = tau[j];
+        if(tj == 0.0) continue;   // uniform across the CTA
+        const double* __restrict__ x = w + j + static_cast<long long>(j) * m;
+        const int len = m - j;
+        for(int k = j + warp; k < n; k += nwarp) {
+            double* __restrict__ c = Q + j + static_cast<long long>(k) * m;
+            double dot = lane == 0 ? c[0] : 0.0;
+            for(int r = 1 + lane; r < len; r += 32) dot = fma(x[r], c[r], dot);
+            for(int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            const double f = tj * dot;
+            if(lane == 0) c[0] -= f;
+            for(int r = 1 + lane; r < len; r += 32) c[r] = fma(-f, x[r], c[r]);
+        }
+        __syncthreads();
+    }
+    for(long long e = tid; e < static_cast<long long>(n) * n; e += blockDim.x) {
+        const int r = static_cast<int>(e % n), c = static_cast<int>(e / n);
+        R[e] = (r <= c && r < m) ? w[r + static_cast<long long>(c) * m] : 0.0;
+    }
+}
+}   // namespace
+
+void Context::tqr(const Tensor& t, Tensor** Qo, Tensor** Ro)
+{
+    const Layout& L = *t.layout;
+    const bool tall = L.cdom->dim() > L.ccod->dim();
+    BasisPtr middle = tall ? L.ccod->forget_history() : L.cdom->forget_history();   // Tensor.cpp:760
+    for(size_t i = 0; i < L.sector.size(); ++i)
+        if(middle->inner_dim(L.sector[i]) != L.cols[i])
+            throw std::invalid_argument("tQR: a sector block is wider than tall while the middle basis is the domain -- the reference builds inconsistent "
+                                        "factors in this case (Tensor.cpp:766-776); permute the tensor so that every block has rows >= cols");
+    LayoutPtr LQ = layout_custom(L.dom, {middle}, L.sector), LR = layout_custom({middle}, L.cod, L.sector);
+    std::unique_ptr<Tensor> Q(new Tensor(this, LQ, false)), R(new Tensor(this, LR, true));
+    const int nb = static_cast<int>(L.sector.size());
+    if(nb == 0 || L.size == 0) {
+        *Qo = Q.release();
+        *Ro = R.release();
+        return;
+    }
+    std::vector<QrBlock> blocks;
+    for(int i = 0; i < nb; ++i) {
+        if(L.rows[i] == 0 || L.cols[i] == 0) continue;
+        QrBlock b;
+        b.a_off = L.off[i];
+        b.q_off = LQ->off[i];
+        b.r_off = LR->off[i];
+        b.w_off = L.off[i];
+        b.m = static_cast<int>(L.rows[i]);
+        b.n = static_cast<int>(L.cols[i]);
+        blocks.push_back(b);
+    }
+    ProfScope prof(*this, CAT_OTHER, 0.0);
+    double *d_W = nullptr, *d_tau = nullptr;
+    QrBlock* d_blocks = nullptr;
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_W), sizeof(double) * L.size, stream), "tQR work");
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_tau), sizeof(double) * std::max<int64_t>(LR->size, 1), stream), "tQR tau");
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_blocks), sizeof(QrBlock) * blocks.size(), stream), "tQR meta");
+    upload_async(d_blocks, blocks.data(), sizeof(QrBlock) * blocks.size());
+    qr_householder_kernel<<<static_cast<unsigned>(blocks.size()), 256, 0, stream>>>(t.d, d_W, Q->d, R->d, d_tau, d_blocks);
+    check_cuda(cudaGetLastError(), "qr_householder_kernel launch");
+    ++launches;
+    check_cuda(cudaFreeAsync(d_W, stream), "tQR free");
+    check_cuda(cudaFreeAsync(d_tau, stream), "tQR free");
+    check_cuda(cudaFreeAsync(d_blocks, stream), "tQR free");
+    *Qo = Q.release();
+    *Ro = R.release();
 }
 
 }   // namespace xb

@@ -87,135 +87,224 @@ __device__ __forceinline__ void panel_pair(int step, int g, int& p, int& q)
         a = SP - 1;
         b = step;
     } else {
-        a = (step + g) % (SP - 1);
-        b = (step - g + (SP - 1)) % (SP - 1);
+        a = step + g;
+        if(a >= SP - 1) a -= SP - 1;
+        b = step - g;
+        if(b < 0) b += SP - 1;
     }
     p = a < b ? a : b;
     q = a < b ? b : a;
 }
 
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Jacobi rotation that annihilates g_pq of [[a, c], [c, b]]; false if the pair is already orthogonal to `tol`.
+__device__ __forceinline__ bool jacobi_rotation(double a, double b, double c, double tol2, double& cs, double& sn)
+{
+    cs = 1.0;
+    sn = 0.0;
+    if(!(a > 0.0 && b > 0.0 && c * c > tol2 * a * b)) return false;
+    const double zeta = (b - a) / (2.0 * c);
+    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    cs = rsqrt(1.0 + t * t);
+    sn = cs * t;
+    return true;
+}
+
+constexpr int XS_LD = SCH + 4;   // == 4 mod 16: the DMMA fragment loads of both operand roles hit 16 distinct banks per half-warp
+constexpr int VL_LD = SP + 4;
+constexpr int SVD_MAX_INNER = 8;
+
+// One round of the block one-sided Jacobi method: every (sector block, column-block pair) of the round is handled by a
+// cluster of CL CTAs that split the rows.  Phase 1: Gram matrix G = X^T X of the 32-column panel on the FP64 tensor
+// cores (partial sums exchanged through distributed shared memory, summed in a fixed order so that all CTAs of the
+// cluster hold bit-identical G).  Phase 2: cyclic two-sided Jacobi on G in shared memory -- thread (k, l) owns the 2x2
+// intersection of rotation pair k's rows and pair l's columns, so a step needs only two barriers; every CTA of the
+// cluster runs it redundantly (deterministic => identical rotations).  Phase 3: X <- X Vl and V <- V Vl on the tensor
+// cores for this CTA's row slices.
+template <int CL>
 __global__ void __launch_bounds__(SVD_THREADS)
 svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock* __restrict__ blocks, const SvdTask* __restrict__ tasks, int* __restrict__ rotated)
 {
-    __shared__ double G[SP][SP + 1];
-    __shared__ double Vl[SP][SP + 1];
-    __shared__ double Xs[SP][SCH + 1];
+    __shared__ __align__(16) double Xs[SP][XS_LD];
+    __shared__ __align__(16) double G[SP][SP + 1];
+    __shared__ __align__(16) double Vl[SP][VL_LD];
+    __shared__ __align__(16) double Gpart[SP][SP];   // this CTA's partial Gram matrix (read by the cluster peers)
     __shared__ int colidx[SP];
-    __shared__ int s_any, s_total;
 
-    const int tid = threadIdx.x;
-    const SvdTask task = tasks[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned crank = 0;
+    if(CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const SvdTask task = tasks[blockIdx.x / CL];
     const SvdBlock blk = blocks[task.block];
     if(tid < SP) {
         int c = tid < SB ? task.bi * SB + tid : (task.bj >= 0 ? task.bj * SB + (tid - SB) : -1);
         if(c >= blk.cols) c = -1;
         colidx[tid] = c;
     }
-    if(tid == 0) s_total = 0;
     __syncthreads();
 
-    // ---- Gram matrix of the panel
+    // row slices of this CTA (multiples of SCH so that chunks never straddle CTAs)
+    auto slice = [&](int nrows, int& lo, int& hi) {
+        const int chunks = (nrows + SCH - 1) / SCH;
+        const int per = (chunks + CL - 1) / CL;
+        lo = min(nrows, static_cast<int>(crank) * per * SCH);
+        hi = min(nrows, (static_cast<int>(crank) + 1) * per * SCH);
+    };
+    auto load_chunk = [&](const double* __restrict__ M, int nrows, int r0) {
+        // 64 rows x 32 columns; a warp reads 32 consecutive rows of one column (256 B, coalesced)
+#pragma unroll
+        for(int it = 0; it < (SP * SCH) / SVD_THREADS; ++it) {
+            const int e = tid + it * SVD_THREADS;
+            const int col = e / SCH, row = e % SCH;
+            const int gr = r0 + row, gc = colidx[col];
+            Xs[col][row] = (gc >= 0 && gr < nrows) ? M[gr + static_cast<long long>(gc) * nrows] : 0.0;
+        }
+    };
+
+    // ---- phase 1: Gram matrix. warp w owns output tiles (ti = w/2, tj = 2*(w&1) + {0,1}) of the 4x4 grid of 8x8 tiles
     {
-        const int i = tid & 31, j0 = (tid >> 5) * 4;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for(int r0 = 0; r0 < blk.rows; r0 += SCH) {
-            for(int e = tid; e < SP * SCH; e += SVD_THREADS) {
-                const int col = e / SCH, row = e % SCH;
-                const int gr = r0 + row, gc = colidx[col];
-                Xs[col][row] = (gc >= 0 && gr < blk.rows) ? W[blk.w_off + gr + static_cast<long long>(gc) * blk.rows] : 0.0;
-            }
+        const int ti = warp >> 1, tj0 = (warp & 1) * 2;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        int lo, hi;
+        slice(blk.rows, lo, hi);
+        const double* __restrict__ Wm = W + blk.w_off;
+        for(int r0 = lo; r0 < hi; r0 += SCH) {
+            load_chunk(Wm, blk.rows, r0);
             __syncthreads();
-#pragma unroll 8
-            for(int row = 0; row < SCH; ++row) {
-                const double xi = Xs[i][row];
+#pragma unroll 4
+            for(int k0 = 0; k0 < SCH; k0 += 4) {
+                const double a = Xs[ti * 8 + (lane >> 2)][k0 + (lane & 3)];
 #pragma unroll
-                for(int k = 0; k < 4; ++k) acc[k] = fma(xi, Xs[j0 + k][row], acc[k]);
+                for(int j = 0; j < 2; ++j) {
+                    const double b = Xs[(tj0 + j) * 8 + (lane >> 2)][k0 + (lane & 3)];
+                    dmma_8x8x4(acc[j][0], acc[j][1], a, b);
+                }
             }
             __syncthreads();
         }
 #pragma unroll
-        for(int k = 0; k < 4; ++k) G[i][j0 + k] = acc[k];
-        for(int e = tid; e < SP * SP; e += SVD_THREADS) Vl[e / SP][e % SP] = (e / SP == e % SP) ? 1.0 : 0.0;
+        for(int j = 0; j < 2; ++j) {
+            const int r = ti * 8 + (lane >> 2), c = (tj0 + j) * 8 + 2 * (lane & 3);
+            Gpart[r][c] = acc[j][0];
+            Gpart[r][c + 1] = acc[j][1];
+        }
     }
-    __syncthreads();
-
-    // ---- cyclic Jacobi on G (two-sided), rotations accumulated in Vl
-    const int grp = tid >> 4, l = tid & 15;
-    for(int sweep = 0; sweep < 10; ++sweep) {
-        if(tid == 0) s_any = 0;
+    if(CL > 1) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    } else {
         __syncthreads();
+    }
+    for(int e = tid; e < SP * SP; e += SVD_THREADS) {
+        const int r = e / SP, c = e % SP;
+        double sum = 0.0;
+        if(CL > 1) {
+            const unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(&Gpart[r][c]));
+#pragma unroll
+            for(int cr = 0; cr < CL; ++cr) {   // fixed order: bit-identical in every CTA of the cluster
+                unsigned remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(cr));
+                double v;
+                asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+                sum += v;
+            }
+        } else {
+            sum = Gpart[r][c];
+        }
+        G[r][c] = sum;
+        Vl[r][c] = (r == c) ? 1.0 : 0.0;
+    }
+    if(CL > 1) {   // peers must not exit (or overwrite Gpart) before everybody has read it
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    } else {
+        __syncthreads();
+    }
+
+    // ---- phase 2: cyclic two-sided Jacobi on G; thread (k, l) owns rows {p_k, q_k} x columns {p_l, q_l}
+    const int k = tid >> 4, l = tid & 15;
+    const double tol2 = blk.tol * blk.tol;
+    int total = 0;
+    for(int sweep = 0; sweep < SVD_MAX_INNER; ++sweep) {
+        int any = 0;
         for(int step = 0; step < SP - 1; ++step) {
-            int p, q;
-            panel_pair(step, grp, p, q);
-            const double a = G[p][p], b = G[q][q], c = G[p][q];
-            double cs = 1.0, sn = 0.0;
-            const bool rot = (a > 0.0 && b > 0.0 && fabs(c) > blk.tol * sqrt(a * b));
-            if(rot) {
-                const double zeta = (b - a) / (2.0 * c);
-                const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                cs = 1.0 / sqrt(1.0 + t * t);
-                sn = cs * t;
-            }
-            __syncthreads();   // everybody has read its pivots
-            if(rot) {
-                if(l == 0) s_any = 1;
-#pragma unroll
-                for(int h = 0; h < 2; ++h) {   // columns p, q of G and Vl
-                    const int r = l + 16 * h;
-                    const double gp = G[r][p], gq = G[r][q];
-                    G[r][p] = cs * gp - sn * gq;
-                    G[r][q] = sn * gp + cs * gq;
-                    const double vp = Vl[r][p], vq = Vl[r][q];
-                    Vl[r][p] = cs * vp - sn * vq;
-                    Vl[r][q] = sn * vp + cs * vq;
+            int pk, qk, pl, ql;
+            panel_pair(step, k, pk, qk);
+            panel_pair(step, l, pl, ql);
+            double ck, sk, cl, sl;
+            const bool rk = jacobi_rotation(G[pk][pk], G[qk][qk], G[pk][qk], tol2, ck, sk);
+            const bool rl = jacobi_rotation(G[pl][pl], G[ql][ql], G[pl][ql], tol2, cl, sl);
+            any |= rk ? 1 : 0;
+            // G <- J^T G J on the owned 2x2 block
+            const double g00 = G[pk][pl], g01 = G[pk][ql], g10 = G[qk][pl], g11 = G[qk][ql];
+            // Vl <- Vl J: rows k and k + 16, columns {p_l, q_l}
+            const double v0p = Vl[k][pl], v0q = Vl[k][ql], v1p = Vl[k + 16][pl], v1q = Vl[k + 16][ql];
+            __syncthreads();   // everybody has read the old values
+            if(rk || rl) {
+                // columns: g[:, p] = c g[:, p] - s g[:, q];  g[:, q] = s g[:, p] + c g[:, q]
+                const double h00 = cl * g00 - sl * g01, h01 = sl * g00 + cl * g01;
+                const double h10 = cl * g10 - sl * g11, h11 = sl * g10 + cl * g11;
+                // rows: g[p, :] = c g[p, :] - s g[q, :];  g[q, :] = s g[p, :] + c g[q, :]
+                double n00 = ck * h00 - sk * h10, n01 = ck * h01 - sk * h11;
+                double n10 = sk * h00 + ck * h10, n11 = sk * h01 + ck * h11;
+                if(k == l && rk) {   // the pivot block itself: off-diagonal annihilated exactly
+                    n01 = 0.0;
+                    n10 = 0.0;
                 }
+                G[pk][pl] = n00;
+                G[pk][ql] = n01;
+                G[qk][pl] = n10;
+                G[qk][ql] = n11;
             }
-            __syncthreads();
-            if(rot) {
-#pragma unroll
-                for(int h = 0; h < 2; ++h) {   // rows p, q of G
-                    const int r = l + 16 * h;
-                    const double gp = G[p][r], gq = G[q][r];
-                    G[p][r] = cs * gp - sn * gq;
-                    G[q][r] = sn * gp + cs * gq;
-                }
+            if(rl) {
+                Vl[k][pl] = cl * v0p - sl * v0q;
+                Vl[k][ql] = sl * v0p + cl * v0q;
+                Vl[k + 16][pl] = cl * v1p - sl * v1q;
+                Vl[k + 16][ql] = sl * v1p + cl * v1q;
             }
             __syncthreads();
         }
-        if(tid == 0 && s_any) s_total = 1;
-        const int any = s_any;
-        __syncthreads();
+        any = __syncthreads_or(any);
         if(!any) break;
+        total = 1;
     }
-    if(!s_total) return;   // panel already orthogonal: nothing to update
-    if(tid == 0) atomicExch(rotated, 1);
+    if(!total) return;   // panel already orthogonal (uniform over the cluster: identical G everywhere)
+    if(tid == 0 && crank == 0) atomicExch(rotated, 1);
 
-    // ---- panel updates  X <- X * Vl  for W (rows) and V (cols)
+    // ---- phase 3: X <- X * Vl for this CTA's rows of W and of V. warp w owns 8 rows of the 64-row chunk, all 32 columns.
     for(int which = 0; which < 2; ++which) {
         double* __restrict__ M = which == 0 ? W + blk.w_off : V + blk.v_off;
         const int nrows = which == 0 ? blk.rows : blk.cols;
-        const int row = tid & (SCH - 1), c0 = (tid >> 6) * 8;
-        for(int r0 = 0; r0 < nrows; r0 += SCH) {
-            for(int e = tid; e < SP * SCH; e += SVD_THREADS) {
-                const int col = e / SCH, rr = e % SCH;
-                const int gr = r0 + rr, gc = colidx[col];
-                Xs[col][rr] = (gc >= 0 && gr < nrows) ? M[gr + static_cast<long long>(gc) * nrows] : 0.0;
-            }
+        int lo, hi;
+        slice(nrows, lo, hi);
+        for(int r0 = lo; r0 < hi; r0 += SCH) {
+            load_chunk(M, nrows, r0);
             __syncthreads();
-            double out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 4
-            for(int k = 0; k < SP; ++k) {
-                const double x = Xs[k][row];
+            double out[4][2];
 #pragma unroll
-                for(int c = 0; c < 8; ++c) out[c] = fma(x, Vl[k][c0 + c], out[c]);
+            for(int j = 0; j < 4; ++j) out[j][0] = out[j][1] = 0.0;
+#pragma unroll
+            for(int k0 = 0; k0 < SP; k0 += 4) {
+                const double a = Xs[k0 + (lane & 3)][warp * 8 + (lane >> 2)];   // A[row][k] = X[row][k]
+#pragma unroll
+                for(int j = 0; j < 4; ++j) {
+                    const double b = Vl[k0 + (lane & 3)][j * 8 + (lane >> 2)];   // B[k][col] = Vl[k][col]
+                    dmma_8x8x4(out[j][0], out[j][1], a, b);
+                }
             }
-            const int gr = r0 + row;
+            const int gr = r0 + warp * 8 + (lane >> 2);
             if(gr < nrows) {
 #pragma unroll
-                for(int c = 0; c < 8; ++c) {
-                    const int gc = colidx[c0 + c];
-                    if(gc >= 0) M[gr + static_cast<long long>(gc) * nrows] = out[c];
-                }
+                for(int j = 0; j < 4; ++j)
+#pragma unroll
+                    for(int h = 0; h < 2; ++h) {
+                        const int gc = colidx[j * 8 + 2 * (lane & 3) + h];
+                        if(gc >= 0) M[gr + static_cast<long long>(gc) * nrows] = out[j][h];
+                    }
             }
             __syncthreads();
         }
@@ -392,13 +481,33 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         ++ctx.launches;
     }
     int* h_flag = static_cast<int*>(ctx.pinned(sizeof(int)));
+    int max_rows = 0;
+    for(const SvdBlock& b : R.blocks) max_rows = std::max(max_rows, b.rows);
+    const int cluster = max_rows > 2 * SCH ? 4 : 1;   // split the rows of a panel over a 4-CTA cluster once there are enough of them
     const int max_sweeps = 40;
     for(R.sweeps = 0; R.sweeps < max_sweeps; ++R.sweeps) {
         check_cuda(cudaMemsetAsync(d_flag, 0, sizeof(int), s), "svd flag reset");
         for(size_t r = 0; r + 1 < round_begin.size(); ++r) {
             const int cnt = round_begin[r + 1] - round_begin[r];
             if(cnt == 0) continue;
-            svd_round_kernel<<<cnt, SVD_THREADS, 0, s>>>(R.d_W, R.d_V, d_blocks, d_tasks + round_begin[r], d_flag);
+            if(cluster > 1) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(static_cast<unsigned>(cnt) * cluster);
+                cfg.blockDim = dim3(SVD_THREADS);
+                cfg.stream = s;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = cluster;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                check_cuda(cudaLaunchKernelEx(&cfg, svd_round_kernel<4>, R.d_W, R.d_V, static_cast<const SvdBlock*>(d_blocks),
+                                              static_cast<const SvdTask*>(d_tasks + round_begin[r]), d_flag),
+                           "svd_round_kernel<4> launch");
+            } else {
+                svd_round_kernel<1><<<cnt, SVD_THREADS, 0, s>>>(R.d_W, R.d_V, d_blocks, d_tasks + round_begin[r], d_flag);
+            }
             ++ctx.launches;
         }
         check_cuda(cudaGetLastError(), "svd_round_kernel launch");

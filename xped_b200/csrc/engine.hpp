@@ -41,7 +41,7 @@ constexpr int PERM_MAXLEG = 8;
 constexpr int PERM_TILE_ELEMS = 2048;   // doubles per tile (16 KiB of payload)
 constexpr int PERM_BUF_ELEMS = 3072;    // shared buffer incl. bank-conflict padding
 constexpr int PERM_THREADS = 256;
-constexpr int PERM_ITER = PERM_TILE_ELEMS / PERM_THREADS;
+constexpr int PERM_STRIP = 8;   // longest per-thread strip
 
 struct PermTask   // one destination sub-block (target tree pair) = sum_k coeff_k * transpose(src_k)
 {
@@ -60,6 +60,13 @@ struct PermTask   // one destination sub-block (target tree pair) = sum_k coeff_
     int tl_d[PERM_MAXLEG];           // tile legs in dst order
     int tl_s[PERM_MAXLEG];           // tile legs in src order
     unsigned magic[PERM_MAXLEG];     // ceil(2^32 / w[leg]) for fast division by the tile extent
+    // Thread work items of the two phases.  An item is (x along the fastest tile leg of that side, a strip of <= L
+    // consecutive indices of the second-fastest tile leg, the remaining tile legs): lanes run along the contiguous
+    // leg, every thread walks its strip with constant address increments, so the mixed-radix index decomposition is
+    // paid once per strip instead of once per element.
+    int strip_s, nchunk_s, items_s;   // read phase (source order)
+    int strip_d, nchunk_d, items_d;   // write phase (destination order)
+    unsigned magic_chunk_s, magic_chunk_d;
 };
 
 struct PermSrc
@@ -84,7 +91,7 @@ struct PermutePlan
     ~PermutePlan();
 };
 
-constexpr int GEMM_TILE_M = 64, GEMM_TILE_N = 64;   // CTA tile of gemm_grouped_kernel
+constexpr int GEMM_TILE_N = 64;   // CTA tile of gemm_grouped_kernel is tile_m x 64 with tile_m = 128 (large sectors) or 64
 
 struct GemmItem   // one (sector, tile) of a grouped product
 {
@@ -222,7 +229,7 @@ struct ProfScope
 
 // ---- kernel launchers (kernels.cu) ----
 void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s);
-void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, cudaStream_t s);
+void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, int tile_m, cudaStream_t s);
 void launch_scale_copy(const double* x, double* y, double alpha, int64_t n, cudaStream_t s);
 void launch_axpby(const double* x, const double* y, double* z, double alpha, double beta, int64_t n, cudaStream_t s);
 void launch_absmax(const double* x, int64_t n, double* d_out, cudaStream_t s);

@@ -18,6 +18,51 @@
 namespace xb {
 
 // ================================================================================================ permute
+// Decompose work item `it` of one phase: x along the fastest tile leg `order[0]`, strip start c1 along `order[1]`, the
+// other tile legs; returns false if the item lies outside the (clipped) tile.  `stride` holds the global strides of the
+// side being addressed (source strides in the read phase, destination strides in the write phase).
+__device__ __forceinline__ bool perm_item(const PermTask& T, const int* __restrict__ order, const int* __restrict__ stride, const int* __restrict__ lim,
+                                          int nchunk, unsigned magic_chunk, int strip, int it, int& off, int& pos, int& cnt, int& gstep, int& sstep)
+{
+    const int ntl = T.ntl;
+    if(ntl == 0) {
+        off = 0;
+        pos = 0;
+        cnt = 1;
+        gstep = sstep = 0;
+        return true;
+    }
+    const int la = order[0];
+    int r = __umulhi(static_cast<unsigned>(it), T.magic[la]);
+    const int x = it - r * T.w[la];
+    bool ok = x < lim[la];
+    off = x * stride[la];
+    pos = x * T.smstride[la];
+    cnt = 1;
+    gstep = sstep = 0;
+    if(ntl >= 2) {
+        const int lb = order[1];
+        int q = nchunk > 1 ? __umulhi(static_cast<unsigned>(r), magic_chunk) : 0;
+        const int c1 = (r - q * nchunk) * strip;
+        r = q;
+        cnt = min(strip, lim[lb] - c1);
+        gstep = stride[lb];
+        sstep = T.smstride[lb];
+        off += c1 * gstep;
+        pos += c1 * sstep;
+        for(int j = 2; j < ntl; ++j) {
+            const int l = order[j];
+            q = __umulhi(static_cast<unsigned>(r), T.magic[l]);
+            const int c = r - q * T.w[l];
+            r = q;
+            ok = ok && (c < lim[l]);
+            off += c * stride[l];
+            pos += c * T.smstride[l];
+        }
+    }
+    return ok && cnt > 0;
+}
+
 __global__ void __launch_bounds__(PERM_THREADS)
 permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const PermTask* __restrict__ tasks,
                const PermSrc* __restrict__ srcs, const PermTile* __restrict__ tiles)
@@ -36,82 +81,62 @@ permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const P
         for(int i = tid; i < static_cast<int>(sizeof(PermTask) / sizeof(int)); i += PERM_THREADS) s[i] = g[i];
     }
     __syncthreads();
-    if(tid == 0) {
-        int r = tile.tile;
-        for(int l = 0; l < T.nleg; ++l) {
+    if(tid < PERM_MAXLEG) {
+        int r = tile.tile, b = 0, lim = 1;
+        for(int l = 0; l <= tid && l < T.nleg; ++l) {
             const int c = r % T.ntile[l];
             r /= T.ntile[l];
-            const int b = c * T.w[l];
-            s_base[l] = b;
-            s_lim[l] = min(T.w[l], T.dims[l] - b);
+            b = c * T.w[l];
+            lim = min(T.w[l], T.dims[l] - b);
+        }
+        s_base[tid] = tid < T.nleg ? b : 0;
+        s_lim[tid] = tid < T.nleg ? lim : 1;
+    }
+    __syncthreads();
+
+    // ---- read phase: buf = sum_k coeff_k * src_k tile, addressed in source order (lanes along the source-contiguous leg).
+    // The item -> thread map does not depend on k, so the same thread owns the same buf element for every source and the
+    // fan-in accumulates in shared memory without barriers in between.
+    for(int k = 0; k < T.src_count; ++k) {
+        __syncthreads();   // S of the previous source no longer needed
+        if(tid < static_cast<int>(sizeof(PermSrc) / sizeof(int))) reinterpret_cast<int*>(&S)[tid] = reinterpret_cast<const int*>(srcs + T.src_begin + k)[tid];
+        __syncthreads();
+        long long sbase = S.off;
+        for(int l = 0; l < T.nleg; ++l) sbase += static_cast<long long>(s_base[l]) * S.sstride[l];
+        const double* __restrict__ sp = src + sbase;
+        const double coeff = S.coeff;
+        for(int it = tid; it < T.items_s; it += PERM_THREADS) {
+            int off, pos, cnt, gstep, sstep;
+            if(!perm_item(T, T.tl_s, S.sstride, s_lim, T.nchunk_s, T.magic_chunk_s, T.strip_s, it, off, pos, cnt, gstep, sstep)) continue;
+            double v[PERM_STRIP];
+#pragma unroll
+            for(int i = 0; i < PERM_STRIP; ++i)
+                if(i < cnt) v[i] = __ldg(sp + off + i * gstep);
+            if(k == 0) {
+#pragma unroll
+                for(int i = 0; i < PERM_STRIP; ++i)
+                    if(i < cnt) buf[pos + i * sstep] = coeff * v[i];
+            } else {
+#pragma unroll
+                for(int i = 0; i < PERM_STRIP; ++i)
+                    if(i < cnt) buf[pos + i * sstep] = fma(coeff, v[i], buf[pos + i * sstep]);
+            }
         }
     }
     __syncthreads();
 
-    const int ntl = T.ntl;
-    const int vol = T.vol;
+    // ---- write phase: destination order (lanes along the destination-contiguous leg); every element written once
     long long dbase = T.dst_off;
     for(int l = 0; l < T.nleg; ++l) dbase += static_cast<long long>(s_base[l]) * T.dstride[l];
-
-    // write-out coordinates of this thread's elements (fixed for all sources)
-    int d_off[PERM_ITER];
-    int d_pos[PERM_ITER];   // shared-memory position, -1 if outside the tile / tensor
-    double acc[PERM_ITER];
-#pragma unroll
-    for(int it = 0; it < PERM_ITER; ++it) {
-        int e = tid + it * PERM_THREADS;
-        int off = 0, pos = 0;
-        bool ok = e < vol;
-        for(int j = 0; j < ntl; ++j) {
-            const int l = T.tl_d[j];
-            const int q = __umulhi(static_cast<unsigned>(e), T.magic[l]);
-            const int c = e - q * T.w[l];
-            e = q;
-            ok = ok && (c < s_lim[l]);
-            off += c * T.dstride[l];
-            pos += c * T.smstride[l];
-        }
-        d_off[it] = off;
-        d_pos[it] = ok ? pos : -1;
-        acc[it] = 0.0;
-    }
-
-    for(int k = 0; k < T.src_count; ++k) {
-        if(tid < static_cast<int>(sizeof(PermSrc) / sizeof(int))) {
-            reinterpret_cast<int*>(&S)[tid] = reinterpret_cast<const int*>(srcs + T.src_begin + k)[tid];
-        }
-        __syncthreads();   // S visible; also: previous round's reads of buf are complete
-        long long sbase = S.off;
-        for(int l = 0; l < T.nleg; ++l) sbase += static_cast<long long>(s_base[l]) * S.sstride[l];
-        const double* __restrict__ sp = src + sbase;
-#pragma unroll
-        for(int it = 0; it < PERM_ITER; ++it) {
-            int e = tid + it * PERM_THREADS;
-            if(e < vol) {
-                int off = 0, pos = 0;
-                bool ok = true;
-                for(int j = 0; j < ntl; ++j) {
-                    const int l = T.tl_s[j];
-                    const int q = __umulhi(static_cast<unsigned>(e), T.magic[l]);
-                    const int c = e - q * T.w[l];
-                    e = q;
-                    ok = ok && (c < s_lim[l]);
-                    off += c * S.sstride[l];
-                    pos += c * T.smstride[l];
-                }
-                if(ok) buf[pos] = __ldg(sp + off);
-            }
-        }
-        __syncthreads();
-        const double coeff = S.coeff;
-#pragma unroll
-        for(int it = 0; it < PERM_ITER; ++it)
-            if(d_pos[it] >= 0) acc[it] = fma(coeff, buf[d_pos[it]], acc[it]);
-    }
     double* __restrict__ dp = dst + dbase;
+    const bool zero = T.src_count == 0;
+    for(int it = tid; it < T.items_d; it += PERM_THREADS) {
+        int off, pos, cnt, gstep, sstep;
+        if(!perm_item(T, T.tl_d, T.dstride, s_lim, T.nchunk_d, T.magic_chunk_d, T.strip_d, it, off, pos, cnt, gstep, sstep)) continue;
 #pragma unroll
-    for(int it = 0; it < PERM_ITER; ++it)
-        if(d_pos[it] >= 0) dp[d_off[it]] = acc[it];
+        for(int i = 0; i < PERM_STRIP; ++i)
+            if(i < cnt) dp[off + i * gstep] = zero ? 0.0 : buf[pos + i * sstep];
+    }
 }
 
 void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s)
@@ -119,110 +144,6 @@ void launch_permute(const double* src, double* dst, const PermutePlan& plan, cud
     if(plan.n_tiles == 0) return;
     permute_kernel<<<plan.n_tiles, PERM_THREADS, 0, s>>>(src, dst, plan.d_tasks, plan.d_srcs, plan.d_tiles);
     check_cuda(cudaGetLastError(), "permute_kernel launch");
-}
-
-// ================================================================================================ grouped DGEMM
-// CTA tile 64x64, K step 16, 4 warps in a 2x2 grid, each warp 32x32 = 4x4 DMMA m8n8k4 tiles.
-constexpr int GM = 64, GN = 64, GK = 16, GEMM_THREADS = 128;
-constexpr int GPAD = 4;   // keeps fragment loads spread over banks
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-__global__ void __launch_bounds__(GEMM_THREADS)
-gemm_grouped_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, const GemmItem* __restrict__ items)
-{
-    // As[k][m], Bs[k][n]: k-major so that the m8n8k4 fragments (A: row=lane/4, k=lane%4; B: k=lane%4, col=lane/4)
-    // are read with lane-varying m/n (conflict-free) for a fixed k.
-    __shared__ double As[2][GK][GM + GPAD];
-    __shared__ double Bs[2][GK][GN + GPAD];
-
-    const GemmItem it = items[blockIdx.x];
-    const double* __restrict__ Ap = A + it.a_off;
-    const double* __restrict__ Bp = B + it.b_off;
-    double* __restrict__ Cp = C + it.c_off;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
-    const int m0 = it.tm, n0 = it.tn;
-
-    double acc[4][4][2];
-#pragma unroll
-    for(int i = 0; i < 4; ++i)
-#pragma unroll
-        for(int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    // global -> shared loaders: A tile is 64(m) x 16(k), B tile is 16(k) x 64(n); 1024 elements each, 8 per thread
-    auto load_tiles = [&](int buf, int k0) {
-#pragma unroll
-        for(int r = 0; r < (GM * GK) / GEMM_THREADS; ++r) {
-            const int e = tid + r * GEMM_THREADS;
-            // A: op(A)[m][k]; stored column-major (m fastest) unless transposed
-            int mm, kk;
-            if(!it.ta) { mm = e % GM; kk = e / GM; } else { kk = e % GK; mm = e / GK; }
-            const int gm = m0 + mm, gk = k0 + kk;
-            double v = 0.0;
-            if(gm < it.m && gk < it.k) v = it.ta ? Ap[gk + static_cast<long long>(gm) * it.lda] : Ap[gm + static_cast<long long>(gk) * it.lda];
-            As[buf][kk][mm] = v;
-        }
-#pragma unroll
-        for(int r = 0; r < (GN * GK) / GEMM_THREADS; ++r) {
-            const int e = tid + r * GEMM_THREADS;
-            int nn, kk;
-            if(!it.tb) { kk = e % GK; nn = e / GK; } else { nn = e % GN; kk = e / GN; }
-            const int gn = n0 + nn, gk = k0 + kk;
-            double v = 0.0;
-            if(gn < it.n && gk < it.k) v = it.tb ? Bp[gn + static_cast<long long>(gk) * it.ldb] : Bp[gk + static_cast<long long>(gn) * it.ldb];
-            Bs[buf][kk][nn] = v;
-        }
-    };
-
-    const int nk = (it.k + GK - 1) / GK;
-    if(nk > 0) load_tiles(0, 0);
-    __syncthreads();
-    const int fr = lane >> 2, fk = lane & 3;
-    for(int kt = 0; kt < nk; ++kt) {
-        const int cur = kt & 1;
-        if(kt + 1 < nk) load_tiles(cur ^ 1, (kt + 1) * GK);
-#pragma unroll
-        for(int ks = 0; ks < GK; ks += 4) {
-            double a[4], b[4];
-#pragma unroll
-            for(int i = 0; i < 4; ++i) a[i] = As[cur][ks + fk][wm + i * 8 + fr];
-#pragma unroll
-            for(int j = 0; j < 4; ++j) b[j] = Bs[cur][ks + fk][wn + j * 8 + fr];
-#pragma unroll
-            for(int i = 0; i < 4; ++i)
-#pragma unroll
-                for(int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
-        __syncthreads();
-    }
-    // C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}
-#pragma unroll
-    for(int i = 0; i < 4; ++i)
-#pragma unroll
-        for(int j = 0; j < 4; ++j) {
-            const int gm = m0 + wm + i * 8 + fr;
-            const int gn = n0 + wn + j * 8 + 2 * fk;
-            if(gm < it.m) {
-#pragma unroll
-                for(int h = 0; h < 2; ++h)
-                    if(gn + h < it.n) {
-                        double* p = Cp + gm + static_cast<long long>(gn + h) * it.ldc;
-                        const double v = it.alpha * acc[i][j][h];
-                        *p = it.acc ? *p + v : v;
-                    }
-            }
-        }
-}
-
-void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, cudaStream_t s)
-{
-    if(n_items == 0) return;
-    gemm_grouped_kernel<<<n_items, GEMM_THREADS, 0, s>>>(A, B, C, d_items);
-    check_cuda(cudaGetLastError(), "gemm_grouped_kernel launch");
 }
 
 // ================================================================================================ elementwise

@@ -361,6 +361,21 @@ void choose_tiles(PermTask& T, const int* sstride0, int target)
         T.ntile[i] = ceil_div(T.dims[i], T.w[i]);
         T.magic[i] = T.w[i] > 1 ? static_cast<unsigned>(((1ull << 32) + T.w[i] - 1) / T.w[i]) : 0u;
     }
+    // strips: second-fastest tile leg of each side, cut so that there is at least one item per thread
+    auto strips = [&](const int* order, int& strip, int& nchunk, int& items, unsigned& magic_chunk) {
+        strip = 1;
+        nchunk = 1;
+        if(T.ntl >= 2) {
+            const int wb = T.w[order[1]];
+            strip = std::min(PERM_STRIP, wb);
+            while(strip > 1 && (T.vol / wb) * ceil_div(wb, strip) < PERM_THREADS) strip = ceil_div(strip, 2);
+            nchunk = ceil_div(wb, strip);
+        }
+        items = T.ntl >= 2 ? (T.vol / T.w[order[1]]) * nchunk : T.vol;
+        magic_chunk = nchunk > 1 ? static_cast<unsigned>(((1ull << 32) + nchunk - 1) / nchunk) : 0u;
+    };
+    strips(T.tl_s, T.strip_s, T.nchunk_s, T.items_s, T.magic_chunk_s);
+    strips(T.tl_d, T.strip_d, T.nchunk_d, T.items_d, T.magic_chunk_d);
 }
 
 int smem_extent(const PermTask& T)

@@ -101,22 +101,33 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // ~20 bits, then two Newton steps
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+
 // Jacobi rotation that annihilates g_pq of [[a, c], [c, b]]; false if the pair is already orthogonal to `tol`.
+// t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / 2c, evaluated as sign(d) h / (|d| + sqrt(d^2 + h^2)) with
+// d = b - a, h = 2c: one sqrt, one (Newton) reciprocal and one rsqrt on the dependent chain of every Jacobi step.  Only
+// cs = rsqrt(1 + t^2) has to be exact to the last bit for the rotation to be orthogonal; t merely steers the angle.
 __device__ __forceinline__ bool jacobi_rotation(double a, double b, double c, double tol2, double& cs, double& sn)
 {
     cs = 1.0;
     sn = 0.0;
     if(!(a > 0.0 && b > 0.0 && c * c > tol2 * a * b)) return false;
-    const double zeta = (b - a) / (2.0 * c);
-    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    cs = rsqrt(1.0 + t * t);
+    const double d = b - a, h = 2.0 * c;
+    const double t = copysign(1.0, d) * h * fast_rcp(fabs(d) + sqrt(fma(d, d, h * h)));
+    cs = rsqrt(fma(t, t, 1.0));
     sn = cs * t;
     return true;
 }
 
 constexpr int XS_LD = SCH + 4;   // == 4 mod 16: the DMMA fragment loads of both operand roles hit 16 distinct banks per half-warp
 constexpr int VL_LD = SP + 4;
-constexpr int SVD_MAX_INNER = 8;
+constexpr int SVD_MAX_INNER = 1;   // one inner sweep per visit: same number of outer sweeps as full inner convergence (measured), 8x shorter rounds
 
 // One round of the block one-sided Jacobi method: every (sector block, column-block pair) of the round is handled by a
 // cluster of CL CTAs that split the rows.  Phase 1: Gram matrix G = X^T X of the 32-column panel on the FP64 tensor

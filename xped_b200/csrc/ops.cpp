@@ -49,28 +49,33 @@ Tensor* Context::copy(const Tensor& t)
 // ------------------------------------------------------------------------------------------------ grouped GEMM launcher
 void Context::run_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems)
 {
-    std::vector<GemmItem> items;
+    std::vector<GemmItem> items[2];   // [0]: 128 x 64 tiles (sectors with m > 96), [1]: 64 x 64 tiles
     double flops = 0.0;
     for(GemmItem g : problems) {
         if(g.m <= 0 || g.n <= 0) continue;
         flops += 2.0 * g.m * static_cast<double>(g.n) * g.k;
+        const int which = g.m > 96 ? 0 : 1, tile_m = which == 0 ? 128 : 64;
         for(int tn = 0; tn < g.n; tn += GEMM_TILE_N)
-            for(int tm = 0; tm < g.m; tm += GEMM_TILE_M) {
+            for(int tm = 0; tm < g.m; tm += tile_m) {
                 g.tm = tm;
                 g.tn = tn;
-                items.push_back(g);
+                items[which].push_back(g);
             }
     }
-    if(items.empty()) return;
+    if(items[0].empty() && items[1].empty()) return;
     ProfScope prof(*this, CAT_GEMM, flops);
-    // heavy tiles first: k is the per-tile cost
-    std::stable_sort(items.begin(), items.end(), [](const GemmItem& x, const GemmItem& y) { return x.k > y.k; });
-    GemmItem* d_items = nullptr;
-    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_items), items.size() * sizeof(GemmItem), stream), "cudaMallocAsync gemm items");
-    upload_async(d_items, items.data(), items.size() * sizeof(GemmItem));
-    launch_gemm_grouped(A, B, C, d_items, static_cast<int>(items.size()), stream);
-    check_cuda(cudaFreeAsync(d_items, stream), "cudaFreeAsync gemm items");
-    ++launches;
+    for(int which = 0; which < 2; ++which) {
+        auto& v = items[which];
+        if(v.empty()) continue;
+        // heavy tiles first: k is the per-tile cost
+        std::stable_sort(v.begin(), v.end(), [](const GemmItem& x, const GemmItem& y) { return x.k > y.k; });
+        GemmItem* d_items = nullptr;
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_items), v.size() * sizeof(GemmItem), stream), "cudaMallocAsync gemm items");
+        upload_async(d_items, v.data(), v.size() * sizeof(GemmItem));
+        launch_gemm_grouped(A, B, C, d_items, static_cast<int>(v.size()), which == 0 ? 128 : 64, stream);
+        check_cuda(cudaFreeAsync(d_items, stream), "cudaFreeAsync gemm items");
+        ++launches;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ operator*

@@ -33,4 +33,13 @@ elif what == "su2":
         ctx.sync()
     r = Q @ Q
     ctx.sync()
+elif what == "svd":
+    ctx = xb.Context([("SU2", 0, 0)])
+    a, e = ctx.basis([(1, 2), (2, 2)]), ctx.basis([(1, 8), (2, 14), (3, 16), (4, 12), (5, 8), (6, 4), (7, 2)])
+    Q4 = ctx.tensor([e, a, a], [e, a, a]).setRandom(1)
+    Q1 = ctx.tensor([e, a, a], [e, a, a]).setRandom(2)
+    M = Q4 @ Q1
+    U, S, Vd = M.tSVD(64, 1e-10, False)
+    ctx.sync()
+    print("tSVD done", ctx.stats())
 ctx.close()

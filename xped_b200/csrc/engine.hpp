@@ -198,7 +198,11 @@ private:
     size_t scratch_bytes_ = 0;
     void* pinned_ = nullptr;
     size_t pinned_bytes_ = 0;
-    std::vector<std::pair<void*, size_t>> staging_;   // pinned blocks kept alive until the next sync
+    // pinned staging ring for small metadata uploads (work lists, block descriptors): chunks are reused once the
+    // copies that read them have completed (one fence event per chunk)
+    struct StageChunk { char* p = nullptr; size_t cap = 0, used = 0; cudaEvent_t fence = nullptr; bool pending = false; };
+    std::vector<StageChunk> staging_;
+    size_t stage_cur_ = 0;
 };
 
 void check_cuda(cudaError_t e, const char* what);

@@ -42,7 +42,7 @@ __device__ __forceinline__ bool perm_item(const PermTask& T, const int* __restri
     gstep = sstep = 0;
     if(ntl >= 2) {
         const int lb = order[1];
-        int q = nchunk > 1 ? __umulhi(static_cast<unsigned>(r), magic_chunk) : 0;
+        int q = nchunk > 1 ? __umulhi(static_cast<unsigned>(r), magic_chunk) : r;
         const int c1 = (r - q * nchunk) * strip;
         r = q;
         cnt = min(strip, lim[lb] - c1);

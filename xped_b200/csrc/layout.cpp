@@ -51,7 +51,10 @@ Context::~Context()
     for(cudaEvent_t e : event_pool) cudaEventDestroy(e);
     if(timer_e0) cudaEventDestroy(timer_e0);
     if(timer_e1) cudaEventDestroy(timer_e1);
-    for(auto& p : staging_) cudaFreeHost(p.first);
+    for(auto& c : staging_) {
+        if(c.p) cudaFreeHost(c.p);
+        if(c.fence) cudaEventDestroy(c.fence);
+    }
     if(scratch_) cudaFree(scratch_);
     if(pinned_) cudaFreeHost(pinned_);
     if(stream) cudaStreamDestroy(stream);
@@ -60,8 +63,11 @@ Context::~Context()
 void Context::sync()
 {
     check_cuda(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
-    for(auto& p : staging_) cudaFreeHost(p.first);
-    staging_.clear();
+    for(auto& c : staging_) {
+        c.used = 0;
+        c.pending = false;
+    }
+    stage_cur_ = 0;
 }
 
 cudaEvent_t Context::get_event()
@@ -140,11 +146,40 @@ void* Context::pinned(size_t bytes)
 void Context::upload_async(void* dst, const void* src, size_t bytes)
 {
     if(bytes == 0) return;
-    void* h = nullptr;
-    check_cuda(cudaMallocHost(&h, bytes), "cudaMallocHost staging");
-    std::memcpy(h, src, bytes);
-    staging_.emplace_back(h, bytes);
-    check_cuda(cudaMemcpyAsync(dst, h, bytes, cudaMemcpyHostToDevice, stream), "upload_async");
+    constexpr size_t CHUNK = size_t(1) << 20;
+    constexpr size_t MAX_CHUNKS = 8;
+    const size_t need = (bytes + 15) & ~size_t(15);
+    auto fits = [&](const StageChunk& c) { return c.p && c.cap - c.used >= need; };
+    if(staging_.empty() || !fits(staging_[stage_cur_])) {
+        if(!staging_.empty()) {   // leave the current chunk: fence it
+            StageChunk& c = staging_[stage_cur_];
+            check_cuda(cudaEventRecord(c.fence, stream), "staging fence");
+            c.pending = true;
+        }
+        size_t next = staging_.empty() ? 0 : stage_cur_ + 1;
+        if(next >= staging_.size() && (staging_.size() < MAX_CHUNKS || need > CHUNK)) {
+            StageChunk c;
+            c.cap = std::max(CHUNK, need);
+            check_cuda(cudaMallocHost(reinterpret_cast<void**>(&c.p), c.cap), "cudaMallocHost staging");
+            check_cuda(cudaEventCreateWithFlags(&c.fence, cudaEventDisableTiming), "staging event");
+            staging_.push_back(c);
+            next = staging_.size() - 1;
+        } else {
+            if(next >= staging_.size()) next = 0;
+            for(size_t tries = 0; tries < staging_.size() && staging_[next].cap < need; ++tries) next = (next + 1) % staging_.size();
+            StageChunk& c = staging_[next];
+            if(c.pending) {
+                check_cuda(cudaEventSynchronize(c.fence), "staging wait");
+                c.pending = false;
+            }
+            c.used = 0;
+        }
+        stage_cur_ = next;
+    }
+    StageChunk& c = staging_[stage_cur_];
+    std::memcpy(c.p + c.used, src, bytes);
+    check_cuda(cudaMemcpyAsync(dst, c.p + c.used, bytes, cudaMemcpyHostToDevice, stream), "upload_async");
+    c.used += need;
 }
 
 Tensor::Tensor(Context* c, LayoutPtr l, bool zero) : ctx(c), layout(std::move(l))

@@ -495,7 +495,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
     int max_rows = 0;
     for(const SvdBlock& b : R.blocks) max_rows = std::max(max_rows, b.rows);
     const int cluster = max_rows > 2 * SCH ? 4 : 1;   // split the rows of a panel over a 4-CTA cluster once there are enough of them
-    const int max_sweeps = 40;
+    const int max_sweeps = 150;   // bail-out only; graded CTM corner products need ~30 sweeps without preconditioning
     for(R.sweeps = 0; R.sweeps < max_sweeps; ++R.sweeps) {
         check_cuda(cudaMemsetAsync(d_flag, 0, sizeof(int), s), "svd flag reset");
         for(size_t r = 0; r + 1 < round_begin.size(); ++r) {
@@ -530,7 +530,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         cudaFreeAsync(d_meta, s);
         cudaFreeAsync(R.d_W, s);
         cudaFreeAsync(R.d_V, s);
-        throw std::runtime_error("tSVD: block Jacobi did not converge in 40 sweeps");
+        throw std::runtime_error("tSVD: block Jacobi did not converge in 150 sweeps");
     }
     {
         dim3 grid(32, static_cast<unsigned>(std::min(nb, 64)));

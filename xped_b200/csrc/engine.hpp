@@ -67,6 +67,10 @@ struct PermTask   // one destination sub-block (target tree pair) = sum_k coeff_
     int strip_s, nchunk_s, items_s;   // read phase (source order)
     int strip_d, nchunk_d, items_d;   // write phase (destination order)
     unsigned magic_chunk_s, magic_chunk_d;
+    // first source inline: Abelian symmetries have fan-in 1, so most tasks never touch the PermSrc table
+    long long src0_off;
+    double src0_coeff;
+    int src0_stride[PERM_MAXLEG];
 };
 
 struct PermSrc
@@ -76,12 +80,13 @@ struct PermSrc
     int sstride[PERM_MAXLEG];   // source stride of each (dst-ordered) leg
 };
 
-struct PermTile { int task; int tile; };
+struct PermTile { int task; unsigned short c[PERM_MAXLEG]; };   // task + tile coordinate along each merged leg (no divisions on the device)
 
 struct PermutePlan
 {
     LayoutPtr out;
     int n_tasks = 0, n_srcs = 0, n_tiles = 0;
+    int tiles_per_cta = 1;
     PermTask* d_tasks = nullptr;
     PermSrc* d_srcs = nullptr;
     PermTile* d_tiles = nullptr;

@@ -63,86 +63,127 @@ __device__ __forceinline__ bool perm_item(const PermTask& T, const int* __restri
     return ok && cnt > 0;
 }
 
-__global__ void __launch_bounds__(PERM_THREADS)
-permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const PermTask* __restrict__ tasks,
-               const PermSrc* __restrict__ srcs, const PermTile* __restrict__ tiles)
+// Read phase for one source: every thread first issues ALL of its global loads (up to 16 independent 8-byte loads in
+// flight per thread), then scales / accumulates them into the shared tile.  STRIP is the task's strip length.
+template <int STRIP>
+__device__ __noinline__ void perm_read(const PermTask& T, const int* __restrict__ sstride, const int* __restrict__ lim, const double* __restrict__ sp,
+                                       double coeff, bool first, double* __restrict__ buf, int tid)
+{
+    constexpr int MAXI = 8 / STRIP;   // 8 independent loads in flight per thread and pass
+    for(int base = tid; base < T.items_s; base += MAXI * PERM_THREADS) {
+        double v[MAXI][STRIP];
+        int pos[MAXI], cnt[MAXI], sstep = 0;
+#pragma unroll
+        for(int j = 0; j < MAXI; ++j) {
+            const int it = base + j * PERM_THREADS;
+            cnt[j] = 0;
+            pos[j] = 0;
+            if(it < T.items_s) {
+                int off, c, gstep, ss;
+                if(perm_item(T, T.tl_s, sstride, lim, T.nchunk_s, T.magic_chunk_s, STRIP, it, off, pos[j], c, gstep, ss)) {
+                    cnt[j] = c;
+                    sstep = ss;
+#pragma unroll
+                    for(int i = 0; i < STRIP; ++i)
+                        if(i < c) v[j][i] = __ldg(sp + off + i * gstep);
+                }
+            }
+        }
+#pragma unroll
+        for(int j = 0; j < MAXI; ++j) {
+#pragma unroll
+            for(int i = 0; i < STRIP; ++i)
+                if(i < cnt[j]) {
+                    double* b = buf + pos[j] + i * sstep;
+                    *b = first ? coeff * v[j][i] : fma(coeff, v[j][i], *b);
+                }
+        }
+    }
+}
+
+__device__ __forceinline__ void perm_read_dispatch(const PermTask& T, const int* __restrict__ sstride, const int* __restrict__ lim, const double* __restrict__ sp,
+                                                   double coeff, bool first, double* __restrict__ buf, int tid)
+{
+    switch(T.strip_s) {
+    case 8: perm_read<8>(T, sstride, lim, sp, coeff, first, buf, tid); break;
+    case 4: perm_read<4>(T, sstride, lim, sp, coeff, first, buf, tid); break;
+    case 2: perm_read<2>(T, sstride, lim, sp, coeff, first, buf, tid); break;
+    default: perm_read<1>(T, sstride, lim, sp, coeff, first, buf, tid); break;
+    }
+}
+
+// Each CTA walks `tiles_per_cta` consecutive entries of the tile list (mostly tiles of one task, so the task record is
+// staged once).  Per tile: read phase (source order) -> barrier -> write phase (destination order) -> barrier.
+__global__ void __launch_bounds__(PERM_THREADS, 3)
+permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const PermTask* __restrict__ tasks, const PermSrc* __restrict__ srcs,
+               const PermTile* __restrict__ tiles, int n_tiles, int tiles_per_cta)
 {
     __shared__ PermTask T;
     __shared__ PermSrc S;
     __shared__ double buf[PERM_BUF_ELEMS];
+    __shared__ PermTile s_tile;
     __shared__ int s_base[PERM_MAXLEG];
     __shared__ int s_lim[PERM_MAXLEG];
 
     const int tid = threadIdx.x;
-    const PermTile tile = tiles[blockIdx.x];
-    {   // stage the task record
-        const int* g = reinterpret_cast<const int*>(tasks + tile.task);
-        int* s = reinterpret_cast<int*>(&T);
-        for(int i = tid; i < static_cast<int>(sizeof(PermTask) / sizeof(int)); i += PERM_THREADS) s[i] = g[i];
-    }
-    __syncthreads();
-    if(tid < PERM_MAXLEG) {
-        int r = tile.tile, b = 0, lim = 1;
-        for(int l = 0; l <= tid && l < T.nleg; ++l) {
-            const int c = r % T.ntile[l];
-            r /= T.ntile[l];
-            b = c * T.w[l];
-            lim = min(T.w[l], T.dims[l] - b);
+    const int t0 = blockIdx.x * tiles_per_cta, t1 = min(n_tiles, t0 + tiles_per_cta);
+    int staged = -1;
+    for(int ti = t0; ti < t1; ++ti) {
+        if(tid < static_cast<int>(sizeof(PermTile) / sizeof(int))) reinterpret_cast<int*>(&s_tile)[tid] = reinterpret_cast<const int*>(tiles + ti)[tid];
+        __syncthreads();   // also: the previous tile's write phase has finished reading buf / T
+        const int task = s_tile.task;
+        if(task != staged) {
+            const int* g = reinterpret_cast<const int*>(tasks + task);
+            int* s = reinterpret_cast<int*>(&T);
+            for(int i = tid; i < static_cast<int>(sizeof(PermTask) / sizeof(int)); i += PERM_THREADS) s[i] = g[i];
+            staged = task;
+            __syncthreads();
         }
-        s_base[tid] = tid < T.nleg ? b : 0;
-        s_lim[tid] = tid < T.nleg ? lim : 1;
-    }
-    __syncthreads();
-
-    // ---- read phase: buf = sum_k coeff_k * src_k tile, addressed in source order (lanes along the source-contiguous leg).
-    // The item -> thread map does not depend on k, so the same thread owns the same buf element for every source and the
-    // fan-in accumulates in shared memory without barriers in between.
-    for(int k = 0; k < T.src_count; ++k) {
-        __syncthreads();   // S of the previous source no longer needed
-        if(tid < static_cast<int>(sizeof(PermSrc) / sizeof(int))) reinterpret_cast<int*>(&S)[tid] = reinterpret_cast<const int*>(srcs + T.src_begin + k)[tid];
+        if(tid < PERM_MAXLEG) {
+            const bool on = tid < T.nleg;
+            const int b = on ? s_tile.c[tid] * T.w[tid] : 0;
+            s_base[tid] = b;
+            s_lim[tid] = on ? min(T.w[tid], T.dims[tid] - b) : 1;
+        }
         __syncthreads();
-        long long sbase = S.off;
-        for(int l = 0; l < T.nleg; ++l) sbase += static_cast<long long>(s_base[l]) * S.sstride[l];
-        const double* __restrict__ sp = src + sbase;
-        const double coeff = S.coeff;
-        for(int it = tid; it < T.items_s; it += PERM_THREADS) {
-            int off, pos, cnt, gstep, sstep;
-            if(!perm_item(T, T.tl_s, S.sstride, s_lim, T.nchunk_s, T.magic_chunk_s, T.strip_s, it, off, pos, cnt, gstep, sstep)) continue;
-            double v[PERM_STRIP];
-#pragma unroll
-            for(int i = 0; i < PERM_STRIP; ++i)
-                if(i < cnt) v[i] = __ldg(sp + off + i * gstep);
-            if(k == 0) {
-#pragma unroll
-                for(int i = 0; i < PERM_STRIP; ++i)
-                    if(i < cnt) buf[pos + i * sstep] = coeff * v[i];
-            } else {
-#pragma unroll
-                for(int i = 0; i < PERM_STRIP; ++i)
-                    if(i < cnt) buf[pos + i * sstep] = fma(coeff, v[i], buf[pos + i * sstep]);
-            }
-        }
-    }
-    __syncthreads();
 
-    // ---- write phase: destination order (lanes along the destination-contiguous leg); every element written once
-    long long dbase = T.dst_off;
-    for(int l = 0; l < T.nleg; ++l) dbase += static_cast<long long>(s_base[l]) * T.dstride[l];
-    double* __restrict__ dp = dst + dbase;
-    const bool zero = T.src_count == 0;
-    for(int it = tid; it < T.items_d; it += PERM_THREADS) {
-        int off, pos, cnt, gstep, sstep;
-        if(!perm_item(T, T.tl_d, T.dstride, s_lim, T.nchunk_d, T.magic_chunk_d, T.strip_d, it, off, pos, cnt, gstep, sstep)) continue;
-#pragma unroll
-        for(int i = 0; i < PERM_STRIP; ++i)
-            if(i < cnt) dp[off + i * gstep] = zero ? 0.0 : buf[pos + i * sstep];
+        // ---- read phase: buf = sum_k coeff_k * src_k tile. The item -> thread map does not depend on k, so the same thread
+        // owns the same buf element for every source and the fan-in accumulates in shared memory without barriers.
+        if(T.src_count > 0) {
+            long long sbase = T.src0_off;
+            for(int l = 0; l < T.nleg; ++l) sbase += static_cast<long long>(s_base[l]) * T.src0_stride[l];
+            perm_read_dispatch(T, T.src0_stride, s_lim, src + sbase, T.src0_coeff, true, buf, tid);
+        }
+        for(int k = 1; k < T.src_count; ++k) {
+            __syncthreads();   // S of the previous source no longer needed
+            if(tid < static_cast<int>(sizeof(PermSrc) / sizeof(int))) reinterpret_cast<int*>(&S)[tid] = reinterpret_cast<const int*>(srcs + T.src_begin + k)[tid];
+            __syncthreads();
+            long long sbase = S.off;
+            for(int l = 0; l < T.nleg; ++l) sbase += static_cast<long long>(s_base[l]) * S.sstride[l];
+            perm_read_dispatch(T, S.sstride, s_lim, src + sbase, S.coeff, false, buf, tid);
+        }
+        __syncthreads();
+
+        // ---- write phase: destination order (lanes along the destination-contiguous leg); every element written once
+        long long dbase = T.dst_off;
+        for(int l = 0; l < T.nleg; ++l) dbase += static_cast<long long>(s_base[l]) * T.dstride[l];
+        double* __restrict__ dp = dst + dbase;
+        const bool zero = T.src_count == 0;
+        const int strip = T.strip_d;
+        for(int it = tid; it < T.items_d; it += PERM_THREADS) {
+            int off, pos, cnt, gstep, sstep;
+            if(!perm_item(T, T.tl_d, T.dstride, s_lim, T.nchunk_d, T.magic_chunk_d, strip, it, off, pos, cnt, gstep, sstep)) continue;
+            for(int i = 0; i < cnt; ++i) dp[off + i * gstep] = zero ? 0.0 : buf[pos + i * sstep];
+        }
     }
 }
 
 void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s)
 {
     if(plan.n_tiles == 0) return;
-    permute_kernel<<<plan.n_tiles, PERM_THREADS, 0, s>>>(src, dst, plan.d_tasks, plan.d_srcs, plan.d_tiles);
+    const int tpc = plan.tiles_per_cta < 1 ? 1 : plan.tiles_per_cta;
+    const int grid = (plan.n_tiles + tpc - 1) / tpc;
+    permute_kernel<<<grid, PERM_THREADS, 0, s>>>(src, dst, plan.d_tasks, plan.d_srcs, plan.d_tiles, plan.n_tiles, tpc);
     check_cuda(cudaGetLastError(), "permute_kernel launch");
 }
 

@@ -402,8 +402,8 @@ void choose_tiles(PermTask& T, const int* sstride0, int target)
         nchunk = 1;
         if(T.ntl >= 2) {
             const int wb = T.w[order[1]];
-            strip = std::min(PERM_STRIP, wb);
-            while(strip > 1 && (T.vol / wb) * ceil_div(wb, strip) < PERM_THREADS) strip = ceil_div(strip, 2);
+            strip = 1;
+            while(strip * 2 <= std::min(PERM_STRIP, wb) && (T.vol / wb) * ceil_div(wb, strip * 2) >= PERM_THREADS) strip *= 2;   // power of two: 1, 2, 4, 8
             nchunk = ceil_div(wb, strip);
         }
         items = T.ntl >= 2 ? (T.vol / T.w[order[1]]) * nchunk : T.vol;
@@ -636,13 +636,32 @@ std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shif
         long long nt = 1;
         for(int j = 0; j < n; ++j) nt *= T.ntile[j];
         const int tid = static_cast<int>(h_tasks.size());
-        for(long long x = 0; x < nt; ++x) h_tiles.push_back({tid, static_cast<int>(x)});
+        if(!t.srcs.empty()) {
+            const PermSrc& s0 = h_srcs[T.src_begin];
+            T.src0_off = s0.off;
+            T.src0_coeff = s0.coeff;
+            for(int j = 0; j < n; ++j) T.src0_stride[j] = s0.sstride[j];
+        }
+        for(long long x = 0; x < nt; ++x) {
+            PermTile pt;
+            std::memset(&pt, 0, sizeof(pt));
+            pt.task = tid;
+            long long r = x;
+            for(int j = 0; j < n; ++j) {
+                if(T.ntile[j] > 65535) throw std::length_error("permute plan: more than 65535 tiles along one leg");
+                pt.c[j] = static_cast<unsigned short>(r % T.ntile[j]);
+                r /= T.ntile[j];
+            }
+            h_tiles.push_back(pt);
+        }
         plan->max_fan_in = std::max(plan->max_fan_in, T.src_count);
         h_tasks.push_back(T);
     }
     plan->n_tasks = static_cast<int>(h_tasks.size());
     plan->n_srcs = static_cast<int>(h_srcs.size());
     plan->n_tiles = static_cast<int>(h_tiles.size());
+    // consecutive tiles (mostly of the same task) per CTA: amortises the task staging, keeps >= 16 CTAs per SM in the grid
+    plan->tiles_per_cta = std::max(1, std::min(8, plan->n_tiles / (sm_count * 16)));
     if(plan->n_tasks) {
         check_cuda(cudaMalloc(&plan->d_tasks, h_tasks.size() * sizeof(PermTask)), "cudaMalloc plan tasks");
         check_cuda(cudaMemcpy(plan->d_tasks, h_tasks.data(), h_tasks.size() * sizeof(PermTask), cudaMemcpyHostToDevice), "upload plan tasks");

@@ -101,27 +101,21 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ double fast_rcp(double x)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // ~20 bits, then two Newton steps
-    r = fma(r, fma(-x, r, 1.0), r);
-    return fma(r, fma(-x, r, 1.0), r);
-}
-
 // Jacobi rotation that annihilates g_pq of [[a, c], [c, b]]; false if the pair is already orthogonal to `tol`.
-// t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / 2c, evaluated as sign(d) h / (|d| + sqrt(d^2 + h^2)) with
-// d = b - a, h = 2c: one sqrt, one (Newton) reciprocal and one rsqrt on the dependent chain of every Jacobi step.  Only
-// cs = rsqrt(1 + t^2) has to be exact to the last bit for the rotation to be orthogonal; t merely steers the angle.
+// With d = b - a, h = 2c, D = |d| + sqrt(d^2 + h^2):  t = sign(d) h / D,  cs = 1 / sqrt(1 + t^2) = D / sqrt(D^2 + h^2),
+// sn = cs t = sign(d) h / sqrt(D^2 + h^2): two reciprocal square roots and no division on the dependent chain of a Jacobi step.
+// cs^2 + sn^2 = (D^2 + h^2) rs^2 = 1 up to the rounding of rs, so the rotation is orthogonal to working precision.
 __device__ __forceinline__ bool jacobi_rotation(double a, double b, double c, double tol2, double& cs, double& sn)
 {
     cs = 1.0;
     sn = 0.0;
     if(!(a > 0.0 && b > 0.0 && c * c > tol2 * a * b)) return false;
     const double d = b - a, h = 2.0 * c;
-    const double t = copysign(1.0, d) * h * fast_rcp(fabs(d) + sqrt(fma(d, d, h * h)));
-    cs = rsqrt(fma(t, t, 1.0));
-    sn = cs * t;
+    const double r2 = fma(d, d, h * h);
+    const double D = fabs(d) + r2 * rsqrt(r2);
+    const double rs = rsqrt(fma(D, D, h * h));
+    cs = D * rs;
+    sn = copysign(h, d * h) * rs;
     return true;
 }
 
@@ -246,9 +240,12 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
             int pk, qk, pl, ql;
             panel_pair(step, k, pk, qk);
             panel_pair(step, l, pl, ql);
+            // every thread computes the rotation of its column pair l only; lane l of the warp (l = lane & 15) holds pair k's
             double ck, sk, cl, sl;
-            const bool rk = jacobi_rotation(G[pk][pk], G[qk][qk], G[pk][qk], tol2, ck, sk);
             const bool rl = jacobi_rotation(G[pl][pl], G[ql][ql], G[pl][ql], tol2, cl, sl);
+            ck = __shfl_sync(0xffffffffu, cl, k);
+            sk = __shfl_sync(0xffffffffu, sl, k);
+            const bool rk = __shfl_sync(0xffffffffu, static_cast<int>(rl), k) != 0;
             any |= rk ? 1 : 0;
             // G <- J^T G J on the owned 2x2 block
             const double g00 = G[pk][pl], g01 = G[pk][ql], g10 = G[qk][pl], g11 = G[qk][ql];

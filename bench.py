@@ -333,7 +333,10 @@ def run_b200(args):
 
     extras, dgemm_peak = ({}, None)
     if rank == 0 and not args.no_extras:
+        ksampler = ClockSampler(local)
+        ksampler.start()
         extras, dgemm_peak = kernel_sections(xb, local, torch)
+        extras["clocks"] = ksampler.stop()
 
     if rank == 0:
         ms_step = total_ms / args.steps

@@ -63,75 +63,58 @@ __device__ __forceinline__ bool perm_item(const PermTask& T, const int* __restri
     return ok && cnt > 0;
 }
 
-// Read phase for one source: every thread first issues ALL of its global loads (up to 16 independent 8-byte loads in
-// flight per thread), then scales / accumulates them into the shared tile.  STRIP is the task's strip length.
-template <int STRIP>
-__device__ __noinline__ void perm_read(const PermTask& T, const int* __restrict__ sstride, const int* __restrict__ lim, const double* __restrict__ sp,
-                                       double coeff, bool first, double* __restrict__ buf, int tid)
+// Read phase for one source: lanes along the source-contiguous leg, each thread walks strips of the second-fastest
+// leg; the loads of a strip are issued back to back, then scaled / accumulated into the shared tile.
+__device__ __forceinline__ void perm_read(const PermTask& T, const int* __restrict__ sstride, const int* __restrict__ lim, const double* __restrict__ sp,
+                                          double coeff, bool first, double* __restrict__ buf, int tid)
 {
-    constexpr int MAXI = 8 / STRIP;   // 8 independent loads in flight per thread and pass
-    for(int base = tid; base < T.items_s; base += MAXI * PERM_THREADS) {
-        double v[MAXI][STRIP];
-        int pos[MAXI], cnt[MAXI], sstep = 0;
+    const int strip = T.strip_s, items = T.items_s, nchunk = T.nchunk_s;
+    const unsigned magic = T.magic_chunk_s;
+    for(int it = tid; it < items; it += PERM_THREADS) {
+        int off, pos, cnt, gstep, sstep;
+        if(!perm_item(T, T.tl_s, sstride, lim, nchunk, magic, strip, it, off, pos, cnt, gstep, sstep)) continue;
+        double v[PERM_STRIP];
 #pragma unroll
-        for(int j = 0; j < MAXI; ++j) {
-            const int it = base + j * PERM_THREADS;
-            cnt[j] = 0;
-            pos[j] = 0;
-            if(it < T.items_s) {
-                int off, c, gstep, ss;
-                if(perm_item(T, T.tl_s, sstride, lim, T.nchunk_s, T.magic_chunk_s, STRIP, it, off, pos[j], c, gstep, ss)) {
-                    cnt[j] = c;
-                    sstep = ss;
+        for(int i = 0; i < PERM_STRIP; ++i)
+            if(i < cnt) v[i] = __ldg(sp + off + i * gstep);
+        if(first) {
 #pragma unroll
-                    for(int i = 0; i < STRIP; ++i)
-                        if(i < c) v[j][i] = __ldg(sp + off + i * gstep);
-                }
-            }
+            for(int i = 0; i < PERM_STRIP; ++i)
+                if(i < cnt) buf[pos + i * sstep] = coeff * v[i];
+        } else {
+#pragma unroll
+            for(int i = 0; i < PERM_STRIP; ++i)
+                if(i < cnt) buf[pos + i * sstep] = fma(coeff, v[i], buf[pos + i * sstep]);
         }
-#pragma unroll
-        for(int j = 0; j < MAXI; ++j) {
-#pragma unroll
-            for(int i = 0; i < STRIP; ++i)
-                if(i < cnt[j]) {
-                    double* b = buf + pos[j] + i * sstep;
-                    *b = first ? coeff * v[j][i] : fma(coeff, v[j][i], *b);
-                }
-        }
-    }
-}
-
-__device__ __forceinline__ void perm_read_dispatch(const PermTask& T, const int* __restrict__ sstride, const int* __restrict__ lim, const double* __restrict__ sp,
-                                                   double coeff, bool first, double* __restrict__ buf, int tid)
-{
-    switch(T.strip_s) {
-    case 8: perm_read<8>(T, sstride, lim, sp, coeff, first, buf, tid); break;
-    case 4: perm_read<4>(T, sstride, lim, sp, coeff, first, buf, tid); break;
-    case 2: perm_read<2>(T, sstride, lim, sp, coeff, first, buf, tid); break;
-    default: perm_read<1>(T, sstride, lim, sp, coeff, first, buf, tid); break;
     }
 }
 
 // Each CTA walks `tiles_per_cta` consecutive entries of the tile list (mostly tiles of one task, so the task record is
-// staged once).  Per tile: read phase (source order) -> barrier -> write phase (destination order) -> barrier.
-__global__ void __launch_bounds__(PERM_THREADS, 3)
+// staged once; the next tile's record is prefetched while the current tile moves).  Per tile: read phase (source
+// order) -> barrier -> write phase (destination order) -> barrier.
+__global__ void __launch_bounds__(PERM_THREADS, 4)
 permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const PermTask* __restrict__ tasks, const PermSrc* __restrict__ srcs,
                const PermTile* __restrict__ tiles, int n_tiles, int tiles_per_cta)
 {
     __shared__ PermTask T;
     __shared__ PermSrc S;
     __shared__ double buf[PERM_BUF_ELEMS];
-    __shared__ PermTile s_tile;
+    __shared__ int s_tile[2][sizeof(PermTile) / sizeof(int)];
     __shared__ int s_base[PERM_MAXLEG];
     __shared__ int s_lim[PERM_MAXLEG];
 
+    constexpr int TILE_INTS = static_cast<int>(sizeof(PermTile) / sizeof(int));
     const int tid = threadIdx.x;
     const int t0 = blockIdx.x * tiles_per_cta, t1 = min(n_tiles, t0 + tiles_per_cta);
+    if(tid < TILE_INTS) s_tile[0][tid] = reinterpret_cast<const int*>(tiles + t0)[tid];
+    __syncthreads();
     int staged = -1;
     for(int ti = t0; ti < t1; ++ti) {
-        if(tid < static_cast<int>(sizeof(PermTile) / sizeof(int))) reinterpret_cast<int*>(&s_tile)[tid] = reinterpret_cast<const int*>(tiles + ti)[tid];
-        __syncthreads();   // also: the previous tile's write phase has finished reading buf / T
-        const int task = s_tile.task;
+        const int cur = (ti - t0) & 1;
+        int nxt_word = 0;
+        if(tid < TILE_INTS && ti + 1 < t1) nxt_word = reinterpret_cast<const int*>(tiles + ti + 1)[tid];   // prefetch, consumed at the end of the iteration
+        const PermTile& tile = *reinterpret_cast<const PermTile*>(s_tile[cur]);
+        const int task = tile.task;
         if(task != staged) {
             const int* g = reinterpret_cast<const int*>(tasks + task);
             int* s = reinterpret_cast<int*>(&T);
@@ -141,7 +124,7 @@ permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const P
         }
         if(tid < PERM_MAXLEG) {
             const bool on = tid < T.nleg;
-            const int b = on ? s_tile.c[tid] * T.w[tid] : 0;
+            const int b = on ? tile.c[tid] * T.w[tid] : 0;
             s_base[tid] = b;
             s_lim[tid] = on ? min(T.w[tid], T.dims[tid] - b) : 1;
         }
@@ -152,7 +135,7 @@ permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const P
         if(T.src_count > 0) {
             long long sbase = T.src0_off;
             for(int l = 0; l < T.nleg; ++l) sbase += static_cast<long long>(s_base[l]) * T.src0_stride[l];
-            perm_read_dispatch(T, T.src0_stride, s_lim, src + sbase, T.src0_coeff, true, buf, tid);
+            perm_read(T, T.src0_stride, s_lim, src + sbase, T.src0_coeff, true, buf, tid);
         }
         for(int k = 1; k < T.src_count; ++k) {
             __syncthreads();   // S of the previous source no longer needed
@@ -160,7 +143,7 @@ permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const P
             __syncthreads();
             long long sbase = S.off;
             for(int l = 0; l < T.nleg; ++l) sbase += static_cast<long long>(s_base[l]) * S.sstride[l];
-            perm_read_dispatch(T, S.sstride, s_lim, src + sbase, S.coeff, false, buf, tid);
+            perm_read(T, S.sstride, s_lim, src + sbase, S.coeff, false, buf, tid);
         }
         __syncthreads();
 
@@ -173,8 +156,12 @@ permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const P
         for(int it = tid; it < T.items_d; it += PERM_THREADS) {
             int off, pos, cnt, gstep, sstep;
             if(!perm_item(T, T.tl_d, T.dstride, s_lim, T.nchunk_d, T.magic_chunk_d, strip, it, off, pos, cnt, gstep, sstep)) continue;
-            for(int i = 0; i < cnt; ++i) dp[off + i * gstep] = zero ? 0.0 : buf[pos + i * sstep];
+#pragma unroll
+            for(int i = 0; i < PERM_STRIP; ++i)
+                if(i < cnt) dp[off + i * gstep] = zero ? 0.0 : buf[pos + i * sstep];
         }
+        if(tid < TILE_INTS) s_tile[cur ^ 1][tid] = nxt_word;
+        __syncthreads();   // buf / T / s_base free for the next tile; next tile record visible
     }
 }
 

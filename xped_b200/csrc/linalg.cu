@@ -79,23 +79,6 @@ __global__ void svd_init_kernel(const double* __restrict__ A, double* __restrict
     }
 }
 
-__device__ __forceinline__ void panel_pair(int step, int g, int& p, int& q)
-{
-    // round-robin tournament on SP = 32 players: 31 steps x 16 disjoint pairs
-    int a, b;
-    if(g == 0) {
-        a = SP - 1;
-        b = step;
-    } else {
-        a = step + g;
-        if(a >= SP - 1) a -= SP - 1;
-        b = step - g;
-        if(b < 0) b += SP - 1;
-    }
-    p = a < b ? a : b;
-    q = a < b ? b : a;
-}
-
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -121,23 +104,34 @@ __device__ __forceinline__ bool jacobi_rotation(double a, double b, double c, do
 
 constexpr int XS_LD = SCH + 4;   // == 4 mod 16: the DMMA fragment loads of both operand roles hit 16 distinct banks per half-warp
 constexpr int VL_LD = SP + 4;
-constexpr int SVD_MAX_INNER = 1;   // one inner sweep per visit: same number of outer sweeps as full inner convergence (measured), 8x shorter rounds
+constexpr int G_LD = SP + 1;
+
+// Round-robin tournament by physically rotating the players ("caterpillar"): position 0 is fixed, the others move one
+// seat per step along 2 -> 4 -> ... -> 30 -> 31 -> 29 -> ... -> 1 -> 2.  The pairs of every step are then always the
+// seats (2g, 2g+1), all shared-memory addresses of the Jacobi step are loop invariants, and after 31 steps every pair
+// has met once and everybody is back in its original seat.
+__device__ __forceinline__ int seat_next(int x)
+{
+    if(x == 0) return 0;
+    if((x & 1) == 0) return x == SP - 2 ? SP - 1 : x + 2;   // top row moves right, the last one drops to the bottom row
+    return x == 1 ? 2 : x - 2;                              // bottom row moves left, the first one climbs to the top row
+}
 
 // One round of the block one-sided Jacobi method: every (sector block, column-block pair) of the round is handled by a
 // cluster of CL CTAs that split the rows.  Phase 1: Gram matrix G = X^T X of the 32-column panel on the FP64 tensor
 // cores (partial sums exchanged through distributed shared memory, summed in a fixed order so that all CTAs of the
-// cluster hold bit-identical G).  Phase 2: cyclic two-sided Jacobi on G in shared memory -- thread (k, l) owns the 2x2
-// intersection of rotation pair k's rows and pair l's columns, so a step needs only two barriers; every CTA of the
-// cluster runs it redundantly (deterministic => identical rotations).  Phase 3: X <- X Vl and V <- V Vl on the tensor
-// cores for this CTA's row slices.
+// cluster hold bit-identical G).  Phase 2: one cyclic two-sided Jacobi sweep on G in shared memory -- thread (k, l) owns
+// the 2x2 intersection of rotation pair k's rows and pair l's columns, G and Vl are double buffered and written to the
+// rotated seats, so a step costs ONE barrier and no index arithmetic; every CTA of the cluster runs it redundantly
+// (deterministic => identical rotations).  Phase 3: X <- X Vl and V <- V Vl on the tensor cores for this CTA's row
+// slices, the next 64-row chunk being prefetched into registers while the current one is multiplied.
 template <int CL>
 __global__ void __launch_bounds__(SVD_THREADS)
 svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock* __restrict__ blocks, const SvdTask* __restrict__ tasks, int* __restrict__ rotated)
 {
-    __shared__ __align__(16) double Xs[SP][XS_LD];
-    __shared__ __align__(16) double G[SP][SP + 1];
-    __shared__ __align__(16) double Vl[SP][VL_LD];
-    __shared__ __align__(16) double Gpart[SP][SP];   // this CTA's partial Gram matrix (read by the cluster peers)
+    __shared__ __align__(16) double Xs[SP * XS_LD];          // chunk staging [col][row]; during phase 2: second Vl buffer
+    __shared__ __align__(16) double Gs[2][SP * G_LD];        // Gs[1] doubles as this CTA's partial Gram matrix in phase 1
+    __shared__ __align__(16) double Vls[SP * VL_LD];
     __shared__ int colidx[SP];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -159,33 +153,45 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
         lo = min(nrows, static_cast<int>(crank) * per * SCH);
         hi = min(nrows, (static_cast<int>(crank) + 1) * per * SCH);
     };
-    auto load_chunk = [&](const double* __restrict__ M, int nrows, int r0) {
-        // 64 rows x 32 columns; a warp reads 32 consecutive rows of one column (256 B, coalesced)
+    // 64 rows x 32 columns per chunk; a warp reads 32 consecutive rows of one column (256 B, coalesced)
+    constexpr int PER_THREAD = (SP * SCH) / SVD_THREADS;
+    auto fetch = [&](const double* __restrict__ M, int nrows, int r0, double (&r)[PER_THREAD]) {
 #pragma unroll
-        for(int it = 0; it < (SP * SCH) / SVD_THREADS; ++it) {
+        for(int it = 0; it < PER_THREAD; ++it) {
             const int e = tid + it * SVD_THREADS;
             const int col = e / SCH, row = e % SCH;
             const int gr = r0 + row, gc = colidx[col];
-            Xs[col][row] = (gc >= 0 && gr < nrows) ? M[gr + static_cast<long long>(gc) * nrows] : 0.0;
+            r[it] = (gc >= 0 && gr < nrows) ? M[gr + static_cast<long long>(gc) * nrows] : 0.0;
+        }
+    };
+    auto stage = [&](const double (&r)[PER_THREAD]) {
+#pragma unroll
+        for(int it = 0; it < PER_THREAD; ++it) {
+            const int e = tid + it * SVD_THREADS;
+            Xs[(e / SCH) * XS_LD + (e % SCH)] = r[it];
         }
     };
 
     // ---- phase 1: Gram matrix. warp w owns output tiles (ti = w/2, tj = 2*(w&1) + {0,1}) of the 4x4 grid of 8x8 tiles
+    double* __restrict__ Gpart = Gs[1];
     {
         const int ti = warp >> 1, tj0 = (warp & 1) * 2;
         double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
         int lo, hi;
         slice(blk.rows, lo, hi);
         const double* __restrict__ Wm = W + blk.w_off;
+        double reg[PER_THREAD];
+        if(lo < hi) fetch(Wm, blk.rows, lo, reg);
         for(int r0 = lo; r0 < hi; r0 += SCH) {
-            load_chunk(Wm, blk.rows, r0);
+            stage(reg);
             __syncthreads();
+            if(r0 + SCH < hi) fetch(Wm, blk.rows, r0 + SCH, reg);   // prefetch the next chunk
 #pragma unroll 4
             for(int k0 = 0; k0 < SCH; k0 += 4) {
-                const double a = Xs[ti * 8 + (lane >> 2)][k0 + (lane & 3)];
+                const double a = Xs[(ti * 8 + (lane >> 2)) * XS_LD + k0 + (lane & 3)];
 #pragma unroll
                 for(int j = 0; j < 2; ++j) {
-                    const double b = Xs[(tj0 + j) * 8 + (lane >> 2)][k0 + (lane & 3)];
+                    const double b = Xs[((tj0 + j) * 8 + (lane >> 2)) * XS_LD + k0 + (lane & 3)];
                     dmma_8x8x4(acc[j][0], acc[j][1], a, b);
                 }
             }
@@ -194,8 +200,8 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
 #pragma unroll
         for(int j = 0; j < 2; ++j) {
             const int r = ti * 8 + (lane >> 2), c = (tj0 + j) * 8 + 2 * (lane & 3);
-            Gpart[r][c] = acc[j][0];
-            Gpart[r][c + 1] = acc[j][1];
+            Gpart[r * G_LD + c] = acc[j][0];
+            Gpart[r * G_LD + c + 1] = acc[j][1];
         }
     }
     if(CL > 1) {
@@ -204,11 +210,12 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
     } else {
         __syncthreads();
     }
+    double* __restrict__ Vl1 = Xs;   // second Vl buffer (aliases the chunk staging area, unused in phase 2)
     for(int e = tid; e < SP * SP; e += SVD_THREADS) {
         const int r = e / SP, c = e % SP;
         double sum = 0.0;
         if(CL > 1) {
-            const unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(&Gpart[r][c]));
+            const unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(&Gpart[r * G_LD + c]));
 #pragma unroll
             for(int cr = 0; cr < CL; ++cr) {   // fixed order: bit-identical in every CTA of the cluster
                 unsigned remote;
@@ -218,89 +225,116 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
                 sum += v;
             }
         } else {
-            sum = Gpart[r][c];
+            sum = Gpart[r * G_LD + c];
         }
-        G[r][c] = sum;
-        Vl[r][c] = (r == c) ? 1.0 : 0.0;
+        Gs[0][r * G_LD + c] = sum;
+        Vl1[r * VL_LD + c] = (r == c) ? 1.0 : 0.0;   // the sweep starts in buffer 1 and ends (31 swaps later) in Vls
     }
-    if(CL > 1) {   // peers must not exit (or overwrite Gpart) before everybody has read it
+    if(CL > 1) {   // peers must not overwrite their Gpart (= Gs[1]) or exit before everybody has read it
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     } else {
         __syncthreads();
     }
 
-    // ---- phase 2: cyclic two-sided Jacobi on G; thread (k, l) owns rows {p_k, q_k} x columns {p_l, q_l}
-    const int k = tid >> 4, l = tid & 15;
-    const double tol2 = blk.tol * blk.tol;
-    int total = 0;
-    for(int sweep = 0; sweep < SVD_MAX_INNER; ++sweep) {
+    // ---- phase 2: one cyclic two-sided Jacobi sweep on G; thread (k, l): rows {2k, 2k+1} x columns {2l, 2l+1}
+    {
+        const int k = tid >> 4, l = tid & 15;
+        const double tol2 = blk.tol * blk.tol;
+        const int r0 = 2 * k, r1 = 2 * k + 1, c0 = 2 * l, c1 = 2 * l + 1;
+        const int nr0 = seat_next(r0), nr1 = seat_next(r1), nc0 = seat_next(c0), nc1 = seat_next(c1);
+        // loop-invariant offsets
+        const int g00 = r0 * G_LD + c0, g01 = r0 * G_LD + c1, g10 = r1 * G_LD + c0, g11 = r1 * G_LD + c1;
+        const int h00 = nr0 * G_LD + nc0, h01 = nr0 * G_LD + nc1, h10 = nr1 * G_LD + nc0, h11 = nr1 * G_LD + nc1;
+        const int pa = c0 * G_LD + c0, pb = c1 * G_LD + c1, pc = c0 * G_LD + c1;   // pivots of column pair l
+        const int v0p = k * VL_LD + c0, v0q = k * VL_LD + c1, v1p = (k + 16) * VL_LD + c0, v1q = (k + 16) * VL_LD + c1;
+        const int w0p = k * VL_LD + nc0, w0q = k * VL_LD + nc1, w1p = (k + 16) * VL_LD + nc0, w1q = (k + 16) * VL_LD + nc1;
         int any = 0;
-        for(int step = 0; step < SP - 1; ++step) {
-            int pk, qk, pl, ql;
-            panel_pair(step, k, pk, qk);
-            panel_pair(step, l, pl, ql);
-            // every thread computes the rotation of its column pair l only; lane l of the warp (l = lane & 15) holds pair k's
-            double ck, sk, cl, sl;
-            const bool rl = jacobi_rotation(G[pl][pl], G[ql][ql], G[pl][ql], tol2, cl, sl);
-            ck = __shfl_sync(0xffffffffu, cl, k);
-            sk = __shfl_sync(0xffffffffu, sl, k);
+        auto jacobi_step = [&](const double* __restrict__ Gc, double* __restrict__ Gn, const double* __restrict__ Vc, double* __restrict__ Vn) {
+            double cl, sl;
+            const bool rl = jacobi_rotation(Gc[pa], Gc[pb], Gc[pc], tol2, cl, sl);
+            const double ck = __shfl_sync(0xffffffffu, cl, k);   // lane k of the warp (l == k there) holds pair k's rotation
+            const double sk = __shfl_sync(0xffffffffu, sl, k);
             const bool rk = __shfl_sync(0xffffffffu, static_cast<int>(rl), k) != 0;
-            any |= rk ? 1 : 0;
-            // G <- J^T G J on the owned 2x2 block
-            const double g00 = G[pk][pl], g01 = G[pk][ql], g10 = G[qk][pl], g11 = G[qk][ql];
-            // Vl <- Vl J: rows k and k + 16, columns {p_l, q_l}
-            const double v0p = Vl[k][pl], v0q = Vl[k][ql], v1p = Vl[k + 16][pl], v1q = Vl[k + 16][ql];
-            __syncthreads();   // everybody has read the old values
-            if(rk || rl) {
-                // columns: g[:, p] = c g[:, p] - s g[:, q];  g[:, q] = s g[:, p] + c g[:, q]
-                const double h00 = cl * g00 - sl * g01, h01 = sl * g00 + cl * g01;
-                const double h10 = cl * g10 - sl * g11, h11 = sl * g10 + cl * g11;
-                // rows: g[p, :] = c g[p, :] - s g[q, :];  g[q, :] = s g[p, :] + c g[q, :]
-                double n00 = ck * h00 - sk * h10, n01 = ck * h01 - sk * h11;
-                double n10 = sk * h00 + ck * h10, n11 = sk * h01 + ck * h11;
-                if(k == l && rk) {   // the pivot block itself: off-diagonal annihilated exactly
-                    n01 = 0.0;
-                    n10 = 0.0;
-                }
-                G[pk][pl] = n00;
-                G[pk][ql] = n01;
-                G[qk][pl] = n10;
-                G[qk][ql] = n11;
+            any |= rl ? 1 : 0;
+            const double a00 = Gc[g00], a01 = Gc[g01], a10 = Gc[g10], a11 = Gc[g11];
+            // columns: g[:, p] = c g[:, p] - s g[:, q];  g[:, q] = s g[:, p] + c g[:, q]
+            const double b00 = cl * a00 - sl * a01, b01 = sl * a00 + cl * a01;
+            const double b10 = cl * a10 - sl * a11, b11 = sl * a10 + cl * a11;
+            // rows: g[p, :] = c g[p, :] - s g[q, :];  g[q, :] = s g[p, :] + c g[q, :]
+            double n00 = ck * b00 - sk * b10, n01 = ck * b01 - sk * b11;
+            double n10 = sk * b00 + ck * b10, n11 = sk * b01 + ck * b11;
+            if(k == l && rk) {   // the pivot block itself: off-diagonal annihilated exactly
+                n01 = 0.0;
+                n10 = 0.0;
             }
-            if(rl) {
-                Vl[k][pl] = cl * v0p - sl * v0q;
-                Vl[k][ql] = sl * v0p + cl * v0q;
-                Vl[k + 16][pl] = cl * v1p - sl * v1q;
-                Vl[k + 16][ql] = sl * v1p + cl * v1q;
-            }
+            Gn[h00] = n00;
+            Gn[h01] = n01;
+            Gn[h10] = n10;
+            Gn[h11] = n11;
+            const double x0p = Vc[v0p], x0q = Vc[v0q], x1p = Vc[v1p], x1q = Vc[v1q];
+            Vn[w0p] = cl * x0p - sl * x0q;
+            Vn[w0q] = sl * x0p + cl * x0q;
+            Vn[w1p] = cl * x1p - sl * x1q;
+            Vn[w1q] = sl * x1p + cl * x1q;
             __syncthreads();
+        };
+        // double buffering: even steps Gs[0] -> Gs[1], Vl1 -> Vls; odd steps back
+#pragma unroll 1
+        for(int step = 0; step < (SP - 2) / 2; ++step) {
+            jacobi_step(Gs[0], Gs[1], Vl1, Vls);
+            jacobi_step(Gs[1], Gs[0], Vls, Vl1);
         }
+        jacobi_step(Gs[0], Gs[1], Vl1, Vls);
+        // 31 swaps: the rotation matrix now sits in Vls, everybody back in the original seat
         any = __syncthreads_or(any);
-        if(!any) break;
-        total = 1;
+        if(!any) return;   // panel already orthogonal (uniform over the cluster: identical G everywhere)
     }
-    if(!total) return;   // panel already orthogonal (uniform over the cluster: identical G everywhere)
     if(tid == 0 && crank == 0) atomicExch(rotated, 1);
 
     // ---- phase 3: X <- X * Vl for this CTA's rows of W and of V. warp w owns 8 rows of the 64-row chunk, all 32 columns.
-    for(int which = 0; which < 2; ++which) {
-        double* __restrict__ M = which == 0 ? W + blk.w_off : V + blk.v_off;
-        const int nrows = which == 0 ? blk.rows : blk.cols;
-        int lo, hi;
-        slice(nrows, lo, hi);
-        for(int r0 = lo; r0 < hi; r0 += SCH) {
-            load_chunk(M, nrows, r0);
+    {
+        int wlo, whi, vlo, vhi;
+        slice(blk.rows, wlo, whi);
+        slice(blk.cols, vlo, vhi);
+        const int nw = (whi - wlo + SCH - 1) / SCH, nv = (vhi - vlo + SCH - 1) / SCH;
+        double reg[PER_THREAD];
+        auto chunk_of = [&](int c, double*& M, int& nrows, int& r0) {
+            if(c < nw) {
+                M = W + blk.w_off;
+                nrows = blk.rows;
+                r0 = wlo + c * SCH;
+            } else {
+                M = V + blk.v_off;
+                nrows = blk.cols;
+                r0 = vlo + (c - nw) * SCH;
+            }
+        };
+        double* M;
+        int nrows, r0;
+        if(nw + nv > 0) {
+            chunk_of(0, M, nrows, r0);
+            fetch(M, nrows, r0, reg);
+        }
+        for(int c = 0; c < nw + nv; ++c) {
+            chunk_of(c, M, nrows, r0);
+            stage(reg);
             __syncthreads();
+            if(c + 1 < nw + nv) {   // prefetch the next chunk while this one is multiplied
+                double* M2;
+                int n2, r2;
+                chunk_of(c + 1, M2, n2, r2);
+                fetch(M2, n2, r2, reg);
+            }
             double out[4][2];
 #pragma unroll
             for(int j = 0; j < 4; ++j) out[j][0] = out[j][1] = 0.0;
 #pragma unroll
             for(int k0 = 0; k0 < SP; k0 += 4) {
-                const double a = Xs[k0 + (lane & 3)][warp * 8 + (lane >> 2)];   // A[row][k] = X[row][k]
+                const double a = Xs[(k0 + (lane & 3)) * XS_LD + warp * 8 + (lane >> 2)];   // A[row][k] = X[row][k]
 #pragma unroll
                 for(int j = 0; j < 4; ++j) {
-                    const double b = Vl[k0 + (lane & 3)][j * 8 + (lane >> 2)];   // B[k][col] = Vl[k][col]
+                    const double b = Vls[(k0 + (lane & 3)) * VL_LD + j * 8 + (lane >> 2)];   // B[k][col] = Vl[k][col]
                     dmma_8x8x4(out[j][0], out[j][1], a, b);
                 }
             }

@@ -27,6 +27,8 @@ typedef struct xb_ctx xb_ctx;
 typedef struct xb_basis xb_basis;   /* Qbasis<Symmetry,1>  (include/Xped/Core/Qbasis.hpp:37-268) */
 typedef struct xb_tensor xb_tensor; /* Tensor<double,Rank,CoRank,Symmetry> (include/Xped/Core/Tensor.hpp:59-444) */
 typedef struct xb_ctm xb_ctm;       /* CTM<double,Symmetry,2> (include/Xped/PEPS/CTM.hpp:60-312) */
+typedef struct xb_dist_plan xb_dist_plan; /* exchange plan of one sector-sharded permute (no reference counterpart: the
+                                             reference's distributed storage is the Cyclops backend, Interfaces/TensorInterface_Cyclops_impl.cpp) */
 
 enum xb_status {
     XB_OK = 0,
@@ -47,6 +49,9 @@ const char* xb_version(void);
 
 /* ---- context: one per GPU / host thread (replaces mpi::XpedWorld threading, include/Xped/Util/Mpi.hpp:17-47) */
 int xb_ctx_create(xb_ctx** ctx, int device, const xb_sym_factor* factors, int n_factors);
+/* host-metadata-only context (bases, layouts, owner maps, exchange plans) for a process without a GPU; every call that
+ * would touch tensor data fails with XB_ERR_NO_DEVICE.  It is NOT a CPU fallback: it cannot hold or move tensor data. */
+int xb_ctx_create_planning(xb_ctx** ctx, const xb_sym_factor* factors, int n_factors);
 int xb_ctx_free(xb_ctx* ctx);
 int xb_ctx_sync(xb_ctx* ctx);
 int xb_ctx_nq(const xb_ctx* ctx);
@@ -124,6 +129,45 @@ int xb_decompose(xb_ctx* ctx, const xb_tensor* T1, const xb_tensor* T2, int64_t 
 /* contract_L / contract_R  src/MPS/MpsContractions.cpp:11-51 / :54-105 */
 int xb_contract_L(xb_ctx* ctx, const xb_tensor* Bold, const xb_tensor* Bra, const xb_tensor* Ket, xb_tensor** Bnew);
 int xb_contract_R(xb_ctx* ctx, const xb_tensor* Bold, const xb_tensor* Bra, const xb_tensor* Ket, xb_tensor** Bnew);
+
+/* ---- sector sharding over the GPUs of one box ----------------------------------------------------
+ * One process / context per GPU.  A sharded tensor = on every rank a tensor holding only the sectors that rank owns
+ * (xb_tensor_create_sectors), plus an owner map over the canonical sector list that every rank computes identically
+ * (xb_dist_owner_lpt: deterministic LPT greedy).  Products, decompositions and element-wise maps act on the shards
+ * (sectors are independent, src/Core/TensorBase.cpp:262-279); a permute moves sub-blocks between sectors
+ * (src/Core/Tensor.cpp:198-208) and has ONE exchange step: pack -> alltoallv (issued by the host framework over NCCL with the
+ * counts below) -> gather.  The reference's distributed path is MPI/Cyclops (XPED_USE_MPI, include/Xped/Util/Mpi.hpp). */
+/* canonical structure of Tensor(domain, codomain) without allocating it; q == NULL: only the sector count */
+int xb_layout_structure(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int* n_sectors, int* q,
+                        int64_t* rows, int64_t* cols, int64_t* offsets);
+/* a shard: Tensor(domain, codomain) holding only the listed sectors, in that order, zero-initialised */
+int xb_tensor_create_sectors(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, const int* q, int n_sectors,
+                             xb_tensor** out);
+/* counter-based fill of a shard: sector i takes the values the unsharded tensor has at storage offset global_offsets[i] */
+int xb_tensor_set_random_at(xb_tensor* t, uint64_t seed, const int64_t* global_offsets);
+int xb_dist_owner_lpt(const double* cost, int n, int world, int* owner);
+/* plan of permute<shift,p> (adjoint != 0: permute_adj) of the canonical tensor on (domain | codomain) for rank my_rank of world;
+ * owner_in: one rank per input sector; owner_out: one rank per output sector or NULL (LPT on rows*cols*(rows+cols)) */
+int xb_dist_permute_plan(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n,
+                         int adjoint, const int* owner_in, const int* owner_out, int n_out_sectors, int my_rank, int world, xb_dist_plan** out);
+int xb_dist_plan_free(xb_dist_plan* plan);
+/* alltoallv counts in doubles, `world` entries each; segments are ordered by peer rank */
+int xb_dist_plan_counts(const xb_dist_plan* plan, int64_t* send_counts, int64_t* recv_counts);
+/* output side: sector count and owner map of the output's canonical sectors, its leg bases (rank + corank fresh handles); any pointer may be NULL */
+int xb_dist_plan_out(const xb_dist_plan* plan, int* n_out_sectors, int* owner_out, xb_basis** legs, int* out_rank, int* out_corank);
+/* sector labels of this rank's input (which = 0) / output (which = 1) shard; q == NULL: only the count */
+int xb_dist_plan_local_sectors(const xb_dist_plan* plan, int which, int* n_sectors, int* q);
+/* the plan's work lists as flat int64 records (introspection, CPU tests of the exchange logic); out == NULL: only the count.
+ * which = 0 pack:    peer, send_off, src_off, nleg, dims[16], src_stride[16]
+ *         1 tasks:   dst_off, nleg, src_begin, src_count, dims[16], dst_stride[16]
+ *         2 sources: remote, off (shard offset, or receive-buffer offset if remote), coeff (double bits), 0, src_stride[16] */
+int xb_dist_plan_records(const xb_dist_plan* plan, int which, int64_t* n_records, int64_t* out);
+/* the three device steps of a sharded permute; d_send / d_recv are device buffers of sum(send_counts) / sum(recv_counts) doubles */
+int xb_dist_permute_pack(xb_ctx* ctx, const xb_dist_plan* plan, const xb_tensor* local_in, double* d_send);
+int xb_dist_permute_local(xb_ctx* ctx, const xb_dist_plan* plan, const xb_tensor* local_in, xb_tensor** local_out);
+int xb_dist_permute_remote(xb_ctx* ctx, const xb_dist_plan* plan, const xb_tensor* local_in, const double* d_recv, xb_tensor* local_out);
+/* operator* on shards: the result holds exactly the listed sectors (the ones this rank owns of the product) */
+int xb_multiply_sectors(xb_ctx* ctx, const xb_tensor* a, int adj_a, const xb_tensor* b, int adj_b, const int* q, int n_sectors, xb_tensor** out);
 
 /* ---- CTM driver (1x1 unit cell, TRank = 2, corner projectors)  src/PEPS/CTM.cpp:45-244,385-420,924-1760 ------
  * A: iPEPS site tensor Tensor<double,2,3> (left, top | right, bottom, phys), include/Xped/PEPS/iPEPS.hpp. */

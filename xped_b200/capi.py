@@ -33,6 +33,7 @@ SIGNATURES = {
     "xb_last_error": (C.c_char_p, []),
     "xb_version": (C.c_char_p, []),
     "xb_ctx_create": (C.c_int, [PP, C.c_int, C.POINTER(SymFactor), C.c_int]),
+    "xb_ctx_create_planning": (C.c_int, [PP, C.POINTER(SymFactor), C.c_int]),
     "xb_ctx_free": (C.c_int, [P]),
     "xb_ctx_sync": (C.c_int, [P]),
     "xb_ctx_nq": (C.c_int, [P]),
@@ -78,6 +79,20 @@ SIGNATURES = {
     "xb_decompose": (C.c_int, [P, P, P, C.c_int64, PP, PP]),
     "xb_contract_L": (C.c_int, [P, P, P, P, PP]),
     "xb_contract_R": (C.c_int, [P, P, P, P, PP]),
+    "xb_layout_structure": (C.c_int, [P, PP, C.c_int, PP, C.c_int, IP, IP, LP, LP, LP]),
+    "xb_tensor_create_sectors": (C.c_int, [P, PP, C.c_int, PP, C.c_int, IP, C.c_int, PP]),
+    "xb_tensor_set_random_at": (C.c_int, [P, C.c_uint64, LP]),
+    "xb_dist_owner_lpt": (C.c_int, [DP, C.c_int, C.c_int, IP]),
+    "xb_dist_permute_plan": (C.c_int, [P, PP, C.c_int, PP, C.c_int, C.c_int, IP, C.c_int, C.c_int, IP, IP, C.c_int, C.c_int, C.c_int, PP]),
+    "xb_dist_plan_free": (C.c_int, [P]),
+    "xb_dist_plan_counts": (C.c_int, [P, LP, LP]),
+    "xb_dist_plan_out": (C.c_int, [P, IP, IP, PP, IP, IP]),
+    "xb_dist_plan_local_sectors": (C.c_int, [P, C.c_int, IP, IP]),
+    "xb_dist_plan_records": (C.c_int, [P, C.c_int, LP, LP]),
+    "xb_dist_permute_pack": (C.c_int, [P, P, P, C.c_void_p]),
+    "xb_dist_permute_local": (C.c_int, [P, P, P, PP]),
+    "xb_dist_permute_remote": (C.c_int, [P, P, P, C.c_void_p, P]),
+    "xb_multiply_sectors": (C.c_int, [P, P, C.c_int, P, C.c_int, IP, C.c_int, PP]),
     "xb_ctm_create": (C.c_int, [P, P, C.c_int64, PP]),
     "xb_ctm_free": (C.c_int, [P]),
     "xb_ctm_step": (C.c_int, [P]),

@@ -16,6 +16,7 @@ struct xb_ctx { Context impl; xb_ctx(int dev, const std::vector<Factor>& f) : im
 struct xb_basis { xb_ctx* ctx; BasisPtr b; };
 struct xb_tensor { xb_ctx* ctx; std::unique_ptr<Tensor> t; };
 struct xb_ctm { xb_ctx* ctx; std::unique_ptr<Ctm> c; };
+struct xb_dist_plan { xb_ctx* ctx; std::shared_ptr<DistPermutePlan> p; };
 
 namespace {
 thread_local std::string g_err;
@@ -77,9 +78,12 @@ int xb_ctx_create(xb_ctx** ctx, int device, const xb_sym_factor* factors, int n_
             f.push_back({static_cast<Kind>(factors[i].kind), factors[i].N, factors[i].fermionic != 0});
         }
         if(f.empty()) f.push_back({Kind::U0, 0, false});
+        if(device < -1) throw std::invalid_argument("device index < -1");
         *ctx = new xb_ctx(device, f);
     });
 }
+
+int xb_ctx_create_planning(xb_ctx** ctx, const xb_sym_factor* factors, int n_factors) { return xb_ctx_create(ctx, -1, factors, n_factors); }
 
 int xb_ctx_free(xb_ctx* ctx)
 {
@@ -90,6 +94,7 @@ int xb_ctx_sync(xb_ctx* ctx)
 {
     return guard([&] {
         need(ctx, "ctx");
+        if(ctx->impl.planning_only()) return;
         ctx->impl.sync();
     });
 }
@@ -334,6 +339,200 @@ int xb_tensor_set_random(xb_tensor* t, uint64_t seed)
     return guard([&] {
         need(t, "tensor");
         t->ctx->impl.fill(*t->t, 2, 0.0, seed);
+    });
+}
+
+
+// ---------------------------------------------------------------------------------------------- sector sharding
+namespace {
+void collect_bases(xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, std::vector<BasisPtr>& d, std::vector<BasisPtr>& c)
+{
+    if(rank < 0 || corank < 0 || rank > MAXR || corank > MAXR) throw std::invalid_argument("rank/corank out of range");
+    for(int i = 0; i < rank; ++i) {
+        need(domain[i], "domain basis");
+        d.push_back(domain[i]->b);
+    }
+    for(int i = 0; i < corank; ++i) {
+        need(codomain[i], "codomain basis");
+        c.push_back(codomain[i]->b);
+    }
+}
+}   // namespace
+
+int xb_layout_structure(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int* n_sectors, int* q, int64_t* rows,
+                        int64_t* cols, int64_t* offsets)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(n_sectors, "n_sectors");
+        std::vector<BasisPtr> d, c;
+        collect_bases(domain, rank, codomain, corank, d, c);
+        LayoutPtr L = ctx->impl.layout(d, c);
+        *n_sectors = static_cast<int>(L->sector.size());
+        if(!q) return;
+        const int nq = ctx->impl.sym->Nq();
+        for(size_t i = 0; i < L->sector.size(); ++i) {
+            for(int k = 0; k < nq; ++k) q[i * nq + k] = L->sector[i][k];
+            rows[i] = L->rows[i];
+            cols[i] = L->cols[i];
+            offsets[i] = L->off[i];
+        }
+    });
+}
+
+int xb_tensor_create_sectors(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, const int* q, int n_sectors,
+                             xb_tensor** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(out, "out");
+        std::vector<BasisPtr> d, c;
+        collect_bases(domain, rank, codomain, corank, d, c);
+        std::vector<Q> qs;
+        for(int i = 0; i < n_sectors; ++i) qs.push_back(make_q(*ctx->impl.sym, q + i * ctx->impl.sym->Nq()));
+        *out = wrap(ctx, new Tensor(&ctx->impl, ctx->impl.layout_custom(d, c, qs), true));
+    });
+}
+
+int xb_tensor_set_random_at(xb_tensor* t, uint64_t seed, const int64_t* global_offsets)
+{
+    return guard([&] {
+        need(t, "tensor");
+        need(global_offsets, "global_offsets");
+        Context& c = t->ctx->impl;
+        const Layout& L = *t->t->layout;
+        for(size_t i = 0; i < L.sector.size(); ++i) {
+            launch_fill_random(t->t->d + L.off[i], seed, L.rows[i] * L.cols[i], c.stream, global_offsets[i]);
+            ++c.launches;
+        }
+    });
+}
+
+int xb_dist_owner_lpt(const double* cost, int n, int world, int* owner)
+{
+    return guard([&] {
+        need(owner, "owner");
+        std::vector<double> v(cost, cost + (n > 0 ? n : 0));
+        std::vector<int> o = lpt_owner(v, world);
+        std::copy(o.begin(), o.end(), owner);
+    });
+}
+
+int xb_dist_permute_plan(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n,
+                         int adjoint, const int* owner_in, const int* owner_out, int n_out_sectors, int my_rank, int world, xb_dist_plan** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(out, "out");
+        need(owner_in, "owner_in");
+        std::vector<BasisPtr> d, c;
+        collect_bases(domain, rank, codomain, corank, d, c);
+        LayoutPtr L = ctx->impl.layout(d, c);
+        std::vector<int> oi(owner_in, owner_in + L->sector.size()), oo;
+        if(owner_out) oo.assign(owner_out, owner_out + n_out_sectors);
+        *out = new xb_dist_plan{ctx, ctx->impl.dist_permute_plan(L, shift, std::vector<int>(p, p + n), adjoint != 0, oi, oo, my_rank, world)};
+    });
+}
+
+int xb_dist_plan_free(xb_dist_plan* plan)
+{
+    return guard([&] { delete plan; });
+}
+
+int xb_dist_plan_counts(const xb_dist_plan* plan, int64_t* send_counts, int64_t* recv_counts)
+{
+    return guard([&] {
+        need(plan, "plan");
+        std::copy(plan->p->send_counts.begin(), plan->p->send_counts.end(), send_counts);
+        std::copy(plan->p->recv_counts.begin(), plan->p->recv_counts.end(), recv_counts);
+    });
+}
+
+int xb_dist_plan_out(const xb_dist_plan* plan, int* n_out_sectors, int* owner_out, xb_basis** legs, int* out_rank, int* out_corank)
+{
+    return guard([&] {
+        need(plan, "plan");
+        const DistPermutePlan& P = *plan->p;
+        if(n_out_sectors) *n_out_sectors = static_cast<int>(P.owner_out.size());
+        if(owner_out) std::copy(P.owner_out.begin(), P.owner_out.end(), owner_out);
+        const Layout& L = *P.out_global;
+        if(out_rank) *out_rank = L.rank();
+        if(out_corank) *out_corank = L.corank();
+        if(legs)
+            for(int i = 0; i < L.rank() + L.corank(); ++i) legs[i] = new xb_basis{plan->ctx, i < L.rank() ? L.dom[i] : L.cod[i - L.rank()]};
+    });
+}
+
+int xb_dist_plan_local_sectors(const xb_dist_plan* plan, int which, int* n_sectors, int* q)
+{
+    return guard([&] {
+        need(plan, "plan");
+        need(n_sectors, "n_sectors");
+        const Layout& L = which == 0 ? *plan->p->in_local : *plan->p->out_local;
+        *n_sectors = static_cast<int>(L.sector.size());
+        if(!q) return;
+        const int nq = plan->ctx->impl.sym->Nq();
+        for(size_t i = 0; i < L.sector.size(); ++i)
+            for(int k = 0; k < nq; ++k) q[i * nq + k] = L.sector[i][k];
+    });
+}
+
+int xb_dist_plan_records(const xb_dist_plan* plan, int which, int64_t* n_records, int64_t* out)
+{
+    return guard([&] {
+        need(plan, "plan");
+        need(n_records, "n_records");
+        const DistPermutePlan& P = *plan->p;
+        const std::vector<int64_t>& v = which == 0 ? P.pack_records : which == 1 ? P.task_records : P.src_records;
+        const int width = which == 0 ? DistPermutePlan::PACK_REC : which == 1 ? DistPermutePlan::TASK_REC : DistPermutePlan::SRC_REC;
+        if(which < 0 || which > 2) throw std::invalid_argument("xb_dist_plan_records: which must be 0 (pack), 1 (tasks) or 2 (sources)");
+        *n_records = static_cast<int64_t>(v.size()) / width;
+        if(out) std::copy(v.begin(), v.end(), out);
+    });
+}
+
+int xb_dist_permute_pack(xb_ctx* ctx, const xb_dist_plan* plan, const xb_tensor* local_in, double* d_send)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(plan, "plan");
+        need(local_in, "local_in");
+        ctx->impl.dist_pack(*plan->p, *local_in->t, d_send);
+    });
+}
+
+int xb_dist_permute_local(xb_ctx* ctx, const xb_dist_plan* plan, const xb_tensor* local_in, xb_tensor** local_out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(plan, "plan");
+        need(local_in, "local_in");
+        need(local_out, "local_out");
+        *local_out = wrap(ctx, ctx->impl.dist_local(*plan->p, *local_in->t));
+    });
+}
+
+int xb_dist_permute_remote(xb_ctx* ctx, const xb_dist_plan* plan, const xb_tensor* local_in, const double* d_recv, xb_tensor* local_out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(plan, "plan");
+        need(local_in, "local_in");
+        need(local_out, "local_out");
+        ctx->impl.dist_remote(*plan->p, *local_in->t, d_recv, *local_out->t);
+    });
+}
+
+int xb_multiply_sectors(xb_ctx* ctx, const xb_tensor* a, int adj_a, const xb_tensor* b, int adj_b, const int* q, int n_sectors, xb_tensor** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(a, "a");
+        need(b, "b");
+        need(out, "out");
+        std::vector<Q> qs;
+        for(int i = 0; i < n_sectors; ++i) qs.push_back(make_q(*ctx->impl.sym, q + i * ctx->impl.sym->Nq()));
+        *out = wrap(ctx, ctx->impl.multiply_sectors(*a->t, adj_a != 0, *b->t, adj_b != 0, &qs));
     });
 }
 

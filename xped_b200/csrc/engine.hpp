@@ -96,6 +96,29 @@ struct PermutePlan
     ~PermutePlan();
 };
 
+// Sector-sharded permute: every rank owns whole sectors; a permute has ONE exchange step.
+//   pack    owned source sub-blocks that a peer's destination tasks need -> dense segments of the send buffer (one launch)
+//   (NCCL alltoallv of the send buffer, issued by the host framework: torch.distributed.all_to_all_single)
+//   local   destination tasks whose sources are all owned by this rank (overlaps the exchange)
+//   remote  destination tasks with at least one received source; source offsets >= `split` address the receive buffer
+struct DistPermutePlan
+{
+    int rank = 0, world = 1;
+    LayoutPtr in_global, out_global, in_local, out_local;
+    std::vector<int> owner_in, owner_out;   // per sector of the global layouts
+    std::vector<int64_t> send_counts, recv_counts, send_displs, recv_displs;   // doubles, per peer
+    int64_t send_total = 0, recv_total = 0;
+    int64_t split = 0;   // = in_local->size
+    PermutePlan pack, local, remote;
+    int64_t bytes_local = 0;   // algorithmic bytes moved through this rank's HBM by local + remote: 8 * (N_in_local + N_out_local)
+    // host copies of the three work lists for introspection and the CPU (gloo) tests: flat int64 records
+    static constexpr int MAXL = 16;
+    static constexpr int PACK_REC = 4 + 2 * MAXL;   // peer, send_off, src_off, nleg, dims[16], sstride[16]
+    static constexpr int TASK_REC = 4 + 2 * MAXL;   // dst_off, nleg, src_begin, src_count, dims[16], dstride[16]
+    static constexpr int SRC_REC = 4 + MAXL;        // remote flag, off (local tensor or receive buffer), coeff bits, 0, sstride[16]
+    std::vector<int64_t> pack_records, task_records, src_records;
+};
+
 constexpr int GEMM_TILE_N = 64;   // CTA tile of gemm_grouped_kernel is tile_m x 64 with tile_m = 128 (large sectors) or 64
 
 struct GemmItem   // one (sector, tile) of a grouped product
@@ -147,6 +170,14 @@ public:
     LayoutPtr layout(const std::vector<BasisPtr>& dom, const std::vector<BasisPtr>& cod);
     LayoutPtr layout_custom(const std::vector<BasisPtr>& dom, const std::vector<BasisPtr>& cod, const std::vector<Q>& sectors);
     std::shared_ptr<PermutePlan> permute_plan(const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan);
+    // sector-sharded permute: exchange plan of rank `rank` for the global tensor layout `in` (cached)
+    std::shared_ptr<DistPermutePlan> dist_permute_plan(const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan,
+                                                       const std::vector<int>& owner_in, const std::vector<int>& owner_out, int rank, int world);
+    void dist_pack(const DistPermutePlan& plan, const Tensor& local_in, double* d_send);
+    Tensor* dist_local(const DistPermutePlan& plan, const Tensor& local_in);
+    void dist_remote(const DistPermutePlan& plan, const Tensor& local_in, const double* d_recv, Tensor& local_out);
+    Tensor* multiply_sectors(const Tensor& a, bool adj_a, const Tensor& b, bool adj_b, const std::vector<Q>* out_sectors);
+    bool planning_only() const { return device < 0; }
 
     // ---- ops (all asynchronous on `stream` unless they return host values) ----
     Tensor* permute(const Tensor& t, int shift, const std::vector<int>& pi);
@@ -199,6 +230,7 @@ private:
     std::unordered_map<std::string, BasisPtr> coupled_cache_;
     std::unordered_map<std::string, LayoutPtr> layout_cache_;
     std::unordered_map<std::string, std::shared_ptr<PermutePlan>> plan_cache_;
+    std::unordered_map<std::string, std::shared_ptr<DistPermutePlan>> dist_plan_cache_;
     void* scratch_ = nullptr;
     size_t scratch_bytes_ = 0;
     void* pinned_ = nullptr;
@@ -238,13 +270,17 @@ struct ProfScope
 
 // ---- kernel launchers (kernels.cu) ----
 void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s);
+// sources with offset >= split are read from src2 + (offset - split): sharded permute reading [local shard | receive buffer]
+void launch_permute2(const double* src, const double* src2, long long split, double* dst, const PermutePlan& plan, cudaStream_t s);
+// deterministic LPT greedy (largest cost first, ties by index, least-loaded rank, ties lowest rank)
+std::vector<int> lpt_owner(const std::vector<double>& cost, int world);
 void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, int tile_m, cudaStream_t s);
 void launch_scale_copy(const double* x, double* y, double alpha, int64_t n, cudaStream_t s);
 void launch_axpby(const double* x, const double* y, double* z, double alpha, double beta, int64_t n, cudaStream_t s);
 void launch_absmax(const double* x, int64_t n, double* d_out, cudaStream_t s);
 void launch_scale_by_inv(const double* x, double* y, const double* d_scalar, int64_t n, cudaStream_t s);
 void launch_fill_constant(double* x, double v, int64_t n, cudaStream_t s);
-void launch_fill_random(double* x, uint64_t seed, int64_t n, cudaStream_t s);
+void launch_fill_random(double* x, uint64_t seed, int64_t n, cudaStream_t s, int64_t index_base = 0);   // element i gets the value of counter i + index_base
 struct BlockDesc { long long off; int rows, cols; double weight; };
 void launch_transpose_blocks(const double* src, double* dst, const BlockDesc* d_src_blocks, const long long* d_dst_off, int nblocks, cudaStream_t s);
 void launch_set_identity(double* x, const BlockDesc* d_blocks, int nblocks, cudaStream_t s);

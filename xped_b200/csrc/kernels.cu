@@ -93,8 +93,8 @@ __device__ __forceinline__ void perm_read(const PermTask& T, const int* __restri
 // staged once; the next tile's record is prefetched while the current tile moves).  Per tile: read phase (source
 // order) -> barrier -> write phase (destination order) -> barrier.
 __global__ void __launch_bounds__(PERM_THREADS, 4)
-permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const PermTask* __restrict__ tasks, const PermSrc* __restrict__ srcs,
-               const PermTile* __restrict__ tiles, int n_tiles, int tiles_per_cta)
+permute_kernel(const double* __restrict__ src, const double* __restrict__ src2, long long split, double* __restrict__ dst,
+               const PermTask* __restrict__ tasks, const PermSrc* __restrict__ srcs, const PermTile* __restrict__ tiles, int n_tiles, int tiles_per_cta)
 {
     __shared__ PermTask T;
     __shared__ PermSrc S;
@@ -134,16 +134,26 @@ permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const P
         // owns the same buf element for every source and the fan-in accumulates in shared memory without barriers.
         if(T.src_count > 0) {
             long long sbase = T.src0_off;
+            const double* sb = src;
+            if(sbase >= split) {   // sharded permute: this source sits in the receive buffer
+                sb = src2;
+                sbase -= split;
+            }
             for(int l = 0; l < T.nleg; ++l) sbase += static_cast<long long>(s_base[l]) * T.src0_stride[l];
-            perm_read(T, T.src0_stride, s_lim, src + sbase, T.src0_coeff, true, buf, tid);
+            perm_read(T, T.src0_stride, s_lim, sb + sbase, T.src0_coeff, true, buf, tid);
         }
         for(int k = 1; k < T.src_count; ++k) {
             __syncthreads();   // S of the previous source no longer needed
             if(tid < static_cast<int>(sizeof(PermSrc) / sizeof(int))) reinterpret_cast<int*>(&S)[tid] = reinterpret_cast<const int*>(srcs + T.src_begin + k)[tid];
             __syncthreads();
             long long sbase = S.off;
+            const double* sb = src;
+            if(sbase >= split) {
+                sb = src2;
+                sbase -= split;
+            }
             for(int l = 0; l < T.nleg; ++l) sbase += static_cast<long long>(s_base[l]) * S.sstride[l];
-            perm_read(T, S.sstride, s_lim, src + sbase, S.coeff, false, buf, tid);
+            perm_read(T, S.sstride, s_lim, sb + sbase, S.coeff, false, buf, tid);
         }
         __syncthreads();
 
@@ -165,13 +175,18 @@ permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const P
     }
 }
 
-void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s)
+void launch_permute2(const double* src, const double* src2, long long split, double* dst, const PermutePlan& plan, cudaStream_t s)
 {
     if(plan.n_tiles == 0) return;
     const int tpc = plan.tiles_per_cta < 1 ? 1 : plan.tiles_per_cta;
     const int grid = (plan.n_tiles + tpc - 1) / tpc;
-    permute_kernel<<<grid, PERM_THREADS, 0, s>>>(src, dst, plan.d_tasks, plan.d_srcs, plan.d_tiles, plan.n_tiles, tpc);
+    permute_kernel<<<grid, PERM_THREADS, 0, s>>>(src, src2, split, dst, plan.d_tasks, plan.d_srcs, plan.d_tiles, plan.n_tiles, tpc);
     check_cuda(cudaGetLastError(), "permute_kernel launch");
+}
+
+void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s)
+{
+    launch_permute2(src, src, INT64_MAX, dst, plan, s);
 }
 
 // ================================================================================================ elementwise
@@ -224,12 +239,12 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z)
     return z ^ (z >> 31);
 }
 
-__global__ void fill_random_kernel(double* __restrict__ x, unsigned long long seed, long long n)
+__global__ void fill_random_kernel(double* __restrict__ x, unsigned long long seed, long long n, long long index_base)
 {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const unsigned long long key = splitmix64(seed);
     for(long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned long long r = splitmix64(key ^ (static_cast<unsigned long long>(i) * 0xD1342543DE82EF95ull));
+        const unsigned long long r = splitmix64(key ^ (static_cast<unsigned long long>(i + index_base) * 0xD1342543DE82EF95ull));
         x[i] = static_cast<double>(r >> 11) * (2.0 / 9007199254740992.0) - 1.0;
     }
 }
@@ -243,10 +258,10 @@ void launch_fill_constant(double* x, double v, int64_t n, cudaStream_t s)
     check_cuda(cudaGetLastError(), "fill_constant_kernel launch");
 }
 
-void launch_fill_random(double* x, uint64_t seed, int64_t n, cudaStream_t s)
+void launch_fill_random(double* x, uint64_t seed, int64_t n, cudaStream_t s, int64_t index_base)
 {
     if(n == 0) return;
-    fill_random_kernel<<<grid_for(n, 256, 148), 256, 0, s>>>(x, seed, n);
+    fill_random_kernel<<<grid_for(n, 256, 148), 256, 0, s>>>(x, seed, n, index_base);
     check_cuda(cudaGetLastError(), "fill_random_kernel launch");
 }
 

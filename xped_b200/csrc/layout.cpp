@@ -7,6 +7,7 @@
 // cached; the data then moves in one kernel launch (kernels.cu: permute_kernel).
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <numeric>
 #include <stdexcept>
 
@@ -22,6 +23,7 @@ void check_cuda(cudaError_t e, const char* what)
 // ------------------------------------------------------------------------------------------------ Context
 Context::Context(int dev, const std::vector<Factor>& factors) : sym(std::make_shared<Symmetry>(factors)), device(dev)
 {
+    if(dev < 0) return;   // planning-only context: host metadata (bases, layouts, owner maps, exchange plans); every compute call fails
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if(e != cudaSuccess || count == 0) {
@@ -41,6 +43,7 @@ Context::Context(int dev, const std::vector<Factor>& factors) : sym(std::make_sh
 
 Context::~Context()
 {
+    if(device < 0) return;
     cudaSetDevice(device);
     if(stream) cudaStreamSynchronize(stream);
     plan_cache_.clear();
@@ -184,6 +187,7 @@ void Context::upload_async(void* dst, const void* src, size_t bytes)
 
 Tensor::Tensor(Context* c, LayoutPtr l, bool zero) : ctx(c), layout(std::move(l))
 {
+    if(ctx->planning_only()) throw std::runtime_error("xped_b200: no CUDA device -- planning-only context cannot hold tensor data (no CPU fallback)");
     const size_t bytes = static_cast<size_t>(std::max<int64_t>(layout->size, 1)) * sizeof(double);
     check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d), bytes, ctx->stream), "cudaMallocAsync(block arena)");
     if(zero) check_cuda(cudaMemsetAsync(d, 0, bytes, ctx->stream), "cudaMemsetAsync");
@@ -291,14 +295,27 @@ struct SubBlock   // geometry of one (tree, cotree) sub-block inside its sector 
     int nlegs;
     int64_t dims[MAXR * 2];
     int64_t stride[MAXR * 2];
+    int sector = -1, ia = -1, ib = -1;   // identity of the sub-block: (sector, tree, cotree) positions in its layout
+    int64_t rel = 0, ld = 0;             // base - off[sector]; leading dimension of the sector matrix
+    int rank_d = 0;                      // number of domain legs
+    int64_t count() const
+    {
+        int64_t c = 1;
+        for(int k = 0; k < nlegs; ++k) c *= dims[k];
+        return c;
+    }
 };
 
 SubBlock geometry(const Layout& L, int sector, const Tree& dt, const Tree& ct)
 {
     SubBlock g;
-    const int64_t ro = L.cdom->left_offset(dt), co = L.ccod->left_offset(ct);
+    const int64_t ro = L.cdom->left_offset(dt, &g.ia), co = L.ccod->left_offset(ct, &g.ib);
     const int64_t ld = L.rows[sector];
-    g.base = L.off[sector] + ro + co * ld;
+    g.sector = sector;
+    g.rel = ro + co * ld;
+    g.ld = ld;
+    g.rank_d = dt.rank;
+    g.base = L.off[sector] + g.rel;
     g.nlegs = dt.rank + ct.rank;
     int64_t s = 1;
     for(int k = 0; k < dt.rank; ++k) {
@@ -428,17 +445,19 @@ int smem_extent(const PermTask& T)
 
 }   // namespace
 
-std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan)
+// Destination tasks of permute<shift,p> (or of its adjoint) over the GLOBAL layouts: the recoupling sums of
+// Tensor.cpp:83-214 / :258-333 in gather form.  Shared by the single-GPU plan and the sector-sharded exchange plan.
+struct TaskSet
 {
-    std::string key = in->sig + (adjoint_plan ? "@adj" : "@fwd") + std::to_string(shift) + ":";
-    for(int p : pi) key += std::to_string(p) + ",";
-    auto hit = plan_cache_.find(key);
-    if(hit != plan_cache_.end()) {
-        ++plan_hits;
-        return hit->second;
-    }
-    ++plan_misses;
+    LayoutPtr out;
+    std::vector<DstTask> tasks;   // storage order of `out`
+    std::vector<int> leg_of;      // destination leg j <- source leg leg_of[j]
+    int N = 0;
+    bool identity = false;
+};
 
+static TaskSet build_tasks(Context& ctx, const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan, bool keep_identity = false)
+{
     const int R = in->rank(), C = in->corank(), N = R + C;
     if(static_cast<int>(pi.size()) != N) throw std::invalid_argument("permute: permutation has wrong length");
     {
@@ -449,17 +468,15 @@ std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shif
     }
     std::vector<int> pinv(N);
     for(int i = 0; i < N; ++i) pinv[pi[i]] = i;
-    const Symmetry& S = *sym;
-
-    auto plan = std::make_shared<PermutePlan>();
+    const Symmetry& S = *ctx.sym;
+    TaskSet ts;
+    ts.N = N;
     bool is_identity = (shift == 0);
     for(int i = 0; i < N && is_identity; ++i) is_identity = (pi[i] == i);
-    if(is_identity) {   // Tensor.cpp:344 / :263
-        plan->out = in;
-        plan->identity_copy = true;
-        plan->bytes = 16 * in->size;
-        plan_cache_.emplace(key, plan);
-        return plan;
+    ts.identity = is_identity;
+    if(is_identity && !keep_identity) {
+        ts.out = in;
+        return ts;
     }
 
     // ---- output bases: Tensor.cpp:157-174 (forward) / :273-287 (adjoint; pi_inv and the opposite shift)
@@ -480,12 +497,12 @@ std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shif
         }
         (to_domain ? nd : nc).push_back(b);
     }
-    LayoutPtr out = layout(nd, nc);
-    plan->out = out;
-    plan->bytes = 8 * (in->size + out->size);
+    LayoutPtr out = ctx.layout(nd, nc);
+    ts.out = out;
+    ts.leg_of = leg_of;
 
     // ---- destination tasks, one per (sector, tree, cotree) of the output, in storage order
-    std::vector<DstTask> tasks;
+    std::vector<DstTask>& tasks = ts.tasks;
     std::vector<std::vector<int>> task_index(out->sector.size());   // [sector][a * ncod + b]
     std::vector<int> ncod(out->sector.size());
     for(size_t j = 0; j < out->sector.size(); ++j) {
@@ -566,7 +583,14 @@ std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shif
         }
     }
 
-    // ---- lower to device records
+    return ts;
+}
+
+// Lower destination tasks to device records (tiles, strips, shared-memory packing) and upload them.
+static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const std::vector<int>& leg_of, int N, PermutePlan& planref)
+{
+    PermutePlan* plan = &planref;
+    const int sm_count = ctx.sm_count;
     std::vector<PermTask> h_tasks;
     std::vector<PermSrc> h_srcs;
     std::vector<PermTile> h_tiles;
@@ -662,6 +686,7 @@ std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shif
     plan->n_tiles = static_cast<int>(h_tiles.size());
     // consecutive tiles (mostly of the same task) per CTA: amortises the task staging, keeps >= 16 CTAs per SM in the grid
     plan->tiles_per_cta = std::max(1, std::min(8, plan->n_tiles / (sm_count * 16)));
+    if(ctx.planning_only()) return;
     if(plan->n_tasks) {
         check_cuda(cudaMalloc(&plan->d_tasks, h_tasks.size() * sizeof(PermTask)), "cudaMalloc plan tasks");
         check_cuda(cudaMemcpy(plan->d_tasks, h_tasks.data(), h_tasks.size() * sizeof(PermTask), cudaMemcpyHostToDevice), "upload plan tasks");
@@ -671,6 +696,262 @@ std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shif
     if(plan->n_srcs) {
         check_cuda(cudaMalloc(&plan->d_srcs, h_srcs.size() * sizeof(PermSrc)), "cudaMalloc plan sources");
         check_cuda(cudaMemcpy(plan->d_srcs, h_srcs.data(), h_srcs.size() * sizeof(PermSrc), cudaMemcpyHostToDevice), "upload plan sources");
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ sector sharding
+std::vector<int> lpt_owner(const std::vector<double>& cost, int world)
+{
+    if(world < 1) throw std::invalid_argument("lpt_owner: world < 1");
+    std::vector<int> order(cost.size()), owner(cost.size(), 0);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<double> load(world, 0.0);
+    for(int i : order) {
+        int best = 0;
+        for(int r = 1; r < world; ++r)
+            if(load[r] < load[best]) best = r;
+        owner[i] = best;
+        load[best] += cost[i];
+    }
+    return owner;
+}
+
+namespace {
+SubBlock dense_block(const SubBlock& g, int64_t base)   // the same sub-block packed densely (leg 0 fastest) at `base`
+{
+    SubBlock d = g;
+    d.base = base;
+    int64_t s = 1;
+    for(int k = 0; k < g.nlegs; ++k) {
+        d.stride[k] = s;
+        s *= g.dims[k];
+    }
+    return d;
+}
+
+void append_task_record(std::vector<int64_t>& tasks, std::vector<int64_t>& srcs, const DstTask& t, const std::vector<int>& leg_of, int64_t split)
+{
+    constexpr int L = DistPermutePlan::MAXL;
+    const size_t o = tasks.size();
+    tasks.resize(o + DistPermutePlan::TASK_REC, 0);
+    tasks[o + 0] = t.dst.base;
+    tasks[o + 1] = t.dst.nlegs;
+    tasks[o + 2] = static_cast<int64_t>(srcs.size() / DistPermutePlan::SRC_REC);
+    tasks[o + 3] = static_cast<int64_t>(t.srcs.size());
+    for(int j = 0; j < L; ++j) {
+        tasks[o + 4 + j] = j < t.dst.nlegs ? t.dst.dims[j] : 1;
+        tasks[o + 4 + L + j] = j < t.dst.nlegs ? t.dst.stride[j] : 0;
+    }
+    for(const Contribution& c : t.srcs) {
+        const size_t so = srcs.size();
+        srcs.resize(so + DistPermutePlan::SRC_REC, 0);
+        const bool remote = c.src.base >= split;
+        srcs[so + 0] = remote ? 1 : 0;
+        srcs[so + 1] = remote ? c.src.base - split : c.src.base;
+        std::memcpy(&srcs[so + 2], &c.coeff, sizeof(double));
+        for(int j = 0; j < t.dst.nlegs; ++j) srcs[so + 4 + j] = c.src.stride[leg_of[j]];
+    }
+}
+}   // namespace
+
+std::shared_ptr<DistPermutePlan> Context::dist_permute_plan(const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan,
+                                                            const std::vector<int>& owner_in, const std::vector<int>& owner_out_arg, int rank, int world)
+{
+    if(world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("dist_permute_plan: bad rank / world");
+    if(owner_in.size() != in->sector.size()) throw std::invalid_argument("dist_permute_plan: owner_in needs one entry per input sector");
+    for(int o : owner_in)
+        if(o < 0 || o >= world) throw std::invalid_argument("dist_permute_plan: owner_in entry out of range");
+    std::string key = in->sig + (adjoint_plan ? "@adj" : "@fwd") + std::to_string(shift) + ":";
+    for(int p : pi) key += std::to_string(p) + ",";
+    key += "|r" + std::to_string(rank) + "/" + std::to_string(world) + "|";
+    for(int o : owner_in) key += std::to_string(o) + ",";
+    key += "|";
+    for(int o : owner_out_arg) key += std::to_string(o) + ",";
+    auto hit = dist_plan_cache_.find(key);
+    if(hit != dist_plan_cache_.end()) {
+        ++plan_hits;
+        return hit->second;
+    }
+    ++plan_misses;
+
+    TaskSet ts = build_tasks(*this, in, shift, pi, adjoint_plan, true);
+    const LayoutPtr& out = ts.out;
+    auto plan = std::make_shared<DistPermutePlan>();
+    DistPermutePlan& P = *plan;
+    P.rank = rank;
+    P.world = world;
+    P.in_global = in;
+    P.out_global = out;
+    P.owner_in = owner_in;
+    if(owner_out_arg.empty()) {   // default: LPT on the cost of a product / decomposition of the output's blocks
+        std::vector<double> cost(out->sector.size());
+        for(size_t j = 0; j < cost.size(); ++j)
+            cost[j] = static_cast<double>(out->rows[j]) * static_cast<double>(out->cols[j]) * static_cast<double>(out->rows[j] + out->cols[j]);
+        P.owner_out = lpt_owner(cost, world);
+    } else {
+        if(owner_out_arg.size() != out->sector.size()) throw std::invalid_argument("dist_permute_plan: owner_out needs one entry per output sector");
+        for(int o : owner_out_arg)
+            if(o < 0 || o >= world) throw std::invalid_argument("dist_permute_plan: owner_out entry out of range");
+        P.owner_out = owner_out_arg;
+    }
+    // ---- this rank's shards
+    auto shard = [&](const LayoutPtr& L, const std::vector<int>& owner, std::vector<int>& local_index) {
+        std::vector<Q> mine;
+        local_index.assign(L->sector.size(), -1);
+        for(size_t i = 0; i < L->sector.size(); ++i)
+            if(owner[i] == rank) {
+                local_index[i] = static_cast<int>(mine.size());
+                mine.push_back(L->sector[i]);
+            }
+        return layout_custom(L->dom, L->cod, mine);
+    };
+    std::vector<int> loc_in, loc_out;
+    P.in_local = shard(in, P.owner_in, loc_in);
+    P.out_local = shard(out, P.owner_out, loc_out);
+    P.split = P.in_local->size;
+    P.bytes_local = 8 * (P.in_local->size + P.out_local->size);
+
+    // ---- transfers: source sub-block (sector, tree, cotree) owned by rs and needed by a destination task owned by rd != rs.
+    // Both sides enumerate the same global task list in the same order, so the dense segment offsets agree without any
+    // metadata communication.
+    using Key = std::array<int, 3>;
+    std::vector<std::map<Key, SubBlock>> send(world), recv(world);
+    for(const DstTask& t : ts.tasks) {
+        const int rd = P.owner_out[t.dst.sector];
+        for(const Contribution& c : t.srcs) {
+            const int rs = P.owner_in[c.src.sector];
+            if(rs == rd) continue;
+            const Key k{c.src.sector, c.src.ia, c.src.ib};
+            if(rs == rank) send[rd].emplace(k, c.src);
+            if(rd == rank) recv[rs].emplace(k, c.src);
+        }
+    }
+    auto number = [&](std::vector<std::map<Key, SubBlock>>& lists, std::vector<int64_t>& counts, std::vector<int64_t>& displs, int64_t& total,
+                      std::vector<std::map<Key, int64_t>>& offset) {
+        counts.assign(world, 0);
+        displs.assign(world, 0);
+        offset.assign(world, {});
+        total = 0;
+        for(int p = 0; p < world; ++p) {
+            displs[p] = total;
+            for(const auto& [k, g] : lists[p]) {
+                offset[p][k] = total;
+                total += g.count();
+            }
+            counts[p] = total - displs[p];
+        }
+    };
+    std::vector<std::map<Key, int64_t>> send_off, recv_off;
+    number(send, P.send_counts, P.send_displs, P.send_total, send_off);
+    number(recv, P.recv_counts, P.recv_displs, P.recv_total, recv_off);
+
+    auto localise = [&](const SubBlock& g, const LayoutPtr& L, const std::vector<int>& loc) {
+        SubBlock l = g;
+        l.base = L->off[loc[g.sector]] + g.rel;
+        return l;
+    };
+    // ---- pack tasks (identity leg map)
+    std::vector<DstTask> pack_tasks;
+    std::vector<int> ident(ts.N);
+    std::iota(ident.begin(), ident.end(), 0);
+    for(int p = 0; p < world; ++p)
+        for(const auto& [k, g] : send[p]) {
+            DstTask t;
+            t.dst = dense_block(g, send_off[p][k]);
+            t.srcs.push_back({localise(g, P.in_local, loc_in), 1.0});
+            const size_t o = P.pack_records.size();
+            P.pack_records.resize(o + DistPermutePlan::PACK_REC, 0);
+            P.pack_records[o + 0] = p;
+            P.pack_records[o + 1] = t.dst.base;
+            P.pack_records[o + 2] = t.srcs[0].src.base;
+            P.pack_records[o + 3] = g.nlegs;
+            for(int j = 0; j < DistPermutePlan::MAXL; ++j) {
+                P.pack_records[o + 4 + j] = j < g.nlegs ? g.dims[j] : 1;
+                P.pack_records[o + 4 + DistPermutePlan::MAXL + j] = j < g.nlegs ? t.srcs[0].src.stride[j] : 0;
+            }
+            pack_tasks.push_back(std::move(t));
+        }
+    // ---- this rank's destination tasks
+    std::vector<DstTask> local_tasks, remote_tasks;
+    for(const DstTask& g : ts.tasks) {
+        if(P.owner_out[g.dst.sector] != rank) continue;
+        DstTask t;
+        t.dst = localise(g.dst, P.out_local, loc_out);
+        bool any_remote = false;
+        for(const Contribution& c : g.srcs) {
+            const int rs = P.owner_in[c.src.sector];
+            if(rs == rank) {
+                t.srcs.push_back({localise(c.src, P.in_local, loc_in), c.coeff});
+            } else {
+                any_remote = true;
+                t.srcs.push_back({dense_block(c.src, P.split + recv_off[rs].at(Key{c.src.sector, c.src.ia, c.src.ib})), c.coeff});
+            }
+        }
+        append_task_record(P.task_records, P.src_records, t, ts.leg_of, P.split);
+        (any_remote ? remote_tasks : local_tasks).push_back(std::move(t));
+    }
+    lower_tasks(*this, pack_tasks, ident, ts.N, P.pack);
+    lower_tasks(*this, local_tasks, ts.leg_of, ts.N, P.local);
+    lower_tasks(*this, remote_tasks, ts.leg_of, ts.N, P.remote);
+    P.pack.bytes = 16 * P.send_total;
+    dist_plan_cache_.emplace(key, plan);
+    return plan;
+}
+
+void Context::dist_pack(const DistPermutePlan& plan, const Tensor& local_in, double* d_send)
+{
+    if(local_in.layout.get() != plan.in_local.get()) throw std::invalid_argument("dist_pack: tensor is not this rank's input shard of the plan");
+    if(plan.send_total == 0) return;
+    ProfScope prof(*this, CAT_PERMUTE, static_cast<double>(plan.pack.bytes));
+    launch_permute(local_in.d, d_send, plan.pack, stream);
+    ++launches;
+}
+
+Tensor* Context::dist_local(const DistPermutePlan& plan, const Tensor& local_in)
+{
+    if(local_in.layout.get() != plan.in_local.get()) throw std::invalid_argument("dist_local: tensor is not this rank's input shard of the plan");
+    auto* out = new Tensor(this, plan.out_local, false);
+    if(plan.local.n_tiles) {
+        ProfScope prof(*this, CAT_PERMUTE, static_cast<double>(plan.bytes_local));
+        launch_permute(local_in.d, out->d, plan.local, stream);
+        ++launches;
+    }
+    return out;
+}
+
+void Context::dist_remote(const DistPermutePlan& plan, const Tensor& local_in, const double* d_recv, Tensor& local_out)
+{
+    if(local_in.layout.get() != plan.in_local.get() || local_out.layout.get() != plan.out_local.get())
+        throw std::invalid_argument("dist_remote: tensors are not this rank's shards of the plan");
+    if(plan.remote.n_tiles == 0) return;
+    if(plan.recv_total > 0 && !d_recv) throw std::invalid_argument("dist_remote: receive buffer missing");
+    ProfScope prof(*this, CAT_PERMUTE, 0.0);
+    launch_permute2(local_in.d, d_recv, plan.split, local_out.d, plan.remote, stream);
+    ++launches;
+}
+
+std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan)
+{
+    std::string key = in->sig + (adjoint_plan ? "@adj" : "@fwd") + std::to_string(shift) + ":";
+    for(int p : pi) key += std::to_string(p) + ",";
+    auto hit = plan_cache_.find(key);
+    if(hit != plan_cache_.end()) {
+        ++plan_hits;
+        return hit->second;
+    }
+    ++plan_misses;
+    auto plan = std::make_shared<PermutePlan>();
+    TaskSet ts = build_tasks(*this, in, shift, pi, adjoint_plan);
+    if(ts.identity) {   // Tensor.cpp:344 / :263
+        plan->out = in;
+        plan->identity_copy = true;
+        plan->bytes = 16 * in->size;
+    } else {
+        plan->out = ts.out;
+        plan->bytes = 8 * (in->size + ts.out->size);
+        lower_tasks(*this, ts.tasks, ts.leg_of, ts.N, *plan);
     }
     plan_cache_.emplace(key, plan);
     return plan;

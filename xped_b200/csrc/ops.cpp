@@ -81,7 +81,11 @@ void Context::run_gemm(const double* A, const double* B, double* C, const std::v
 // ------------------------------------------------------------------------------------------------ operator*
 // TensorBase::operator* (src/Core/TensorBase.cpp:243-288). Operands may be lazy adjoints (AdjointOp.hpp:26-69):
 // the block is then read transposed, domain/codomain swap roles, the sector list stays the operand's.
-Tensor* Context::multiply(const Tensor& a, bool adj_a, const Tensor& b, bool adj_b)
+Tensor* Context::multiply(const Tensor& a, bool adj_a, const Tensor& b, bool adj_b) { return multiply_sectors(a, adj_a, b, adj_b, nullptr); }
+
+// `out_sectors` (sector-sharded operands): the result holds exactly these sectors in this order (the ones this
+// rank owns) instead of the canonical list; operands are shards, sectors absent from either stay zero blocks.
+Tensor* Context::multiply_sectors(const Tensor& a, bool adj_a, const Tensor& b, bool adj_b, const std::vector<Q>* out_sectors)
 {
     const Layout& LA = *a.layout;
     const Layout& LB = *b.layout;
@@ -92,7 +96,7 @@ Tensor* Context::multiply(const Tensor& a, bool adj_a, const Tensor& b, bool adj
     if(a_cod.size() != b_dom.size()) throw std::invalid_argument("operator*: CoRank of left operand != Rank of right operand");
     for(size_t i = 0; i < a_cod.size(); ++i)   // DEBUG_ASSERT(coupledCodomain == coupledDomain), TensorBase.cpp:254
         if(!a_cod[i]->same_sectors(*b_dom[i])) throw std::invalid_argument("operator*: coupledCodomain(left) != coupledDomain(right)");
-    LayoutPtr LO = layout(a_dom, b_cod);
+    LayoutPtr LO = out_sectors ? layout_custom(a_dom, b_cod, *out_sectors) : layout(a_dom, b_cod);
     auto* out = new Tensor(this, LO, true);   // Tout.setZero(); sectors missing in an operand stay zero blocks
 
     std::vector<GemmItem> items;

@@ -180,6 +180,45 @@ def test_tsvd_graded_spectrum_and_multiplets(ctxs):
         assert np.abs(gS.download() - oS.data).max() < 1e-13
 
 
+@pytest.mark.parametrize("case", ["U0_square", "U0_tall", "U1_big", "SU2_graded"])
+def test_tsvd_large_blocks(ctxs, case):
+    """Blocks wide enough for the QR-preconditioned path (>= 32 columns), the 4- and 8-CTA cluster round kernels and
+    tall panels; same checks as test_tsvd (sigma 1e-12, truncated reconstruction, orthonormality)."""
+    if case == "U0_square":
+        ctx, osym = ctxs("U0")
+        g, o = pair(ctx, osym, [[((), 40)], [((), 5)]], [[((), 8)], [((), 25)]], 71)          # one 200 x 200 block
+        _svd_checks(g, o, 1000, 1e-10, False)
+        _svd_checks(g, o, 30, 1e-10, False)
+    elif case == "U0_tall":
+        ctx, osym = ctxs("U0")
+        g, o = pair(ctx, osym, [[((), 30)], [((), 11)]], [[((), 77)]], 72)                      # 330 x 77
+        _svd_checks(g, o, 1000, 0.0, False)
+        _svd_checks(g.adjoint(), o.adjoint(), 20, 1e-10, False)                                 # 77 x 330 (transposed work matrix)
+    elif case == "U1_big":
+        ctx, osym = ctxs("U1")
+        B = [((q,), 12) for q in range(-2, 3)]
+        g, o = pair(ctx, osym, [B, B], [B, B], 73)                                              # 9 sectors, block side 144 ... 720
+        _svd_checks(g, o, 10 ** 6, 1e-10, False)
+        _svd_checks(g, o, 64, 1e-10, False)
+    else:
+        ctx, osym = ctxs("SU2")
+        ent = [((1,), 30), ((2,), 41), ((3,), 25)]
+        g, o = pair(ctx, osym, [ent, [((1,), 2), ((2,), 1)]], [ent, [((1,), 2), ((2,), 1)]], 74)
+        rng = np.random.default_rng(5)
+        for i in range(len(o.sector)):                                                          # graded spectra over 16 decades
+            m, n = o.block(i).shape
+            k = min(m, n)
+            q1, _ = np.linalg.qr(rng.standard_normal((m, k)))
+            q2, _ = np.linalg.qr(rng.standard_normal((n, k)))
+            o.block(i)[...] = q1 @ np.diag(10.0 ** (-16.0 * np.arange(k) / k)) @ q2.T
+        g.upload(o.data)
+        _svd_checks(g, o, 48, 1e-10, False)
+        gU, gS, gV = g.tSVD(10 ** 6, 1e-10, False)
+        oU, oS, oV = o.tSVD(10 ** 6, 1e-10, False)
+        assert gS.structure() == oS.structure()
+        assert np.abs(gS.download() - oS.data).max() < 1e-13
+
+
 @pytest.mark.parametrize("name", ["SU2", "U1"])
 def test_decompose_projectors(ctxs, name):
     ctx, osym = ctxs(name)

@@ -12,12 +12,15 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
 #include <stdexcept>
 
 #include "engine.hpp"
+#include "precond.hpp"
 
 namespace xb {
 
@@ -37,7 +40,7 @@ struct SvdBlock
     double tol;
 };
 
-struct SvdTask { int block, bi, bj; };
+struct SvdTask { int block, bi, bj, mode; };   // mode 0: all pairs of the 32-column panel (31 steps), 1: cross pairs only (16 steps)
 
 // per-block diagonal shift 1.5 * ||A_q||_F for teigh: A_q + c_q 1 is positive definite with condition number <= 5
 __global__ void block_shift_kernel(const double* __restrict__ A, const long long* __restrict__ a_off, const SvdBlock* __restrict__ blocks, int nblocks,
@@ -127,8 +130,19 @@ __device__ __forceinline__ int seat_next(int x)
 // slices, the next 64-row chunk being prefetched into registers while the current one is multiplied.
 template <int CL>
 __global__ void __launch_bounds__(SVD_THREADS)
-svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock* __restrict__ blocks, const SvdTask* __restrict__ tasks, int* __restrict__ rotated)
+svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock* __restrict__ blocks, const SvdTask* __restrict__ tasks, int* __restrict__ rotated,
+                 unsigned long long* __restrict__ tprof)
 {
+    // optional phase timing (XB_SVD_PROF=1): thread 0 of CTA 0 accumulates clock64() deltas per phase
+    const bool prof = tprof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long tp = prof ? clock64() : 0;
+    auto lap = [&](int slot) {
+        if(prof) {
+            const long long now = clock64();
+            atomicAdd(tprof + slot, static_cast<unsigned long long>(now - tp));
+            tp = now;
+        }
+    };
     __shared__ __align__(16) double Xs[SP * XS_LD];          // chunk staging [col][row]; during phase 2: second Vl buffer
     __shared__ __align__(16) double Gs[2][SP * G_LD];        // Gs[1] doubles as this CTA's partial Gram matrix in phase 1
     __shared__ __align__(16) double Vls[SP * VL_LD];
@@ -204,6 +218,7 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
             Gpart[r * G_LD + c + 1] = acc[j][1];
         }
     }
+    lap(0);   // setup + Gram
     if(CL > 1) {
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
@@ -237,6 +252,7 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
         __syncthreads();
     }
 
+    lap(1);   // cluster reduction of G
     // ---- phase 2: one cyclic two-sided Jacobi sweep on G; thread (k, l): rows {2k, 2k+1} x columns {2l, 2l+1}
     {
         const int k = tid >> 4, l = tid & 15;
@@ -288,6 +304,7 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
         jacobi_step(Gs[0], Gs[1], Vl1, Vls);
         // 31 swaps: the rotation matrix now sits in Vls, everybody back in the original seat
         any = __syncthreads_or(any);
+        lap(2);   // inner Jacobi sweep
         if(!any) return;   // panel already orthogonal (uniform over the cluster: identical G everywhere)
     }
     if(tid == 0 && crank == 0) atomicExch(rotated, 1);
@@ -351,6 +368,262 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
             __syncthreads();
         }
     }
+    lap(3);   // panel update
+    if(prof) atomicAdd(tprof + 7, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Round kernel, resident form (the default): the CTA's row slice of the 32-column W panel is loaded ONCE into shared
+// memory ([col][row], pitch == 4 mod 16) and stays there for the Gram phase and the update phase; the V slice is
+// prefetched into registers before the Jacobi sweep so that its L2 latency hides behind the sweep.  Shared-memory
+// columns are interleaved (even seats: block bi, odd seats: block bj): in cross mode (every round but the first of a
+// sweep) only the 16 x 16 pairs between the two blocks are rotated -- 16 steps with the odd seats shifting by one --
+// because the pairs inside a block are visited once per sweep in round 0 (standard cyclic-by-blocks ordering).
+template <int CL, int VREG>
+__global__ void __launch_bounds__(SVD_THREADS, VREG <= 20 ? 2 : 1)
+svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock* __restrict__ blocks, const SvdTask* __restrict__ tasks,
+                          int* __restrict__ rotated, unsigned long long* __restrict__ tprof, int rs)
+{
+    extern __shared__ __align__(16) double dsm[];
+    const int LD = rs + 4;                     // rs is a multiple of 16
+    double* __restrict__ Xw = dsm;             // SP x LD
+    double* __restrict__ G0 = Xw + SP * LD;    // SP x G_LD
+    double* __restrict__ G1 = G0 + SP * G_LD;  // partial Gram matrix in phase 1
+    double* __restrict__ VlA = G1 + SP * G_LD; // SP x VL_LD
+    double* __restrict__ VlB = VlA + SP * VL_LD;
+    __shared__ int colidx[SP];
+
+    const bool prof = tprof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long tp = prof ? clock64() : 0;
+    auto lap = [&](int slot) {
+        if(prof) {
+            const long long now = clock64();
+            atomicAdd(tprof + slot, static_cast<unsigned long long>(now - tp));
+            tp = now;
+        }
+    };
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    unsigned crank = 0;
+    if(CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const SvdTask task = tasks[blockIdx.x / CL];
+    const SvdBlock blk = blocks[task.block];
+    if(tid < SP) {
+        const int i = tid >> 1;
+        int c = (tid & 1) ? (task.bj >= 0 ? task.bj * SB + i : -1) : task.bi * SB + i;
+        if(c >= blk.cols) c = -1;
+        colidx[tid] = c;
+    }
+    __syncthreads();
+
+    auto slice = [&](int nrows, int& lo, int& hi) {
+        const int per = (((nrows + CL - 1) / CL) + 7) & ~7;
+        lo = min(nrows, static_cast<int>(crank) * per);
+        hi = min(nrows, lo + per);
+    };
+    int wlo, whi, vlo, vhi;
+    slice(blk.rows, wlo, whi);
+    slice(blk.cols, vlo, vhi);
+    // warp w owns columns w, w+8, w+16, w+24 of the slice; lanes run along the rows (coalesced)
+    constexpr int RI = VREG / 4;
+    auto fetch = [&](const double* __restrict__ M, int nrows, int lo, int hi, double (&r)[VREG]) {
+#pragma unroll
+        for(int ci = 0; ci < 4; ++ci) {
+            const int gc = colidx[warp + 8 * ci];
+            const double* __restrict__ colp = M + static_cast<long long>(gc < 0 ? 0 : gc) * nrows;
+#pragma unroll
+            for(int ri = 0; ri < RI; ++ri) {
+                const int gr = lo + lane + 32 * ri;
+                r[ci * RI + ri] = (gc >= 0 && gr < hi) ? colp[gr] : 0.0;
+            }
+        }
+    };
+    auto stage = [&](const double (&r)[VREG]) {
+#pragma unroll
+        for(int ci = 0; ci < 4; ++ci)
+#pragma unroll
+            for(int ri = 0; ri < RI; ++ri) {
+                const int row = lane + 32 * ri;
+                if(row < rs) Xw[(warp + 8 * ci) * LD + row] = r[ci * RI + ri];
+            }
+    };
+    double* __restrict__ Wm = W + blk.w_off;
+    double* __restrict__ Vm = V + blk.v_off;
+    double reg[VREG];
+    fetch(Wm, blk.rows, wlo, whi, reg);
+    stage(reg);
+    __syncthreads();
+    fetch(Vm, blk.cols, vlo, vhi, reg);   // in flight during the Gram phase and the Jacobi sweep
+    lap(0);
+
+    // ---- phase 1: Gram matrix of the slice. warp w owns tiles (ti = w/2, tj = 2*(w&1) + {0,1}) of the 4x4 grid of 8x8 tiles
+    {
+        const int ti = warp >> 1, tj0 = (warp & 1) * 2;
+        // two k-interleaved accumulator sets per output tile: four independent DMMA chains per warp
+        double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+        const int kend = (whi - wlo + 7) & ~7;   // rows beyond the slice are zero-filled up to rs (a multiple of 16)
+        const double* __restrict__ pa = Xw + (ti * 8 + fr) * LD + fk;
+        const double* __restrict__ pb0 = Xw + (tj0 * 8 + fr) * LD + fk;
+        const double* __restrict__ pb1 = pb0 + 8 * LD;
+#pragma unroll 2
+        for(int k0 = 0; k0 < kend; k0 += 8) {
+            const double a0 = pa[k0], a1 = pa[k0 + 4];
+            dmma_8x8x4(acc[0][0][0], acc[0][0][1], a0, pb0[k0]);
+            dmma_8x8x4(acc[0][1][0], acc[0][1][1], a0, pb1[k0]);
+            dmma_8x8x4(acc[1][0][0], acc[1][0][1], a1, pb0[k0 + 4]);
+            dmma_8x8x4(acc[1][1][0], acc[1][1][1], a1, pb1[k0 + 4]);
+        }
+#pragma unroll
+        for(int j = 0; j < 2; ++j) {
+            const int r = ti * 8 + fr, c = (tj0 + j) * 8 + 2 * fk;
+            G1[r * G_LD + c] = acc[0][j][0] + acc[1][j][0];
+            G1[r * G_LD + c + 1] = acc[0][j][1] + acc[1][j][1];
+        }
+    }
+    lap(1);
+    if(CL > 1) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    } else {
+        __syncthreads();
+    }
+    {
+        // every thread sums 4 elements; all remote loads are issued before the first use (fixed order: bit-identical G in all CTAs)
+        double part[4][CL];
+#pragma unroll
+        for(int i = 0; i < 4; ++i) {
+            const int e = tid + i * SVD_THREADS, r = e / SP, c = e % SP;
+            if(CL > 1) {
+                const unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(&G1[r * G_LD + c]));
+#pragma unroll
+                for(int cr = 0; cr < CL; ++cr) {
+                    unsigned remote;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(cr));
+                    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(part[i][cr]) : "r"(remote));
+                }
+            } else {
+                part[i][0] = G1[r * G_LD + c];
+            }
+        }
+#pragma unroll
+        for(int i = 0; i < 4; ++i) {
+            const int e = tid + i * SVD_THREADS, r = e / SP, c = e % SP;
+            double sum = part[i][0];
+#pragma unroll
+            for(int cr = 1; cr < CL; ++cr) sum += part[i][cr];
+            G0[r * G_LD + c] = sum;
+            VlA[r * VL_LD + c] = (r == c) ? 1.0 : 0.0;
+        }
+    }
+    if(CL > 1) {   // peers must not overwrite G1 or exit before everybody has read it
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    } else {
+        __syncthreads();
+    }
+    lap(2);
+
+    // ---- phase 2: Jacobi steps on G; thread (k, l): rows {2k, 2k+1} x columns {2l, 2l+1}; pairs are always the seats (2g, 2g+1)
+    const double* Vl = VlA;
+    {
+        const bool cross = task.mode != 0;
+        auto nxt = [&](int x) { return cross ? ((x & 1) ? ((x + 2) & (SP - 1)) : x) : seat_next(x); };
+        const int k = tid >> 4, l = tid & 15;
+        const double tol2 = blk.tol * blk.tol;
+        const int r0 = 2 * k, r1 = 2 * k + 1, c0 = 2 * l, c1 = 2 * l + 1;
+        const int nr0 = nxt(r0), nr1 = nxt(r1), nc0 = nxt(c0), nc1 = nxt(c1);
+        const int g00 = r0 * G_LD + c0, g01 = r0 * G_LD + c1, g10 = r1 * G_LD + c0, g11 = r1 * G_LD + c1;
+        const int h00 = nr0 * G_LD + nc0, h01 = nr0 * G_LD + nc1, h10 = nr1 * G_LD + nc0, h11 = nr1 * G_LD + nc1;
+        const int pa = c0 * G_LD + c0, pb = c1 * G_LD + c1, pc = c0 * G_LD + c1;
+        const int v0p = k * VL_LD + c0, v0q = k * VL_LD + c1, v1p = (k + 16) * VL_LD + c0, v1q = (k + 16) * VL_LD + c1;
+        const int w0p = k * VL_LD + nc0, w0q = k * VL_LD + nc1, w1p = (k + 16) * VL_LD + nc0, w1q = (k + 16) * VL_LD + nc1;
+        int any = 0;
+        auto jacobi_step = [&](const double* __restrict__ Gc, double* __restrict__ Gn, const double* __restrict__ Vc, double* __restrict__ Vn) {
+            double cl, sl;
+            const double a00 = Gc[g00], a01 = Gc[g01], a10 = Gc[g10], a11 = Gc[g11];
+            const double x0p = Vc[v0p], x0q = Vc[v0q], x1p = Vc[v1p], x1q = Vc[v1q];
+            const bool rl = jacobi_rotation(Gc[pa], Gc[pb], Gc[pc], tol2, cl, sl);
+            const double ck = __shfl_sync(0xffffffffu, cl, k);
+            const double sk = __shfl_sync(0xffffffffu, sl, k);
+            const bool rk = __shfl_sync(0xffffffffu, static_cast<int>(rl), k) != 0;
+            any |= rl ? 1 : 0;
+            const double b00 = cl * a00 - sl * a01, b01 = sl * a00 + cl * a01;
+            const double b10 = cl * a10 - sl * a11, b11 = sl * a10 + cl * a11;
+            double n00 = ck * b00 - sk * b10, n01 = ck * b01 - sk * b11;
+            double n10 = sk * b00 + ck * b10, n11 = sk * b01 + ck * b11;
+            if(k == l && rk) {
+                n01 = 0.0;
+                n10 = 0.0;
+            }
+            Gn[h00] = n00;
+            Gn[h01] = n01;
+            Gn[h10] = n10;
+            Gn[h11] = n11;
+            Vn[w0p] = cl * x0p - sl * x0q;
+            Vn[w0q] = sl * x0p + cl * x0q;
+            Vn[w1p] = cl * x1p - sl * x1q;
+            Vn[w1q] = sl * x1p + cl * x1q;
+            __syncthreads();
+        };
+        const int nsteps = cross ? SB : SP - 1;
+#pragma unroll 1
+        for(int step = 0; step + 1 < nsteps; step += 2) {
+            jacobi_step(G0, G1, VlA, VlB);
+            jacobi_step(G1, G0, VlB, VlA);
+        }
+        if(nsteps & 1) {
+            jacobi_step(G0, G1, VlA, VlB);
+            Vl = VlB;
+        }
+        any = __syncthreads_or(any);
+        lap(3);
+        if(!any) return;   // panel already orthogonal (uniform over the cluster: identical G everywhere)
+    }
+    if(tid == 0 && crank == 0) atomicExch(rotated, 1);
+
+    // ---- phase 3: X <- X * Vl for the resident W slice, then for the V slice (registers -> shared). warp w: 8-row groups w, w+8, ...
+    auto multiply_slice = [&](double* __restrict__ M, int nrows, int lo, int hi) {
+        const int ngroups = (hi - lo + 7) >> 3;
+        for(int g = 2 * warp; g < ngroups; g += 2 * (SVD_THREADS / 32)) {   // two 8-row groups per pass: eight independent DMMA chains
+            double out[2][4][2];
+#pragma unroll
+            for(int u = 0; u < 2; ++u)
+#pragma unroll
+                for(int j = 0; j < 4; ++j) out[u][j][0] = out[u][j][1] = 0.0;
+#pragma unroll
+            for(int k0 = 0; k0 < SP; k0 += 4) {
+                const double* __restrict__ xp = Xw + (k0 + fk) * LD + g * 8 + fr;   // rows beyond the slice are zero-filled
+                const double a0 = xp[0], a1 = xp[8];
+#pragma unroll
+                for(int j = 0; j < 4; ++j) {
+                    const double b = Vl[(k0 + fk) * VL_LD + j * 8 + fr];
+                    dmma_8x8x4(out[0][j][0], out[0][j][1], a0, b);
+                    dmma_8x8x4(out[1][j][0], out[1][j][1], a1, b);
+                }
+            }
+#pragma unroll
+            for(int u = 0; u < 2; ++u) {
+                const int gr = lo + (g + u) * 8 + fr;
+                if(gr < hi) {
+#pragma unroll
+                    for(int j = 0; j < 4; ++j)
+#pragma unroll
+                        for(int h = 0; h < 2; ++h) {
+                            const int gc = colidx[j * 8 + 2 * fk + h];
+                            if(gc >= 0) M[gr + static_cast<long long>(gc) * nrows] = out[u][j][h];
+                        }
+                }
+            }
+        }
+    };
+    multiply_slice(Wm, blk.rows, wlo, whi);
+    __syncthreads();
+    stage(reg);
+    __syncthreads();
+    multiply_slice(Vm, blk.cols, vlo, vhi);
+    lap(4);
+    if(prof) atomicAdd(tprof + 7, 1ull);
 }
 
 // column norms -> singular values; one warp per column
@@ -404,7 +677,7 @@ void schedule(int block, int nb, std::vector<std::vector<SvdTask>>& rounds)
     if(nb <= 0) return;
     if(nb == 1) {
         if(rounds.empty()) rounds.resize(1);
-        rounds[0].push_back({block, 0, -1});
+        rounds[0].push_back({block, 0, -1, 0});
         return;
     }
     const int n = nb + (nb & 1);   // even number of players, player n-1 may be the dummy
@@ -422,9 +695,9 @@ void schedule(int block, int nb, std::vector<std::vector<SvdTask>>& rounds)
             if(a > b) std::swap(a, b);
             if(b >= nb) {
                 // bye: orthogonalise inside the lone block only in the first round (it meets every other block later)
-                if(r == 0) rounds[r].push_back({block, a, -1});
+                if(r == 0) rounds[r].push_back({block, a, -1, 0});
             } else {
-                rounds[r].push_back({block, a, b});
+                rounds[r].push_back({block, a, b, r == 0 ? 0 : 1});
             }
         }
     }
@@ -522,34 +795,101 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         check_cuda(cudaGetLastError(), "svd_init_kernel launch");
         ++ctx.launches;
     }
+    // QR preconditioning (precond.cu): (W, V) <- (A Q_B, Q_B); blocks narrower than two column blocks gain nothing
+    {
+        static const bool no_precond = std::getenv("XB_SVD_NOPRECOND") != nullptr;
+        int pre_max_rows = 0;
+        std::vector<QrPreBlock> pre;
+        long long boff = 0, yoff = 0;
+        for(const SvdBlock& b : R.blocks) {
+            if(b.cols < 2 * SB) continue;
+            QrPreBlock q;
+            q.w_off = b.w_off;
+            q.v_off = b.v_off;
+            q.b_off = boff;
+            q.y_off = yoff;
+            q.t_off = static_cast<long long>(pre.size()) * 256;
+            q.m = b.rows;
+            q.n = b.cols;
+            boff += static_cast<long long>(b.cols) * (b.rows + b.cols);
+            yoff += static_cast<long long>(b.cols) * 16;
+            pre_max_rows = std::max(pre_max_rows, b.cols);
+            pre.push_back(q);
+        }
+        if(!shifted && !no_precond && !pre.empty() && svd_precondition_supported(pre_max_rows)) {
+            double* d_aug = nullptr;
+            QrPreBlock* d_pre = nullptr;
+            const long long aug_elems = boff + yoff + 256 * static_cast<long long>(pre.size());
+            check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_aug), sizeof(double) * aug_elems, s), "svd precondition workspace");
+            check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_pre), sizeof(QrPreBlock) * pre.size(), s), "svd precondition meta");
+            ctx.upload_async(d_pre, pre.data(), sizeof(QrPreBlock) * pre.size());
+            launch_svd_precondition(R.d_W, R.d_V, d_aug, d_aug + boff, d_aug + boff + yoff, d_pre, pre, s, &ctx.launches);
+            check_cuda(cudaFreeAsync(d_aug, s), "svd precondition free");
+            check_cuda(cudaFreeAsync(d_pre, s), "svd precondition free");
+        }
+    }
     int* h_flag = static_cast<int*>(ctx.pinned(sizeof(int)));
+    unsigned long long* d_tprof = nullptr;
+    static const bool svd_prof = std::getenv("XB_SVD_PROF") != nullptr;
+    if(svd_prof) {
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_tprof), 8 * sizeof(unsigned long long), s), "svd prof");
+        check_cuda(cudaMemsetAsync(d_tprof, 0, 8 * sizeof(unsigned long long), s), "svd prof reset");
+    }
     int max_rows = 0;
     for(const SvdBlock& b : R.blocks) max_rows = std::max(max_rows, b.rows);
-    const int cluster = max_rows > 2 * SCH ? 4 : 1;   // split the rows of a panel over a 4-CTA cluster once there are enough of them
-    const int max_sweeps = 150;   // bail-out only; graded CTM corner products need ~30 sweeps without preconditioning
+    // resident kernel: cluster of CL CTAs per panel pair, each keeps its row slice (<= rs rows) of the panel in shared memory
+    const int cluster = max_rows <= 160 ? 1 : (max_rows <= 640 ? 4 : 8);
+    const bool resident = max_rows <= 2560;
+    int rs = 16;
+    for(const SvdBlock& b : R.blocks) {
+        const int per = (((b.rows + cluster - 1) / cluster) + 7) & ~7;   // cols <= rows, so the V slice is never longer
+        rs = std::max(rs, (per + 15) & ~15);
+    }
+    const size_t dyn_smem = sizeof(double) * (static_cast<size_t>(SP) * (rs + 4) + 2 * SP * G_LD + 2 * SP * VL_LD);
+    auto launch_round = [&](const SvdTask* d_round_tasks, int cnt) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(SVD_THREADS);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const SvdBlock* cb = d_blocks;
+        if(!resident) {
+            cfg.gridDim = dim3(static_cast<unsigned>(cnt) * 4);
+            attr[0].val.clusterDim.x = 4;
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_kernel<4>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof), "svd_round_kernel<4> launch");
+            return;
+        }
+        cfg.gridDim = dim3(static_cast<unsigned>(cnt) * cluster);
+        cfg.dynamicSmemBytes = dyn_smem;
+        attr[0].val.clusterDim.x = cluster;
+        if(cluster == 1)
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<1, 20>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<1> launch");
+        else if(cluster == 4)
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<4, 20>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<4> launch");
+        else
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<8, 40>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<8> launch");
+    };
+    {
+        static bool configured = false;
+        if(!configured) {
+            const int max_dyn = 200 * 1024;
+            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<1, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
+            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<4, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
+            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<8, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
+            configured = true;
+        }
+    }
+    const int max_sweeps = 150;   // bail-out only
     for(R.sweeps = 0; R.sweeps < max_sweeps; ++R.sweeps) {
         check_cuda(cudaMemsetAsync(d_flag, 0, sizeof(int), s), "svd flag reset");
         for(size_t r = 0; r + 1 < round_begin.size(); ++r) {
             const int cnt = round_begin[r + 1] - round_begin[r];
             if(cnt == 0) continue;
-            if(cluster > 1) {
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(static_cast<unsigned>(cnt) * cluster);
-                cfg.blockDim = dim3(SVD_THREADS);
-                cfg.stream = s;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeClusterDimension;
-                attr[0].val.clusterDim.x = cluster;
-                attr[0].val.clusterDim.y = 1;
-                attr[0].val.clusterDim.z = 1;
-                cfg.attrs = attr;
-                cfg.numAttrs = 1;
-                check_cuda(cudaLaunchKernelEx(&cfg, svd_round_kernel<4>, R.d_W, R.d_V, static_cast<const SvdBlock*>(d_blocks),
-                                              static_cast<const SvdTask*>(d_tasks + round_begin[r]), d_flag),
-                           "svd_round_kernel<4> launch");
-            } else {
-                svd_round_kernel<1><<<cnt, SVD_THREADS, 0, s>>>(R.d_W, R.d_V, d_blocks, d_tasks + round_begin[r], d_flag);
-            }
+            launch_round(d_tasks + round_begin[r], cnt);
             ++ctx.launches;
         }
         check_cuda(cudaGetLastError(), "svd_round_kernel launch");
@@ -575,6 +915,14 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         check_cuda(cudaMemcpyAsync(R.shift.data(), d_shift, sizeof(double) * nb, cudaMemcpyDeviceToHost, s), "shift readback");
     }
     check_cuda(cudaStreamSynchronize(s), "svd sync");
+    if(svd_prof) {
+        unsigned long long h[8];
+        check_cuda(cudaMemcpy(h, d_tprof, sizeof(h), cudaMemcpyDeviceToHost), "svd prof readback");
+        check_cuda(cudaFreeAsync(d_tprof, s), "svd prof free");
+        const double n = h[7] ? static_cast<double>(h[7]) : 1.0;
+        std::fprintf(stderr, "[svd prof] blocks %d max_rows %d cluster %d rs %d sweeps %d rounds/sweep %zu | CTA0 cycles/round: p0 %.0f p1 %.0f p2 %.0f p3 %.0f p4 %.0f (updates %llu)\n",
+                     nb, max_rows, cluster, rs, R.sweeps + 1, round_begin.size() - 1, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[7]);
+    }
     check_cuda(cudaFreeAsync(d_meta, s), "svd meta free");
     return R;
 }

@@ -54,6 +54,27 @@ def test_permute_all_24x5(ctxs, name):
             assert_same(g.permute(shift, p), o.permute(shift, p), TOL, f"{name} permute<{shift},{p}>")
 
 
+@pytest.mark.parametrize("name,dim", [("U1", 4), ("U1", 6), ("Z3", 2), ("U0", 8)])
+def test_permute_bulk_path(ctxs, name, dim, monkeypatch):
+    """The cp.async.bulk form of the permute (normally used for >= 8 MB tensors) forced on small tensors whose runs obey
+    the 16-byte rules (even multiplicities): all 24 permutations x 5 shifts, bit-exact against the oracle (coefficients
+    of bosonic Abelian symmetries are 1, so the permute is a pure data movement)."""
+    monkeypatch.setenv("XB_PERMUTE_BULK", "1")
+    ctx, osym = ctxs(name)
+    if name == "U1":
+        B = [((q,), dim) for q in range(-2, 3)]
+    elif name == "Z3":
+        B = [((q,), dim) for q in range(3)]
+    else:
+        B = [((), dim)]
+    g, o = pair(ctx, osym, [B, B], [B, B], 81)
+    for p in itertools.permutations(range(4)):
+        for shift in (0, 1, -1, 2, -2):
+            gp, op = g.permute(shift, p), o.permute(shift, p)
+            assert gp.structure() == op.structure()
+            assert np.array_equal(gp.download(), op.data), f"{name} bulk permute p={p} shift={shift}"
+
+
 @pytest.mark.parametrize("name", ["SU2", "U1", "fU1xSU2"])
 def test_permute_ctm_shaped(ctxs, name):
     """The (3,3)<->(4,2)/(1,5)-style regroupings contractCorner issues, incl. 6- and 7-leg tensors."""

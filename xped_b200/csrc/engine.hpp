@@ -82,6 +82,31 @@ struct PermSrc
 
 struct PermTile { int task; unsigned short c[PERM_MAXLEG]; };   // task + tile coordinate along each merged leg (no divisions on the device)
 
+// ---- bulk-copy (TMA) form of a permute plan: used when every contiguous run of every task is 16-byte aligned and an even
+// number of doubles long (cp.async.bulk needs 16-byte addresses and sizes) and the fan-in is 1 (Abelian symmetries).
+// A tile is wx (destination-contiguous leg 0) x wy (source-contiguous leg `ls`) x nz (all other legs).  Source runs
+// (wy doubles each, one per (x, z)) are fetched by cp.async.bulk into shared memory, transposed there (a batch of nz
+// wx x wy transposes with the coefficient applied), and the destination runs (wx doubles, one per (y, z)) leave through
+// cp.async.bulk stores.  ls == 0 (same fastest leg on both sides): runs are copied through shared memory unchanged.
+constexpr int BULK_TILE_ELEMS = 2304;
+constexpr int BULK_BUF_ELEMS = 2816;   // one staging buffer incl. run padding
+constexpr int BULK_THREADS = 256;
+struct BulkTask
+{
+    long long dst_off, src_off;
+    double coeff;
+    int nleg, ls;             // ls: source-contiguous leg (0 => copy mode)
+    int wx, wy, nz;           // tile extents: leg 0, leg ls, product over the other legs
+    int rs_s, rs_d;           // shared-memory pitch of a source / destination run (even)
+    int nxh, nyh;             // ceil(wx / 2), ceil(wy / 16): item grid of the transposing pass
+    int nzleg;                // number of z legs
+    int dims[PERM_MAXLEG], w[PERM_MAXLEG];
+    int dstride[PERM_MAXLEG], sstride[PERM_MAXLEG];
+    int zleg[PERM_MAXLEG];    // the z legs (dst order)
+    unsigned zmagic[PERM_MAXLEG];   // ceil(2^32 / w[zleg[i]])
+    unsigned magic_wx, magic_wy, magic_nxh, magic_nyh;
+};
+
 struct PermutePlan
 {
     LayoutPtr out;
@@ -90,6 +115,10 @@ struct PermutePlan
     PermTask* d_tasks = nullptr;
     PermSrc* d_srcs = nullptr;
     PermTile* d_tiles = nullptr;
+    // bulk-copy form (nullptr if the plan does not qualify)
+    BulkTask* d_btasks = nullptr;
+    PermTile* d_btiles = nullptr;
+    int n_btiles = 0, btiles_per_cta = 1;
     bool identity_copy = false;   // permute<0, identity>: plain copy (Tensor.cpp:344)
     int64_t bytes = 0;            // algorithmic bytes: 8*(N_src + N_dst)
     int max_fan_in = 0;

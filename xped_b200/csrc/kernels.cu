@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "engine.hpp"
 
@@ -175,6 +176,235 @@ permute_kernel(const double* __restrict__ src, const double* __restrict__ src2, 
     }
 }
 
+// ================================================================================================ permute, bulk-copy form
+// Tiles move through shared memory with cp.async.bulk (the TMA engine, 1-D form): one instruction per contiguous run,
+// completion of the loads on an mbarrier (complete_tx), stores as bulk groups.  The SM's load/store units and the
+// integer pipe only see the in-shared-memory transpose (a 2 x 16 lane grid: 16 consecutive source elements, two adjacent
+// destination elements; run pitches with pitch/2 odd make both sides conflict-free), no per-element global addressing.
+// quotient by a small divisor through its magic number ceil(2^32 / d); d == 1 has no 32-bit magic number
+__device__ __forceinline__ int magic_div(int v, int d, unsigned magic) { return d == 1 ? v : static_cast<int>(__umulhi(static_cast<unsigned>(v), magic)); }
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void bulk_load(unsigned dst_smem, const double* gsrc, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_smem), "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(double* gdst, unsigned src_smem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    // bounded spin: a byte-count mismatch must surface as a launch failure, never as a hung GPU
+    const long long t0 = clock64();
+    for(;;) {
+        unsigned done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if(done) return;
+        if(clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
+__global__ void __launch_bounds__(BULK_THREADS)
+permute_bulk_kernel(const double* __restrict__ src, double* __restrict__ dst, const BulkTask* __restrict__ tasks, const PermTile* __restrict__ tiles, int n_tiles,
+                    int tiles_per_cta)
+{
+    __shared__ __align__(128) double bufA[BULK_BUF_ELEMS];   // source runs (transpose mode) / staging buffer 0 (copy mode)
+    __shared__ __align__(128) double bufB[BULK_BUF_ELEMS];   // destination runs (transpose mode) / staging buffer 1 (copy mode)
+    __shared__ __align__(8) unsigned long long bar_storage[2];
+    __shared__ BulkTask T;
+    __shared__ int s_tile[2][sizeof(PermTile) / sizeof(int)];
+
+    constexpr int TILE_INTS = static_cast<int>(sizeof(PermTile) / sizeof(int));
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * tiles_per_cta, t1 = min(n_tiles, t0 + tiles_per_cta);
+    if(t0 >= t1) return;
+    const unsigned bar[2] = {smem_u32(&bar_storage[0]), smem_u32(&bar_storage[1])};
+    if(tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar[0]));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar[1]));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if(tid < TILE_INTS) s_tile[0][tid] = reinterpret_cast<const int*>(tiles + t0)[tid];
+    __syncthreads();
+
+    // geometry of tile `slot` (uniform over the CTA): tile origin, clipped extents
+    auto stage_task = [&](int task) {
+        const int* g = reinterpret_cast<const int*>(tasks + task);
+        int* sdst = reinterpret_cast<int*>(&T);
+        for(int i = tid; i < static_cast<int>(sizeof(BulkTask) / sizeof(int)); i += BULK_THREADS) sdst[i] = g[i];
+    };
+    // run r of the load (is_load) or store side: global element offset, validity and length
+    auto run_geom = [&](const PermTile& tile, bool is_load, int r, long long& goff, int& len, int& slot_index) -> bool {
+        // transpose mode: load run = (x, z), r = z * wx + x;  store run = (y, z), r = z * wy + y.  copy mode: r = z.
+        const bool copy = T.ls == 0;
+        int z = r, inner = 0;
+        const int wi = copy ? 1 : (is_load ? T.wx : T.wy);
+        if(!copy) {
+            z = magic_div(r, wi, is_load ? T.magic_wx : T.magic_wy);
+            inner = r - z * wi;
+        }
+        slot_index = r;
+        const int* __restrict__ gs = is_load ? T.sstride : T.dstride;
+        const int lrun = is_load ? T.ls : 0;        // the leg along which this side's runs are contiguous
+        const int lin = is_load ? 0 : T.ls;          // the leg enumerated by `inner` (transpose mode)
+        long long off = is_load ? T.src_off : T.dst_off;
+        bool ok = true;
+        {
+            const int b = tile.c[lrun] * T.w[lrun];
+            len = min(T.w[lrun], T.dims[lrun] - b);
+            off += static_cast<long long>(b) * gs[lrun];   // stride 1
+        }
+        if(!copy) {
+            const int b = tile.c[lin] * T.w[lin];
+            ok = inner < min(T.w[lin], T.dims[lin] - b);
+            off += static_cast<long long>(b + inner) * gs[lin];
+        }
+        for(int i = 0; i < T.nzleg; ++i) {
+            const int l = T.zleg[i];
+            const int q = magic_div(z, T.w[l], T.zmagic[i]);
+            const int c = z - q * T.w[l];
+            z = q;
+            const int b = tile.c[l] * T.w[l];
+            ok = ok && (c < T.dims[l] - b);
+            off += static_cast<long long>(b + c) * gs[l];
+        }
+        goff = off;
+        return ok;
+    };
+    auto tile_bytes = [&](const PermTile& tile) {
+        long long v = 8;
+        for(int l = 0; l < T.nleg; ++l) v *= min(T.w[l], T.dims[l] - tile.c[l] * T.w[l]);
+        return static_cast<unsigned>(v);
+    };
+    auto issue_loads = [&](const PermTile& tile, double* buf, unsigned barrier) {
+        const bool copy = T.ls == 0;
+        const int nrun = copy ? T.nz : T.nz * T.wx;
+        const int pitch = T.rs_s;
+        if(tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(barrier), "r"(tile_bytes(tile)) : "memory");
+        }
+        for(int r = tid; r < nrun; r += BULK_THREADS) {
+            long long goff;
+            int len, si;
+            if(run_geom(tile, true, r, goff, len, si)) bulk_load(smem_u32(buf + si * pitch), src + goff, static_cast<unsigned>(len) * 8u, barrier);
+        }
+    };
+    auto issue_stores = [&](const PermTile& tile, const double* buf) {
+        const bool copy = T.ls == 0;
+        const int nrun = copy ? T.nz : T.nz * T.wy;
+        const int pitch = T.rs_d;
+        for(int r = tid; r < nrun; r += BULK_THREADS) {
+            long long goff;
+            int len, si;
+            if(run_geom(tile, false, r, goff, len, si)) bulk_store(dst + goff, smem_u32(buf + si * pitch), static_cast<unsigned>(len) * 8u);
+        }
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+    };
+
+    int staged = reinterpret_cast<const PermTile*>(s_tile[0])->task;
+    stage_task(staged);
+    __syncthreads();
+    unsigned phase[2] = {0u, 0u};
+    // prologue: loads of the first tile
+    issue_loads(*reinterpret_cast<const PermTile*>(s_tile[0]), bufA, bar[0]);
+    for(int ti = t0; ti < t1; ++ti) {
+        const int cur = (ti - t0) & 1;
+        const PermTile tile = *reinterpret_cast<const PermTile*>(s_tile[cur]);
+        const bool copy = T.ls == 0;
+        const bool has_next = ti + 1 < t1;
+        if(has_next && tid < TILE_INTS) s_tile[cur ^ 1][tid] = reinterpret_cast<const int*>(tiles + ti + 1)[tid];
+        if(copy) {
+            // staging buffers alternate: A for even tiles of the CTA, B for odd ones; each has its own mbarrier
+            double* bcur = cur ? bufB : bufA;
+            double* bnext = cur ? bufA : bufB;
+            // the stores of tile ti-1 read bnext: they must have finished reading before the next loads overwrite it
+            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            __syncthreads();   // also publishes s_tile[cur ^ 1]
+            bool next_same = false;
+            if(has_next) {
+                const PermTile& nt = *reinterpret_cast<const PermTile*>(s_tile[cur ^ 1]);
+                next_same = nt.task == staged;
+                if(next_same) issue_loads(nt, bnext, bar[cur ^ 1]);
+            }
+            mbar_wait(bar[cur], phase[cur]);
+            phase[cur] ^= 1u;
+            issue_stores(tile, bcur);
+            if(has_next && !next_same) {   // task switch: the task record is replaced once nobody needs the old one
+                const PermTile& nt = *reinterpret_cast<const PermTile*>(s_tile[cur ^ 1]);
+                __syncthreads();
+                staged = nt.task;
+                stage_task(staged);
+                __syncthreads();
+                if(T.ls == 0) {
+                    issue_loads(nt, bnext, bar[cur ^ 1]);
+                } else {   // next task transposes: its loads always go to bufA / bar[0] with the parity tracked per barrier
+                    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+                    __syncthreads();
+                    issue_loads(nt, bufA, bar[0]);
+                }
+            }
+        } else {
+            // transpose mode: loads land in bufA (bar[0]), destination runs are built in bufB
+            __syncthreads();   // publishes s_tile[cur ^ 1]
+            mbar_wait(bar[0], phase[0]);
+            phase[0] ^= 1u;
+            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // stores of the previous tile have finished reading bufB
+            __syncthreads();
+            {
+                const int rs_s = T.rs_s, rs_d = T.rs_d, wx = T.wx, wy = T.wy, nxh = T.nxh, nyh = T.nyh;
+                const unsigned m_nyh = T.magic_nyh, m_nxh = T.magic_nxh;
+                const double coeff = T.coeff;
+                const int total = T.nz * nxh * nyh * 32;
+                const int y_lo = tid & 15, x_lo = (tid >> 4) & 1;
+                for(int e = tid; e < total; e += BULK_THREADS) {
+                    int rest = e >> 5;
+                    int q = magic_div(rest, nyh, m_nyh);
+                    const int y = (rest - q * nyh) * 16 + y_lo;
+                    rest = q;
+                    q = magic_div(rest, nxh, m_nxh);
+                    const int x = (rest - q * nxh) * 2 + x_lo;
+                    const int z = q;
+                    if(x < wx && y < wy) bufB[(z * wy + y) * rs_d + x] = coeff * bufA[(z * wx + x) * rs_s + y];
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes to bufB -> visible to the bulk stores
+            __syncthreads();
+            bool next_same = false;
+            if(has_next) {
+                const PermTile& nt = *reinterpret_cast<const PermTile*>(s_tile[cur ^ 1]);
+                next_same = nt.task == staged;
+                if(next_same) issue_loads(nt, bufA, bar[0]);   // overlaps the stores of this tile
+            }
+            issue_stores(tile, bufB);
+            if(has_next && !next_same) {
+                const PermTile& nt = *reinterpret_cast<const PermTile*>(s_tile[cur ^ 1]);
+                __syncthreads();
+                staged = nt.task;
+                stage_task(staged);
+                __syncthreads();
+                if(T.ls == 0) {
+                    // copy mode expects tile parity `cur ^ 1` in buffer (cur ^ 1): A for 0, B for 1; B may still be read by the stores
+                    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+                    __syncthreads();
+                    issue_loads(nt, (cur ^ 1) ? bufB : bufA, bar[cur ^ 1]);
+                } else {
+                    issue_loads(nt, bufA, bar[0]);
+                }
+            }
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // all stores complete before the shared memory is released
+}
+
 void launch_permute2(const double* src, const double* src2, long long split, double* dst, const PermutePlan& plan, cudaStream_t s)
 {
     if(plan.n_tiles == 0) return;
@@ -186,6 +416,17 @@ void launch_permute2(const double* src, const double* src2, long long split, dou
 
 void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s)
 {
+    // bulk-copy form for bandwidth-bound sizes (XB_PERMUTE_BULK=0 / 1 forces never / whenever the plan qualifies)
+    const char* bulk_env = std::getenv("XB_PERMUTE_BULK");   // read per call so that tests can toggle it
+    const int bulk_mode = bulk_env ? std::atoi(bulk_env) : -1;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+    if(plan.d_btasks && aligned && bulk_mode != 0 && (bulk_mode == 1 || plan.bytes >= (8ll << 20))) {
+        const int tpc = plan.btiles_per_cta < 1 ? 1 : plan.btiles_per_cta;
+        const int grid = (plan.n_btiles + tpc - 1) / tpc;
+        permute_bulk_kernel<<<grid, BULK_THREADS, 0, s>>>(src, dst, plan.d_btasks, plan.d_btiles, plan.n_btiles, tpc);
+        check_cuda(cudaGetLastError(), "permute_bulk_kernel launch");
+        return;
+    }
     launch_permute2(src, src, INT64_MAX, dst, plan, s);
 }
 

@@ -203,6 +203,8 @@ PermutePlan::~PermutePlan()
     if(d_tasks) cudaFree(d_tasks);
     if(d_srcs) cudaFree(d_srcs);
     if(d_tiles) cudaFree(d_tiles);
+    if(d_btasks) cudaFree(d_btasks);
+    if(d_btiles) cudaFree(d_btiles);
 }
 
 // ------------------------------------------------------------------------------------------------ layouts
@@ -587,6 +589,113 @@ static TaskSet build_tasks(Context& ctx, const LayoutPtr& in, int shift, const s
 }
 
 // Lower destination tasks to device records (tiles, strips, shared-memory packing) and upload them.
+// Bulk-copy (cp.async.bulk) lowering of one merged task; false if the task does not meet the 16-byte rules.
+static bool lower_bulk_task(const PermTask& T, std::vector<BulkTask>& btasks, std::vector<PermTile>& btiles)
+{
+    if(T.src_count != 1 || T.nleg < 1) return false;
+    const int n = T.nleg;
+    if(T.dstride[0] != 1) return false;
+    int ls = -1;
+    for(int j = 0; j < n; ++j)
+        if(T.src0_stride[j] == 1) ls = j;
+    if(ls < 0) return false;
+    auto even = [](long long v) { return (v & 1) == 0; };
+    if(!even(T.dst_off) || !even(T.src0_off) || !even(T.dims[0]) || !even(T.dims[ls])) return false;
+    for(int j = 0; j < n; ++j) {
+        if(j != 0 && !even(T.dstride[j])) return false;
+        if(j != ls && !even(T.src0_stride[j])) return false;
+    }
+    if(ls == 0 && T.src0_coeff != 1.0) return false;   // copy mode moves the runs untouched
+    BulkTask B;
+    std::memset(&B, 0, sizeof(B));
+    B.dst_off = T.dst_off;
+    B.src_off = T.src0_off;
+    B.coeff = T.src0_coeff;
+    B.nleg = n;
+    B.ls = ls;
+    for(int j = 0; j < n; ++j) {
+        B.dims[j] = T.dims[j];
+        B.dstride[j] = T.dstride[j];
+        B.sstride[j] = T.src0_stride[j];
+        B.w[j] = 1;
+    }
+    auto even_chunk = [](int dim, int cap) {   // largest even extent <= cap that splits `dim` evenly
+        if(dim <= cap) return dim;
+        int parts = ceil_div(dim, cap);
+        int w = ceil_div(dim, parts);
+        if(w & 1) ++w;
+        return std::min(w, cap & ~1);
+    };
+    long long vol;
+    if(ls == 0) {
+        B.w[0] = even_chunk(T.dims[0], BULK_TILE_ELEMS);
+        vol = B.w[0];
+    } else {
+        B.w[0] = even_chunk(T.dims[0], 48);
+        B.w[ls] = even_chunk(T.dims[ls], 48);
+        vol = static_cast<long long>(B.w[0]) * B.w[ls];
+    }
+    // z legs: grow in dst order while the tile stays within the budget
+    for(int j = 1; j < n; ++j) {
+        if(j == ls) continue;
+        const long long room = BULK_TILE_ELEMS / vol;
+        if(room < 2) break;
+        int w = static_cast<int>(std::min<long long>(T.dims[j], room));
+        if(w < T.dims[j]) w = ceil_div(T.dims[j], ceil_div(T.dims[j], w));
+        B.w[j] = w;
+        vol *= w;
+        if(w < T.dims[j]) break;
+    }
+    B.wx = B.w[0];
+    B.wy = ls == 0 ? 1 : B.w[ls];
+    B.nz = 1;
+    for(int j = 1; j < n; ++j) {
+        if(j == ls) continue;
+        B.zleg[B.nzleg] = j;
+        B.zmagic[B.nzleg] = static_cast<unsigned>(((1ull << 32) + B.w[j] - 1) / B.w[j]);
+        ++B.nzleg;
+        B.nz *= B.w[j];
+    }
+    if(ls == 0) {
+        B.rs_s = B.rs_d = B.wx;
+        if(static_cast<long long>(B.nz) * B.rs_s > BULK_BUF_ELEMS) return false;
+    } else {
+        B.rs_s = B.wy + 2;
+        if((B.rs_s / 2) % 2 == 0) B.rs_s += 2;   // pitch / 2 odd: the 2 x 16 lane grid of the transposing pass is conflict-free
+        B.rs_d = B.wx + 2;
+        if((B.rs_d / 2) % 2 == 0) B.rs_d += 2;
+        if(static_cast<long long>(B.nz) * B.wx * B.rs_s > BULK_BUF_ELEMS || static_cast<long long>(B.nz) * B.wy * B.rs_d > BULK_BUF_ELEMS) return false;
+    }
+    B.nxh = ceil_div(B.wx, 2);
+    B.nyh = ceil_div(B.wy, 16);
+    auto magic = [](int d) { return static_cast<unsigned>(((1ull << 32) + d - 1) / d); };
+    B.magic_wx = magic(B.wx);
+    B.magic_wy = magic(B.wy);
+    B.magic_nxh = magic(B.nxh);
+    B.magic_nyh = magic(B.nyh);
+    int ntile[PERM_MAXLEG];
+    long long nt = 1;
+    for(int j = 0; j < n; ++j) {
+        ntile[j] = ceil_div(T.dims[j], B.w[j]);
+        if(ntile[j] > 65535) return false;
+        nt *= ntile[j];
+    }
+    const int id = static_cast<int>(btasks.size());
+    for(long long x = 0; x < nt; ++x) {
+        PermTile pt;
+        std::memset(&pt, 0, sizeof(pt));
+        pt.task = id;
+        long long r = x;
+        for(int j = 0; j < n; ++j) {
+            pt.c[j] = static_cast<unsigned short>(r % ntile[j]);
+            r /= ntile[j];
+        }
+        btiles.push_back(pt);
+    }
+    btasks.push_back(B);
+    return true;
+}
+
 static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const std::vector<int>& leg_of, int N, PermutePlan& planref)
 {
     PermutePlan* plan = &planref;
@@ -594,6 +703,9 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
     std::vector<PermTask> h_tasks;
     std::vector<PermSrc> h_srcs;
     std::vector<PermTile> h_tiles;
+    std::vector<BulkTask> h_btasks;
+    std::vector<PermTile> h_btiles;
+    bool bulk_ok = true;
     h_tasks.reserve(tasks.size());
     for(const DstTask& t : tasks) {
         if(t.dst.nlegs != N) throw std::logic_error("permute plan: leg count mismatch");
@@ -680,6 +792,7 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
         }
         plan->max_fan_in = std::max(plan->max_fan_in, T.src_count);
         h_tasks.push_back(T);
+        if(bulk_ok) bulk_ok = lower_bulk_task(T, h_btasks, h_btiles);
     }
     plan->n_tasks = static_cast<int>(h_tasks.size());
     plan->n_srcs = static_cast<int>(h_srcs.size());
@@ -692,6 +805,14 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
         check_cuda(cudaMemcpy(plan->d_tasks, h_tasks.data(), h_tasks.size() * sizeof(PermTask), cudaMemcpyHostToDevice), "upload plan tasks");
         check_cuda(cudaMalloc(&plan->d_tiles, h_tiles.size() * sizeof(PermTile)), "cudaMalloc plan tiles");
         check_cuda(cudaMemcpy(plan->d_tiles, h_tiles.data(), h_tiles.size() * sizeof(PermTile), cudaMemcpyHostToDevice), "upload plan tiles");
+    }
+    if(bulk_ok && !h_btiles.empty()) {
+        plan->n_btiles = static_cast<int>(h_btiles.size());
+        plan->btiles_per_cta = std::max(1, std::min(16, plan->n_btiles / (sm_count * 8)));
+        check_cuda(cudaMalloc(&plan->d_btasks, h_btasks.size() * sizeof(BulkTask)), "cudaMalloc bulk tasks");
+        check_cuda(cudaMemcpy(plan->d_btasks, h_btasks.data(), h_btasks.size() * sizeof(BulkTask), cudaMemcpyHostToDevice), "upload bulk tasks");
+        check_cuda(cudaMalloc(&plan->d_btiles, h_btiles.size() * sizeof(PermTile)), "cudaMalloc bulk tiles");
+        check_cuda(cudaMemcpy(plan->d_btiles, h_btiles.data(), h_btiles.size() * sizeof(PermTile), cudaMemcpyHostToDevice), "upload bulk tiles");
     }
     if(plan->n_srcs) {
         check_cuda(cudaMalloc(&plan->d_srcs, h_srcs.size() * sizeof(PermSrc)), "cudaMalloc plan sources");

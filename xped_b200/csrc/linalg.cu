@@ -386,11 +386,12 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
 {
     extern __shared__ __align__(16) double dsm[];
     const int LD = rs + 4;                     // rs is a multiple of 16
-    double* __restrict__ Xw = dsm;             // SP x LD
-    double* __restrict__ G0 = Xw + SP * LD;    // SP x G_LD
-    double* __restrict__ G1 = G0 + SP * G_LD;  // partial Gram matrix in phase 1
-    double* __restrict__ VlA = G1 + SP * G_LD; // SP x VL_LD
-    double* __restrict__ VlB = VlA + SP * VL_LD;
+    double* __restrict__ Xw = dsm;                 // SP x LD
+    double* __restrict__ Gp0 = Xw + SP * LD;       // G in 2x2-block planes: plane (r&1)*2 + (c&1), index (r>>1)*16 + (c>>1); two buffers
+    double* __restrict__ Gp1 = Gp0 + SP * SP;
+    double* __restrict__ Vp0 = Gp1 + SP * SP;      // Vl in planes: plane (r>=16)*2 + (c&1), index (r&15)*16 + (c>>1); two buffers
+    double* __restrict__ Vp1 = Vp0 + SP * SP;
+    double* __restrict__ G1 = Vp1 + SP * SP;       // partial Gram matrix (phase 1, SP x G_LD); afterwards Vl in [k][n] form (SP x VL_LD)
     __shared__ int colidx[SP];
 
     const bool prof = tprof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
@@ -512,8 +513,8 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
             double sum = part[i][0];
 #pragma unroll
             for(int cr = 1; cr < CL; ++cr) sum += part[i][cr];
-            G0[r * G_LD + c] = sum;
-            VlA[r * VL_LD + c] = (r == c) ? 1.0 : 0.0;
+            Gp0[((r & 1) * 2 + (c & 1)) * (SP * SP / 4) + (r >> 1) * 16 + (c >> 1)] = sum;
+            Vp0[((r >> 4) * 2 + (c & 1)) * (SP * SP / 4) + (r & 15) * 16 + (c >> 1)] = (r == c) ? 1.0 : 0.0;
         }
     }
     if(CL > 1) {   // peers must not overwrite G1 or exit before everybody has read it
@@ -524,25 +525,28 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
     }
     lap(2);
 
-    // ---- phase 2: Jacobi steps on G; thread (k, l): rows {2k, 2k+1} x columns {2l, 2l+1}; pairs are always the seats (2g, 2g+1)
-    const double* Vl = VlA;
+    // ---- phase 2: Jacobi steps on G; thread (k, l) owns the 2x2 block rows {2k, 2k+1} x columns {2l, 2l+1}; pairs are always the
+    // seats (2g, 2g+1).  G and Vl live in four planes (one per position inside the 2x2 block), so that all loads of a step are
+    // unit-stride over the threads (no bank conflicts) and the stores to the rotated seats are permutations of them.
+    double* __restrict__ Vl = G1;
     {
+        constexpr int PL = SP * SP / 4;
         const bool cross = task.mode != 0;
         auto nxt = [&](int x) { return cross ? ((x & 1) ? ((x + 2) & (SP - 1)) : x) : seat_next(x); };
         const int k = tid >> 4, l = tid & 15;
         const double tol2 = blk.tol * blk.tol;
         const int r0 = 2 * k, r1 = 2 * k + 1, c0 = 2 * l, c1 = 2 * l + 1;
         const int nr0 = nxt(r0), nr1 = nxt(r1), nc0 = nxt(c0), nc1 = nxt(c1);
-        const int g00 = r0 * G_LD + c0, g01 = r0 * G_LD + c1, g10 = r1 * G_LD + c0, g11 = r1 * G_LD + c1;
-        const int h00 = nr0 * G_LD + nc0, h01 = nr0 * G_LD + nc1, h10 = nr1 * G_LD + nc0, h11 = nr1 * G_LD + nc1;
-        const int pa = c0 * G_LD + c0, pb = c1 * G_LD + c1, pc = c0 * G_LD + c1;
-        const int v0p = k * VL_LD + c0, v0q = k * VL_LD + c1, v1p = (k + 16) * VL_LD + c0, v1q = (k + 16) * VL_LD + c1;
-        const int w0p = k * VL_LD + nc0, w0q = k * VL_LD + nc1, w1p = (k + 16) * VL_LD + nc0, w1q = (k + 16) * VL_LD + nc1;
+        auto gidx = [](int r, int c) { return ((r & 1) * 2 + (c & 1)) * PL + (r >> 1) * 16 + (c >> 1); };
+        auto vidx = [](int r, int c) { return ((r >> 4) * 2 + (c & 1)) * PL + (r & 15) * 16 + (c >> 1); };
+        const int h00 = gidx(nr0, nc0), h01 = gidx(nr0, nc1), h10 = gidx(nr1, nc0), h11 = gidx(nr1, nc1);
+        const int pa = 17 * l, pb = 3 * PL + 17 * l, pc = PL + 17 * l;   // pivot block (l, l)
+        const int w0p = vidx(k, nc0), w0q = vidx(k, nc1), w1p = vidx(k + 16, nc0), w1q = vidx(k + 16, nc1);
         int any = 0;
         auto jacobi_step = [&](const double* __restrict__ Gc, double* __restrict__ Gn, const double* __restrict__ Vc, double* __restrict__ Vn) {
             double cl, sl;
-            const double a00 = Gc[g00], a01 = Gc[g01], a10 = Gc[g10], a11 = Gc[g11];
-            const double x0p = Vc[v0p], x0q = Vc[v0q], x1p = Vc[v1p], x1q = Vc[v1q];
+            const double a00 = Gc[tid], a01 = Gc[PL + tid], a10 = Gc[2 * PL + tid], a11 = Gc[3 * PL + tid];
+            const double x0p = Vc[tid], x0q = Vc[PL + tid], x1p = Vc[2 * PL + tid], x1q = Vc[3 * PL + tid];
             const bool rl = jacobi_rotation(Gc[pa], Gc[pb], Gc[pc], tol2, cl, sl);
             const double ck = __shfl_sync(0xffffffffu, cl, k);
             const double sk = __shfl_sync(0xffffffffu, sl, k);
@@ -569,16 +573,23 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
         const int nsteps = cross ? SB : SP - 1;
 #pragma unroll 1
         for(int step = 0; step + 1 < nsteps; step += 2) {
-            jacobi_step(G0, G1, VlA, VlB);
-            jacobi_step(G1, G0, VlB, VlA);
+            jacobi_step(Gp0, Gp1, Vp0, Vp1);
+            jacobi_step(Gp1, Gp0, Vp1, Vp0);
         }
+        const double* Vfin = Vp0;
         if(nsteps & 1) {
-            jacobi_step(G0, G1, VlA, VlB);
-            Vl = VlB;
+            jacobi_step(Gp0, Gp1, Vp0, Vp1);
+            Vfin = Vp1;
         }
         any = __syncthreads_or(any);
         lap(3);
         if(!any) return;   // panel already orthogonal (uniform over the cluster: identical G everywhere)
+        // everybody is back in the original seat: Vl[row][col] in the [k][n] form the DMMA fragments of phase 3 read
+        Vl[k * VL_LD + c0] = Vfin[tid];
+        Vl[k * VL_LD + c1] = Vfin[PL + tid];
+        Vl[(k + 16) * VL_LD + c0] = Vfin[2 * PL + tid];
+        Vl[(k + 16) * VL_LD + c1] = Vfin[3 * PL + tid];
+        __syncthreads();
     }
     if(tid == 0 && crank == 0) atomicExch(rotated, 1);
 
@@ -823,7 +834,23 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_aug), sizeof(double) * aug_elems, s), "svd precondition workspace");
             check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_pre), sizeof(QrPreBlock) * pre.size(), s), "svd precondition meta");
             ctx.upload_async(d_pre, pre.data(), sizeof(QrPreBlock) * pre.size());
+            static const bool pre_prof = std::getenv("XB_SVD_PROF") != nullptr;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if(pre_prof) {
+                e0 = ctx.get_event();
+                e1 = ctx.get_event();
+                cudaEventRecord(e0, s);
+            }
             launch_svd_precondition(R.d_W, R.d_V, d_aug, d_aug + boff, d_aug + boff + yoff, d_pre, pre, s, &ctx.launches);
+            if(pre_prof) {
+                cudaEventRecord(e1, s);
+                cudaEventSynchronize(e1);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                std::fprintf(stderr, "[svd prof] QR preconditioner: %zu blocks, n_max %d, %.3f ms\n", pre.size(), pre_max_rows, ms);
+                ctx.event_pool.push_back(e0);
+                ctx.event_pool.push_back(e1);
+            }
             check_cuda(cudaFreeAsync(d_aug, s), "svd precondition free");
             check_cuda(cudaFreeAsync(d_pre, s), "svd precondition free");
         }
@@ -845,7 +872,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         const int per = (((b.rows + cluster - 1) / cluster) + 7) & ~7;   // cols <= rows, so the V slice is never longer
         rs = std::max(rs, (per + 15) & ~15);
     }
-    const size_t dyn_smem = sizeof(double) * (static_cast<size_t>(SP) * (rs + 4) + 2 * SP * G_LD + 2 * SP * VL_LD);
+    const size_t dyn_smem = sizeof(double) * (static_cast<size_t>(SP) * (rs + 4) + 4 * SP * SP + SP * VL_LD);
     auto launch_round = [&](const SvdTask* d_round_tasks, int cnt) {
         cudaLaunchConfig_t cfg = {};
         cfg.blockDim = dim3(SVD_THREADS);

@@ -98,8 +98,10 @@ struct BulkTask
     int nleg, ls;             // ls: source-contiguous leg (0 => copy mode)
     int wx, wy, nz;           // tile extents: leg 0, leg ls, product over the other legs
     int rs_s, rs_d;           // shared-memory pitch of a source / destination run (even)
-    int nxh, nyh;             // ceil(wx / 2), ceil(wy / 16): item grid of the transposing pass
+    int nxh, nyh;             // ceil(wx / gx), ceil(wy / gy): item grid of the transposing pass (lane grid gx x gy = 2 x 16 or 4 x 8)
+    int gx_shift;             // log2(gx)
     int nzleg;                // number of z legs
+    int mrg_load, mrg_store;  // > 1: that many consecutive runs are contiguous in global memory and in the staging buffer (one bulk operation)
     int dims[PERM_MAXLEG], w[PERM_MAXLEG];
     int dstride[PERM_MAXLEG], sstride[PERM_MAXLEG];
     int zleg[PERM_MAXLEG];    // the z legs (dst order)
@@ -118,7 +120,8 @@ struct PermutePlan
     // bulk-copy form (nullptr if the plan does not qualify)
     BulkTask* d_btasks = nullptr;
     PermTile* d_btiles = nullptr;
-    int n_btiles = 0, btiles_per_cta = 1;
+    int2* d_branges = nullptr;   // per CTA: (first tile, tile count), all tiles of one task
+    int n_btiles = 0, n_branges = 0;
     bool identity_copy = false;   // permute<0, identity>: plain copy (Tensor.cpp:344)
     int64_t bytes = 0;            // algorithmic bytes: 8*(N_src + N_dst)
     int max_fan_in = 0;

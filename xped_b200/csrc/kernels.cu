@@ -213,193 +213,159 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
     }
 }
 
-__global__ void __launch_bounds__(BULK_THREADS)
-permute_bulk_kernel(const double* __restrict__ src, double* __restrict__ dst, const BulkTask* __restrict__ tasks, const PermTile* __restrict__ tiles, int n_tiles,
-                    int tiles_per_cta)
+// A CTA works on a range of consecutive tiles of ONE task (ranges are cut on the host).  Two staging buffers: copy mode
+// alternates them (the loads of tile i+1 are in flight while tile i drains through its bulk stores); transpose mode
+// receives the source runs in buffer 0 and builds the destination runs in buffer 1 (the loads of tile i+1 overlap the
+// stores of tile i).  Five CTAs per SM hide the rest of the latency -- measured to beat a deeper per-CTA ring at
+// three CTAs per SM, because the issue rate of small (192-byte) bulk operations is what limits the short-run cases.
+// Runs that are contiguous in global memory AND in the staging buffer are merged into one bulk operation.
+constexpr int BULK_MAX_TILES_PER_CTA = 32;
+__global__ void __launch_bounds__(BULK_THREADS, 5)
+permute_bulk_kernel(const double* __restrict__ src, double* __restrict__ dst, const BulkTask* __restrict__ tasks, const PermTile* __restrict__ tiles,
+                    const int2* __restrict__ ranges)
 {
-    __shared__ __align__(128) double bufA[BULK_BUF_ELEMS];   // source runs (transpose mode) / staging buffer 0 (copy mode)
-    __shared__ __align__(128) double bufB[BULK_BUF_ELEMS];   // destination runs (transpose mode) / staging buffer 1 (copy mode)
+    __shared__ __align__(128) double bufA[BULK_BUF_ELEMS];
+    __shared__ __align__(128) double bufB[BULK_BUF_ELEMS];
     __shared__ __align__(8) unsigned long long bar_storage[2];
     __shared__ BulkTask T;
-    __shared__ int s_tile[2][sizeof(PermTile) / sizeof(int)];
+    __shared__ PermTile s_tiles[BULK_MAX_TILES_PER_CTA];
 
     constexpr int TILE_INTS = static_cast<int>(sizeof(PermTile) / sizeof(int));
     const int tid = threadIdx.x;
-    const int t0 = blockIdx.x * tiles_per_cta, t1 = min(n_tiles, t0 + tiles_per_cta);
-    if(t0 >= t1) return;
+    const int2 range = ranges[blockIdx.x];
+    const int t0 = range.x, nt = range.y;
+    double* const buf[2] = {bufA, bufB};
     const unsigned bar[2] = {smem_u32(&bar_storage[0]), smem_u32(&bar_storage[1])};
     if(tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar[0]));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar[1]));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if(tid < TILE_INTS) s_tile[0][tid] = reinterpret_cast<const int*>(tiles + t0)[tid];
-    __syncthreads();
-
-    // geometry of tile `slot` (uniform over the CTA): tile origin, clipped extents
-    auto stage_task = [&](int task) {
-        const int* g = reinterpret_cast<const int*>(tasks + task);
+    for(int i = tid; i < nt * TILE_INTS; i += BULK_THREADS) reinterpret_cast<int*>(s_tiles)[i] = reinterpret_cast<const int*>(tiles + t0)[i];
+    {
+        const int* g = reinterpret_cast<const int*>(tasks + tiles[t0].task);
         int* sdst = reinterpret_cast<int*>(&T);
         for(int i = tid; i < static_cast<int>(sizeof(BulkTask) / sizeof(int)); i += BULK_THREADS) sdst[i] = g[i];
-    };
-    // run r of the load (is_load) or store side: global element offset, validity and length
-    auto run_geom = [&](const PermTile& tile, bool is_load, int r, long long& goff, int& len, int& slot_index) -> bool {
-        // transpose mode: load run = (x, z), r = z * wx + x;  store run = (y, z), r = z * wy + y.  copy mode: r = z.
-        const bool copy = T.ls == 0;
-        int z = r, inner = 0;
-        const int wi = copy ? 1 : (is_load ? T.wx : T.wy);
-        if(!copy) {
-            z = magic_div(r, wi, is_load ? T.magic_wx : T.magic_wy);
-            inner = r - z * wi;
-        }
-        slot_index = r;
+    }
+    __syncthreads();
+    const bool copy = T.ls == 0;
+
+    // Every thread owns the same (up to two) load runs and store runs in every tile of the CTA, and bulk plans only use tile
+    // extents that divide the leg extents (no clipped tiles): byte counts and offsets relative to the tile origin are
+    // computed once, before the tile loop.
+    //   transpose mode: load run = (x, z), r = z * wx + x;  store run = (y, z), r = z * wy + y.   copy mode: r = z.
+    // merge group g > 1: the runs r .. r + g - 1 (consecutive along the first enumerated index) are contiguous in global memory and
+    // in the staging buffer; only the leader issues, for the whole group.
+    struct Run { long long rel; int smem; unsigned bytes; };   // bytes == 0: nothing to issue
+    auto prep = [&](bool is_load, int r) {
+        Run R;
+        R.rel = 0;
+        R.smem = 0;
+        R.bytes = 0u;
+        const int nrun = copy ? T.nz : T.nz * (is_load ? T.wx : T.wy);
+        if(r >= nrun) return R;
+        const int group = is_load ? T.mrg_load : T.mrg_store;
         const int* __restrict__ gs = is_load ? T.sstride : T.dstride;
-        const int lrun = is_load ? T.ls : 0;        // the leg along which this side's runs are contiguous
-        const int lin = is_load ? 0 : T.ls;          // the leg enumerated by `inner` (transpose mode)
-        long long off = is_load ? T.src_off : T.dst_off;
-        bool ok = true;
-        {
-            const int b = tile.c[lrun] * T.w[lrun];
-            len = min(T.w[lrun], T.dims[lrun] - b);
-            off += static_cast<long long>(b) * gs[lrun];   // stride 1
-        }
+        int z = r, count = 1;
+        bool leader = true;
         if(!copy) {
-            const int b = tile.c[lin] * T.w[lin];
-            ok = inner < min(T.w[lin], T.dims[lin] - b);
-            off += static_cast<long long>(b + inner) * gs[lin];
+            const int wi = is_load ? T.wx : T.wy;
+            z = magic_div(r, wi, is_load ? T.magic_wx : T.magic_wy);
+            const int inner = r - z * wi;
+            R.rel += static_cast<long long>(inner) * gs[is_load ? 0 : T.ls];
+            if(group > 1) {
+                leader = inner == 0;
+                count = group;
+            }
         }
         for(int i = 0; i < T.nzleg; ++i) {
             const int l = T.zleg[i];
             const int q = magic_div(z, T.w[l], T.zmagic[i]);
             const int c = z - q * T.w[l];
             z = q;
-            const int b = tile.c[l] * T.w[l];
-            ok = ok && (c < T.dims[l] - b);
-            off += static_cast<long long>(b + c) * gs[l];
+            R.rel += static_cast<long long>(c) * gs[l];
+            if(copy && i == 0 && group > 1) {
+                leader = c == 0;
+                count = group;
+            }
         }
-        goff = off;
-        return ok;
+        if(leader) R.bytes = static_cast<unsigned>((is_load ? (copy ? T.wx : T.wy) : T.wx) * count) * 8u;
+        R.smem = r * (is_load ? T.rs_s : T.rs_d);
+        return R;
     };
-    auto tile_bytes = [&](const PermTile& tile) {
-        long long v = 8;
-        for(int l = 0; l < T.nleg; ++l) v *= min(T.w[l], T.dims[l] - tile.c[l] * T.w[l]);
-        return static_cast<unsigned>(v);
+    const Run ld0 = prep(true, tid), ld1 = prep(true, tid + BULK_THREADS), st0 = prep(false, tid), st1 = prep(false, tid + BULK_THREADS);
+    unsigned tile_bytes = 8u;
+    for(int l = 0; l < T.nleg; ++l) tile_bytes *= static_cast<unsigned>(T.w[l]);
+
+    auto origin = [&](int i, bool is_load) {
+        const PermTile& tile = s_tiles[i];
+        long long o = is_load ? T.src_off : T.dst_off;
+        const int* __restrict__ gs = is_load ? T.sstride : T.dstride;
+        for(int l = 0; l < T.nleg; ++l) o += static_cast<long long>(tile.c[l] * T.w[l]) * gs[l];
+        return o;
     };
-    auto issue_loads = [&](const PermTile& tile, double* buf, unsigned barrier) {
-        const bool copy = T.ls == 0;
-        const int nrun = copy ? T.nz : T.nz * T.wx;
-        const int pitch = T.rs_s;
-        if(tid == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(barrier), "r"(tile_bytes(tile)) : "memory");
-        }
-        for(int r = tid; r < nrun; r += BULK_THREADS) {
-            long long goff;
-            int len, si;
-            if(run_geom(tile, true, r, goff, len, si)) bulk_load(smem_u32(buf + si * pitch), src + goff, static_cast<unsigned>(len) * 8u, barrier);
-        }
+    auto issue_loads = [&](int i, int slot) {
+        const double* __restrict__ base = src + origin(i, true);
+        if(tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar[slot]), "r"(tile_bytes) : "memory");
+        if(ld0.bytes) bulk_load(smem_u32(buf[slot] + ld0.smem), base + ld0.rel, ld0.bytes, bar[slot]);
+        if(ld1.bytes) bulk_load(smem_u32(buf[slot] + ld1.smem), base + ld1.rel, ld1.bytes, bar[slot]);
     };
-    auto issue_stores = [&](const PermTile& tile, const double* buf) {
-        const bool copy = T.ls == 0;
-        const int nrun = copy ? T.nz : T.nz * T.wy;
-        const int pitch = T.rs_d;
-        for(int r = tid; r < nrun; r += BULK_THREADS) {
-            long long goff;
-            int len, si;
-            if(run_geom(tile, false, r, goff, len, si)) bulk_store(dst + goff, smem_u32(buf + si * pitch), static_cast<unsigned>(len) * 8u);
-        }
+    auto issue_stores = [&](int i, int slot) {
+        double* __restrict__ base = dst + origin(i, false);
+        if(st0.bytes) bulk_store(base + st0.rel, smem_u32(buf[slot] + st0.smem), st0.bytes);
+        if(st1.bytes) bulk_store(base + st1.rel, smem_u32(buf[slot] + st1.smem), st1.bytes);
         asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
     };
 
-    int staged = reinterpret_cast<const PermTile*>(s_tile[0])->task;
-    stage_task(staged);
-    __syncthreads();
-    unsigned phase[2] = {0u, 0u};
-    // prologue: loads of the first tile
-    issue_loads(*reinterpret_cast<const PermTile*>(s_tile[0]), bufA, bar[0]);
-    for(int ti = t0; ti < t1; ++ti) {
-        const int cur = (ti - t0) & 1;
-        const PermTile tile = *reinterpret_cast<const PermTile*>(s_tile[cur]);
-        const bool copy = T.ls == 0;
-        const bool has_next = ti + 1 < t1;
-        if(has_next && tid < TILE_INTS) s_tile[cur ^ 1][tid] = reinterpret_cast<const int*>(tiles + ti + 1)[tid];
-        if(copy) {
-            // staging buffers alternate: A for even tiles of the CTA, B for odd ones; each has its own mbarrier
-            double* bcur = cur ? bufB : bufA;
-            double* bnext = cur ? bufA : bufB;
-            // the stores of tile ti-1 read bnext: they must have finished reading before the next loads overwrite it
-            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-            __syncthreads();   // also publishes s_tile[cur ^ 1]
-            bool next_same = false;
-            if(has_next) {
-                const PermTile& nt = *reinterpret_cast<const PermTile*>(s_tile[cur ^ 1]);
-                next_same = nt.task == staged;
-                if(next_same) issue_loads(nt, bnext, bar[cur ^ 1]);
-            }
-            mbar_wait(bar[cur], phase[cur]);
-            phase[cur] ^= 1u;
-            issue_stores(tile, bcur);
-            if(has_next && !next_same) {   // task switch: the task record is replaced once nobody needs the old one
-                const PermTile& nt = *reinterpret_cast<const PermTile*>(s_tile[cur ^ 1]);
+    if(copy) {
+        // tile i: buffer / barrier i & 1
+        issue_loads(0, 0);
+        for(int i = 0; i < nt; ++i) {
+            const int slot = i & 1;
+            if(i + 1 < nt) {
+                // the other buffer was drained by the stores of tile i - 1: they must have finished reading it
+                asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
                 __syncthreads();
-                staged = nt.task;
-                stage_task(staged);
-                __syncthreads();
-                if(T.ls == 0) {
-                    issue_loads(nt, bnext, bar[cur ^ 1]);
-                } else {   // next task transposes: its loads always go to bufA / bar[0] with the parity tracked per barrier
-                    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-                    __syncthreads();
-                    issue_loads(nt, bufA, bar[0]);
-                }
+                issue_loads(i + 1, slot ^ 1);
             }
-        } else {
-            // transpose mode: loads land in bufA (bar[0]), destination runs are built in bufB
-            __syncthreads();   // publishes s_tile[cur ^ 1]
-            mbar_wait(bar[0], phase[0]);
-            phase[0] ^= 1u;
-            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // stores of the previous tile have finished reading bufB
+            mbar_wait(bar[slot], static_cast<unsigned>(i >> 1) & 1u);
+            issue_stores(i, slot);
+        }
+    } else {
+        // lane grid gx x gy (2 x 16, or 4 x 8 when wy is a multiple of 8 but not of 16): gy consecutive source elements per row
+        // (conflict-free for any pitch), gx adjacent destination elements (destination pitch / 2 odd => distinct bank pairs).
+        // A warp walks units (z, x_hi); inside a unit only y advances, by constant address increments.
+        const int rs_s = T.rs_s, rs_d = T.rs_d, wx = T.wx, wy = T.wy, nxh = T.nxh;
+        const unsigned m_nxh = T.magic_nxh;
+        const double coeff = T.coeff;
+        const int gxs = T.gx_shift, gx = 1 << gxs, gy = 32 >> gxs;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int y_lo = lane & (gy - 1), x_lo = lane >> (5 - gxs);
+        const int units = T.nz * nxh;
+        const double* __restrict__ S = bufA;
+        double* __restrict__ D = bufB;
+        issue_loads(0, 0);
+        for(int i = 0; i < nt; ++i) {
+            mbar_wait(bar[0], static_cast<unsigned>(i) & 1u);
+            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the stores of tile i - 1 have finished reading D
             __syncthreads();
-            {
-                const int rs_s = T.rs_s, rs_d = T.rs_d, wx = T.wx, wy = T.wy, nxh = T.nxh, nyh = T.nyh;
-                const unsigned m_nyh = T.magic_nyh, m_nxh = T.magic_nxh;
-                const double coeff = T.coeff;
-                const int total = T.nz * nxh * nyh * 32;
-                const int y_lo = tid & 15, x_lo = (tid >> 4) & 1;
-                for(int e = tid; e < total; e += BULK_THREADS) {
-                    int rest = e >> 5;
-                    int q = magic_div(rest, nyh, m_nyh);
-                    const int y = (rest - q * nyh) * 16 + y_lo;
-                    rest = q;
-                    q = magic_div(rest, nxh, m_nxh);
-                    const int x = (rest - q * nxh) * 2 + x_lo;
-                    const int z = q;
-                    if(x < wx && y < wy) bufB[(z * wy + y) * rs_d + x] = coeff * bufA[(z * wx + x) * rs_s + y];
+            for(int u = warp; u < units; u += BULK_THREADS / 32) {
+                const int z = magic_div(u, nxh, m_nxh);
+                const int x = (u - z * nxh) * gx + x_lo;
+                if(x < wx) {
+                    const double* __restrict__ sp = S + (z * wx + x) * rs_s + y_lo;
+                    double* __restrict__ dp = D + (z * wy + y_lo) * rs_d + x;
+                    for(int y = y_lo; y < wy; y += gy) {
+                        *dp = coeff * *sp;
+                        sp += gy;
+                        dp += gy * rs_d;
+                    }
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes to bufB -> visible to the bulk stores
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes to D -> visible to the bulk stores
             __syncthreads();
-            bool next_same = false;
-            if(has_next) {
-                const PermTile& nt = *reinterpret_cast<const PermTile*>(s_tile[cur ^ 1]);
-                next_same = nt.task == staged;
-                if(next_same) issue_loads(nt, bufA, bar[0]);   // overlaps the stores of this tile
-            }
-            issue_stores(tile, bufB);
-            if(has_next && !next_same) {
-                const PermTile& nt = *reinterpret_cast<const PermTile*>(s_tile[cur ^ 1]);
-                __syncthreads();
-                staged = nt.task;
-                stage_task(staged);
-                __syncthreads();
-                if(T.ls == 0) {
-                    // copy mode expects tile parity `cur ^ 1` in buffer (cur ^ 1): A for 0, B for 1; B may still be read by the stores
-                    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-                    __syncthreads();
-                    issue_loads(nt, (cur ^ 1) ? bufB : bufA, bar[cur ^ 1]);
-                } else {
-                    issue_loads(nt, bufA, bar[0]);
-                }
-            }
+            if(i + 1 < nt) issue_loads(i + 1, 0);   // overlaps the stores of this tile
+            issue_stores(i, 1);
         }
     }
     asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // all stores complete before the shared memory is released
@@ -421,9 +387,7 @@ void launch_permute(const double* src, double* dst, const PermutePlan& plan, cud
     const int bulk_mode = bulk_env ? std::atoi(bulk_env) : -1;
     const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
     if(plan.d_btasks && aligned && bulk_mode != 0 && (bulk_mode == 1 || plan.bytes >= (8ll << 20))) {
-        const int tpc = plan.btiles_per_cta < 1 ? 1 : plan.btiles_per_cta;
-        const int grid = (plan.n_btiles + tpc - 1) / tpc;
-        permute_bulk_kernel<<<grid, BULK_THREADS, 0, s>>>(src, dst, plan.d_btasks, plan.d_btiles, plan.n_btiles, tpc);
+        permute_bulk_kernel<<<plan.n_branges, BULK_THREADS, 0, s>>>(src, dst, plan.d_btasks, plan.d_btiles, plan.d_branges);
         check_cuda(cudaGetLastError(), "permute_bulk_kernel launch");
         return;
     }

@@ -205,6 +205,7 @@ PermutePlan::~PermutePlan()
     if(d_tiles) cudaFree(d_tiles);
     if(d_btasks) cudaFree(d_btasks);
     if(d_btiles) cudaFree(d_btiles);
+    if(d_branges) cudaFree(d_branges);
 }
 
 // ------------------------------------------------------------------------------------------------ layouts
@@ -619,20 +620,22 @@ static bool lower_bulk_task(const PermTask& T, std::vector<BulkTask>& btasks, st
         B.sstride[j] = T.src0_stride[j];
         B.w[j] = 1;
     }
-    auto even_chunk = [](int dim, int cap) {   // largest even extent <= cap that splits `dim` evenly
-        if(dim <= cap) return dim;
-        int parts = ceil_div(dim, cap);
-        int w = ceil_div(dim, parts);
-        if(w & 1) ++w;
-        return std::min(w, cap & ~1);
+    // tile extents divide the leg extents (the kernel has no clipped tiles); run legs need even extents
+    auto divisor = [](int dim, long long cap, bool need_even) {
+        int best = 0;
+        for(int w = 1; w <= dim && w <= cap; ++w)
+            if(dim % w == 0 && (!need_even || (w & 1) == 0)) best = w;
+        return best;
     };
     long long vol;
     if(ls == 0) {
-        B.w[0] = even_chunk(T.dims[0], BULK_TILE_ELEMS);
+        B.w[0] = divisor(T.dims[0], BULK_TILE_ELEMS, true);
+        if(B.w[0] < 8) return false;
         vol = B.w[0];
     } else {
-        B.w[0] = even_chunk(T.dims[0], 48);
-        B.w[ls] = even_chunk(T.dims[ls], 48);
+        B.w[0] = divisor(T.dims[0], 48, true);
+        B.w[ls] = divisor(T.dims[ls], 48, true);
+        if(B.w[0] < 8 || B.w[ls] < 8) return false;
         vol = static_cast<long long>(B.w[0]) * B.w[ls];
     }
     // z legs: grow in dst order while the tile stays within the budget
@@ -640,8 +643,7 @@ static bool lower_bulk_task(const PermTask& T, std::vector<BulkTask>& btasks, st
         if(j == ls) continue;
         const long long room = BULK_TILE_ELEMS / vol;
         if(room < 2) break;
-        int w = static_cast<int>(std::min<long long>(T.dims[j], room));
-        if(w < T.dims[j]) w = ceil_div(T.dims[j], ceil_div(T.dims[j], w));
+        const int w = divisor(T.dims[j], room, false);
         B.w[j] = w;
         vol *= w;
         if(w < T.dims[j]) break;
@@ -656,18 +658,28 @@ static bool lower_bulk_task(const PermTask& T, std::vector<BulkTask>& btasks, st
         ++B.nzleg;
         B.nz *= B.w[j];
     }
+    B.mrg_load = B.mrg_store = 1;
     if(ls == 0) {
         B.rs_s = B.rs_d = B.wx;
         if(static_cast<long long>(B.nz) * B.rs_s > BULK_BUF_ELEMS) return false;
+        // runs along the first z leg that continue each other in global memory (whole leg 0 inside the tile)
+        if(B.nzleg > 0 && B.wx == T.dims[0]) {
+            const int l1 = B.zleg[0];
+            if(B.sstride[l1] == B.wx) B.mrg_load = B.w[l1];
+            if(B.dstride[l1] == B.wx) B.mrg_store = B.w[l1];
+        }
     } else {
-        B.rs_s = B.wy + 2;
-        if((B.rs_s / 2) % 2 == 0) B.rs_s += 2;   // pitch / 2 odd: the 2 x 16 lane grid of the transposing pass is conflict-free
+        B.rs_s = B.wy;   // the transposing pass reads 16 consecutive elements of a source run: conflict-free for any pitch
         B.rs_d = B.wx + 2;
-        if((B.rs_d / 2) % 2 == 0) B.rs_d += 2;
+        if((B.rs_d / 2) % 2 == 0) B.rs_d += 2;   // pitch / 2 odd: the 16 destination rows written by a warp hit distinct bank pairs
         if(static_cast<long long>(B.nz) * B.wx * B.rs_s > BULK_BUF_ELEMS || static_cast<long long>(B.nz) * B.wy * B.rs_d > BULK_BUF_ELEMS) return false;
+        if(B.wy == T.dims[ls] && B.sstride[0] == B.wy) B.mrg_load = B.wx;   // the wx source runs of one z are one contiguous piece
     }
-    B.nxh = ceil_div(B.wx, 2);
-    B.nyh = ceil_div(B.wy, 16);
+    // every thread of the kernel owns at most two runs per side; short runs are not worth a bulk operation
+    if((ls == 0 ? B.nz : B.nz * B.wx) > 2 * BULK_THREADS || (ls == 0 ? B.nz : B.nz * B.wy) > 2 * BULK_THREADS) return false;
+    B.gx_shift = (B.wy % 16 != 0 && B.wy % 8 == 0) ? 2 : 1;
+    B.nxh = ceil_div(B.wx, 1 << B.gx_shift);
+    B.nyh = ceil_div(B.wy, 32 >> B.gx_shift);
     auto magic = [](int d) { return static_cast<unsigned>(((1ull << 32) + d - 1) / d); };
     B.magic_wx = magic(B.wx);
     B.magic_wy = magic(B.wy);
@@ -808,7 +820,18 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
     }
     if(bulk_ok && !h_btiles.empty()) {
         plan->n_btiles = static_cast<int>(h_btiles.size());
-        plan->btiles_per_cta = std::max(1, std::min(16, plan->n_btiles / (sm_count * 8)));
+        // CTA ranges: consecutive tiles of one task, about 16 CTAs per SM in the grid, at most 32 tiles per CTA
+        const int tpc = std::max(1, std::min(32, plan->n_btiles / (sm_count * 16)));
+        std::vector<int2> ranges;
+        for(size_t b = 0; b < h_btiles.size();) {
+            size_t e = b;
+            while(e < h_btiles.size() && h_btiles[e].task == h_btiles[b].task && e - b < static_cast<size_t>(tpc)) ++e;
+            ranges.push_back(make_int2(static_cast<int>(b), static_cast<int>(e - b)));
+            b = e;
+        }
+        plan->n_branges = static_cast<int>(ranges.size());
+        check_cuda(cudaMalloc(&plan->d_branges, ranges.size() * sizeof(int2)), "cudaMalloc bulk ranges");
+        check_cuda(cudaMemcpy(plan->d_branges, ranges.data(), ranges.size() * sizeof(int2), cudaMemcpyHostToDevice), "upload bulk ranges");
         check_cuda(cudaMalloc(&plan->d_btasks, h_btasks.size() * sizeof(BulkTask)), "cudaMalloc bulk tasks");
         check_cuda(cudaMemcpy(plan->d_btasks, h_btasks.data(), h_btasks.size() * sizeof(BulkTask), cudaMemcpyHostToDevice), "upload bulk tasks");
         check_cuda(cudaMalloc(&plan->d_btiles, h_btiles.size() * sizeof(PermTile)), "cudaMalloc bulk tiles");

@@ -31,3 +31,14 @@ if "perm" in what:
             ms, nbytes = T.bench_permute(shift, p, reps=5)
             print(f"perm p={p} shift={shift:+d}: {ms:.3f} ms {nbytes/ms/1e6:.0f} GB/s", flush=True)
     ctx.close()
+if "w3" in what:
+    ctx3 = xb.Context([("SU2", 0, 0)])
+    a, e = ctx3.basis([(1, 3), (2, 3)]), ctx3.basis([(1, 16), (2, 32), (3, 36), (4, 30), (5, 18), (6, 8), (7, 4)])
+    Q4 = ctx3.tensor([e, a, a], [e, a, a]).setRandom(1)
+    Q1 = ctx3.tensor([e, a, a], [e, a, a]).setRandom(2)
+    M = Q4 @ Q1
+    for rep in range(2):
+        ctx3.sync(); ctx3.timer_start()
+        U, S, Vd = M.tSVD(144, 1e-10, False)
+        print(f"tSVD W3: {ctx3.timer_stop():.1f} ms", flush=True)
+    ctx3.close()

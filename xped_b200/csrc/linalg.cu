@@ -517,12 +517,9 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
             Vp0[((r >> 4) * 2 + (c & 1)) * (SP * SP / 4) + (r & 15) * 16 + (c >> 1)] = (r == c) ? 1.0 : 0.0;
         }
     }
-    if(CL > 1) {   // peers must not overwrite G1 or exit before everybody has read it
-        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-    } else {
-        __syncthreads();
-    }
+    // peers must not overwrite G1 (with Vl, after the sweep) or exit before everybody has read it: arrive now, wait after the sweep
+    if(CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    __syncthreads();
     lap(2);
 
     // ---- phase 2: Jacobi steps on G; thread (k, l) owns the 2x2 block rows {2k, 2k+1} x columns {2l, 2l+1}; pairs are always the
@@ -582,6 +579,7 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
             Vfin = Vp1;
         }
         any = __syncthreads_or(any);
+        if(CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
         lap(3);
         if(!any) return;   // panel already orthogonal (uniform over the cluster: identical G everywhere)
         // everybody is back in the original seat: Vl[row][col] in the [k][n] form the DMMA fragments of phase 3 read
@@ -811,7 +809,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         static const bool no_precond = std::getenv("XB_SVD_NOPRECOND") != nullptr;
         int pre_max_rows = 0;
         std::vector<QrPreBlock> pre;
-        long long boff = 0, yoff = 0;
+        long long boff = 0, yoff = 0, poff = 0;
         for(const SvdBlock& b : R.blocks) {
             if(b.cols < 2 * SB) continue;
             QrPreBlock q;
@@ -820,6 +818,8 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             q.b_off = boff;
             q.y_off = yoff;
             q.t_off = static_cast<long long>(pre.size()) * 256;
+            q.p_off = poff;
+            poff += b.rows;
             q.m = b.rows;
             q.n = b.cols;
             boff += static_cast<long long>(b.cols) * (b.rows + b.cols);
@@ -830,7 +830,8 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         if(!shifted && !no_precond && !pre.empty() && svd_precondition_supported(pre_max_rows)) {
             double* d_aug = nullptr;
             QrPreBlock* d_pre = nullptr;
-            const long long aug_elems = boff + yoff + 256 * static_cast<long long>(pre.size());
+            const long long toff = 256 * static_cast<long long>(pre.size());
+            const long long aug_elems = boff + yoff + toff + 2 * poff;   // [B | 1], Y, T, row norms, row order (ints in the last segment)
             check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_aug), sizeof(double) * aug_elems, s), "svd precondition workspace");
             check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_pre), sizeof(QrPreBlock) * pre.size(), s), "svd precondition meta");
             ctx.upload_async(d_pre, pre.data(), sizeof(QrPreBlock) * pre.size());
@@ -841,7 +842,8 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
                 e1 = ctx.get_event();
                 cudaEventRecord(e0, s);
             }
-            launch_svd_precondition(R.d_W, R.d_V, d_aug, d_aug + boff, d_aug + boff + yoff, d_pre, pre, s, &ctx.launches);
+            launch_svd_precondition(R.d_W, R.d_V, d_aug, d_aug + boff, d_aug + boff + yoff, d_aug + boff + yoff + toff,
+                                    reinterpret_cast<int*>(d_aug + boff + yoff + toff + poff), d_pre, pre, s, &ctx.launches);
             if(pre_prof) {
                 cudaEventRecord(e1, s);
                 cudaEventSynchronize(e1);

@@ -42,7 +42,37 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 // ---- pack: Baug = [W^T | 1]   /   unpack: W = lower(R_B^T), V = (Q_B^T)^T.  32x32 tiles through shared memory.
 // grid = (ceil((m_max + n_max) / 32), ceil(n_max / 32), nblocks), block = (32, 8)
-__global__ void qr_pack_kernel(const double* __restrict__ W, double* __restrict__ Baug, const QrPreBlock* __restrict__ blocks)
+// Row order of the factorisation (de Rijk / pivoting by initial norms): column j of B = A^T is row perm[j] of A, rows sorted by
+// decreasing norm.  A row permutation of W = A V changes neither the Gram matrices nor V, so the Jacobi stage is unaffected,
+// while the triangular factor becomes graded from the start (two sweeps fewer on the CTM matrices).
+__global__ void qr_row_norms_kernel(const double* __restrict__ W, double* __restrict__ nrm, const QrPreBlock* __restrict__ blocks)
+{
+    const QrPreBlock d = blocks[blockIdx.y];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if(r >= d.m) return;
+    double s = 0.0;
+    for(int c = 0; c < d.n; ++c) {
+        const double v = W[d.w_off + r + static_cast<long long>(c) * d.m];
+        s = fma(v, v, s);
+    }
+    nrm[d.p_off + r] = s;
+}
+
+__global__ void qr_rank_rows_kernel(const double* __restrict__ nrm, int* __restrict__ perm, const QrPreBlock* __restrict__ blocks)
+{
+    const QrPreBlock d = blocks[blockIdx.y];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if(r >= d.m) return;
+    const double mine = nrm[d.p_off + r];
+    int rank = 0;
+    for(int j = 0; j < d.m; ++j) {
+        const double o = nrm[d.p_off + j];
+        rank += (o > mine || (o == mine && j < r)) ? 1 : 0;
+    }
+    perm[d.p_off + rank] = r;   // ranks are a permutation: ties are broken by the row index
+}
+
+__global__ void qr_pack_kernel(const double* __restrict__ W, double* __restrict__ Baug, const int* __restrict__ perm, const QrPreBlock* __restrict__ blocks)
 {
     __shared__ double tile[32][33];
     const QrPreBlock d = blocks[blockIdx.z];
@@ -51,7 +81,7 @@ __global__ void qr_pack_kernel(const double* __restrict__ W, double* __restrict_
     for(int j = threadIdx.y; j < 32; j += 8) {
         const int r = r0 + threadIdx.x, c = c0 + j;
         double v = 0.0;
-        if(r < d.m + d.n && c < d.n) v = r < d.m ? W[d.w_off + r + static_cast<long long>(c) * d.m] : (r - d.m == c ? 1.0 : 0.0);
+        if(r < d.m + d.n && c < d.n) v = r < d.m ? W[d.w_off + perm[d.p_off + r] + static_cast<long long>(c) * d.m] : (r - d.m == c ? 1.0 : 0.0);
         tile[j][threadIdx.x] = v;
     }
     __syncthreads();
@@ -61,7 +91,8 @@ __global__ void qr_pack_kernel(const double* __restrict__ W, double* __restrict_
     }
 }
 
-__global__ void qr_unpack_kernel(const double* __restrict__ Baug, double* __restrict__ W, double* __restrict__ V, const QrPreBlock* __restrict__ blocks)
+__global__ void qr_unpack_kernel(const double* __restrict__ Baug, double* __restrict__ W, double* __restrict__ V, const int* __restrict__ perm,
+                                 const QrPreBlock* __restrict__ blocks)
 {
     __shared__ double tile[32][33];
     const QrPreBlock d = blocks[blockIdx.z];
@@ -78,8 +109,8 @@ __global__ void qr_unpack_kernel(const double* __restrict__ Baug, double* __rest
         const int r = r0 + threadIdx.x, c = c0 + j;
         if(r < d.m + d.n && c < d.n) {
             const double v = tile[threadIdx.x][j];
-            if(r < d.m)
-                W[d.w_off + r + static_cast<long long>(c) * d.m] = r >= c ? v : 0.0;   // R_B is upper trapezoidal; below its diagonal Baug holds stale data
+            if(r < d.m)   // R_B is upper trapezoidal (below its diagonal Baug holds stale data); rows go back to their original places
+                W[d.w_off + perm[d.p_off + r] + static_cast<long long>(c) * d.m] = r >= c ? v : 0.0;
             else
                 V[d.v_off + (r - d.m) + static_cast<long long>(c) * d.n] = v;
         }
@@ -372,8 +403,8 @@ qr_update_kernel(double* __restrict__ Baug, const double* __restrict__ Ybuf, con
 
 bool svd_precondition_supported(int max_rows) { return max_rows <= RPT * QR_THREADS * 4; }
 
-void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, double* Tbuf, const QrPreBlock* d_blocks, const std::vector<QrPreBlock>& h_blocks,
-                             cudaStream_t s, int64_t* launches)
+void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, double* Tbuf, double* nrm, int* perm, const QrPreBlock* d_blocks,
+                             const std::vector<QrPreBlock>& h_blocks, cudaStream_t s, int64_t* launches)
 {
     const int nb = static_cast<int>(h_blocks.size());
     if(nb == 0) return;
@@ -383,9 +414,14 @@ void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, d
         mn_max = std::max(mn_max, b.m + b.n);
     }
     const dim3 tgrid(static_cast<unsigned>((mn_max + 31) / 32), static_cast<unsigned>((n_max + 31) / 32), static_cast<unsigned>(nb)), tblock(32, 8);
-    qr_pack_kernel<<<tgrid, tblock, 0, s>>>(W, Baug, d_blocks);
+    int m_max = 0;
+    for(const QrPreBlock& b : h_blocks) m_max = std::max(m_max, b.m);
+    const dim3 rgrid(static_cast<unsigned>((m_max + 127) / 128), static_cast<unsigned>(nb));
+    qr_row_norms_kernel<<<rgrid, 128, 0, s>>>(W, nrm, d_blocks);
+    qr_rank_rows_kernel<<<rgrid, 128, 0, s>>>(nrm, perm, d_blocks);
+    qr_pack_kernel<<<tgrid, tblock, 0, s>>>(W, Baug, perm, d_blocks);
     check_cuda(cudaGetLastError(), "qr_pack_kernel launch");
-    ++*launches;
+    *launches += 3;
     const int cluster = n_max <= RPT * QR_THREADS ? 1 : 4;
     for(int k0 = 0; k0 < n_max; k0 += PW) {
         if(cluster == 1) {
@@ -412,7 +448,7 @@ void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, d
         }
         *launches += 2;
     }
-    qr_unpack_kernel<<<tgrid, tblock, 0, s>>>(Baug, W, V, d_blocks);
+    qr_unpack_kernel<<<tgrid, tblock, 0, s>>>(Baug, W, V, perm, d_blocks);
     check_cuda(cudaGetLastError(), "qr_unpack_kernel launch");
     ++*launches;
 }

@@ -12,11 +12,12 @@ struct QrPreBlock
     long long w_off, v_off;   // work matrix (m x n, column-major) and accumulator (n x n) of the Jacobi stage
     long long b_off;          // augmented matrix [A^T | 1], n x (m + n), column-major
     long long y_off, t_off;   // Householder panel (<= n x 16) and compact-WY factor (16 x 16)
+    long long p_off;          // row norms / row order (m entries)
     int m, n;                 // m >= n
 };
 
 bool svd_precondition_supported(int max_rows);
-void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, double* Tbuf, const QrPreBlock* d_blocks, const std::vector<QrPreBlock>& h_blocks,
-                             cudaStream_t s, int64_t* launches);
+void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, double* Tbuf, double* nrm, int* perm, const QrPreBlock* d_blocks,
+                             const std::vector<QrPreBlock>& h_blocks, cudaStream_t s, int64_t* launches);
 
 }   // namespace xb

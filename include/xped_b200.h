@@ -129,6 +129,13 @@ int xb_decompose(xb_ctx* ctx, const xb_tensor* T1, const xb_tensor* T2, int64_t 
 /* contract_L / contract_R  src/MPS/MpsContractions.cpp:11-51 / :54-105 */
 int xb_contract_L(xb_ctx* ctx, const xb_tensor* Bold, const xb_tensor* Bra, const xb_tensor* Ket, xb_tensor** Bnew);
 int xb_contract_R(xb_ctx* ctx, const xb_tensor* Bold, const xb_tensor* Bra, const xb_tensor* Ket, xb_tensor** Bnew);
+/* Mps::leftSweepStep / Mps::rightSweepStep (DMRG::BROOM::SVD)  src/MPS/Mps.cpp:181-202 / :204-229 on the site tensors Ac[loc] (Tensor<2,1>)
+ * and its neighbour Ac[loc-1] / Ac[loc+1] (NULL at the chain end or for DISCARD_U / DISCARD_V; *A_nb_new is then NULL).
+ * trunc_weight / entropy receive truncWeight[loc] and S[loc]. */
+int xb_mps_left_sweep_step(xb_ctx* ctx, const xb_tensor* A_loc, const xb_tensor* A_prev, int64_t max_nsv, double eps_svd, xb_tensor** A_loc_new,
+                           xb_tensor** A_nb_new, double* trunc_weight, double* entropy);
+int xb_mps_right_sweep_step(xb_ctx* ctx, const xb_tensor* A_loc, const xb_tensor* A_next, int64_t max_nsv, double eps_svd, xb_tensor** A_loc_new,
+                            xb_tensor** A_nb_new, double* trunc_weight, double* entropy);
 
 /* ---- sector sharding over the GPUs of one box ----------------------------------------------------
  * One process / context per GPU.  A sharded tensor = on every rank a tensor holding only the sectors that rank owns

@@ -4,6 +4,8 @@ Restates src/MPS/MpsContractions.cpp:11-51 (contract_L) and :54-105 (contract_R)
 domain trees (Qin, sigma) -> Q, the dims[1] row slices of each tree's sub-matrix, `optimal_prod_add`
 (src/Interfaces/MatrixInterface_Eigen_impl.cpp:180-196) as a plain triple product.  Pinned by the reference's own
 identity tests/mps_tests.hpp:19-47: contract_L/R must equal the permute + operator* formulation.
+Also the SVD sweep steps Mps::leftSweepStep / rightSweepStep (src/MPS/Mps.cpp:181-229) and dot (src/MPS/MpsAlgebra.cpp:14-51);
+the reference tests hold no values for them ("parity unpinned"): pinned by invariants (norm conservation, orthonormality).
 """
 from __future__ import annotations
 
@@ -56,3 +58,37 @@ def contract_R(Bold: Tensor, Bra: Tensor, Ket: Tensor) -> Tensor:
             Mtmp *= sym.coeff_rightOrtho(Q, Qin)
             Bnew.block(Bnew.dict[Qin])[...] += Mtmp
     return Bnew
+
+
+def left_sweep_step(Ac, loc, max_Nsv=10000, eps_svd=1.0e-10, DISCARD_U=False):
+    """Mps::leftSweepStep, DMRG::BROOM::SVD (src/MPS/Mps.cpp:181-202); Ac is the list of site tensors, modified in place."""
+    U, S, Vd, info = Ac[loc].permute(+1, (0, 2, 1)).tSVD(max_Nsv, eps_svd, False, return_info=True)
+    left = U @ S
+    Ac[loc] = Vd.permute(-1, (0, 2, 1))
+    if loc != 0 and not DISCARD_U:
+        Ac[loc - 1] = Ac[loc - 1] @ left
+    return info
+
+
+def right_sweep_step(Ac, loc, max_Nsv=10000, eps_svd=1.0e-10, DISCARD_V=False):
+    """Mps::rightSweepStep, DMRG::BROOM::SVD (src/MPS/Mps.cpp:204-229)."""
+    U, S, Vd, info = Ac[loc].tSVD(max_Nsv, eps_svd, False, return_info=True)
+    right = S @ Vd
+    Ac[loc] = U
+    if loc != len(Ac) - 1 and not DISCARD_V:
+        Ac[loc + 1] = (right @ Ac[loc + 1].permute(+1, (0, 1, 2))).permute(-1, (0, 1, 2))
+    return info
+
+
+def dot(BraAc, KetAc, direction="RIGHT"):
+    """dot (src/MPS/MpsAlgebra.cpp:14-51)."""
+    sym = KetAc[0].sym
+    if direction == "RIGHT":
+        B = Tensor.Identity(sym, [KetAc[0].uncoupled_domain[0]], [BraAc[0].uncoupled_domain[0]])
+        for l in range(len(BraAc)):
+            B = contract_L(B, BraAc[l], KetAc[l])
+        return B.norm()
+    B = Tensor.Identity(sym, [KetAc[-1].uncoupled_codomain[0]], [BraAc[-1].uncoupled_codomain[0]])
+    for l in range(len(BraAc) - 1, -1, -1):
+        B = contract_R(B, BraAc[l], KetAc[l])
+    return B.norm()

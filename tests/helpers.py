@@ -61,3 +61,15 @@ def assert_same(g, o, tol=1e-12, what=""):
     assert g.structure() == o.structure(), f"{what}: block structure differs"
     e = rel_err(g, o)
     assert e < tol, f"{what}: relative Frobenius error {e:.3e} >= {tol}"
+
+
+def mps_chain_bases(osym, spec, L, loc_entries, chi_cap):
+    """Auxiliary bases of an open chain: aux[0] = vacuum, aux[l+1] = (aux[l] x loc) with every sector dimension capped at
+    `chi_cap` (a small stand-in for Mps::gen_maxBasis, src/MPS/Mps.cpp:68-179); returned as [(q, dim)] lists."""
+    loc = obasis(osym, loc_entries)
+    aux = [[(osym.qvacuum(), 1)]]
+    for _ in range(L):
+        comb = obasis(osym, aux[-1]).combine(loc).forgetHistory()
+        aux.append([(q, min(d, chi_cap)) for q, _, d in comb.data])
+    aux[-1] = [(osym.qvacuum(), 1)]   # target quantum number Qtot = vacuum, one state (Mps constructor: Qtot)
+    return aux

@@ -1,0 +1,80 @@
+"""Mps::leftSweepStep / rightSweepStep / dot (src/MPS/Mps.cpp:181-229, src/MPS/MpsAlgebra.cpp:14-51).
+CPU part: the oracle restatement obeys the invariants that define a sweep (norm conserved, site tensors become isometries).
+GPU part: the device sweep against the oracle -- truncation weights, entropies and bond spectra (gauge invariant)."""
+import numpy as np
+import pytest
+
+import xped_oracle as xo
+from helpers import SPECS, mps_chain_bases, obasis, pair
+from xped_oracle.mps import dot as odot
+from xped_oracle.mps import left_sweep_step, right_sweep_step
+from xped_oracle.rng import uniform_fill
+
+LOC = {"SU2": [((2,), 1)], "U1": [((1,), 1), ((-1,), 1)], "U0": [((), 2)]}
+
+
+def oracle_chain(osym, name, L, chi, seed0):
+    aux = mps_chain_bases(osym, SPECS[name], L, LOC[name], chi)
+    Ac = []
+    for l in range(L):
+        t = xo.Tensor(osym, [obasis(osym, aux[l]), obasis(osym, LOC[name])], [obasis(osym, aux[l + 1])])
+        t.data = uniform_fill(seed0 + l, t.plainSize())
+        Ac.append(t)
+    return aux, Ac
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1", "U0"])
+def test_oracle_sweeps_conserve_the_state(name):
+    osym = xo.Symmetry.from_spec(SPECS[name])
+    L = 6
+    _, Ac = oracle_chain(osym, name, L, 6, 100)
+    n0 = odot(Ac, Ac, "RIGHT")
+    assert abs(odot(Ac, Ac, "LEFT") - n0) <= 1e-12 * n0
+    for l in range(L - 1):
+        right_sweep_step(Ac, l)
+    assert abs(odot(Ac, Ac, "RIGHT") - n0) <= 1e-11 * n0   # the norm travels with S * Vdag into the next site
+    for l in range(L - 1):                                    # left-isometries: A^dagger A = 1 on the right bond
+        one = Ac[l].adjoint() @ Ac[l]
+        eye = one.copy()
+        eye.setIdentity()
+        assert np.abs(one.data - eye.data).max() < 1e-12
+    right_sweep_step(Ac, L - 1)                               # the last step drops S * Vdag (Mps.cpp:226): the state is normalised
+    assert abs(odot(Ac, Ac, "RIGHT") - 1.0) <= 1e-11
+    for l in range(L - 1, 0, -1):
+        left_sweep_step(Ac, l)
+    assert abs(odot(Ac, Ac, "LEFT") - 1.0) <= 1e-11
+    assert abs(odot(Ac, Ac, "RIGHT") - 1.0) <= 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,chi", [("SU2", 8), ("U1", 6), ("U0", 7)])
+def test_gpu_sweeps_match_the_oracle(name, chi):
+    import xped_b200 as xb
+    ctx = xb.Context(SPECS[name])
+    try:
+        osym = xo.Symmetry.from_spec(SPECS[name])
+        L = 6
+        aux, oAc = oracle_chain(osym, name, L, chi, 200)
+        gAc = []
+        for l in range(L):
+            g, o = pair(ctx, osym, [aux[l], LOC[name]], [aux[l + 1]], 200 + l)
+            assert np.array_equal(o.data, oAc[l].data)
+            gAc.append(g)
+        psi = xb.Mps(gAc, max_Nsv=5, eps_svd=1e-10)           # truncating sweep: max_Nsv below the bond dimensions
+        n0 = odot(oAc, oAc, "RIGHT")
+        assert abs(xb.dot(psi, psi, "RIGHT") - n0) <= 1e-12 * n0
+        assert abs(xb.dot(psi, psi, "LEFT") - n0) <= 1e-12 * n0
+        for sweep, order, gstep, ostep in (("right", range(L), psi.rightSweepStep, right_sweep_step),
+                                           ("left", range(L - 1, -1, -1), psi.leftSweepStep, left_sweep_step)):
+            for l in order:
+                gstep(l)
+                info = ostep(oAc, l, 5, 1e-10)
+                assert psi.Ac[l].structure() == oAc[l].structure(), f"{sweep} sweep, site {l}"
+                scale = max(info["truncWeight"], 1e-30, n0 * n0)
+                assert abs(psi.truncWeight[l] - info["truncWeight"]) <= 1e-10 * scale, f"{sweep} sweep, site {l}: truncWeight"
+                if l != L - 1:
+                    assert abs(psi.S[l] - info["entropy"]) <= 1e-9 * max(abs(info["entropy"]), n0 * n0), f"{sweep} sweep, site {l}: entropy"
+            ng, no = xb.dot(psi, psi, "RIGHT"), odot(oAc, oAc, "RIGHT")
+            assert abs(ng - no) <= 1e-10 * no, f"norm after the {sweep} sweep"
+    finally:
+        ctx.close()

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small driver for ncu captures of the two roofline kernels on bandwidth/compute-bound sizes (run under gpurun):
 
-    ncu --set full --clock-control none --import-source on -k regex:permute_kernel -c 3 -o gpurun_out/permute python tools/profile_kernels.py permute
+    ncu --set full --clock-control none --import-source on -k regex:permute_bulk -c 3 -o gpurun_out/permute python tools/profile_kernels.py permute
     ncu --set full --clock-control none --import-source on -k regex:gemm_grouped  -c 1 -o gpurun_out/gemm    python tools/profile_kernels.py gemm
 """
 import os
@@ -17,7 +17,7 @@ if what in ("permute", "gemm"):
     B = ctx.basis([(q, dim) for q in range(-4, 5)])
     T = ctx.tensor([B, B], [B, B]).setRandom(0)
     if what == "permute":
-        for shift, p in [(0, (1, 0, 2, 3)), (0, (2, 3, 0, 1)), (1, (3, 2, 1, 0))]:
+        for shift, p in [(0, (0, 1, 3, 2)), (0, (1, 0, 2, 3)), (1, (3, 2, 1, 0))]:   # copy mode, merged-load transpose, full reversal
             r = T.permute(shift, p)
             ctx.sync()
             del r

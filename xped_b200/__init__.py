@@ -5,3 +5,4 @@ ctypes mirror of the reference's Tensor interface. Nothing here imports oracle/.
 """
 from .capi import LIB_PATH, SIGNATURES, XbError, load  # noqa: F401
 from .tensor import CTM, Context, Qbasis, Tensor, contract_L, contract_R, decompose  # noqa: F401
+from .mps import Mps, dot  # noqa: F401

@@ -79,6 +79,8 @@ SIGNATURES = {
     "xb_decompose": (C.c_int, [P, P, P, C.c_int64, PP, PP]),
     "xb_contract_L": (C.c_int, [P, P, P, P, PP]),
     "xb_contract_R": (C.c_int, [P, P, P, P, PP]),
+    "xb_mps_left_sweep_step": (C.c_int, [P, P, P, C.c_int64, C.c_double, PP, PP, DP, DP]),
+    "xb_mps_right_sweep_step": (C.c_int, [P, P, P, C.c_int64, C.c_double, PP, PP, DP, DP]),
     "xb_layout_structure": (C.c_int, [P, PP, C.c_int, PP, C.c_int, IP, IP, LP, LP, LP]),
     "xb_tensor_create_sectors": (C.c_int, [P, PP, C.c_int, PP, C.c_int, IP, C.c_int, PP]),
     "xb_tensor_set_random_at": (C.c_int, [P, C.c_uint64, LP]),

@@ -705,6 +705,30 @@ int xb_contract_L(xb_ctx* ctx, const xb_tensor* Bold, const xb_tensor* Bra, cons
     });
 }
 
+int xb_mps_left_sweep_step(xb_ctx* ctx, const xb_tensor* A_loc, const xb_tensor* A_prev, int64_t max_nsv, double eps_svd, xb_tensor** A_loc_new,
+                           xb_tensor** A_nb_new, double* trunc_weight, double* entropy)
+{
+    return guard([&] {
+        need(A_loc, "A_loc");
+        Tensor *a = nullptr, *b = nullptr;
+        ctx->impl.mps_left_sweep_step(*A_loc->t, A_prev ? A_prev->t.get() : nullptr, max_nsv, eps_svd, &a, &b, trunc_weight, entropy);
+        *A_loc_new = wrap(ctx, a);
+        *A_nb_new = b ? wrap(ctx, b) : nullptr;
+    });
+}
+
+int xb_mps_right_sweep_step(xb_ctx* ctx, const xb_tensor* A_loc, const xb_tensor* A_next, int64_t max_nsv, double eps_svd, xb_tensor** A_loc_new,
+                            xb_tensor** A_nb_new, double* trunc_weight, double* entropy)
+{
+    return guard([&] {
+        need(A_loc, "A_loc");
+        Tensor *a = nullptr, *b = nullptr;
+        ctx->impl.mps_right_sweep_step(*A_loc->t, A_next ? A_next->t.get() : nullptr, max_nsv, eps_svd, &a, &b, trunc_weight, entropy);
+        *A_loc_new = wrap(ctx, a);
+        *A_nb_new = b ? wrap(ctx, b) : nullptr;
+    });
+}
+
 int xb_contract_R(xb_ctx* ctx, const xb_tensor* Bold, const xb_tensor* Bra, const xb_tensor* Ket, xb_tensor** Bnew)
 {
     return guard([&] {

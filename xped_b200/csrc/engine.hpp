@@ -232,6 +232,11 @@ public:
     void teigh(const Tensor& t, Tensor** D, Tensor** V);
     void contract_L(const Tensor& Bold, const Tensor& Bra, const Tensor& Ket, Tensor** Bnew);
     void contract_R(const Tensor& Bold, const Tensor& Bra, const Tensor& Ket, Tensor** Bnew);
+    // Mps::leftSweepStep / rightSweepStep with DMRG::BROOM::SVD (src/MPS/Mps.cpp:181-229); `neighbour` may be null (chain end / DISCARD)
+    void mps_left_sweep_step(const Tensor& Aloc, const Tensor* Aprev, int64_t max_nsv, double eps_svd, Tensor** Aloc_new, Tensor** Aprev_new, double* trunc_weight,
+                             double* entropy);
+    void mps_right_sweep_step(const Tensor& Aloc, const Tensor* Anext, int64_t max_nsv, double eps_svd, Tensor** Aloc_new, Tensor** Anext_new, double* trunc_weight,
+                              double* entropy);
     void sync();
     // grouped product launcher: one GemmItem per problem (tm = tn = 0); tiles, sorts, uploads and launches
     void run_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems);

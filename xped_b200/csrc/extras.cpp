@@ -224,3 +224,47 @@ void Context::contract_R(const Tensor& Bold, const Tensor& Bra, const Tensor& Ke
 }
 
 }   // namespace xb
+
+namespace xb {
+
+// ------------------------------------------------------------------------------------------------ MPS sweep steps
+// Mps::leftSweepStep (src/MPS/Mps.cpp:181-202):  [U, S, Vdag] = Ac[loc].permute<+1,0,2,1>().tSVD(max_Nsv, eps_svd, truncWeight, entropy, ., false);
+//   Ac[loc] = Vdag.permute<-1,0,2,1>();  Ac[loc-1] = Ac[loc-1] * (U * S).
+void Context::mps_left_sweep_step(const Tensor& Aloc, const Tensor* Aprev, int64_t max_nsv, double eps_svd, Tensor** Aloc_new, Tensor** Aprev_new,
+                                  double* trunc_weight, double* entropy)
+{
+    if(Aloc.layout->rank() != 2 || Aloc.layout->corank() != 1) throw std::invalid_argument("leftSweepStep: site tensor must be a Tensor<2,1>");
+    std::unique_ptr<Tensor> p(permute(Aloc, +1, {0, 2, 1}));
+    SvdResult r = tsvd(*p, max_nsv, eps_svd, false);
+    std::unique_ptr<Tensor> U(r.U), S(r.S), Vd(r.Vd);
+    if(trunc_weight) *trunc_weight = r.trunc_weight;
+    if(entropy) *entropy = r.entropy;
+    *Aloc_new = permute(*Vd, -1, {0, 2, 1});
+    *Aprev_new = nullptr;
+    if(Aprev) {
+        std::unique_ptr<Tensor> left(multiply(*U, false, *S, false));
+        *Aprev_new = multiply(*Aprev, false, *left, false);
+    }
+}
+
+// Mps::rightSweepStep (src/MPS/Mps.cpp:204-229):  [U, S, Vdag] = Ac[loc].tSVD(...);  Ac[loc] = U;
+//   Ac[loc+1] = ((S * Vdag) * Ac[loc+1].permute<+1,0,1,2>()).permute<-1,0,1,2>().
+void Context::mps_right_sweep_step(const Tensor& Aloc, const Tensor* Anext, int64_t max_nsv, double eps_svd, Tensor** Aloc_new, Tensor** Anext_new,
+                                   double* trunc_weight, double* entropy)
+{
+    if(Aloc.layout->rank() != 2 || Aloc.layout->corank() != 1) throw std::invalid_argument("rightSweepStep: site tensor must be a Tensor<2,1>");
+    SvdResult r = tsvd(Aloc, max_nsv, eps_svd, false);
+    std::unique_ptr<Tensor> U(r.U), S(r.S), Vd(r.Vd);
+    if(trunc_weight) *trunc_weight = r.trunc_weight;
+    if(entropy) *entropy = r.entropy;
+    *Anext_new = nullptr;
+    if(Anext) {
+        std::unique_ptr<Tensor> right(multiply(*S, false, *Vd, false));
+        std::unique_ptr<Tensor> np(permute(*Anext, +1, {0, 1, 2}));
+        std::unique_ptr<Tensor> prod(multiply(*right, false, *np, false));
+        *Anext_new = permute(*prod, -1, {0, 1, 2});
+    }
+    *Aloc_new = U.release();
+}
+
+}   // namespace xb

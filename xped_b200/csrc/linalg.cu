@@ -98,7 +98,15 @@ __device__ __forceinline__ bool jacobi_rotation(double a, double b, double c, do
     if(!(a > 0.0 && b > 0.0 && c * c > tol2 * a * b)) return false;
     const double d = b - a, h = 2.0 * c;
     const double r2 = fma(d, d, h * h);
+#ifdef XB_JACOBI_APPROX_ANGLE
+    // |d| + sqrt(r2) only fixes the rotation ANGLE: a 2^-22 accurate square root leaves cs^2 + sn^2 = 1 intact (see below)
+    double rs1;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs1) : "d"(r2));
+    if(r2 < 1.0e-280) rs1 = rsqrt(r2);   // the approximation flushes denormals
+    const double D = fabs(d) + r2 * rs1;
+#else
     const double D = fabs(d) + r2 * rsqrt(r2);
+#endif
     const double rs = rsqrt(fma(D, D, h * h));
     cs = D * rs;
     sn = copysign(h, d * h) * rs;
@@ -867,7 +875,8 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
     int max_rows = 0;
     for(const SvdBlock& b : R.blocks) max_rows = std::max(max_rows, b.rows);
     // resident kernel: cluster of CL CTAs per panel pair, each keeps its row slice (<= rs rows) of the panel in shared memory
-    const int cluster = max_rows <= 160 ? 1 : (max_rows <= 640 ? 4 : 8);
+    static const int cl_env = std::getenv("XB_SVD_CL") ? std::atoi(std::getenv("XB_SVD_CL")) : 0;   // experiment knob: 2 => two CTAs per pair up to 640 rows
+    const int cluster = max_rows <= 160 ? 1 : (max_rows <= 640 ? (cl_env == 2 ? 2 : 4) : 8);
     const bool resident = max_rows <= 2560;
     int rs = 16;
     for(const SvdBlock& b : R.blocks) {
@@ -897,6 +906,8 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         attr[0].val.clusterDim.x = cluster;
         if(cluster == 1)
             check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<1, 20>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<1> launch");
+        else if(cluster == 2)
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<2, 40>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<2> launch");
         else if(cluster == 4)
             check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<4, 20>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<4> launch");
         else
@@ -908,6 +919,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             const int max_dyn = 200 * 1024;
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<1, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<4, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
+            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<2, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<8, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             configured = true;
         }

@@ -98,7 +98,7 @@ __device__ __forceinline__ bool jacobi_rotation(double a, double b, double c, do
     if(!(a > 0.0 && b > 0.0 && c * c > tol2 * a * b)) return false;
     const double d = b - a, h = 2.0 * c;
     const double r2 = fma(d, d, h * h);
-#ifdef XB_JACOBI_APPROX_ANGLE
+#ifndef XB_JACOBI_EXACT_ANGLE
     // |d| + sqrt(r2) only fixes the rotation ANGLE: a 2^-22 accurate square root leaves cs^2 + sn^2 = 1 intact (see below)
     double rs1;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs1) : "d"(r2));
@@ -817,7 +817,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         static const bool no_precond = std::getenv("XB_SVD_NOPRECOND") != nullptr;
         int pre_max_rows = 0;
         std::vector<QrPreBlock> pre;
-        long long boff = 0, yoff = 0, poff = 0;
+        long long boff = 0, yoff = 0, poff = 0, qoff = 0;
         for(const SvdBlock& b : R.blocks) {
             if(b.cols < 2 * SB) continue;
             QrPreBlock q;
@@ -828,6 +828,8 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             q.t_off = static_cast<long long>(pre.size()) * 256;
             q.p_off = poff;
             poff += b.rows;
+            q.q_off = qoff;
+            qoff += static_cast<long long>((b.cols + 31) / 32) * b.rows;
             q.m = b.rows;
             q.n = b.cols;
             boff += static_cast<long long>(b.cols) * (b.rows + b.cols);
@@ -839,7 +841,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             double* d_aug = nullptr;
             QrPreBlock* d_pre = nullptr;
             const long long toff = 256 * static_cast<long long>(pre.size());
-            const long long aug_elems = boff + yoff + toff + 2 * poff;   // [B | 1], Y, T, row norms, row order (ints in the last segment)
+            const long long aug_elems = boff + yoff + toff + qoff + poff;   // [B | 1], Y, T, partial row norms, row order (ints in the last segment)
             check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_aug), sizeof(double) * aug_elems, s), "svd precondition workspace");
             check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_pre), sizeof(QrPreBlock) * pre.size(), s), "svd precondition meta");
             ctx.upload_async(d_pre, pre.data(), sizeof(QrPreBlock) * pre.size());
@@ -851,7 +853,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
                 cudaEventRecord(e0, s);
             }
             launch_svd_precondition(R.d_W, R.d_V, d_aug, d_aug + boff, d_aug + boff + yoff, d_aug + boff + yoff + toff,
-                                    reinterpret_cast<int*>(d_aug + boff + yoff + toff + poff), d_pre, pre, s, &ctx.launches);
+                                    reinterpret_cast<int*>(d_aug + boff + yoff + toff + qoff), d_pre, pre, s, &ctx.launches);
             if(pre_prof) {
                 cudaEventRecord(e1, s);
                 cudaEventSynchronize(e1);
@@ -875,8 +877,8 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
     int max_rows = 0;
     for(const SvdBlock& b : R.blocks) max_rows = std::max(max_rows, b.rows);
     // resident kernel: cluster of CL CTAs per panel pair, each keeps its row slice (<= rs rows) of the panel in shared memory
-    static const int cl_env = std::getenv("XB_SVD_CL") ? std::atoi(std::getenv("XB_SVD_CL")) : 0;   // experiment knob: 2 => two CTAs per pair up to 640 rows
-    const int cluster = max_rows <= 160 ? 1 : (max_rows <= 640 ? (cl_env == 2 ? 2 : 4) : 8);
+    // up to 640 rows two CTAs per pair (one CTA per SM, nothing shares its FP64 pipe) beat four at two per SM: 55.5 vs 57.8 ms per CTM step
+    const int cluster = max_rows <= 160 ? 1 : (max_rows <= 640 ? 2 : 8);
     const bool resident = max_rows <= 2560;
     int rs = 16;
     for(const SvdBlock& b : R.blocks) {
@@ -908,8 +910,6 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<1, 20>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<1> launch");
         else if(cluster == 2)
             check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<2, 40>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<2> launch");
-        else if(cluster == 4)
-            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<4, 20>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<4> launch");
         else
             check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<8, 40>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<8> launch");
     };
@@ -918,7 +918,6 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         if(!configured) {
             const int max_dyn = 200 * 1024;
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<1, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
-            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<4, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<2, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<8, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             configured = true;

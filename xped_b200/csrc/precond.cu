@@ -21,6 +21,8 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "engine.hpp"
@@ -45,28 +47,40 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // Row order of the factorisation (de Rijk / pivoting by initial norms): column j of B = A^T is row perm[j] of A, rows sorted by
 // decreasing norm.  A row permutation of W = A V changes neither the Gram matrices nor V, so the Jacobi stage is unaffected,
 // while the triangular factor becomes graded from the start (two sweeps fewer on the CTM matrices).
-__global__ void qr_row_norms_kernel(const double* __restrict__ W, double* __restrict__ nrm, const QrPreBlock* __restrict__ blocks)
+constexpr int NORM_CHUNK = 32;   // columns per partial sum
+__global__ void qr_row_norms_kernel(const double* __restrict__ W, double* __restrict__ part, const QrPreBlock* __restrict__ blocks)
 {
-    const QrPreBlock d = blocks[blockIdx.y];
+    // part[chunk][row] = sum over the chunk's columns of W[row][c]^2   (grid: rows/128 x chunks x blocks)
+    const QrPreBlock d = blocks[blockIdx.z];
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if(r >= d.m) return;
+    const int c0 = blockIdx.y * NORM_CHUNK;
+    if(r >= d.m || c0 >= d.n) return;
     double s = 0.0;
-    for(int c = 0; c < d.n; ++c) {
+    const int c1 = min(d.n, c0 + NORM_CHUNK);
+    for(int c = c0; c < c1; ++c) {
         const double v = W[d.w_off + r + static_cast<long long>(c) * d.m];
         s = fma(v, v, s);
     }
-    nrm[d.p_off + r] = s;
+    part[d.q_off + static_cast<long long>(blockIdx.y) * d.m + r] = s;
 }
 
-__global__ void qr_rank_rows_kernel(const double* __restrict__ nrm, int* __restrict__ perm, const QrPreBlock* __restrict__ blocks)
+__global__ void qr_rank_rows_kernel(const double* __restrict__ part, int* __restrict__ perm, const QrPreBlock* __restrict__ blocks)
 {
+    extern __shared__ double nrm[];   // all row norms of the block (every CTA reduces the partial sums in the same fixed order)
     const QrPreBlock d = blocks[blockIdx.y];
+    const int nchunk = (d.n + NORM_CHUNK - 1) / NORM_CHUNK;
+    for(int r = threadIdx.x; r < d.m; r += blockDim.x) {
+        double s = 0.0;
+        for(int k = 0; k < nchunk; ++k) s += part[d.q_off + static_cast<long long>(k) * d.m + r];
+        nrm[r] = s;
+    }
+    __syncthreads();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if(r >= d.m) return;
-    const double mine = nrm[d.p_off + r];
+    const double mine = nrm[r];
     int rank = 0;
     for(int j = 0; j < d.m; ++j) {
-        const double o = nrm[d.p_off + j];
+        const double o = nrm[j];
         rank += (o > mine || (o == mine && j < r)) ? 1 : 0;
     }
     perm[d.p_off + rank] = r;   // ranks are a permutation: ties are broken by the row index
@@ -118,13 +132,29 @@ __global__ void qr_unpack_kernel(const double* __restrict__ Baug, double* __rest
 }
 
 // ---- panel factorisation ----------------------------------------------------------------------------------------
+// The column loop is NOT unrolled (an unrolled 16-step body overflows the instruction cache: 64 us per panel measured):
+// after every step the register columns are shifted by one so that the active column is always register column 0.
 template <int CL>
 __global__ void __launch_bounds__(QR_THREADS)
-qr_panel_kernel(double* __restrict__ Baug, double* __restrict__ Ybuf, double* __restrict__ Tbuf, const QrPreBlock* __restrict__ blocks, int k0)
+qr_panel_kernel(double* __restrict__ Baug, double* __restrict__ Ybuf, double* __restrict__ Tbuf, const QrPreBlock* __restrict__ blocks, int k0,
+                unsigned long long* __restrict__ tprof)
 {
-    __shared__ double red[QR_THREADS / 32][PW];   // per-warp partial sums of one column step
-    __shared__ double xch[2][2 * PW];             // [buffer][ sums (16) | diagonal row (16) ] of this CTA, double buffered over the column steps
-    __shared__ double tot[2 * PW];                // cluster-wide sums | diagonal row
+    constexpr int NW = QR_THREADS / 32;
+    const bool prof = tprof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long tp = prof ? clock64() : 0;
+    auto lap = [&](int slot) {
+        if(prof) {
+            const long long now = clock64();
+            atomicAdd(tprof + slot, static_cast<unsigned long long>(now - tp));
+            tp = now;
+        }
+    };
+    __shared__ double red[NW][PW];            // per-warp partial sums of one column step
+    __shared__ double xch[2][2 * PW];         // [buffer][ sums (16) | diagonal row (16) ] of this CTA, double buffered over the column steps
+    __shared__ double tot[2 * PW];            // cluster-wide sums | diagonal row
+    __shared__ double gpart[NW][PW][PW + 1];  // per-warp partial Gram matrices of Y
+    __shared__ double gx[PW * PW];            // this CTA's Gram matrix of Y (exchanged over the cluster)
+    __shared__ double GY[PW][PW + 1];
     __shared__ double Tsm[PW][PW + 1];
     __shared__ double tau_sm[PW];
 
@@ -132,14 +162,15 @@ qr_panel_kernel(double* __restrict__ Baug, double* __restrict__ Ybuf, double* __
     const int n = d.n;
     if(k0 >= n) return;   // uniform over the cluster
     const int h = n - k0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
     unsigned crank = 0;
     if(CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const int per = max(PW, (h + CL - 1) / CL);   // the 16 diagonal rows always sit in CTA 0
     const int lo = static_cast<int>(crank) * per;
     double* __restrict__ P = Baug + d.b_off + k0 + static_cast<long long>(k0) * n;   // panel origin, leading dimension n
+    double* __restrict__ Y = Ybuf + d.y_off;                                          // h x 16, leading dimension h
 
-    // local row l = lo + tid + 256 i  (relative to the panel origin); grow = k0 + l
+    // local row l = lo + tid + 256 i  (relative to the panel origin)
     double x[RPT][PW];
     int lrow[RPT];
     bool rv[RPT];
@@ -151,39 +182,69 @@ qr_panel_kernel(double* __restrict__ Baug, double* __restrict__ Ybuf, double* __
         for(int c = 0; c < PW; ++c) x[i][c] = rv[i] ? P[lrow[i] + static_cast<long long>(c) * n] : 0.0;   // m >= 16: columns k0 .. k0+15 always exist in [B | 1]
     }
     for(int e = tid; e < PW * (PW + 1); e += QR_THREADS) (&Tsm[0][0])[e] = 0.0;
-    if(tid < PW) tau_sm[tid] = 0.0;
     __syncthreads();
+    lap(0);
 
-    // One reduction round: slot c >= j carries s_c = sum_{rows below the diagonal of column j} x[.][j] x[.][c];
-    // slot a < j - 1 carries z_a = Y[:, a]^T Y[:, j-1] (columns < j are already in their final Y form).
-    auto reduce_round = [&](double (&ps)[PW], int buf, bool with_diag_row, int j) {
+#pragma unroll 1
+    for(int j = 0; j < PW; ++j) {
+        // register column c holds panel column j + c; slot c: s_c = sum_{rows below the diagonal} x[.][0] x[.][c]  (slot 0: sigma^2)
+        double ps[PW];
 #pragma unroll
-        for(int c = 0; c < PW; ++c) {
-            double v = ps[c];
+        for(int c = 0; c < PW; ++c) ps[c] = 0.0;
 #pragma unroll
-            for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            ps[c] = v;
+        for(int i = 0; i < RPT; ++i) {
+            const double xa = (rv[i] && lrow[i] > j) ? x[i][0] : 0.0;
+#pragma unroll
+            for(int c = 0; c < PW; ++c) ps[c] = fma(xa, x[i][c], ps[c]);
         }
-        if(lane == 0) {
+        // transposing butterfly: 16 values over 32 lanes in 8 + 4 + 2 + 1 + 1 shuffles (instead of 16 x 5); after the four
+        // halving steps lane l holds the sum over its 16-lane class of value ((l >> 4) & 1) * 8 + ((l >> 3) & 1) * 4 + ...,
+        // the last step adds the two classes
 #pragma unroll
-            for(int c = 0; c < PW; ++c) red[warp][c] = ps[c];
+        for(int k = 0; k < 8; ++k) {
+            const bool up = (lane & 16) != 0;
+            const double send = up ? ps[k] : ps[k + 8], keep = up ? ps[k + 8] : ps[k];
+            ps[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
-        if(with_diag_row && crank == 0 && tid == j) {   // the owner of the diagonal row publishes it
+#pragma unroll
+        for(int k = 0; k < 4; ++k) {
+            const bool up = (lane & 8) != 0;
+            const double send = up ? ps[k] : ps[k + 4], keep = up ? ps[k + 4] : ps[k];
+            ps[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+        for(int k = 0; k < 2; ++k) {
+            const bool up = (lane & 4) != 0;
+            const double send = up ? ps[k] : ps[k + 2], keep = up ? ps[k + 2] : ps[k];
+            ps[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        {
+            const bool up = (lane & 2) != 0;
+            const double send = up ? ps[0] : ps[1], keep = up ? ps[1] : ps[0];
+            ps[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        ps[0] += __shfl_xor_sync(0xffffffffu, ps[0], 1);
+        const int buf = j & 1;
+        if((lane & 1) == 0) {   // lane bits (16, 8, 4, 2) select the value index bits (8, 4, 2, 1)
+            const int c = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            red[warp][c] = ps[0];
+        }
+        if(crank == 0 && tid == j) {   // the owner of the diagonal row publishes it
 #pragma unroll
             for(int c = 0; c < PW; ++c) xch[buf][PW + c] = x[0][c];
         }
         __syncthreads();
         if(tid < PW) {
-            double s = 0.0;
+            double sum = 0.0;
 #pragma unroll
-            for(int w = 0; w < QR_THREADS / 32; ++w) s += red[w][tid];
-            xch[buf][tid] = s;
+            for(int w = 0; w < NW; ++w) sum += red[w][tid];
+            xch[buf][tid] = sum;
         }
         if(CL > 1) {
             asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
             asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
             if(tid < 2 * PW) {
-                double s = 0.0;
+                double sum = 0.0;
                 const unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(&xch[buf][tid]));
                 if(tid < PW) {
                     double part[CL];
@@ -194,108 +255,129 @@ qr_panel_kernel(double* __restrict__ Baug, double* __restrict__ Ybuf, double* __
                         asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(part[cr]) : "r"(remote));
                     }
 #pragma unroll
-                    for(int cr = 0; cr < CL; ++cr) s += part[cr];   // fixed order: identical in every CTA
+                    for(int cr = 0; cr < CL; ++cr) sum += part[cr];   // fixed order: identical in every CTA
                 } else {
                     unsigned remote;
                     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
-                    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(s) : "r"(remote));
+                    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(sum) : "r"(remote));
                 }
-                tot[tid] = s;
+                tot[tid] = sum;
             }
         } else {
             __syncthreads();
             if(tid < 2 * PW) tot[tid] = xch[buf][tid];
         }
         __syncthreads();
-    };
 
-#pragma unroll
-    for(int j = 0; j < PW; ++j) {
-        const int gd = j;   // diagonal row of column j, relative to the panel origin
-        double ps[PW];
-#pragma unroll
-        for(int c = 0; c < PW; ++c) ps[c] = 0.0;
-#pragma unroll
-        for(int i = 0; i < RPT; ++i) {
-            const bool below = rv[i] && lrow[i] > gd;
-#pragma unroll
-            for(int c = j; c < PW; ++c) ps[c] = fma(below ? x[i][j] : 0.0, x[i][c], ps[c]);
-            if(j >= 2) {
-#pragma unroll
-                for(int a = 0; a < j - 1; ++a) ps[a] = fma(x[i][a], x[i][j - 1], ps[a]);
-            }
-        }
-        reduce_round(ps, j & 1, true, j);
-
-        // T column j-1 (compact WY, forward columnwise):  T[0:j-1, j-1] = -tau_{j-1} T[0:j-1, 0:j-1] z
-        if(j >= 2 && crank == 0 && tid < j - 1) {
-            double s = 0.0;
-            for(int l = tid; l < j - 1; ++l) s = fma(Tsm[tid][l], tot[l], s);
-            Tsm[tid][j - 1] = -tau_sm[j - 1] * s;
-        }
-        const double sigma2 = tot[j], alpha = tot[PW + j];
+        lap(1);
+        const double sigma2 = tot[0], alpha = tot[PW];
         double beta = alpha, tau = 0.0, scale = 0.0;
-        if(sigma2 > 0.0) {   // dlarfg; sigma2 == 0  =>  H = 1
-            beta = -copysign(sqrt(fma(alpha, alpha, sigma2)), alpha);
-            tau = (beta - alpha) / beta;
-            scale = 1.0 / (alpha - beta);
+        if(sigma2 > 0.0) {   // dlarfg; sigma2 == 0  =>  H = 1.  One reciprocal square root and one division on the chain:
+            const double nrm2 = fma(alpha, alpha, sigma2), rn = rsqrt(nrm2), nrm = nrm2 * rn;   // nrm = ||(alpha, x)||
+            beta = -copysign(nrm, alpha);
+            tau = fma(fabs(alpha), rn, 1.0);                  // (beta - alpha) / beta = 1 + |alpha| / nrm
+            scale = copysign(1.0 / (fabs(alpha) + nrm), alpha);   // 1 / (alpha - beta)
         }
         double f[PW];
 #pragma unroll
-        for(int c = j + 1; c < PW; ++c) f[c] = tau * fma(scale, tot[c], tot[PW + c]);   // tau * v^T a_c
+        for(int c = 1; c < PW; ++c) f[c] = tau * fma(scale, tot[c], tot[PW + c]);   // tau * v^T a_c
 #pragma unroll
         for(int i = 0; i < RPT; ++i) {
-            if(rv[i] && lrow[i] > gd) {
-                const double v = x[i][j] * scale;
+            double yv = 0.0;   // rows above the diagonal (their R entries were stored when their row was finished)
+            if(rv[i] && lrow[i] > j) {
+                yv = x[i][0] * scale;
 #pragma unroll
-                for(int c = j + 1; c < PW; ++c) x[i][c] = fma(-f[c], v, x[i][c]);
-                x[i][j] = v;
-            } else if(rv[i] && lrow[i] == gd) {   // the diagonal row: finished row j of R
-                P[gd + static_cast<long long>(j) * n] = beta;
+                for(int c = 1; c < PW; ++c) x[i][c] = fma(-f[c], yv, x[i][c]);
+            } else if(rv[i] && lrow[i] == j) {   // the diagonal row: finished row j of R
+                P[j + static_cast<long long>(j) * n] = beta;
 #pragma unroll
-                for(int c = j + 1; c < PW; ++c) {
+                for(int c = 1; c < PW; ++c) {
                     x[i][c] -= f[c];
-                    P[gd + static_cast<long long>(c) * n] = x[i][c];
+                    if(j + c < PW) P[j + static_cast<long long>(j + c) * n] = x[i][c];
                 }
-                x[i][j] = 1.0;
-            } else {
-                x[i][j] = 0.0;   // rows above the diagonal (their R entries were stored when their row was finished)
+                yv = 1.0;
             }
+            if(rv[i]) Y[lrow[i] + static_cast<long long>(j) * h] = yv;
+#pragma unroll
+            for(int c = 1; c < PW; ++c) x[i][c - 1] = x[i][c];   // shift: the next active column becomes register column 0
+            x[i][PW - 1] = 0.0;
         }
         if(crank == 0 && tid == 0) {
             tau_sm[j] = tau;
             Tsm[j][j] = tau;
         }
         __syncthreads();
+        lap(2);
     }
-    {   // Gram entries of the last column, then T column 15
-        double ps[PW];
-#pragma unroll
-        for(int c = 0; c < PW; ++c) ps[c] = 0.0;
-#pragma unroll
-        for(int i = 0; i < RPT; ++i)
-#pragma unroll
-            for(int a = 0; a < PW - 1; ++a) ps[a] = fma(x[i][a], x[i][PW - 1], ps[a]);
-        reduce_round(ps, 0, false, 0);
-        if(crank == 0 && tid < PW - 1) {
-            double s = 0.0;
-            for(int l = tid; l < PW - 1; ++l) s = fma(Tsm[tid][l], tot[l], s);
-            Tsm[tid][PW - 1] = -tau_sm[PW - 1] * s;
+
+    // ---- Gram matrix of Y (this CTA's rows) on DMMA, K split over the warps; then the compact-WY factor T
+    {
+        const int hi = min(h, lo + per);
+        const int nrows = max(0, hi - lo);
+        const int kw = (((nrows + NW - 1) / NW) + 3) & ~3;
+        const int kb = lo + warp * kw, ke = min(hi, kb + kw);
+        double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+        for(int k = kb; k < ke; k += 4) {
+            const int kk = k + fk;
+            const bool kv = kk < ke;
+            const double a0 = kv ? Y[kk + static_cast<long long>(fr) * h] : 0.0;
+            const double a1 = kv ? Y[kk + static_cast<long long>(8 + fr) * h] : 0.0;
+            dmma(acc[0][0][0], acc[0][0][1], a0, a0);
+            dmma(acc[0][1][0], acc[0][1][1], a0, a1);
+            dmma(acc[1][0][0], acc[1][0][1], a1, a0);
+            dmma(acc[1][1][0], acc[1][1][1], a1, a1);
         }
-        __syncthreads();
+#pragma unroll
+        for(int it = 0; it < 2; ++it)
+#pragma unroll
+            for(int jt = 0; jt < 2; ++jt) {
+                gpart[warp][it * 8 + fr][jt * 8 + 2 * fk] = acc[it][jt][0];
+                gpart[warp][it * 8 + fr][jt * 8 + 2 * fk + 1] = acc[it][jt][1];
+            }
     }
-    // Y (h x 16, column-major, leading dimension h) and T (16 x 16, row-major, upper triangular)
-    double* __restrict__ Y = Ybuf + d.y_off;
+    __syncthreads();
+    {
+        double sum = 0.0;
 #pragma unroll
-    for(int i = 0; i < RPT; ++i)
-        if(rv[i]) {
+        for(int w = 0; w < NW; ++w) sum += gpart[w][tid / PW][tid % PW];   // 256 threads: one entry each, fixed order
+        gx[tid] = sum;
+    }
+    if(CL > 1) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        double part[CL];
+        const unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(&gx[tid]));
 #pragma unroll
-            for(int c = 0; c < PW; ++c) Y[lrow[i] + static_cast<long long>(c) * h] = x[i][c];
+        for(int cr = 0; cr < CL; ++cr) {
+            unsigned remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(cr));
+            asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(part[cr]) : "r"(remote));
         }
+        double sum = 0.0;
+#pragma unroll
+        for(int cr = 0; cr < CL; ++cr) sum += part[cr];
+        GY[tid / PW][tid % PW] = sum;
+    } else {
+        GY[tid / PW][tid % PW] = gx[tid];
+    }
+    __syncthreads();
+    lap(3);
+    // forward columnwise recurrence (dlarft):  T[0:j, j] = -tau_j T[0:j, 0:j] (Y[:, 0:j]^T y_j);  row a of T only needs row a
+    if(crank == 0 && tid < PW) {
+        const int a = tid;
+        for(int j = a + 1; j < PW; ++j) {
+            double sum = 0.0;
+            for(int l = a; l < j; ++l) sum = fma(Tsm[a][l], GY[l][j], sum);
+            Tsm[a][j] = -tau_sm[j] * sum;
+        }
+    }
+    __syncthreads();
     if(crank == 0) {
         for(int e = tid; e < PW * PW; e += QR_THREADS) Tbuf[d.t_off + e] = Tsm[e / PW][e % PW];
     }
-    if(CL > 1) {   // nobody leaves while a peer may still read its xch
+    lap(4);
+    if(prof) atomicAdd(tprof + 7, 1ull);
+    if(CL > 1) {   // nobody leaves while a peer may still read its shared memory
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     }
@@ -416,16 +498,23 @@ void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, d
     const dim3 tgrid(static_cast<unsigned>((mn_max + 31) / 32), static_cast<unsigned>((n_max + 31) / 32), static_cast<unsigned>(nb)), tblock(32, 8);
     int m_max = 0;
     for(const QrPreBlock& b : h_blocks) m_max = std::max(m_max, b.m);
+    const dim3 ngrid(static_cast<unsigned>((m_max + 127) / 128), static_cast<unsigned>((n_max + NORM_CHUNK - 1) / NORM_CHUNK), static_cast<unsigned>(nb));
     const dim3 rgrid(static_cast<unsigned>((m_max + 127) / 128), static_cast<unsigned>(nb));
-    qr_row_norms_kernel<<<rgrid, 128, 0, s>>>(W, nrm, d_blocks);
-    qr_rank_rows_kernel<<<rgrid, 128, 0, s>>>(nrm, perm, d_blocks);
+    qr_row_norms_kernel<<<ngrid, 128, 0, s>>>(W, nrm, d_blocks);
+    qr_rank_rows_kernel<<<rgrid, 128, sizeof(double) * m_max, s>>>(nrm, perm, d_blocks);
     qr_pack_kernel<<<tgrid, tblock, 0, s>>>(W, Baug, perm, d_blocks);
     check_cuda(cudaGetLastError(), "qr_pack_kernel launch");
     *launches += 3;
     const int cluster = n_max <= RPT * QR_THREADS ? 1 : 4;
+    unsigned long long* d_tprof = nullptr;
+    static const bool qr_prof = std::getenv("XB_SVD_PROF") != nullptr;
+    if(qr_prof) {
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_tprof), 8 * sizeof(unsigned long long), s), "qr prof");
+        check_cuda(cudaMemsetAsync(d_tprof, 0, 8 * sizeof(unsigned long long), s), "qr prof reset");
+    }
     for(int k0 = 0; k0 < n_max; k0 += PW) {
         if(cluster == 1) {
-            qr_panel_kernel<1><<<nb, QR_THREADS, 0, s>>>(Baug, Ybuf, Tbuf, d_blocks, k0);
+            qr_panel_kernel<1><<<nb, QR_THREADS, 0, s>>>(Baug, Ybuf, Tbuf, d_blocks, k0, d_tprof);
         } else {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(static_cast<unsigned>(nb) * cluster);
@@ -438,7 +527,7 @@ void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, d
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            check_cuda(cudaLaunchKernelEx(&cfg, qr_panel_kernel<4>, Baug, Ybuf, Tbuf, d_blocks, k0), "qr_panel_kernel<4> launch");
+            check_cuda(cudaLaunchKernelEx(&cfg, qr_panel_kernel<4>, Baug, Ybuf, Tbuf, d_blocks, k0, d_tprof), "qr_panel_kernel<4> launch");
         }
         check_cuda(cudaGetLastError(), "qr_panel_kernel launch");
         const int slabs = (mn_max - k0 - PW + SLAB - 1) / SLAB;
@@ -447,6 +536,15 @@ void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, d
             check_cuda(cudaGetLastError(), "qr_update_kernel launch");
         }
         *launches += 2;
+    }
+    if(qr_prof) {
+        unsigned long long hp[8];
+        check_cuda(cudaMemcpyAsync(hp, d_tprof, sizeof(hp), cudaMemcpyDeviceToHost, s), "qr prof readback");
+        check_cuda(cudaStreamSynchronize(s), "qr prof sync");
+        check_cuda(cudaFreeAsync(d_tprof, s), "qr prof free");
+        const double np = hp[7] ? static_cast<double>(hp[7]) : 1.0;
+        std::fprintf(stderr, "[qr prof] panels %llu | CTA0 cycles/panel: load %.0f reduce(16 steps) %.0f update(16 steps) %.0f gram %.0f T %.0f\n", hp[7], hp[0] / np,
+                     hp[1] / np, hp[2] / np, hp[3] / np, hp[4] / np);
     }
     qr_unpack_kernel<<<tgrid, tblock, 0, s>>>(Baug, W, V, perm, d_blocks);
     check_cuda(cudaGetLastError(), "qr_unpack_kernel launch");

@@ -12,7 +12,8 @@ struct QrPreBlock
     long long w_off, v_off;   // work matrix (m x n, column-major) and accumulator (n x n) of the Jacobi stage
     long long b_off;          // augmented matrix [A^T | 1], n x (m + n), column-major
     long long y_off, t_off;   // Householder panel (<= n x 16) and compact-WY factor (16 x 16)
-    long long p_off;          // row norms / row order (m entries)
+    long long p_off;          // row order (m entries)
+    long long q_off;          // partial row norms (ceil(n / 32) x m entries)
     int m, n;                 // m >= n
 };
 

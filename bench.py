@@ -230,6 +230,46 @@ def kernel_sections(xb, device, torch):
     return out, dgemm_peak
 
 
+def sharded_section(xb, torch, dist, local, world):
+    """BASELINE.json configs[4]: the W4 contraction + permute sweep sharded by sector over the ranks.
+    Every rank owns whole sectors (LPT on flops); T*T is purely local, a permute has ONE exchange step (pack kernel -> NCCL
+    alltoallv over NVLink -> gather kernel).  Times are CUDA events on the context stream (which waits for the NCCL stream),
+    max over ranks; bytes / flops are those of the GLOBAL tensor."""
+    from xped_b200.sharded import Comm, ShardedTensor
+    ctx = xb.Context([("U1", 0, 0)], device=local)
+    comm = Comm()
+    B = u1_basis(ctx, 4, 24)
+    T = ShardedTensor.zeros(ctx, comm, [B, B], [B, B]).setRandom(0)
+    nelem = T.plainSize()
+    mine = sum(T.rows[i] * T.cols[i] for i in T.my_sectors())
+    flops = sum(2.0 * r * c * c for r, c in zip(T.rows, T.cols))
+    my_flops = sum(2.0 * T.rows[i] * T.cols[i] * T.cols[i] for i in T.my_sectors())
+
+    def timed(fn, reps):
+        fn()                       # warm-up: plans, exchange buffers, NCCL channels
+        ctx.sync()
+        dist.barrier()
+        ctx.timer_start()
+        for _ in range(reps):
+            fn()
+        ms = ctx.timer_stop() / reps
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out = {"tensor": f"W4: U(1) Tensor<2,2>, leg q=-4..4 x 24, {nelem} elements, 17 sectors over {world} ranks (LPT on flops)",
+           "local_fraction_of_elements": mine / nelem, "local_fraction_of_flops": my_flops / flops, "permutes": []}
+    for shift, p in [(0, (1, 0, 2, 3)), (1, (2, 3, 0, 1)), (-1, (3, 2, 1, 0)), (0, (0, 2, 1, 3))]:
+        ms = timed(lambda: T.permute(shift, p), 3)
+        out["permutes"].append({"p": list(p), "shift": shift, "ms": ms, "GBps_global": 16.0 * nelem / ms / 1e6})
+    ms = timed(lambda: T @ T, 2)
+    out["multiply"] = {"op": "T*T", "flops": flops, "ms": ms, "TFLOPs_global": flops / ms / 1e9}
+    ms = timed(lambda: T.contract([-1, -2, 1, 2], T, [1, 2, -3, -4], 2), 2)
+    out["contract"] = {"op": "contract<{-1,-2,1,2},{1,2,-3,-4},2>(T, T): 3 sharded permutes + local product", "ms": ms}
+    ctx.close()
+    return out
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -242,6 +282,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- xped_b200 has no CPU fallback (use --impl reference for the CPU oracle arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its version banner otherwise)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -332,6 +373,12 @@ def run_b200(args):
         dist.all_reduce(lt)
         launches = int(lt.item())
 
+    sharded = None
+    if world > 1 and not args.no_extras:
+        try:
+            sharded = sharded_section(xb, torch, dist, local, world)
+        except Exception as e:   # the headline line must survive a failure of the optional section
+            sharded = {"error": f"{type(e).__name__}: {e}"}
     extras, dgemm_peak = ({}, None)
     if rank == 0 and not args.no_extras:
         ksampler = ClockSampler(local)
@@ -385,6 +432,8 @@ def run_b200(args):
                 "step_breakdown": {"ms_per_step_with_event_pairs": prof_ms / args.steps,
                                    "per_step": {k: {"ms": v[0] / args.steps, "launch_groups": v[1] / args.steps, "share": shares[k]} for k, v in prof.items()}},
                 "kernels": extras}
+        if sharded is not None:
+            line["sharded_w4"] = sharded
         if cpu_sps is not None:
             line["cpu_baseline"] = {"value": cpu_sps, "unit": "steps/s", "cores": blas_threads(), "kind": "port",
                                     "sample": f"{args.cpu_steps} grow_all() steps of the same D=4 chi=64 workload after 3 warm-up steps, oracle/xped_oracle "

@@ -185,7 +185,7 @@ def _nccl_worker(rank, world, port, out):
                 assert r.structure() == orr.structure()
                 worst = max(worst, float(np.linalg.norm(r.gather() - orr.data) / np.linalg.norm(orr.data)))
             worst = max(worst, _products(ctx, comm, osym, name))
-            worst = max(worst, abs(T.squaredNorm() - float(ot.data @ ot.data)) / float(ot.data @ ot.data))
+            worst = max(worst, abs(T.squaredNorm() - ot.squaredNorm()) / ot.squaredNorm())   # (T * T^dagger).trace(): weighted by the sector degeneracy
             worst = max(worst, abs(T.maxNorm() - float(np.abs(ot.data).max())))
             ctx.close()
         res = torch.tensor([worst], dtype=torch.float64, device="cuda")

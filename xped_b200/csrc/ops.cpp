@@ -1,6 +1,8 @@
 // Whole-tensor operations of the B200 backend (the methods of Xped::Tensor that sit on the hot path).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -63,6 +65,17 @@ void Context::run_gemm(const double* A, const double* B, double* C, const std::v
             }
     }
     if(items[0].empty() && items[1].empty()) return;
+    static const bool gemm_log = std::getenv("XB_GEMM_LOG") != nullptr;
+    if(gemm_log) {
+        int mm = 0, mn = 0, mk = 0;
+        for(const GemmItem& g : problems) {
+            mm = std::max(mm, g.m);
+            mn = std::max(mn, g.n);
+            mk = std::max(mk, g.k);
+        }
+        std::fprintf(stderr, "[gemm] problems %zu flops %.3e max(m,n,k) = (%d,%d,%d) tiles128 %zu tiles64 %zu\n", problems.size(), flops, mm, mn, mk, items[0].size(),
+                     items[1].size());
+    }
     ProfScope prof(*this, CAT_GEMM, flops);
     for(int which = 0; which < 2; ++which) {
         auto& v = items[which];

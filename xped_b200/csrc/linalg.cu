@@ -387,18 +387,23 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
 // columns are interleaved (even seats: block bi, odd seats: block bj): in cross mode (every round but the first of a
 // sweep) only the 16 x 16 pairs between the two blocks are rotated -- 16 steps with the odd seats shifting by one --
 // because the pairs inside a block are visited once per sweep in round 0 (standard cyclic-by-blocks ordering).
-template <int CL, int VREG>
-__global__ void __launch_bounds__(SVD_THREADS, VREG <= 20 ? 2 : 1)
+// DB = false: G and Vl planes are updated in place (read -> barrier -> write -> barrier per Jacobi step instead of one barrier with
+// double buffering): 16 KB less shared memory, which lets two CTAs of the 304-row variant share an SM (D=6: 2700 CTAs per round).
+// SOLO (the 8-CTA variant): only rank 0 of the cluster reduces the Gram matrix and runs the Jacobi sweep; the peers sleep in the
+// cluster barrier (their SM is shared with a CTA of another pair) and then copy the 32 x 32 rotation matrix through DSMEM.
+template <int CL, int VREG, bool DB>
+__global__ void __launch_bounds__(SVD_THREADS, (VREG <= 20 || !DB) ? 2 : 1)
 svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock* __restrict__ blocks, const SvdTask* __restrict__ tasks,
                           int* __restrict__ rotated, unsigned long long* __restrict__ tprof, int rs)
 {
     extern __shared__ __align__(16) double dsm[];
+    constexpr bool SOLO = CL >= 8;
     const int LD = rs + 4;                     // rs is a multiple of 16
     double* __restrict__ Xw = dsm;                 // SP x LD
     double* __restrict__ Gp0 = Xw + SP * LD;       // G in 2x2-block planes: plane (r&1)*2 + (c&1), index (r>>1)*16 + (c>>1); two buffers
-    double* __restrict__ Gp1 = Gp0 + SP * SP;
+    double* __restrict__ Gp1 = DB ? Gp0 + SP * SP : Gp0;
     double* __restrict__ Vp0 = Gp1 + SP * SP;      // Vl in planes: plane (r>=16)*2 + (c&1), index (r&15)*16 + (c>>1); two buffers
-    double* __restrict__ Vp1 = Vp0 + SP * SP;
+    double* __restrict__ Vp1 = DB ? Vp0 + SP * SP : Vp0;
     double* __restrict__ G1 = Vp1 + SP * SP;       // partial Gram matrix (phase 1, SP x G_LD); afterwards Vl in [k][n] form (SP x VL_LD)
     __shared__ int colidx[SP];
 
@@ -497,7 +502,9 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
     } else {
         __syncthreads();
     }
-    {
+    double* __restrict__ Vl = SOLO ? G1 + SP * VL_LD : G1;   // SOLO: a region of its own (peers copy it while G1 may still be read)
+    const bool solver = !SOLO || crank == 0;
+    if(solver) {
         // every thread sums 4 elements; all remote loads are issued before the first use (fixed order: bit-identical G in all CTAs)
         double part[4][CL];
 #pragma unroll
@@ -525,16 +532,17 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
             Vp0[((r >> 4) * 2 + (c & 1)) * (SP * SP / 4) + (r & 15) * 16 + (c >> 1)] = (r == c) ? 1.0 : 0.0;
         }
     }
-    // peers must not overwrite G1 (with Vl, after the sweep) or exit before everybody has read it: arrive now, wait after the sweep
-    if(CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    // second barrier.  Not SOLO: peers must not overwrite G1 (with Vl, after the sweep) or exit before everybody has read it: arrive
+    // now, wait after the sweep.  SOLO: the peers arrive at once, rank 0 after its sweep; completion = "Vl of rank 0 is ready".
+    if(CL > 1 && !(SOLO && crank == 0)) asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     __syncthreads();
     lap(2);
 
     // ---- phase 2: Jacobi steps on G; thread (k, l) owns the 2x2 block rows {2k, 2k+1} x columns {2l, 2l+1}; pairs are always the
     // seats (2g, 2g+1).  G and Vl live in four planes (one per position inside the 2x2 block), so that all loads of a step are
     // unit-stride over the threads (no bank conflicts) and the stores to the rotated seats are permutations of them.
-    double* __restrict__ Vl = G1;
-    {
+    int any_rot = 0;
+    if(solver) {
         constexpr int PL = SP * SP / 4;
         const bool cross = task.mode != 0;
         auto nxt = [&](int x) { return cross ? ((x & 1) ? ((x + 2) & (SP - 1)) : x) : seat_next(x); };
@@ -565,6 +573,7 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
                 n01 = 0.0;
                 n10 = 0.0;
             }
+            if(!DB) __syncthreads();   // in place: everybody has read its 2x2 blocks before the rotated seats are overwritten
             Gn[h00] = n00;
             Gn[h01] = n01;
             Gn[h10] = n10;
@@ -587,15 +596,47 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
             Vfin = Vp1;
         }
         any = __syncthreads_or(any);
-        if(CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        any_rot = any;
+        if(CL > 1 && !SOLO) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
         lap(3);
-        if(!any) return;   // panel already orthogonal (uniform over the cluster: identical G everywhere)
-        // everybody is back in the original seat: Vl[row][col] in the [k][n] form the DMMA fragments of phase 3 read
-        Vl[k * VL_LD + c0] = Vfin[tid];
-        Vl[k * VL_LD + c1] = Vfin[PL + tid];
-        Vl[(k + 16) * VL_LD + c0] = Vfin[2 * PL + tid];
-        Vl[(k + 16) * VL_LD + c1] = Vfin[3 * PL + tid];
+        if(any || SOLO) {
+            // everybody is back in the original seat: Vl[row][col] in the [k][n] form the DMMA fragments of phase 3 read
+            Vl[k * VL_LD + c0] = Vfin[tid];
+            Vl[k * VL_LD + c1] = Vfin[PL + tid];
+            Vl[(k + 16) * VL_LD + c0] = Vfin[2 * PL + tid];
+            Vl[(k + 16) * VL_LD + c1] = Vfin[3 * PL + tid];
+            if(SOLO && tid == 0) Vl[SP * VL_LD] = any ? 1.0 : 0.0;
+        }
         __syncthreads();
+    }
+    if(SOLO) {
+        if(crank == 0) asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        if(crank != 0) {   // copy the rotation matrix (and the "rotated at all" flag) of rank 0
+            const unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(Vl));
+            unsigned remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+            double v[5];
+#pragma unroll
+            for(int i = 0; i < 5; ++i) {
+                const int e = tid + i * SVD_THREADS;
+                v[i] = 0.0;
+                if(e <= SP * VL_LD) asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v[i]) : "r"(remote + 8u * static_cast<unsigned>(e)));
+            }
+#pragma unroll
+            for(int i = 0; i < 5; ++i) {
+                const int e = tid + i * SVD_THREADS;
+                if(e <= SP * VL_LD) Vl[e] = v[i];
+            }
+        }
+        __syncthreads();
+        any_rot = Vl[SP * VL_LD] != 0.0;
+        // third barrier: rank 0 may not leave before the peers have copied; everybody arrives now and waits at the very end
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    }
+    if(!any_rot) {   // panel already orthogonal (uniform over the cluster)
+        if(SOLO) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        return;
     }
     if(tid == 0 && crank == 0) atomicExch(rotated, 1);
 
@@ -639,6 +680,7 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
     stage(reg);
     __syncthreads();
     multiply_slice(Vm, blk.cols, vlo, vhi);
+    if(SOLO) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     lap(4);
     if(prof) atomicAdd(tprof + 7, 1ull);
 }
@@ -885,7 +927,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         const int per = (((b.rows + cluster - 1) / cluster) + 7) & ~7;   // cols <= rows, so the V slice is never longer
         rs = std::max(rs, (per + 15) & ~15);
     }
-    const size_t dyn_smem = sizeof(double) * (static_cast<size_t>(SP) * (rs + 4) + 4 * SP * SP + SP * VL_LD);
+    const size_t dyn_smem = sizeof(double) * (static_cast<size_t>(SP) * (rs + 4) + (cluster == 8 ? 2 : 4) * SP * SP + (cluster == 8 ? 2 : 1) * SP * VL_LD + 2);   // <8, 40, false>: single-buffered planes, Vl in a region of its own
     auto launch_round = [&](const SvdTask* d_round_tasks, int cnt) {
         cudaLaunchConfig_t cfg = {};
         cfg.blockDim = dim3(SVD_THREADS);
@@ -907,19 +949,19 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         cfg.dynamicSmemBytes = dyn_smem;
         attr[0].val.clusterDim.x = cluster;
         if(cluster == 1)
-            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<1, 20>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<1> launch");
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<1, 20, true>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<1> launch");
         else if(cluster == 2)
-            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<2, 40>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<2> launch");
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<2, 40, true>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<2> launch");
         else
-            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<8, 40>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<8> launch");
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<8, 40, false>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<8> launch");
     };
     {
         static bool configured = false;
         if(!configured) {
             const int max_dyn = 200 * 1024;
-            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<1, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
-            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<2, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
-            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<8, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
+            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<1, 20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
+            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<2, 40, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
+            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<8, 40, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             configured = true;
         }
     }

@@ -241,6 +241,11 @@ public:
     // grouped product launcher: one GemmItem per problem (tm = tn = 0); tiles, sorts, uploads and launches
     void run_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems);
 
+    // one Jacobi sweep (flag reset + all rounds) as an instantiated CUDA graph, keyed by layout; valid while the stream-ordered pool
+    // hands the same work buffers back (it does in a steady CTM run), re-captured otherwise
+    struct SweepGraph { cudaGraphExec_t exec = nullptr; const void *w = nullptr, *v = nullptr, *meta = nullptr; int rounds = 0; };
+    std::unordered_map<std::string, SweepGraph> sweep_graphs;
+
     // statistics for bench / gpu_launches
     int64_t launches = 0;
     int64_t plan_hits = 0, plan_misses = 0;

@@ -43,6 +43,9 @@ Context::Context(int dev, const std::vector<Factor>& factors) : sym(std::make_sh
 
 Context::~Context()
 {
+    for(auto& kv : sweep_graphs)
+        if(kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+
     if(device < 0) return;
     cudaSetDevice(device);
     if(stream) cudaStreamSynchronize(stream);

@@ -966,13 +966,58 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         }
     }
     const int max_sweeps = 150;   // bail-out only
+    // The rounds of a sweep are launch-latency-bound at CTM sizes: the sweep (flag reset + all rounds) is captured once into a CUDA
+    // graph and replayed; the instantiated graph is kept per layout and reused as long as the pool returns the same buffers.
+    static const bool no_graph = std::getenv("XB_SVD_NOGRAPH") != nullptr;
+    Context::SweepGraph* sg = nullptr;
+    int rounds_per_sweep = 0;
+    for(size_t r = 0; r + 1 < round_begin.size(); ++r) rounds_per_sweep += round_begin[r + 1] > round_begin[r] ? 1 : 0;
+    if(!no_graph && !svd_prof && rounds_per_sweep >= 8) {
+        const std::string key = L.sig + (shifted ? "#eigh" : "#svd");
+        Context::SweepGraph& g = ctx.sweep_graphs[key];
+        if(g.exec == nullptr || g.w != R.d_W || g.v != R.d_V || g.meta != d_meta) {
+            if(g.exec) cudaGraphExecDestroy(g.exec);
+            g = Context::SweepGraph();
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if(ok) {
+                try {
+                    check_cuda(cudaMemsetAsync(d_flag, 0, sizeof(int), s), "svd flag reset");
+                    for(size_t r = 0; r + 1 < round_begin.size(); ++r) {
+                        const int cnt = round_begin[r + 1] - round_begin[r];
+                        if(cnt > 0) launch_round(d_tasks + round_begin[r], cnt);
+                    }
+                } catch(...) {
+                    ok = false;
+                }
+                ok = (cudaStreamEndCapture(s, &graph) == cudaSuccess) && ok && graph != nullptr;
+            }
+            if(ok) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+            if(graph) cudaGraphDestroy(graph);
+            if(ok) {
+                g.w = R.d_W;
+                g.v = R.d_V;
+                g.meta = d_meta;
+                g.rounds = rounds_per_sweep;
+            } else {
+                cudaGetLastError();   // clear; fall back to plain launches
+                g = Context::SweepGraph();
+            }
+        }
+        if(g.exec) sg = &g;
+    }
     for(R.sweeps = 0; R.sweeps < max_sweeps; ++R.sweeps) {
+        if(sg) {
+            check_cuda(cudaGraphLaunch(sg->exec, s), "svd sweep graph launch");
+            ctx.launches += sg->rounds;
+        } else {
         check_cuda(cudaMemsetAsync(d_flag, 0, sizeof(int), s), "svd flag reset");
         for(size_t r = 0; r + 1 < round_begin.size(); ++r) {
             const int cnt = round_begin[r + 1] - round_begin[r];
             if(cnt == 0) continue;
             launch_round(d_tasks + round_begin[r], cnt);
             ++ctx.launches;
+        }
         }
         check_cuda(cudaGetLastError(), "svd_round_kernel launch");
         check_cuda(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s), "svd flag readback");

@@ -100,6 +100,9 @@ struct BulkTask
     int rs_s, rs_d;           // shared-memory pitch of a source / destination run (even)
     int nxh, nyh;             // ceil(wx / gx), ceil(wy / gy): item grid of the transposing pass (lane grid gx x gy = 2 x 16 or 4 x 8)
     int gx_shift;             // log2(gx)
+    int nzc, gp;              // transpose mode: extent of the first z leg when its source runs continue each other (else 1) and the
+                              // staging pitch of one (z_rest, x) group of nzc source runs
+    unsigned magic_nzc;
     int nzleg;                // number of z legs
     int mrg_load, mrg_store;  // > 1: that many consecutive runs are contiguous in global memory and in the staging buffer (one bulk operation)
     int dims[PERM_MAXLEG], w[PERM_MAXLEG];

@@ -268,14 +268,28 @@ permute_bulk_kernel(const double* __restrict__ src, double* __restrict__ dst, co
         const int* __restrict__ gs = is_load ? T.sstride : T.dstride;
         int z = r, count = 1;
         bool leader = true;
+        int group_index = r;   // position of the run's (z_rest, x) group in the staging buffer (loads of the transpose mode)
+        int zc_in_group = 0;
         if(!copy) {
-            const int wi = is_load ? T.wx : T.wy;
-            z = magic_div(r, wi, is_load ? T.magic_wx : T.magic_wy);
-            const int inner = r - z * wi;
-            R.rel += static_cast<long long>(inner) * gs[is_load ? 0 : T.ls];
-            if(group > 1) {
-                leader = inner == 0;
-                count = group;
+            if(is_load && T.nzc > 1) {   // z-merge: r = (z_rest * wx + x) * nzc + zc
+                const int t = magic_div(r, T.nzc, T.magic_nzc);
+                zc_in_group = r - t * T.nzc;
+                const int zr = magic_div(t, T.wx, T.magic_wx);
+                const int x = t - zr * T.wx;
+                group_index = t;
+                z = zr * T.nzc + zc_in_group;
+                R.rel += static_cast<long long>(x) * gs[0];
+                leader = zc_in_group == 0;
+                count = T.nzc;
+            } else {
+                const int wi = is_load ? T.wx : T.wy;
+                z = magic_div(r, wi, is_load ? T.magic_wx : T.magic_wy);
+                const int inner = r - z * wi;
+                R.rel += static_cast<long long>(inner) * gs[is_load ? 0 : T.ls];
+                if(group > 1) {
+                    leader = inner == 0;
+                    count = group;
+                }
             }
         }
         for(int i = 0; i < T.nzleg; ++i) {
@@ -290,7 +304,7 @@ permute_bulk_kernel(const double* __restrict__ src, double* __restrict__ dst, co
             }
         }
         if(leader) R.bytes = static_cast<unsigned>((is_load ? (copy ? T.wx : T.wy) : T.wx) * count) * 8u;
-        R.smem = r * (is_load ? T.rs_s : T.rs_d);
+        R.smem = (!copy && is_load) ? group_index * T.gp + zc_in_group * T.wy : r * (is_load ? T.rs_s : T.rs_d);
         return R;
     };
     const Run ld0 = prep(true, tid), ld1 = prep(true, tid + BULK_THREADS), st0 = prep(false, tid), st1 = prep(false, tid + BULK_THREADS);
@@ -335,8 +349,8 @@ permute_bulk_kernel(const double* __restrict__ src, double* __restrict__ dst, co
         // lane grid gx x gy (2 x 16, or 4 x 8 when wy is a multiple of 8 but not of 16): gy consecutive source elements per row
         // (conflict-free for any pitch), gx adjacent destination elements (destination pitch / 2 odd => distinct bank pairs).
         // A warp walks units (z, x_hi); inside a unit only y advances, by constant address increments.
-        const int rs_s = T.rs_s, rs_d = T.rs_d, wx = T.wx, wy = T.wy, nxh = T.nxh;
-        const unsigned m_nxh = T.magic_nxh;
+        const int rs_d = T.rs_d, wx = T.wx, wy = T.wy, nxh = T.nxh, nzc = T.nzc, gp = T.gp;
+        const unsigned m_nxh = T.magic_nxh, m_nzc = T.magic_nzc;
         const double coeff = T.coeff;
         const int gxs = T.gx_shift, gx = 1 << gxs, gy = 32 >> gxs;
         const int lane = tid & 31, warp = tid >> 5;
@@ -353,7 +367,8 @@ permute_bulk_kernel(const double* __restrict__ src, double* __restrict__ dst, co
                 const int z = magic_div(u, nxh, m_nxh);
                 const int x = (u - z * nxh) * gx + x_lo;
                 if(x < wx) {
-                    const double* __restrict__ sp = S + (z * wx + x) * rs_s + y_lo;
+                    const int zr = magic_div(z, nzc, m_nzc), zc = z - zr * nzc;
+                    const double* __restrict__ sp = S + (zr * wx + x) * gp + zc * wy + y_lo;
                     double* __restrict__ dp = D + (z * wy + y_lo) * rs_d + x;
                     for(int y = y_lo; y < wy; y += gy) {
                         *dp = coeff * *sp;

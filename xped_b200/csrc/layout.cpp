@@ -641,9 +641,25 @@ static bool lower_bulk_task(const PermTask& T, std::vector<BulkTask>& btasks, st
         if(B.w[0] < 8 || B.w[ls] < 8) return false;
         vol = static_cast<long long>(B.w[0]) * B.w[ls];
     }
-    // z legs: grow in dst order while the tile stays within the budget
+    // z legs.  Transpose mode: a leg whose source stride continues a full source run (sstride == dims[ls] == wy) goes first: its
+    // runs are contiguous in global memory and are fetched by ONE bulk operation per (x, z_rest) (no 128-byte lines shared between
+    // tiles, a quarter of the operations).  Then grow in dst order while the tile stays within the budget.
+    int lc = -1;
+    if(ls != 0 && B.w[ls] == T.dims[ls]) {
+        for(int j = 1; j < n; ++j)
+            if(j != ls && T.dims[j] > 1 && T.src0_stride[j] == T.dims[ls]) lc = j;
+    }
+    if(lc >= 0) {
+        const int w = divisor(T.dims[lc], BULK_TILE_ELEMS / vol, false);
+        if(w >= 2) {
+            B.w[lc] = w;
+            vol *= w;
+        } else {
+            lc = -1;
+        }
+    }
     for(int j = 1; j < n; ++j) {
-        if(j == ls) continue;
+        if(j == ls || j == lc) continue;
         const long long room = BULK_TILE_ELEMS / vol;
         if(room < 2) break;
         const int w = divisor(T.dims[j], room, false);
@@ -654,8 +670,16 @@ static bool lower_bulk_task(const PermTask& T, std::vector<BulkTask>& btasks, st
     B.wx = B.w[0];
     B.wy = ls == 0 ? 1 : B.w[ls];
     B.nz = 1;
+    B.nzc = 1;
+    if(lc >= 0) {   // the continuation leg is the fastest z digit
+        B.zleg[0] = lc;
+        B.zmagic[0] = static_cast<unsigned>(((1ull << 32) + B.w[lc] - 1) / B.w[lc]);
+        B.nzleg = 1;
+        B.nz = B.w[lc];
+        B.nzc = B.w[lc];
+    }
     for(int j = 1; j < n; ++j) {
-        if(j == ls) continue;
+        if(j == ls || j == lc) continue;
         B.zleg[B.nzleg] = j;
         B.zmagic[B.nzleg] = static_cast<unsigned>(((1ull << 32) + B.w[j] - 1) / B.w[j]);
         ++B.nzleg;
@@ -672,15 +696,25 @@ static bool lower_bulk_task(const PermTask& T, std::vector<BulkTask>& btasks, st
             if(B.dstride[l1] == B.wx) B.mrg_store = B.w[l1];
         }
     } else {
-        B.rs_s = B.wy;   // the transposing pass reads 16 consecutive elements of a source run: conflict-free for any pitch
+        B.rs_s = B.wy;   // the transposing pass reads gy consecutive elements of a source run: conflict-free inside a row for any pitch
+        B.gx_shift = (B.wy % 16 != 0 && B.wy % 8 == 0) ? 2 : 1;
+        B.gp = B.nzc * B.wy;   // pitch of the nzc runs of one (z_rest, x): contiguous so that they can arrive in one bulk operation
+        if(B.gx_shift == 2 && B.gp % 16 == 0) B.gp += 8;   // 4 x 8 lane grid: the four rows must not fall onto the same eight bank pairs
         B.rs_d = B.wx + 2;
-        if((B.rs_d / 2) % 2 == 0) B.rs_d += 2;   // pitch / 2 odd: the 16 destination rows written by a warp hit distinct bank pairs
-        if(static_cast<long long>(B.nz) * B.wx * B.rs_s > BULK_BUF_ELEMS || static_cast<long long>(B.nz) * B.wy * B.rs_d > BULK_BUF_ELEMS) return false;
-        if(B.wy == T.dims[ls] && B.sstride[0] == B.wy) B.mrg_load = B.wx;   // the wx source runs of one z are one contiguous piece
+        if((B.rs_d / 2) % 2 == 0) B.rs_d += 2;   // pitch / 2 odd: the destination rows written by a warp hit distinct bank pairs
+        if(static_cast<long long>(B.nz / B.nzc) * B.wx * B.gp > BULK_BUF_ELEMS || static_cast<long long>(B.nz) * B.wy * B.rs_d > BULK_BUF_ELEMS) return false;
+        if(B.nzc > 1)
+            B.mrg_load = B.nzc;   // z-merge
+        else if(B.wy == T.dims[ls] && B.sstride[0] == B.wy && B.gp == B.wy)
+            B.mrg_load = B.wx;    // x-merge: the wx source runs of one z are one contiguous piece
     }
     // every thread of the kernel owns at most two runs per side; short runs are not worth a bulk operation
     if((ls == 0 ? B.nz : B.nz * B.wx) > 2 * BULK_THREADS || (ls == 0 ? B.nz : B.nz * B.wy) > 2 * BULK_THREADS) return false;
-    B.gx_shift = (B.wy % 16 != 0 && B.wy % 8 == 0) ? 2 : 1;
+    if(ls == 0) {
+        B.gx_shift = 1;
+        B.gp = B.wx;
+    }
+    B.magic_nzc = static_cast<unsigned>(((1ull << 32) + B.nzc - 1) / B.nzc);
     B.nxh = ceil_div(B.wx, 1 << B.gx_shift);
     B.nyh = ceil_div(B.wy, 32 >> B.gx_shift);
     auto magic = [](int d) { return static_cast<unsigned>(((1ull << 32) + d - 1) / d); };

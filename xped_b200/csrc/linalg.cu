@@ -880,6 +880,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             pre.push_back(q);
         }
         if(!shifted && !no_precond && !pre.empty() && svd_precondition_supported(pre_max_rows)) {
+            static const bool pre_prof = std::getenv("XB_SVD_PROF") != nullptr;
             double* d_aug = nullptr;
             QrPreBlock* d_pre = nullptr;
             const long long toff = 256 * static_cast<long long>(pre.size());
@@ -887,15 +888,54 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_aug), sizeof(double) * aug_elems, s), "svd precondition workspace");
             check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_pre), sizeof(QrPreBlock) * pre.size(), s), "svd precondition meta");
             ctx.upload_async(d_pre, pre.data(), sizeof(QrPreBlock) * pre.size());
-            static const bool pre_prof = std::getenv("XB_SVD_PROF") != nullptr;
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if(pre_prof) {
                 e0 = ctx.get_event();
                 e1 = ctx.get_event();
                 cudaEventRecord(e0, s);
             }
-            launch_svd_precondition(R.d_W, R.d_V, d_aug, d_aug + boff, d_aug + boff + yoff, d_aug + boff + yoff + toff,
-                                    reinterpret_cast<int*>(d_aug + boff + yoff + toff + qoff), d_pre, pre, s, &ctx.launches);
+            auto run_precondition = [&](int64_t* counter) {
+                launch_svd_precondition(R.d_W, R.d_V, d_aug, d_aug + boff, d_aug + boff + yoff, d_aug + boff + yoff + toff,
+                                        reinterpret_cast<int*>(d_aug + boff + yoff + toff + qoff), d_pre, pre, s, counter);
+            };
+            // ~80 short dependent launches: replayed as a CUDA graph like the sweeps (same validity rule: identical buffers)
+            static const bool no_qr_graph = std::getenv("XB_SVD_NOGRAPH") != nullptr;
+            bool replayed = false;
+            if(!no_qr_graph && !pre_prof) {
+                Context::SweepGraph& g = ctx.sweep_graphs[L.sig + "#qr"];
+                if(g.exec == nullptr || g.w != R.d_W || g.v != d_aug || g.meta != d_pre) {
+                    if(g.exec) cudaGraphExecDestroy(g.exec);
+                    g = Context::SweepGraph();
+                    cudaGraph_t graph = nullptr;
+                    int64_t counted = 0;
+                    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                    if(ok) {
+                        try {
+                            run_precondition(&counted);
+                        } catch(...) {
+                            ok = false;
+                        }
+                        ok = (cudaStreamEndCapture(s, &graph) == cudaSuccess) && ok && graph != nullptr;
+                    }
+                    if(ok) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+                    if(graph) cudaGraphDestroy(graph);
+                    if(ok) {
+                        g.w = R.d_W;
+                        g.v = d_aug;
+                        g.meta = d_pre;
+                        g.rounds = static_cast<int>(counted);
+                    } else {
+                        cudaGetLastError();
+                        g = Context::SweepGraph();
+                    }
+                }
+                if(g.exec) {
+                    check_cuda(cudaGraphLaunch(g.exec, s), "svd preconditioner graph launch");
+                    ctx.launches += g.rounds;
+                    replayed = true;
+                }
+            }
+            if(!replayed) run_precondition(&ctx.launches);
             if(pre_prof) {
                 cudaEventRecord(e1, s);
                 cudaEventSynchronize(e1);

@@ -365,6 +365,28 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- bond energy of the SU(2) Heisenberg model on the converged-so-far environment: computeRDM_h,
+    # computeRDM_v and avg() on the device; S.S is -3/4 on the singlet and +1/4 on the triplet sector of phys x phys
+    energy = None
+    if rank == 0:
+        try:
+            H = ctx.tensor([phys, phys], [phys, phys])
+            secs, rows, cols, offs = H.structure()
+            data = np.zeros(H.plainSize())
+            for q, o in zip(secs, offs):
+                stot = (q[0] - 1) / 2.0
+                data[o] = 0.5 * (stot * (stot + 1.0) - 1.5)
+            H.upload(data)
+            ctm.computeRDM_h()   # plan build
+            ctm.computeRDM_v()
+            ctx.sync()
+            ctx.timer_start()
+            rho_h, rho_v = ctm.computeRDM_h(), ctm.computeRDM_v()
+            e_h, e_v = xb.avg_two_site(rho_h, H), xb.avg_two_site(rho_v, H)
+            energy = {"ms": ctx.timer_stop(), "E_h": e_h, "E_v": e_v, "energy_per_site": e_h + e_v,
+                      "what": "computeRDM_h + computeRDM_v + avg(S.S) after the timed CTM steps (random site tensor: not a variational energy)"}
+        except Exception as e:
+            energy = {"error": f"{type(e).__name__}: {e}"}
     if world > 1:
         tt = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -434,6 +456,8 @@ def run_b200(args):
                 "kernels": extras}
         if sharded is not None:
             line["sharded_w4"] = sharded
+        if energy is not None:
+            line["rdm_energy"] = energy
         if cpu_sps is not None:
             line["cpu_baseline"] = {"value": cpu_sps, "unit": "steps/s", "cores": blas_threads(), "kind": "port",
                                     "sample": f"{args.cpu_steps} grow_all() steps of the same D=4 chi=64 workload after 3 warm-up steps, oracle/xped_oracle "

@@ -187,6 +187,10 @@ int xb_ctm_set(xb_ctm* c, int which, const xb_tensor* t);
 /* single directional pieces, for parity tests: corner 0..3 = UL, UR, LR, LL (Opts::CORNER) */
 int xb_ctm_corner(xb_ctm* c, int corner, xb_tensor** Q);                         /* contractCorner  CTM.cpp:1643-1760 */
 int xb_ctm_move(xb_ctm* c, int direction);                                       /* 0 left, 1 right, 2 top, 3 bottom  :924-1183 */
+/* computeRDM_h (which = 0) / computeRDM_v (which = 1)  src/PEPS/CTM.cpp:528-874 (TRank == 2): normalised two-site density matrix */
+int xb_ctm_rdm(xb_ctm* c, int which, xb_tensor** rho);
+/* avg(rho, O, bond) of a two-site observable  src/PEPS/LinearAlgebra.cpp:57-60 */
+int xb_avg_two_site(xb_ctx* ctx, const xb_tensor* rho, const xb_tensor* op, double* out);
 
 /* ---- micro-benchmark hooks (device-resident, timed with CUDA events on the context stream) -------------- */
 /* runs `reps` launches of the cached plan of permute<shift,p>(t); returns avg ms per launch and algorithmic bytes */

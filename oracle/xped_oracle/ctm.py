@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- CPU oracle of the directional CTMRG step (1x1 unit cell, TRank = 2).
 
 Restates src/PEPS/CTM.cpp:45-244 (init, FROM_A), :385-420 (grow_all), :924-1183 (moves), :1185-1337
-(get_projectors, PROJECTION::CORNER), :1339-1641 (renormalize_*), :1643-1760 (contractCorner),
+(get_projectors, PROJECTION::CORNER), :1339-1641 (renormalize_*), :1643-1760 (contractCorner), :528-874 (computeRDM_h / computeRDM_v,
+TRank == 2 branch) with the two-site average of src/PEPS/LinearAlgebra.cpp:36-110,
 src/PEPS/PEPSContractions.cpp:18-43 (decompose) and src/PEPS/iPEPS.cpp:82-116,200-215 (init_basis, updateAdags).
 The reference has no CTM test of its own: parity of this part is pinned only by invariants ("parity unpinned").
 """
@@ -194,3 +195,66 @@ class CTM:
         """CTM.cpp:385-420."""
         for d in range(4):
             self.move(d)
+
+
+    # ---- reduced density matrices and bond observables (CTM.cpp:528-874, LinearAlgebra.cpp:36-110) ----------------------------
+    def _normalised_rdm(self, rho):
+        Id2 = Tensor.Identity(self.sym, rho.uncoupled_codomain, rho.uncoupled_domain)
+        norm = rho.contract([1, 2, 3, 4], _tw(Id2, 0, 1), [3, 4, 1, 2], 0).trace()     # CTM.cpp:661-667
+        return rho.scale(1.0 / norm)
+
+    def computeRDM_h(self):
+        """rho_h (CTM.cpp:585-603 for the network, :660-667 for the normalisation): two horizontally neighbouring sites."""
+        c = lambda a, la, b, lb, r: a.contract(la, b, lb, r)
+        A, Ad = self.A, self.Adag
+        C1T1 = c(self.C1, [-1, 1], self.T1, [1, -2, -3, -4], 1)
+        T4C1T1 = c(self.T4, [1, -1, -2, -3], _tw(C1T1, 0), [1, -4, -5, -6], 3)
+        T4C1T1A = c(T4C1T1, [-1, 1, -2, -3, 2, -4], A, [1, 2, -5, -6, -7], 4)
+        C4T3 = c(self.C4, [-1, 1], self.T3, [-2, -3, 1, -4], 1)
+        C4T3Ad = c(C4T3, [-1, -2, 1, -3], _tw(Ad, 3), [-4, -5, -6, -7, 1], 3)
+        left_half = c(T4C1T1A, [1, 2, -1, 3, -2, 4, -3], C4T3Ad, [1, 4, -4, 2, 3, -5, -6], 3)
+        T1C2 = c(self.T1, [-1, 1, -2, -3], self.C2, [1, -4], 3)
+        T1C2T2 = c(T1C2, [-1, -2, -3, 1], self.T2, [-4, -5, 1, -6], 3)
+        AT1C2T2 = c(_tw(A, 1), [-1, 1, 2, -2, -3], T1C2T2, [-4, 1, -5, 2, -6, -7], 3)
+        T3C3 = c(self.T3, [-1, -2, -3, 1], self.C3, [-4, 1], 3)
+        T3C3Ad = c(T3C3, [-1, 1, -2, -3], Ad, [-4, -5, -6, -7, 1], 3)
+        right_half = c(AT1C2T2, [-1, 1, -2, -3, 2, 3, 4], T3C3Ad, [1, -4, 4, -5, 2, -6, 3], 3)
+        rho = c(left_half, [1, 2, -3, 3, -1, 4], right_half, [2, -4, 1, 3, 4, -2], 2)
+        return self._normalised_rdm(rho)
+
+    def computeRDM_v(self):
+        """rho_v (CTM.cpp:753-779 for the network): two vertically neighbouring sites."""
+        c = lambda a, la, b, lb, r: a.contract(la, b, lb, r)
+        A, Ad = self.A, self.Adag
+        C1T1 = c(self.C1, [-1, 1], self.T1, [1, -2, -3, -4], 1)
+        T4C1T1 = c(self.T4, [1, -1, -2, -3], _tw(C1T1, 0), [1, -4, -5, -6], 3)
+        T4C1T1A = c(T4C1T1, [-1, 1, -2, -3, 2, -4], A, [1, 2, -5, -6, -7], 4)
+        C2T2 = c(self.C2, [-1, 1], self.T2, [-2, -3, 1, -4], 1)
+        AdC2T2 = c(_tw(Ad, 3, 4), [-1, -2, -3, 1, -4], C2T2, [-5, -6, 1, -7], 4)
+        upper_half = c(T4C1T1A, [-1, 1, 2, 3, 4, -2, -3], AdC2T2, [1, 3, -4, -5, 2, 4, -6], 3)
+        C4T3 = c(self.C4, [-1, 1], self.T3, [-2, -3, 1, -4], 1)
+        T4C4T3 = c(self.T4, [-1, 1, -2, -3], C4T3, [1, -4, -5, -6], 3)
+        AT4C4T3 = c(_tw(A, 0), [1, -1, -2, 2, -3], T4C4T3, [-4, 1, -5, 2, -6, -7], 3)
+        T2C3 = c(self.T2, [-1, -2, -3, 1], self.C3, [1, -4], 3)
+        T2C3Ad = c(T2C3, [-1, 1, -2, -3], Ad, [-4, -5, -6, 1, -7], 3)
+        lower_half = c(AT4C4T3, [-1, 1, -2, -3, 2, 3, 4], T2C3Ad, [1, -4, 4, 2, -5, -6, 3], 3)
+        rho = c(upper_half, [1, 2, -3, -1, 3, 4], lower_half, [2, -4, 1, 4, 3, -2], 2)
+        return self._normalised_rdm(rho)
+
+
+def avg_two_site(rho: Tensor, op: Tensor) -> float:
+    """<O> on a bond (LinearAlgebra.cpp:57-60): rho.twist(0).twist(1).contract<{1,2,3,4},{3,4,1,2},0>(O).trace()."""
+    return float(_tw(rho, 0, 1).contract([1, 2, 3, 4], op, [3, 4, 1, 2], 0).trace())
+
+
+def heisenberg_bond_SU2(sym, phys: Qbasis, J=1.0) -> Tensor:
+    """S_1 . S_2 for two spin-1/2 sites as a Tensor<2,2> on (phys, phys | phys, phys): the reference builds it as
+    J * sqrt(3) * tprod(S^dagger, S) (include/Xped/PEPS/Models/Heisenberg.hpp:47); in the coupled basis it is the scalar
+    (S_tot(S_tot+1) - 3/2) / 2 per total-spin sector: -3/4 on the singlet (q = 1), +1/4 on the triplet (q = 3)."""
+    H = Tensor(sym, [phys, phys], [phys, phys])
+    for i, q in enumerate(H.sector):
+        stot = (q[0] - 1) / 2.0
+        blk = H.block(i)
+        assert blk.shape == (1, 1), "heisenberg_bond_SU2 expects one spin-1/2 multiplet per site"
+        blk[...] = J * 0.5 * (stot * (stot + 1.0) - 1.5)
+    return H

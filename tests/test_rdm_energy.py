@@ -1,0 +1,70 @@
+"""computeRDM_h / computeRDM_v and the two-site average (src/PEPS/CTM.cpp:528-874 TRank == 2, src/PEPS/LinearAlgebra.cpp:57-60;
+SURVEY.md section 8f rank 1).  The reference holds no test values for them ("parity unpinned"): the oracle is pinned by
+invariants (unit trace, hermiticity, bounds of the Heisenberg bond energy, symmetry of a rotation-invariant site tensor), the
+device path is compared with the oracle (the RDM is gauge invariant on the chi legs, so the comparison is element-wise)."""
+import numpy as np
+import pytest
+
+import xped_oracle as xo
+from helpers import SPECS, obasis, pair
+from xped_oracle.ctm import CTM as OCTM
+from xped_oracle.ctm import avg_two_site as oavg
+from xped_oracle.ctm import heisenberg_bond_SU2, init_basis
+from xped_oracle.rng import uniform_fill
+
+
+def _octm(name, D, chi, seed):
+    osym = xo.Symmetry.from_spec(SPECS[name])
+    phys_e = [((2,), 1)] if name == "SU2" else [((1,), 1), ((-1,), 1)]
+    phys = obasis(osym, phys_e)
+    aux = init_basis(osym, D, phys)
+    A = xo.Tensor(osym, [aux, aux], [aux, aux, phys])
+    A.data = uniform_fill(seed, A.plainSize())
+    return osym, phys, phys_e, [(q, d) for q, _, d in aux.data], OCTM(A, chi)
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1"])
+def test_oracle_rdm_invariants(name):
+    osym, phys, _, _, c = _octm(name, 3, 9, 5)
+    for _ in range(3):
+        c.grow_all()
+    Id = xo.Tensor.Identity(osym, [phys, phys], [phys, phys])
+    for rho in (c.computeRDM_h(), c.computeRDM_v()):
+        assert rho.rank == 2 and rho.corank == 2
+        assert abs(oavg(rho, Id) - 1.0) < 1e-12                                   # unit trace (CTM.cpp:660-667)
+        herm = np.linalg.norm((rho - rho.adjoint()).data) / np.linalg.norm((rho + rho.adjoint()).data)
+        assert herm < 1e-3, herm                                                   # rho_h_hermitian_check: exact only for a converged environment
+    if name == "SU2":
+        H = heisenberg_bond_SU2(osym, phys)
+        for rho in (c.computeRDM_h(), c.computeRDM_v()):
+            assert -0.75 - 1e-9 <= oavg(rho, H) <= 0.25 + 1e-9                     # spectrum of S.S on two spins 1/2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,D,chi", [("SU2", 3, 10), ("U1", 2, 8)])
+def test_gpu_rdm_and_energy_match_the_oracle(name, D, chi):
+    import xped_b200 as xb
+    ctx = xb.Context(SPECS[name])
+    try:
+        osym, phys, phys_e, aux_e, o = _octm(name, D, chi, 51)
+        gA, oA = pair(ctx, osym, [aux_e, aux_e], [aux_e, aux_e, phys_e], 51)
+        assert np.array_equal(oA.data, o.A.data)
+        g = xb.CTM(gA, chi)
+        gO, oO = pair(ctx, osym, [phys_e, phys_e], [phys_e, phys_e], 77)           # a random two-site observable
+        if name == "SU2":
+            oH = heisenberg_bond_SU2(osym, phys)
+            gH = ctx.tensor([ctx.basis(phys_e)] * 2, [ctx.basis(phys_e)] * 2)
+            assert gH.structure() == oH.structure()
+            gH.upload(oH.data)
+        for step in range(3):
+            for (grho, orho, what) in ((g.computeRDM_h(), o.computeRDM_h(), "rho_h"), (g.computeRDM_v(), o.computeRDM_v(), "rho_v")):
+                assert grho.structure() == orho.structure(), what
+                err = np.linalg.norm(grho.download() - orho.data) / np.linalg.norm(orho.data)
+                assert err < 1e-9, f"step {step} {what}: {err:.2e}"
+                assert abs(xb.avg_two_site(grho, gO) - oavg(orho, oO)) < 1e-9
+                if name == "SU2":
+                    assert abs(xb.avg_two_site(grho, gH) - oavg(orho, oH)) < 1e-9
+            g.grow_all()
+            o.grow_all()
+    finally:
+        ctx.close()

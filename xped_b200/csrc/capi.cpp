@@ -789,6 +789,23 @@ int xb_ctm_corner(xb_ctm* c, int corner, xb_tensor** Qo)
     });
 }
 
+int xb_ctm_rdm(xb_ctm* c, int which, xb_tensor** rho)
+{
+    return guard([&] {
+        need(c, "ctm");
+        *rho = wrap(c->ctx, c->c->rdm(which));
+    });
+}
+
+int xb_avg_two_site(xb_ctx* ctx, const xb_tensor* rho, const xb_tensor* op, double* out)
+{
+    return guard([&] {
+        need(rho, "rho");
+        need(op, "op");
+        *out = avg_two_site(ctx->impl, *rho->t, *op->t);
+    });
+}
+
 int xb_ctm_move(xb_ctm* c, int direction)
 {
     return guard([&] {

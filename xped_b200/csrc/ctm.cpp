@@ -113,6 +113,64 @@ TP Ctm::corner(int c) const
 
 Tensor* Ctm::contract_corner(int c) { return ctx_.copy(*corner(c)); }
 
+// Full contraction X[1,2,3,4] Y[3,4,1,2] of two Tensor<2,2> = trace(X * Y): contract<{1,2,3,4},{3,4,1,2},0>(...).trace() of the
+// reference goes through a Tensor<0,4> * Tensor<4,0> product; the recoupling factors of the leg bending cancel in a full contraction.
+static double full_contraction(Context& ctx, const Tensor& X, const Tensor& Y)
+{
+    std::unique_ptr<Tensor> prod(ctx.multiply(X, false, Y, false));
+    return ctx.trace(*prod);
+}
+
+double avg_two_site(Context& ctx, const Tensor& rho, const Tensor& op)
+{
+    if(rho.layout->rank() != 2 || rho.layout->corank() != 2 || op.layout->rank() != 2 || op.layout->corank() != 2)
+        throw std::invalid_argument("avg: rho and the observable must be Tensor<2,2>");
+    std::unique_ptr<Tensor> a(ctx.twist(rho, 0)), b(ctx.twist(*a, 1));
+    return full_contraction(ctx, *b, op);
+}
+
+Tensor* Ctm::rdm(int which)
+{
+    TP rho;
+    if(which == 0) {   // computeRDM_h, CTM.cpp:585-603
+        TP C1T1 = con(C1_, {-1, 1}, T1_, {1, -2, -3, -4}, 1);
+        TP T4C1T1 = con(T4_, {1, -1, -2, -3}, tw(C1T1, {0}), {1, -4, -5, -6}, 3);
+        TP T4C1T1A = con(T4C1T1, {-1, 1, -2, -3, 2, -4}, A_, {1, 2, -5, -6, -7}, 4);
+        TP C4T3 = con(C4_, {-1, 1}, T3_, {-2, -3, 1, -4}, 1);
+        TP C4T3Ad = con(C4T3, {-1, -2, 1, -3}, tw(Adag_, {3}), {-4, -5, -6, -7, 1}, 3);
+        TP left_half = con(T4C1T1A, {1, 2, -1, 3, -2, 4, -3}, C4T3Ad, {1, 4, -4, 2, 3, -5, -6}, 3);
+        TP T1C2 = con(T1_, {-1, 1, -2, -3}, C2_, {1, -4}, 3);
+        TP T1C2T2 = con(T1C2, {-1, -2, -3, 1}, T2_, {-4, -5, 1, -6}, 3);
+        TP AT1C2T2 = con(tw(A_, {1}), {-1, 1, 2, -2, -3}, T1C2T2, {-4, 1, -5, 2, -6, -7}, 3);
+        TP T3C3 = con(T3_, {-1, -2, -3, 1}, C3_, {-4, 1}, 3);
+        TP T3C3Ad = con(T3C3, {-1, 1, -2, -3}, Adag_, {-4, -5, -6, -7, 1}, 3);
+        TP right_half = con(AT1C2T2, {-1, 1, -2, -3, 2, 3, 4}, T3C3Ad, {1, -4, 4, -5, 2, -6, 3}, 3);
+        rho = con(left_half, {1, 2, -3, 3, -1, 4}, right_half, {2, -4, 1, 3, 4, -2}, 2);
+    } else if(which == 1) {   // computeRDM_v, CTM.cpp:753-779
+        TP C1T1 = con(C1_, {-1, 1}, T1_, {1, -2, -3, -4}, 1);
+        TP T4C1T1 = con(T4_, {1, -1, -2, -3}, tw(C1T1, {0}), {1, -4, -5, -6}, 3);
+        TP T4C1T1A = con(T4C1T1, {-1, 1, -2, -3, 2, -4}, A_, {1, 2, -5, -6, -7}, 4);
+        TP C2T2 = con(C2_, {-1, 1}, T2_, {-2, -3, 1, -4}, 1);
+        TP AdC2T2 = con(tw(Adag_, {3, 4}), {-1, -2, -3, 1, -4}, C2T2, {-5, -6, 1, -7}, 4);
+        TP upper_half = con(T4C1T1A, {-1, 1, 2, 3, 4, -2, -3}, AdC2T2, {1, 3, -4, -5, 2, 4, -6}, 3);
+        TP C4T3 = con(C4_, {-1, 1}, T3_, {-2, -3, 1, -4}, 1);
+        TP T4C4T3 = con(T4_, {-1, 1, -2, -3}, C4T3, {1, -4, -5, -6}, 3);
+        TP AT4C4T3 = con(tw(A_, {0}), {1, -1, -2, 2, -3}, T4C4T3, {-4, 1, -5, 2, -6, -7}, 3);
+        TP T2C3 = con(T2_, {-1, -2, -3, 1}, C3_, {1, -4}, 3);
+        TP T2C3Ad = con(T2C3, {-1, 1, -2, -3}, Adag_, {-4, -5, -6, 1, -7}, 3);
+        TP lower_half = con(AT4C4T3, {-1, 1, -2, -3, 2, 3, 4}, T2C3Ad, {1, -4, 4, 2, -5, -6, 3}, 3);
+        rho = con(upper_half, {1, 2, -3, -1, 3, 4}, lower_half, {2, -4, 1, 4, 3, -2}, 2);
+    } else {
+        throw std::invalid_argument("CTM: rdm selector must be 0 (horizontal) or 1 (vertical)");
+    }
+    // norm = rho.contract<{1,2,3,4},{3,4,1,2},0>(Id2.twist(0).twist(1)).trace();  rho *= 1 / norm   (CTM.cpp:660-667)
+    const Layout& L = *rho->layout;
+    TP Id2(new Tensor(&ctx_, ctx_.layout(L.cod, L.dom), true));
+    ctx_.fill(*Id2, 1, 0.0, 0);
+    const double norm = full_contraction(ctx_, *rho, *tw(Id2, {0, 1}));
+    return ctx_.axpby(1.0 / norm, *rho, 0.0, nullptr);
+}
+
 void Ctm::projectors(int direction, TP& P1, TP& P2) const
 {
     // get_projectors, PROJECTION::CORNER (CTM.cpp:1196-1318); decompose argument order per direction.

@@ -11,6 +11,8 @@ using TP = std::shared_ptr<Tensor>;
 
 // decompose(T1, T2, chi): src/PEPS/PEPSContractions.cpp:18-43
 void decompose_projectors(Context& ctx, const Tensor& T1, const Tensor& T2, int64_t chi, Tensor** P1, Tensor** P2);
+// avg(rho, O, bond) for a two-site observable (src/PEPS/LinearAlgebra.cpp:57-60): rho.twist(0).twist(1).contract<{1,2,3,4},{3,4,1,2},0>(O).trace()
+double avg_two_site(Context& ctx, const Tensor& rho, const Tensor& op);
 
 class Ctm
 {
@@ -20,6 +22,7 @@ public:
     void grow_all();                    // CTM.cpp:385-420
     void move(int direction);           // 0 left, 1 right, 2 top, 3 bottom  (CTM.cpp:924-1183)
     Tensor* contract_corner(int corner);   // 0 UL, 1 UR, 2 LR, 3 LL  (CTM.cpp:1643-1760)
+    Tensor* rdm(int which);             // 0: rho_h, 1: rho_v, normalised  (computeRDM_h / computeRDM_v, CTM.cpp:528-874, TRank == 2)
     const Tensor& get(int which) const;
     void set(int which, Tensor* t);     // takes ownership
 

@@ -348,3 +348,23 @@ class CTM:
         h = C.c_void_p()
         check(self.ctx.lib.xb_ctm_corner(self.h, int(corner), C.byref(h)))
         return Tensor(self.ctx, h)
+
+    def _rdm(self, which):
+        h = C.c_void_p()
+        check(self.ctx.lib.xb_ctm_rdm(self.h, which, C.byref(h)))
+        return Tensor(self.ctx, h)
+
+    def computeRDM_h(self):
+        """normalised rho_h of two horizontally neighbouring sites (CTM::computeRDM_h, src/PEPS/CTM.cpp:528-700)"""
+        return self._rdm(0)
+
+    def computeRDM_v(self):
+        """normalised rho_v of two vertically neighbouring sites (CTM::computeRDM_v, src/PEPS/CTM.cpp:702-874)"""
+        return self._rdm(1)
+
+
+def avg_two_site(rho, op):
+    """avg(rho, O, bond) of a two-site observable (src/PEPS/LinearAlgebra.cpp:57-60)"""
+    out = C.c_double()
+    check(rho.ctx.lib.xb_avg_two_site(rho.ctx.h, rho.h, op.h, C.byref(out)))
+    return out.value

@@ -147,6 +147,10 @@ int xb_mps_right_sweep_step(xb_ctx* ctx, const xb_tensor* A_loc, const xb_tensor
 /* canonical structure of Tensor(domain, codomain) without allocating it; q == NULL: only the sector count */
 int xb_layout_structure(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int* n_sectors, int* q,
                         int64_t* rows, int64_t* cols, int64_t* offsets);
+/* Host-side statistics of the cached plan of permute<shift,p> of the canonical Tensor(domain | codomain) (works in planning-only
+ * contexts): out = {destination tasks, LSU tiles, max fan-in, identity copy?, cp.async.bulk tiles (0 = plan not eligible), algorithmic bytes} */
+int xb_permute_plan_stats(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n,
+                          int64_t out[6]);
 /* a shard: Tensor(domain, codomain) holding only the listed sectors, in that order, zero-initialised */
 int xb_tensor_create_sectors(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, const int* q, int n_sectors,
                              xb_tensor** out);

@@ -54,10 +54,11 @@ def test_permute_all_24x5(ctxs, name):
             assert_same(g.permute(shift, p), o.permute(shift, p), TOL, f"{name} permute<{shift},{p}>")
 
 
-@pytest.mark.parametrize("name,dim", [("U1", 4), ("U1", 6), ("Z3", 2), ("U0", 8)])
+@pytest.mark.parametrize("name,dim", [("U1", 4), ("U1", 8), ("U1", 12), ("Z3", 10), ("U0", 8)])
 def test_permute_bulk_path(ctxs, name, dim, monkeypatch):
     """The cp.async.bulk form of the permute (normally used for >= 8 MB tensors) forced on small tensors whose runs obey
-    the 16-byte rules (even multiplicities): all 24 permutations x 5 shifts, bit-exact against the oracle (coefficients
+    the 16-byte rules (even multiplicities; runs shorter than 8 doubles stay on the LSU form): all 24 permutations x 5 shifts,
+    bit-exact against the oracle (coefficients
     of bosonic Abelian symmetries are 1, so the permute is a pure data movement)."""
     monkeypatch.setenv("XB_PERMUTE_BULK", "1")
     ctx, osym = ctxs(name)

@@ -380,6 +380,24 @@ int xb_layout_structure(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis
     });
 }
 
+int xb_permute_plan_stats(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n, int64_t out[6])
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(out, "out");
+        std::vector<BasisPtr> d, c;
+        collect_bases(domain, rank, codomain, corank, d, c);
+        LayoutPtr L = ctx->impl.layout(d, c);
+        auto plan = ctx->impl.permute_plan(L, shift, std::vector<int>(p, p + n), false);
+        out[0] = plan->n_tasks;
+        out[1] = plan->n_tiles;
+        out[2] = plan->max_fan_in;
+        out[3] = plan->identity_copy ? 1 : 0;
+        out[4] = plan->n_btiles;   // > 0: the plan also has the cp.async.bulk form
+        out[5] = plan->bytes;
+    });
+}
+
 int xb_tensor_create_sectors(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, const int* q, int n_sectors,
                              xb_tensor** out)
 {

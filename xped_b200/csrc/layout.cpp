@@ -848,6 +848,7 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
     plan->n_tiles = static_cast<int>(h_tiles.size());
     // consecutive tiles (mostly of the same task) per CTA: amortises the task staging, keeps >= 16 CTAs per SM in the grid
     plan->tiles_per_cta = std::max(1, std::min(8, plan->n_tiles / (sm_count * 16)));
+    if(bulk_ok && !h_btiles.empty()) plan->n_btiles = static_cast<int>(h_btiles.size());   // also in planning-only contexts (host-logic tests)
     if(ctx.planning_only()) return;
     if(plan->n_tasks) {
         check_cuda(cudaMalloc(&plan->d_tasks, h_tasks.size() * sizeof(PermTask)), "cudaMalloc plan tasks");

@@ -317,3 +317,10 @@ class ShardedTensor:
                 full[self.offsets[i]:self.offsets[i] + n] = data[pos:pos + n]
                 pos += n
         return full
+
+
+def permute_plan_stats(ctx, domain, codomain, shift, p):
+    """host-side statistics of the cached permute plan (no GPU needed): dict with tasks, tiles, max_fan_in, identity, bulk_tiles, bytes"""
+    out = (C.c_int64 * 6)()
+    check(ctx.lib.xb_permute_plan_stats(ctx.h, _handles(domain), len(domain), _handles(codomain), len(codomain), int(shift), _ints(p), len(p), out))
+    return dict(tasks=out[0], tiles=out[1], max_fan_in=out[2], identity=bool(out[3]), bulk_tiles=out[4], bytes=out[5])

@@ -40,7 +40,9 @@ struct SvdBlock
     double tol;
 };
 
-struct SvdTask { int block, bi, bj, mode; };   // mode 0: all pairs of the 32-column panel (31 steps), 1: cross pairs only (16 steps)
+// mode 0: all pairs of the 32-column panel (31 steps), 1: cross pairs only (16 steps); gbi / gbj: indices of the two column blocks in
+// the modification-stamp table (gbj = -1: single block)
+struct SvdTask { int block, bi, bj, mode, gbi, gbj, pad0, pad1; };
 
 // per-block diagonal shift 1.5 * ||A_q||_F for teigh: A_q + c_q 1 is positive definite with condition number <= 5
 __global__ void block_shift_kernel(const double* __restrict__ A, const long long* __restrict__ a_off, const SvdBlock* __restrict__ blocks, int nblocks,
@@ -394,7 +396,8 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
 template <int CL, int VREG, bool DB>
 __global__ void __launch_bounds__(SVD_THREADS, (VREG <= 20 || !DB) ? 2 : 1)
 svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock* __restrict__ blocks, const SvdTask* __restrict__ tasks,
-                          int* __restrict__ rotated, unsigned long long* __restrict__ tprof, int rs)
+                          int* __restrict__ rotated, unsigned long long* __restrict__ tprof, int rs, int* __restrict__ mod, int* __restrict__ clean,
+                          const int* __restrict__ sweep, int round_idx, int n_rounds)
 {
     extern __shared__ __align__(16) double dsm[];
     constexpr bool SOLO = CL >= 8;
@@ -422,6 +425,13 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
     unsigned crank = 0;
     if(CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const SvdTask task = tasks[blockIdx.x / CL];
+    // skip pairs that were found orthogonal and whose column blocks have not been rotated since (uniform over the cluster; the
+    // tables are only written after the cluster barriers of a round, by the CTAs that own the pair)
+    const int t_now = *sweep * n_rounds + round_idx + 1;
+    {
+        const int last_mod = max(mod[task.gbi], task.gbj >= 0 ? mod[task.gbj] : 0);
+        if(clean[blockIdx.x / CL] > last_mod) return;
+    }
     const SvdBlock blk = blocks[task.block];
     if(tid < SP) {
         const int i = tid >> 1;
@@ -635,10 +645,15 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     }
     if(!any_rot) {   // panel already orthogonal (uniform over the cluster)
+        if(tid == 0 && crank == 0) clean[blockIdx.x / CL] = t_now;
         if(SOLO) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
         return;
     }
-    if(tid == 0 && crank == 0) atomicExch(rotated, 1);
+    if(tid == 0 && crank == 0) {
+        atomicExch(rotated, 1);
+        mod[task.gbi] = t_now;
+        if(task.gbj >= 0) mod[task.gbj] = t_now;
+    }
 
     // ---- phase 3: X <- X * Vl for the resident W slice, then for the V slice (registers -> shared). warp w: 8-row groups w, w+8, ...
     auto multiply_slice = [&](double* __restrict__ M, int nrows, int lo, int hi) {
@@ -730,13 +745,15 @@ __global__ void svd_gather_kernel(const double* __restrict__ W, const double* __
     }
 }
 
+__global__ void svd_sweep_bump_kernel(int* sweep) { *sweep += 1; }
+
 // Round-robin schedule over `nb` column blocks: rounds x pairs; a bye (odd nb / nb == 1) becomes a single-block task.
-void schedule(int block, int nb, std::vector<std::vector<SvdTask>>& rounds)
+void schedule(int block, int nb, int gbase, std::vector<std::vector<SvdTask>>& rounds)
 {
     if(nb <= 0) return;
     if(nb == 1) {
         if(rounds.empty()) rounds.resize(1);
-        rounds[0].push_back({block, 0, -1, 0});
+        rounds[0].push_back({block, 0, -1, 0, gbase, -1, 0, 0});
         return;
     }
     const int n = nb + (nb & 1);   // even number of players, player n-1 may be the dummy
@@ -754,9 +771,9 @@ void schedule(int block, int nb, std::vector<std::vector<SvdTask>>& rounds)
             if(a > b) std::swap(a, b);
             if(b >= nb) {
                 // bye: orthogonalise inside the lone block only in the first round (it meets every other block later)
-                if(r == 0) rounds[r].push_back({block, a, -1, 0});
+                if(r == 0) rounds[r].push_back({block, a, -1, 0, gbase + a, -1, 0, 0});
             } else {
-                rounds[r].push_back({block, a, b, r == 0 ? 0 : 1});
+                rounds[r].push_back({block, a, b, r == 0 ? 0 : 1, gbase + a, gbase + b, 0, 0});
             }
         }
     }
@@ -809,7 +826,12 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
 
     // schedule
     std::vector<std::vector<SvdTask>> rounds;
-    for(int i = 0; i < nb; ++i) schedule(i, (R.blocks[i].cols + SB - 1) / SB, rounds);
+    int n_colblocks = 0;
+    for(int i = 0; i < nb; ++i) {
+        const int cb = (R.blocks[i].cols + SB - 1) / SB;
+        schedule(i, cb, n_colblocks, rounds);
+        n_colblocks += cb;
+    }
     std::vector<SvdTask> flat;
     std::vector<int> round_begin;
     for(const auto& r : rounds) {
@@ -826,7 +848,11 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
     o_sigma = (o_sigma + 15) & ~size_t(15);
     const size_t o_shift = o_sigma + sizeof(double) * soff;
     const size_t o_flag = o_shift + sizeof(double) * nb;
-    const size_t meta_bytes = o_flag + 16;
+    // convergence bookkeeping: mod[column block] = time of its last rotation, clean[task] = time the pair was last found orthogonal,
+    // one sweep counter; time = sweep * rounds + round + 1.  A pair whose blocks did not change since it was found clean is skipped.
+    const size_t o_stamps = o_flag + 16;
+    const size_t n_stamps = static_cast<size_t>(n_colblocks) + flat.size() + 4;
+    const size_t meta_bytes = o_stamps + sizeof(int) * n_stamps;
     char* d_meta = nullptr;
     check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_meta), meta_bytes, s), "svd meta");
     std::vector<char> h_meta(o_sigma, 0);
@@ -841,6 +867,10 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
     auto* d_sigma = reinterpret_cast<double*>(d_meta + o_sigma);
     auto* d_flag = reinterpret_cast<int*>(d_meta + o_flag);
     auto* d_shift = reinterpret_cast<double*>(d_meta + o_shift);
+    int* d_mod = reinterpret_cast<int*>(d_meta + o_stamps);
+    int* d_clean = d_mod + n_colblocks;
+    int* d_sweep = d_clean + flat.size();
+    check_cuda(cudaMemsetAsync(d_mod, 0, sizeof(int) * n_stamps, s), "svd stamps reset");
 
     {
         if(shifted) {
@@ -968,7 +998,9 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         rs = std::max(rs, (per + 15) & ~15);
     }
     const size_t dyn_smem = sizeof(double) * (static_cast<size_t>(SP) * (rs + 4) + (cluster == 8 ? 2 : 4) * SP * SP + (cluster == 8 ? 2 : 1) * SP * VL_LD + 2);   // <8, 40, false>: single-buffered planes, Vl in a region of its own
-    auto launch_round = [&](const SvdTask* d_round_tasks, int cnt) {
+    const int n_rounds_total = static_cast<int>(round_begin.size()) - 1;
+    auto launch_round = [&](const SvdTask* d_round_tasks, int cnt, int round_idx) {
+        int* d_round_clean = d_clean + (d_round_tasks - d_tasks);
         cudaLaunchConfig_t cfg = {};
         cfg.blockDim = dim3(SVD_THREADS);
         cfg.stream = s;
@@ -989,11 +1021,14 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         cfg.dynamicSmemBytes = dyn_smem;
         attr[0].val.clusterDim.x = cluster;
         if(cluster == 1)
-            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<1, 20, true>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<1> launch");
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<1, 20, true>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs, d_mod, d_round_clean,
+                                          static_cast<const int*>(d_sweep), round_idx, n_rounds_total), "svd_round_resident_kernel<1> launch");
         else if(cluster == 2)
-            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<2, 40, true>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<2> launch");
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<2, 40, true>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs, d_mod, d_round_clean,
+                                          static_cast<const int*>(d_sweep), round_idx, n_rounds_total), "svd_round_resident_kernel<2> launch");
         else
-            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<8, 40, false>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs), "svd_round_resident_kernel<8> launch");
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<8, 40, false>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs, d_mod, d_round_clean,
+                                          static_cast<const int*>(d_sweep), round_idx, n_rounds_total), "svd_round_resident_kernel<8> launch");
     };
     {
         static bool configured = false;
@@ -1023,9 +1058,10 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             if(ok) {
                 try {
                     check_cuda(cudaMemsetAsync(d_flag, 0, sizeof(int), s), "svd flag reset");
+                    svd_sweep_bump_kernel<<<1, 1, 0, s>>>(d_sweep);
                     for(size_t r = 0; r + 1 < round_begin.size(); ++r) {
                         const int cnt = round_begin[r + 1] - round_begin[r];
-                        if(cnt > 0) launch_round(d_tasks + round_begin[r], cnt);
+                        if(cnt > 0) launch_round(d_tasks + round_begin[r], cnt, static_cast<int>(r));
                     }
                 } catch(...) {
                     ok = false;
@@ -1052,10 +1088,11 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             ctx.launches += sg->rounds;
         } else {
         check_cuda(cudaMemsetAsync(d_flag, 0, sizeof(int), s), "svd flag reset");
+        svd_sweep_bump_kernel<<<1, 1, 0, s>>>(d_sweep);
         for(size_t r = 0; r + 1 < round_begin.size(); ++r) {
             const int cnt = round_begin[r + 1] - round_begin[r];
             if(cnt == 0) continue;
-            launch_round(d_tasks + round_begin[r], cnt);
+            launch_round(d_tasks + round_begin[r], cnt, static_cast<int>(r));
             ++ctx.launches;
         }
         }

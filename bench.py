@@ -226,6 +226,26 @@ def kernel_sections(xb, device, torch):
     U, S, Vd = M.tSVD(144, 1e-10, False)
     out["tsvd_w3"] = {"op": "tSVD(144, 1e-10) of M = Q4*Q1 (blocks 36..2394, 10800 singular values)", "ms": ctx3.timer_stop()}
     del U, S, Vd, M, Q4, Q1
+    # ---- the north-star target workload: one CTMRG step at D=6, chi=144 (SU(2), 1x1 cell, FROM_A; chi saturates after two steps)
+    try:
+        a6, phys6 = ctx3.basis(aux3), ctx3.basis([(2, 1)])
+        A6 = ctx3.tensor([a6, a6], [a6, a6, phys6]).setRandom(0)
+        ctm6 = xb.CTM(A6, 144)
+        for _ in range(3):
+            ctm6.grow_all()
+        ctx3.sync()
+        ctx3.profile(True)
+        ctx3.profile_read()
+        ctx3.timer_start()
+        ctm6.grow_all()
+        ms6 = ctx3.timer_stop()
+        prof6 = ctx3.profile_read()
+        ctx3.profile(False)
+        out["ctm_d6_chi144"] = {"op": "grow_all() at D=6 (aux {1:3, 2:3}), chi=144, step 4 from FROM_A, entirely on the device", "ms_per_step": ms6,
+                                "per_step": {k: {"ms": v[0], "launch_groups": v[1]} for k, v in prof6.items()}}
+        del ctm6, A6
+    except Exception as e:
+        out["ctm_d6_chi144"] = {"error": f"{type(e).__name__}: {e}"}
     ctx3.close()
     return out, dgemm_peak
 

@@ -202,7 +202,7 @@ def test_tsvd_graded_spectrum_and_multiplets(ctxs):
         assert np.abs(gS.download() - oS.data).max() < 1e-13
 
 
-@pytest.mark.parametrize("case", ["U0_square", "U0_tall", "U0_very_tall", "U1_big", "SU2_graded"])
+@pytest.mark.parametrize("case", ["U0_square", "U0_tall", "U0_very_tall", "U0_tallest", "U1_big", "SU2_graded"])
 def test_tsvd_large_blocks(ctxs, case):
     """Blocks wide enough for the QR-preconditioned path (>= 32 columns), the 4- and 8-CTA cluster round kernels and
     tall panels; same checks as test_tsvd (sigma 1e-12, truncated reconstruction, orthonormality)."""
@@ -218,9 +218,13 @@ def test_tsvd_large_blocks(ctxs, case):
         _svd_checks(g.adjoint(), o.adjoint(), 20, 1e-10, False)                                 # 77 x 330 (transposed work matrix)
     elif case == "U0_very_tall":
         ctx, osym = ctxs("U0")
-        g, o = pair(ctx, osym, [[((), 650)], [((), 4)]], [[((), 40)]], 75)                      # 2600 x 40: beyond the resident round kernel
+        g, o = pair(ctx, osym, [[((), 650)], [((), 4)]], [[((), 40)]], 75)                      # 2600 x 40: the 16-CTA cluster round kernel
         _svd_checks(g, o, 1000, 0.0, False)
         _svd_checks(g, o, 12, 1e-10, False)
+    elif case == "U0_tallest":
+        ctx, osym = ctxs("U0")
+        g, o = pair(ctx, osym, [[((), 925)], [((), 4)]], [[((), 36)]], 76)                      # 3700 x 36: beyond the resident round kernels (chunked fallback)
+        _svd_checks(g, o, 1000, 0.0, False)
     elif case == "U1_big":
         ctx, osym = ctxs("U1")
         B = [((q,), 12) for q in range(-2, 3)]

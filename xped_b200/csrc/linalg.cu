@@ -515,30 +515,37 @@ svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const 
     double* __restrict__ Vl = SOLO ? G1 + SP * VL_LD : G1;   // SOLO: a region of its own (peers copy it while G1 may still be read)
     const bool solver = !SOLO || crank == 0;
     if(solver) {
-        // every thread sums 4 elements; all remote loads are issued before the first use (fixed order: bit-identical G in all CTAs)
-        double part[4][CL];
+        // every thread sums 4 elements; the remote loads are issued in batches of (up to) 8 ranks before their first use (fixed
+        // order: bit-identical G in all CTAs)
+        constexpr int BATCH = CL < 8 ? CL : 8;
+        double sum[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for(int i = 0; i < 4; ++i) {
-            const int e = tid + i * SVD_THREADS, r = e / SP, c = e % SP;
-            if(CL > 1) {
-                const unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(&G1[r * G_LD + c]));
+        for(int c0r = 0; c0r < CL; c0r += BATCH) {
+            double part[4][BATCH];
 #pragma unroll
-                for(int cr = 0; cr < CL; ++cr) {
-                    unsigned remote;
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(cr));
-                    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(part[i][cr]) : "r"(remote));
+            for(int i = 0; i < 4; ++i) {
+                const int e = tid + i * SVD_THREADS, r = e / SP, c = e % SP;
+                if(CL > 1) {
+                    const unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(&G1[r * G_LD + c]));
+#pragma unroll
+                    for(int cr = 0; cr < BATCH; ++cr) {
+                        unsigned remote;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(c0r + cr));
+                        asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(part[i][cr]) : "r"(remote));
+                    }
+                } else {
+                    part[i][0] = G1[r * G_LD + c];
                 }
-            } else {
-                part[i][0] = G1[r * G_LD + c];
             }
+#pragma unroll
+            for(int i = 0; i < 4; ++i)
+#pragma unroll
+                for(int cr = 0; cr < BATCH; ++cr) sum[i] += part[i][cr];
         }
 #pragma unroll
         for(int i = 0; i < 4; ++i) {
             const int e = tid + i * SVD_THREADS, r = e / SP, c = e % SP;
-            double sum = part[i][0];
-#pragma unroll
-            for(int cr = 1; cr < CL; ++cr) sum += part[i][cr];
-            Gp0[((r & 1) * 2 + (c & 1)) * (SP * SP / 4) + (r >> 1) * 16 + (c >> 1)] = sum;
+            Gp0[((r & 1) * 2 + (c & 1)) * (SP * SP / 4) + (r >> 1) * 16 + (c >> 1)] = sum[i];
             Vp0[((r >> 4) * 2 + (c & 1)) * (SP * SP / 4) + (r & 15) * 16 + (c >> 1)] = (r == c) ? 1.0 : 0.0;
         }
     }
@@ -889,6 +896,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         static const bool no_precond = std::getenv("XB_SVD_NOPRECOND") != nullptr;
         int pre_max_rows = 0;
         std::vector<QrPreBlock> pre;
+        std::vector<int> pre_index;   // sector block of every entry of `pre`
         long long boff = 0, yoff = 0, poff = 0, qoff = 0;
         for(const SvdBlock& b : R.blocks) {
             if(b.cols < 2 * SB) continue;
@@ -908,6 +916,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             yoff += static_cast<long long>(b.cols) * 16;
             pre_max_rows = std::max(pre_max_rows, b.cols);
             pre.push_back(q);
+            pre_index.push_back(static_cast<int>(&b - R.blocks.data()));
         }
         if(!shifted && !no_precond && !pre.empty() && svd_precondition_supported(pre_max_rows)) {
             static const bool pre_prof = std::getenv("XB_SVD_PROF") != nullptr;
@@ -975,6 +984,49 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
                 ctx.event_pool.push_back(e0);
                 ctx.event_pool.push_back(e1);
             }
+            // second step (square blocks): one more QR for one to three sweeps fewer
+            {
+                static const int qr2_env = std::getenv("XB_SVD_QR2") ? std::atoi(std::getenv("XB_SVD_QR2")) : -1;
+                std::vector<QrPreBlock> pre2;
+                std::vector<int> pre2_index;
+                long long roff = 0;
+                for(size_t k = 0; k < pre.size(); ++k) {
+                    if(pre[k].m != pre[k].n) continue;
+                    QrPreBlock q = pre[k];
+                    q.q_off = roff;
+                    roff += static_cast<long long>(q.n) * q.n;
+                    pre2.push_back(q);
+                    pre2_index.push_back(pre_index[k]);
+                }
+                const bool want2 = qr2_env > 0;   // opt-in (XB_SVD_QR2=1): measured neutral (D=6: 13 instead of 14 sweeps for one more QR; D=4: 51.9 vs 49.3 ms per step)
+                if(want2 && !pre2.empty()) {
+                    double* d_rtmp = nullptr;
+                    QrPreBlock* d_pre2 = nullptr;
+                    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_rtmp), sizeof(double) * roff, s), "svd precondition R2");
+                    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_pre2), sizeof(QrPreBlock) * pre2.size(), s), "svd precondition meta 2");
+                    ctx.upload_async(d_pre2, pre2.data(), sizeof(QrPreBlock) * pre2.size());
+                    launch_svd_precondition2_factor(R.d_W, d_aug, d_aug + boff, d_aug + boff + yoff, d_rtmp, d_pre2, pre2, s, &ctx.launches);
+                    std::vector<GemmItem> items;   // W' = V0 * R2^T
+                    for(const QrPreBlock& q : pre2) {
+                        GemmItem g;
+                        std::memset(&g, 0, sizeof(g));
+                        g.a_off = q.v_off;
+                        g.b_off = q.q_off;
+                        g.c_off = q.w_off;
+                        g.m = g.n = g.k = q.n;
+                        g.lda = g.ldb = g.ldc = q.n;
+                        g.ta = 0;
+                        g.tb = 1;
+                        g.alpha = 1.0;
+                        items.push_back(g);
+                    }
+                    ctx.run_gemm(R.d_V, d_rtmp, R.d_W, items);
+                    launch_svd_precondition2_q(d_aug, R.d_V, d_pre2, pre2, s, &ctx.launches);
+                    for(int i : pre2_index) R.transposed[i] = !R.transposed[i];   // W now carries the other side's vectors
+                    check_cuda(cudaFreeAsync(d_rtmp, s), "svd precondition free");
+                    check_cuda(cudaFreeAsync(d_pre2, s), "svd precondition free");
+                }
+            }
             check_cuda(cudaFreeAsync(d_aug, s), "svd precondition free");
             check_cuda(cudaFreeAsync(d_pre, s), "svd precondition free");
         }
@@ -989,15 +1041,18 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
     int max_rows = 0;
     for(const SvdBlock& b : R.blocks) max_rows = std::max(max_rows, b.rows);
     // resident kernel: cluster of CL CTAs per panel pair, each keeps its row slice (<= rs rows) of the panel in shared memory
-    // up to 640 rows two CTAs per pair (one CTA per SM, nothing shares its FP64 pipe) beat four at two per SM: 55.5 vs 57.8 ms per CTM step
-    const int cluster = max_rows <= 160 ? 1 : (max_rows <= 640 ? 2 : 8);
-    const bool resident = max_rows <= 2560;
+    // up to 640 rows two CTAs per pair (one CTA per SM, nothing shares its FP64 pipe) beat four at two per SM: 55.5 vs 57.8 ms per CTM step;
+    // 8 CTAs (304-row slices, two CTAs per SM) up to 2432 rows; a 16-CTA cluster (non-portable size, 224-row slices) up to 3584 rows
+    // (the D=6, chi=144 CTM blocks have ~3100); beyond that the chunked kernel
+    static const bool cl16 = std::getenv("XB_SVD_CL16") != nullptr && std::atoi(std::getenv("XB_SVD_CL16")) != 0;   // opt-in until verified on the GPU
+    const int cluster = max_rows <= 160 ? 1 : (max_rows <= 640 ? 2 : ((max_rows <= 2432 || !cl16) ? 8 : 16));
+    const bool resident = max_rows <= (cl16 ? 3584 : 2432);
     int rs = 16;
     for(const SvdBlock& b : R.blocks) {
         const int per = (((b.rows + cluster - 1) / cluster) + 7) & ~7;   // cols <= rows, so the V slice is never longer
         rs = std::max(rs, (per + 15) & ~15);
     }
-    const size_t dyn_smem = sizeof(double) * (static_cast<size_t>(SP) * (rs + 4) + (cluster == 8 ? 2 : 4) * SP * SP + (cluster == 8 ? 2 : 1) * SP * VL_LD + 2);   // <8, 40, false>: single-buffered planes, Vl in a region of its own
+    const size_t dyn_smem = sizeof(double) * (static_cast<size_t>(SP) * (rs + 4) + (cluster >= 8 ? 2 : 4) * SP * SP + (cluster >= 8 ? 2 : 1) * SP * VL_LD + 2);   // <8, 40, false>: single-buffered planes, Vl in a region of its own
     const int n_rounds_total = static_cast<int>(round_begin.size()) - 1;
     auto launch_round = [&](const SvdTask* d_round_tasks, int cnt, int round_idx) {
         int* d_round_clean = d_clean + (d_round_tasks - d_tasks);
@@ -1026,6 +1081,9 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         else if(cluster == 2)
             check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<2, 40, true>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs, d_mod, d_round_clean,
                                           static_cast<const int*>(d_sweep), round_idx, n_rounds_total), "svd_round_resident_kernel<2> launch");
+        else if(cluster == 16)
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<16, 28, false>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs, d_mod, d_round_clean,
+                                          static_cast<const int*>(d_sweep), round_idx, n_rounds_total), "svd_round_resident_kernel<16> launch");
         else
             check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<8, 40, false>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs, d_mod, d_round_clean,
                                           static_cast<const int*>(d_sweep), round_idx, n_rounds_total), "svd_round_resident_kernel<8> launch");
@@ -1037,6 +1095,8 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<1, 20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<2, 40, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<8, 40, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
+            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<16, 28, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
+            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<16, 28, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "svd cluster attr");
             configured = true;
         }
     }

@@ -483,28 +483,10 @@ qr_update_kernel(double* __restrict__ Baug, const double* __restrict__ Ybuf, con
 
 }   // namespace
 
-bool svd_precondition_supported(int max_rows) { return max_rows <= RPT * QR_THREADS * 4; }
-
-void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, double* Tbuf, double* nrm, int* perm, const QrPreBlock* d_blocks,
-                             const std::vector<QrPreBlock>& h_blocks, cudaStream_t s, int64_t* launches)
+namespace {
+// Householder panels + trailing updates over [B | 1] of all blocks (shared by both preconditioning stages)
+void run_panels(double* Baug, double* Ybuf, double* Tbuf, const QrPreBlock* d_blocks, int nb, int n_max, int mn_max, cudaStream_t s, int64_t* launches)
 {
-    const int nb = static_cast<int>(h_blocks.size());
-    if(nb == 0) return;
-    int n_max = 0, mn_max = 0;
-    for(const QrPreBlock& b : h_blocks) {
-        n_max = std::max(n_max, b.n);
-        mn_max = std::max(mn_max, b.m + b.n);
-    }
-    const dim3 tgrid(static_cast<unsigned>((mn_max + 31) / 32), static_cast<unsigned>((n_max + 31) / 32), static_cast<unsigned>(nb)), tblock(32, 8);
-    int m_max = 0;
-    for(const QrPreBlock& b : h_blocks) m_max = std::max(m_max, b.m);
-    const dim3 ngrid(static_cast<unsigned>((m_max + 127) / 128), static_cast<unsigned>((n_max + NORM_CHUNK - 1) / NORM_CHUNK), static_cast<unsigned>(nb));
-    const dim3 rgrid(static_cast<unsigned>((m_max + 127) / 128), static_cast<unsigned>(nb));
-    qr_row_norms_kernel<<<ngrid, 128, 0, s>>>(W, nrm, d_blocks);
-    qr_rank_rows_kernel<<<rgrid, 128, sizeof(double) * m_max, s>>>(nrm, perm, d_blocks);
-    qr_pack_kernel<<<tgrid, tblock, 0, s>>>(W, Baug, perm, d_blocks);
-    check_cuda(cudaGetLastError(), "qr_pack_kernel launch");
-    *launches += 3;
     const int cluster = n_max <= RPT * QR_THREADS ? 1 : 4;
     unsigned long long* d_tprof = nullptr;
     static const bool qr_prof = std::getenv("XB_SVD_PROF") != nullptr;
@@ -546,8 +528,110 @@ void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, d
         std::fprintf(stderr, "[qr prof] panels %llu | CTA0 cycles/panel: load %.0f reduce(16 steps) %.0f update(16 steps) %.0f gram %.0f T %.0f\n", hp[7], hp[0] / np,
                      hp[1] / np, hp[2] / np, hp[3] / np, hp[4] / np);
     }
+}
+
+// ---- stage 2 (square blocks): [W0 | 1] -> [R2 | Q2^T] with W0 = Q2 R2 -------------------------------------------------------
+__global__ void qr2_pack_kernel(const double* __restrict__ W, double* __restrict__ Baug, const QrPreBlock* __restrict__ blocks)
+{
+    const QrPreBlock d = blocks[blockIdx.y];
+    const long long cnt = 2ll * d.n * d.n, stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for(long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < cnt; e += stride) {
+        const int r = static_cast<int>(e % d.n), c = static_cast<int>(e / d.n);
+        Baug[d.b_off + e] = c < d.n ? W[d.w_off + e] : (r == c - d.n ? 1.0 : 0.0);
+    }
+}
+
+__global__ void qr2_unpack_r_kernel(const double* __restrict__ Baug, double* __restrict__ Rtmp, const QrPreBlock* __restrict__ blocks)
+{
+    const QrPreBlock d = blocks[blockIdx.y];
+    const long long cnt = static_cast<long long>(d.n) * d.n, stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for(long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < cnt; e += stride) {
+        const int r = static_cast<int>(e % d.n), c = static_cast<int>(e / d.n);
+        Rtmp[d.q_off + e] = r <= c ? Baug[d.b_off + e] : 0.0;   // below the diagonal Baug holds stale data
+    }
+}
+
+// V = (Q2^T)^T: 32 x 32 tiles; grid = (ceil(n_max / 32), ceil(n_max / 32), nblocks), block = (32, 8)
+__global__ void qr2_unpack_q_kernel(const double* __restrict__ Baug, double* __restrict__ V, const QrPreBlock* __restrict__ blocks)
+{
+    __shared__ double tile[32][33];
+    const QrPreBlock d = blocks[blockIdx.z];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    if(r0 >= d.n || c0 >= d.n) return;
+    for(int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + threadIdx.x, r = r0 + j;   // P[c][r] = Baug[c + (n + r) n]
+        tile[j][threadIdx.x] = (r < d.n && c < d.n) ? Baug[d.b_off + c + static_cast<long long>(d.n + r) * d.n] : 0.0;
+    }
+    __syncthreads();
+    for(int j = threadIdx.y; j < 32; j += 8) {
+        const int r = r0 + threadIdx.x, c = c0 + j;
+        if(r < d.n && c < d.n) V[d.v_off + r + static_cast<long long>(c) * d.n] = tile[threadIdx.x][j];
+    }
+}
+}   // namespace
+
+bool svd_precondition_supported(int max_rows) { return max_rows <= RPT * QR_THREADS * 4; }
+
+void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, double* Tbuf, double* nrm, int* perm, const QrPreBlock* d_blocks,
+                             const std::vector<QrPreBlock>& h_blocks, cudaStream_t s, int64_t* launches)
+{
+    const int nb = static_cast<int>(h_blocks.size());
+    if(nb == 0) return;
+    int n_max = 0, mn_max = 0;
+    for(const QrPreBlock& b : h_blocks) {
+        n_max = std::max(n_max, b.n);
+        mn_max = std::max(mn_max, b.m + b.n);
+    }
+    const dim3 tgrid(static_cast<unsigned>((mn_max + 31) / 32), static_cast<unsigned>((n_max + 31) / 32), static_cast<unsigned>(nb)), tblock(32, 8);
+    int m_max = 0;
+    for(const QrPreBlock& b : h_blocks) m_max = std::max(m_max, b.m);
+    const dim3 ngrid(static_cast<unsigned>((m_max + 127) / 128), static_cast<unsigned>((n_max + NORM_CHUNK - 1) / NORM_CHUNK), static_cast<unsigned>(nb));
+    const dim3 rgrid(static_cast<unsigned>((m_max + 127) / 128), static_cast<unsigned>(nb));
+    qr_row_norms_kernel<<<ngrid, 128, 0, s>>>(W, nrm, d_blocks);
+    qr_rank_rows_kernel<<<rgrid, 128, sizeof(double) * m_max, s>>>(nrm, perm, d_blocks);
+    qr_pack_kernel<<<tgrid, tblock, 0, s>>>(W, Baug, perm, d_blocks);
+    check_cuda(cudaGetLastError(), "qr_pack_kernel launch");
+    *launches += 3;
+    run_panels(Baug, Ybuf, Tbuf, d_blocks, nb, n_max, mn_max, s, launches);
     qr_unpack_kernel<<<tgrid, tblock, 0, s>>>(Baug, W, V, perm, d_blocks);
     check_cuda(cudaGetLastError(), "qr_unpack_kernel launch");
+    ++*launches;
+}
+
+}   // namespace xb
+
+namespace xb {
+
+// Second preconditioning step for SQUARE blocks (Drmac-Veselic: a QR factorisation of the first triangular factor): with the state
+// (W0, V0) of the first step and W0 = Q2 R2, the TRANSPOSED problem A^T = V S U^T starts from  W' = A^T Q2 = V0 R2^T,  U' = Q2
+// (Gram(W') = R2 R2^T is closer to diagonal than Gram(W0) = R2^T R2: three to four sweeps fewer).  This routine factorises
+// [W0 | 1] and leaves R2 (upper triangular) in Rtmp (offsets q_off); the caller forms W' = V0 R2^T with the grouped GEMM and then
+// calls launch_svd_precondition2_q, which overwrites V0 by Q2.  The roles of W and V (left / right vectors) are swapped afterwards.
+void launch_svd_precondition2_factor(const double* W, double* Baug, double* Ybuf, double* Tbuf, double* Rtmp, const QrPreBlock* d_blocks,
+                                     const std::vector<QrPreBlock>& h_blocks, cudaStream_t s, int64_t* launches)
+{
+    const int nb = static_cast<int>(h_blocks.size());
+    if(nb == 0) return;
+    int n_max = 0;
+    for(const QrPreBlock& b : h_blocks) n_max = std::max(n_max, b.n);
+    qr2_pack_kernel<<<dim3(296, static_cast<unsigned>(nb)), 256, 0, s>>>(W, Baug, d_blocks);
+    check_cuda(cudaGetLastError(), "qr2_pack_kernel launch");
+    ++*launches;
+    run_panels(Baug, Ybuf, Tbuf, d_blocks, nb, n_max, 2 * n_max, s, launches);
+    qr2_unpack_r_kernel<<<dim3(296, static_cast<unsigned>(nb)), 256, 0, s>>>(Baug, Rtmp, d_blocks);
+    check_cuda(cudaGetLastError(), "qr2_unpack_r_kernel launch");
+    ++*launches;
+}
+
+void launch_svd_precondition2_q(const double* Baug, double* V, const QrPreBlock* d_blocks, const std::vector<QrPreBlock>& h_blocks, cudaStream_t s, int64_t* launches)
+{
+    const int nb = static_cast<int>(h_blocks.size());
+    if(nb == 0) return;
+    int n_max = 0;
+    for(const QrPreBlock& b : h_blocks) n_max = std::max(n_max, b.n);
+    const dim3 grid(static_cast<unsigned>((n_max + 31) / 32), static_cast<unsigned>((n_max + 31) / 32), static_cast<unsigned>(nb));
+    qr2_unpack_q_kernel<<<grid, dim3(32, 8), 0, s>>>(Baug, V, d_blocks);
+    check_cuda(cudaGetLastError(), "qr2_unpack_q_kernel launch");
     ++*launches;
 }
 

@@ -21,4 +21,10 @@ bool svd_precondition_supported(int max_rows);
 void launch_svd_precondition(double* W, double* V, double* Baug, double* Ybuf, double* Tbuf, double* nrm, int* perm, const QrPreBlock* d_blocks,
                              const std::vector<QrPreBlock>& h_blocks, cudaStream_t s, int64_t* launches);
 
+// second step for square blocks (see precond.cu): factorise [W0 | 1], R2 -> Rtmp (offsets q_off); after the caller's GEMM W' = V0 R2^T,
+// launch_svd_precondition2_q overwrites V by Q2
+void launch_svd_precondition2_factor(const double* W, double* Baug, double* Ybuf, double* Tbuf, double* Rtmp, const QrPreBlock* d_blocks,
+                                     const std::vector<QrPreBlock>& h_blocks, cudaStream_t s, int64_t* launches);
+void launch_svd_precondition2_q(const double* Baug, double* V, const QrPreBlock* d_blocks, const std::vector<QrPreBlock>& h_blocks, cudaStream_t s, int64_t* launches);
+
 }   // namespace xb

@@ -141,7 +141,7 @@ __device__ __forceinline__ int seat_next(int x)
 template <int CL>
 __global__ void __launch_bounds__(SVD_THREADS)
 svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock* __restrict__ blocks, const SvdTask* __restrict__ tasks, int* __restrict__ rotated,
-                 unsigned long long* __restrict__ tprof)
+                 unsigned long long* __restrict__ tprof, int* __restrict__ mod, int* __restrict__ clean, const int* __restrict__ sweep, int round_idx, int n_rounds)
 {
     // optional phase timing (XB_SVD_PROF=1): thread 0 of CTA 0 accumulates clock64() deltas per phase
     const bool prof = tprof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
@@ -162,9 +162,16 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
     unsigned crank = 0;
     if(CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const SvdTask task = tasks[blockIdx.x / CL];
+    // skip pairs found orthogonal whose column blocks were not rotated since (see the resident kernel)
+    const int t_now = *sweep * n_rounds + round_idx + 1;
+    {
+        const int last_mod = max(mod[task.gbi], task.gbj >= 0 ? mod[task.gbj] : 0);
+        if(clean[blockIdx.x / CL] > last_mod) return;
+    }
     const SvdBlock blk = blocks[task.block];
-    if(tid < SP) {
-        int c = tid < SB ? task.bi * SB + tid : (task.bj >= 0 ? task.bj * SB + (tid - SB) : -1);
+    if(tid < SP) {   // interleaved seats: even = block bi, odd = block bj (cross mode rotates only pairs between the two blocks)
+        const int i = tid >> 1;
+        int c = (tid & 1) ? (task.bj >= 0 ? task.bj * SB + i : -1) : task.bi * SB + i;
         if(c >= blk.cols) c = -1;
         colidx[tid] = c;
     }
@@ -268,7 +275,9 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
         const int k = tid >> 4, l = tid & 15;
         const double tol2 = blk.tol * blk.tol;
         const int r0 = 2 * k, r1 = 2 * k + 1, c0 = 2 * l, c1 = 2 * l + 1;
-        const int nr0 = seat_next(r0), nr1 = seat_next(r1), nc0 = seat_next(c0), nc1 = seat_next(c1);
+        const bool cross = task.mode != 0;
+        auto nxt = [&](int x) { return cross ? ((x & 1) ? ((x + 2) & (SP - 1)) : x) : seat_next(x); };
+        const int nr0 = nxt(r0), nr1 = nxt(r1), nc0 = nxt(c0), nc1 = nxt(c1);
         // loop-invariant offsets
         const int g00 = r0 * G_LD + c0, g01 = r0 * G_LD + c1, g10 = r1 * G_LD + c0, g11 = r1 * G_LD + c1;
         const int h00 = nr0 * G_LD + nc0, h01 = nr0 * G_LD + nc1, h10 = nr1 * G_LD + nc0, h11 = nr1 * G_LD + nc1;
@@ -306,18 +315,29 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
             __syncthreads();
         };
         // double buffering: even steps Gs[0] -> Gs[1], Vl1 -> Vls; odd steps back
+        const int nsteps = cross ? SB : SP - 1;
 #pragma unroll 1
-        for(int step = 0; step < (SP - 2) / 2; ++step) {
+        for(int step = 0; step + 1 < nsteps; step += 2) {
             jacobi_step(Gs[0], Gs[1], Vl1, Vls);
             jacobi_step(Gs[1], Gs[0], Vls, Vl1);
         }
-        jacobi_step(Gs[0], Gs[1], Vl1, Vls);
-        // 31 swaps: the rotation matrix now sits in Vls, everybody back in the original seat
+        if(nsteps & 1) jacobi_step(Gs[0], Gs[1], Vl1, Vls);
         any = __syncthreads_or(any);
         lap(2);   // inner Jacobi sweep
-        if(!any) return;   // panel already orthogonal (uniform over the cluster: identical G everywhere)
+        if(!any) {   // panel already orthogonal (uniform over the cluster: identical G everywhere)
+            if(tid == 0 && crank == 0) clean[blockIdx.x / CL] = t_now;
+            return;
+        }
+        if(!(nsteps & 1)) {   // an even number of steps leaves the rotation matrix in Vl1 (= the chunk staging area): move it to Vls
+            for(int e = tid; e < SP * SP; e += SVD_THREADS) Vls[(e / SP) * VL_LD + (e % SP)] = Vl1[(e / SP) * VL_LD + (e % SP)];
+            __syncthreads();
+        }
     }
-    if(tid == 0 && crank == 0) atomicExch(rotated, 1);
+    if(tid == 0 && crank == 0) {
+        atomicExch(rotated, 1);
+        mod[task.gbi] = t_now;
+        if(task.gbj >= 0) mod[task.gbj] = t_now;
+    }
 
     // ---- phase 3: X <- X * Vl for this CTA's rows of W and of V. warp w owns 8 rows of the 64-row chunk, all 32 columns.
     {
@@ -1069,7 +1089,9 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         if(!resident) {
             cfg.gridDim = dim3(static_cast<unsigned>(cnt) * 4);
             attr[0].val.clusterDim.x = 4;
-            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_kernel<4>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof), "svd_round_kernel<4> launch");
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_kernel<4>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, d_mod, d_round_clean, static_cast<const int*>(d_sweep),
+                                          round_idx, n_rounds_total),
+                       "svd_round_kernel<4> launch");
             return;
         }
         cfg.gridDim = dim3(static_cast<unsigned>(cnt) * cluster);

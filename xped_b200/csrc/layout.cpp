@@ -162,8 +162,17 @@ void Context::upload_async(void* dst, const void* src, size_t bytes)
             check_cuda(cudaEventRecord(c.fence, stream), "staging fence");
             c.pending = true;
         }
-        size_t next = staging_.empty() ? 0 : stage_cur_ + 1;
-        if(next >= staging_.size() && (staging_.size() < MAX_CHUNKS || need > CHUNK)) {
+        // next chunk in ring order that is large enough; grow the ring if there is none (a request larger than every chunk must never
+        // be squeezed into one) or, while the ring is small, if that chunk is still in flight
+        size_t next = SIZE_MAX;
+        for(size_t tries = 1; tries <= staging_.size(); ++tries) {
+            const size_t cand = (stage_cur_ + tries) % staging_.size();
+            if(staging_[cand].cap >= need) {
+                next = cand;
+                break;
+            }
+        }
+        if(next == SIZE_MAX || (staging_.size() < MAX_CHUNKS && staging_[next].pending)) {
             StageChunk c;
             c.cap = std::max(CHUNK, need);
             check_cuda(cudaMallocHost(reinterpret_cast<void**>(&c.p), c.cap), "cudaMallocHost staging");
@@ -171,8 +180,6 @@ void Context::upload_async(void* dst, const void* src, size_t bytes)
             staging_.push_back(c);
             next = staging_.size() - 1;
         } else {
-            if(next >= staging_.size()) next = 0;
-            for(size_t tries = 0; tries < staging_.size() && staging_[next].cap < need; ++tries) next = (next + 1) % staging_.size();
             StageChunk& c = staging_[next];
             if(c.pending) {
                 check_cuda(cudaEventSynchronize(c.fence), "staging wait");
@@ -183,6 +190,7 @@ void Context::upload_async(void* dst, const void* src, size_t bytes)
         stage_cur_ = next;
     }
     StageChunk& c = staging_[stage_cur_];
+    if(c.cap - c.used < need) throw std::logic_error("upload_async: staging chunk too small");
     std::memcpy(c.p + c.used, src, bytes);
     check_cuda(cudaMemcpyAsync(dst, c.p + c.used, bytes, cudaMemcpyHostToDevice, stream), "upload_async");
     c.used += need;

@@ -301,8 +301,13 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- xped_b200 has no CPU fallback (use --impl reference for the CPU oracle arm)")
     torch.cuda.set_device(local)
+    real_stdout = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its version banner otherwise)
+        # keep stdout to the ONE JSON line: NCCL prints its version banner to the C-level stdout when the first communicator is
+        # created, so file descriptor 1 points to stderr for the rest of the run and the line goes to a duplicate of the real stdout
+        sys.stdout.flush()
+        real_stdout = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -482,7 +487,7 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": cpu_sps, "unit": "steps/s", "cores": blas_threads(), "kind": "port",
                                     "sample": f"{args.cpu_steps} grow_all() steps of the same D=4 chi=64 workload after 3 warm-up steps, oracle/xped_oracle "
                                               "(numpy restatement of the reference algorithm)", "ms_per_step": cpu_ms}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout or sys.stdout, flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

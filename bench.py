@@ -137,6 +137,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use all the host threads it can (set before numpy loads its BLAS)
+    if "TORCHELASTIC_RUN_ID" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = str(os.cpu_count() or 1)
     sps, ms = time_oracle(args.warmup, args.steps)
     cores = blas_threads()
     line = {"impl": "reference", "metric": "ctmrg_steps_per_s", "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,

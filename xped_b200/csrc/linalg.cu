@@ -414,7 +414,7 @@ svd_round_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock*
 // SOLO (the 8-CTA variant): only rank 0 of the cluster reduces the Gram matrix and runs the Jacobi sweep; the peers sleep in the
 // cluster barrier (their SM is shared with a CTA of another pair) and then copy the 32 x 32 rotation matrix through DSMEM.
 template <int CL, int VREG, bool DB>
-__global__ void __launch_bounds__(SVD_THREADS, (VREG <= 20 || !DB) ? 2 : 1)
+__global__ void __launch_bounds__(SVD_THREADS, (VREG <= 20 || (!DB && VREG <= 40)) ? 2 : 1)
 svd_round_resident_kernel(double* __restrict__ W, double* __restrict__ V, const SvdBlock* __restrict__ blocks, const SvdTask* __restrict__ tasks,
                           int* __restrict__ rotated, unsigned long long* __restrict__ tprof, int rs, int* __restrict__ mod, int* __restrict__ clean,
                           const int* __restrict__ sweep, int round_idx, int n_rounds)
@@ -1064,9 +1064,14 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
     // up to 640 rows two CTAs per pair (one CTA per SM, nothing shares its FP64 pipe) beat four at two per SM: 55.5 vs 57.8 ms per CTM step;
     // 8 CTAs (304-row slices, two CTAs per SM) up to 2432 rows; a 16-CTA cluster (non-portable size, 224-row slices) up to 3584 rows
     // (the D=6, chi=144 CTM blocks have ~3100); beyond that the chunked kernel
-    static const bool cl16 = std::getenv("XB_SVD_CL16") != nullptr && std::atoi(std::getenv("XB_SVD_CL16")) != 0;   // opt-in until verified on the GPU
+    // 8 CTAs per pair beyond 640 rows: 304-row slices (two CTAs per SM) up to 2432 rows; the chunked kernel beyond (the D=6, chi=144 CTM
+    // blocks have ~3100 rows).  Measured on those blocks: chunked 0.57 s per tSVD, 416-row resident slices at one CTA per SM
+    // (XB_SVD_WIDE=1) 0.91 s, a 16-CTA cluster (XB_SVD_CL16=1) 1.18 s -- both stay opt-in.
+    static const bool cl16 = std::getenv("XB_SVD_CL16") != nullptr && std::atoi(std::getenv("XB_SVD_CL16")) != 0;
+    static const bool no_wide = !(std::getenv("XB_SVD_WIDE") != nullptr && std::atoi(std::getenv("XB_SVD_WIDE")) != 0);
+    const bool wide = !cl16 && !no_wide && max_rows > 2432 && max_rows <= 3328;
     const int cluster = max_rows <= 160 ? 1 : (max_rows <= 640 ? 2 : ((max_rows <= 2432 || !cl16) ? 8 : 16));
-    const bool resident = max_rows <= (cl16 ? 3584 : 2432);
+    const bool resident = max_rows <= (cl16 ? 3584 : (no_wide ? 2432 : 3328));
     int rs = 16;
     for(const SvdBlock& b : R.blocks) {
         const int per = (((b.rows + cluster - 1) / cluster) + 7) & ~7;   // cols <= rows, so the V slice is never longer
@@ -1106,6 +1111,9 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         else if(cluster == 16)
             check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<16, 28, false>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs, d_mod, d_round_clean,
                                           static_cast<const int*>(d_sweep), round_idx, n_rounds_total), "svd_round_resident_kernel<16> launch");
+        else if(wide)
+            check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<8, 52, false>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs, d_mod, d_round_clean,
+                                          static_cast<const int*>(d_sweep), round_idx, n_rounds_total), "svd_round_resident_kernel<8, 52> launch");
         else
             check_cuda(cudaLaunchKernelEx(&cfg, svd_round_resident_kernel<8, 40, false>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, rs, d_mod, d_round_clean,
                                           static_cast<const int*>(d_sweep), round_idx, n_rounds_total), "svd_round_resident_kernel<8> launch");
@@ -1117,6 +1125,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<1, 20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<2, 40, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<8, 40, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
+            check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<8, 52, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<16, 28, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<16, 28, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "svd cluster attr");
             configured = true;

@@ -1092,6 +1092,20 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         cfg.numAttrs = 1;
         const SvdBlock* cb = d_blocks;
         if(!resident) {
+            static const int chunked_cl = std::getenv("XB_SVD_CHUNKED_CL") ? std::atoi(std::getenv("XB_SVD_CHUNKED_CL")) : 4;   // experiment knob
+            if(chunked_cl == 8 || chunked_cl == 2) {
+                cfg.gridDim = dim3(static_cast<unsigned>(cnt) * chunked_cl);
+                attr[0].val.clusterDim.x = chunked_cl;
+                if(chunked_cl == 8)
+                    check_cuda(cudaLaunchKernelEx(&cfg, svd_round_kernel<8>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, d_mod, d_round_clean,
+                                                  static_cast<const int*>(d_sweep), round_idx, n_rounds_total),
+                               "svd_round_kernel<8> launch");
+                else
+                    check_cuda(cudaLaunchKernelEx(&cfg, svd_round_kernel<2>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, d_mod, d_round_clean,
+                                                  static_cast<const int*>(d_sweep), round_idx, n_rounds_total),
+                               "svd_round_kernel<2> launch");
+                return;
+            }
             cfg.gridDim = dim3(static_cast<unsigned>(cnt) * 4);
             attr[0].val.clusterDim.x = 4;
             check_cuda(cudaLaunchKernelEx(&cfg, svd_round_kernel<4>, R.d_W, R.d_V, cb, d_round_tasks, d_flag, d_tprof, d_mod, d_round_clean, static_cast<const int*>(d_sweep),

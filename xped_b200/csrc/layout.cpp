@@ -1143,6 +1143,9 @@ std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shif
         plan->bytes = 8 * (in->size + ts.out->size);
         lower_tasks(*this, ts.tasks, ts.leg_of, ts.N, *plan);
     }
+    // bound the cache: a CTM run whose chi bases still change from step to step creates ~200 new plans (a few MB of device tables each)
+    // per step; plans in use stay alive through their shared_ptr
+    if(plan_cache_.size() >= 4096) plan_cache_.clear();
     plan_cache_.emplace(key, plan);
     return plan;
 }

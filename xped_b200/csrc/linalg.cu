@@ -1154,6 +1154,11 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
     for(size_t r = 0; r + 1 < round_begin.size(); ++r) rounds_per_sweep += round_begin[r + 1] > round_begin[r] ? 1 : 0;
     if(!no_graph && !svd_prof && rounds_per_sweep >= 8) {
         const std::string key = L.sig + (shifted ? "#eigh" : "#svd");
+        if(ctx.sweep_graphs.size() >= 256 && ctx.sweep_graphs.find(key) == ctx.sweep_graphs.end()) {   // bound the cache (layouts that keep changing)
+            for(auto& kv : ctx.sweep_graphs)
+                if(kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+            ctx.sweep_graphs.clear();
+        }
         Context::SweepGraph& g = ctx.sweep_graphs[key];
         if(g.exec == nullptr || g.w != R.d_W || g.v != R.d_V || g.meta != d_meta) {
             if(g.exec) cudaGraphExecDestroy(g.exec);

@@ -216,3 +216,29 @@ def test_exchange_over_gloo_world2(name):
         p.join(180)
         assert p.exitcode == 0
     assert out.get(timeout=10) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["SU2", "fU1xSU2"])
+def test_recoupling_cache_across_multiplicities(name):
+    """Plans for layouts that differ only in the sector multiplicities share the label-keyed recoupling cache of the context
+    (Context::recoupling_cache): the second and third tensor are planned from cache hits and must still match the oracle."""
+    spec, dom_e, cod_e = CASES[name]
+    ctx = PlanningContext(spec)
+    osym = xo.Symmetry.from_spec(spec)
+    for bump, seed in ((0, 21), (1, 22), (3, 23)):
+        de = [[(q, d + bump * (1 + (k + i) % 2)) for k, (q, d) in enumerate(e)] for i, e in enumerate(dom_e)]
+        ce = [[(q, d + bump * (1 + (k + i + 1) % 2)) for k, (q, d) in enumerate(e)] for i, e in enumerate(cod_e)]
+        dom, cod = [ctx.basis(e) for e in de], [ctx.basis(e) for e in ce]
+        ot = xo.Tensor(osym, [obasis(osym, e) for e in de], [obasis(osym, e) for e in ce])
+        ot.data = uniform_fill(seed, ot.plainSize())
+        st = layout_structure(ctx, dom, cod)
+        assert st == ot.structure()
+        owner = default_owner(ctx, st[1], st[2], 2)
+        for shift, p in PERMS:
+            for adjoint in (False, True):
+                ref = ot.permute_adj(shift, p) if adjoint else ot.permute(shift, p)
+                full, ost, _ = simulate(ctx, dom, cod, ot, st, shift, p, 2, owner, adjoint=adjoint)
+                assert ost == ref.structure()
+                err = np.linalg.norm(full - ref.data) / max(np.linalg.norm(ref.data), 1e-300)
+                assert err < 1e-13, (name, bump, shift, p, adjoint, err)
+    ctx.close()

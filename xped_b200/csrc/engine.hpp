@@ -275,6 +275,13 @@ private:
     std::unordered_map<std::string, BasisPtr> coupled_cache_;
     std::unordered_map<std::string, LayoutPtr> layout_cache_;
     std::unordered_map<std::string, std::shared_ptr<PermutePlan>> plan_cache_;
+public:
+    // recoupling results of treepair::permute keyed by the sector LABELS of the tree pair (+ shift, permutation, dual flags): they do not
+    // depend on the multiplicities, so plans for layouts that only differ in sector dimensions (a CTM run whose chi bases still move)
+    // reuse them; `dims_follow_permutation` records that the multiplicities of the result trees are those of the argument legs p[k]
+    struct RecouplingEntry { std::vector<std::pair<TreePair, double>> items; bool dims_follow_permutation = false; };
+    std::unordered_map<std::string, RecouplingEntry> recoupling_cache;
+private:
     std::unordered_map<std::string, std::shared_ptr<DistPermutePlan>> dist_plan_cache_;
     void* scratch_ = nullptr;
     size_t scratch_bytes_ = 0;

@@ -6,6 +6,9 @@
 // into a gather plan (each destination sub-block = sum_k coeff_k * transpose(src_k)), tiled, uploaded and
 // cached; the data then moves in one kernel launch (kernels.cu: permute_kernel).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -470,6 +473,71 @@ struct TaskSet
     bool identity = false;
 };
 
+// treepair::permute (src/Core/treepair.cpp:143-217) through the label-keyed cache of the context; the result is written to `out` with
+// the multiplicities of the CURRENT trees (result leg k carries the multiplicity of argument leg pi[k]).
+static void recoupled_pairs(Context& ctx, const Symmetry& S, int shift, const Tree& dt, const Tree& ct, const std::vector<int>& pi,
+                            std::vector<std::pair<TreePair, double>>& out)
+{
+    std::string key;
+    key.reserve(512);
+    auto put = [&key](const void* p, size_t n) { key.append(static_cast<const char*>(p), n); };
+    auto put_tree = [&](const Tree& t) {
+        put(&t.rank, sizeof(int));
+        for(int i = 0; i < t.rank; ++i) {
+            put(t.unc[i].data(), sizeof(Q));
+            const char dual = t.dual[i] ? 1 : 0;
+            put(&dual, 1);
+        }
+        for(int i = 0; i < t.n_inter(); ++i) put(t.inter[i].data(), sizeof(Q));
+        put(t.coupled.data(), sizeof(Q));
+    };
+    put(&shift, sizeof(int));
+    put(pi.data(), sizeof(int) * pi.size());
+    put_tree(dt);
+    put_tree(ct);
+    const int R = dt.rank, N = dt.rank + ct.rank;
+    auto arg_dim = [&](int leg) { return leg < R ? dt.dims[leg] : ct.dims[leg - R]; };
+    auto it = ctx.recoupling_cache.find(key);
+    if(it == ctx.recoupling_cache.end()) {
+        Context::RecouplingEntry e;
+        PairMap fresh = treepair_permute(S, shift, dt, ct, pi);
+        e.items.assign(fresh.begin(), fresh.end());
+        e.dims_follow_permutation = true;   // verified on this instance, relied upon for the later ones
+        for(const auto& item : e.items) {
+            const Tree& rd = item.first.d;
+            const Tree& rc = item.first.c;
+            if(rd.rank + rc.rank != N) e.dims_follow_permutation = false;
+            for(int k = 0; k < N && e.dims_follow_permutation; ++k) {
+                const int64_t have = k < rd.rank ? rd.dims[k] : rc.dims[k - rd.rank];
+                if(have != arg_dim(pi[k])) e.dims_follow_permutation = false;
+            }
+        }
+        if(ctx.recoupling_cache.size() >= 200000) ctx.recoupling_cache.clear();
+        it = ctx.recoupling_cache.emplace(std::move(key), std::move(e)).first;
+        out = it->second.items;
+        return;
+    }
+    const Context::RecouplingEntry& e = it->second;
+    if(!e.dims_follow_permutation) {   // should not happen; keep the exact path
+        PairMap fresh = treepair_permute(S, shift, dt, ct, pi);
+        out.assign(fresh.begin(), fresh.end());
+        return;
+    }
+    out = e.items;
+    for(auto& item : out) {
+        Tree& rd = item.first.d;
+        Tree& rc = item.first.c;
+        for(int k = 0; k < N; ++k) {
+            if(k < rd.rank)
+                rd.dims[k] = arg_dim(pi[k]);
+            else
+                rc.dims[k - rd.rank] = arg_dim(pi[k]);
+        }
+        rd.compute_dim();
+        rc.compute_dim();
+    }
+}
+
 static TaskSet build_tasks(Context& ctx, const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan, bool keep_identity = false)
 {
     const int R = in->rank(), C = in->corank(), N = R + C;
@@ -517,6 +585,7 @@ static TaskSet build_tasks(Context& ctx, const LayoutPtr& in, int shift, const s
 
     // ---- destination tasks, one per (sector, tree, cotree) of the output, in storage order
     std::vector<DstTask>& tasks = ts.tasks;
+    std::vector<std::pair<TreePair, double>> recoupled;
     std::vector<std::vector<int>> task_index(out->sector.size());   // [sector][a * ncod + b]
     std::vector<int> ncod(out->sector.size());
     for(size_t j = 0; j < out->sector.size(); ++j) {
@@ -572,7 +641,8 @@ static TaskSet build_tasks(Context& ctx, const LayoutPtr& in, int shift, const s
                                 tasks[dst_task(ndt, nct)].srcs.push_back({g, cd * cc});
                             }
                     } else {   // Tensor.cpp:179-210
-                        for(const auto& [pr, coeff] : treepair_permute(S, shift, dt, ct, pi)) {
+                        recoupled_pairs(ctx, S, shift, dt, ct, pi, recoupled);
+                        for(const auto& [pr, coeff] : recoupled) {
                             if(std::abs(coeff) < 1.e-10) continue;
                             tasks[dst_task(pr.d, pr.c)].srcs.push_back({g, coeff});
                         }
@@ -587,7 +657,8 @@ static TaskSet build_tasks(Context& ctx, const LayoutPtr& in, int shift, const s
             for(size_t a = 0; a < dts.size(); ++a)
                 for(size_t b = 0; b < cts.size(); ++b) {
                     DstTask& t = tasks[task_index[j][a * cts.size() + b]];
-                    for(const auto& [pr, coeff] : treepair_permute(S, shift, dts[a], cts[b], pi)) {
+                    recoupled_pairs(ctx, S, shift, dts[a], cts[b], pi, recoupled);
+                    for(const auto& [pr, coeff] : recoupled) {
                         if(std::abs(coeff) < 1.e-10) continue;
                         const int i = in->find(pr.d.coupled);
                         if(i < 0) throw std::logic_error("permute_adj plan: source sector missing");
@@ -1133,7 +1204,10 @@ std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shif
     }
     ++plan_misses;
     auto plan = std::make_shared<PermutePlan>();
+    static const bool plan_prof = std::getenv("XB_PLAN_PROF") != nullptr;
+    const auto tp0 = std::chrono::steady_clock::now();
     TaskSet ts = build_tasks(*this, in, shift, pi, adjoint_plan);
+    const auto tp1 = std::chrono::steady_clock::now();
     if(ts.identity) {   // Tensor.cpp:344 / :263
         plan->out = in;
         plan->identity_copy = true;
@@ -1145,6 +1219,11 @@ std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shif
     }
     // bound the cache: a CTM run whose chi bases still change from step to step creates ~200 new plans (a few MB of device tables each)
     // per step; plans in use stay alive through their shared_ptr
+    if(plan_prof) {
+        const auto tp2 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[plan prof] tasks %d tiles %d: build_tasks %.2f ms, lower_tasks %.2f ms\n", plan->n_tasks, plan->n_tiles,
+                     std::chrono::duration<double, std::milli>(tp1 - tp0).count(), std::chrono::duration<double, std::milli>(tp2 - tp1).count());
+    }
     if(plan_cache_.size() >= 4096) plan_cache_.clear();
     plan_cache_.emplace(key, plan);
     return plan;

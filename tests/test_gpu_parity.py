@@ -134,6 +134,20 @@ def test_multiply_adjoint_contract(ctxs, name):
     assert np.linalg.norm(a[fin] - b[fin]) <= TOL * max(np.linalg.norm(b[fin]), 1e-300)
 
 
+def test_multiply_split_k(ctxs):
+    """Products with few output tiles and a long contraction run as K slices + a deterministic reduction (ops.cpp run_gemm):
+    normal and lazily adjoint operands (TensorBase.cpp:243-288, AdjointOp.hpp:26-69)."""
+    ctx, osym = ctxs("U0")
+    gA, oA = pair(ctx, osym, [[((), 31)]], [[((), 612)]], 91)
+    gB, oB = pair(ctx, osym, [[((), 612)]], [[((), 33)]], 92)
+    gC, oC = pair(ctx, osym, [[((), 612)]], [[((), 140)]], 93)
+    assert_same(gA @ gB, oA @ oB, TOL, "(31 x 612) (612 x 33)")
+    assert_same(gA.multiply(gA, False, True), oA @ oA.adjoint(), TOL, "A A^dagger")
+    assert_same(gB.multiply(gB, True, False), oB.adjoint() @ oB, TOL, "B^dagger B")
+    assert_same(gC.multiply(gB, True, False), oC.adjoint() @ oB, TOL, "C^dagger B (140 x 612) (612 x 33)")
+    assert_same(gB.multiply(gA, True, True), oB.adjoint() @ oA.adjoint(), TOL, "B^dagger A^dagger")
+
+
 def test_error_codes(ctxs):
     ctx, _ = ctxs("U1")
     B, C = ctx.basis([(0, 2), (1, 1)]), ctx.basis([(0, 1), (-1, 2)])

@@ -168,6 +168,9 @@ struct GemmItem   // one (sector, tile) of a grouped product
     double alpha;
 };
 
+// one split-K problem: C[c_off + i + j ldc] = sum_s scratch[s_off + s m n + i + j m]
+struct SplitKJob { long long c_off, s_off; int m, n, ldc, split; };
+
 class Context;
 
 struct Tensor
@@ -327,6 +330,7 @@ void launch_permute2(const double* src, const double* src2, long long split, dou
 // deterministic LPT greedy (largest cost first, ties by index, least-loaded rank, ties lowest rank)
 std::vector<int> lpt_owner(const std::vector<double>& cost, int world);
 void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, int tile_m, cudaStream_t s);
+void launch_splitk_reduce(const double* scratch, double* C, const SplitKJob* d_jobs, int n_jobs, cudaStream_t s);
 void launch_scale_copy(const double* x, double* y, double alpha, int64_t n, cudaStream_t s);
 void launch_axpby(const double* x, const double* y, double* z, double alpha, double beta, int64_t n, cudaStream_t s);
 void launch_absmax(const double* x, int64_t n, double* d_out, cudaStream_t s);

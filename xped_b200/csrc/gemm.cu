@@ -197,6 +197,25 @@ template <int BM> void launch_one(const double* A, const double* B, double* C, c
 
 }   // namespace
 
+// split-K epilogue: the K slices of a problem were written to scratch by gemm_grouped_kernel; summed here in slice order (deterministic)
+__global__ void splitk_reduce_kernel(const double* __restrict__ scratch, double* __restrict__ C, const SplitKJob* __restrict__ jobs)
+{
+    const SplitKJob j = jobs[blockIdx.y];
+    const long long cnt = static_cast<long long>(j.m) * j.n, stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for(long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < cnt; e += stride) {
+        double sum = 0.0;
+        for(int s = 0; s < j.split; ++s) sum += scratch[j.s_off + s * cnt + e];
+        C[j.c_off + (e % j.m) + (e / j.m) * j.ldc] = sum;
+    }
+}
+
+void launch_splitk_reduce(const double* scratch, double* C, const SplitKJob* d_jobs, int n_jobs, cudaStream_t s)
+{
+    if(n_jobs == 0) return;
+    splitk_reduce_kernel<<<dim3(8, static_cast<unsigned>(n_jobs)), 256, 0, s>>>(scratch, C, d_jobs);
+    check_cuda(cudaGetLastError(), "splitk_reduce_kernel launch");
+}
+
 void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, int tile_m, cudaStream_t s)
 {
     if(n_items == 0) return;

@@ -52,11 +52,47 @@ Tensor* Context::copy(const Tensor& t)
 void Context::run_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems)
 {
     std::vector<GemmItem> items[2];   // [0]: 128 x 64 tiles (sectors with m > 96), [1]: 64 x 64 tiles
+    std::vector<SplitKJob> jobs;      // problems with few tiles and a long K: K is cut into slices, the partial products are summed afterwards
+    long long scratch_elems = 0;
     double flops = 0.0;
+    static const bool no_split = std::getenv("XB_GEMM_NOSPLIT") != nullptr;
     for(GemmItem g : problems) {
         if(g.m <= 0 || g.n <= 0) continue;
         flops += 2.0 * g.m * static_cast<double>(g.n) * g.k;
         const int which = g.m > 96 ? 0 : 1, tile_m = which == 0 ? 128 : 64;
+        const int ntiles = ((g.m + tile_m - 1) / tile_m) * ((g.n + GEMM_TILE_N - 1) / GEMM_TILE_N);
+        int split = 1;
+        if(!no_split && !g.acc && g.k >= 256 && ntiles <= 32) split = std::max(1, std::min(8, std::min(g.k / 96, sm_count / ntiles)));
+        if(split > 1) {
+            const int kchunk = ((((g.k + split - 1) / split) + 7) / 8) * 8;
+            SplitKJob job;
+            job.c_off = g.c_off;
+            job.s_off = scratch_elems;
+            job.m = g.m;
+            job.n = g.n;
+            job.ldc = g.ldc;
+            job.split = 0;
+            for(int k0 = 0; k0 < g.k; k0 += kchunk) {
+                GemmItem h = g;
+                h.k = std::min(kchunk, g.k - k0);
+                h.a_off += g.ta ? k0 : static_cast<long long>(k0) * g.lda;
+                h.b_off += g.tb ? static_cast<long long>(k0) * g.ldb : k0;
+                h.c_off = scratch_elems + static_cast<long long>(job.split) * g.m * g.n;   // relative to the scratch buffer; rebased below
+                h.ldc = g.m;
+                h.pad_ = 1;   // marks a scratch destination
+                ++job.split;
+                for(int tn = 0; tn < g.n; tn += GEMM_TILE_N)
+                    for(int tm = 0; tm < g.m; tm += tile_m) {
+                        h.tm = tm;
+                        h.tn = tn;
+                        items[which].push_back(h);
+                    }
+            }
+            scratch_elems += static_cast<long long>(job.split) * g.m * g.n;
+            jobs.push_back(job);
+            continue;
+        }
+        g.pad_ = 0;
         for(int tn = 0; tn < g.n; tn += GEMM_TILE_N)
             for(int tm = 0; tm < g.m; tm += tile_m) {
                 g.tm = tm;
@@ -73,13 +109,24 @@ void Context::run_gemm(const double* A, const double* B, double* C, const std::v
             mn = std::max(mn, g.n);
             mk = std::max(mk, g.k);
         }
-        std::fprintf(stderr, "[gemm] problems %zu flops %.3e max(m,n,k) = (%d,%d,%d) tiles128 %zu tiles64 %zu\n", problems.size(), flops, mm, mn, mk, items[0].size(),
-                     items[1].size());
+        std::fprintf(stderr, "[gemm] problems %zu flops %.3e max(m,n,k) = (%d,%d,%d) tiles128 %zu tiles64 %zu split-K jobs %zu\n", problems.size(), flops, mm, mn, mk,
+                     items[0].size(), items[1].size(), jobs.size());
     }
     ProfScope prof(*this, CAT_GEMM, flops);
+    double* d_scratch = nullptr;
+    long long rebase = 0;
+    if(scratch_elems > 0) {
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_scratch), sizeof(double) * scratch_elems, stream), "cudaMallocAsync split-K scratch");
+        rebase = (reinterpret_cast<intptr_t>(d_scratch) - reinterpret_cast<intptr_t>(C)) / static_cast<intptr_t>(sizeof(double));   // both 256-byte aligned
+    }
     for(int which = 0; which < 2; ++which) {
         auto& v = items[which];
         if(v.empty()) continue;
+        for(GemmItem& it : v)
+            if(it.pad_) {
+                it.c_off += rebase;
+                it.pad_ = 0;
+            }
         // heavy tiles first: k is the per-tile cost
         std::stable_sort(v.begin(), v.end(), [](const GemmItem& x, const GemmItem& y) { return x.k > y.k; });
         GemmItem* d_items = nullptr;
@@ -87,6 +134,15 @@ void Context::run_gemm(const double* A, const double* B, double* C, const std::v
         upload_async(d_items, v.data(), v.size() * sizeof(GemmItem));
         launch_gemm_grouped(A, B, C, d_items, static_cast<int>(v.size()), which == 0 ? 128 : 64, stream);
         check_cuda(cudaFreeAsync(d_items, stream), "cudaFreeAsync gemm items");
+        ++launches;
+    }
+    if(!jobs.empty()) {
+        SplitKJob* d_jobs = nullptr;
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_jobs), jobs.size() * sizeof(SplitKJob), stream), "cudaMallocAsync split-K jobs");
+        upload_async(d_jobs, jobs.data(), jobs.size() * sizeof(SplitKJob));
+        launch_splitk_reduce(d_scratch, C, d_jobs, static_cast<int>(jobs.size()), stream);
+        check_cuda(cudaFreeAsync(d_jobs, stream), "cudaFreeAsync split-K jobs");
+        check_cuda(cudaFreeAsync(d_scratch, stream), "cudaFreeAsync split-K scratch");
         ++launches;
     }
 }

@@ -1,13 +1,16 @@
 // Hand-written sm_100a kernels for the Xped hot path.
 //
-//  permute_kernel      batched strided scaled-accumulate tensor transpose: the whole of
+//  permute_bulk_kernel / permute_kernel
+//                      batched strided scaled-accumulate tensor transpose: the whole of
 //                      Tensor::permute / permute_adj (src/Core/Tensor.cpp:83-214,258-333) in ONE launch.
-//                      HBM-bound: every source element is read once per consumer tile through a
-//                      coalesced, shared-memory staged tile; every destination element is written once.
-//                      (TMA is not usable here: sub-block origins and leading dimensions are arbitrary
-//                      multiples of 8 bytes, cp.async.bulk[.tensor] needs 16-byte aligned boxes/strides.)
-//  gemm_grouped_kernel ragged per-sector C_q += op(A_q) * op(B_q) (src/Core/TensorBase.cpp:262-279) on the
-//                      FP64 tensor cores (mma.sync m8n8k4 DMMA; tcgen05 has no FP64 kind).
+//                      HBM-bound: every source element is read once, every destination element written once.
+//                      Bulk form: tiles move through shared memory with the TMA engine's 1-D cp.async.bulk (one
+//                      operation per contiguous run; needs 16-byte aligned runs of even length, fan-in 1);
+//                      LSU form for everything else (SU(2) fan-in > 1, odd run lengths, small tensors, sharded gather).
+//                      Tensor maps (cp.async.bulk.tensor) are not used: sub-block origins and leading dimensions are
+//                      arbitrary multiples of 8 bytes and change with every buffer.
+//  (gemm.cu)           gemm_grouped_kernel: ragged per-sector C_q += op(A_q) * op(B_q) (src/Core/TensorBase.cpp:262-279) on
+//                      the FP64 tensor cores (mma.sync m8n8k4 DMMA; tcgen05 has no FP64 kind).
 //  small fused elementwise / reduction kernels for AdjointOp, DiagCoeffUnaryOp, maxNorm, trace.
 #include <cuda_runtime.h>
 

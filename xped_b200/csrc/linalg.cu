@@ -2,10 +2,14 @@
 //
 // Reference: Tensor::tSVD / full_svd_impl / cutoff_matrices (src/Core/Tensor.cpp:478-633) loops over sectors and
 // calls LAPACK/Eigen per block (src/Interfaces/PlainInterface_Eigen_impl.cpp:114-127); here ALL sector blocks are
-// decomposed together by a block one-sided Jacobi (Hestenes) method:
-//   work matrix W_q (tall side first) and accumulator V_q = I; one kernel launch per round-robin round handles
-//   every (column-block pair, sector) in parallel: Gram matrix of the 2x16 columns -> cyclic Jacobi
-//   eigen-rotation in shared memory -> panel update of W_q and V_q.  Converged columns of W_q are sigma_j * u_j.
+// decomposed together by a QR-preconditioned block one-sided Jacobi (Hestenes) method:
+//   work matrix W_q (tall side first) and accumulator V_q, started from (A Q_B, Q_B) with A^T = Q_B R_B (precond.cu);
+//   one kernel launch per round-robin round handles every (column-block pair, sector) in parallel: Gram matrix of the
+//   2x16 columns -> Jacobi rotations on it in shared memory (cyclic by blocks: only the 16x16 cross pairs after the first
+//   round of a sweep) -> panel update of W_q and V_q.  Converged columns of W_q are sigma_j * u_j.  Pairs whose blocks did
+//   not change since they were found orthogonal are skipped; a sweep is replayed as a CUDA graph.
+//   svd_round_resident_kernel (row slices resident in shared memory, clusters of 1 / 2 / 8 CTAs) up to 2432 rows,
+//   svd_round_kernel (rows streamed in 64-row chunks, clusters of 4) beyond.
 // The singular values of all sectors are then sorted globally on the host (<= ~1e4 numbers) for the truncation
 // decision (Tensor.cpp:543-557) and one gather kernel writes the truncated U, Sigma, V^dagger.
 #include <cuda_runtime.h>

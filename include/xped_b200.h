@@ -195,6 +195,9 @@ int xb_ctm_move(xb_ctm* c, int direction);                                      
 int xb_ctm_rdm(xb_ctm* c, int which, xb_tensor** rho);
 /* avg(rho, O, bond) of a two-site observable  src/PEPS/LinearAlgebra.cpp:57-60 */
 int xb_avg_two_site(xb_ctx* ctx, const xb_tensor* rho, const xb_tensor* op, double* out);
+/* rho1 = normalised partial trace of a two-site density matrix (CTM.cpp:675-678); avg(rho1, O) of a one-site observable (LinearAlgebra.cpp:22-24) */
+int xb_rdm_one_site(xb_ctx* ctx, const xb_tensor* rho, xb_tensor** rho1);
+int xb_avg_one_site(xb_ctx* ctx, const xb_tensor* rho1, const xb_tensor* op, double* out);
 
 /* ---- micro-benchmark hooks (device-resident, timed with CUDA events on the context stream) -------------- */
 /* runs `reps` launches of the cached plan of permute<shift,p>(t); returns avg ms per launch and algorithmic bytes */

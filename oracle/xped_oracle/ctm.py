@@ -242,6 +242,19 @@ class CTM:
         return self._normalised_rdm(rho)
 
 
+def rdm_one_site(rho: Tensor) -> Tensor:
+    """rho1 from a two-site density matrix (CTM.cpp:675-678): trace over the second site, normalised by its twisted trace."""
+    sym = rho.sym
+    Id = Tensor.Identity(sym, [rho.uncoupled_codomain[1]], [rho.uncoupled_domain[1]])
+    rho1 = rho.contract([-1, 1, -2, 2], _tw(Id, 0), [2, 1], 1)
+    return rho1.scale(1.0 / _tw(rho1, 0).trace())
+
+
+def avg_one_site(rho1: Tensor, op: Tensor) -> float:
+    """<O> on a site (LinearAlgebra.cpp:22-24): rho1.twist(0).contract<{1,2},{2,1},0>(O).trace()."""
+    return float(_tw(rho1, 0).contract([1, 2], op, [2, 1], 0).trace())
+
+
 def avg_two_site(rho: Tensor, op: Tensor) -> float:
     """<O> on a bond (LinearAlgebra.cpp:57-60): rho.twist(0).twist(1).contract<{1,2,3,4},{3,4,1,2},0>(O).trace()."""
     return float(_tw(rho, 0, 1).contract([1, 2, 3, 4], op, [3, 4, 1, 2], 0).trace())

@@ -8,7 +8,9 @@ import pytest
 import xped_oracle as xo
 from helpers import SPECS, obasis, pair
 from xped_oracle.ctm import CTM as OCTM
+from xped_oracle.ctm import avg_one_site as oavg1
 from xped_oracle.ctm import avg_two_site as oavg
+from xped_oracle.ctm import rdm_one_site as ordm1
 from xped_oracle.ctm import heisenberg_bond_SU2, init_basis
 from xped_oracle.rng import uniform_fill
 
@@ -34,6 +36,9 @@ def test_oracle_rdm_invariants(name):
         assert abs(oavg(rho, Id) - 1.0) < 1e-12                                   # unit trace (CTM.cpp:660-667)
         herm = np.linalg.norm((rho - rho.adjoint()).data) / np.linalg.norm((rho + rho.adjoint()).data)
         assert herm < 1e-3, herm                                                   # rho_h_hermitian_check: exact only for a converged environment
+        rho1 = ordm1(rho)
+        Id1 = xo.Tensor.Identity(osym, [phys], [phys])
+        assert rho1.rank == 1 and rho1.corank == 1 and abs(oavg1(rho1, Id1) - 1.0) < 1e-12
     if name == "SU2":
         H = heisenberg_bond_SU2(osym, phys)
         for rho in (c.computeRDM_h(), c.computeRDM_v()):
@@ -51,6 +56,7 @@ def test_gpu_rdm_and_energy_match_the_oracle(name, D, chi):
         assert np.array_equal(oA.data, o.A.data)
         g = xb.CTM(gA, chi)
         gO, oO = pair(ctx, osym, [phys_e, phys_e], [phys_e, phys_e], 77)           # a random two-site observable
+        gO1, oO1 = pair(ctx, osym, [phys_e], [phys_e], 78)                           # a random one-site observable
         if name == "SU2":
             oH = heisenberg_bond_SU2(osym, phys)
             gH = ctx.tensor([ctx.basis(phys_e)] * 2, [ctx.basis(phys_e)] * 2)
@@ -62,6 +68,10 @@ def test_gpu_rdm_and_energy_match_the_oracle(name, D, chi):
                 err = np.linalg.norm(grho.download() - orho.data) / np.linalg.norm(orho.data)
                 assert err < 1e-9, f"step {step} {what}: {err:.2e}"
                 assert abs(xb.avg_two_site(grho, gO) - oavg(orho, oO)) < 1e-9
+                grho1, orho1 = xb.rdm_one_site(grho), ordm1(orho)
+                assert grho1.structure() == orho1.structure()
+                assert np.linalg.norm(grho1.download() - orho1.data) < 1e-9 * np.linalg.norm(orho1.data)
+                assert abs(xb.avg_one_site(grho1, gO1) - oavg1(orho1, oO1)) < 1e-9
                 if name == "SU2":
                     assert abs(xb.avg_two_site(grho, gH) - oavg(orho, oH)) < 1e-9
             g.grow_all()

@@ -104,6 +104,8 @@ SIGNATURES = {
     "xb_permute_plan_stats": (C.c_int, [P, PP, C.c_int, PP, C.c_int, C.c_int, IP, C.c_int, LP]),
     "xb_ctm_rdm": (C.c_int, [P, C.c_int, PP]),
     "xb_avg_two_site": (C.c_int, [P, P, P, DP]),
+    "xb_rdm_one_site": (C.c_int, [P, P, PP]),
+    "xb_avg_one_site": (C.c_int, [P, P, P, DP]),
     "xb_ctm_move": (C.c_int, [P, C.c_int]),
     "xb_bench_permute": (C.c_int, [P, P, C.c_int, IP, C.c_int, C.c_int, DP, LP]),
     "xb_bench_multiply": (C.c_int, [P, P, P, C.c_int, DP, DP]),

@@ -815,6 +815,23 @@ int xb_ctm_rdm(xb_ctm* c, int which, xb_tensor** rho)
     });
 }
 
+int xb_rdm_one_site(xb_ctx* ctx, const xb_tensor* rho, xb_tensor** rho1)
+{
+    return guard([&] {
+        need(rho, "rho");
+        *rho1 = wrap(ctx, rdm_one_site(ctx->impl, *rho->t));
+    });
+}
+
+int xb_avg_one_site(xb_ctx* ctx, const xb_tensor* rho1, const xb_tensor* op, double* out)
+{
+    return guard([&] {
+        need(rho1, "rho1");
+        need(op, "op");
+        *out = avg_one_site(ctx->impl, *rho1->t, *op->t);
+    });
+}
+
 int xb_avg_two_site(xb_ctx* ctx, const xb_tensor* rho, const xb_tensor* op, double* out)
 {
     return guard([&] {

@@ -129,6 +129,28 @@ double avg_two_site(Context& ctx, const Tensor& rho, const Tensor& op)
     return full_contraction(ctx, *b, op);
 }
 
+Tensor* rdm_one_site(Context& ctx, const Tensor& rho)
+{
+    if(rho.layout->rank() != 2 || rho.layout->corank() != 2) throw std::invalid_argument("rdm_one_site: rho must be a Tensor<2,2>");
+    const Layout& L = *rho.layout;
+    std::unique_ptr<Tensor> Id(new Tensor(&ctx, ctx.layout({L.cod[1]}, {L.dom[1]}), true));
+    ctx.fill(*Id, 1, 0.0, 0);
+    std::unique_ptr<Tensor> Idt(ctx.twist(*Id, 0));
+    std::unique_ptr<Tensor> rho1(ctx.contract(rho, {-1, 1, -2, 2}, *Idt, {2, 1}, 1));
+    std::unique_ptr<Tensor> tw(ctx.twist(*rho1, 0));
+    const double norm = ctx.trace(*tw);
+    return ctx.axpby(1.0 / norm, *rho1, 0.0, nullptr);
+}
+
+double avg_one_site(Context& ctx, const Tensor& rho1, const Tensor& op)
+{
+    if(rho1.layout->rank() != 1 || rho1.layout->corank() != 1 || op.layout->rank() != 1 || op.layout->corank() != 1)
+        throw std::invalid_argument("avg: rho1 and the observable must be Tensor<1,1>");
+    std::unique_ptr<Tensor> a(ctx.twist(rho1, 0));
+    std::unique_ptr<Tensor> prod(ctx.multiply(*a, false, op, false));   // contract<{1,2},{2,1},0>(O).trace() = trace(rho1 * O)
+    return ctx.trace(*prod);
+}
+
 Tensor* Ctm::rdm(int which)
 {
     TP rho;

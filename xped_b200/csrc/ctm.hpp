@@ -13,6 +13,9 @@ using TP = std::shared_ptr<Tensor>;
 void decompose_projectors(Context& ctx, const Tensor& T1, const Tensor& T2, int64_t chi, Tensor** P1, Tensor** P2);
 // avg(rho, O, bond) for a two-site observable (src/PEPS/LinearAlgebra.cpp:57-60): rho.twist(0).twist(1).contract<{1,2,3,4},{3,4,1,2},0>(O).trace()
 double avg_two_site(Context& ctx, const Tensor& rho, const Tensor& op);
+// rho1 from a two-site density matrix (src/PEPS/CTM.cpp:675-678) and avg(rho1, O) of a one-site observable (LinearAlgebra.cpp:22-24)
+Tensor* rdm_one_site(Context& ctx, const Tensor& rho);
+double avg_one_site(Context& ctx, const Tensor& rho1, const Tensor& op);
 
 class Ctm
 {

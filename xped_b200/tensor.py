@@ -368,3 +368,17 @@ def avg_two_site(rho, op):
     out = C.c_double()
     check(rho.ctx.lib.xb_avg_two_site(rho.ctx.h, rho.h, op.h, C.byref(out)))
     return out.value
+
+
+def rdm_one_site(rho):
+    """rho1 = normalised partial trace over the second site of a two-site density matrix (src/PEPS/CTM.cpp:675-678)"""
+    h = C.c_void_p()
+    check(rho.ctx.lib.xb_rdm_one_site(rho.ctx.h, rho.h, C.byref(h)))
+    return Tensor(rho.ctx, h)
+
+
+def avg_one_site(rho1, op):
+    """avg(rho1, O) of a one-site observable (src/PEPS/LinearAlgebra.cpp:22-24)"""
+    out = C.c_double()
+    check(rho1.ctx.lib.xb_avg_one_site(rho1.ctx.h, rho1.h, op.h, C.byref(out)))
+    return out.value

@@ -254,6 +254,25 @@ def kernel_sections(xb, device, torch):
         del ctm6, A6
     except Exception as e:
         out["ctm_d6_chi144"] = {"error": f"{type(e).__name__}: {e}"}
+    # ---- configs[0]: the reference's own benchmarks/bench.cpp workload (SU(2) spin-1/2 chain, L = 20, Minit = 200, Qinit = 10:
+    # <Psi|Psi> by dot() ten times, then one sweep of SVD steps); latency-bound at these sizes: reported as ms
+    try:
+        psi = xb.random_mps(ctx3, 20, [((2,), 1)], (1,), 200, 10, seed=0)
+        xb.dot(psi, psi, "RIGHT")
+        ctx3.sync()
+        ctx3.timer_start()
+        for _ in range(10):
+            nrm = xb.dot(psi, psi, "RIGHT")
+        ms_dot = ctx3.timer_stop() / 10
+        ctx3.timer_start()
+        for l in range(psi.length()):
+            psi.rightSweepStep(l)
+        ms_sweep = ctx3.timer_stop()
+        out["mps_bench_cpp"] = {"op": "benchmarks/bench.cpp: SU(2) spin-1/2 chain, L=20, Minit=200, Qinit=10", "dot_ms": ms_dot, "right_sweep_ms": ms_sweep,
+                                "norm_before_sweep": nrm, "norm_after_sweep": xb.dot(psi, psi, "RIGHT"),
+                                "bond_dims": [sum(d for _, d in psi.Ac[l].leg_basis(2).entries()) for l in range(psi.length())]}
+    except Exception as e:
+        out["mps_bench_cpp"] = {"error": f"{type(e).__name__}: {e}"}
     ctx3.close()
     return out, dgemm_peak
 

@@ -92,3 +92,52 @@ def dot(BraAc, KetAc, direction="RIGHT"):
     for l in range(len(BraAc) - 1, -1, -1):
         B = contract_R(B, BraAc[l], KetAc[l])
     return B.norm()
+
+
+def gen_aux_bases(sym, L, qloc, Qtarget, Minit, Qinit):
+    """Mps::gen_maxBasis + gen_auxBasis (src/MPS/Mps.cpp:56-127), Qbasis::intersection / truncate (src/Core/Qbasis.cpp:398-408,278-304)
+    restated on oracle Qbasis objects; returns the bond bases as [(q, dim)] lists.  Ties of the distance sort keep their order (the
+    reference's std::sort is unstable there: parity unpinned for ties)."""
+    from .basis import Qbasis
+    if not isinstance(qloc, list):
+        qloc = [qloc] * L
+    vac, Qtarget = sym.qvacuum(), tuple(Qtarget)
+    nq = len(vac)
+    mk = lambda entries: Qbasis.from_list(sym, entries)
+    ent = lambda b: [(q, d) for q, _, d in b.data]
+
+    def intersection(a, b):
+        out = Qbasis(sym)
+        for q, _, d in a.data:
+            other = [e for e in b.data if e[0] == q]
+            if other:
+                out.push_back(q, min(d, other[0][2]))
+        return out
+
+    maxb = [None] * (L + 1)
+    maxb[0], maxb[L] = mk([(vac, 1)]), mk([(Qtarget, 1)])
+    fl, fr = [None] * (L - 1), [None] * (L - 1)
+    fl[0] = maxb[0].combine(qloc[0]).forgetHistory()
+    for l in range(1, L - 1):
+        fl[l] = fl[l - 1].combine(qloc[l]).forgetHistory()
+    fr[L - 2] = maxb[L].combine(qloc[L - 1]).forgetHistory()
+    for l in range(L - 2, 0, -1):
+        fr[l - 1] = fr[l].combine(qloc[l]).forgetHistory()
+    for l in range(L - 1):
+        maxb[l + 1] = intersection(fl[l], fr[l])
+    qaux = []
+    for l in range(L + 1):
+        entries = ent(maxb[l])
+        qs = [q for q, _ in entries]
+        if len(qs) > Qinit:
+            mean = [Qtarget[k] * l / L for k in range(nq)]
+            qmin, qmax = min(qs), max(qs)
+            dist = lambda q: sum((((q[k] - mean[k]) / (qmax[k] - qmin[k])) ** 2 if qmax[k] != qmin[k] else 0.0) for k in range(nq)) ** 0.5
+            kept = set(sorted(qs, key=dist)[:Qinit])
+            entries = [(q, d) for q, d in entries if q in kept]
+        if Minit < sum(d for _, d in entries):
+            n = len(entries)
+            D, rem = Minit // n, Minit % n
+            entries = [(q, min(d, D + rem if q == vac else D)) for q, d in entries]
+        qaux.append(entries)
+    return qaux

@@ -78,3 +78,31 @@ def test_gpu_sweeps_match_the_oracle(name, chi):
             assert abs(ng - no) <= 1e-10 * no, f"norm after the {sweep} sweep"
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("name,L,Qtarget,Minit,Qinit", [("SU2", 8, (1,), 12, 3), ("SU2", 10, (3,), 200, 10), ("U1", 8, (0,), 10, 3), ("U1", 7, (1,), 6, 2)])
+def test_aux_basis_generator_matches_the_oracle(name, L, Qtarget, Minit, Qinit):
+    """Mps::gen_maxBasis / gen_auxBasis (src/MPS/Mps.cpp:56-127): the product's host logic (planning-only context, no GPU) against
+    the oracle restatement, plus the defining properties (ends, reachability from both sides, caps)."""
+    from xped_b200.sharded import PlanningContext
+    from xped_b200.mps import gen_aux_bases
+    from xped_oracle.mps import gen_aux_bases as ogen
+    ctx = PlanningContext(SPECS[name])
+    osym = xo.Symmetry.from_spec(SPECS[name])
+    got = gen_aux_bases(ctx, L, LOC[name], Qtarget, Minit, Qinit)
+    ref = ogen(osym, L, obasis(osym, LOC[name]), Qtarget, Minit, Qinit)
+    assert got == ref
+    assert got[0] == [(osym.qvacuum(), 1)] and got[L] == [(tuple(Qtarget), 1)]
+    for l in range(L + 1):
+        assert len(got[l]) <= max(Qinit, 1) and sum(d for _, d in got[l]) <= max(Minit, len(got[l]))
+    ctx.close()
+
+
+def test_aux_basis_known_answer_su2_singlet():
+    """Spin-1/2 chain of four sites with total spin 0: the bond sectors are forced (q = 2S+1): 1 | 2 | 1,3 | 2 | 1."""
+    from xped_b200.sharded import PlanningContext
+    from xped_b200.mps import gen_aux_bases
+    ctx = PlanningContext(SPECS["SU2"])
+    got = gen_aux_bases(ctx, 4, LOC["SU2"], (1,), 100, 10)
+    assert got == [[((1,), 1)], [((2,), 1)], [((1,), 1), ((3,), 1)], [((2,), 1)], [((1,), 1)]]
+    ctx.close()

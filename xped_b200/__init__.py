@@ -5,4 +5,4 @@ ctypes mirror of the reference's Tensor interface. Nothing here imports oracle/.
 """
 from .capi import LIB_PATH, SIGNATURES, XbError, load  # noqa: F401
 from .tensor import CTM, Context, Qbasis, Tensor, avg_one_site, avg_two_site, contract_L, contract_R, decompose, rdm_one_site  # noqa: F401
-from .mps import Mps, dot  # noqa: F401
+from .mps import Mps, dot, gen_aux_bases, random_mps  # noqa: F401

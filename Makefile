@@ -1,14 +1,21 @@
 # In-tree build of the product library (sm_100a only) and nothing else.
 NVCC ?= nvcc
-SRC := xped_b200/csrc/core.cpp xped_b200/csrc/layout.cpp xped_b200/csrc/ops.cpp xped_b200/csrc/extras.cpp \
-       xped_b200/csrc/ctm.cpp xped_b200/csrc/capi.cpp xped_b200/csrc/kernels.cu xped_b200/csrc/gemm.cu xped_b200/csrc/linalg.cu xped_b200/csrc/precond.cu
-HDR := xped_b200/csrc/core.hpp xped_b200/csrc/engine.hpp xped_b200/csrc/ctm.hpp xped_b200/csrc/precond.hpp include/xped_b200.h
+CSRC := xped_b200/csrc
+SRC := $(CSRC)/core.cpp $(CSRC)/layout.cpp $(CSRC)/ops.cpp $(CSRC)/extras.cpp $(CSRC)/ctm.cpp $(CSRC)/capi.cpp \
+       $(CSRC)/kernels.cu $(CSRC)/gemm.cu $(CSRC)/linalg.cu $(CSRC)/precond.cu $(CSRC)/rsvd.cu
+HDR := $(wildcard $(CSRC)/*.hpp) include/xped_b200.h
 LIB := xped_b200/lib/libxped_b200.so
-FLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function --shared
+OBJDIR := build/obj
+OBJ := $(patsubst $(CSRC)/%,$(OBJDIR)/%.o,$(SRC))
+FLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function
 
-$(LIB): $(SRC) $(HDR)
+$(LIB): $(OBJ)
 	mkdir -p xped_b200/lib
-	$(NVCC) $(FLAGS) -o $@ $(SRC)
+	$(NVCC) $(FLAGS) --shared -o $@ $(OBJ)
+
+$(OBJDIR)/%.o: $(CSRC)/% $(HDR)
+	mkdir -p $(OBJDIR)
+	$(NVCC) $(FLAGS) -c -o $@ $<
 
 clean:
-	rm -f $(LIB)
+	rm -rf $(LIB) $(OBJDIR)

@@ -121,8 +121,11 @@ int xb_tsvd(xb_ctx* ctx, const xb_tensor* t, int64_t max_keep, double eps_svd, i
 /* reverse rule of the full SVD + truncation  include/Xped/AD/ADTensor.hpp:253-325,356-371 */
 int xb_tsvd_backward(xb_ctx* ctx, const xb_tensor* A, const xb_tensor* U, const xb_tensor* S, const xb_tensor* Vdag, const xb_tensor* dU,
                      const xb_tensor* dS, const xb_tensor* dVdag, xb_tensor** dA);
-/* Tensor::tQR()  src/Core/Tensor.cpp:757-780 (tall blocks) ; Tensor::teigh()  :782-803 */
-int xb_tqr(xb_ctx* ctx, const xb_tensor* t, xb_tensor** Q, xb_tensor** R);
+/* Tensor::tQR(bool RETURN_LQ)  src/Core/Tensor.cpp:757-780: Q (domain -> middle), R (middle -> codomain), middle = the smaller coupled basis.
+ * Blocks are Q_full 1(m x mid), 1(mid x m) R_full (mid = inner dimension of the middle basis; the reference's matrices wherever those fit
+ * its own bases).  return_lq != 0: the adjoint blocks (Q^T, R^T) like the reference, square blocks only (XB_ERR_INVALID otherwise).
+ * Tensor::teigh()  :782-803 */
+int xb_tqr(xb_ctx* ctx, const xb_tensor* t, int return_lq, xb_tensor** Q, xb_tensor** R);
 int xb_teigh(xb_ctx* ctx, const xb_tensor* t, xb_tensor** D, xb_tensor** V);
 /* decompose(T1,T2,chi)  src/PEPS/PEPSContractions.cpp:18-43: CTM projectors P1 = S^-1/2 U^+ T1, P2 = T2 V S^-1/2 */
 int xb_decompose(xb_ctx* ctx, const xb_tensor* T1, const xb_tensor* T2, int64_t chi, xb_tensor** P1, xb_tensor** P2);

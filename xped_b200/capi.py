@@ -74,7 +74,7 @@ SIGNATURES = {
     "xb_squared_norm": (C.c_int, [P, P, DP]),
     "xb_tsvd": (C.c_int, [P, P, C.c_int64, C.c_double, C.c_int, PP, PP, PP, DP, DP]),
     "xb_tsvd_backward": (C.c_int, [P, P, P, P, P, P, P, P, PP]),
-    "xb_tqr": (C.c_int, [P, P, PP, PP]),
+    "xb_tqr": (C.c_int, [P, P, C.c_int, PP, PP]),
     "xb_teigh": (C.c_int, [P, P, PP, PP]),
     "xb_decompose": (C.c_int, [P, P, P, C.c_int64, PP, PP]),
     "xb_contract_L": (C.c_int, [P, P, P, P, PP]),

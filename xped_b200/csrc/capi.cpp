@@ -677,12 +677,13 @@ int xb_tsvd_backward(xb_ctx* ctx, const xb_tensor* A, const xb_tensor* U, const 
     });
 }
 
-int xb_tqr(xb_ctx* ctx, const xb_tensor* t, xb_tensor** Qo, xb_tensor** Ro)
+int xb_tqr(xb_ctx* ctx, const xb_tensor* t, int return_lq, xb_tensor** Qo, xb_tensor** Ro)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(t, "tensor");
         Tensor *q = nullptr, *r = nullptr;
-        ctx->impl.tqr(*t->t, &q, &r);
+        ctx->impl.tqr(*t->t, return_lq != 0, &q, &r);
         *Qo = wrap(ctx, q);
         *Ro = wrap(ctx, r);
     });

@@ -171,7 +171,22 @@ struct GemmItem   // one (sector, tile) of a grouped product
 // one split-K problem: C[c_off + i + j ldc] = sum_s scratch[s_off + s m n + i + j m]
 struct SplitKJob { long long c_off, s_off; int m, n, ldc, split; };
 
+// a grouped product whose tile lists are already on the device: launched any number of times (iterative solvers, graph capture)
+struct PreparedGemm
+{
+    const double *A = nullptr, *B = nullptr;
+    double* C = nullptr;
+    GemmItem* d_items[2] = {nullptr, nullptr};
+    int n_items[2] = {0, 0};
+    SplitKJob* d_jobs = nullptr;
+    int n_jobs = 0;
+    double* d_scratch = nullptr;
+    int launches = 0;
+    double flops = 0.0;
+};
+
 class Context;
+struct RsvdPlan;   // cached state of the truncated tSVD for one layout (rsvd.cu)
 
 struct Tensor
 {
@@ -233,8 +248,15 @@ public:
     double squared_norm(const Tensor& t);
     void fill(Tensor& t, int mode, double value, uint64_t seed);                 // 0 constant, 1 identity, 2 counter-based uniform[-1,1]
     SvdResult tsvd(const Tensor& t, int64_t max_keep, double eps_svd, bool preserve_multiplets);
+    // the two algorithms behind tsvd(): full batched Jacobi on every sector block, and (few kept values out of many) randomized block subspace
+    // iteration + Jacobi on the projected blocks with an a-posteriori residual check (returns false => caller falls back to the full path)
+    SvdResult tsvd_full(const Tensor& t, int64_t max_keep, double eps_svd, bool preserve_multiplets);
+    bool tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, bool preserve_multiplets, SvdResult* out);
+    int64_t svd_truncated_calls = 0, svd_truncated_fallbacks = 0, svd_truncated_iters = 0;
+    std::unordered_map<std::string, std::shared_ptr<RsvdPlan>> rsvd_plans;
+    void clear_rsvd_plans();
     Tensor* tsvd_backward(const Tensor& A, const Tensor& U, const Tensor& S, const Tensor& Vd, const Tensor* dU, const Tensor* dS, const Tensor* dVd);
-    void tqr(const Tensor& t, Tensor** Qo, Tensor** Ro);
+    void tqr(const Tensor& t, bool return_lq, Tensor** Qo, Tensor** Ro);
     void teigh(const Tensor& t, Tensor** D, Tensor** V);
     void contract_L(const Tensor& Bold, const Tensor& Bra, const Tensor& Ket, Tensor** Bnew);
     void contract_R(const Tensor& Bold, const Tensor& Bra, const Tensor& Ket, Tensor** Bnew);
@@ -246,10 +268,13 @@ public:
     void sync();
     // grouped product launcher: one GemmItem per problem (tm = tn = 0); tiles, sorts, uploads and launches
     void run_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems);
+    PreparedGemm prepare_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems);
+    void launch_gemm(const PreparedGemm& P);
+    void free_gemm(PreparedGemm& P);
 
     // one Jacobi sweep (flag reset + all rounds) as an instantiated CUDA graph, keyed by layout; valid while the stream-ordered pool
     // hands the same work buffers back (it does in a steady CTM run), re-captured otherwise
-    struct SweepGraph { cudaGraphExec_t exec = nullptr; const void *w = nullptr, *v = nullptr, *meta = nullptr; int rounds = 0; };
+    struct SweepGraph { cudaGraphExec_t exec = nullptr; const void *w = nullptr, *v = nullptr, *meta = nullptr, *x = nullptr; int rounds = 0; };
     std::unordered_map<std::string, SweepGraph> sweep_graphs;
 
     // statistics for bench / gpu_launches

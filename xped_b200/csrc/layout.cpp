@@ -52,6 +52,7 @@ Context::~Context()
     if(device < 0) return;
     cudaSetDevice(device);
     if(stream) cudaStreamSynchronize(stream);
+    clear_rsvd_plans();
     plan_cache_.clear();
     for(const ProfRec& r : prof_recs) {
         cudaEventDestroy(r.e0);

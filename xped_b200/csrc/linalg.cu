@@ -25,6 +25,7 @@
 
 #include "engine.hpp"
 #include "precond.hpp"
+#include "svd_internal.hpp"
 
 namespace xb {
 
@@ -34,15 +35,6 @@ constexpr int SB = 16;    // column-block width
 constexpr int SP = 32;    // panel = two column blocks
 constexpr int SCH = 64;   // rows per staged chunk
 constexpr int SVD_THREADS = 256;
-
-struct SvdBlock
-{
-    long long w_off;   // work matrix, rows x cols, column-major, ld = rows
-    long long v_off;   // accumulator, cols x cols
-    long long s_off;   // singular values (cols)
-    int rows, cols;
-    double tol;
-};
 
 // mode 0: all pairs of the 32-column panel (31 steps), 1: cross pairs only (16 steps); gbi / gbj: indices of the two column blocks in
 // the modification-stamp table (gbj = -1: single block)
@@ -810,22 +802,26 @@ void schedule(int block, int nb, int gbase, std::vector<std::vector<SvdTask>>& r
     }
 }
 
-struct JacobiResult
-{
-    std::vector<SvdBlock> blocks;
-    std::vector<int> transposed;
-    std::vector<double> sigma;   // host copy, per block at s_off
-    std::vector<double> shift;   // host copy of the per-block diagonal shift (teigh only)
-    double* d_W = nullptr;
-    double* d_V = nullptr;
-    int sweeps = 0;
-};
+}   // namespace
 
-// One-sided block Jacobi on every sector block of `t`. Leaves W (= sigma_j u_j columns) and V on the device.
-JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
+JacobiInput jacobi_input(const Tensor& t)
 {
     const Layout& L = *t.layout;
-    const int nb = static_cast<int>(L.sector.size());
+    JacobiInput in;
+    in.d = t.d;
+    in.sig = L.sig;
+    for(size_t i = 0; i < L.sector.size(); ++i) {
+        in.off.push_back(L.off[i]);
+        in.rows.push_back(static_cast<int>(L.rows[i]));
+        in.cols.push_back(static_cast<int>(L.cols[i]));
+    }
+    return in;
+}
+
+// One-sided block Jacobi on every block of `in`. Leaves W (= sigma_j u_j columns), V and the singular values on the device.
+JacobiResult jacobi_all(Context& ctx, const JacobiInput& in, bool shifted, bool host_sigma)
+{
+    const int nb = static_cast<int>(in.off.size());
     JacobiResult R;
     R.blocks.resize(nb);
     R.transposed.resize(nb);
@@ -833,7 +829,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
     std::vector<long long> a_off(nb);
     std::vector<int> a_rows(nb);
     for(int i = 0; i < nb; ++i) {
-        const int m = static_cast<int>(L.rows[i]), n = static_cast<int>(L.cols[i]);
+        const int m = in.rows[i], n = in.cols[i];
         const bool tr = m < n;
         R.transposed[i] = tr;
         SvdBlock& b = R.blocks[i];
@@ -846,12 +842,14 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         woff += static_cast<long long>(b.rows) * b.cols;
         voff += static_cast<long long>(b.cols) * b.cols;
         soff += b.cols;
-        a_off[i] = L.off[i];
+        a_off[i] = in.off[i];
         a_rows[i] = m;
     }
-    R.sigma.assign(static_cast<size_t>(soff), 0.0);
+    R.n_sigma = soff;
+    if(host_sigma) R.sigma.assign(static_cast<size_t>(soff), 0.0);
     if(nb == 0 || woff == 0) return R;
     cudaStream_t s = ctx.stream;
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&R.d_sigma), sizeof(double) * std::max<long long>(soff, 1), s), "svd sigma");
     check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&R.d_W), sizeof(double) * std::max<long long>(woff, 1), s), "svd W");
     check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&R.d_V), sizeof(double) * std::max<long long>(voff, 1), s), "svd V");
 
@@ -877,7 +875,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
     o_tasks = (o_tasks + 15) & ~size_t(15);
     size_t o_sigma = o_tasks + sizeof(SvdTask) * flat.size();
     o_sigma = (o_sigma + 15) & ~size_t(15);
-    const size_t o_shift = o_sigma + sizeof(double) * soff;
+    const size_t o_shift = o_sigma;
     const size_t o_flag = o_shift + sizeof(double) * nb;
     // convergence bookkeeping: mod[column block] = time of its last rotation, clean[task] = time the pair was last found orthogonal,
     // one sweep counter; time = sweep * rounds + round + 1.  A pair whose blocks did not change since it was found clean is skipped.
@@ -895,7 +893,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
     ctx.upload_async(d_meta, h_meta.data(), h_meta.size());
     auto* d_blocks = reinterpret_cast<SvdBlock*>(d_meta + o_blocks);
     auto* d_tasks = reinterpret_cast<SvdTask*>(d_meta + o_tasks);
-    auto* d_sigma = reinterpret_cast<double*>(d_meta + o_sigma);
+    double* d_sigma = R.d_sigma;
     auto* d_flag = reinterpret_cast<int*>(d_meta + o_flag);
     auto* d_shift = reinterpret_cast<double*>(d_meta + o_shift);
     int* d_mod = reinterpret_cast<int*>(d_meta + o_stamps);
@@ -905,12 +903,12 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
 
     {
         if(shifted) {
-            block_shift_kernel<<<nb, 256, 0, s>>>(t.d, reinterpret_cast<long long*>(d_meta + o_aoff), d_blocks, nb, d_shift);
+            block_shift_kernel<<<nb, 256, 0, s>>>(in.d, reinterpret_cast<long long*>(d_meta + o_aoff), d_blocks, nb, d_shift);
             check_cuda(cudaGetLastError(), "block_shift_kernel launch");
             ++ctx.launches;
         }
         dim3 grid(64, static_cast<unsigned>(std::min(nb, 64)));
-        svd_init_kernel<<<grid, 256, 0, s>>>(t.d, R.d_W, R.d_V, d_blocks, reinterpret_cast<long long*>(d_meta + o_aoff),
+        svd_init_kernel<<<grid, 256, 0, s>>>(in.d, R.d_W, R.d_V, d_blocks, reinterpret_cast<long long*>(d_meta + o_aoff),
                                             reinterpret_cast<int*>(d_meta + o_arows), reinterpret_cast<int*>(d_meta + o_tr), nb, shifted ? d_shift : nullptr);
         check_cuda(cudaGetLastError(), "svd_init_kernel launch");
         ++ctx.launches;
@@ -965,8 +963,15 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
             static const bool no_qr_graph = std::getenv("XB_SVD_NOGRAPH") != nullptr;
             bool replayed = false;
             if(!no_qr_graph && !pre_prof) {
-                Context::SweepGraph& g = ctx.sweep_graphs[L.sig + "#qr"];
-                if(g.exec == nullptr || g.w != R.d_W || g.v != d_aug || g.meta != d_pre) {
+                const std::string qr_key = in.sig + "#qr";
+                if(ctx.sweep_graphs.size() >= 256 && ctx.sweep_graphs.find(qr_key) == ctx.sweep_graphs.end()) {   // bound the cache (layouts that keep changing)
+                    for(auto& kv : ctx.sweep_graphs)
+                        if(kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+                    ctx.sweep_graphs.clear();
+                }
+                Context::SweepGraph& g = ctx.sweep_graphs[qr_key];
+                // the captured launches write W, the augmented workspace AND V: all three (and the descriptor table) must be the captured buffers
+                if(g.exec == nullptr || g.w != R.d_W || g.v != d_aug || g.meta != d_pre || g.x != R.d_V) {
                     if(g.exec) cudaGraphExecDestroy(g.exec);
                     g = Context::SweepGraph();
                     cudaGraph_t graph = nullptr;
@@ -986,6 +991,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
                         g.w = R.d_W;
                         g.v = d_aug;
                         g.meta = d_pre;
+                        g.x = R.d_V;
                         g.rounds = static_cast<int>(counted);
                     } else {
                         cudaGetLastError();
@@ -1157,7 +1163,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
     int rounds_per_sweep = 0;
     for(size_t r = 0; r + 1 < round_begin.size(); ++r) rounds_per_sweep += round_begin[r + 1] > round_begin[r] ? 1 : 0;
     if(!no_graph && !svd_prof && rounds_per_sweep >= 8) {
-        const std::string key = L.sig + (shifted ? "#eigh" : "#svd");
+        const std::string key = in.sig + (shifted ? "#eigh" : "#svd");
         if(ctx.sweep_graphs.size() >= 256 && ctx.sweep_graphs.find(key) == ctx.sweep_graphs.end()) {   // bound the cache (layouts that keep changing)
             for(auto& kv : ctx.sweep_graphs)
                 if(kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -1219,6 +1225,7 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         cudaFreeAsync(d_meta, s);
         cudaFreeAsync(R.d_W, s);
         cudaFreeAsync(R.d_V, s);
+        cudaFreeAsync(R.d_sigma, s);
         throw std::runtime_error("tSVD: block Jacobi did not converge in 150 sweeps");
     }
     {
@@ -1227,12 +1234,12 @@ JacobiResult jacobi_all(Context& ctx, const Tensor& t, bool shifted)
         check_cuda(cudaGetLastError(), "svd_norms_kernel launch");
         ++ctx.launches;
     }
-    check_cuda(cudaMemcpyAsync(R.sigma.data(), d_sigma, sizeof(double) * soff, cudaMemcpyDeviceToHost, s), "sigma readback");
+    if(host_sigma) check_cuda(cudaMemcpyAsync(R.sigma.data(), d_sigma, sizeof(double) * soff, cudaMemcpyDeviceToHost, s), "sigma readback");
     if(shifted) {
         R.shift.resize(nb);
         check_cuda(cudaMemcpyAsync(R.shift.data(), d_shift, sizeof(double) * nb, cudaMemcpyDeviceToHost, s), "shift readback");
     }
-    check_cuda(cudaStreamSynchronize(s), "svd sync");
+    if(host_sigma || shifted) check_cuda(cudaStreamSynchronize(s), "svd sync");
     if(svd_prof) {
         unsigned long long h[8];
         check_cuda(cudaMemcpy(h, d_tprof, sizeof(h), cudaMemcpyDeviceToHost), "svd prof readback");
@@ -1249,18 +1256,37 @@ void free_jacobi(Context& ctx, JacobiResult& R)
 {
     if(R.d_W) cudaFreeAsync(R.d_W, ctx.stream);
     if(R.d_V) cudaFreeAsync(R.d_V, ctx.stream);
-    R.d_W = R.d_V = nullptr;
+    if(R.d_sigma) cudaFreeAsync(R.d_sigma, ctx.stream);
+    R.d_W = R.d_V = R.d_sigma = nullptr;
 }
-
-}   // namespace
 
 // ------------------------------------------------------------------------------------------------ tSVD
 SvdResult Context::tsvd(const Tensor& t, int64_t max_keep, double eps_svd, bool preserve_multiplets)
 {
+    if(t.layout->sector.empty()) throw std::invalid_argument("tSVD: tensor has no blocks");
+    SvdResult res;
+    if(tsvd_truncated(t, max_keep, eps_svd, preserve_multiplets, &res)) return res;
+    return tsvd_full(t, max_keep, eps_svd, preserve_multiplets);
+}
+
+SvdResult Context::tsvd_full(const Tensor& t, int64_t max_keep, double eps_svd, bool preserve_multiplets)
+{
     const Layout& L = *t.layout;
     if(L.sector.empty()) throw std::invalid_argument("tSVD: tensor has no blocks");
     ProfScope prof(*this, CAT_SVD, 0.0);
-    JacobiResult J = jacobi_all(*this, t, false);
+    int64_t n_sv = 0;
+    for(size_t i = 0; i < L.sector.size(); ++i) n_sv += std::min(L.rows[i], L.cols[i]);
+    if(n_sv == 0) throw std::invalid_argument("tSVD: tensor has no singular values");
+    static const bool host_select = std::getenv("XB_SVD_HOSTSELECT") != nullptr;
+    if(!host_select && svd_device_select_supported(n_sv, static_cast<int>(L.sector.size()))) {
+        // singular values stay on the device: sort / truncation there, one small read-back (kept counts, truncWeight, entropy)
+        JacobiResult Jd = jacobi_all(*this, jacobi_input(t), false, false);
+        SvdResult r = svd_full_device_select(*this, t, Jd, max_keep, eps_svd, preserve_multiplets);
+        free_jacobi(*this, Jd);
+        return r;
+    }
+    // more values than the shared-memory sort holds: truncation decision on the host
+    JacobiResult J = jacobi_all(*this, jacobi_input(t), false, true);
     struct SV { int sector; int col; int k; double s; };
     std::vector<SV> all;
     for(size_t i = 0; i < L.sector.size(); ++i) {
@@ -1386,7 +1412,7 @@ void Context::teigh(const Tensor& t, Tensor** Do, Tensor** Vo)
         return;
     }
     ProfScope prof(*this, CAT_SVD, 0.0);
-    JacobiResult J = jacobi_all(*this, t, true);
+    JacobiResult J = jacobi_all(*this, jacobi_input(t), true, true);
     std::vector<EighCol> cols;
     for(size_t i = 0; i < L.sector.size(); ++i) {
         const SvdBlock& b = J.blocks[i];
@@ -1425,7 +1451,7 @@ void Context::teigh(const Tensor& t, Tensor** Do, Tensor** Vo)
 // R's diagonal signs equal the reference's; the trailing update is spread over the CTA's warps (one column per warp,
 // lanes along the contiguous rows).  All blocks of a tensor run concurrently in one launch.
 namespace {
-struct QrBlock { long long a_off, q_off, r_off, w_off; int m, n; };
+struct QrBlock { long long a_off, q_off, r_off, w_off, t_off; int m, n, mid, lq; };
 
 __device__ double block_sum(double v, double* sm)
 {
@@ -1446,7 +1472,8 @@ qr_householder_kernel(const double* __restrict__ A, double* __restrict__ W, doub
     const QrBlock d = blocks[blockIdx.x];
     const int m = d.m, n = d.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     double* __restrict__ w = W + d.w_off;       // m x n work copy, column-major
-    double* __restrict__ tau = taus + d.r_off;   // scratch slotted like R (n*n >= min(m, n) scalars per block)
+    const int mid = d.mid;                         // inner dimension of the middle basis in this sector (Tensor.cpp:760)
+    double* __restrict__ tau = taus + d.t_off;   // min(m, n) scalars per block
     const long long cnt = static_cast<long long>(m) * n;
     for(long long e = tid; e < cnt; e += blockDim.x) w[e] = A[d.a_off + e];
     __syncthreads();
@@ -1484,11 +1511,12 @@ qr_householder_kernel(const double* __restrict__ A, double* __restrict__ W, doub
         }
         __syncthreads();
     }
-    // R = 1(n x m) * R_full : n x n, rows >= min(m, n) are zero
+    // R = 1(mid x m) * R_full : mid x n, rows >= min(m, n) are zero (the reference's 1(n x m) R_full whenever the middle basis is the codomain)
     double* __restrict__ R = Ro + d.r_off;
     double* __restrict__ Q = Qo + d.q_off;
-    // Q = H_1 ... H_k * 1(m x n)  (dorg2r recurrence, backwards), built directly in the output block
-    for(long long e = tid; e < cnt; e += blockDim.x) {
+    // Q = H_1 ... H_k * 1(m x mid)  (dorg2r recurrence, backwards), built directly in the output block
+    const long long qcnt = static_cast<long long>(m) * mid;
+    for(long long e = tid; e < qcnt; e += blockDim.x) {
         const int r = static_cast<int>(e % m), c = static_cast<int>(e / m);
         Q[e] = (r == c) ? 1.0 : 0.0;
     }
@@ -1498,7 +1526,7 @@ qr_householder_kernel(const double* __restrict__ A, double* __restrict__ W, doub
         if(tj == 0.0) continue;   // uniform across the CTA
         const double* __restrict__ x = w + j + static_cast<long long>(j) * m;
         const int len = m - j;
-        for(int k = j + warp; k < n; k += nwarp) {
+        for(int k = j + warp; k < mid; k += nwarp) {
             double* __restrict__ c = Q + j + static_cast<long long>(k) * m;
             double dot = lane == 0 ? c[0] : 0.0;
             for(int r = 1 + lane; r < len; r += 32) dot = fma(x[r], c[r], dot);
@@ -1509,24 +1537,46 @@ qr_householder_kernel(const double* __restrict__ A, double* __restrict__ W, doub
         }
         __syncthreads();
     }
-    for(long long e = tid; e < static_cast<long long>(n) * n; e += blockDim.x) {
-        const int r = static_cast<int>(e % n), c = static_cast<int>(e / n);
-        R[e] = (r <= c && r < m) ? w[r + static_cast<long long>(c) * m] : 0.0;
+    if(!d.lq) {
+        for(long long e = tid; e < static_cast<long long>(mid) * n; e += blockDim.x) {
+            const int r = static_cast<int>(e % mid), c = static_cast<int>(e / mid);
+            R[e] = (r <= c && r < m) ? w[r + static_cast<long long>(c) * m] : 0.0;
+        }
+    } else {
+        // RETURN_LQ (Tensor.cpp:767-769): the adjoints of both factors; only reached for square blocks (m == n == mid)
+        for(long long e = tid; e < static_cast<long long>(n) * n; e += blockDim.x) {
+            const int r = static_cast<int>(e % n), c = static_cast<int>(e / n);
+            R[e] = (c <= r) ? w[c + static_cast<long long>(r) * m] : 0.0;   // R^T: lower triangular
+        }
+        for(long long e = tid; e < qcnt; e += blockDim.x) {   // in-place transpose of the square Q
+            const int r = static_cast<int>(e % m), c = static_cast<int>(e / m);
+            if(r < c) {
+                const double a = Q[r + static_cast<long long>(c) * m], b = Q[c + static_cast<long long>(r) * m];
+                Q[r + static_cast<long long>(c) * m] = b;
+                Q[c + static_cast<long long>(r) * m] = a;
+            }
+        }
     }
 }
 }   // namespace
 
-void Context::tqr(const Tensor& t, Tensor** Qo, Tensor** Ro)
+// Tensor::tQR(RETURN_LQ) (src/Core/Tensor.cpp:757-780).  The reference multiplies the full Householder factors by 1(m x n) / 1(n x m), which gives blocks
+// that fit the bases of Q (domain -> middle) and R (middle -> codomain) only when the middle basis is the coupled codomain; here the
+// identities are 1(m x mid) / 1(mid x m) with mid = middle.inner_dim(q): the same matrices whenever the reference's are consistent, and
+// Q (m x m, orthogonal) / R (m x n, upper trapezoidal) when the middle basis is the coupled domain.  RETURN_LQ returns the adjoint blocks
+// (Q^T, R^T) like the reference; they fit the bases only for square blocks, anything else is XB_ERR_INVALID.
+void Context::tqr(const Tensor& t, bool return_lq, Tensor** Qo, Tensor** Ro)
 {
     const Layout& L = *t.layout;
     const bool tall = L.cdom->dim() > L.ccod->dim();
     BasisPtr middle = tall ? L.ccod->forget_history() : L.cdom->forget_history();   // Tensor.cpp:760
-    for(size_t i = 0; i < L.sector.size(); ++i)
-        if(middle->inner_dim(L.sector[i]) != L.cols[i])
-            throw std::invalid_argument("tQR: a sector block is wider than tall while the middle basis is the domain -- the reference builds inconsistent "
-                                        "factors in this case (Tensor.cpp:766-776); permute the tensor so that every block has rows >= cols");
+    if(return_lq)
+        for(size_t i = 0; i < L.sector.size(); ++i)
+            if(L.rows[i] != L.cols[i])
+                throw std::invalid_argument("tQR(RETURN_LQ): the adjoint factors of a non-square sector block do not fit the bases of the result "
+                                            "(the reference builds inconsistent tensors in this case, Tensor.cpp:767-769)");
     LayoutPtr LQ = layout_custom(L.dom, {middle}, L.sector), LR = layout_custom({middle}, L.cod, L.sector);
-    std::unique_ptr<Tensor> Q(new Tensor(this, LQ, false)), R(new Tensor(this, LR, true));
+    std::unique_ptr<Tensor> Q(new Tensor(this, LQ, true)), R(new Tensor(this, LR, true));
     const int nb = static_cast<int>(L.sector.size());
     if(nb == 0 || L.size == 0) {
         *Qo = Q.release();
@@ -1534,6 +1584,7 @@ void Context::tqr(const Tensor& t, Tensor** Qo, Tensor** Ro)
         return;
     }
     std::vector<QrBlock> blocks;
+    long long toff = 0;
     for(int i = 0; i < nb; ++i) {
         if(L.rows[i] == 0 || L.cols[i] == 0) continue;
         QrBlock b;
@@ -1541,15 +1592,19 @@ void Context::tqr(const Tensor& t, Tensor** Qo, Tensor** Ro)
         b.q_off = LQ->off[i];
         b.r_off = LR->off[i];
         b.w_off = L.off[i];
+        b.t_off = toff;
         b.m = static_cast<int>(L.rows[i]);
         b.n = static_cast<int>(L.cols[i]);
+        b.mid = static_cast<int>(middle->inner_dim(L.sector[i]));
+        b.lq = return_lq ? 1 : 0;
+        toff += std::min(b.m, b.n);
         blocks.push_back(b);
     }
     ProfScope prof(*this, CAT_OTHER, 0.0);
     double *d_W = nullptr, *d_tau = nullptr;
     QrBlock* d_blocks = nullptr;
     check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_W), sizeof(double) * L.size, stream), "tQR work");
-    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_tau), sizeof(double) * std::max<int64_t>(LR->size, 1), stream), "tQR tau");
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_tau), sizeof(double) * std::max<long long>(toff, 1), stream), "tQR tau");
     check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_blocks), sizeof(QrBlock) * blocks.size(), stream), "tQR meta");
     upload_async(d_blocks, blocks.data(), sizeof(QrBlock) * blocks.size());
     qr_householder_kernel<<<static_cast<unsigned>(blocks.size()), 256, 0, stream>>>(t.d, d_W, Q->d, R->d, d_tau, d_blocks);

@@ -49,16 +49,19 @@ Tensor* Context::copy(const Tensor& t)
 }
 
 // ------------------------------------------------------------------------------------------------ grouped GEMM launcher
-void Context::run_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems)
+PreparedGemm Context::prepare_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems)
 {
+    PreparedGemm P;
+    P.A = A;
+    P.B = B;
+    P.C = C;
     std::vector<GemmItem> items[2];   // [0]: 128 x 64 tiles (sectors with m > 96), [1]: 64 x 64 tiles
     std::vector<SplitKJob> jobs;      // problems with few tiles and a long K: K is cut into slices, the partial products are summed afterwards
     long long scratch_elems = 0;
-    double flops = 0.0;
     static const bool no_split = std::getenv("XB_GEMM_NOSPLIT") != nullptr;
     for(GemmItem g : problems) {
         if(g.m <= 0 || g.n <= 0) continue;
-        flops += 2.0 * g.m * static_cast<double>(g.n) * g.k;
+        P.flops += 2.0 * g.m * static_cast<double>(g.n) * g.k;
         const int which = g.m > 96 ? 0 : 1, tile_m = which == 0 ? 128 : 64;
         const int ntiles = ((g.m + tile_m - 1) / tile_m) * ((g.n + GEMM_TILE_N - 1) / GEMM_TILE_N);
         int split = 1;
@@ -100,7 +103,7 @@ void Context::run_gemm(const double* A, const double* B, double* C, const std::v
                 items[which].push_back(g);
             }
     }
-    if(items[0].empty() && items[1].empty()) return;
+    if(items[0].empty() && items[1].empty()) return P;
     static const bool gemm_log = std::getenv("XB_GEMM_LOG") != nullptr;
     if(gemm_log) {
         int mm = 0, mn = 0, mk = 0;
@@ -109,15 +112,13 @@ void Context::run_gemm(const double* A, const double* B, double* C, const std::v
             mn = std::max(mn, g.n);
             mk = std::max(mk, g.k);
         }
-        std::fprintf(stderr, "[gemm] problems %zu flops %.3e max(m,n,k) = (%d,%d,%d) tiles128 %zu tiles64 %zu split-K jobs %zu\n", problems.size(), flops, mm, mn, mk,
+        std::fprintf(stderr, "[gemm] problems %zu flops %.3e max(m,n,k) = (%d,%d,%d) tiles128 %zu tiles64 %zu split-K jobs %zu\n", problems.size(), P.flops, mm, mn, mk,
                      items[0].size(), items[1].size(), jobs.size());
     }
-    ProfScope prof(*this, CAT_GEMM, flops);
-    double* d_scratch = nullptr;
     long long rebase = 0;
     if(scratch_elems > 0) {
-        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_scratch), sizeof(double) * scratch_elems, stream), "cudaMallocAsync split-K scratch");
-        rebase = (reinterpret_cast<intptr_t>(d_scratch) - reinterpret_cast<intptr_t>(C)) / static_cast<intptr_t>(sizeof(double));   // both 256-byte aligned
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&P.d_scratch), sizeof(double) * scratch_elems, stream), "cudaMallocAsync split-K scratch");
+        rebase = (reinterpret_cast<intptr_t>(P.d_scratch) - reinterpret_cast<intptr_t>(C)) / static_cast<intptr_t>(sizeof(double));   // both 256-byte aligned
     }
     for(int which = 0; which < 2; ++which) {
         auto& v = items[which];
@@ -129,22 +130,44 @@ void Context::run_gemm(const double* A, const double* B, double* C, const std::v
             }
         // heavy tiles first: k is the per-tile cost
         std::stable_sort(v.begin(), v.end(), [](const GemmItem& x, const GemmItem& y) { return x.k > y.k; });
-        GemmItem* d_items = nullptr;
-        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_items), v.size() * sizeof(GemmItem), stream), "cudaMallocAsync gemm items");
-        upload_async(d_items, v.data(), v.size() * sizeof(GemmItem));
-        launch_gemm_grouped(A, B, C, d_items, static_cast<int>(v.size()), which == 0 ? 128 : 64, stream);
-        check_cuda(cudaFreeAsync(d_items, stream), "cudaFreeAsync gemm items");
-        ++launches;
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&P.d_items[which]), v.size() * sizeof(GemmItem), stream), "cudaMallocAsync gemm items");
+        upload_async(P.d_items[which], v.data(), v.size() * sizeof(GemmItem));
+        P.n_items[which] = static_cast<int>(v.size());
+        ++P.launches;
     }
     if(!jobs.empty()) {
-        SplitKJob* d_jobs = nullptr;
-        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_jobs), jobs.size() * sizeof(SplitKJob), stream), "cudaMallocAsync split-K jobs");
-        upload_async(d_jobs, jobs.data(), jobs.size() * sizeof(SplitKJob));
-        launch_splitk_reduce(d_scratch, C, d_jobs, static_cast<int>(jobs.size()), stream);
-        check_cuda(cudaFreeAsync(d_jobs, stream), "cudaFreeAsync split-K jobs");
-        check_cuda(cudaFreeAsync(d_scratch, stream), "cudaFreeAsync split-K scratch");
-        ++launches;
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&P.d_jobs), jobs.size() * sizeof(SplitKJob), stream), "cudaMallocAsync split-K jobs");
+        upload_async(P.d_jobs, jobs.data(), jobs.size() * sizeof(SplitKJob));
+        P.n_jobs = static_cast<int>(jobs.size());
+        ++P.launches;
     }
+    return P;
+}
+
+void Context::launch_gemm(const PreparedGemm& P)
+{
+    if(P.launches == 0) return;
+    ProfScope prof(*this, CAT_GEMM, P.flops);
+    for(int which = 0; which < 2; ++which)
+        if(P.n_items[which] > 0) launch_gemm_grouped(P.A, P.B, P.C, P.d_items[which], P.n_items[which], which == 0 ? 128 : 64, stream);
+    if(P.n_jobs > 0) launch_splitk_reduce(P.d_scratch, P.C, P.d_jobs, P.n_jobs, stream);
+    launches += P.launches;
+}
+
+void Context::free_gemm(PreparedGemm& P)
+{
+    for(int which = 0; which < 2; ++which)
+        if(P.d_items[which]) check_cuda(cudaFreeAsync(P.d_items[which], stream), "cudaFreeAsync gemm items");
+    if(P.d_jobs) check_cuda(cudaFreeAsync(P.d_jobs, stream), "cudaFreeAsync split-K jobs");
+    if(P.d_scratch) check_cuda(cudaFreeAsync(P.d_scratch, stream), "cudaFreeAsync split-K scratch");
+    P = PreparedGemm();
+}
+
+void Context::run_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems)
+{
+    PreparedGemm P = prepare_gemm(A, B, C, problems);
+    launch_gemm(P);
+    free_gemm(P);
 }
 
 // ------------------------------------------------------------------------------------------------ operator*

@@ -1,0 +1,1016 @@
+// tSVD drivers: device-wide singular-value sort + global truncation (Tensor::tSVD, src/Core/Tensor.cpp:543-598) and the
+// truncated algorithm used when only a few singular values out of many are kept (CTM projectors: chi of ~10^4).
+//
+// 1. svd_select_kernel -- ONE CTA sorts the singular values of all sectors (bitonic network in shared memory, <= 16384 values),
+//    applies the reference's truncation rules (keep the maxKeep largest, drop values < eps_svd, PRESERVE_MULTIPLETS, never return an
+//    empty basis), accumulates truncWeight and the entropy, and writes per sector the kept count and the column order.  The host
+//    reads back one small record (kept counts, two scalars) to build the output bases; the gather kernel takes the column
+//    lists from device memory.
+// 2. Context::tsvd_truncated -- randomized block subspace iteration per sector (all sectors batched in every launch):
+//       X <- orth(B^T orth(B X))  with B_q the tall orientation of the sector block and X_q of width K = maxKeep + 32 (<= 160),
+//    orthonormalisation by (shifted) Cholesky-QR on grouped DMMA GEMMs, then the batched one-sided Jacobi SVD of the projected
+//    blocks Y_q = B_q X_q (tall, K columns) gives Ritz triplets.  A-posteriori check on the device: the residuals
+//    ||B^T u - sigma v|| of every kept triplet (<= 16 eps sqrt(m) sigma_max), and at least 8 Ritz values below the cut in every
+//    projected sector (the cut lies inside the computed part of each spectrum).  Not satisfied => more iterations (count predicted
+//    from the Ritz spectrum), and if the budget is exhausted the caller falls back to the full Jacobi path.  Sectors with
+//    min(m, n) <= K are decomposed exactly (X = 1).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <stdexcept>
+
+#include "engine.hpp"
+#include "svd_internal.hpp"
+
+namespace xb {
+
+namespace {
+
+constexpr int SEL_THREADS = 1024;
+constexpr int SEL_MAX = 16384;   // capacity of the shared-memory sort
+constexpr int SEL_COL_BITS = 14;
+constexpr int NORM_PARTS = 32;
+
+struct SelSector
+{
+    long long s_off;   // first singular value of the sector in the sigma array
+    int count;
+    int direct;        // 1: exact values (no residual / exhaustion check)
+    double deg;        // Symmetry::degeneracy(q)
+};
+
+struct SelParams
+{
+    long long max_keep;
+    double eps_svd;
+    double tol_rel;   // residual tolerance relative to sigma_max (ritz mode)
+    int preserve, ritz, nsec, n_total, guard, pad;
+};
+
+struct SelHeader
+{
+    int nkeep, verdict, nkeep0, pad;
+    double trunc_weight, entropy, cut, max_res, rate, smax;
+};
+
+__device__ __forceinline__ bool before_a(double ka, int pa, double kb, int pb)
+{   // (sector asc, sigma desc, column asc)
+    const int sa = pa >> SEL_COL_BITS, sb = pb >> SEL_COL_BITS;
+    if(sa != sb) return sa < sb;
+    if(ka != kb) return ka > kb;
+    return pa < pb;
+}
+__device__ __forceinline__ bool before_b(double ka, int pa, double kb, int pb)
+{   // (sigma desc, sector asc, rank inside the sector asc)
+    if(ka != kb) return ka > kb;
+    return pa < pb;
+}
+
+template <bool MODE_A> __device__ void bitonic_sort(double* key, int* pay, int N)
+{
+    for(int k = 2; k <= N; k <<= 1) {
+        for(int j = k >> 1; j > 0; j >>= 1) {
+            for(int i = threadIdx.x; i < N; i += blockDim.x) {
+                const int x = i ^ j;
+                if(x > i) {
+                    const double ki = key[i], kx = key[x];
+                    const int pi = pay[i], px = pay[x];
+                    const bool up = (i & k) == 0;
+                    const bool x_first = MODE_A ? before_a(kx, px, ki, pi) : before_b(kx, px, ki, pi);
+                    if(x_first == up) {
+                        key[i] = kx;
+                        key[x] = ki;
+                        pay[i] = px;
+                        pay[x] = pi;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ double block_sum_det(double v, double* red)
+{   // deterministic: fixed tree
+    for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if(threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for(int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if(threadIdx.x == 0) red[32] = s;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+svd_select_kernel(const double* __restrict__ sigma, const SelSector* __restrict__ secs, const double* __restrict__ res, const double* __restrict__ normpart,
+                  SelParams P, int N, int* __restrict__ perm, SelHeader* __restrict__ hdr, int* __restrict__ kept)
+{
+    extern __shared__ __align__(16) unsigned char raw[];
+    double* key = reinterpret_cast<double*>(raw);
+    double* red = key + N;                               // 40
+    int* pay = reinterpret_cast<int*>(red + 40);         // N
+    int* soff = pay + N;                                 // nsec + 1
+    int* cnt1 = soff + P.nsec + 1;                       // entries of each sector among the first nkeep1 (count + eps filter)
+    int* cnt2 = cnt1 + P.nsec;                           // kept entries of each sector
+    __shared__ int sh_i[8];
+    const int tid = threadIdx.x, T = blockDim.x, n = P.n_total;
+
+    for(int q = tid; q < P.nsec; q += T) {
+        soff[q] = static_cast<int>(secs[q].s_off);
+        cnt1[q] = 0;
+        cnt2[q] = 0;
+    }
+    if(tid == 0) soff[P.nsec] = n;
+    __syncthreads();
+    for(int i = tid; i < N; i += T) {
+        if(i < n) {
+            int lo = 0, hi = P.nsec;   // last sector with soff <= i
+            while(hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if(soff[mid] <= i) lo = mid; else hi = mid;
+            }
+            // empty sectors share an offset with their successor: move to the last one starting at soff[lo]
+            key[i] = sigma[i];
+            pay[i] = (lo << SEL_COL_BITS) | (i - soff[lo]);
+        } else {
+            key[i] = -1.0;
+            pay[i] = INT_MAX;
+        }
+    }
+    __syncthreads();
+    bitonic_sort<true>(key, pay, N);
+    // per-sector descending order: position p <-> (sector, k = p - soff); remember the column of every (sector, k)
+    for(int p = tid; p < n; p += T) {
+        const int sec = pay[p] >> SEL_COL_BITS, col = pay[p] & ((1 << SEL_COL_BITS) - 1);
+        perm[p] = col;
+        pay[p] = (sec << SEL_COL_BITS) | (p - soff[sec]);
+    }
+    __syncthreads();
+    bitonic_sort<false>(key, pay, N);
+
+    const int nkeep0 = static_cast<int>(P.max_keep < 0 ? 0 : (P.max_keep < n ? P.max_keep : n));
+    if(tid == 0) {
+        // numerically tied values (<= 1e-12 relative) around the cut are ordered by (sector, k): the decision does not depend on rounding noise
+        if(nkeep0 > 0 && nkeep0 < n && key[nkeep0 - 1] - key[nkeep0] <= 1.e-12 * key[nkeep0 - 1]) {
+            int i = nkeep0 - 1, j = nkeep0 + 1;
+            while(i > 0 && key[i - 1] - key[i] <= 1.e-12 * key[i - 1]) --i;
+            while(j < n && key[j - 1] - key[j] <= 1.e-12 * key[i]) ++j;
+            for(int a = i + 1; a < j; ++a) {
+                const double ka = key[a];
+                const int pa = pay[a];
+                int b = a - 1;
+                while(b >= i && pay[b] > pa) {
+                    key[b + 1] = key[b];
+                    pay[b + 1] = pay[b];
+                    --b;
+                }
+                key[b + 1] = ka;
+                pay[b + 1] = pa;
+            }
+        }
+        // eps filter (Tensor.cpp:551-557): the dropped values are the tail of the first nkeep0
+        int lo = 0, hi = nkeep0;   // first position with key < eps
+        if(P.eps_svd > 0.0) {
+            while(lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if(key[mid] < P.eps_svd) hi = mid; else lo = mid + 1;
+            }
+        } else
+            lo = nkeep0;
+        sh_i[0] = lo;    // nkeep1
+        sh_i[1] = -1;    // end of multiplet
+    }
+    __syncthreads();
+    const int nkeep1 = sh_i[0];
+    if(P.preserve) {   // Tensor.cpp:569-584: cut at the last gap > 0.1 (relative)
+        int best = -1;
+        for(int i = tid + 1; i < nkeep1; i += T) {
+            const double rel = 2.0 * (key[i - 1] - key[i]) / (key[i - 1] + key[i]);
+            if(rel > 0.1) best = i;
+        }
+        if(best >= 0) atomicMax(&sh_i[1], best);
+        __syncthreads();
+    }
+    int nkeep = (P.preserve && sh_i[1] != -1) ? sh_i[1] : nkeep1;
+    for(int p = tid; p < nkeep1; p += T) {
+        const int sec = pay[p] >> SEL_COL_BITS;
+        atomicAdd(&cnt1[sec], 1);
+        if(p < nkeep) atomicAdd(&cnt2[sec], 1);
+    }
+    // truncWeight (Tensor.cpp:548): everything beyond the first maxKeep values
+    double tw = 0.0, ent = 0.0;
+    if(P.ritz) {
+        for(int p = tid; p < nkeep0; p += T) tw -= secs[pay[p] >> SEL_COL_BITS].deg * key[p] * key[p];
+        for(int q = tid; q < P.nsec; q += T) {
+            double tot = 0.0;
+            for(int k = 0; k < NORM_PARTS; ++k) tot += normpart[q * NORM_PARTS + k];
+            tw += secs[q].deg * tot;
+        }
+    } else {
+        for(int p = nkeep0 + tid; p < n; p += T) tw += secs[pay[p] >> SEL_COL_BITS].deg * key[p] * key[p];
+    }
+    tw = block_sum_det(tw, red);
+    if(nkeep == 0 && n > 0) {   // Tensor.cpp:586-590: keep the first entry of the unsorted list = largest value of the first non-empty sector
+        if(tid == 0) {
+            int q0 = 0;
+            while(q0 < P.nsec && secs[q0].count == 0) ++q0;
+            cnt2[q0] = 1;
+            const double s = sigma[soff[q0] + perm[soff[q0]]];
+            sh_i[2] = q0;
+            red[33] = -secs[q0].deg * s * s * log(s * s);
+        }
+        __syncthreads();
+        ent = red[33];
+        nkeep = 1;
+    } else {
+        for(int p = tid; p < nkeep; p += T) {
+            const double s = key[p];
+            ent += -secs[pay[p] >> SEL_COL_BITS].deg * s * s * log(s * s);
+        }
+        ent = block_sum_det(ent, red);
+    }
+    __syncthreads();
+    // a-posteriori check of Ritz triplets
+    int verdict = 0;
+    double max_res = 0.0, rate = 0.0;
+    const double smax = n > 0 ? key[0] : 0.0;
+    const double cutref = nkeep1 > 0 ? key[nkeep1 - 1] : smax;
+    if(P.ritz) {
+        double mr = 0.0;
+        const int ncheck = min(n, nkeep1 + 2);
+        for(int p = tid; p < ncheck; p += T) {
+            const int sec = pay[p] >> SEL_COL_BITS, k = pay[p] & ((1 << SEL_COL_BITS) - 1);
+            if(secs[sec].direct) continue;
+            const double r = res[soff[sec] + perm[soff[sec] + k]];
+            if(p < nkeep1)
+                mr = fmax(mr, r);
+            else if(r > 1.e-3 * cutref)
+                mr = fmax(mr, 1.e300);   // a discarded value next to the cut that is far from converged could still overtake it
+        }
+        // max via ordered-int trick is unnecessary: reduce with fmax (order independent)
+        for(int o = 16; o > 0; o >>= 1) mr = fmax(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+        __syncthreads();
+        if((tid & 31) == 0) red[tid >> 5] = mr;
+        __syncthreads();
+        if(tid == 0) {
+            double m = 0.0;
+            for(int w = 0; w < (T >> 5); ++w) m = fmax(m, red[w]);
+            red[34] = m;
+            double rt = 0.0;
+            int exhausted = 0;
+            for(int q = 0; q < P.nsec; ++q) {
+                if(secs[q].direct || secs[q].count == 0) continue;
+                if(secs[q].count - cnt1[q] < P.guard) exhausted = 1;
+                const double smin = sigma[soff[q] + perm[soff[q] + secs[q].count - 1]];
+                rt = fmax(rt, cutref > 0.0 ? smin / cutref : 1.0);
+            }
+            red[35] = rt;
+            sh_i[3] = exhausted;
+        }
+        __syncthreads();
+        max_res = red[34];
+        rate = red[35];
+        if(!(max_res <= P.tol_rel * smax)) verdict |= 1;
+        if(sh_i[3]) verdict |= 2;
+    }
+    for(int q = tid; q < P.nsec; q += T) kept[q] = cnt2[q];
+    if(tid == 0) {
+        hdr->nkeep = nkeep;
+        hdr->verdict = verdict;
+        hdr->nkeep0 = nkeep0;
+        hdr->pad = 0;
+        hdr->trunc_weight = tw < 0.0 ? 0.0 : tw;
+        hdr->entropy = ent;
+        hdr->cut = cutref;
+        hdr->max_res = smax > 0.0 ? max_res / smax : 0.0;
+        hdr->rate = rate;
+        hdr->smax = smax;
+    }
+}
+
+struct GatherSec
+{
+    long long w_off, v_off, u_dst, vd_dst, s_dst, sel_off;
+    int wl, vl, ldw, ldv, nret, w_is_u;
+};
+
+// writes the kept columns: U (or V^dagger rows) from W / sigma, the other factor from V, Sigma on the diagonal
+__global__ void svd_gather_sel_kernel(const double* __restrict__ W, const double* __restrict__ V, const double* __restrict__ sigma, const int* __restrict__ perm,
+                                      double* __restrict__ U, double* __restrict__ S, double* __restrict__ Vd, const GatherSec* __restrict__ secs)
+{
+    const GatherSec g = secs[blockIdx.y];
+    for(int r = blockIdx.x; r < g.nret; r += gridDim.x) {
+        const int col = perm[g.sel_off + r];
+        const double sg = sigma[g.sel_off + col];
+        const double inv = sg > 0.0 ? 1.0 / sg : 0.0;
+        const double* w = W + g.w_off + static_cast<long long>(col) * g.ldw;
+        const double* v = V + g.v_off + static_cast<long long>(col) * g.ldv;
+        if(g.w_is_u) {
+            for(int i = threadIdx.x; i < g.wl; i += blockDim.x) U[g.u_dst + static_cast<long long>(r) * g.wl + i] = w[i] * inv;
+            for(int i = threadIdx.x; i < g.vl; i += blockDim.x) Vd[g.vd_dst + r + static_cast<long long>(i) * g.nret] = v[i];
+        } else {
+            for(int i = threadIdx.x; i < g.vl; i += blockDim.x) U[g.u_dst + static_cast<long long>(r) * g.vl + i] = v[i];
+            for(int i = threadIdx.x; i < g.wl; i += blockDim.x) Vd[g.vd_dst + r + static_cast<long long>(i) * g.nret] = w[i] * inv;
+        }
+        if(threadIdx.x == 0) S[g.s_dst + r + static_cast<long long>(r) * g.nret] = sg;
+    }
+}
+
+// ---- pieces of the truncated path --------------------------------------------------------------------------------------------
+struct RsvdSec
+{
+    long long a_off, x_off, y_off, g_off, s_off;
+    int m, n, tr, mb, nb, K, direct, pad;
+};
+
+__global__ void rsvd_identity_kernel(double* __restrict__ X, const RsvdSec* __restrict__ secs, const int* __restrict__ list, int nlist)
+{
+    const RsvdSec s = secs[list[blockIdx.y]];
+    const long long cnt = static_cast<long long>(s.nb) * s.K;
+    for(long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < cnt; e += static_cast<long long>(gridDim.x) * blockDim.x)
+        X[s.x_off + e] = (e % s.nb == e / s.nb) ? 1.0 : 0.0;
+}
+
+// partial squared Frobenius norms of the sector blocks (fixed partition => deterministic)
+__global__ void rsvd_norm2_kernel(const double* __restrict__ A, const RsvdSec* __restrict__ secs, double* __restrict__ part)
+{
+    __shared__ double sm[33];
+    const RsvdSec s = secs[blockIdx.y];
+    const long long cnt = static_cast<long long>(s.m) * s.n;
+    const long long chunk = (cnt + gridDim.x - 1) / gridDim.x;
+    const long long e0 = chunk * blockIdx.x, e1 = e0 + chunk < cnt ? e0 + chunk : cnt;
+    double v = 0.0;
+    for(long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) v = fma(A[s.a_off + e], A[s.a_off + e], v);
+    for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        double t = 0.0;
+        for(int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += sm[w];
+        part[blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+// Cholesky factor of the Gram matrix G (K x K, + shift_rel * max diag) and M = L^-T (upper triangular) so that Y M has orthonormal
+// columns.  One CTA per projected sector; the matrix lives in shared memory (pitch K + 1).  diag[sector] = min pivot / max diagonal
+// (~ 1 / cond^2 of the basis); a non-positive pivot sets *bad (the pass is then not an orthonormalisation).
+constexpr int CHOL_THREADS = 1024;
+__global__ void __launch_bounds__(CHOL_THREADS)
+rsvd_chol_kernel(const double* __restrict__ G, double* __restrict__ M, const RsvdSec* __restrict__ secs, const int* __restrict__ list, double shift_rel,
+                 double* __restrict__ diag, int* __restrict__ bad)
+{
+    extern __shared__ __align__(16) double csm[];
+    const int sec = list[blockIdx.x];
+    const RsvdSec s = secs[sec];
+    const int K = s.K, ld = K + 1, tid = threadIdx.x, T = blockDim.x;
+    double* S = csm;              // K x K, pitch ld (lower triangle used)
+    double* dl = csm + ld * K;    // diagonal of L
+    __shared__ double sh_max, sh_minpiv;
+    __shared__ int sh_bad;
+    const double* g = G + s.g_off;
+    for(int e = tid; e < K * K; e += T) {
+        const int i = e % K, j = e / K;
+        S[i + j * ld] = g[e];
+    }
+    if(tid == 0) {
+        sh_bad = 0;
+        sh_minpiv = 1.e300;
+    }
+    __syncthreads();
+    if(tid < 32) {
+        double m = 0.0;
+        for(int j = tid; j < K; j += 32) m = fmax(m, S[j + j * ld]);
+        for(int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if(tid == 0) sh_max = m;
+    }
+    __syncthreads();
+    const double gmax = sh_max > 0.0 ? sh_max : 1.0;
+    const double shift = shift_rel * gmax;
+    for(int j = 0; j < K; ++j) {
+        double d = S[j + j * ld] + shift;
+        bool isbad = false;
+        if(!(d > 0.0) || !isfinite(d)) {
+            isbad = true;
+            d = gmax * 1.e-30;
+        }
+        const double ljj = sqrt(d), inv = 1.0 / ljj;
+        if(tid == 0) {
+            dl[j] = ljj;
+            if(isbad) sh_bad = 1;
+            sh_minpiv = fmin(sh_minpiv, d / gmax);
+        }
+        __syncthreads();   // everybody has read the pivot
+        for(int i = j + 1 + tid; i < K; i += T) S[i + j * ld] *= inv;
+        __syncthreads();
+        // trailing update of the lower triangle: warp w takes columns c = j + 1 + w, + 32, ...; lanes run down the column
+        for(int c = j + 1 + (tid >> 5); c < K; c += T >> 5) {
+            const double f = S[c + j * ld];
+            for(int i = c + (tid & 31); i < K; i += 32) S[i + c * ld] = fma(-S[i + j * ld], f, S[i + c * ld]);
+        }
+        __syncthreads();
+    }
+    // M(c, k) = (L^-1)(k, c): four lanes per column c of L^-1 (forward substitution, lanes split the dot products);
+    // x_c[c] = 1 / L_cc ; x_c[i] = -(sum_{k=c}^{i-1} L_ik x_c[k]) / L_ii ; stored at m_out[c + i * K].  All threads run the same trip counts.
+    double* m_out = M + s.g_off;
+    const int lane4 = tid & 3, c = tid >> 2;
+    const bool has_col = c < K;
+    if(has_col) {
+        if(lane4 == 0) m_out[c + c * K] = 1.0 / dl[c];
+        for(int i = lane4; i < c; i += 4) m_out[c + i * K] = 0.0;
+    }
+    __syncwarp(0xffffffffu);
+    for(int i = 1; i < K; ++i) {
+        double acc = 0.0;
+        if(has_col && i > c)
+            for(int k = c + lane4; k < i; k += 4) acc = fma(S[i + k * ld], m_out[c + k * K], acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if(has_col && i > c && lane4 == 0) m_out[c + i * K] = -acc / dl[i];
+        __syncwarp(0xffffffffu);
+    }
+    if(tid == 0) {
+        diag[sec] = sh_minpiv;
+        if(sh_bad) atomicOr(bad, 1);
+    }
+}
+
+// residual of the Ritz triplets: res[id] = || Zr_i - sigma_i^2 v_i || / sigma_i  with Zr = B^T W (W_i = sigma_i u_i); one warp per column
+__global__ void rsvd_residual_kernel(const double* __restrict__ Zr, const double* __restrict__ Vf, const double* __restrict__ sigma, const RsvdSec* __restrict__ secs,
+                                     const int* __restrict__ list, double* __restrict__ res)
+{
+    const RsvdSec s = secs[list[blockIdx.y]];
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for(int c = blockIdx.x * warps + warp; c < s.K; c += gridDim.x * warps) {
+        const double sg = sigma[s.s_off + c];
+        const double* z = Zr + s.x_off + static_cast<long long>(c) * s.nb;
+        const double* v = Vf + s.x_off + static_cast<long long>(c) * s.nb;
+        double acc = 0.0;
+        for(int r = lane; r < s.nb; r += 32) {
+            const double d = fma(-sg * sg, v[r], z[r]);
+            acc = fma(d, d, acc);
+        }
+        for(int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if(lane == 0) res[s.s_off + c] = sg > 0.0 ? sqrt(acc) / sg : 0.0;
+    }
+}
+
+GemmItem gemm_item(long long a_off, long long b_off, long long c_off, int m, int n, int k, int lda, int ldb, int ldc, int ta, int tb)
+{
+    GemmItem g;
+    std::memset(&g, 0, sizeof(g));
+    g.a_off = a_off;
+    g.b_off = b_off;
+    g.c_off = c_off;
+    g.m = m;
+    g.n = n;
+    g.k = k;
+    g.lda = lda;
+    g.ldb = ldb;
+    g.ldc = ldc;
+    g.ta = ta;
+    g.tb = tb;
+    g.alpha = 1.0;
+    return g;
+}
+
+struct Selection
+{
+    SelHeader hdr;
+    std::vector<int> kept;
+    int* d_perm = nullptr;   // column order per sector (device), valid until freed by the caller
+};
+
+// runs the device-wide sort / truncation; synchronises once to read the small result record
+Selection svd_select(Context& ctx, const double* d_sigma, int n_total, const std::vector<SelSector>& secs, const double* d_res, const double* d_normpart, double tol_rel,
+                     int64_t max_keep, double eps_svd, bool preserve, bool ritz)
+{
+    cudaStream_t s = ctx.stream;
+    const int nsec = static_cast<int>(secs.size());
+    Selection R;
+    int N = 2;
+    while(N < n_total) N <<= 1;
+    SelSector* d_secs = nullptr;
+    char* d_out = nullptr;   // header | kept[nsec]
+    const size_t out_bytes = sizeof(SelHeader) + sizeof(int) * nsec;
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_secs), sizeof(SelSector) * nsec, s), "svd select meta");
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_out), out_bytes, s), "svd select out");
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&R.d_perm), sizeof(int) * std::max(n_total, 1), s), "svd select perm");
+    ctx.upload_async(d_secs, secs.data(), sizeof(SelSector) * nsec);
+    SelParams P;
+    P.max_keep = max_keep;
+    P.eps_svd = eps_svd;
+    P.tol_rel = tol_rel;
+    P.preserve = preserve ? 1 : 0;
+    P.ritz = ritz ? 1 : 0;
+    P.nsec = nsec;
+    P.n_total = n_total;
+    P.guard = 8;
+    P.pad = 0;
+    const size_t smem = sizeof(double) * (N + 40) + sizeof(int) * (N + 3 * static_cast<size_t>(nsec) + 8);
+    static bool configured = false;
+    if(!configured) {
+        check_cuda(cudaFuncSetAttribute(svd_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024), "svd select smem attr");
+        configured = true;
+    }
+    svd_select_kernel<<<1, SEL_THREADS, smem, s>>>(d_sigma, d_secs, d_res, d_normpart, P, N, R.d_perm, reinterpret_cast<SelHeader*>(d_out),
+                                                  reinterpret_cast<int*>(d_out + sizeof(SelHeader)));
+    check_cuda(cudaGetLastError(), "svd_select_kernel launch");
+    ++ctx.launches;
+    char* h = static_cast<char*>(ctx.pinned(out_bytes));
+    check_cuda(cudaMemcpyAsync(h, d_out, out_bytes, cudaMemcpyDeviceToHost, s), "svd select readback");
+    check_cuda(cudaStreamSynchronize(s), "svd select sync");
+    std::memcpy(&R.hdr, h, sizeof(SelHeader));
+    R.kept.resize(nsec);
+    std::memcpy(R.kept.data(), h + sizeof(SelHeader), sizeof(int) * nsec);
+    check_cuda(cudaFreeAsync(d_secs, s), "svd select free");
+    check_cuda(cudaFreeAsync(d_out, s), "svd select free");
+    return R;
+}
+
+// per input sector: where its W / V columns live
+struct FactorSrc
+{
+    long long w_off, v_off, s_off;
+    int wl, vl, ldw, ldv, w_is_u;
+};
+
+// builds the truncated basis and the three output tensors from a selection (Tensor.cpp:592-633) and launches the gather
+SvdResult svd_finish(Context& ctx, const Layout& L, const Selection& sel, const std::vector<FactorSrc>& src, const double* d_W, const double* d_V,
+                     const double* d_sigma)
+{
+    SvdResult res;
+    res.trunc_weight = sel.hdr.trunc_weight;
+    res.entropy = sel.hdr.entropy;
+    std::map<Q, int> ordered;   // std::map => ascending qarray order
+    for(size_t i = 0; i < L.sector.size(); ++i)
+        if(sel.kept[i] > 0) ordered[L.sector[i]] = static_cast<int>(i);
+    auto trunc = std::make_shared<Qbasis>(ctx.sym, 1);
+    std::vector<Q> qs;
+    for(const auto& [q, i] : ordered) {
+        trunc->push_back(q, static_cast<int64_t>(sel.kept[i]));
+        qs.push_back(q);
+    }
+    BasisPtr tb = trunc;
+    LayoutPtr LU = ctx.layout_custom(L.dom, {tb}, qs), LS = ctx.layout_custom({tb}, {tb}, qs), LV = ctx.layout_custom({tb}, L.cod, qs);
+    res.U = new Tensor(&ctx, LU, false);
+    res.S = new Tensor(&ctx, LS, true);
+    res.Vd = new Tensor(&ctx, LV, false);
+    std::vector<GatherSec> gs;
+    int max_ret = 1;
+    for(size_t k = 0; k < qs.size(); ++k) {
+        const int i = ordered[qs[k]];
+        const FactorSrc& f = src[i];
+        GatherSec g;
+        g.w_off = f.w_off;
+        g.v_off = f.v_off;
+        g.u_dst = LU->off[k];
+        g.vd_dst = LV->off[k];
+        g.s_dst = LS->off[k];
+        g.sel_off = f.s_off;
+        g.wl = f.wl;
+        g.vl = f.vl;
+        g.ldw = f.ldw;
+        g.ldv = f.ldv;
+        g.nret = sel.kept[i];
+        g.w_is_u = f.w_is_u;
+        max_ret = std::max(max_ret, g.nret);
+        gs.push_back(g);
+    }
+    if(gs.empty()) return res;
+    GatherSec* d_gs = nullptr;
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_gs), sizeof(GatherSec) * gs.size(), ctx.stream), "svd gather meta");
+    ctx.upload_async(d_gs, gs.data(), sizeof(GatherSec) * gs.size());
+    dim3 grid(static_cast<unsigned>(std::min(max_ret, 512)), static_cast<unsigned>(gs.size()));
+    svd_gather_sel_kernel<<<grid, 128, 0, ctx.stream>>>(d_W, d_V, d_sigma, sel.d_perm, res.U->d, res.S->d, res.Vd->d, d_gs);
+    check_cuda(cudaGetLastError(), "svd_gather_sel_kernel launch");
+    ++ctx.launches;
+    check_cuda(cudaFreeAsync(d_gs, ctx.stream), "svd gather free");
+    return res;
+}
+
+}   // namespace
+
+bool svd_device_select_supported(long long n_total, int nsec) { return n_total <= SEL_MAX && nsec <= 4096; }
+
+// full path: Jacobi on every block, device-wide sort / truncation, gather
+SvdResult svd_full_device_select(Context& ctx, const Tensor& t, JacobiResult& J, int64_t max_keep, double eps_svd, bool preserve_multiplets)
+{
+    const Layout& L = *t.layout;
+    std::vector<SelSector> secs(L.sector.size());
+    std::vector<FactorSrc> src(L.sector.size());
+    for(size_t i = 0; i < L.sector.size(); ++i) {
+        const SvdBlock& b = J.blocks[i];
+        secs[i] = {b.s_off, b.cols, 1, static_cast<double>(ctx.sym->degeneracy(L.sector[i]))};
+        src[i] = {b.w_off, b.v_off, b.s_off, b.rows, b.cols, b.rows, b.cols, J.transposed[i] ? 0 : 1};
+    }
+    Selection sel = svd_select(ctx, J.d_sigma, static_cast<int>(J.n_sigma), secs, nullptr, nullptr, 0.0, max_keep, eps_svd, preserve_multiplets, false);
+    SvdResult res = svd_finish(ctx, L, sel, src, J.d_W, J.d_V, J.d_sigma);
+    check_cuda(cudaFreeAsync(sel.d_perm, ctx.stream), "svd select free");
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------ truncated tSVD
+// Everything that depends only on the layout (block shapes) and K lives in a cached plan: one device arena with fixed offsets (so that the
+// pointers baked into the captured CUDA graphs stay valid from call to call), the prepared tile lists of the grouped products, and the
+// instantiated graphs of the launch sequences (start, n iterations + polish + projection).
+struct RsvdPlan
+{
+    Context* ctx = nullptr;
+    int nsec = 0, n_proj = 0, K0 = 0, mb_max = 0, uses = 0, iters_hint = 0;
+    long long xo = 0, yo = 0, go = 0, so = 0, ao = 0;
+    std::vector<RsvdSec> secs;
+    std::vector<long long> w_off, v_off;
+    std::vector<int> proj_list, direct_list;
+    char* arena = nullptr;
+    double *dA = nullptr, *dX = nullptr, *dX2 = nullptr, *dZ = nullptr, *dY = nullptr, *dY2 = nullptr, *dG = nullptr, *dM = nullptr, *dDiag = nullptr, *dRes = nullptr,
+           *dNorm = nullptr;
+    RsvdSec* d_secs = nullptr;
+    int *d_proj = nullptr, *d_direct = nullptr, *d_bad = nullptr;
+    PreparedGemm g_bx, g_bx_all, g_gy, g_ym, g_bty, g_gx2, g_x2m, g_gx, g_xm, g_btw, g_xv;
+    size_t chol_smem = 0;
+    double tol_rel = 0.0, shift_it = 0.0;
+    cudaGraphExec_t graph_start = nullptr;
+    std::map<int, cudaGraphExec_t> graph_iter;   // key: number of iterations
+    std::map<int, int> graph_launches;           // kernel launches inside each graph (key -1: start)
+    JacobiInput jin;
+    std::vector<SelSector> sel_secs;
+    ~RsvdPlan()
+    {
+        if(graph_start) cudaGraphExecDestroy(graph_start);
+        for(auto& kv : graph_iter)
+            if(kv.second) cudaGraphExecDestroy(kv.second);
+        for(PreparedGemm* g : {&g_bx, &g_bx_all, &g_gy, &g_ym, &g_bty, &g_gx2, &g_x2m, &g_gx, &g_xm, &g_btw, &g_xv}) {
+            for(int w = 0; w < 2; ++w)
+                if(g->d_items[w]) cudaFree(g->d_items[w]);
+            if(g->d_jobs) cudaFree(g->d_jobs);
+            if(g->d_scratch) cudaFree(g->d_scratch);
+        }
+        if(arena) cudaFree(arena);
+    }
+};
+
+namespace {
+
+void rsvd_chol(RsvdPlan& P, double shift_rel)
+{
+    rsvd_chol_kernel<<<P.n_proj, CHOL_THREADS, P.chol_smem, P.ctx->stream>>>(P.dG, P.dM, P.d_secs, P.d_proj, shift_rel, P.dDiag, P.d_bad);
+    check_cuda(cudaGetLastError(), "rsvd_chol_kernel launch");
+    ++P.ctx->launches;
+}
+void rsvd_polish(RsvdPlan& P)
+{   // X <- orthonormal to working precision (two unshifted Cholesky-QR passes)
+    Context& c = *P.ctx;
+    c.launch_gemm(P.g_gx);
+    rsvd_chol(P, 0.0);
+    c.launch_gemm(P.g_xm);
+    c.launch_gemm(P.g_gx2);
+    rsvd_chol(P, 0.0);
+    c.launch_gemm(P.g_x2m);
+}
+void rsvd_start(RsvdPlan& P)
+{   // random X (identity on the exactly treated sectors), ||A_q||_F^2, orthonormalise
+    Context& c = *P.ctx;
+    cudaStream_t s = c.stream;
+    check_cuda(cudaMemsetAsync(P.d_bad, 0, sizeof(int), s), "rsvd flag reset");
+    check_cuda(cudaMemsetAsync(P.dRes, 0, sizeof(double) * std::max<long long>(P.so, 1), s), "rsvd residual reset");
+    launch_fill_random(P.dX, 0x5eedc0ffeeull + static_cast<uint64_t>(P.xo), P.xo, s);
+    ++c.launches;
+    if(!P.direct_list.empty()) {
+        rsvd_identity_kernel<<<dim3(8, static_cast<unsigned>(P.direct_list.size())), 256, 0, s>>>(P.dX, P.d_secs, P.d_direct, static_cast<int>(P.direct_list.size()));
+        check_cuda(cudaGetLastError(), "rsvd_identity_kernel launch");
+        ++c.launches;
+    }
+    rsvd_norm2_kernel<<<dim3(NORM_PARTS, P.nsec), 256, 0, s>>>(P.dA, P.d_secs, P.dNorm);
+    check_cuda(cudaGetLastError(), "rsvd_norm2_kernel launch");
+    ++c.launches;
+    rsvd_polish(P);
+}
+void rsvd_iterate(RsvdPlan& P, int iters)
+{   // `iters` subspace iterations X <- orth(B^T orth(B X)), orthonormalise, project: Y = B X
+    Context& c = *P.ctx;
+    for(int it = 0; it < iters; ++it) {
+        c.launch_gemm(P.g_bx);
+        c.launch_gemm(P.g_gy);
+        rsvd_chol(P, P.shift_it);
+        c.launch_gemm(P.g_ym);
+        c.launch_gemm(P.g_bty);
+        c.launch_gemm(P.g_gx2);
+        rsvd_chol(P, P.shift_it);
+        c.launch_gemm(P.g_x2m);
+    }
+    rsvd_polish(P);
+    c.launch_gemm(P.g_bx_all);
+}
+
+// runs `body` directly, or captures it once into a CUDA graph and replays it
+template <typename F> void run_or_replay(RsvdPlan& P, cudaGraphExec_t* slot, int key, bool use_graph, F body)
+{
+    Context& c = *P.ctx;
+    cudaStream_t s = c.stream;
+    if(!use_graph) {
+        body();
+        return;
+    }
+    if(*slot == nullptr) {
+        const bool prof_saved = c.profiling;
+        c.profiling = false;   // no event records inside a capture
+        const int64_t l0 = c.launches;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if(ok) {
+            try {
+                body();
+            } catch(...) {
+                ok = false;
+            }
+            ok = (cudaStreamEndCapture(s, &graph) == cudaSuccess) && ok && graph != nullptr;
+        }
+        if(ok) ok = cudaGraphInstantiate(slot, graph, 0) == cudaSuccess;
+        if(graph) cudaGraphDestroy(graph);
+        c.profiling = prof_saved;
+        P.graph_launches[key] = static_cast<int>(c.launches - l0);
+        c.launches = l0;
+        if(!ok) {
+            cudaGetLastError();
+            *slot = nullptr;
+            body();
+            return;
+        }
+    }
+    check_cuda(cudaGraphLaunch(*slot, s), "rsvd graph launch");
+    c.launches += P.graph_launches[key];
+}
+
+std::shared_ptr<RsvdPlan> build_rsvd_plan(Context& ctx, const Layout& L, int K0)
+{
+    auto Pp = std::make_shared<RsvdPlan>();
+    RsvdPlan& P = *Pp;
+    P.ctx = &ctx;
+    P.K0 = K0;
+    const int nsec = static_cast<int>(L.sector.size());
+    P.nsec = nsec;
+    P.secs.resize(nsec);
+    P.w_off.resize(nsec);
+    P.v_off.resize(nsec);
+    long long wo = 0, vo = 0;
+    for(int i = 0; i < nsec; ++i) {
+        RsvdSec& s = P.secs[i];
+        s.a_off = L.off[i];
+        s.m = static_cast<int>(L.rows[i]);
+        s.n = static_cast<int>(L.cols[i]);
+        s.tr = s.m < s.n;
+        s.mb = std::max(s.m, s.n);
+        s.nb = std::min(s.m, s.n);
+        s.direct = s.nb <= K0;
+        s.K = s.direct ? s.nb : K0;
+        s.pad = 0;
+        s.x_off = P.xo;
+        s.y_off = P.yo;
+        s.g_off = P.go;
+        s.s_off = P.so;
+        P.w_off[i] = wo;   // where jacobi_all puts the work matrix / accumulator of the projected block
+        P.v_off[i] = vo;
+        wo += static_cast<long long>(s.mb) * s.K;
+        vo += static_cast<long long>(s.K) * s.K;
+        P.xo += static_cast<long long>(s.nb) * s.K;
+        P.yo += static_cast<long long>(s.mb) * s.K;
+        P.go += static_cast<long long>(s.K) * s.K;
+        P.so += s.K;
+        P.mb_max = std::max(P.mb_max, s.mb);
+        (s.direct ? P.direct_list : P.proj_list).push_back(i);
+        // keep every buffer segment 16-byte aligned for the vectorised GEMM loads
+        P.xo += P.xo & 1;
+        P.yo += P.yo & 1;
+        P.go += P.go & 1;
+    }
+    P.n_proj = static_cast<int>(P.proj_list.size());
+    P.ao = L.size + (L.size & 1);
+    // ---- one arena
+    auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+    const size_t bX = al(sizeof(double) * std::max<long long>(P.xo, 1)), bY = al(sizeof(double) * std::max<long long>(P.yo, 1)),
+                 bG = al(sizeof(double) * std::max<long long>(P.go, 1)), bA = al(sizeof(double) * std::max<long long>(P.ao, 1));
+    const size_t bDiag = al(sizeof(double) * nsec), bRes = al(sizeof(double) * std::max<long long>(P.so, 1)), bNorm = al(sizeof(double) * nsec * NORM_PARTS);
+    const size_t bSecs = al(sizeof(RsvdSec) * nsec), bList = al(sizeof(int) * nsec);
+    const size_t total = bA + 3 * bX + 2 * bY + 2 * bG + bDiag + bRes + bNorm + bSecs + 2 * bList + 256;
+    check_cuda(cudaMalloc(reinterpret_cast<void**>(&P.arena), total), "rsvd arena");
+    char* p = P.arena;
+    auto take = [&](size_t b) { char* r = p; p += b; return r; };
+    P.dA = reinterpret_cast<double*>(take(bA));
+    P.dX = reinterpret_cast<double*>(take(bX));
+    P.dX2 = reinterpret_cast<double*>(take(bX));
+    P.dZ = reinterpret_cast<double*>(take(bX));
+    P.dY = reinterpret_cast<double*>(take(bY));
+    P.dY2 = reinterpret_cast<double*>(take(bY));
+    P.dG = reinterpret_cast<double*>(take(bG));
+    P.dM = reinterpret_cast<double*>(take(bG));
+    P.dDiag = reinterpret_cast<double*>(take(bDiag));
+    P.dRes = reinterpret_cast<double*>(take(bRes));
+    P.dNorm = reinterpret_cast<double*>(take(bNorm));
+    P.d_secs = reinterpret_cast<RsvdSec*>(take(bSecs));
+    P.d_proj = reinterpret_cast<int*>(take(bList));
+    P.d_direct = reinterpret_cast<int*>(take(bList));
+    P.d_bad = reinterpret_cast<int*>(take(256));
+    ctx.upload_async(P.d_secs, P.secs.data(), sizeof(RsvdSec) * nsec);
+    if(!P.proj_list.empty()) ctx.upload_async(P.d_proj, P.proj_list.data(), sizeof(int) * P.proj_list.size());
+    if(!P.direct_list.empty()) ctx.upload_async(P.d_direct, P.direct_list.data(), sizeof(int) * P.direct_list.size());
+
+    // ---- prepared products (tile lists uploaded once)
+    std::vector<GemmItem> i_bx, i_bx_all, i_gy, i_ym, i_bty, i_gx2, i_x2m, i_xv, i_btw;
+    for(int i = 0; i < nsec; ++i) {
+        const RsvdSec& c = P.secs[i];
+        const GemmItem bx = gemm_item(c.a_off, c.x_off, c.y_off, c.mb, c.K, c.nb, c.m, c.nb, c.mb, c.tr ? 1 : 0, 0);   // Y = B X (B = A or A^T)
+        i_bx_all.push_back(bx);
+        i_xv.push_back(gemm_item(c.x_off, P.v_off[i], c.x_off, c.nb, c.K, c.K, c.nb, c.K, c.nb, 0, 0));
+        if(c.direct) continue;
+        i_bx.push_back(bx);
+        i_gy.push_back(gemm_item(c.y_off, c.y_off, c.g_off, c.K, c.K, c.mb, c.mb, c.mb, c.K, 1, 0));
+        i_ym.push_back(gemm_item(c.y_off, c.g_off, c.y_off, c.mb, c.K, c.K, c.mb, c.K, c.mb, 0, 0));
+        i_bty.push_back(gemm_item(c.a_off, c.y_off, c.x_off, c.nb, c.K, c.mb, c.m, c.mb, c.nb, c.tr ? 0 : 1, 0));
+        i_btw.push_back(gemm_item(c.a_off, P.w_off[i], c.x_off, c.nb, c.K, c.mb, c.m, c.mb, c.nb, c.tr ? 0 : 1, 0));
+        i_gx2.push_back(gemm_item(c.x_off, c.x_off, c.g_off, c.K, c.K, c.nb, c.nb, c.nb, c.K, 1, 0));
+        i_x2m.push_back(gemm_item(c.x_off, c.g_off, c.x_off, c.nb, c.K, c.K, c.nb, c.K, c.nb, 0, 0));
+    }
+    P.g_bx = ctx.prepare_gemm(P.dA, P.dX, P.dY, i_bx);
+    P.g_bx_all = ctx.prepare_gemm(P.dA, P.dX, P.dY, i_bx_all);
+    P.g_gy = ctx.prepare_gemm(P.dY, P.dY, P.dG, i_gy);
+    P.g_ym = ctx.prepare_gemm(P.dY, P.dM, P.dY2, i_ym);
+    P.g_bty = ctx.prepare_gemm(P.dA, P.dY2, P.dX2, i_bty);
+    P.g_gx2 = ctx.prepare_gemm(P.dX2, P.dX2, P.dG, i_gx2);
+    P.g_x2m = ctx.prepare_gemm(P.dX2, P.dM, P.dX, i_x2m);
+    P.g_gx = ctx.prepare_gemm(P.dX, P.dX, P.dG, i_gx2);    // same shapes, other buffers (polishing)
+    P.g_xm = ctx.prepare_gemm(P.dX, P.dM, P.dX2, i_x2m);
+    P.g_btw = ctx.prepare_gemm(P.dA, nullptr, P.dZ, i_btw);   // Zr = B^T W: the B operand (Jacobi work matrix) is set per check
+    P.g_xv = ctx.prepare_gemm(P.dX, nullptr, P.dX2, i_xv);    // V = X Vrot: the B operand (Jacobi accumulator) is set per check
+    P.chol_smem = sizeof(double) * (static_cast<size_t>(K0 + 1) * K0 + K0);
+    check_cuda(cudaFuncSetAttribute(rsvd_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024), "rsvd chol smem attr");
+    P.tol_rel = 16.0 * 2.220446049250313e-16 * std::sqrt(static_cast<double>(P.mb_max));
+    P.shift_it = 1.e-13 * P.mb_max;   // keeps the factorisation of a numerically rank-deficient basis going (subspace iteration only needs a basis)
+    P.sel_secs.resize(nsec);
+    for(int i = 0; i < nsec; ++i) P.sel_secs[i] = {P.secs[i].s_off, P.secs[i].K, P.secs[i].direct, static_cast<double>(ctx.sym->degeneracy(L.sector[i]))};
+    P.jin.d = P.dY;
+    P.jin.sig = L.sig + "#rsvd" + std::to_string(K0);
+    for(int i = 0; i < nsec; ++i) {
+        P.jin.off.push_back(P.secs[i].y_off);
+        P.jin.rows.push_back(P.secs[i].mb);
+        P.jin.cols.push_back(P.secs[i].K);
+    }
+    return Pp;
+}
+
+}   // namespace
+
+void Context::clear_rsvd_plans() { rsvd_plans.clear(); }
+
+bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, bool preserve_multiplets, SvdResult* out)
+{
+    static const int mode = std::getenv("XB_SVD_TRUNC") ? std::atoi(std::getenv("XB_SVD_TRUNC")) : 1;
+    static const bool verbose = std::getenv("XB_SVD_PROF") != nullptr;
+    static const bool no_graph = std::getenv("XB_SVD_NOGRAPH") != nullptr;
+    static const int max_iters = std::getenv("XB_SVD_TRUNC_MAXIT") ? std::atoi(std::getenv("XB_SVD_TRUNC_MAXIT")) : 60;
+    static const int first_iters = std::getenv("XB_SVD_TRUNC_IT0") ? std::atoi(std::getenv("XB_SVD_TRUNC_IT0")) : 8;
+    if(mode == 0 || max_keep <= 0) return false;
+    const Layout& L = *t.layout;
+    const int nsec = static_cast<int>(L.sector.size());
+    constexpr int KMAX = 160;
+    if(max_keep + 16 > KMAX || nsec > 4096) return false;
+    const int K0 = static_cast<int>(std::min<int64_t>(KMAX, ((max_keep + 32 + 15) / 16) * 16));
+    {   // enough of a reduction?
+        long long sum_nb = 0, sum_k = 0;
+        int n_proj = 0;
+        for(int i = 0; i < nsec; ++i) {
+            const long long nb = std::min(L.rows[i], L.cols[i]);
+            sum_nb += nb;
+            sum_k += std::min<long long>(nb, K0);
+            if(nb > K0) ++n_proj;
+        }
+        if(n_proj == 0 || sum_k * 2 > sum_nb || sum_k > SEL_MAX) return false;
+    }
+    const std::string key = L.sig + "#" + std::to_string(K0);
+    auto it = rsvd_plans.find(key);
+    if(it == rsvd_plans.end()) {
+        if(rsvd_plans.size() >= 12) {
+            check_cuda(cudaStreamSynchronize(stream), "rsvd plan eviction sync");
+            rsvd_plans.clear();
+        }
+        it = rsvd_plans.emplace(key, build_rsvd_plan(*this, L, K0)).first;
+    }
+    RsvdPlan& P = *it->second;
+    ++P.uses;
+    ++svd_truncated_calls;
+    ProfScope prof(*this, CAT_SVD, 0.0);
+    cudaStream_t s = stream;
+    const bool use_graph = !no_graph && P.uses >= 2;   // a layout seen once (chi bases still moving) is not worth an instantiation
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float t_iter = 0.f, t_jac = 0.f, t_chk = 0.f;
+    auto mark = [&](int k) {
+        if(!verbose) return;
+        if(!ev[k]) ev[k] = get_event();
+        cudaEventRecord(ev[k], s);
+    };
+    auto lap = [&](int a, int b, float& acc) {
+        if(!verbose) return;
+        cudaEventSynchronize(ev[b]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[a], ev[b]);
+        acc += ms;
+    };
+
+    mark(0);
+    check_cuda(cudaMemcpyAsync(P.dA, t.d, sizeof(double) * L.size, cudaMemcpyDeviceToDevice, s), "rsvd copy-in");
+    run_or_replay(P, &P.graph_start, -1, use_graph, [&]() { rsvd_start(P); });
+
+    int iters_done = 0, next_iters = P.iters_hint > 0 ? P.iters_hint : first_iters, checks = 0;
+    bool ok = false;
+    JacobiResult J;
+    Selection sel;
+    while(true) {
+        next_iters = std::max(1, std::min(next_iters, max_iters - iters_done));
+        {
+            const int n_it = next_iters;
+            cudaGraphExec_t& slot = P.graph_iter[n_it];
+            run_or_replay(P, &slot, n_it, use_graph, [&]() { rsvd_iterate(P, n_it); });
+        }
+        iters_done += next_iters;
+        mark(1);
+        // Rayleigh-Ritz: Jacobi SVD of Y = B X
+        J = jacobi_all(*this, P.jin, false, false);
+        mark(2);
+        bool layout_ok = true;
+        for(int i = 0; i < nsec; ++i)
+            if(J.transposed[i] || J.blocks[i].w_off != P.w_off[i] || J.blocks[i].v_off != P.v_off[i] || J.blocks[i].s_off != P.secs[i].s_off) layout_ok = false;
+        if(!layout_ok) break;
+        // V = X Vrot (-> X2), Zr = B^T W, residuals of the Ritz triplets
+        P.g_xv.B = J.d_V;
+        launch_gemm(P.g_xv);
+        P.g_btw.B = J.d_W;
+        launch_gemm(P.g_btw);
+        if(P.n_proj > 0) {
+            rsvd_residual_kernel<<<dim3(8, P.n_proj), 256, 0, s>>>(P.dZ, P.dX2, J.d_sigma, P.d_secs, P.d_proj, P.dRes);
+            check_cuda(cudaGetLastError(), "rsvd_residual_kernel launch");
+            ++launches;
+        }
+        sel = svd_select(*this, J.d_sigma, static_cast<int>(P.so), P.sel_secs, P.dRes, P.dNorm, P.tol_rel, max_keep, eps_svd, preserve_multiplets, true);
+        ++checks;
+        int h_bad = 0;
+        check_cuda(cudaMemcpy(&h_bad, P.d_bad, sizeof(int), cudaMemcpyDeviceToHost), "rsvd flag readback");
+        mark(3);
+        if(verbose) {
+            lap(0, 1, t_iter);
+            lap(1, 2, t_jac);
+            lap(2, 3, t_chk);
+            std::fprintf(stderr,
+                         "[rsvd] K %d sectors %d (projected %d) iters %d: verdict %d max_res %.2e (tol %.2e) rate %.3f nkeep %d cut/smax %.2e jacobi sweeps %d bad %d | ms: "
+                         "iterate %.3f jacobi %.3f check %.3f graph %d\n",
+                         K0, nsec, P.n_proj, iters_done, sel.hdr.verdict, sel.hdr.max_res, P.tol_rel, sel.hdr.rate, sel.hdr.nkeep,
+                         sel.hdr.smax > 0 ? sel.hdr.cut / sel.hdr.smax : 0.0, J.sweeps + 1, h_bad, t_iter, t_jac, t_chk, use_graph ? 1 : 0);
+            t_iter = t_jac = t_chk = 0.f;
+        }
+        if(sel.hdr.verdict == 0 && !h_bad) {
+            ok = true;
+            break;
+        }
+        if((sel.hdr.verdict & 2) || h_bad || iters_done >= max_iters) break;
+        // predicted number of further iterations: the residual of a kept triplet shrinks by (sigma_{K+1} / sigma_i)^2 <= rate^2 per iteration
+        const double r2 = std::min(0.98, std::max(1.e-4, sel.hdr.rate * sel.hdr.rate));
+        const double need = std::log(std::max(P.tol_rel / std::max(sel.hdr.max_res, 1.e-300), 1.e-300)) / std::log(r2);
+        next_iters = static_cast<int>(std::min<double>(std::max(2.0, std::ceil(need) + 1.0), 16.0));
+        if(sel.hdr.max_res > 1.0) next_iters = 8;   // sentinel: a value next to the cut is far from converged
+        // continue from the Ritz vectors
+        mark(0);
+        check_cuda(cudaMemcpyAsync(P.dX, P.dX2, sizeof(double) * P.xo, cudaMemcpyDeviceToDevice, s), "rsvd restart copy");
+        check_cuda(cudaFreeAsync(sel.d_perm, s), "rsvd free");
+        sel.d_perm = nullptr;
+        free_jacobi(*this, J);
+    }
+    svd_truncated_iters += iters_done;
+    if(ok) {
+        // next call on this layout: start with what was needed (one projection instead of two); shrink slowly when there was slack
+        P.iters_hint = (checks == 1 && sel.hdr.max_res < 0.02 * P.tol_rel && iters_done > 2) ? iters_done - 1 : iters_done;
+        std::vector<FactorSrc> src(nsec);
+        for(int i = 0; i < nsec; ++i) {
+            const RsvdSec& c = P.secs[i];
+            src[i] = {J.blocks[i].w_off, c.x_off, c.s_off, c.mb, c.nb, c.mb, c.nb, c.tr ? 0 : 1};
+        }
+        *out = svd_finish(*this, L, sel, src, J.d_W, P.dX2, J.d_sigma);
+    } else
+        ++svd_truncated_fallbacks;
+    if(sel.d_perm) check_cuda(cudaFreeAsync(sel.d_perm, s), "rsvd free");
+    free_jacobi(*this, J);
+    for(cudaEvent_t e : ev)
+        if(e) event_pool.push_back(e);
+    return ok;
+}
+
+}   // namespace xb

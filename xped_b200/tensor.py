@@ -279,7 +279,7 @@ class Tensor:
         check(fn(*args, C.byref(a), C.byref(b)))
         return Tensor(self.ctx, a), Tensor(self.ctx, b)
 
-    def tQR(self): return self._pair(self.ctx.lib.xb_tqr, self.ctx.h, self.h)
+    def tQR(self, RETURN_LQ=False): return self._pair(self.ctx.lib.xb_tqr, self.ctx.h, self.h, int(bool(RETURN_LQ)))
     def teigh(self): return self._pair(self.ctx.lib.xb_teigh, self.ctx.h, self.h)
 
     # -- measurement hooks

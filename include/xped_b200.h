@@ -55,6 +55,14 @@ int xb_ctx_create_planning(xb_ctx** ctx, const xb_sym_factor* factors, int n_fac
 int xb_ctx_free(xb_ctx* ctx);
 int xb_ctx_sync(xb_ctx* ctx);
 int xb_ctx_nq(const xb_ctx* ctx);
+/* integer options / counters.  set: "svd.truncated" = 1 / 0 forces / forbids the truncated tSVD algorithm (randomized subspace iteration + Jacobi on the
+ * projected blocks, used when maxKeep << number of singular values; falls back to the full Jacobi path when its residual check fails), -1 = default;
+ * "svd.call_tag" = an integer naming the call site of the following tSVD calls: the truncated algorithm starts from the subspace the previous call with the
+ * same (tensor layout, tag) ended with (plus fresh random columns), which in an iteration that converges (CTMRG: one tag per move direction) cuts its work
+ * several times; any tag is always correct, the a-posteriori check does not depend on the start.
+ * get: the same key, and the counters "svd.truncated_calls", "svd.truncated_fallbacks", "svd.truncated_iterations" */
+int xb_ctx_set_int(xb_ctx* ctx, const char* key, int64_t value);
+int xb_ctx_get_int(const xb_ctx* ctx, const char* key, int64_t* value);
 /* counters: [0] kernel launches, [1] permute-plan cache hits, [2] plan cache misses */
 int xb_ctx_stats(const xb_ctx* ctx, int64_t out[3]);
 
@@ -83,6 +91,19 @@ int xb_tensor_structure(const xb_tensor* t, int* q /* nsec*Nq */, int64_t* rows,
 /* number of (tree, cotree) pairs and, per pair: sector index, row offset (leftOffset), col offset, rows, cols */
 int64_t xb_tensor_num_tree_pairs(const xb_tensor* t);
 int xb_tensor_tree_pairs(const xb_tensor* t, int64_t* out5 /* npairs*5 */);
+/* FusionTree<Rank> f1 / FusionTree<CoRank> f2 of tree pair `pair` (enumeration order of xb_tensor_tree_pairs): q_uncoupled (Rank+CoRank)*Nq ints,
+ * q_intermediate (max(Rank-2,0) + max(CoRank-2,0))*Nq ints, q_coupled Nq ints, dims Rank+CoRank (include/Xped/Core/FusionTree.hpp:28-35); any pointer may be NULL */
+int xb_tensor_tree_pair_trees(const xb_tensor* t, int64_t pair, int* q_uncoupled, int* q_intermediate, int* q_coupled, int64_t* dims);
+/* index of the tree pair (f1, f2) given by its labels (FusionTree::operator== compares labels, FusionTree.cpp:66-85), or -1 */
+int64_t xb_tensor_find_tree_pair(const xb_tensor* t, const int* q_uncoupled, const int* q_intermediate, const int* q_coupled);
+/* Tensor::view(f1, f2) / l-value subMatrix(f1, f2)  src/Core/Tensor.cpp:830-905, Tensor.hpp:196-216: the f1.dim x f2.dim sub-block IN PLACE --
+ * device pointer to its (0, 0) element and the leading dimension (rows of the sector block); column-major, the row / column multi-index runs
+ * over the legs with leg 0 fastest.  Valid while the tensor lives; order your work after the context stream (xb_ctx_stream). */
+int xb_view(const xb_tensor* t, int64_t pair, double** dev_ptr, int64_t* ld, int64_t* rows, int64_t* cols);
+/* Tensor::subBlock(f1, f2) / const subMatrix  src/Core/Tensor.cpp:907-981: a dense copy of the sub-block on the host (n = f1.dim * f2.dim doubles,
+ * = the rank-(Rank+CoRank) tensor of dims f1.dims x f2.dims in column-major order); xb_set_sub_block writes one back (setSubTensor on a view) */
+int xb_sub_block(const xb_tensor* t, int64_t pair, double* host, int64_t n);
+int xb_set_sub_block(xb_tensor* t, int64_t pair, const double* host, int64_t n);
 /* raw `m_data` image, host <-> device (Tensor::data()/set_data(), Tensor.hpp:137-152) */
 int xb_tensor_upload(xb_tensor* t, const double* host, int64_t n);
 int xb_tensor_download(const xb_tensor* t, double* host, int64_t n);

@@ -427,3 +427,79 @@ def test_tsvd_backward(ctxs, name):
         ograd = o.tSVD_backward(o_dU, o_dS, o_dV)
         assert_same(ggrad, ograd, 1e-9, f"{name} tSVD_backward")
         assert_same(g.tSVD_backward(gU, gS, gV, g_dU, None, None), o.tSVD_backward(o_dU, None, None), 1e-9, f"{name} tSVD_backward (dU only)")
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1", "fU1xSU2"])
+def test_sub_block_view_sub_matrix(ctxs, name):
+    """Tensor::subBlock / subMatrix / view (include/Xped/Core/Tensor.hpp:191-216, src/Core/Tensor.cpp:830-981): every tree pair's dense
+    sub-block equals the oracle's bit for bit (it is a strided copy), the trees reported through the C ABI are the oracle's, the pair is
+    found again by its labels, view() addresses the same elements in place, and writing a sub-block back changes exactly that sub-block."""
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(91)
+    ents = [rand_entries(SPECS[name], 7, rng, 3) for _ in range(4)]
+    g, o = pair(ctx, osym, ents[:2], ents[2:], 55)
+    opairs = [(i, dt, ct) for i, q in enumerate(o.sector) for dt in o.domain.tree(q) for ct in o.codomain.tree(q)]
+    assert len(opairs) == len(g.tree_pairs())
+    full = g.download()
+    for k, (i, dt, ct) in enumerate(opairs):
+        qu, qi, qc, dims = g.tree_pair_trees(k)
+        assert [tuple(q) for q in qu] == [tuple(q) for q in list(dt.q_uncoupled) + list(ct.q_uncoupled)]
+        assert tuple(qc) == tuple(dt.q_coupled) and dims == list(dt.dims) + list(ct.dims)
+        assert [tuple(q) for q in qi] == [tuple(q) for q in list(dt.q_intermediates) + list(ct.q_intermediates)]
+        assert g.find_tree_pair(qu, qi, qc) == k
+        ob = o.subBlock(dt, ct)
+        gb = g.subBlock(k)
+        assert gb.shape == ob.shape and np.array_equal(gb, ob)
+        assert np.array_equal(g.subMatrix(k), o._sub(i, dt, ct))
+        ptr, ld, r, c = g.view(k)
+        assert (r, c) == o._sub(i, dt, ct).shape and ld == o.shape_of(i)[0] and ptr != 0
+    # l-value use: overwrite one sub-block, everything else unchanged
+    k = len(opairs) // 2
+    i, dt, ct = opairs[k]
+    new = rng.uniform(-1, 1, o.subBlock(dt, ct).shape)
+    g.setSubBlock(k, new)
+    o._sub(i, dt, ct)[...] = new.reshape(o._sub(i, dt, ct).shape, order="F")
+    assert np.array_equal(g.download(), o.data)
+    assert not np.array_equal(full, o.data) or new.size == 0
+
+
+@pytest.mark.parametrize("name", ["SU2", "U1"])
+def test_tqr_wide_blocks_and_return_lq(ctxs, name):
+    """tQR beyond the tall case (src/Core/Tensor.cpp:757-780).  (a) middle basis = coupled domain (the tensor is wider than tall): blocks are
+    Q_full 1(m x mid), 1(mid x m) R_full -- Q orthogonal, Q R = A, and where the reference's own matrices fit its bases (square blocks) they
+    are the oracle's.  (b) RETURN_LQ on a square tensor: the adjoint blocks of both factors, as the reference returns them.  (c) RETURN_LQ on
+    non-square blocks does not fit the bases: XB_ERR_INVALID."""
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(53)
+    inb, loc = rand_entries(SPECS[name], 10, rng), rand_entries(SPECS[name], 4, rng, 2)
+    # (a) wide: A(1, 2)
+    g, o = pair(ctx, osym, [inb], [inb, loc], 61)
+    assert o.domain.dim() <= o.codomain.dim()
+    gQ, gR = g.tQR()
+    assert_same(gQ @ gR, o, 1e-12, "Q*R (wide)")
+    one = gQ.multiply(gQ, True, False)
+    assert np.abs(one.download() - one.clone().setIdentity().download()).max() < 1e-12
+    oQ, oR = o.tQR()
+    rows, cols = g.structure()[1], g.structure()[2]
+    qs, rs = gQ.structure(), gR.structure()
+    for i in range(len(o.sector)):
+        m, n = o.shape_of(i)
+        assert (qs[1][i], qs[2][i]) == (m, m) and (rs[1][i], rs[2][i]) == (m, n)
+        gq = gQ.download()[qs[3][i]:qs[3][i] + m * m].reshape((m, m), order="F")
+        gr = gR.download()[rs[3][i]:rs[3][i] + m * n].reshape((m, n), order="F")
+        oq, orr = oQ.block(i), oR.block(i)        # reference shapes: m x n and n x n (zero padded / cropped)
+        k = min(m, n)
+        assert np.abs(gr[:k, :] - orr[:k, :]).max() < 1e-11 * max(1.0, np.abs(orr).max())
+        assert np.abs(gq[:, :k] - oq[:, :k]).max() < 1e-11
+        assert np.abs(np.tril(gr, -1)).max() == 0.0
+    # (b) RETURN_LQ, square blocks
+    g2, o2 = pair(ctx, osym, [inb, loc], [inb, loc], 62)
+    gQ2, gR2 = g2.tQR(True)
+    oQ2, oR2 = o2.tQR(True)
+    assert_same(gQ2, oQ2, 1e-11, "Q^T")
+    assert_same(gR2, oR2, 1e-11, "R^T")
+    assert_same(gQ2.adjoint() @ gR2.adjoint(), o2, 1e-12, "(Q^T)^T (R^T)^T = A")
+    # (c)
+    with pytest.raises(xb.XbError) as ei:
+        g.tQR(True)
+    assert ei.value.status == 1   # XB_ERR_INVALID

@@ -32,6 +32,5 @@ print("sigma head", s[:6], "tail", s[-4:])
 rec = (U @ S) @ Vd
 print("||U S Vd||_F", rec.norm(), " ||M||_F", M.norm())
 np.save(f"gpurun_out/rsvd_sigma_D{D}_trunc{os.environ.get('XB_SVD_TRUNC', '1')}.npy", S.download())
-np.save(f"gpurun_out/rsvd_rec_D{D}_trunc{os.environ.get('XB_SVD_TRUNC', '1')}.npy", rec.download())
 c1 = ctm.get("C1"); 
 print("C1 maxnorm", c1.maxNorm(), "sqnorm", c1.squaredNorm())

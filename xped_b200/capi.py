@@ -36,6 +36,8 @@ SIGNATURES = {
     "xb_ctx_create_planning": (C.c_int, [PP, C.POINTER(SymFactor), C.c_int]),
     "xb_ctx_free": (C.c_int, [P]),
     "xb_ctx_sync": (C.c_int, [P]),
+    "xb_ctx_set_int": (C.c_int, [P, C.c_char_p, C.c_int64]),
+    "xb_ctx_get_int": (C.c_int, [P, C.c_char_p, LP]),
     "xb_ctx_nq": (C.c_int, [P]),
     "xb_ctx_stats": (C.c_int, [P, LP]),
     "xb_basis_create": (C.c_int, [P, IP, LP, C.c_int, PP]),
@@ -55,6 +57,11 @@ SIGNATURES = {
     "xb_tensor_structure": (C.c_int, [P, IP, LP, LP, LP]),
     "xb_tensor_num_tree_pairs": (C.c_int64, [P]),
     "xb_tensor_tree_pairs": (C.c_int, [P, LP]),
+    "xb_tensor_tree_pair_trees": (C.c_int, [P, C.c_int64, IP, IP, IP, LP]),
+    "xb_tensor_find_tree_pair": (C.c_int64, [P, IP, IP, IP]),
+    "xb_view": (C.c_int, [P, C.c_int64, C.POINTER(C.c_void_p), LP, LP, LP]),
+    "xb_sub_block": (C.c_int, [P, C.c_int64, DP, C.c_int64]),
+    "xb_set_sub_block": (C.c_int, [P, C.c_int64, DP, C.c_int64]),
     "xb_tensor_upload": (C.c_int, [P, DP, C.c_int64]),
     "xb_tensor_download": (C.c_int, [P, DP, C.c_int64]),
     "xb_tensor_set_zero": (C.c_int, [P]),

@@ -99,6 +99,43 @@ int xb_ctx_sync(xb_ctx* ctx)
     });
 }
 
+int xb_ctx_set_int(xb_ctx* ctx, const char* key, int64_t value)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(key, "key");
+        const std::string k(key);
+        if(k == "svd.truncated")
+            ctx->impl.opt_svd_truncated = value < 0 ? -1 : (value != 0 ? 1 : 0);
+        else if(k == "svd.call_tag")
+            ctx->impl.svd_call_tag = static_cast<int>(value);
+        else
+            throw std::invalid_argument("xb_ctx_set_int: unknown key '" + k + "'");
+    });
+}
+
+int xb_ctx_get_int(const xb_ctx* ctx, const char* key, int64_t* value)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(key, "key");
+        need(value, "value");
+        const std::string k(key);
+        if(k == "svd.truncated")
+            *value = ctx->impl.opt_svd_truncated;
+        else if(k == "svd.call_tag")
+            *value = ctx->impl.svd_call_tag;
+        else if(k == "svd.truncated_calls")
+            *value = ctx->impl.svd_truncated_calls;
+        else if(k == "svd.truncated_fallbacks")
+            *value = ctx->impl.svd_truncated_fallbacks;
+        else if(k == "svd.truncated_iterations")
+            *value = ctx->impl.svd_truncated_iters;
+        else
+            throw std::invalid_argument("xb_ctx_get_int: unknown key '" + k + "'");
+    });
+}
+
 int xb_ctx_nq(const xb_ctx* ctx) { return ctx ? ctx->impl.sym->Nq() : -1; }
 
 int xb_ctx_stats(const xb_ctx* ctx, int64_t out[3])
@@ -285,6 +322,140 @@ int xb_tensor_tree_pairs(const xb_tensor* t, int64_t* out5)
                 ro += dt.dim;
             }
         }
+    });
+}
+
+// ---- sub-blocks of one tree pair (Tensor::subMatrix / subBlock / view, include/Xped/Core/Tensor.hpp:191-216, src/Core/Tensor.cpp:830-981)
+namespace {
+struct PairLoc { int sector; int64_t ro, co; const Tree* dt; const Tree* ct; };
+PairLoc locate_pair(const Layout& L, int64_t pair)
+{
+    if(pair < 0) throw std::invalid_argument("tree pair index < 0");
+    int64_t n = 0;
+    for(size_t i = 0; i < L.sector.size(); ++i) {
+        const auto& dts = L.cdom->trees(L.sector[i]);
+        const auto& cts = L.ccod->trees(L.sector[i]);
+        const int64_t here = static_cast<int64_t>(dts.size()) * static_cast<int64_t>(cts.size());
+        if(pair < n + here) {
+            const int64_t a = (pair - n) / static_cast<int64_t>(cts.size()), b = (pair - n) % static_cast<int64_t>(cts.size());
+            int64_t ro = 0, co = 0;
+            for(int64_t k = 0; k < a; ++k) ro += dts[k].dim;
+            for(int64_t k = 0; k < b; ++k) co += cts[k].dim;
+            return {static_cast<int>(i), ro, co, &dts[a], &cts[b]};
+        }
+        n += here;
+    }
+    throw std::invalid_argument("tree pair index out of range");
+}
+}   // namespace
+
+int xb_tensor_tree_pair_trees(const xb_tensor* t, int64_t pair, int* q_uncoupled, int* q_intermediate, int* q_coupled, int64_t* dims)
+{
+    return guard([&] {
+        need(t, "tensor");
+        const Layout& L = *t->t->layout;
+        const int nq = t->ctx->impl.sym->Nq();
+        const PairLoc loc = locate_pair(L, pair);
+        const int R = L.rank(), C = L.corank();
+        const int ni_d = R >= 2 ? R - 2 : 0, ni_c = C >= 2 ? C - 2 : 0;
+        for(int i = 0; i < R; ++i) {
+            if(q_uncoupled) for(int k = 0; k < nq; ++k) q_uncoupled[i * nq + k] = loc.dt->unc[i][k];
+            if(dims) dims[i] = loc.dt->dims[i];
+        }
+        for(int i = 0; i < C; ++i) {
+            if(q_uncoupled) for(int k = 0; k < nq; ++k) q_uncoupled[(R + i) * nq + k] = loc.ct->unc[i][k];
+            if(dims) dims[R + i] = loc.ct->dims[i];
+        }
+        if(q_intermediate) {
+            for(int i = 0; i < ni_d; ++i) for(int k = 0; k < nq; ++k) q_intermediate[i * nq + k] = loc.dt->inter[i][k];
+            for(int i = 0; i < ni_c; ++i) for(int k = 0; k < nq; ++k) q_intermediate[(ni_d + i) * nq + k] = loc.ct->inter[i][k];
+        }
+        if(q_coupled) for(int k = 0; k < nq; ++k) q_coupled[k] = loc.dt->coupled[k];
+    });
+}
+
+int64_t xb_tensor_find_tree_pair(const xb_tensor* t, const int* q_uncoupled, const int* q_intermediate, const int* q_coupled)
+{
+    if(!t || !q_uncoupled || !q_coupled) return -1;
+    const Layout& L = *t->t->layout;
+    const Symmetry& sym = *t->ctx->impl.sym;
+    const int nq = sym.Nq(), R = L.rank(), C = L.corank();
+    const int ni_d = R >= 2 ? R - 2 : 0, ni_c = C >= 2 ? C - 2 : 0;
+    auto same = [&](const Q& q, const int* p) {
+        for(int k = 0; k < nq; ++k)
+            if(q[k] != p[k]) return false;
+        return true;
+    };
+    int64_t n = 0;
+    for(size_t i = 0; i < L.sector.size(); ++i) {
+        const auto& dts = L.cdom->trees(L.sector[i]);
+        const auto& cts = L.ccod->trees(L.sector[i]);
+        if(same(L.sector[i], q_coupled)) {
+            for(size_t a = 0; a < dts.size(); ++a) {
+                bool ok = true;
+                for(int l = 0; l < R && ok; ++l) ok = same(dts[a].unc[l], q_uncoupled + l * nq);
+                for(int l = 0; l < ni_d && ok; ++l) ok = q_intermediate && same(dts[a].inter[l], q_intermediate + l * nq);
+                if(!ok) continue;
+                for(size_t b = 0; b < cts.size(); ++b) {
+                    bool okc = true;
+                    for(int l = 0; l < C && okc; ++l) okc = same(cts[b].unc[l], q_uncoupled + (R + l) * nq);
+                    for(int l = 0; l < ni_c && okc; ++l) okc = q_intermediate && same(cts[b].inter[l], q_intermediate + (ni_d + l) * nq);
+                    if(okc) return n + static_cast<int64_t>(a) * static_cast<int64_t>(cts.size()) + static_cast<int64_t>(b);
+                }
+            }
+        }
+        n += static_cast<int64_t>(dts.size()) * static_cast<int64_t>(cts.size());
+    }
+    return -1;
+}
+
+int xb_view(const xb_tensor* t, int64_t pair, double** dev_ptr, int64_t* ld, int64_t* rows, int64_t* cols)
+{
+    return guard([&] {
+        need(t, "tensor");
+        need(dev_ptr, "dev_ptr");
+        const Layout& L = *t->t->layout;
+        const PairLoc loc = locate_pair(L, pair);
+        *dev_ptr = t->t->d + L.off[loc.sector] + loc.ro + loc.co * L.rows[loc.sector];
+        if(ld) *ld = L.rows[loc.sector];
+        if(rows) *rows = loc.dt->dim;
+        if(cols) *cols = loc.ct->dim;
+    });
+}
+
+int xb_sub_block(const xb_tensor* t, int64_t pair, double* host, int64_t n)
+{
+    return guard([&] {
+        need(t, "tensor");
+        need(host, "host buffer");
+        const Layout& L = *t->t->layout;
+        const PairLoc loc = locate_pair(L, pair);
+        const int64_t r = loc.dt->dim, c = loc.ct->dim;
+        if(n != r * c) throw std::invalid_argument("sub_block: n != f1.dim * f2.dim");
+        if(n == 0) return;
+        Context& ctx = t->ctx->impl;
+        const double* src = t->t->d + L.off[loc.sector] + loc.ro + loc.co * L.rows[loc.sector];
+        check_cuda(cudaMemcpy2DAsync(host, sizeof(double) * r, src, sizeof(double) * L.rows[loc.sector], sizeof(double) * r, static_cast<size_t>(c),
+                                     cudaMemcpyDeviceToHost, ctx.stream), "sub_block download");
+        check_cuda(cudaStreamSynchronize(ctx.stream), "sub_block sync");
+    });
+}
+
+int xb_set_sub_block(xb_tensor* t, int64_t pair, const double* host, int64_t n)
+{
+    return guard([&] {
+        need(t, "tensor");
+        need(host, "host buffer");
+        const Layout& L = *t->t->layout;
+        const PairLoc loc = locate_pair(L, pair);
+        const int64_t r = loc.dt->dim, c = loc.ct->dim;
+        if(n != r * c) throw std::invalid_argument("set_sub_block: n != f1.dim * f2.dim");
+        if(n == 0) return;
+        Context& ctx = t->ctx->impl;
+        double* dst = t->t->d + L.off[loc.sector] + loc.ro + loc.co * L.rows[loc.sector];
+        check_cuda(cudaMemcpy2DAsync(dst, sizeof(double) * L.rows[loc.sector], host, sizeof(double) * r, sizeof(double) * r, static_cast<size_t>(c),
+                                     cudaMemcpyHostToDevice, ctx.stream), "sub_block upload");
+        check_cuda(cudaStreamSynchronize(ctx.stream), "sub_block sync");   // the caller's buffer is pageable: do not return before it was read
     });
 }
 
@@ -596,6 +767,7 @@ int xb_contract(xb_ctx* ctx, const xb_tensor* a, const int* la, int na, const xb
 int xb_adjoint(xb_ctx* ctx, const xb_tensor* t, xb_tensor** out)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(t, "tensor");
         *out = wrap(ctx, ctx->impl.adjoint(*t->t));
     });
@@ -604,6 +776,7 @@ int xb_adjoint(xb_ctx* ctx, const xb_tensor* t, xb_tensor** out)
 int xb_twist(xb_ctx* ctx, const xb_tensor* t, int leg, xb_tensor** out)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(t, "tensor");
         *out = wrap(ctx, ctx->impl.twist(*t->t, leg));
     });
@@ -612,6 +785,7 @@ int xb_twist(xb_ctx* ctx, const xb_tensor* t, int leg, xb_tensor** out)
 int xb_axpby(xb_ctx* ctx, double alpha, const xb_tensor* x, double beta, const xb_tensor* y, xb_tensor** out)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(x, "x");
         *out = wrap(ctx, ctx->impl.axpby(alpha, *x->t, beta, y ? y->t.get() : nullptr));
     });
@@ -620,6 +794,7 @@ int xb_axpby(xb_ctx* ctx, double alpha, const xb_tensor* x, double beta, const x
 int xb_diag_map(xb_ctx* ctx, const xb_tensor* t, int op, xb_tensor** out)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(t, "tensor");
         if(op < 0 || op > 2) throw std::invalid_argument("diag_map: op must be 0, 1 or 2");
         *out = wrap(ctx, ctx->impl.diag_map(*t->t, op));
@@ -629,6 +804,7 @@ int xb_diag_map(xb_ctx* ctx, const xb_tensor* t, int op, xb_tensor** out)
 int xb_max_norm(xb_ctx* ctx, const xb_tensor* t, double* out)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(t, "tensor");
         *out = ctx->impl.max_norm(*t->t);
     });
@@ -637,6 +813,7 @@ int xb_max_norm(xb_ctx* ctx, const xb_tensor* t, double* out)
 int xb_trace(xb_ctx* ctx, const xb_tensor* t, double* out)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(t, "tensor");
         *out = ctx->impl.trace(*t->t);
     });
@@ -645,6 +822,7 @@ int xb_trace(xb_ctx* ctx, const xb_tensor* t, double* out)
 int xb_squared_norm(xb_ctx* ctx, const xb_tensor* t, double* out)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(t, "tensor");
         *out = ctx->impl.squared_norm(*t->t);
     });
@@ -692,6 +870,7 @@ int xb_tqr(xb_ctx* ctx, const xb_tensor* t, int return_lq, xb_tensor** Qo, xb_te
 int xb_teigh(xb_ctx* ctx, const xb_tensor* t, xb_tensor** D, xb_tensor** V)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(t, "tensor");
         Tensor *d = nullptr, *v = nullptr;
         ctx->impl.teigh(*t->t, &d, &v);
@@ -703,6 +882,7 @@ int xb_teigh(xb_ctx* ctx, const xb_tensor* t, xb_tensor** D, xb_tensor** V)
 int xb_decompose(xb_ctx* ctx, const xb_tensor* T1, const xb_tensor* T2, int64_t chi, xb_tensor** P1, xb_tensor** P2)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(T1, "T1");
         need(T2, "T2");
         Tensor *p1 = nullptr, *p2 = nullptr;
@@ -715,6 +895,7 @@ int xb_decompose(xb_ctx* ctx, const xb_tensor* T1, const xb_tensor* T2, int64_t 
 int xb_contract_L(xb_ctx* ctx, const xb_tensor* Bold, const xb_tensor* Bra, const xb_tensor* Ket, xb_tensor** Bnew)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(Bold, "Bold");
         need(Bra, "Bra");
         need(Ket, "Ket");
@@ -751,6 +932,7 @@ int xb_mps_right_sweep_step(xb_ctx* ctx, const xb_tensor* A_loc, const xb_tensor
 int xb_contract_R(xb_ctx* ctx, const xb_tensor* Bold, const xb_tensor* Bra, const xb_tensor* Ket, xb_tensor** Bnew)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(Bold, "Bold");
         need(Bra, "Bra");
         need(Ket, "Ket");
@@ -819,6 +1001,7 @@ int xb_ctm_rdm(xb_ctm* c, int which, xb_tensor** rho)
 int xb_rdm_one_site(xb_ctx* ctx, const xb_tensor* rho, xb_tensor** rho1)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(rho, "rho");
         *rho1 = wrap(ctx, rdm_one_site(ctx->impl, *rho->t));
     });
@@ -827,6 +1010,7 @@ int xb_rdm_one_site(xb_ctx* ctx, const xb_tensor* rho, xb_tensor** rho1)
 int xb_avg_one_site(xb_ctx* ctx, const xb_tensor* rho1, const xb_tensor* op, double* out)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(rho1, "rho1");
         need(op, "op");
         *out = avg_one_site(ctx->impl, *rho1->t, *op->t);
@@ -836,6 +1020,7 @@ int xb_avg_one_site(xb_ctx* ctx, const xb_tensor* rho1, const xb_tensor* op, dou
 int xb_avg_two_site(xb_ctx* ctx, const xb_tensor* rho, const xb_tensor* op, double* out)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(rho, "rho");
         need(op, "op");
         *out = avg_two_site(ctx->impl, *rho->t, *op->t);
@@ -854,6 +1039,7 @@ int xb_ctm_move(xb_ctm* c, int direction)
 int xb_bench_permute(xb_ctx* ctx, const xb_tensor* t, int shift, const int* p, int n, int reps, double* ms_per_launch, int64_t* bytes)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(t, "tensor");
         Context& c = ctx->impl;
         auto plan = c.permute_plan(t->t->layout, shift, std::vector<int>(p, p + n), false);
@@ -883,6 +1069,7 @@ int xb_bench_permute(xb_ctx* ctx, const xb_tensor* t, int shift, const int* p, i
 int xb_bench_multiply(xb_ctx* ctx, const xb_tensor* a, const xb_tensor* b, int reps, double* ms_per_launch, double* flops)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(a, "a");
         need(b, "b");
         Context& c = ctx->impl;

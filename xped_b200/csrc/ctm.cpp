@@ -205,7 +205,15 @@ void Ctm::projectors(int direction, TP& P1, TP& P2) const
     default: throw std::invalid_argument("CTM: direction must be 0..3");
     }
     Tensor *p1 = nullptr, *p2 = nullptr;
-    decompose_projectors(ctx_, *Qa, *Qb, chi_, &p1, &p2);
+    const int tag_saved = ctx_.svd_call_tag;
+    ctx_.svd_call_tag = 1 + direction;   // one warm-start subspace per move direction
+    try {
+        decompose_projectors(ctx_, *Qa, *Qb, chi_, &p1, &p2);
+    } catch(...) {
+        ctx_.svd_call_tag = tag_saved;
+        throw;
+    }
+    ctx_.svd_call_tag = tag_saved;
     P1.reset(p1);
     P2.reset(p2);
 }

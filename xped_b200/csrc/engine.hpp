@@ -253,6 +253,8 @@ public:
     SvdResult tsvd_full(const Tensor& t, int64_t max_keep, double eps_svd, bool preserve_multiplets);
     bool tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, bool preserve_multiplets, SvdResult* out);
     int64_t svd_truncated_calls = 0, svd_truncated_fallbacks = 0, svd_truncated_iters = 0;
+    int svd_call_tag = 0;   // call-site tag of the next tSVD calls ("svd.call_tag"): the truncated path keeps one plan + warm-start subspace per (layout, tag)
+    int opt_svd_truncated = -1;   // -1: XB_SVD_TRUNC environment default (on), 0 / 1: forced (xb_ctx_set_int "svd.truncated")
     std::unordered_map<std::string, std::shared_ptr<RsvdPlan>> rsvd_plans;
     void clear_rsvd_plans();
     Tensor* tsvd_backward(const Tensor& A, const Tensor& U, const Tensor& S, const Tensor& Vd, const Tensor* dU, const Tensor* dS, const Tensor* dVd);

@@ -201,18 +201,20 @@ template <int BM> void launch_one(const double* A, const double* B, double* C, c
 __global__ void splitk_reduce_kernel(const double* __restrict__ scratch, double* __restrict__ C, const SplitKJob* __restrict__ jobs)
 {
     const SplitKJob j = jobs[blockIdx.y];
-    const long long cnt = static_cast<long long>(j.m) * j.n, stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for(long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < cnt; e += stride) {
+    const int cnt = j.m * j.n, stride = gridDim.x * blockDim.x;   // split problems have <= 32 tiles: cnt < 2^31
+    const double* __restrict__ sc = scratch + j.s_off;
+    for(int e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += stride) {
         double sum = 0.0;
-        for(int s = 0; s < j.split; ++s) sum += scratch[j.s_off + s * cnt + e];
-        C[j.c_off + (e % j.m) + (e / j.m) * j.ldc] = sum;
+        for(int s = 0; s < j.split; ++s) sum += sc[static_cast<long long>(s) * cnt + e];
+        const int col = e / j.m;
+        C[j.c_off + (e - col * j.m) + static_cast<long long>(col) * j.ldc] = sum;
     }
 }
 
 void launch_splitk_reduce(const double* scratch, double* C, const SplitKJob* d_jobs, int n_jobs, cudaStream_t s)
 {
     if(n_jobs == 0) return;
-    splitk_reduce_kernel<<<dim3(8, static_cast<unsigned>(n_jobs)), 256, 0, s>>>(scratch, C, d_jobs);
+    splitk_reduce_kernel<<<dim3(32, static_cast<unsigned>(n_jobs)), 256, 0, s>>>(scratch, C, d_jobs);
     check_cuda(cudaGetLastError(), "splitk_reduce_kernel launch");
 }
 

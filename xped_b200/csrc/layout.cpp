@@ -239,6 +239,7 @@ BasisPtr Context::coupled(const std::vector<BasisPtr>& uncoupled)
     auto it = coupled_cache_.find(key);
     if(it != coupled_cache_.end()) return it->second;
     BasisPtr b = build_fusion_tree(sym, uncoupled);
+    if(coupled_cache_.size() >= 8192) coupled_cache_.clear();   // bases that keep changing (non-converged chi): bound the cache; entries are shared_ptr, users keep theirs
     coupled_cache_.emplace(key, b);
     return b;
 }
@@ -276,6 +277,7 @@ LayoutPtr Context::layout(const std::vector<BasisPtr>& dom, const std::vector<Ba
     L->ccod = coupled(cod);
     fill_sectors(*L, nullptr);
     L->sig = key;
+    if(layout_cache_.size() >= 8192) layout_cache_.clear();
     layout_cache_.emplace(key, L);
     return L;
 }
@@ -300,6 +302,7 @@ LayoutPtr Context::layout_custom(const std::vector<BasisPtr>& dom, const std::ve
         if(L->cdom->find(q) < 0 || L->ccod->find(q) < 0) throw std::invalid_argument("layout_custom: sector not in both coupled bases");
     fill_sectors(*L, &sectors);
     L->sig = key;
+    if(layout_cache_.size() >= 8192) layout_cache_.clear();
     layout_cache_.emplace(key, L);
     return L;
 }
@@ -1158,6 +1161,7 @@ std::shared_ptr<DistPermutePlan> Context::dist_permute_plan(const LayoutPtr& in,
     lower_tasks(*this, local_tasks, ts.leg_of, ts.N, P.local);
     lower_tasks(*this, remote_tasks, ts.leg_of, ts.N, P.remote);
     P.pack.bytes = 16 * P.send_total;
+    if(dist_plan_cache_.size() >= 512) dist_plan_cache_.clear();   // plans own device tables; callers hold shared_ptr copies while they run
     dist_plan_cache_.emplace(key, plan);
     return plan;
 }

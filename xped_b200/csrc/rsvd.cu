@@ -343,6 +343,32 @@ __global__ void rsvd_identity_kernel(double* __restrict__ X, const RsvdSec* __re
         X[s.x_off + e] = (e % s.nb == e / s.nb) ? 1.0 : 0.0;
 }
 
+// warm start: X[:, r] = previous Ritz vector with the r-th largest value of its sector (column order from the previous selection); the last `nrand`
+// columns of every projected sector are fresh random vectors (a direction the previous subspace lacked shows up through them)
+__global__ void rsvd_warm_start_kernel(double* __restrict__ X, const double* __restrict__ Vprev, const int* __restrict__ perm_prev, const RsvdSec* __restrict__ secs,
+                                       int nrand, unsigned long long seed)
+{
+    const RsvdSec s = secs[blockIdx.y];
+    for(int r = blockIdx.x; r < s.K; r += gridDim.x) {
+        double* dst = X + s.x_off + static_cast<long long>(r) * s.nb;
+        if(s.direct) {
+            for(int i = threadIdx.x; i < s.nb; i += blockDim.x) dst[i] = i == r ? 1.0 : 0.0;
+        } else if(r < s.K - nrand) {
+            const double* src = Vprev + s.x_off + static_cast<long long>(perm_prev[s.s_off + r]) * s.nb;
+            for(int i = threadIdx.x; i < s.nb; i += blockDim.x) dst[i] = src[i];
+        } else {
+            for(int i = threadIdx.x; i < s.nb; i += blockDim.x) {
+                unsigned long long z = seed ^ (static_cast<unsigned long long>(s.x_off + static_cast<long long>(r) * s.nb + i) * 0xD1342543DE82EF95ull);
+                z += 0x9E3779B97F4A7C15ull;
+                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                z ^= z >> 31;
+                dst[i] = static_cast<double>(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+            }
+        }
+    }
+}
+
 // partial squared Frobenius norms of the sector blocks (fixed partition => deterministic)
 __global__ void rsvd_norm2_kernel(const double* __restrict__ A, const RsvdSec* __restrict__ secs, double* __restrict__ part)
 {
@@ -364,85 +390,152 @@ __global__ void rsvd_norm2_kernel(const double* __restrict__ A, const RsvdSec* _
 }
 
 // Cholesky factor of the Gram matrix G (K x K, + shift_rel * max diag) and M = L^-T (upper triangular) so that Y M has orthonormal
-// columns.  One CTA per projected sector; the matrix lives in shared memory (pitch K + 1).  diag[sector] = min pivot / max diagonal
-// (~ 1 / cond^2 of the basis); a non-positive pivot sets *bad (the pass is then not an orthonormalisation).
-constexpr int CHOL_THREADS = 1024;
-__global__ void __launch_bounds__(CHOL_THREADS)
+// columns.  One CTA per projected sector, the whole matrix REGISTER-resident: 32 x 32 threads, thread (ty, tx) owns the elements
+// (i, c) with i = ty (mod 32), c = tx (mod 32) -- NB x NB doubles, NB = ceil(K / 32).  Right-looking factorisation: the owners of
+// column j publish it (unscaled) in shared memory, everybody applies the rank-1 update to its own elements: ONE barrier per column
+// (the column buffer is double-buffered, pivots through rsqrt: no division).  Then L X = 1 is solved in place the same way (the owners
+// publish column j of L and the finished row j of X, rank-1 update of the rows below: no reductions, one barrier per row) and M = X^T is written out.
+// diag[sector] = min pivot / max diagonal (~ 1 / cond^2 of the basis); a non-positive pivot sets *bad (the pass is then not an
+// orthonormalisation).
+template <int NBR, int NBC, int TY>   // rows i = ii * TY + ty (ii < NBR), columns c = cc * 32 + tx (cc < NBC); NBR * TY >= K, NBC * 32 >= K
+__global__ void __launch_bounds__(32 * TY, 1)
 rsvd_chol_kernel(const double* __restrict__ G, double* __restrict__ M, const RsvdSec* __restrict__ secs, const int* __restrict__ list, double shift_rel,
                  double* __restrict__ diag, int* __restrict__ bad)
 {
-    extern __shared__ __align__(16) double csm[];
+    __shared__ double col[2][NBC * 32], row[2][NBC * 32], dinv[NBC * 32];
+    __shared__ double red[32];
     const int sec = list[blockIdx.x];
     const RsvdSec s = secs[sec];
-    const int K = s.K, ld = K + 1, tid = threadIdx.x, T = blockDim.x;
-    double* S = csm;              // K x K, pitch ld (lower triangle used)
-    double* dl = csm + ld * K;    // diagonal of L
-    __shared__ double sh_max, sh_minpiv;
-    __shared__ int sh_bad;
+    const int K = s.K, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const double* g = G + s.g_off;
-    for(int e = tid; e < K * K; e += T) {
-        const int i = e % K, j = e / K;
-        S[i + j * ld] = g[e];
-    }
-    if(tid == 0) {
-        sh_bad = 0;
-        sh_minpiv = 1.e300;
-    }
+    double a[NBR][NBC];
+    double gmax = 0.0;
+#pragma unroll
+    for(int ii = 0; ii < NBR; ++ii)
+#pragma unroll
+        for(int cc = 0; cc < NBC; ++cc) {
+            const int i = ii * TY + ty, c = cc * 32 + tx;
+            a[ii][cc] = (i < K && c < K) ? g[i + c * K] : (i == c ? 1.0 : 0.0);   // identity padding: decoupled
+            if(i == c && i < K) gmax = fmax(gmax, a[ii][cc]);
+        }
+    // largest diagonal entry (every thread ends up with it)
+    for(int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if(tx == 0) red[ty] = gmax;
     __syncthreads();
-    if(tid < 32) {
-        double m = 0.0;
-        for(int j = tid; j < K; j += 32) m = fmax(m, S[j + j * ld]);
-        for(int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if(tid == 0) sh_max = m;
-    }
-    __syncthreads();
-    const double gmax = sh_max > 0.0 ? sh_max : 1.0;
-    const double shift = shift_rel * gmax;
+    gmax = tx < TY ? red[tx] : 0.0;
+    for(int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if(!(gmax > 0.0)) gmax = 1.0;
+    const double shift = shift_rel * gmax, gmax_inv = 1.0 / gmax;
+    // ---- right-looking Cholesky: one barrier per column, no divisions (rsqrt of the pivot, inverse pivot = rsqrt^2).  Few warps with many
+    // elements each: the per-column scalar work is paid per warp and the kernel is bound by the instruction issue rate.
+    double minpiv = 1.e300;
+    bool anybad = false;
     for(int j = 0; j < K; ++j) {
-        double d = S[j + j * ld] + shift;
-        bool isbad = false;
+        const int jc = j >> 5, jx = j & 31, b = j & 1;
+        if(tx == jx) {
+#pragma unroll
+            for(int cc = 0; cc < NBC; ++cc)
+                if(cc == jc) {
+#pragma unroll
+                    for(int ii = 0; ii < NBR; ++ii) col[b][ii * TY + ty] = a[ii][cc];
+                }
+        }
+        __syncthreads();
+        double d = col[b][j] + shift;
         if(!(d > 0.0) || !isfinite(d)) {
-            isbad = true;
+            anybad = true;
             d = gmax * 1.e-30;
         }
-        const double ljj = sqrt(d), inv = 1.0 / ljj;
-        if(tid == 0) {
-            dl[j] = ljj;
-            if(isbad) sh_bad = 1;
-            sh_minpiv = fmin(sh_minpiv, d / gmax);
+        minpiv = fmin(minpiv, d * gmax_inv);
+        const double rs = rsqrt(d), inv = rs * rs;
+        if(tid == 0) dinv[j] = rs;   // 1 / L_jj for the inversion
+        // masked multipliers instead of predicated updates: rows / columns <= j contribute a - 0 * x = a (exactly), so the NBR x NBC update is
+        // NBR + NBC selects and NBR * NBC plain FMAs
+        double ci[NBR], cj[NBC];
+#pragma unroll
+        for(int k = 0; k < NBR; ++k) ci[k] = (k * TY + ty > j) ? col[b][k * TY + ty] : 0.0;
+#pragma unroll
+        for(int k = 0; k < NBC; ++k) cj[k] = (k * 32 + tx > j) ? col[b][k * 32 + tx] * inv : 0.0;
+#pragma unroll
+        for(int ii = 0; ii < NBR; ++ii)
+#pragma unroll
+            for(int cc = 0; cc < NBC; ++cc) a[ii][cc] = fma(-ci[ii], cj[cc], a[ii][cc]);
+        if(tx == jx) {   // column j of L (zeros above the diagonal)
+#pragma unroll
+            for(int cc = 0; cc < NBC; ++cc)
+                if(cc == jc) {
+#pragma unroll
+                    for(int ii = 0; ii < NBR; ++ii) {
+                        const int i = ii * TY + ty;
+                        a[ii][cc] = i > j ? ci[ii] * rs : (i == j ? d * rs : 0.0);
+                    }
+                }
         }
-        __syncthreads();   // everybody has read the pivot
-        for(int i = j + 1 + tid; i < K; i += T) S[i + j * ld] *= inv;
-        __syncthreads();
-        // trailing update of the lower triangle: warp w takes columns c = j + 1 + w, + 32, ...; lanes run down the column
-        for(int c = j + 1 + (tid >> 5); c < K; c += T >> 5) {
-            const double f = S[c + j * ld];
-            for(int i = c + (tid & 31); i < K; i += 32) S[i + c * ld] = fma(-S[i + j * ld], f, S[i + c * ld]);
-        }
-        __syncthreads();
     }
-    // M(c, k) = (L^-1)(k, c): four lanes per column c of L^-1 (forward substitution, lanes split the dot products);
-    // x_c[c] = 1 / L_cc ; x_c[i] = -(sum_{k=c}^{i-1} L_ik x_c[k]) / L_ii ; stored at m_out[c + i * K].  All threads run the same trip counts.
+    __syncthreads();
+    // ---- X = L^-1 in place, row by row (solve L X = 1 right-looking): at step j the owners publish column j of L and the finished row j of X
+    // (= R_j / L_jj); every element (i > j, c <= j) takes its rank-1 update.  Position (i, c) holds L_ic until step c, the running X_ic afterwards.
+#pragma unroll
+    for(int ii = 0; ii < NBR; ++ii)
+#pragma unroll
+        for(int cc = 0; cc < NBC; ++cc)
+            if(cc * 32 + tx > ii * TY + ty) a[ii][cc] = 0.0;   // strict upper triangle: symmetric left-overs of the updates
+    for(int j = 0; j < K; ++j) {
+        const int jc = j >> 5, jx = j & 31, b = j & 1, jr = j % TY, jrr = j / TY;
+        const double xjj = dinv[j];
+        if(tx == jx) {
+#pragma unroll
+            for(int cc = 0; cc < NBC; ++cc)
+                if(cc == jc) {
+#pragma unroll
+                    for(int ii = 0; ii < NBR; ++ii) col[b][ii * TY + ty] = a[ii][cc];   // L[:, j] (rows > j are still L)
+                }
+        }
+        if(ty == jr) {
+#pragma unroll
+            for(int ii = 0; ii < NBR; ++ii)
+                if(ii == jrr) {
+#pragma unroll
+                    for(int cc = 0; cc < NBC; ++cc) {
+                        const int c = cc * 32 + tx;
+                        const double v = c < j ? a[ii][cc] * xjj : (c == j ? xjj : 0.0);   // finished row j of X
+                        a[ii][cc] = v;
+                        row[b][c] = v;
+                    }
+                }
+        }
+        __syncthreads();
+        double ci[NBR], rj[NBC];
+#pragma unroll
+        for(int k = 0; k < NBR; ++k) ci[k] = (k * TY + ty > j) ? col[b][k * TY + ty] : 0.0;   // L[i][j], rows below j only
+#pragma unroll
+        for(int k = 0; k < NBC; ++k) rj[k] = (k * 32 + tx < j) ? row[b][k * 32 + tx] : 0.0;   // X[j][c], columns left of j only
+#pragma unroll
+        for(int ii = 0; ii < NBR; ++ii)
+#pragma unroll
+            for(int cc = 0; cc < NBC; ++cc) a[ii][cc] = fma(-ci[ii], rj[cc], a[ii][cc]);
+        if(tx == jx) {   // column j below the diagonal: L_ij -> X_ij = -L_ij / L_jj
+#pragma unroll
+            for(int cc = 0; cc < NBC; ++cc)
+                if(cc == jc) {
+#pragma unroll
+                    for(int ii = 0; ii < NBR; ++ii)
+                        if(ii * TY + ty > j) a[ii][cc] = -ci[ii] * xjj;
+                }
+        }
+    }
+    // M(r, c) = X(c, r)
     double* m_out = M + s.g_off;
-    const int lane4 = tid & 3, c = tid >> 2;
-    const bool has_col = c < K;
-    if(has_col) {
-        if(lane4 == 0) m_out[c + c * K] = 1.0 / dl[c];
-        for(int i = lane4; i < c; i += 4) m_out[c + i * K] = 0.0;
-    }
-    __syncwarp(0xffffffffu);
-    for(int i = 1; i < K; ++i) {
-        double acc = 0.0;
-        if(has_col && i > c)
-            for(int k = c + lane4; k < i; k += 4) acc = fma(S[i + k * ld], m_out[c + k * K], acc);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if(has_col && i > c && lane4 == 0) m_out[c + i * K] = -acc / dl[i];
-        __syncwarp(0xffffffffu);
-    }
+#pragma unroll
+    for(int ii = 0; ii < NBR; ++ii)
+#pragma unroll
+        for(int cc = 0; cc < NBC; ++cc) {
+            const int i = ii * TY + ty, c = cc * 32 + tx;
+            if(i < K && c < K) m_out[c + i * K] = a[ii][cc];
+        }
     if(tid == 0) {
-        diag[sec] = sh_minpiv;
-        if(sh_bad) atomicOr(bad, 1);
+        diag[sec] = minpiv;
+        if(anybad) atomicOr(bad, 1);
     }
 }
 
@@ -641,6 +734,11 @@ struct RsvdPlan
     PreparedGemm g_bx, g_bx_all, g_gy, g_ym, g_bty, g_gx2, g_x2m, g_gx, g_xm, g_btw, g_xv;
     size_t chol_smem = 0;
     double tol_rel = 0.0, shift_it = 0.0;
+    double* dVprev = nullptr;   // Ritz vectors of the previous successful call on this plan (warm start)
+    int* d_perm_prev = nullptr;
+    bool have_prev = false;
+    int hold = 0;   // calls during which iters_hint is not lowered (after a projection that was not converged)
+    cudaGraphExec_t graph_warm = nullptr;
     cudaGraphExec_t graph_start = nullptr;
     std::map<int, cudaGraphExec_t> graph_iter;   // key: number of iterations
     std::map<int, int> graph_launches;           // kernel launches inside each graph (key -1: start)
@@ -649,6 +747,7 @@ struct RsvdPlan
     ~RsvdPlan()
     {
         if(graph_start) cudaGraphExecDestroy(graph_start);
+        if(graph_warm) cudaGraphExecDestroy(graph_warm);
         for(auto& kv : graph_iter)
             if(kv.second) cudaGraphExecDestroy(kv.second);
         for(PreparedGemm* g : {&g_bx, &g_bx_all, &g_gy, &g_ym, &g_bty, &g_gx2, &g_x2m, &g_gx, &g_xm, &g_btw, &g_xv}) {
@@ -665,7 +764,17 @@ namespace {
 
 void rsvd_chol(RsvdPlan& P, double shift_rel)
 {
-    rsvd_chol_kernel<<<P.n_proj, CHOL_THREADS, P.chol_smem, P.ctx->stream>>>(P.dG, P.dM, P.d_secs, P.d_proj, shift_rel, P.dDiag, P.d_bad);
+    cudaStream_t s = P.ctx->stream;
+#define XB_CHOL(NBR, NBC, TY) rsvd_chol_kernel<NBR, NBC, TY><<<P.n_proj, 32 * TY, 0, s>>>(P.dG, P.dM, P.d_secs, P.d_proj, shift_rel, P.dDiag, P.d_bad)
+    switch((P.K0 + 31) / 32) {
+    // few warps with many elements each: the kernel is bound by the instruction issue rate (per-step overhead is paid per warp)
+    case 1: XB_CHOL(4, 1, 8); break;
+    case 2: XB_CHOL(8, 2, 8); break;
+    case 3: XB_CHOL(12, 3, 8); break;
+    case 4: XB_CHOL(16, 4, 8); break;
+    default: XB_CHOL(10, 5, 16); break;  // K <= 160: 50 doubles per thread at 512 threads
+    }
+#undef XB_CHOL
     check_cuda(cudaGetLastError(), "rsvd_chol_kernel launch");
     ++P.ctx->launches;
 }
@@ -679,18 +788,26 @@ void rsvd_polish(RsvdPlan& P)
     rsvd_chol(P, 0.0);
     c.launch_gemm(P.g_x2m);
 }
-void rsvd_start(RsvdPlan& P)
-{   // random X (identity on the exactly treated sectors), ||A_q||_F^2, orthonormalise
+constexpr int WARM_RANDOM_COLS = 16;
+void rsvd_start(RsvdPlan& P, bool warm)
+{   // X = random (cold) or the previous Ritz vectors + a few random columns (warm), identity on the exactly treated sectors; ||A_q||_F^2; orthonormalise
     Context& c = *P.ctx;
     cudaStream_t s = c.stream;
     check_cuda(cudaMemsetAsync(P.d_bad, 0, sizeof(int), s), "rsvd flag reset");
     check_cuda(cudaMemsetAsync(P.dRes, 0, sizeof(double) * std::max<long long>(P.so, 1), s), "rsvd residual reset");
-    launch_fill_random(P.dX, 0x5eedc0ffeeull + static_cast<uint64_t>(P.xo), P.xo, s);
-    ++c.launches;
-    if(!P.direct_list.empty()) {
-        rsvd_identity_kernel<<<dim3(8, static_cast<unsigned>(P.direct_list.size())), 256, 0, s>>>(P.dX, P.d_secs, P.d_direct, static_cast<int>(P.direct_list.size()));
-        check_cuda(cudaGetLastError(), "rsvd_identity_kernel launch");
+    if(warm) {
+        rsvd_warm_start_kernel<<<dim3(static_cast<unsigned>(P.K0), static_cast<unsigned>(P.nsec)), 128, 0, s>>>(P.dX, P.dVprev, P.d_perm_prev, P.d_secs, WARM_RANDOM_COLS,
+                                                                                                                0x5eedc0ffeeull + static_cast<uint64_t>(P.xo));
+        check_cuda(cudaGetLastError(), "rsvd_warm_start_kernel launch");
         ++c.launches;
+    } else {
+        launch_fill_random(P.dX, 0x5eedc0ffeeull + static_cast<uint64_t>(P.xo), P.xo, s);
+        ++c.launches;
+        if(!P.direct_list.empty()) {
+            rsvd_identity_kernel<<<dim3(8, static_cast<unsigned>(P.direct_list.size())), 256, 0, s>>>(P.dX, P.d_secs, P.d_direct, static_cast<int>(P.direct_list.size()));
+            check_cuda(cudaGetLastError(), "rsvd_identity_kernel launch");
+            ++c.launches;
+        }
     }
     rsvd_norm2_kernel<<<dim3(NORM_PARTS, P.nsec), 256, 0, s>>>(P.dA, P.d_secs, P.dNorm);
     check_cuda(cudaGetLastError(), "rsvd_norm2_kernel launch");
@@ -803,7 +920,8 @@ std::shared_ptr<RsvdPlan> build_rsvd_plan(Context& ctx, const Layout& L, int K0)
                  bG = al(sizeof(double) * std::max<long long>(P.go, 1)), bA = al(sizeof(double) * std::max<long long>(P.ao, 1));
     const size_t bDiag = al(sizeof(double) * nsec), bRes = al(sizeof(double) * std::max<long long>(P.so, 1)), bNorm = al(sizeof(double) * nsec * NORM_PARTS);
     const size_t bSecs = al(sizeof(RsvdSec) * nsec), bList = al(sizeof(int) * nsec);
-    const size_t total = bA + 3 * bX + 2 * bY + 2 * bG + bDiag + bRes + bNorm + bSecs + 2 * bList + 256;
+    const size_t bPerm = al(sizeof(int) * std::max<long long>(P.so, 1));
+    const size_t total = bA + 4 * bX + 2 * bY + 2 * bG + bDiag + bRes + bNorm + bSecs + 2 * bList + bPerm + 256;
     check_cuda(cudaMalloc(reinterpret_cast<void**>(&P.arena), total), "rsvd arena");
     char* p = P.arena;
     auto take = [&](size_t b) { char* r = p; p += b; return r; };
@@ -811,6 +929,8 @@ std::shared_ptr<RsvdPlan> build_rsvd_plan(Context& ctx, const Layout& L, int K0)
     P.dX = reinterpret_cast<double*>(take(bX));
     P.dX2 = reinterpret_cast<double*>(take(bX));
     P.dZ = reinterpret_cast<double*>(take(bX));
+    P.dVprev = reinterpret_cast<double*>(take(bX));
+    P.d_perm_prev = reinterpret_cast<int*>(take(bPerm));
     P.dY = reinterpret_cast<double*>(take(bY));
     P.dY2 = reinterpret_cast<double*>(take(bY));
     P.dG = reinterpret_cast<double*>(take(bG));
@@ -853,8 +973,6 @@ std::shared_ptr<RsvdPlan> build_rsvd_plan(Context& ctx, const Layout& L, int K0)
     P.g_xm = ctx.prepare_gemm(P.dX, P.dM, P.dX2, i_x2m);
     P.g_btw = ctx.prepare_gemm(P.dA, nullptr, P.dZ, i_btw);   // Zr = B^T W: the B operand (Jacobi work matrix) is set per check
     P.g_xv = ctx.prepare_gemm(P.dX, nullptr, P.dX2, i_xv);    // V = X Vrot: the B operand (Jacobi accumulator) is set per check
-    P.chol_smem = sizeof(double) * (static_cast<size_t>(K0 + 1) * K0 + K0);
-    check_cuda(cudaFuncSetAttribute(rsvd_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024), "rsvd chol smem attr");
     P.tol_rel = 16.0 * 2.220446049250313e-16 * std::sqrt(static_cast<double>(P.mb_max));
     P.shift_it = 1.e-13 * P.mb_max;   // keeps the factorisation of a numerically rank-deficient basis going (subspace iteration only needs a basis)
     P.sel_secs.resize(nsec);
@@ -875,7 +993,8 @@ void Context::clear_rsvd_plans() { rsvd_plans.clear(); }
 
 bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, bool preserve_multiplets, SvdResult* out)
 {
-    static const int mode = std::getenv("XB_SVD_TRUNC") ? std::atoi(std::getenv("XB_SVD_TRUNC")) : 1;
+    static const int env_mode = std::getenv("XB_SVD_TRUNC") ? std::atoi(std::getenv("XB_SVD_TRUNC")) : 1;
+    const int mode = opt_svd_truncated >= 0 ? opt_svd_truncated : env_mode;
     static const bool verbose = std::getenv("XB_SVD_PROF") != nullptr;
     static const bool no_graph = std::getenv("XB_SVD_NOGRAPH") != nullptr;
     static const int max_iters = std::getenv("XB_SVD_TRUNC_MAXIT") ? std::atoi(std::getenv("XB_SVD_TRUNC_MAXIT")) : 60;
@@ -897,7 +1016,7 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
         }
         if(n_proj == 0 || sum_k * 2 > sum_nb || sum_k > SEL_MAX) return false;
     }
-    const std::string key = L.sig + "#" + std::to_string(K0);
+    const std::string key = L.sig + "#" + std::to_string(K0) + "#" + std::to_string(svd_call_tag);   // one plan (and warm-start state) per call site
     auto it = rsvd_plans.find(key);
     if(it == rsvd_plans.end()) {
         if(rsvd_plans.size() >= 12) {
@@ -929,9 +1048,16 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
 
     mark(0);
     check_cuda(cudaMemcpyAsync(P.dA, t.d, sizeof(double) * L.size, cudaMemcpyDeviceToDevice, s), "rsvd copy-in");
-    run_or_replay(P, &P.graph_start, -1, use_graph, [&]() { rsvd_start(P); });
+    static const bool no_warm = std::getenv("XB_SVD_NOWARM") != nullptr;
+    const bool warm = P.have_prev && !no_warm;
+    if(warm)
+        run_or_replay(P, &P.graph_warm, -2, use_graph, [&]() { rsvd_start(P, true); });
+    else
+        run_or_replay(P, &P.graph_start, -1, use_graph, [&]() { rsvd_start(P, false); });
+    P.have_prev = false;
 
     int iters_done = 0, next_iters = P.iters_hint > 0 ? P.iters_hint : first_iters, checks = 0;
+    if(!warm && P.iters_hint > 0) next_iters = std::max(next_iters, first_iters);
     bool ok = false;
     JacobiResult J;
     Selection sel;
@@ -972,9 +1098,9 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
             lap(2, 3, t_chk);
             std::fprintf(stderr,
                          "[rsvd] K %d sectors %d (projected %d) iters %d: verdict %d max_res %.2e (tol %.2e) rate %.3f nkeep %d cut/smax %.2e jacobi sweeps %d bad %d | ms: "
-                         "iterate %.3f jacobi %.3f check %.3f graph %d\n",
+                         "iterate %.3f jacobi %.3f check %.3f graph %d warm %d\n",
                          K0, nsec, P.n_proj, iters_done, sel.hdr.verdict, sel.hdr.max_res, P.tol_rel, sel.hdr.rate, sel.hdr.nkeep,
-                         sel.hdr.smax > 0 ? sel.hdr.cut / sel.hdr.smax : 0.0, J.sweeps + 1, h_bad, t_iter, t_jac, t_chk, use_graph ? 1 : 0);
+                         sel.hdr.smax > 0 ? sel.hdr.cut / sel.hdr.smax : 0.0, J.sweeps + 1, h_bad, t_iter, t_jac, t_chk, use_graph ? 1 : 0, warm ? 1 : 0);
             t_iter = t_jac = t_chk = 0.f;
         }
         if(sel.hdr.verdict == 0 && !h_bad) {
@@ -996,14 +1122,27 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
     }
     svd_truncated_iters += iters_done;
     if(ok) {
-        // next call on this layout: start with what was needed (one projection instead of two); shrink slowly when there was slack
-        P.iters_hint = (checks == 1 && sel.hdr.max_res < 0.02 * P.tol_rel && iters_done > 2) ? iters_done - 1 : iters_done;
+        // next call from this call site: when one projection sufficed, try fewer iterations (the warm start may need far fewer than a cold one; the
+        // residual floor hides how many were spare); when it did not, remember what was needed and hold that for a while
+        if(checks == 1) {
+            if(P.hold > 0)
+                --P.hold;
+            else
+                P.iters_hint = std::max(2, std::min(iters_done - 1, static_cast<int>(std::ceil(0.6 * iters_done))));
+        } else {
+            P.iters_hint = iters_done;
+            P.hold = 6;
+        }
         std::vector<FactorSrc> src(nsec);
         for(int i = 0; i < nsec; ++i) {
             const RsvdSec& c = P.secs[i];
             src[i] = {J.blocks[i].w_off, c.x_off, c.s_off, c.mb, c.nb, c.mb, c.nb, c.tr ? 0 : 1};
         }
         *out = svd_finish(*this, L, sel, src, J.d_W, P.dX2, J.d_sigma);
+        // keep the Ritz vectors and their order for the next call from this call site
+        check_cuda(cudaMemcpyAsync(P.dVprev, P.dX2, sizeof(double) * P.xo, cudaMemcpyDeviceToDevice, s), "rsvd warm-start save");
+        check_cuda(cudaMemcpyAsync(P.d_perm_prev, sel.d_perm, sizeof(int) * P.so, cudaMemcpyDeviceToDevice, s), "rsvd warm-start save");
+        P.have_prev = true;
     } else
         ++svd_truncated_fallbacks;
     if(sel.d_perm) check_cuda(cudaFreeAsync(sel.d_perm, s), "rsvd free");

@@ -45,6 +45,14 @@ class Context:
         check(self.lib.xb_ctx_stats(self.h, out))
         return {"launches": out[0], "plan_hits": out[1], "plan_misses": out[2]}
 
+    def set_int(self, key, value):
+        check(self.lib.xb_ctx_set_int(self.h, key.encode(), int(value)))
+
+    def get_int(self, key):
+        v = C.c_int64()
+        check(self.lib.xb_ctx_get_int(self.h, key.encode(), C.byref(v)))
+        return v.value
+
     def flush_l2(self):
         check(self.lib.xb_flush_l2(self.h))
 
@@ -194,6 +202,46 @@ class Tensor:
         buf = (C.c_int64 * max(5 * n, 1))()
         check(self.ctx.lib.xb_tensor_tree_pairs(self.h, buf))
         return np.frombuffer(buf, dtype=np.int64, count=5 * n).reshape(n, 5).copy()
+
+    # ---- sub-blocks of one tree pair (Tensor::subBlock / view / subMatrix, Tensor.hpp:191-216); `pair` = index in tree_pairs() order
+    def tree_pair_trees(self, pair):
+        """(q_uncoupled per leg, q_intermediates, q_coupled, dims per leg) of the fusion-tree pair."""
+        nq, R, Cr = max(self.ctx.Nq, 1), self.rank, self.corank
+        ni = max(R - 2, 0) + max(Cr - 2, 0)
+        qu, qi, qc = (C.c_int * ((R + Cr) * nq))(), (C.c_int * max(ni * nq, 1))(), (C.c_int * nq)()
+        dims = (C.c_int64 * (R + Cr))()
+        check(self.ctx.lib.xb_tensor_tree_pair_trees(self.h, int(pair), qu, qi, qc, dims))
+        n = self.ctx.Nq
+        return ([tuple(qu[i * nq:i * nq + n]) for i in range(R + Cr)], [tuple(qi[i * nq:i * nq + n]) for i in range(ni)], tuple(qc[:n]), list(dims))
+
+    def find_tree_pair(self, q_uncoupled, q_intermediates, q_coupled):
+        flat = lambda qs: _ints([x for q in qs for x in (q if isinstance(q, (tuple, list)) else (q,))] or [0])
+        return int(self.ctx.lib.xb_tensor_find_tree_pair(self.h, flat(q_uncoupled), flat(q_intermediates), flat([q_coupled])))
+
+    def subBlock(self, pair):
+        """Dense copy of the sub-block as an array of shape f1.dims + f2.dims (column-major over the legs, Tensor.cpp:962-981)."""
+        dims = self.tree_pair_trees(pair)[3]
+        n = int(np.prod(dims)) if dims else 1
+        out = np.empty(n, dtype=np.float64)
+        check(self.ctx.lib.xb_sub_block(self.h, int(pair), out.ctypes.data_as(C.POINTER(C.c_double)), n))
+        return out.reshape(dims, order="F")
+
+    def subMatrix(self, pair):
+        dims = self.tree_pair_trees(pair)[3]
+        r = int(np.prod(dims[:self.rank])) if self.rank else 1
+        return self.subBlock(pair).reshape((r, -1), order="F")
+
+    def setSubBlock(self, pair, block):
+        b = np.asfortranarray(np.asarray(block, dtype=np.float64)).reshape(-1, order="F")
+        b = np.ascontiguousarray(b)
+        check(self.ctx.lib.xb_set_sub_block(self.h, int(pair), b.ctypes.data_as(C.POINTER(C.c_double)), b.size))
+        return self
+
+    def view(self, pair):
+        """(device pointer, leading dimension, rows, cols) of the sub-block in place (Tensor::view)."""
+        ptr, ld, r, c = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(self.ctx.lib.xb_view(self.h, int(pair), C.byref(ptr), C.byref(ld), C.byref(r), C.byref(c)))
+        return ptr.value, ld.value, r.value, c.value
 
     def upload(self, data):
         a = np.ascontiguousarray(data, dtype=np.float64)

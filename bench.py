@@ -111,8 +111,21 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+CPU_KIND_NOTE = ("oracle/xped_oracle: restatement of the reference algorithm (src/PEPS/CTM.cpp, src/Core/Tensor.cpp) executed the way an optimised "
+                 "Eigen + BLAS build runs it -- recoupling coefficients cached per (tensor structure, shift, permutation) like XPED_CACHE_PERMUTE_OUTPUT, "
+                 "sub-block transposes in the compiled kernel oracle/csrc/xped_oracle_kernels.c (serial like the reference's loop), per-block GEMM and "
+                 "gesdd SVD in OpenBLAS / LAPACK with all host threads")
+
+
+def install_fast_oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from xped_oracle import fast
+    fast.install()
+
+
 def time_oracle(warmup, steps):
     import numpy as np  # noqa: F401  (loads the BLAS the oracle's GEMM / SVD calls use)
+    install_fast_oracle()
     ctm = oracle_ctm(0)
     for _ in range(warmup):
         ctm.grow_all()
@@ -147,8 +160,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (counter-based uniform[-1,1] site tensor, seed 0)", "config": config_dict(1),
             "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} grow_all() steps after {args.warmup} warm-up steps, oracle/xped_oracle (numpy restatement; "
-                                       "python loops over tree pairs on 1 core, per-block GEMM/SVD in OpenBLAS/LAPACK threads)"},
+                             "sample": f"{args.steps} grow_all() steps after {args.warmup} warm-up steps; " + CPU_KIND_NOTE},
             "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -165,7 +177,45 @@ def su2_corner_pair(ctx, aux, env, seeds):
     return [ctx.tensor([e, a, a], [e, a, a]).setRandom(s) for s in seeds]
 
 
-def kernel_sections(xb, device, torch):
+def oracle_tensor_like(xo, osym, g):
+    """oracle tensor with the bases and the storage image of a device tensor"""
+    r, c = g.rank, g.corank
+    legs = []
+    for i in range(r + c):
+        b = g.leg_basis(i)
+        ent = [(tuple(q), d) for q, d in b.entries()]
+        if b.IS_CONJ():      # a conjugated leg basis (Qbasis::conj, dual fusion trees): rebuild it as the conj() of its pre-image
+            legs.append(xo.Qbasis.from_list(osym, [(tuple(osym.conj(q)), d) for q, d in ent]).conj())
+        else:
+            legs.append(xo.Qbasis.from_list(osym, ent))
+    t = xo.Tensor(osym, legs[:r], legs[r:])
+    if t.structure() != g.structure():
+        raise RuntimeError("oracle / device structure mismatch")
+    t.data = g.download()
+    return t
+
+
+def cpu_d6_left_move(xb, ctx, ctm, A):
+    install_fast_oracle()
+    import xped_oracle as xo
+    from xped_oracle.ctm import CTM as OCTM
+    osym = xo.Symmetry.SU2()
+    oA = oracle_tensor_like(xo, osym, A)
+    octm = OCTM(oA, 144)
+    for nm in ENV:
+        setattr(octm, nm, oracle_tensor_like(xo, osym, ctm.get(nm)))
+    t0 = time.perf_counter()
+    octm.move(0)
+    dt = time.perf_counter() - t0
+    ctx.sync()
+    ctx.timer_start()
+    ctm.move(0)
+    gpu_ms = ctx.timer_stop()
+    return {"cpu_ms": dt * 1e3, "gpu_ms_same_move": gpu_ms, "cores": blas_threads(), "kind": "port",
+            "sample": "ONE left move (a quarter of a grow_all() step) at D=6 chi=144 from the device's environment after 5 steps; " + CPU_KIND_NOTE}
+
+
+def kernel_sections(xb, device, torch, cpu_d6=False):
     """permute HBM GB/s and contract FP64 TFLOP/s on the large tensors (W4, W3)"""
     out = {}
     # ---- FP64 tensor peak: cuBLAS DGEMM 8192^3 measured here (MEASURED_PEAKS.json has no FP64 entry)
@@ -250,10 +300,83 @@ def kernel_sections(xb, device, torch):
             steps6.append({"ms": ms6, "device_ms": {k: v[0] for k, v in prof6.items()}, "launch_groups": {k: v[1] for k, v in prof6.items()}})
         best = min(steps6, key=lambda r: r["ms"])
         out["ctm_d6_chi144"] = {"op": "grow_all() at D=6 (aux {1:3, 2:3}), chi=144, steps 4 and 5 from FROM_A, entirely on the device", "ms_per_step": best["ms"],
-                                "steps": steps6}
+                                "steps": steps6,
+                                "tsvd": {"truncated_calls": ctx3.get_int("svd.truncated_calls"), "fallbacks_to_full_jacobi": ctx3.get_int("svd.truncated_fallbacks"),
+                                         "subspace_iterations": ctx3.get_int("svd.truncated_iterations")}}
+        if cpu_d6:
+            # the reference algorithm on the host cores at the SAME size: one left move (1 of the 4 moves of a step: two corners, one tSVD of blocks up to
+            # ~3060^2, renormalisation) from the environment the device has now
+            try:
+                out["ctm_d6_chi144"]["cpu_left_move"] = cpu_d6_left_move(xb, ctx3, ctm6, A6)
+            except Exception as e:
+                out["ctm_d6_chi144"]["cpu_left_move"] = {"error": f"{type(e).__name__}: {e}"}
         del ctm6, A6
     except Exception as e:
         out["ctm_d6_chi144"] = {"error": f"{type(e).__name__}: {e}"}
+    # ---- configs[4] size sweep on one GPU: the same U(1) Tensor<2,2> with 8 / 16 / 24 / 32 states per charge
+    try:
+        sweep = []
+        ctxs = xb.Context([("U1", 0, 0)], device=device)
+        for dim in (8, 16, 32):
+            Bs = u1_basis(ctxs, 4, dim)
+            Ts = ctxs.tensor([Bs, Bs], [Bs, Bs]).setRandom(0)
+            tot_ms, tot_b = 0.0, 0.0
+            for p in [(1, 0, 2, 3), (0, 1, 3, 2), (2, 3, 0, 1), (0, 2, 1, 3), (3, 2, 1, 0)]:
+                Ts.bench_permute(0, p, reps=1)
+                ctxs.flush_l2()
+                ms, nbytes = Ts.bench_permute(0, p, reps=3)
+                tot_ms += ms
+                tot_b += nbytes
+            ms, fl = Ts.bench_multiply(Ts, reps=2)
+            sweep.append({"dim_per_charge": dim, "elements": Ts.plainSize(), "permute_GBps_aggregate": tot_b / tot_ms / 1e6, "contract_TFLOPs": fl / ms / 1e9})
+            del Ts
+        out["w4_dim_sweep"] = {"op": "5 permutes (shift 0) + T*T of the U(1) Tensor<2,2>, leg q=-4..4 x dim; dim = 24 is permute_w4 / contract_w4 above", "cases": sweep}
+        # ---- configs[0a]: the small U(1) Tensor<2,2> (q = -2..2 x 4 states: ~2e4 elements): latency-bound, microseconds per operation
+        Bm = u1_basis(ctxs, 2, 4)
+        Tm = ctxs.tensor([Bm, Bm], [Bm, Bm]).setRandom(0)
+        import itertools
+        us = []
+        for shift in (-2, -1, 0, 1, 2):
+            for p in itertools.permutations(range(4)):
+                Tm.bench_permute(shift, p, reps=1)
+                ms, _ = Tm.bench_permute(shift, p, reps=20)
+                us.append(1e3 * ms)
+        us.sort()
+        ms_mm, _ = Tm.bench_multiply(Tm, reps=50)
+        out["small_u1"] = {"op": "configs[0a]: U(1) Tensor<2,2>, leg q=-2..2 x 4 (%d elements): all 24 x 5 permute<shift,p> and T*T" % Tm.plainSize(),
+                           "permute_us_median": us[len(us) // 2], "permute_us_max": us[-1], "multiply_us": 1e3 * ms_mm}
+        del Tm
+        ctxs.close()
+    except Exception as e:
+        out["w4_dim_sweep"] = {"error": f"{type(e).__name__}: {e}"}
+    # ---- configs[2]: U(1) x U(1) Hubbard MPS transfer contraction at bond dimension ~2000 (89 sectors, blocks <= 159)
+    try:
+        from xped_b200.workloads import hubbard_bond_basis
+        ctxh = xb.Context([("U1", 0, 1), ("U1", 0, 0)], device=device)
+        bond = hubbard_bond_basis(2000)
+        loc = [((0, 0), 1), ((1, 1), 1), ((1, -1), 1), ((2, 0), 1)]
+        bb, lb = ctxh.basis(bond), ctxh.basis(loc)
+        comb = dict((tuple(q), d) for q, d in bb.combine(lb).entries())
+        outb = ctxh.basis([(q, min(d, comb[q])) for q, d in bond if q in comb])
+        Ah = ctxh.tensor([bb, lb], [outb]).setRandom(5)
+        Lh = ctxh.tensor([bb], [bb]).setRandom(6)
+        Rh = ctxh.tensor([outb], [outb]).setRandom(7)
+
+        def timed_us(fn, reps=20):
+            fn()
+            ctxh.sync()
+            ctxh.timer_start()
+            for _ in range(reps):
+                fn()
+            return 1e3 * ctxh.timer_stop() / reps
+        out["hubbard_m2000"] = {"op": "configs[2]: contract_L / contract_R on A(2,1), bond basis %d states in %d sectors, four-state Hubbard site" %
+                                      (sum(d for _, d in bond), len(bond)), "A_elements": Ah.plainSize(),
+                                "contract_L_us": timed_us(lambda: xb.contract_L(Lh, Ah, Ah)), "contract_R_us": timed_us(lambda: xb.contract_R(Rh, Ah, Ah)),
+                                "permute_multiply_formulation_us": timed_us(lambda: (Ah @ Rh).permute(1, (0, 1, 2)).multiply(Ah.permute(1, (0, 1, 2)), False, True))}
+        del Ah, Lh, Rh
+        ctxh.close()
+    except Exception as e:
+        out["hubbard_m2000"] = {"error": f"{type(e).__name__}: {e}"}
     # ---- configs[0]: the reference's own benchmarks/bench.cpp workload (SU(2) spin-1/2 chain, L = 20, Minit = 200, Qinit = 10:
     # <Psi|Psi> by dot() ten times, then one sweep of SVD steps); latency-bound at these sizes: reported as ms
     try:
@@ -457,7 +580,7 @@ def run_b200(args):
     if rank == 0 and not args.no_extras:
         ksampler = ClockSampler(local)
         ksampler.start()
-        extras, dgemm_peak = kernel_sections(xb, local, torch)
+        extras, dgemm_peak = kernel_sections(xb, local, torch, cpu_d6=(world == 1 and args.cpu_steps > 0))
         extras["clocks"] = ksampler.stop()
 
     if rank == 0:
@@ -512,8 +635,8 @@ def run_b200(args):
             line["rdm_energy"] = energy
         if cpu_sps is not None:
             line["cpu_baseline"] = {"value": cpu_sps, "unit": "steps/s", "cores": blas_threads(), "kind": "port",
-                                    "sample": f"{args.cpu_steps} grow_all() steps of the same D=4 chi=64 workload after 3 warm-up steps, oracle/xped_oracle "
-                                              "(numpy restatement of the reference algorithm)", "ms_per_step": cpu_ms}
+                                    "sample": f"{args.cpu_steps} grow_all() steps of the same D=4 chi=64 workload after 3 warm-up steps; " + CPU_KIND_NOTE,
+                                    "ms_per_step": cpu_ms}
         print(json.dumps(line), file=real_stdout or sys.stdout, flush=True)
     ctx.close()
     if world > 1:

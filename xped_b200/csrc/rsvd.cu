@@ -770,7 +770,16 @@ void rsvd_chol(RsvdPlan& P, double shift_rel)
     // few warps with many elements each: the kernel is bound by the instruction issue rate (per-step overhead is paid per warp)
     case 1: XB_CHOL(4, 1, 8); break;
     case 2: XB_CHOL(8, 2, 8); break;
-    case 3: XB_CHOL(12, 3, 8); break;
+    case 3: {
+        static const int ty = std::getenv("XB_CHOL_TY") ? std::atoi(std::getenv("XB_CHOL_TY")) : 8;   // experiment knob
+        if(ty == 4)
+            XB_CHOL(24, 3, 4);
+        else if(ty == 16)
+            XB_CHOL(6, 3, 16);
+        else
+            XB_CHOL(12, 3, 8);
+        break;
+    }
     case 4: XB_CHOL(16, 4, 8); break;
     default: XB_CHOL(10, 5, 16); break;  // K <= 160: 50 doubles per thread at 512 threads
     }
@@ -1111,6 +1120,7 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
         // predicted number of further iterations: the residual of a kept triplet shrinks by (sigma_{K+1} / sigma_i)^2 <= rate^2 per iteration
         const double r2 = std::min(0.98, std::max(1.e-4, sel.hdr.rate * sel.hdr.rate));
         const double need = std::log(std::max(P.tol_rel / std::max(sel.hdr.max_res, 1.e-300), 1.e-300)) / std::log(r2);
+        if(sel.hdr.max_res <= 1.0 && need > static_cast<double>(max_iters - iters_done)) break;   // flat spectrum: the budget cannot be met, hand over to the full path now
         next_iters = static_cast<int>(std::min<double>(std::max(2.0, std::ceil(need) + 1.0), 16.0));
         if(sel.hdr.max_res > 1.0) next_iters = 8;   // sentinel: a value next to the cut is far from converged
         // continue from the Ritz vectors

@@ -223,6 +223,29 @@ int xb_avg_two_site(xb_ctx* ctx, const xb_tensor* rho, const xb_tensor* op, doub
 int xb_rdm_one_site(xb_ctx* ctx, const xb_tensor* rho, xb_tensor** rho1);
 int xb_avg_one_site(xb_ctx* ctx, const xb_tensor* rho1, const xb_tensor* op, double* out);
 
+/* ---- reverse-mode AD (include/Xped/AD/ADTensor.hpp; replaces the stan::math tape): between xb_tape_begin and xb_tape_end the differentiable entry
+ * points above record their reverse rule -- xb_permute (:171-185, permute_adj), xb_multiply (:749-758), xb_contract (:193-219, as its three permutes and the
+ * product), xb_adjoint (:137-150), xb_twist (:589-602), xb_axpby (:640-676), xb_diag_map (:559-586), xb_tsvd (:237-374, full path + xb_tsvd_backward),
+ * xb_tensor_clone, xb_normalize_max (maxNorm rule :502-529 fused with the division), xb_normalize_trace (trace rule :531-546 with operator*(tensor, var)
+ * :690-706), xb_decompose.  The loss is a weighted sum of traces: xb_tape_seed_trace(v, w) adds w * d trace(v) / d v (Tensor::WeightedIdentity); any other
+ * cotangent can be injected with xb_tape_seed.  xb_tape_backward runs the rules in reverse order; xb_tape_grad returns a copy of the accumulated adjoint
+ * (plain d loss / d m_data element, the convention of the reference's adj() tensors) or NULL.  The tape keeps the values it needs alive until xb_tape_end. */
+int xb_tape_begin(xb_ctx* ctx);
+int xb_tape_end(xb_ctx* ctx);
+int xb_tape_seed_trace(xb_ctx* ctx, const xb_tensor* v, double weight);
+int xb_tape_seed(xb_ctx* ctx, const xb_tensor* v, const xb_tensor* adj);
+int xb_tape_backward(xb_ctx* ctx);
+int xb_tape_grad(xb_ctx* ctx, const xb_tensor* v, xb_tensor** g);
+int xb_tape_size(xb_ctx* ctx, int64_t* n_nodes);
+/* t * (1 / t.maxNorm())  (renormalize_*: src/PEPS/CTM.cpp:1369,1381,1409) and x * (1 / trace(x * w))  (density-matrix normalisation, CTM.cpp:660-667) */
+int xb_normalize_max(xb_ctx* ctx, const xb_tensor* t, xb_tensor** out);
+int xb_normalize_trace(xb_ctx* ctx, const xb_tensor* x, const xb_tensor* w, xb_tensor** out);
+/* E(A) = avg(rho_h, op_h) + avg(rho_v, op_v) of the 1x1 iPEPS A after `steps` grow_all() steps from CTM_INIT::FROM_A, and dE/dA by the reverse sweep
+ * (what the reference's energy functor hands to the optimiser, src/PEPS/CTMSolver.cpp:40-75).  checkpoint != 0: one checkpoint per move, replayed during the
+ * reverse sweep (src/PEPS/CTM.cpp:399-419,976-987,1327-1335,1407-1416,1751-1758) -- same gradient, less memory.  dA may be NULL (value only). */
+int xb_ctm_energy_grad(xb_ctx* ctx, const xb_tensor* A, int64_t chi, int steps, const xb_tensor* op_h, const xb_tensor* op_v, int checkpoint, double* energy,
+                       xb_tensor** dA);
+
 /* ---- micro-benchmark hooks (device-resident, timed with CUDA events on the context stream) -------------- */
 /* runs `reps` launches of the cached plan of permute<shift,p>(t); returns avg ms per launch and algorithmic bytes */
 int xb_bench_permute(xb_ctx* ctx, const xb_tensor* t, int shift, const int* p, int n, int reps, double* ms_per_launch, int64_t* bytes);

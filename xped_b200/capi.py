@@ -36,6 +36,16 @@ SIGNATURES = {
     "xb_ctx_create_planning": (C.c_int, [PP, C.POINTER(SymFactor), C.c_int]),
     "xb_ctx_free": (C.c_int, [P]),
     "xb_ctx_sync": (C.c_int, [P]),
+    "xb_tape_begin": (C.c_int, [P]),
+    "xb_tape_end": (C.c_int, [P]),
+    "xb_tape_seed_trace": (C.c_int, [P, P, C.c_double]),
+    "xb_tape_seed": (C.c_int, [P, P, P]),
+    "xb_tape_backward": (C.c_int, [P]),
+    "xb_tape_grad": (C.c_int, [P, P, PP]),
+    "xb_tape_size": (C.c_int, [P, LP]),
+    "xb_normalize_max": (C.c_int, [P, P, PP]),
+    "xb_normalize_trace": (C.c_int, [P, P, P, PP]),
+    "xb_ctm_energy_grad": (C.c_int, [P, P, C.c_int64, C.c_int, P, P, C.c_int, C.POINTER(C.c_double), PP]),
     "xb_ctx_set_int": (C.c_int, [P, C.c_char_p, C.c_int64]),
     "xb_ctx_get_int": (C.c_int, [P, C.c_char_p, LP]),
     "xb_ctx_nq": (C.c_int, [P]),

@@ -1,18 +1,25 @@
 // extern "C" boundary: include/xped_b200.h.  Exceptions are mapped to status codes + xb_last_error().
 #include "../../include/xped_b200.h"
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <new>
 #include <stdexcept>
 #include <string>
 
+#include "ad.hpp"
 #include "ctm.hpp"
 #include "engine.hpp"
 
 using namespace xb;
 
-struct xb_ctx { Context impl; xb_ctx(int dev, const std::vector<Factor>& f) : impl(dev, f) {} };
+struct xb_ctx
+{
+    Context impl;
+    std::unique_ptr<Tape> user_tape;   // xb_tape_begin .. xb_tape_end
+    xb_ctx(int dev, const std::vector<Factor>& f) : impl(dev, f) {}
+};
 struct xb_basis { xb_ctx* ctx; BasisPtr b; };
 struct xb_tensor { xb_ctx* ctx; std::unique_ptr<Tensor> t; };
 struct xb_ctm { xb_ctx* ctx; std::unique_ptr<Ctm> c; };
@@ -52,6 +59,20 @@ xb_tensor* wrap(xb_ctx* ctx, Tensor* t) { return new xb_tensor{ctx, std::unique_
 void need(const void* p, const char* what)
 {
     if(!p) throw std::invalid_argument(std::string("null argument: ") + what);
+}
+
+// In-place writes (upload, fills) while an AD tape is alive: the tape may hold this buffer as a recorded value, so the tensor moves to fresh storage first
+// (full overwrite: no copy; partial overwrite: the old contents are copied) -- the handle becomes a new, untracked value, like assigning a new tensor.
+void detach_for_write(xb_tensor* t, bool keep_contents)
+{
+    Context& c = t->ctx->impl;
+    if(c.tape == nullptr) return;
+    Tensor& T = *t->t;
+    const size_t bytes = static_cast<size_t>(std::max<int64_t>(T.layout->size, 1)) * sizeof(double);
+    auto fresh = std::make_shared<DevBuf>(&c, bytes, false);
+    if(keep_contents) check_cuda(cudaMemcpyAsync(fresh->p, T.d, bytes, cudaMemcpyDeviceToDevice, c.stream), "detach copy");
+    T.buf = fresh;
+    T.d = fresh->p;
 }
 
 Q make_q(const Symmetry& s, const int* q)
@@ -145,6 +166,120 @@ int xb_ctx_stats(const xb_ctx* ctx, int64_t out[3])
         out[0] = ctx->impl.launches;
         out[1] = ctx->impl.plan_hits;
         out[2] = ctx->impl.plan_misses;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------- reverse-mode AD
+int xb_tape_begin(xb_ctx* ctx)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        if(ctx->impl.tape) throw std::invalid_argument("xb_tape_begin: a tape is already recording");
+        ctx->user_tape.reset(new Tape(ctx->impl));
+        ctx->impl.tape = ctx->user_tape.get();
+    });
+}
+
+int xb_tape_end(xb_ctx* ctx)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        ctx->impl.tape = nullptr;
+        ctx->user_tape.reset();
+    });
+}
+
+int xb_tape_seed_trace(xb_ctx* ctx, const xb_tensor* v, double weight)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(v, "tensor");
+        if(!ctx->user_tape) throw std::invalid_argument("no tape: call xb_tape_begin first");
+        ctx->user_tape->seed_trace(*v->t, weight);
+    });
+}
+
+int xb_tape_seed(xb_ctx* ctx, const xb_tensor* v, const xb_tensor* adj)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(v, "tensor");
+        need(adj, "adjoint");
+        if(!ctx->user_tape) throw std::invalid_argument("no tape: call xb_tape_begin first");
+        if(adj->t->layout->size != v->t->layout->size || adj->t->layout->sector != v->t->layout->sector)
+            throw std::invalid_argument("xb_tape_seed: the adjoint must have the block structure of its value");
+        ctx->user_tape->seed(*v->t, *adj->t);
+    });
+}
+
+int xb_tape_backward(xb_ctx* ctx)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        if(!ctx->user_tape) throw std::invalid_argument("no tape: call xb_tape_begin first");
+        ctx->user_tape->backward();
+    });
+}
+
+int xb_tape_grad(xb_ctx* ctx, const xb_tensor* v, xb_tensor** g)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(v, "tensor");
+        need(g, "out");
+        if(!ctx->user_tape) throw std::invalid_argument("no tape: call xb_tape_begin first");
+        Tensor* a = ctx->user_tape->grad(*v->t);
+        if(!a) {
+            *g = nullptr;
+            return;
+        }
+        TapePause pause(ctx->impl);
+        *g = wrap(ctx, ctx->impl.copy(*a));
+    });
+}
+
+int xb_tape_size(xb_ctx* ctx, int64_t* n_nodes)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(n_nodes, "out");
+        *n_nodes = ctx->user_tape ? static_cast<int64_t>(ctx->user_tape->size()) : 0;
+    });
+}
+
+int xb_normalize_max(xb_ctx* ctx, const xb_tensor* t, xb_tensor** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(t, "tensor");
+        need(out, "out");
+        *out = wrap(ctx, ctx->impl.scale_by_inv_maxnorm(*t->t));
+    });
+}
+
+int xb_normalize_trace(xb_ctx* ctx, const xb_tensor* x, const xb_tensor* w, xb_tensor** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(x, "tensor");
+        need(w, "weight");
+        need(out, "out");
+        *out = wrap(ctx, ctx->impl.scale_by_inv_contraction(*x->t, *w->t));
+    });
+}
+
+int xb_ctm_energy_grad(xb_ctx* ctx, const xb_tensor* A, int64_t chi, int steps, const xb_tensor* op_h, const xb_tensor* op_v, int checkpoint, double* energy,
+                       xb_tensor** dA)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(A, "A");
+        need(op_h, "op_h");
+        need(op_v, "op_v");
+        need(energy, "energy");
+        Tensor* g = nullptr;
+        *energy = ctm_energy_grad(ctx->impl, *A->t, chi, steps, *op_h->t, *op_v->t, checkpoint != 0, dA ? &g : nullptr);
+        if(dA) *dA = wrap(ctx, g);
     });
 }
 
@@ -445,6 +580,7 @@ int xb_set_sub_block(xb_tensor* t, int64_t pair, const double* host, int64_t n)
 {
     return guard([&] {
         need(t, "tensor");
+        detach_for_write(t, true);
         need(host, "host buffer");
         const Layout& L = *t->t->layout;
         const PairLoc loc = locate_pair(L, pair);
@@ -463,6 +599,7 @@ int xb_tensor_upload(xb_tensor* t, const double* host, int64_t n)
 {
     return guard([&] {
         need(t, "tensor");
+        detach_for_write(t, false);
         if(n != t->t->layout->size) throw std::invalid_argument("upload: size != plainSize()");
         Context& c = t->ctx->impl;
         check_cuda(cudaMemcpyAsync(t->t->d, host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream), "upload");
@@ -485,6 +622,7 @@ int xb_tensor_set_zero(xb_tensor* t)
 {
     return guard([&] {
         need(t, "tensor");
+        detach_for_write(t, false);
         check_cuda(cudaMemsetAsync(t->t->d, 0, sizeof(double) * t->t->layout->size, t->ctx->impl.stream), "set_zero");
     });
 }
@@ -493,6 +631,7 @@ int xb_tensor_set_identity(xb_tensor* t)
 {
     return guard([&] {
         need(t, "tensor");
+        detach_for_write(t, false);
         t->ctx->impl.fill(*t->t, 1, 0.0, 0);
     });
 }
@@ -501,6 +640,7 @@ int xb_tensor_set_constant(xb_tensor* t, double v)
 {
     return guard([&] {
         need(t, "tensor");
+        detach_for_write(t, false);
         t->ctx->impl.fill(*t->t, 0, v, 0);
     });
 }
@@ -509,6 +649,7 @@ int xb_tensor_set_random(xb_tensor* t, uint64_t seed)
 {
     return guard([&] {
         need(t, "tensor");
+        detach_for_write(t, false);
         t->ctx->impl.fill(*t->t, 2, 0.0, seed);
     });
 }
@@ -587,6 +728,7 @@ int xb_tensor_set_random_at(xb_tensor* t, uint64_t seed, const int64_t* global_o
 {
     return guard([&] {
         need(t, "tensor");
+        detach_for_write(t, false);
         need(global_offsets, "global_offsets");
         Context& c = t->ctx->impl;
         const Layout& L = *t->t->layout;

@@ -4,6 +4,8 @@
 // the max-norm normalisation never leaves the device.
 #include "ctm.hpp"
 
+#include "ad.hpp"
+
 #include <stdexcept>
 
 namespace xb {
@@ -189,8 +191,7 @@ Tensor* Ctm::rdm(int which)
     const Layout& L = *rho->layout;
     TP Id2(new Tensor(&ctx_, ctx_.layout(L.cod, L.dom), true));
     ctx_.fill(*Id2, 1, 0.0, 0);
-    const double norm = full_contraction(ctx_, *rho, *tw(Id2, {0, 1}));
-    return ctx_.axpby(1.0 / norm, *rho, 0.0, nullptr);
+    return ctx_.scale_by_inv_contraction(*rho, *tw(Id2, {0, 1}));
 }
 
 void Ctm::projectors(int direction, TP& P1, TP& P2) const
@@ -218,7 +219,39 @@ void Ctm::projectors(int direction, TP& P1, TP& P2) const
     P2.reset(p2);
 }
 
+Ctm::Ctm(Context& ctx, int64_t chi, const std::vector<TP>& t) : ctx_(ctx), chi_(chi)
+{
+    if(t.size() != 10) throw std::invalid_argument("CTM: 10 tensors expected (C1..C4, T1..T4, A, Adag)");
+    C1_ = t[0]; C2_ = t[1]; C3_ = t[2]; C4_ = t[3];
+    T1_ = t[4]; T2_ = t[5]; T3_ = t[6]; T4_ = t[7];
+    A_ = t[8]; Adag_ = t[9];
+}
+
+std::vector<TP> Ctm::all_tensors() const { return {C1_, C2_, C3_, C4_, T1_, T2_, T3_, T4_, A_, Adag_}; }
+
+// AD with checkpointing (src/PEPS/CTM.cpp:976-987 and the like: the reference wraps contractCorner / get_projectors / renormalize_* of a move in
+// stan checkpoints that re-run them during the reverse sweep): here ONE checkpoint per move -- the forward pass keeps only the environment at the
+// move boundaries, the reverse sweep replays the move under a sub-tape.
 void Ctm::move(int direction)
+{
+    if(ctx_.taping() && checkpoint_moves) {
+        Context* ctx = &ctx_;
+        const int64_t chi = chi_;
+        std::vector<TP> outs = ctx_.tape->checkpoint(all_tensors(), [ctx, chi, direction](const std::vector<TP>& in) {
+            Ctm tmp(*ctx, chi, in);
+            tmp.move_impl(direction);
+            std::vector<TP> all = tmp.all_tensors();
+            all.resize(8);   // the environment; A and Adag are inputs only
+            return all;
+        });
+        C1_ = outs[0]; C2_ = outs[1]; C3_ = outs[2]; C4_ = outs[3];
+        T1_ = outs[4]; T2_ = outs[5]; T3_ = outs[6]; T4_ = outs[7];
+        return;
+    }
+    move_impl(direction);
+}
+
+void Ctm::move_impl(int direction)
 {
     TP P1, P2;
     projectors(direction, P1, P2);
@@ -288,6 +321,40 @@ void Ctm::grow_all()
     move(1);
     move(2);
     move(3);
+}
+
+// E(A) = avg(rho_h, O_h) + avg(rho_v, O_v) after `steps` grow_all() from CTM_INIT::FROM_A, and dE/dA by the reverse sweep over the tape
+// (the energy functional the reference's optimiser differentiates, src/PEPS/CTMSolver.cpp:40-75, for a 1x1 unit cell).
+double ctm_energy_grad(Context& ctx, const Tensor& A, int64_t chi, int steps, const Tensor& op_h, const Tensor& op_v, bool checkpoint, Tensor** dA)
+{
+    if(ctx.tape) throw std::invalid_argument("ctm_energy_grad: a tape is already recording on this context");
+    Tape tape(ctx);
+    struct Guard
+    {
+        Context& c;
+        ~Guard() { c.tape = nullptr; }
+    } guard{ctx};
+    ctx.tape = dA ? &tape : nullptr;
+    double energy = 0.0;
+    {
+        Ctm ctm(ctx, A, chi);
+        ctm.checkpoint_moves = checkpoint;
+        for(int s = 0; s < steps; ++s) ctm.grow_all();
+        for(int which = 0; which < 2; ++which) {
+            TP rho(ctm.rdm(which));
+            TP a(ctx.twist(*rho, 0)), b(ctx.twist(*a, 1));
+            TP prod(ctx.multiply(*b, false, which == 0 ? op_h : op_v, false));   // avg(): src/PEPS/LinearAlgebra.cpp:57-60
+            energy += ctx.trace(*prod);
+            if(dA) tape.seed_trace(*prod, 1.0);
+        }
+    }
+    if(dA) {
+        tape.backward();
+        Tensor* g = tape.grad(A);
+        ctx.tape = nullptr;
+        *dA = g ? ctx.copy(*g) : new Tensor(&ctx, A.layout, true);
+    }
+    return energy;
 }
 
 const Tensor& Ctm::get(int which) const

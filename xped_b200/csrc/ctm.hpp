@@ -2,6 +2,7 @@
 // Mirrors Xped::CTM<double,Symmetry,2> (include/Xped/PEPS/CTM.hpp:60-312, src/PEPS/CTM.cpp).
 #pragma once
 #include <memory>
+#include <vector>
 
 #include "engine.hpp"
 
@@ -16,14 +17,20 @@ double avg_two_site(Context& ctx, const Tensor& rho, const Tensor& op);
 // rho1 from a two-site density matrix (src/PEPS/CTM.cpp:675-678) and avg(rho1, O) of a one-site observable (LinearAlgebra.cpp:22-24)
 Tensor* rdm_one_site(Context& ctx, const Tensor& rho);
 double avg_one_site(Context& ctx, const Tensor& rho1, const Tensor& op);
+// energy of a 1x1 iPEPS after `steps` CTM steps and its gradient w.r.t. the site tensor by reverse-mode AD (dA may be null: value only)
+double ctm_energy_grad(Context& ctx, const Tensor& A, int64_t chi, int steps, const Tensor& op_h, const Tensor& op_v, bool checkpoint, Tensor** dA);
 
 class Ctm
 {
 public:
     Ctm(Context& ctx, const Tensor& A, int64_t chi);   // CTM(A, chi, FROM_A) + init()  (CTM.cpp:45-244)
+    Ctm(Context& ctx, int64_t chi, const std::vector<TP>& tensors);   // view on given C1..C4, T1..T4, A, Adag (checkpoint replay)
+    bool checkpoint_moves = false;     // under an AD tape: record one checkpoint per move instead of every op
+    std::vector<TP> all_tensors() const;
 
     void grow_all();                    // CTM.cpp:385-420
     void move(int direction);           // 0 left, 1 right, 2 top, 3 bottom  (CTM.cpp:924-1183)
+    void move_impl(int direction);
     Tensor* contract_corner(int corner);   // 0 UL, 1 UR, 2 LR, 3 LL  (CTM.cpp:1643-1760)
     Tensor* rdm(int which);             // 0: rho_h, 1: rho_v, normalised  (computeRDM_h / computeRDM_v, CTM.cpp:528-874, TRank == 2)
     const Tensor& get(int which) const;

@@ -186,18 +186,34 @@ struct PreparedGemm
 };
 
 class Context;
+class Tape;
 struct RsvdPlan;   // cached state of the truncated tSVD for one layout (rsvd.cu)
+
+// device storage of a tensor; shared between a Tensor and its aliases (the AD tape keeps values alive through aliases)
+struct DevBuf
+{
+    Context* ctx;
+    double* p = nullptr;
+    DevBuf(Context* c, size_t bytes, bool zero);
+    ~DevBuf();
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
 
 struct Tensor
 {
     Context* ctx = nullptr;
     LayoutPtr layout;
+    std::shared_ptr<DevBuf> buf;
     double* d = nullptr;
     Tensor(Context* c, LayoutPtr l, bool zero);
-    ~Tensor();
     Tensor(const Tensor&) = delete;
     Tensor& operator=(const Tensor&) = delete;
     int64_t size() const { return layout->size; }
+    Tensor* alias() const;   // second handle on the same storage (no copy)
+    const DevBuf* id() const { return buf.get(); }
+private:
+    Tensor() = default;
 };
 
 struct SvdResult
@@ -239,11 +255,18 @@ public:
     Tensor* contract(const Tensor& a, const std::vector<int>& l1, const Tensor& b, const std::vector<int>& l2, int res_rank);
     Tensor* adjoint(const Tensor& t);
     Tensor* twist(const Tensor& t, int leg);
+    Tensor* twist_impl(const Tensor& t, int leg);
     Tensor* copy(const Tensor& t);
     Tensor* axpby(double alpha, const Tensor& x, double beta, const Tensor* y);   // alpha*x + beta*y
     Tensor* diag_map(const Tensor& t, int op);                                    // 0 sqrt, 1 inv, 2 inv-sqrt
     double max_norm(const Tensor& t);
     Tensor* scale_by_inv_maxnorm(const Tensor& t);   // t * (1 / t.maxNorm()), scalar stays on the device
+    Tensor* scale_by_inv_contraction(const Tensor& x, const Tensor& w);   // x / trace(x * w)  (density-matrix normalisation, CTM.cpp:660-667)
+    Tensor* weighted_identity(const LayoutPtr& L);                        // Tensor::WeightedIdentity: degeneracy(q) * 1 per sector (reverse rule of trace)
+    double unweighted_trace(const Tensor& t);                             // sum_q tr(block_q)  (ADTensor.hpp:698)
+    // ---- reverse-mode AD (include/Xped/AD/ADTensor.hpp): while a tape is installed and recording, the ops above record their reverse rule
+    Tape* tape = nullptr;
+    bool taping() const;
     double trace(const Tensor& t);
     double squared_norm(const Tensor& t);
     void fill(Tensor& t, int mode, double value, uint64_t seed);                 // 0 constant, 1 identity, 2 counter-based uniform[-1,1]
@@ -378,5 +401,9 @@ void launch_scale_by_diag(const double* src, double* dst, const double* S, const
 void launch_svd_adjoint_core(const double* G1, const double* G2, const double* dS, const double* S, double* M, const BlockDesc* d_blocks, int nblocks,
                              cudaStream_t s);
 void launch_trace(const double* src, const BlockDesc* d_blocks, int nblocks, double* d_out, cudaStream_t s);
+// reverse rules of the element-wise ops (ADTensor.hpp:511-524, 559-586)
+void launch_diag_map_backward(const double* g, const double* y, double* dst, const BlockDesc* d_blocks, int nblocks, int op, cudaStream_t s);
+void launch_dot(const double* a, const double* b, int64_t n, double* d_part /* 129 doubles: [0] receives the result */, cudaStream_t s);
+void launch_maxnorm_scale_backward(const double* g, const double* x, const double* d_m, const double* d_dot, double* out, int64_t n, cudaStream_t s);
 
 }   // namespace xb

@@ -1,4 +1,8 @@
 // teigh / tQR / SVD reverse rule / MPS transfer contractions. (Filled in after the first GPU bring-up.)
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -22,9 +26,29 @@ Tensor* Context::tsvd_backward(const Tensor& A, const Tensor& U, const Tensor& S
     (void)S;
     (void)Vd;
     const Layout& LA = *A.layout;
-    SvdResult F = tsvd(A, INT64_MAX / 4, 0.0, false);
+    SvdResult F = tsvd_full(A, INT64_MAX / 4, 0.0, false);
     std::unique_ptr<Tensor> FU(F.U), FS(F.S), FV(F.Vd);
     const Layout &LU = *FU->layout, &LS = *FS->layout, &LV = *FV->layout;
+    if(std::getenv("XB_DEBUG_SVDBWD")) {
+        // compare the recomputed full factors with the caller's (leading columns / rows per sector)
+        sync();
+        std::vector<double> hf(FU->size()), hu(U.size()), hs(FS->size()), hss(S.size());
+        cudaMemcpy(hf.data(), FU->d, sizeof(double) * hf.size(), cudaMemcpyDeviceToHost);
+        cudaMemcpy(hu.data(), U.d, sizeof(double) * hu.size(), cudaMemcpyDeviceToHost);
+        cudaMemcpy(hs.data(), FS->d, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost);
+        cudaMemcpy(hss.data(), S.d, sizeof(double) * hss.size(), cudaMemcpyDeviceToHost);
+        const Layout& Lu = *U.layout;
+        for(size_t j = 0; j < Lu.sector.size(); ++j) {
+            const int i = LU.find(Lu.sector[j]);
+            double worst = 0.0, worst_s = 0.0;
+            for(int64_t c = 0; c < Lu.cols[j]; ++c) {
+                for(int64_t r = 0; r < Lu.rows[j]; ++r) worst = std::max(worst, std::fabs(hf[LU.off[i] + r + c * LU.rows[i]] - hu[Lu.off[j] + r + c * Lu.rows[j]]));
+                worst_s = std::max(worst_s, std::fabs(hs[LS.off[i] + c + c * LS.rows[i]] - hss[S.layout->off[j] + c + c * S.layout->rows[j]]));
+            }
+            std::fprintf(stderr, "[svd bwd] sector %zu (%lld x %lld kept of %lld): max |FU - U| %.3e, max |FS - S| %.3e\n", j, (long long)Lu.rows[j], (long long)Lu.cols[j],
+                         (long long)LU.cols[i], worst, worst_s);
+        }
+    }
     std::unique_ptr<Tensor> dFU(new Tensor(this, FU->layout, true)), dFS(new Tensor(this, FS->layout, true)), dFV(new Tensor(this, FV->layout, true));
     auto pad = [&](const Tensor* src, Tensor& dst, const char* what) {
         if(!src) return;
@@ -61,6 +85,23 @@ Tensor* Context::tsvd_backward(const Tensor& A, const Tensor& U, const Tensor& S
     upload_async(d_meta + b0 + b1, dv.data(), b1);
     std::unique_ptr<Tensor> M(new Tensor(this, FS->layout, false));
     launch_svd_adjoint_core(G1->d, G2->d, dFS->d, FS->d, M->d, reinterpret_cast<BlockDesc*>(d_meta), nb, stream);
+    if(std::getenv("XB_DEBUG_SVDBWD")) {
+        sync();
+        auto dump = [&](const char* name, const Tensor& T) {
+            std::vector<double> h(T.size());
+            cudaMemcpy(h.data(), T.d, sizeof(double) * h.size(), cudaMemcpyDeviceToHost);
+            std::string fn = std::string("gpurun_out/dbg_") + name + ".bin";
+            if(FILE* f = std::fopen(fn.c_str(), "wb")) {
+                std::fwrite(h.data(), sizeof(double), h.size(), f);
+                std::fclose(f);
+            }
+        };
+        dump("Mcore", *M);
+        dump("G1", *G1);
+        dump("G2", *G2);
+        dump("FS", *FS);
+        dump("dFS", *dFS);
+    }
     std::unique_ptr<Tensor> X1(multiply(*FU, false, *M, false));
     if(X1->layout->sector != LU.sector || X1->layout->size != LU.size) throw std::logic_error("tsvd_backward: layout of U*M differs from U's");
     launch_scale_by_diag(dFU->d, X1->d, FS->d, reinterpret_cast<DiagScaleDesc*>(d_meta + b0), nb, 1, stream);   // X1 += dU S^-1

@@ -555,7 +555,7 @@ __global__ void diag_map_kernel(const double* __restrict__ src, double* __restri
             double v = 0.0;
             if(r == c) {
                 const double x = src[d.off + e];
-                v = op == 0 ? sqrt(x) : (op == 1 ? 1.0 / x : 1.0 / sqrt(x));
+                v = op == 0 ? sqrt(x) : (op == 1 ? 1.0 / x : (op == 2 ? 1.0 / sqrt(x) : x));   // op 3: keep the diagonal
             }
             dst[d.off + e] = v;
         }
@@ -692,11 +692,13 @@ __global__ void svd_adjoint_core_kernel(const double* __restrict__ G1, const dou
             const int i = static_cast<int>(e % r), j = static_cast<int>(e / r);
             const long long ij = d.off + e, ji = d.off + j + static_cast<long long>(i) * r;
             const double si = S[d.off + i + static_cast<long long>(i) * r], sj = S[d.off + j + static_cast<long long>(j) * r];
-            const double dij = sj * sj - si * si;   // vec_diff: F_inv(i,j) = v(j) - v(i)
-            const double fij = fabs(dij) < 1.e-12 ? dij / (dij * dij + 1.e-12) : 1.0 / dij;
-            const double fji = -fij;                // F is antisymmetric (also in its regularised form)
+            // vec_diff: F_inv(i,j) = v(j) - v(i) with v = sigma^2, as (sj - si)(sj + si): exactly 0 on the diagonal (sj * sj - si * si contracts into an FMA whose
+            // rounding residue ~1e-16 sigma^2 exceeds the 1e-12 regularisation threshold for sigma^2 > 1e4 and then gives F_ii ~ 1e11)
+            const double dij = (sj - si) * (sj + si);
+            const double fij = i == j ? 0.0 : (fabs(dij) < 1.e-12 ? dij / (dij * dij + 1.e-12) : 1.0 / dij);
             const double g1ij = G1[ij], g1ji = G1[ji], g2ij = G2[ij], g2ji = G2[ji];
-            double m = dS[ij] + (fij * g1ij + fji * g1ji) * sj + si * (fij * g2ij + fji * g2ji);
+            // F is antisymmetric (also in its regularised form): (F o G + (F o G)^T)_ij = F_ij (G_ij - G_ji).
+            double m = dS[ij] + fij * (g1ij - g1ji) * sj + si * fij * (g2ij - g2ji);
             if(g1ij != 0.0) m -= g1ij / sj;
             if(g2ji != 0.0) m -= g2ji / si;
             M[ij] = m;
@@ -712,4 +714,87 @@ void launch_svd_adjoint_core(const double* G1, const double* G2, const double* d
     svd_adjoint_core_kernel<<<grid, 256, 0, s>>>(G1, G2, dS, S, M, d_blocks, nblocks);
     check_cuda(cudaGetLastError(), "svd_adjoint_core_kernel launch");
 }
+// ---- reverse rules of the element-wise ops (include/Xped/AD/ADTensor.hpp:511-524, 559-586) -------------------------------------------
+// diag_sqrt / diag_inv / their composition: out = diag(g_ii * f'(x_ii)) expressed through the forward result y: sqrt: 0.5 / y, inv: -y^2, inv-sqrt: -0.5 y^3
+__global__ void diag_map_backward_kernel(const double* __restrict__ g, const double* __restrict__ y, double* __restrict__ dst, const BlockDesc* __restrict__ blocks,
+                                         int nblocks, int op)
+{
+    for(int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const BlockDesc d = blocks[b];
+        const long long n = static_cast<long long>(d.rows) * d.cols;
+        for(long long e = threadIdx.x; e < n; e += blockDim.x) {
+            const int r = static_cast<int>(e % d.rows), c = static_cast<int>(e / d.rows);
+            double v = 0.0;
+            if(r == c) {
+                const double yy = y[d.off + e];
+                v = g[d.off + e] * (op == 0 ? 0.5 / yy : (op == 1 ? -yy * yy : -0.5 * yy * yy * yy));
+            }
+            dst[d.off + e] = v;
+        }
+    }
+}
+
+void launch_diag_map_backward(const double* g, const double* y, double* dst, const BlockDesc* d_blocks, int nblocks, int op, cudaStream_t s)
+{
+    if(nblocks == 0) return;
+    diag_map_backward_kernel<<<nblocks < 296 ? nblocks : 296, 256, 0, s>>>(g, y, dst, d_blocks, nblocks, op);
+    check_cuda(cudaGetLastError(), "diag_map_backward_kernel launch");
+}
+
+// <a, b> = sum_i a_i b_i in a fixed order: per-CTA partial sums, then one CTA adds them up (deterministic)
+__global__ void dot_partial_kernel(const double* __restrict__ a, const double* __restrict__ b, long long n, double* __restrict__ part)
+{
+    __shared__ double sm[256];
+    const long long chunk = (n + gridDim.x - 1) / gridDim.x;
+    const long long e0 = chunk * blockIdx.x, e1 = e0 + chunk < n ? e0 + chunk : n;
+    double acc = 0.0;
+    for(long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) acc = fma(a[e], b[e], acc);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for(int o = 128; o > 0; o >>= 1) {
+        if(threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) part[blockIdx.x] = sm[0];
+}
+__global__ void dot_final_kernel(const double* __restrict__ part, int nparts, double* __restrict__ out)
+{
+    if(threadIdx.x == 0) {
+        double s = 0.0;
+        for(int i = 0; i < nparts; ++i) s += part[i];
+        *out = s;
+    }
+}
+
+void launch_dot(const double* a, const double* b, int64_t n, double* d_part /* 129 doubles */, cudaStream_t s)
+{
+    dot_partial_kernel<<<128, 256, 0, s>>>(a, b, n, d_part + 1);
+    dot_final_kernel<<<1, 32, 0, s>>>(d_part + 1, 128, d_part);
+    check_cuda(cudaGetLastError(), "dot kernels launch");
+}
+
+// y = x / m, m = max |x|  =>  adj(x) = g / m - (<g, x> / m^2) sign(x_k) e_k at the position(s) k of the maximum (maxNorm rule, ADTensor.hpp:511-524, fused
+// with the scaling the CTM applies right after it)
+__global__ void maxnorm_scale_backward_kernel(const double* __restrict__ g, const double* __restrict__ x, const double* __restrict__ d_m, const double* __restrict__ d_dot,
+                                              double* __restrict__ out, long long n)
+{
+    const double m = *d_m, inv = 1.0 / m, corr = *d_dot * inv * inv;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for(long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double xi = x[i];
+        double v = g[i] * inv;
+        if(fabs(xi) == m) v -= xi < 0.0 ? -corr : corr;
+        out[i] = v;
+    }
+}
+
+void launch_maxnorm_scale_backward(const double* g, const double* x, const double* d_m, const double* d_dot, double* out, int64_t n, cudaStream_t s)
+{
+    if(n == 0) return;
+    long long gr = (n + 255) / 256;
+    if(gr > 1184) gr = 1184;
+    maxnorm_scale_backward_kernel<<<static_cast<int>(gr), 256, 0, s>>>(g, x, d_m, d_dot, out, n);
+    check_cuda(cudaGetLastError(), "maxnorm_scale_backward_kernel launch");
+}
+
 }   // namespace xb

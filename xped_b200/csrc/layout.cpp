@@ -200,17 +200,33 @@ void Context::upload_async(void* dst, const void* src, size_t bytes)
     c.used += need;
 }
 
+DevBuf::DevBuf(Context* c, size_t bytes, bool zero) : ctx(c)
+{
+    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&p), bytes, ctx->stream), "cudaMallocAsync(block arena)");
+    if(zero) check_cuda(cudaMemsetAsync(p, 0, bytes, ctx->stream), "cudaMemsetAsync");
+}
+
+DevBuf::~DevBuf()
+{
+    if(p) cudaFreeAsync(p, ctx->stream);
+}
+
 Tensor::Tensor(Context* c, LayoutPtr l, bool zero) : ctx(c), layout(std::move(l))
 {
     if(ctx->planning_only()) throw std::runtime_error("xped_b200: no CUDA device -- planning-only context cannot hold tensor data (no CPU fallback)");
     const size_t bytes = static_cast<size_t>(std::max<int64_t>(layout->size, 1)) * sizeof(double);
-    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d), bytes, ctx->stream), "cudaMallocAsync(block arena)");
-    if(zero) check_cuda(cudaMemsetAsync(d, 0, bytes, ctx->stream), "cudaMemsetAsync");
+    buf = std::make_shared<DevBuf>(ctx, bytes, zero);
+    d = buf->p;
 }
 
-Tensor::~Tensor()
+Tensor* Tensor::alias() const
 {
-    if(d) cudaFreeAsync(d, ctx->stream);
+    auto* t = new Tensor();
+    t->ctx = ctx;
+    t->layout = layout;
+    t->buf = buf;
+    t->d = d;
+    return t;
 }
 
 PermutePlan::~PermutePlan()

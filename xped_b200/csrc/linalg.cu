@@ -24,6 +24,7 @@
 #include <stdexcept>
 
 #include "engine.hpp"
+#include "ad.hpp"
 #include "precond.hpp"
 #include "svd_internal.hpp"
 
@@ -1265,6 +1266,24 @@ SvdResult Context::tsvd(const Tensor& t, int64_t max_keep, double eps_svd, bool 
 {
     if(t.layout->sector.empty()) throw std::invalid_argument("tSVD: tensor has no blocks");
     SvdResult res;
+    if(taping()) {
+        // reverse rule of full_svd + cutoff (ADTensor.hpp:237-374): needs the full factors in the gauge of the truncated ones, which the deterministic full path
+        // gives when tsvd_backward recomputes them -- so the forward pass takes the full path too
+        {
+            TapePause pause(*this);
+            res = tsvd_full(t, max_keep, eps_svd, preserve_multiplets);
+        }
+        Tensor *ta = tape->keep(t), *tu = tape->keep(*res.U), *ts = tape->keep(*res.S), *tv = tape->keep(*res.Vd);
+        tape->record([this, ta, tu, ts, tv](Tape& T) {
+            Tensor *gu = T.grad(*tu), *gs = T.grad(*ts), *gv = T.grad(*tv);
+            if(!gu && !gs && !gv) return;
+            // Sigma is stored as dense diagonal blocks: only the diagonal of its adjoint is a derivative (a product downstream leaves values in the
+            // structurally-zero off-diagonal entries too; the reference's rule would add them into dA, ADTensor.hpp:293-297)
+            std::unique_ptr<Tensor> gs_diag(gs ? diag_map(*gs, 3) : nullptr);
+            T.accumulate(*ta, tsvd_backward(*ta, *tu, *ts, *tv, gu, gs_diag.get(), gv));
+        });
+        return res;
+    }
     if(tsvd_truncated(t, max_keep, eps_svd, preserve_multiplets, &res)) return res;
     return tsvd_full(t, max_keep, eps_svd, preserve_multiplets);
 }

@@ -8,6 +8,7 @@
 #include <numeric>
 #include <stdexcept>
 
+#include "ad.hpp"
 #include "engine.hpp"
 
 namespace xb {
@@ -24,6 +25,12 @@ Tensor* Context::permute(const Tensor& t, int shift, const std::vector<int>& pi)
         launch_permute(t.d, out->d, *plan, stream);
     }
     ++launches;
+    if(taping()) {   // ADTensor.hpp:171-185: adj(t) += adj(out).permute_adj<shift, p>()
+        Tensor *tin = tape->keep(t), *tout = tape->keep(*out);
+        tape->record([this, tin, tout, shift, pi](Tape& T) {
+            if(Tensor* g = T.grad(*tout)) T.accumulate(*tin, permute_adj(*g, shift, pi));
+        });
+    }
     return out;
 }
 
@@ -45,6 +52,12 @@ Tensor* Context::copy(const Tensor& t)
 {
     auto* out = new Tensor(this, t.layout, false);
     check_cuda(cudaMemcpyAsync(out->d, t.d, sizeof(double) * t.size(), cudaMemcpyDeviceToDevice, stream), "copy");
+    if(taping()) {
+        Tensor *tin = tape->keep(t), *tout = tape->keep(*out);
+        tape->record([this, tin, tout](Tape& T) {
+            if(Tensor* g = T.grad(*tout)) T.accumulate(*tin, copy(*g));
+        });
+    }
     return out;
 }
 
@@ -217,6 +230,16 @@ Tensor* Context::multiply_sectors(const Tensor& a, bool adj_a, const Tensor& b, 
         items.push_back(g);
     }
     run_gemm(a.d, b.d, out->d, items);
+    if(taping()) {   // ADTensor.hpp:749-758: adj(left) += adj(res) * right^+, adj(right) += left^+ * adj(res); lazy-adjoint operands get the adjoint of that
+        Tensor *ta = tape->keep(a), *tb = tape->keep(b), *tout = tape->keep(*out);
+        tape->record([this, ta, tb, tout, adj_a, adj_b](Tape& T) {
+            Tensor* g = T.grad(*tout);
+            if(!g) return;
+            T.accumulate(*ta, adj_a ? multiply(*tb, adj_b, *g, true) : multiply(*g, false, *tb, !adj_b));
+            g = T.grad(*tout);   // (the map may have rehashed)
+            T.accumulate(*tb, adj_b ? multiply(*g, true, *ta, adj_a) : multiply(*ta, !adj_a, *g, false));
+        });
+    }
     return out;
 }
 
@@ -290,10 +313,32 @@ Tensor* Context::adjoint(const Tensor& t)
     launch_transpose_blocks(t.d, out->d, reinterpret_cast<BlockDesc*>(d_meta), reinterpret_cast<long long*>(d_meta + b1), nb, stream);
     check_cuda(cudaFreeAsync(d_meta, stream), "cudaFreeAsync adjoint meta");
     ++launches;
+    if(taping()) {   // ADTensor.hpp:137-150
+        Tensor *tin = tape->keep(t), *tout = tape->keep(*out);
+        tape->record([this, tin, tout](Tape& T) {
+            if(Tensor* g = T.grad(*tout)) T.accumulate(*tin, adjoint(*g));
+        });
+    }
     return out;
 }
 
 Tensor* Context::twist(const Tensor& t, int leg)
+{
+    Tensor* out = nullptr;
+    {
+        TapePause pause(*this);
+        out = twist_impl(t, leg);
+    }
+    if(taping()) {   // ADTensor.hpp:589-602: adj(t) += adj(res).twist(leg)
+        Tensor *tin = tape->keep(t), *tout = tape->keep(*out);
+        tape->record([this, tin, tout, leg](Tape& T) {
+            if(Tensor* g = T.grad(*tout)) T.accumulate(*tin, twist(*g, leg));
+        });
+    }
+    return out;
+}
+
+Tensor* Context::twist_impl(const Tensor& t, int leg)
 {
     // Tensor::twist (src/Core/Tensor.cpp:357-377): early-out copy for bosonic symmetries (:362).
     if(!sym->fermionic()) return copy(t);
@@ -339,6 +384,18 @@ Tensor* Context::axpby(double alpha, const Tensor& x, double beta, const Tensor*
         launch_axpby(x.d, y->d, out->d, alpha, beta, x.size(), stream);
     }
     ++launches;
+    if(taping()) {   // ADTensor.hpp:640-676
+        Tensor *tx = tape->keep(x), *ty = y ? tape->keep(*y) : nullptr, *tout = tape->keep(*out);
+        tape->record([this, tx, ty, tout, alpha, beta](Tape& T) {
+            Tensor* g = T.grad(*tout);
+            if(!g) return;
+            T.accumulate(*tx, axpby(alpha, *g, 0.0, nullptr));
+            if(ty) {
+                g = T.grad(*tout);
+                T.accumulate(*ty, axpby(beta, *g, 0.0, nullptr));
+            }
+        });
+    }
     return out;
 }
 
@@ -355,6 +412,23 @@ Tensor* Context::diag_map(const Tensor& t, int op)
     launch_diag_map(t.d, out->d, d_meta, nb, op, stream);
     check_cuda(cudaFreeAsync(d_meta, stream), "cudaFreeAsync diag meta");
     ++launches;
+    if(taping()) {   // ADTensor.hpp:559-586 (diag_sqrt: adj * 0.5 / res, diag_inv: adj * (-res^2)) and their composition
+        Tensor *tin = tape->keep(t), *tout = tape->keep(*out);
+        tape->record([this, tin, tout, op](Tape& T) {
+            Tensor* g = T.grad(*tout);
+            if(!g) return;
+            const Layout& Lo = *tout->layout;
+            auto* gi = new Tensor(this, tin->layout, false);
+            auto dd = block_descs(Lo, nullptr);
+            BlockDesc* dm = nullptr;
+            check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&dm), dd.size() * sizeof(BlockDesc), stream), "cudaMallocAsync diag meta");
+            upload_async(dm, dd.data(), dd.size() * sizeof(BlockDesc));
+            launch_diag_map_backward(g->d, tout->d, gi->d, dm, static_cast<int>(dd.size()), op, stream);
+            check_cuda(cudaFreeAsync(dm, stream), "cudaFreeAsync diag meta");
+            ++launches;
+            T.accumulate(*tin, gi);
+        });
+    }
     return out;
 }
 
@@ -404,7 +478,96 @@ Tensor* Context::scale_by_inv_maxnorm(const Tensor& t)
     launch_scale_by_inv(t.d, out->d, d_scalar, t.size(), stream);
     check_cuda(cudaFreeAsync(d_scalar, stream), "cudaFreeAsync maxnorm scalar");
     launches += 2;
+    if(taping()) {   // maxNorm (ADTensor.hpp:502-529) fused with the division that follows it in renormalize_* (CTM.cpp:1369,1381,1409)
+        Tensor *tin = tape->keep(t), *tout = tape->keep(*out);
+        tape->record([this, tin, tout](Tape& T) {
+            Tensor* g = T.grad(*tout);
+            if(!g) return;
+            auto* gi = new Tensor(this, tin->layout, false);
+            double* d_tmp = nullptr;   // [0] max |x|, [1] <g, x>, [2..130] partial sums
+            check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_tmp), sizeof(double) * 132, stream), "cudaMallocAsync maxnorm backward");
+            launch_absmax(tin->d, tin->size(), d_tmp, stream);
+            launch_dot(g->d, tin->d, tin->size(), d_tmp + 1, stream);
+            launch_maxnorm_scale_backward(g->d, tin->d, d_tmp, d_tmp + 1, gi->d, tin->size(), stream);
+            check_cuda(cudaFreeAsync(d_tmp, stream), "cudaFreeAsync maxnorm backward");
+            launches += 4;
+            T.accumulate(*tin, gi);
+        });
+    }
     return out;
+}
+
+// x / trace(x * w): normalisation of a density matrix (CTM.cpp:660-667: norm = rho.contract<...>(Id.twist(0).twist(1)).trace(); rho = rho * (1 / norm)).
+// Reverse rule (operator*(tensor, var) + trace, ADTensor.hpp:531-546,690-706): adj(x) = g / n - (<g, x> / n^2) * d n / d x, d n / d x_q = degeneracy(q) w_q^T.
+Tensor* Context::scale_by_inv_contraction(const Tensor& x, const Tensor& w)
+{
+    double n = 0.0;
+    Tensor* out = nullptr;
+    {
+        TapePause pause(*this);
+        std::unique_ptr<Tensor> prod(multiply(x, false, w, false));
+        n = trace(*prod);
+        out = axpby(1.0 / n, x, 0.0, nullptr);
+    }
+    if(taping()) {
+        Tensor *tx = tape->keep(x), *tw = tape->keep(w), *tout = tape->keep(*out);
+        tape->record([this, tx, tw, tout, n](Tape& T) {
+            Tensor* g = T.grad(*tout);
+            if(!g) return;
+            std::unique_ptr<Tensor> gx(multiply(*g, false, *tx, true));
+            const double inner = unweighted_trace(*gx);   // <g, x>
+            // degeneracy-weighted adjoint of w, laid out like x
+            std::unique_ptr<Tensor> wa(adjoint(*tw));
+            const Layout& L = *wa->layout;
+            std::vector<SubScale> subs;
+            for(size_t i = 0; i < L.sector.size(); ++i)
+                subs.push_back({L.off[i], static_cast<int>(L.rows[i]), static_cast<int>(L.cols[i]), static_cast<int>(L.rows[i]), static_cast<double>(sym->degeneracy(L.sector[i]))});
+            if(!subs.empty()) {
+                SubScale* d_subs = nullptr;
+                check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_subs), subs.size() * sizeof(SubScale), stream), "cudaMallocAsync weights");
+                upload_async(d_subs, subs.data(), subs.size() * sizeof(SubScale));
+                launch_scale_subblocks(wa->d, d_subs, static_cast<int>(subs.size()), stream);
+                check_cuda(cudaFreeAsync(d_subs, stream), "cudaFreeAsync weights");
+                ++launches;
+            }
+            if(wa->layout->size != g->layout->size || wa->layout->sector != g->layout->sector) throw std::logic_error("scale_by_inv_contraction: weight layout differs from the operand's");
+            T.accumulate(*tx, axpby(1.0 / n, *g, -inner / (n * n), wa.get()));
+        });
+    }
+    return out;
+}
+
+Tensor* Context::weighted_identity(const LayoutPtr& L)
+{
+    auto* out = new Tensor(this, L, true);
+    fill(*out, 1, 0.0, 0);
+    std::vector<SubScale> subs;
+    for(size_t i = 0; i < L->sector.size(); ++i)
+        subs.push_back({L->off[i], static_cast<int>(L->rows[i]), static_cast<int>(L->cols[i]), static_cast<int>(L->rows[i]), static_cast<double>(sym->degeneracy(L->sector[i]))});
+    if(!subs.empty()) {
+        SubScale* d_subs = nullptr;
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&d_subs), subs.size() * sizeof(SubScale), stream), "cudaMallocAsync weights");
+        upload_async(d_subs, subs.data(), subs.size() * sizeof(SubScale));
+        launch_scale_subblocks(out->d, d_subs, static_cast<int>(subs.size()), stream);
+        check_cuda(cudaFreeAsync(d_subs, stream), "cudaFreeAsync weights");
+        ++launches;
+    }
+    return out;
+}
+
+double Context::unweighted_trace(const Tensor& t)
+{
+    const Layout& L = *t.layout;
+    auto descs = block_descs(L, nullptr);
+    const size_t bytes = descs.size() * sizeof(BlockDesc);
+    char* d_meta = static_cast<char*>(scratch(bytes + 64));
+    upload_async(d_meta + 64, descs.data(), bytes);
+    launch_trace(t.d, reinterpret_cast<BlockDesc*>(d_meta + 64), static_cast<int>(descs.size()), reinterpret_cast<double*>(d_meta), stream);
+    ++launches;
+    double h = 0.0;
+    check_cuda(cudaMemcpyAsync(&h, d_meta, sizeof(double), cudaMemcpyDeviceToHost, stream), "trace readback");
+    sync();
+    return h;
 }
 
 void Context::fill(Tensor& t, int mode, double value, uint64_t seed)

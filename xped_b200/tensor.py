@@ -45,6 +45,32 @@ class Context:
         check(self.lib.xb_ctx_stats(self.h, out))
         return {"launches": out[0], "plan_hits": out[1], "plan_misses": out[2]}
 
+    # ---- reverse-mode AD tape (include/Xped/AD/ADTensor.hpp): ops issued between tape_begin() and tape_end() record their reverse rule
+    def tape_begin(self):
+        check(self.lib.xb_tape_begin(self.h))
+
+    def tape_end(self):
+        check(self.lib.xb_tape_end(self.h))
+
+    def tape_seed_trace(self, t, weight=1.0):
+        check(self.lib.xb_tape_seed_trace(self.h, t.h, float(weight)))
+
+    def tape_seed(self, t, adj):
+        check(self.lib.xb_tape_seed(self.h, t.h, adj.h))
+
+    def tape_backward(self):
+        check(self.lib.xb_tape_backward(self.h))
+
+    def tape_grad(self, t):
+        g = C.c_void_p()
+        check(self.lib.xb_tape_grad(self.h, t.h, C.byref(g)))
+        return Tensor(self, g) if g.value else None
+
+    def tape_size(self):
+        n = C.c_int64()
+        check(self.lib.xb_tape_size(self.h, C.byref(n)))
+        return n.value
+
     def set_int(self, key, value):
         check(self.lib.xb_ctx_set_int(self.h, key.encode(), int(value)))
 
@@ -295,6 +321,8 @@ class Tensor:
     def axpby(self, alpha, beta, y): return self._out(self.ctx.lib.xb_axpby, self.ctx.h, float(alpha), self.h, float(beta), y.h)
     def __add__(self, other): return self.axpby(1.0, 1.0, other)
     def __sub__(self, other): return self.axpby(1.0, -1.0, other)
+    def normalize_max(self): return self._out(self.ctx.lib.xb_normalize_max, self.ctx.h, self.h)
+    def normalize_trace(self, w): return self._out(self.ctx.lib.xb_normalize_trace, self.ctx.h, self.h, w.h)
     def diag_sqrt(self): return self._out(self.ctx.lib.xb_diag_map, self.ctx.h, self.h, 0)
     def diag_inv(self): return self._out(self.ctx.lib.xb_diag_map, self.ctx.h, self.h, 1)
 
@@ -409,6 +437,13 @@ class CTM:
     def computeRDM_v(self):
         """normalised rho_v of two vertically neighbouring sites (CTM::computeRDM_v, src/PEPS/CTM.cpp:702-874)"""
         return self._rdm(1)
+
+
+def ctm_energy_grad(A, chi, steps, op_h, op_v, checkpoint=False, want_grad=True):
+    """(E, dE/dA) of the 1x1 iPEPS A after `steps` CTM steps (xb_ctm_energy_grad); dE/dA is None when want_grad is False."""
+    e, g = C.c_double(), C.c_void_p()
+    check(A.ctx.lib.xb_ctm_energy_grad(A.ctx.h, A.h, int(chi), int(steps), op_h.h, op_v.h, int(bool(checkpoint)), C.byref(e), C.byref(g) if want_grad else None))
+    return e.value, (Tensor(A.ctx, g) if want_grad else None)
 
 
 def avg_two_site(rho, op):

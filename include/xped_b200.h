@@ -223,6 +223,23 @@ int xb_avg_two_site(xb_ctx* ctx, const xb_tensor* rho, const xb_tensor* op, doub
 int xb_rdm_one_site(xb_ctx* ctx, const xb_tensor* rho, xb_tensor** rho1);
 int xb_avg_one_site(xb_ctx* ctx, const xb_tensor* rho1, const xb_tensor* op, double* out);
 
+/* ---- state interop ----------------------------------------------------------------------------------------------------
+ * Native container: symmetry, leg bases, sector order and the raw m_data image -- the fields the reference serialises through yas
+ * (include/Xped/Core/storage/StorageType_contiguous.hpp:191-204, Qbasis.hpp:249-253, Tensor.hpp:409-413); xb_ctm_save / xb_ctm_load write / read chi, C1..C4,
+ * T1..T4, A, Adag (checkpoint / resume of an environment, examples/chi_ramp.cpp:201-204).  The yas byte format is not reproduced (no yas, no reference-written
+ * file in this image to check against).  Loading checks the symmetry and that the stored block structure follows from the stored bases. */
+int xb_tensor_save(xb_ctx* ctx, const xb_tensor* t, const char* path);
+int xb_tensor_load(xb_ctx* ctx, const char* path, xb_tensor** out);
+int xb_ctm_save(const xb_ctm* c, const char* path);
+int xb_ctm_load(xb_ctx* ctx, const char* path, xb_ctm** out);
+/* IO::loadMatlabTensor  include/Xped/IO/Matlab.hpp:9-95 on the arrays of the HDF5 group (the container itself needs HighFive / libhdf5):
+ * charges[leg][j] / sector_dims[leg][j] = rows 0 / 1 of the leg's `charges` dataset (j < ncharge[leg]); voffs_index / voffs_offset = the columns of `voffs`
+ * (combined charge index with leg 0 fastest, offset into vdat); conj[leg] != 0 marks the leg's basis as dual; charges are multiplied by qn_scale and, for Z_N,
+ * reduced modulo N.  All legs are placed in the domain of a rank-(N,0) tensor coupled to the vacuum, then permute<N - rank>(identity) (:93).  One Abelian factor. */
+int xb_tensor_from_charge_blocks(xb_ctx* ctx, int nlegs, int rank, const int* ncharge, const double* const* charges, const double* const* sector_dims, const int* conj,
+                                 int64_t nblocks, const int64_t* voffs_index, const int64_t* voffs_offset, const double* vdat, int64_t nvdat, int qn_scale,
+                                 xb_tensor** out);
+
 /* ---- reverse-mode AD (include/Xped/AD/ADTensor.hpp; replaces the stan::math tape): between xb_tape_begin and xb_tape_end the differentiable entry
  * points above record their reverse rule -- xb_permute (:171-185, permute_adj), xb_multiply (:749-758), xb_contract (:193-219, as its three permutes and the
  * product), xb_adjoint (:137-150), xb_twist (:589-602), xb_axpby (:640-676), xb_diag_map (:559-586), xb_tsvd (:237-374, full path + xb_tsvd_backward),

@@ -36,6 +36,11 @@ SIGNATURES = {
     "xb_ctx_create_planning": (C.c_int, [PP, C.POINTER(SymFactor), C.c_int]),
     "xb_ctx_free": (C.c_int, [P]),
     "xb_ctx_sync": (C.c_int, [P]),
+    "xb_tensor_save": (C.c_int, [P, P, C.c_char_p]),
+    "xb_tensor_load": (C.c_int, [P, C.c_char_p, PP]),
+    "xb_ctm_save": (C.c_int, [P, C.c_char_p]),
+    "xb_ctm_load": (C.c_int, [P, C.c_char_p, PP]),
+    "xb_tensor_from_charge_blocks": (C.c_int, [P, C.c_int, C.c_int, IP, C.POINTER(DP), C.POINTER(DP), IP, C.c_int64, LP, LP, DP, C.c_int64, C.c_int, PP]),
     "xb_tape_begin": (C.c_int, [P]),
     "xb_tape_end": (C.c_int, [P]),
     "xb_tape_seed_trace": (C.c_int, [P, P, C.c_double]),

@@ -61,13 +61,14 @@ void need(const void* p, const char* what)
     if(!p) throw std::invalid_argument(std::string("null argument: ") + what);
 }
 
-// In-place writes (upload, fills) while an AD tape is alive: the tape may hold this buffer as a recorded value, so the tensor moves to fresh storage first
-// (full overwrite: no copy; partial overwrite: the old contents are copied) -- the handle becomes a new, untracked value, like assigning a new tensor.
+// In-place writes (upload, fills): storage can be shared (an identity permute returns an alias of its operand; an AD tape keeps recorded values alive), so a
+// tensor whose storage has another owner, or any tensor while a tape exists, moves to fresh storage first (full overwrite: no copy; partial overwrite: the
+// old contents are copied) -- copy-on-write; under a tape the handle thereby becomes a new, untracked value, like assigning a new tensor.
 void detach_for_write(xb_tensor* t, bool keep_contents)
 {
     Context& c = t->ctx->impl;
-    if(c.tape == nullptr) return;
     Tensor& T = *t->t;
+    if(c.tape == nullptr && T.buf.use_count() <= 1) return;   // sole owner and no tape: write in place
     const size_t bytes = static_cast<size_t>(std::max<int64_t>(T.layout->size, 1)) * sizeof(double);
     auto fresh = std::make_shared<DevBuf>(&c, bytes, false);
     if(keep_contents) check_cuda(cudaMemcpyAsync(fresh->p, T.d, bytes, cudaMemcpyDeviceToDevice, c.stream), "detach copy");
@@ -166,6 +167,65 @@ int xb_ctx_stats(const xb_ctx* ctx, int64_t out[3])
         out[0] = ctx->impl.launches;
         out[1] = ctx->impl.plan_hits;
         out[2] = ctx->impl.plan_misses;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------- state interop
+int xb_tensor_save(xb_ctx* ctx, const xb_tensor* t, const char* path)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(t, "tensor");
+        need(path, "path");
+        save_tensor(ctx->impl, *t->t, path);
+    });
+}
+
+int xb_tensor_load(xb_ctx* ctx, const char* path, xb_tensor** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(path, "path");
+        need(out, "out");
+        *out = wrap(ctx, load_tensor(ctx->impl, path));
+    });
+}
+
+int xb_ctm_save(const xb_ctm* c, const char* path)
+{
+    return guard([&] {
+        need(c, "ctm");
+        need(path, "path");
+        save_ctm(c->ctx->impl, *c->c, c->c->chi(), path);
+    });
+}
+
+int xb_ctm_load(xb_ctx* ctx, const char* path, xb_ctm** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(path, "path");
+        need(out, "out");
+        *out = new xb_ctm{ctx, std::unique_ptr<Ctm>(load_ctm(ctx->impl, path))};
+    });
+}
+
+int xb_tensor_from_charge_blocks(xb_ctx* ctx, int nlegs, int rank, const int* ncharge, const double* const* charges, const double* const* sector_dims, const int* conj,
+                                 int64_t nblocks, const int64_t* voffs_index, const int64_t* voffs_offset, const double* vdat, int64_t nvdat, int qn_scale,
+                                 xb_tensor** out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(ncharge, "ncharge");
+        need(charges, "charges");
+        need(sector_dims, "sector_dims");
+        need(out, "out");
+        if(nblocks > 0) {
+            need(voffs_index, "voffs_index");
+            need(voffs_offset, "voffs_offset");
+            need(vdat, "vdat");
+        }
+        *out = wrap(ctx, tensor_from_charge_blocks(ctx->impl, nlegs, rank, ncharge, charges, sector_dims, conj, nblocks, voffs_index, voffs_offset, vdat, nvdat, qn_scale));
     });
 }
 

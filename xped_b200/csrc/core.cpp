@@ -387,6 +387,15 @@ void Qbasis::sort()
     data_.swap(nd);
 }
 
+void Qbasis::set_conj_dual()
+{
+    if(depth_ != 1) throw std::logic_error("set_conj_dual() needs a depth-1 basis");
+    sig_.clear();
+    conj_ = true;
+    for(auto& kv : trees_)
+        for(Tree& t : kv.second) t.dual[0] = true;
+}
+
 std::shared_ptr<Qbasis> Qbasis::conj() const
 {
     if(depth_ != 1) throw std::logic_error("conj() needs a depth-1 basis");

@@ -133,6 +133,7 @@ public:
     void push_back(const Q& q, int64_t inner_dim);                              // Qbasis.cpp:34-74
     void push_back(const Q& q, int64_t inner_dim, std::vector<Tree> trees);     // Qbasis.cpp:76-91
     void sort();                                                                // Qbasis.cpp:306-331
+    void set_conj_dual();   // SET_CONJ() + IS_DUAL[0] = true on every tree, charges untouched (what IO::loadMatlabTensor does to a conjugated leg, IO/Matlab.hpp:54-60)
     std::shared_ptr<Qbasis> conj() const;                                       // Qbasis.cpp:418-439
     std::shared_ptr<Qbasis> combine(const Qbasis& other) const;                 // Qbasis.cpp:441-495
     std::shared_ptr<Qbasis> forget_history() const;                             // Qbasis.cpp:410-416

@@ -27,6 +27,7 @@ public:
     Ctm(Context& ctx, int64_t chi, const std::vector<TP>& tensors);   // view on given C1..C4, T1..T4, A, Adag (checkpoint replay)
     bool checkpoint_moves = false;     // under an AD tape: record one checkpoint per move instead of every op
     std::vector<TP> all_tensors() const;
+    int64_t chi() const { return chi_; }
 
     void grow_all();                    // CTM.cpp:385-420
     void move(int direction);           // 0 left, 1 right, 2 top, 3 bottom  (CTM.cpp:924-1183)

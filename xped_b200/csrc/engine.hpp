@@ -349,6 +349,15 @@ private:
 
 void check_cuda(cudaError_t e, const char* what);
 
+// ---- state interop (io.cpp)
+class Ctm;
+void save_tensor(Context& ctx, const Tensor& t, const std::string& path);
+Tensor* load_tensor(Context& ctx, const std::string& path);
+void save_ctm(Context& ctx, const Ctm& c, int64_t chi, const std::string& path);
+Ctm* load_ctm(Context& ctx, const std::string& path);
+Tensor* tensor_from_charge_blocks(Context& ctx, int nlegs, int rank, const int* ncharge, const double* const* charges, const double* const* sdims, const int* conj,
+                                  int64_t nblocks, const int64_t* voffs_index, const int64_t* voffs_offset, const double* vdat, int64_t nvdat, int qn_scale);
+
 // RAII event pair around a launch group; `work` = algorithmic bytes (permute) or flops (GEMM).
 struct ProfScope
 {

@@ -17,6 +17,11 @@ namespace xb {
 Tensor* Context::permute(const Tensor& t, int shift, const std::vector<int>& pi)
 {
     auto plan = permute_plan(t.layout, shift, pi, false);
+    if(plan->identity_copy && plan->out.get() == t.layout.get()) {
+        // permute<0, identity> (short-circuited copy in the reference, Tensor.cpp:344): tensors are immutable values here (writers through the C ABI
+        // detach shared storage first), so the result shares the operand's storage -- no launch, no traffic, and the same value on an AD tape
+        return t.alias();
+    }
     auto* out = new Tensor(this, plan->out, false);
     ProfScope prof(*this, CAT_PERMUTE, static_cast<double>(plan->bytes));
     if(plan->identity_copy) {

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -1026,8 +1027,11 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
         if(n_proj == 0 || sum_k * 2 > sum_nb || sum_k > SEL_MAX) return false;
     }
     const std::string key = L.sig + "#" + std::to_string(K0) + "#" + std::to_string(svd_call_tag);   // one plan (and warm-start state) per call site
+    const auto wall0 = std::chrono::steady_clock::now();
+    bool new_plan = false;
     auto it = rsvd_plans.find(key);
     if(it == rsvd_plans.end()) {
+        new_plan = true;
         if(rsvd_plans.size() >= 12) {
             check_cuda(cudaStreamSynchronize(stream), "rsvd plan eviction sync");
             rsvd_plans.clear();
@@ -1159,6 +1163,9 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
     free_jacobi(*this, J);
     for(cudaEvent_t e : ev)
         if(e) event_pool.push_back(e);
+    if(verbose)
+        std::fprintf(stderr, "[rsvd] wall %.2f ms (new plan %d, cached plans %zu, graph %d)\n",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count(), new_plan ? 1 : 0, rsvd_plans.size(), use_graph ? 1 : 0);
     return ok;
 }
 

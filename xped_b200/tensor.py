@@ -269,6 +269,36 @@ class Tensor:
         check(self.ctx.lib.xb_view(self.h, int(pair), C.byref(ptr), C.byref(ld), C.byref(r), C.byref(c)))
         return ptr.value, ld.value, r.value, c.value
 
+    # ---- state interop: native container (xb_tensor_save / xb_tensor_load) and the charge-block (MATLAB) format of IO::loadMatlabTensor
+    def save(self, path):
+        check(self.ctx.lib.xb_tensor_save(self.ctx.h, self.h, str(path).encode()))
+
+    @staticmethod
+    def load(ctx, path):
+        h = C.c_void_p()
+        check(ctx.lib.xb_tensor_load(ctx.h, str(path).encode(), C.byref(h)))
+        return Tensor(ctx, h)
+
+    @staticmethod
+    def from_charge_blocks(ctx, charges, sector_dims, rank, voffs, vdat, conj=None, qn_scale=1):
+        """IO::loadMatlabTensor (include/Xped/IO/Matlab.hpp:9-95): charges / sector_dims = per leg the two rows of its `charges` dataset,
+        voffs = [(combined charge index, offset into vdat)], vdat = flat block data; rank = number of domain legs of the result."""
+        n = len(charges)
+        ncharge = _ints([len(c) for c in charges])
+        ch = [np.ascontiguousarray(c, dtype=np.float64) for c in charges]
+        sd = [np.ascontiguousarray(d, dtype=np.float64) for d in sector_dims]
+        DPP = C.POINTER(C.c_double) * n
+        chp = DPP(*[a.ctypes.data_as(C.POINTER(C.c_double)) for a in ch])
+        sdp = DPP(*[a.ctypes.data_as(C.POINTER(C.c_double)) for a in sd])
+        idx = np.ascontiguousarray([v[0] for v in voffs], dtype=np.int64)
+        off = np.ascontiguousarray([v[1] for v in voffs], dtype=np.int64)
+        vd = np.ascontiguousarray(vdat, dtype=np.float64)
+        cj = _ints([int(bool(x)) for x in (conj if conj is not None else [0] * n)])
+        h = C.c_void_p()
+        check(ctx.lib.xb_tensor_from_charge_blocks(ctx.h, n, int(rank), ncharge, chp, sdp, cj, len(voffs), idx.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                   off.ctypes.data_as(C.POINTER(C.c_int64)), vd.ctypes.data_as(C.POINTER(C.c_double)), vd.size, int(qn_scale), C.byref(h)))
+        return Tensor(ctx, h)
+
     def upload(self, data):
         a = np.ascontiguousarray(data, dtype=np.float64)
         check(self.ctx.lib.xb_tensor_upload(self.h, a.ctypes.data_as(capi.DP), a.size))
@@ -408,6 +438,17 @@ class CTM:
                 self.ctx.lib.xb_ctm_free(self.h)
         except Exception:
             pass
+
+    def save(self, path):
+        check(self.ctx.lib.xb_ctm_save(self.h, str(path).encode()))
+
+    @staticmethod
+    def load(ctx, path):
+        h = C.c_void_p()
+        check(ctx.lib.xb_ctm_load(ctx.h, str(path).encode(), C.byref(h)))
+        obj = CTM.__new__(CTM)
+        obj.ctx, obj.h = ctx, h
+        return obj
 
     def grow_all(self): check(self.ctx.lib.xb_ctm_step(self.h))
     def move(self, direction): check(self.ctx.lib.xb_ctm_move(self.h, int(direction)))

@@ -264,7 +264,9 @@ def kernel_sections(xb, device, torch, cpu_d6=False):
     env3 = [(1, 16), (2, 32), (3, 36), (4, 30), (5, 18), (6, 8), (7, 4)]
     ctx3 = xb.Context([("SU2", 0, 0)], device=device)
     Q4, Q1 = su2_corner_pair(ctx3, aux3, env3, (1, 2))
-    ms, fl = Q4.bench_multiply(Q1, reps=5)
+    Q4.bench_multiply(Q1, reps=2)
+    ctx3.sync()
+    ms, fl = min(Q4.bench_multiply(Q1, reps=5) for _ in range(3))
     out["contract_w3"] = {"op": "Q4*Q1, SU(2) D=6 chi=144 corners (9 sectors, block side 36..2394)", "flops": fl, "ms": ms, "TFLOPs": fl / ms / 1e9,
                           "frac_of_cublas_dgemm": fl / ms / 1e9 / dgemm_peak}
     prow = []
@@ -278,7 +280,16 @@ def kernel_sections(xb, device, torch, cpu_d6=False):
     ctx3.sync()
     ctx3.timer_start()
     U, S, Vd = M.tSVD(144, 1e-10, False)
-    out["tsvd_w3"] = {"op": "tSVD(144, 1e-10) of M = Q4*Q1 (blocks 36..2394, 10800 singular values)", "ms": ctx3.timer_stop()}
+    cold_ms = ctx3.timer_stop()   # first call on this layout: plan construction, CUDA-graph capture, no warm start
+    del U, S, Vd
+    warm = []
+    for _ in range(3):
+        ctx3.sync()
+        ctx3.timer_start()
+        U, S, Vd = M.tSVD(144, 1e-10, False)
+        warm.append(ctx3.timer_stop())
+    out["tsvd_w3"] = {"op": "tSVD(144, 1e-10) of M = Q4*Q1 (blocks 36..2394, 10800 singular values)", "ms": min(warm), "ms_calls": warm, "ms_first_call": cold_ms,
+                      "note": "first call builds the per-layout plan (buffers, CUDA graphs); later calls on the same layout -- the CTM case -- reuse it and warm-start"}
     del U, S, Vd, M, Q4, Q1
     # ---- the north-star target workload: one CTMRG step at D=6, chi=144 (SU(2), 1x1 cell, FROM_A; chi saturates after two steps)
     try:

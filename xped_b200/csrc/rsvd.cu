@@ -540,6 +540,181 @@ rsvd_chol_kernel(const double* __restrict__ G, double* __restrict__ M, const Rsv
     }
 }
 
+// Blocked form of the same factorisation (used for K > 32): the matrix lives in SHARED memory (column-major, odd pitch), 16-column blocks.
+// Per block step: (1) warp 0 factorises the 16 x 16 diagonal block in registers (lane = row, pivots / multipliers through shuffles) and inverts its factor;
+// (2) panel = A[below, block] * Linv^T (all threads, four outputs each); (3) trailing matrix -= panel * panel^T on 4 x 4 register tiles with rows / columns
+// interleaved by a quarter of the trailing size (consecutive lanes -> consecutive addresses).  Three barriers per 16 columns instead of one per column, and the
+// per-column latency chain (publish -> barrier -> rsqrt -> update) is paid inside one warp.  X = L^-1 is then built by forward substitution in blocks of 16
+// rows, every half-warp owning every 32nd column (columns are independent), straight into the upper triangle of the shared matrix, which thereby becomes M = X^T.
+constexpr int CHB = 16;
+constexpr int CHOL_THREADS = 512;
+__global__ void __launch_bounds__(CHOL_THREADS, 1)
+rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, const RsvdSec* __restrict__ secs, const int* __restrict__ list, double shift_rel,
+                         double* __restrict__ diag, int* __restrict__ bad)
+{
+    extern __shared__ double chol_sh[];
+    __shared__ double red[32];
+    const int sec = list[blockIdx.x];
+    const RsvdSec s = secs[sec];
+    const int K = s.K, Kp = (K + CHB - 1) / CHB * CHB, LD = Kp + 1, nblk = Kp / CHB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* __restrict__ A = chol_sh;              // Kp x LD: A[c * LD + i]
+    double* __restrict__ Pb = A + Kp * LD;         // panel, k-major: Pb[k * Kp + i]
+    double* __restrict__ Li = Pb + CHB * Kp;       // inverse of the current diagonal factor: Li[r * 17 + c]
+    double* __restrict__ dinv = Li + CHB * (CHB + 1);   // 1 / L_jj
+    const double* __restrict__ g = G + s.g_off;
+    double gmax = 0.0;
+    for(int e = tid; e < Kp * Kp; e += CHOL_THREADS) {
+        const int c = e / Kp, i = e - c * Kp;
+        const double v = (i < K && c < K) ? g[i + c * K] : (i == c ? 1.0 : 0.0);   // identity padding: decoupled
+        A[c * LD + i] = v;
+        if(i == c && i < K) gmax = fmax(gmax, v);
+    }
+    for(int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if(lane == 0) red[warp] = gmax;
+    __syncthreads();
+    gmax = lane < CHOL_THREADS / 32 ? red[lane] : 0.0;
+    for(int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if(!(gmax > 0.0)) gmax = 1.0;
+    const double shift = shift_rel * gmax, gmax_inv = 1.0 / gmax;
+    for(int i = tid; i < K; i += CHOL_THREADS) A[i * LD + i] += shift;
+    __syncthreads();
+
+    double minpiv = 1.e300;
+    bool anybad = false;
+    for(int kb = 0; kb < nblk; ++kb) {
+        const int c0 = kb * CHB, r0 = c0 + CHB, nrows = Kp - r0;
+        if(warp == 0) {
+            // ---- diagonal block: lane r (both half-warps redundantly) owns row r
+            const int r = lane & 15;
+            double d[CHB];
+#pragma unroll
+            for(int c = 0; c < CHB; ++c) d[c] = c <= r ? A[(c0 + c) * LD + c0 + r] : 0.0;
+#pragma unroll
+            for(int j = 0; j < CHB; ++j) {
+                double djj = __shfl_sync(0xffffffffu, d[j], j);
+                if(!(djj > 0.0) || !isfinite(djj)) {
+                    anybad = true;
+                    djj = gmax * 1.e-30;
+                }
+                if(c0 + j < K) minpiv = fmin(minpiv, djj * gmax_inv);
+                const double rs = rsqrt(djj);
+                if(lane == j) dinv[c0 + j] = rs;
+                const double l = r > j ? d[j] * rs : (r == j ? djj * rs : 0.0);
+                d[j] = l;
+#pragma unroll
+                for(int c = j + 1; c < CHB; ++c) {
+                    const double lc = __shfl_sync(0xffffffffu, l, c);
+                    d[c] = fma(-l, lc, d[c]);
+                }
+            }
+            __syncwarp();
+            // ---- X = L^-1 of the block by columns: lane c solves L x = e_c (L_ik from its row owner)
+            double x[CHB];
+#pragma unroll
+            for(int i = 0; i < CHB; ++i) {
+                double acc = (i == r) ? 1.0 : 0.0;
+#pragma unroll
+                for(int k = 0; k < i; ++k) acc = fma(-__shfl_sync(0xffffffffu, d[k], i), x[k], acc);
+                x[i] = acc * dinv[c0 + i];
+            }
+            if(lane < CHB) {
+#pragma unroll
+                for(int c = 0; c < CHB; ++c)
+                    if(c <= r) A[(c0 + c) * LD + c0 + r] = d[c];               // L block
+#pragma unroll
+                for(int i = 0; i < CHB; ++i) {
+                    Li[i * (CHB + 1) + r] = x[i];                               // Linv[i][c = r] (zero above the diagonal)
+                    if(i > r) A[(c0 + i) * LD + c0 + r] = x[i];                 // M part: position (row c, col i) = X[i][c]
+                }
+            }
+        }
+        __syncthreads();
+        if(nrows > 0) {
+            // ---- panel: P[i][j] = sum_{c <= j} A[r0 + i][c0 + c] * Linv[j][c]
+            for(int idx = tid; idx < nrows * 4; idx += CHOL_THREADS) {
+                const int jq = idx / nrows, i = idx - jq * nrows;
+                double a[CHB];
+#pragma unroll
+                for(int c = 0; c < CHB; ++c) a[c] = A[(c0 + c) * LD + r0 + i];
+#pragma unroll
+                for(int jj = 0; jj < 4; ++jj) {
+                    const int j = jq * 4 + jj;
+                    double p = 0.0;
+#pragma unroll
+                    for(int c = 0; c < CHB; ++c) p = fma(a[c], Li[j * (CHB + 1) + c], p);   // Linv is lower triangular: entries with c > j are zero
+                    Pb[j * Kp + i] = p;
+                }
+            }
+            __syncthreads();
+            // ---- trailing update (full square: the matrix stays symmetric) + the panel goes back into the matrix
+            const int q = nrows >> 2;
+            for(int t = tid; t < q * q; t += CHOL_THREADS) {
+                const int tc = t / q, ti = t - tc * q;
+                double acc[4][4];
+#pragma unroll
+                for(int a = 0; a < 4; ++a)
+#pragma unroll
+                    for(int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 4
+                for(int k = 0; k < CHB; ++k) {
+                    double pr[4], pc[4];
+#pragma unroll
+                    for(int a = 0; a < 4; ++a) pr[a] = Pb[k * Kp + ti + a * q];
+#pragma unroll
+                    for(int b = 0; b < 4; ++b) pc[b] = Pb[k * Kp + tc + b * q];
+#pragma unroll
+                    for(int a = 0; a < 4; ++a)
+#pragma unroll
+                        for(int b = 0; b < 4; ++b) acc[a][b] = fma(pr[a], pc[b], acc[a][b]);
+                }
+#pragma unroll
+                for(int b = 0; b < 4; ++b)
+#pragma unroll
+                    for(int a = 0; a < 4; ++a) A[(r0 + tc + b * q) * LD + r0 + ti + a * q] -= acc[a][b];
+            }
+            for(int idx = tid; idx < nrows * CHB; idx += CHOL_THREADS) {
+                const int j = idx / nrows, i = idx - j * nrows;
+                A[(c0 + j) * LD + r0 + i] = Pb[j * Kp + i];
+            }
+            __syncthreads();
+        }
+    }
+    // ---- X = L^-1 below the diagonal blocks: column c, rows of block ib:  X[ib][c] = -Linv_ib * sum_{k = 16 jb}^{16 ib - 1} L[ib rows][k] * X[k][c];
+    // X[k][c] sits at A[k * LD + c] (upper triangle), Linv_ib[r][k] (k < r) at A[(16 ib + r) * LD + 16 ib + k], its diagonal in dinv
+    {
+        const int r = lane & 15, half = lane >> 4;
+        const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+        for(int c = warp * 2 + half; c < Kp; c += CHOL_THREADS / 16) {
+            const int jb = c / CHB;
+            for(int ib = jb + 1; ib < nblk; ++ib) {
+                const int row = ib * CHB + r;
+                double sacc = 0.0;
+                for(int k = jb * CHB; k < ib * CHB; ++k) sacc = fma(A[k * LD + row], k == c ? dinv[c] : (k < c ? 0.0 : A[k * LD + c]), sacc);
+                double t = 0.0;
+#pragma unroll
+                for(int k = 0; k < CHB; ++k) {
+                    const double sk = __shfl_sync(hmask, sacc, (half << 4) | k);
+                    const double lik = k < r ? A[row * LD + ib * CHB + k] : (k == r ? dinv[row] : 0.0);
+                    t = fma(-lik, sk, t);
+                }
+                A[row * LD + c] = t;
+                __syncwarp(hmask);
+            }
+        }
+    }
+    __syncthreads();
+    double* __restrict__ m_out = M + s.g_off;
+    for(int e = tid; e < K * K; e += CHOL_THREADS) {
+        const int c = e / K, rr = e - c * K;   // M(rr, c) = X(c, rr)
+        m_out[e] = rr < c ? A[c * LD + rr] : (rr == c ? dinv[c] : 0.0);
+    }
+    if(tid == 0) {
+        diag[sec] = minpiv;
+        if(anybad) atomicOr(bad, 1);
+    }
+}
+
 // residual of the Ritz triplets: res[id] = || Zr_i - sigma_i^2 v_i || / sigma_i  with Zr = B^T W (W_i = sigma_i u_i); one warp per column
 __global__ void rsvd_residual_kernel(const double* __restrict__ Zr, const double* __restrict__ Vf, const double* __restrict__ sigma, const RsvdSec* __restrict__ secs,
                                      const int* __restrict__ list, double* __restrict__ res)
@@ -766,6 +941,21 @@ namespace {
 void rsvd_chol(RsvdPlan& P, double shift_rel)
 {
     cudaStream_t s = P.ctx->stream;
+    static const bool old_form = std::getenv("XB_CHOL_OLD") != nullptr;
+    if(P.K0 > 32 && !old_form) {
+        const int Kp = (P.K0 + CHB - 1) / CHB * CHB;
+        const size_t smem = sizeof(double) * (static_cast<size_t>(Kp) * (Kp + 1) + CHB * Kp + CHB * (CHB + 1) + Kp);
+        static size_t configured = 0;   // NB: per process; the attribute is per device (every device of a process runs the same kernels with the same maximum)
+        if(smem > configured) {
+            const int most = 227 * 1024 - 512;   // the opt-in maximum covers static + dynamic shared memory (256 bytes are static)
+            check_cuda(cudaFuncSetAttribute(rsvd_chol_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, most), "chol smem attr");
+            configured = most;
+        }
+        rsvd_chol_blocked_kernel<<<P.n_proj, CHOL_THREADS, smem, s>>>(P.dG, P.dM, P.d_secs, P.d_proj, shift_rel, P.dDiag, P.d_bad);
+        check_cuda(cudaGetLastError(), "rsvd_chol_blocked_kernel launch");
+        ++P.ctx->launches;
+        return;
+    }
 #define XB_CHOL(NBR, NBC, TY) rsvd_chol_kernel<NBR, NBC, TY><<<P.n_proj, 32 * TY, 0, s>>>(P.dG, P.dM, P.d_secs, P.d_proj, shift_rel, P.dDiag, P.d_bad)
     switch((P.K0 + 31) / 32) {
     // few warps with many elements each: the kernel is bound by the instruction issue rate (per-step overhead is paid per warp)

@@ -202,6 +202,26 @@ int xb_dist_permute_pack(xb_ctx* ctx, const xb_dist_plan* plan, const xb_tensor*
 int xb_dist_permute_local(xb_ctx* ctx, const xb_dist_plan* plan, const xb_tensor* local_in, xb_tensor** local_out);
 int xb_dist_permute_remote(xb_ctx* ctx, const xb_dist_plan* plan, const xb_tensor* local_in, const double* d_recv, xb_tensor* local_out);
 /* operator* on shards: the result holds exactly the listed sectors (the ones this rank owns of the product) */
+/* ---- peer-memory form of the exchange (csrc/dist.cu, csrc/dist_ops.cpp): every rank maps the device arena of every other rank of the box (CUDA IPC), so the
+ * exchange step of a sharded permute is fused into the permute launches (the owner of a source sub-block transposes it straight into the output shard of the
+ * destination's owner over NVLink) and a product can be balanced by ROW PANELS of the heavy sectors.  Start-up: rank 0 calls xb_dist_shm_create(name, world),
+ * all ranks synchronise (any host barrier), every rank calls xb_dist_init (collective; tensors created afterwards live in the arena).  All ranks must issue the
+ * same xb_dist_* operations in the same order.  No reference counterpart (the reference's MPI/Cyclops backend distributes dense blocks inside CTF). */
+int xb_dist_shm_create(const char* shm_name, int world);
+int xb_dist_init(xb_ctx* ctx, int my_rank, int world, int64_t arena_bytes, const char* shm_name);
+int xb_dist_shutdown(xb_ctx* ctx);
+int xb_dist_barrier(xb_ctx* ctx);                          /* stream-ordered barrier over all ranks (device side, NVLink flags) */
+int xb_dist_arena_stats(const xb_ctx* ctx, int64_t out[3]); /* arena bytes, bytes in use, high-water mark */
+int xb_dist_plan_pushable(const xb_dist_plan* plan, int* pushable);   /* 1: fan-in 1 everywhere, xb_dist_permute_push applies */
+int xb_dist_permute_push(xb_ctx* ctx, const xb_dist_plan* plan, const xb_tensor* local_in, xb_tensor** local_out);
+/* operator* on shards (src/Core/TensorBase.cpp:243-288); owner_a / owner_b: owner of every sector of the GLOBAL operands (common sectors must agree); sectors
+ * that overload their owner are cut into row panels of >= panel_rows_min rows computed by other ranks; owner_out (may be null): owner of the result's sectors */
+int xb_dist_multiply(xb_ctx* ctx, const xb_tensor* a_local, const int* owner_a, const xb_tensor* b_local, const int* owner_b, int panel_rows_min, xb_tensor** c_local,
+                     int* owner_out, int n_owner_out);
+/* the deterministic panel assignment used by xb_dist_multiply (host only): per panel (sector, rank, row0, rows) as four int64 */
+int xb_dist_multiply_assignment(const int64_t* m, const int64_t* n, const int64_t* k, const int* owner, int n_sectors, int world, int panel_rows_min,
+                                int64_t* n_panels, int64_t* out);
+
 int xb_multiply_sectors(xb_ctx* ctx, const xb_tensor* a, int adj_a, const xb_tensor* b, int adj_b, const int* q, int n_sectors, xb_tensor** out);
 
 /* ---- CTM driver (1x1 unit cell, TRank = 2, corner projectors)  src/PEPS/CTM.cpp:45-244,385-420,924-1760 ------

@@ -41,6 +41,15 @@ SIGNATURES = {
     "xb_ctm_save": (C.c_int, [P, C.c_char_p]),
     "xb_ctm_load": (C.c_int, [P, C.c_char_p, PP]),
     "xb_tensor_from_charge_blocks": (C.c_int, [P, C.c_int, C.c_int, IP, C.POINTER(DP), C.POINTER(DP), IP, C.c_int64, LP, LP, DP, C.c_int64, C.c_int, PP]),
+    "xb_dist_shm_create": (C.c_int, [C.c_char_p, C.c_int]),
+    "xb_dist_init": (C.c_int, [P, C.c_int, C.c_int, C.c_int64, C.c_char_p]),
+    "xb_dist_shutdown": (C.c_int, [P]),
+    "xb_dist_barrier": (C.c_int, [P]),
+    "xb_dist_arena_stats": (C.c_int, [P, LP]),
+    "xb_dist_plan_pushable": (C.c_int, [P, IP]),
+    "xb_dist_permute_push": (C.c_int, [P, P, P, PP]),
+    "xb_dist_multiply": (C.c_int, [P, P, IP, P, IP, C.c_int, PP, IP, C.c_int]),
+    "xb_dist_multiply_assignment": (C.c_int, [LP, LP, LP, IP, C.c_int, C.c_int, C.c_int, LP, LP]),
     "xb_tape_begin": (C.c_int, [P]),
     "xb_tape_end": (C.c_int, [P]),
     "xb_tape_seed_trace": (C.c_int, [P, P, C.c_double]),

@@ -10,6 +10,7 @@
 
 #include "ad.hpp"
 #include "ctm.hpp"
+#include "dist.hpp"
 #include "engine.hpp"
 
 using namespace xb;
@@ -911,6 +912,117 @@ int xb_dist_permute_remote(xb_ctx* ctx, const xb_dist_plan* plan, const xb_tenso
         need(local_in, "local_in");
         need(local_out, "local_out");
         ctx->impl.dist_remote(*plan->p, *local_in->t, d_recv, *local_out->t);
+    });
+}
+
+int xb_dist_shm_create(const char* shm_name, int world)
+{
+    return guard([&] {
+        need(shm_name, "shm_name");
+        dist_shm_create(shm_name, world);
+    });
+}
+
+int xb_dist_init(xb_ctx* ctx, int my_rank, int world, int64_t arena_bytes, const char* shm_name)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(shm_name, "shm_name");
+        dist_init(ctx->impl, my_rank, world, static_cast<size_t>(arena_bytes), shm_name);
+    });
+}
+
+int xb_dist_shutdown(xb_ctx* ctx)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        ctx->impl.sync();
+        dist_shutdown(ctx->impl);
+    });
+}
+
+int xb_dist_barrier(xb_ctx* ctx)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        dist_barrier(ctx->impl);
+    });
+}
+
+int xb_dist_arena_stats(const xb_ctx* ctx, int64_t out[3])
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(out, "out");
+        dist_arena_stats(ctx->impl, out);
+    });
+}
+
+int xb_dist_plan_pushable(const xb_dist_plan* plan, int* pushable)
+{
+    return guard([&] {
+        need(plan, "plan");
+        need(pushable, "pushable");
+        *pushable = plan->p->push.empty() ? 0 : 1;
+    });
+}
+
+int xb_dist_permute_push(xb_ctx* ctx, const xb_dist_plan* plan, const xb_tensor* local_in, xb_tensor** local_out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(plan, "plan");
+        need(local_in, "local_in");
+        need(local_out, "local_out");
+        *local_out = wrap(ctx, ctx->impl.dist_permute_push(*plan->p, *local_in->t));
+    });
+}
+
+int xb_dist_multiply(xb_ctx* ctx, const xb_tensor* a_local, const int* owner_a, const xb_tensor* b_local, const int* owner_b, int panel_rows_min, xb_tensor** c_local,
+                     int* owner_out, int n_owner_out)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(a_local, "a_local");
+        need(b_local, "b_local");
+        need(owner_a, "owner_a");
+        need(owner_b, "owner_b");
+        need(c_local, "c_local");
+        Context& c = ctx->impl;
+        const Layout& LA = *a_local->t->layout;
+        const Layout& LB = *b_local->t->layout;
+        const size_t na = c.layout(LA.dom, LA.cod)->sector.size(), nb = c.layout(LB.dom, LB.cod)->sector.size();
+        std::vector<int> oo;
+        *c_local = wrap(ctx, c.dist_multiply(*a_local->t, std::vector<int>(owner_a, owner_a + na), *b_local->t, std::vector<int>(owner_b, owner_b + nb),
+                                             panel_rows_min < 2 ? 256 : panel_rows_min, &oo));
+        if(owner_out) {
+            if(n_owner_out != static_cast<int>(oo.size())) throw std::invalid_argument("xb_dist_multiply: owner_out needs one entry per sector of the result");
+            std::copy(oo.begin(), oo.end(), owner_out);
+        }
+    });
+}
+
+int xb_dist_multiply_assignment(const int64_t* m, const int64_t* n, const int64_t* k, const int* owner, int n_sectors, int world, int panel_rows_min,
+                                int64_t* n_panels, int64_t* out)
+{
+    return guard([&] {
+        need(n_panels, "n_panels");
+        if(world < 1 || world > DIST_MAX_WORLD) throw std::invalid_argument("xb_dist_multiply_assignment: world must be 1..8");
+        std::vector<int64_t> vm(m, m + n_sectors), vn(n, n + n_sectors), vk(k, k + n_sectors);
+        std::vector<int> vo(owner, owner + n_sectors);
+        for(int o : vo)
+            if(o < 0 || o >= world) throw std::invalid_argument("xb_dist_multiply_assignment: owner out of range");
+        const auto panels = dist_multiply_assignment(vm, vn, vk, vo, world, panel_rows_min < 2 ? 256 : panel_rows_min, 0.02);
+        if(out) {
+            if(*n_panels < static_cast<int64_t>(panels.size())) throw std::invalid_argument("xb_dist_multiply_assignment: output too small");
+            for(size_t i = 0; i < panels.size(); ++i) {
+                out[4 * i + 0] = panels[i].sector;
+                out[4 * i + 1] = panels[i].rank;
+                out[4 * i + 2] = panels[i].row0;
+                out[4 * i + 3] = panels[i].rows;
+            }
+        }
+        *n_panels = static_cast<int64_t>(panels.size());
     });
 }
 

@@ -145,6 +145,10 @@ struct DistPermutePlan
     int64_t send_total = 0, recv_total = 0;
     int64_t split = 0;   // = in_local->size
     PermutePlan pack, local, remote;
+    // direct-write form (every destination sub-block has at most one source: Abelian plans): push[p] = the tasks whose SOURCE this rank owns and whose
+    // destination rank p owns, lowered against p's output shard -- launched with dst = p's shard (peer-mapped); no buffers, no collective (dist.cu)
+    std::vector<std::unique_ptr<PermutePlan>> push;
+    bool push_zero_fill = false;   // a destination sub-block of this rank has no source at all
     int64_t bytes_local = 0;   // algorithmic bytes moved through this rank's HBM by local + remote: 8 * (N_in_local + N_out_local)
     // host copies of the three work lists for introspection and the CPU (gloo) tests: flat int64 records
     static constexpr int MAXL = 16;
@@ -153,6 +157,11 @@ struct DistPermutePlan
     static constexpr int SRC_REC = 4 + MAXL;        // remote flag, off (local tensor or receive buffer), coeff bits, 0, sstride[16]
     std::vector<int64_t> pack_records, task_records, src_records;
 };
+
+// one row panel C_q[row0 : row0 + rows, :] of a sharded product, computed by `rank` (dist_ops.cpp)
+struct DistPanel { int sector; int rank; int64_t row0, rows; };
+std::vector<DistPanel> dist_multiply_assignment(const std::vector<int64_t>& m, const std::vector<int64_t>& n, const std::vector<int64_t>& k, const std::vector<int>& owner,
+                                                int world, int panel_rows_min, double imbalance_tol);
 
 constexpr int GEMM_TILE_N = 64;   // CTA tile of gemm_grouped_kernel is tile_m x 64 with tile_m = 128 (large sectors) or 64
 
@@ -187,6 +196,7 @@ struct PreparedGemm
 
 class Context;
 class Tape;
+struct DistState;   // peer arenas, mailbox, barrier (dist.cu)
 struct RsvdPlan;   // cached state of the truncated tSVD for one layout (rsvd.cu)
 
 // device storage of a tensor; shared between a Tensor and its aliases (the AD tape keeps values alive through aliases)
@@ -194,6 +204,7 @@ struct DevBuf
 {
     Context* ctx;
     double* p = nullptr;
+    int64_t arena_off = -1;   // >= 0: lives in the peer-mapped arena of the context (dist.cu) at this byte offset
     DevBuf(Context* c, size_t bytes, bool zero);
     ~DevBuf();
     DevBuf(const DevBuf&) = delete;
@@ -245,6 +256,12 @@ public:
     void dist_pack(const DistPermutePlan& plan, const Tensor& local_in, double* d_send);
     Tensor* dist_local(const DistPermutePlan& plan, const Tensor& local_in);
     void dist_remote(const DistPermutePlan& plan, const Tensor& local_in, const double* d_recv, Tensor& local_out);
+    // peer-memory form of the exchange (dist.cu / dist_ops.cpp): needs distributed state (xb_dist_init)
+    DistState* dist = nullptr;
+    bool arena_force = false;   // the next tensor allocations must come from the arena (buffers that peers address)
+    Tensor* dist_permute_push(const DistPermutePlan& plan, const Tensor& local_in);
+    // operator* on shards with row-panel splitting of the heavy sectors; owner maps over the GLOBAL sector lists of the operands (common sectors must agree)
+    Tensor* dist_multiply(const Tensor& a, const std::vector<int>& owner_a, const Tensor& b, const std::vector<int>& owner_b, int panel_rows_min, std::vector<int>* owner_out);
     Tensor* multiply_sectors(const Tensor& a, bool adj_a, const Tensor& b, bool adj_b, const std::vector<Q>* out_sectors);
     bool planning_only() const { return device < 0; }
 

@@ -14,6 +14,7 @@
 #include <numeric>
 #include <stdexcept>
 
+#include "dist.hpp"
 #include "engine.hpp"
 
 namespace xb {
@@ -52,6 +53,7 @@ Context::~Context()
     if(device < 0) return;
     cudaSetDevice(device);
     if(stream) cudaStreamSynchronize(stream);
+    dist_shutdown(*this);
     clear_rsvd_plans();
     plan_cache_.clear();
     for(const ProfRec& r : prof_recs) {
@@ -202,13 +204,24 @@ void Context::upload_async(void* dst, const void* src, size_t bytes)
 
 DevBuf::DevBuf(Context* c, size_t bytes, bool zero) : ctx(c)
 {
-    check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&p), bytes, ctx->stream), "cudaMallocAsync(block arena)");
+    // with distributed state, tensors live in the peer-mapped arena (small ones only on request: they are never exchanged)
+    if(ctx->dist && (ctx->arena_force || bytes >= (1u << 16))) {
+        if(!arena_alloc(*ctx, bytes, &p, &arena_off)) {
+            arena_off = -1;
+            p = nullptr;
+            if(ctx->arena_force) throw std::bad_alloc();
+        }
+    }
+    if(!p) check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&p), bytes, ctx->stream), "cudaMallocAsync(block arena)");
     if(zero) check_cuda(cudaMemsetAsync(p, 0, bytes, ctx->stream), "cudaMemsetAsync");
 }
 
 DevBuf::~DevBuf()
 {
-    if(p) cudaFreeAsync(p, ctx->stream);
+    if(arena_off >= 0)
+        arena_free(*ctx, arena_off);   // host-ordered; reuse is stream-ordered on the context stream, peers are fenced by the barriers of each exchange
+    else if(p)
+        cudaFreeAsync(p, ctx->stream);
 }
 
 Tensor::Tensor(Context* c, LayoutPtr l, bool zero) : ctx(c), layout(std::move(l))
@@ -1078,16 +1091,17 @@ std::shared_ptr<DistPermutePlan> Context::dist_permute_plan(const LayoutPtr& in,
         P.owner_out = owner_out_arg;
     }
     // ---- this rank's shards
-    auto shard = [&](const LayoutPtr& L, const std::vector<int>& owner, std::vector<int>& local_index) {
+    auto shard_of = [&](const LayoutPtr& L, const std::vector<int>& owner, int r, std::vector<int>& local_index) {
         std::vector<Q> mine;
         local_index.assign(L->sector.size(), -1);
         for(size_t i = 0; i < L->sector.size(); ++i)
-            if(owner[i] == rank) {
+            if(owner[i] == r) {
                 local_index[i] = static_cast<int>(mine.size());
                 mine.push_back(L->sector[i]);
             }
         return layout_custom(L->dom, L->cod, mine);
     };
+    auto shard = [&](const LayoutPtr& L, const std::vector<int>& owner, std::vector<int>& local_index) { return shard_of(L, owner, rank, local_index); };
     std::vector<int> loc_in, loc_out;
     P.in_local = shard(in, P.owner_in, loc_in);
     P.out_local = shard(out, P.owner_out, loc_out);
@@ -1177,6 +1191,39 @@ std::shared_ptr<DistPermutePlan> Context::dist_permute_plan(const LayoutPtr& in,
     lower_tasks(*this, local_tasks, ts.leg_of, ts.N, P.local);
     lower_tasks(*this, remote_tasks, ts.leg_of, ts.N, P.remote);
     P.pack.bytes = 16 * P.send_total;
+    // ---- direct-write form: the owner of the SOURCE sub-block transposes it straight into the destination owner's output shard
+    bool fan_in_one = true;
+    for(const DstTask& g : ts.tasks)
+        if(g.srcs.size() > 1) {
+            fan_in_one = false;
+            break;
+        }
+    if(fan_in_one) {
+        std::vector<LayoutPtr> out_shard(world);
+        std::vector<std::vector<int>> loc_of(world);
+        for(int p = 0; p < world; ++p) out_shard[p] = shard_of(out, P.owner_out, p, loc_of[p]);
+        std::vector<std::vector<DstTask>> push_tasks(world);
+        std::vector<int64_t> push_elems(world, 0);
+        for(const DstTask& g : ts.tasks) {
+            const int rd = P.owner_out[g.dst.sector];
+            if(g.srcs.empty()) {
+                if(rd == rank) P.push_zero_fill = true;
+                continue;
+            }
+            if(P.owner_in[g.srcs[0].src.sector] != rank) continue;
+            DstTask t;
+            t.dst = localise(g.dst, out_shard[rd], loc_of[rd]);
+            t.srcs.push_back({localise(g.srcs[0].src, P.in_local, loc_in), g.srcs[0].coeff});
+            push_elems[rd] += t.dst.count();
+            push_tasks[rd].push_back(std::move(t));
+        }
+        P.push.resize(world);
+        for(int p = 0; p < world; ++p) {
+            P.push[p] = std::make_unique<PermutePlan>();
+            lower_tasks(*this, push_tasks[p], ts.leg_of, ts.N, *P.push[p]);
+            P.push[p]->bytes = 16 * push_elems[p];
+        }
+    }
     if(dist_plan_cache_.size() >= 512) dist_plan_cache_.clear();   // plans own device tables; callers hold shared_ptr copies while they run
     dist_plan_cache_.emplace(key, plan);
     return plan;

@@ -143,6 +143,34 @@ class Comm:
         return float(t.item())
 
 
+def enable_peer_memory(ctx, comm, arena_bytes=8 << 30, name=None):
+    """Map every rank's device arena into every other rank (CUDA IPC over NVLink; csrc/dist.cu).  Collective.  Afterwards the tensors of `ctx` live in the
+    arena, sharded permutes of Abelian tensors run as fused permute + exchange launches (xb_dist_permute_push) and products are balanced by row panels
+    (xb_dist_multiply).  Without it (or for plans with recoupling sums) the pack -> NCCL alltoallv -> gather form is used."""
+    import os
+    if getattr(ctx, "_peer_memory", False):
+        return
+    if name is None:
+        name = f"/xb2dist_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
+    if comm.rank == 0:
+        check(ctx.lib.xb_dist_shm_create(name.encode(), comm.world))
+    if comm.world > 1:
+        comm.dist.barrier(group=comm.group)
+    check(ctx.lib.xb_dist_init(ctx.h, comm.rank, comm.world, int(arena_bytes), name.encode()))
+    ctx._peer_memory = True
+
+
+def multiply_panel_assignment(ctx, m, n, k, owner, world, panel_rows_min=256):
+    """the deterministic (sector, rank, row0, rows) panel list of xb_dist_multiply (host only)"""
+    ns = len(m)
+    arr = lambda v: (C.c_int64 * max(ns, 1))(*[int(x) for x in v])
+    cnt = C.c_int64(0)
+    check(ctx.lib.xb_dist_multiply_assignment(arr(m), arr(n), arr(k), _ints(owner), ns, int(world), int(panel_rows_min), C.byref(cnt), None))
+    out = (C.c_int64 * max(4 * cnt.value, 1))()
+    check(ctx.lib.xb_dist_multiply_assignment(arr(m), arr(n), arr(k), _ints(owner), ns, int(world), int(panel_rows_min), C.byref(cnt), out))
+    return [tuple(out[4 * i:4 * i + 4]) for i in range(cnt.value)]
+
+
 class ShardedTensor:
     """Tensor<double,Rank,CoRank,Symmetry> with its sectors distributed over the ranks of `comm`."""
 
@@ -199,6 +227,15 @@ class ShardedTensor:
     def _permute(self, shift, p, owner_out, adjoint):
         import torch
         ctx, lib = self.ctx, self.ctx.lib
+        if getattr(ctx, "_peer_memory", False):
+            plan = PermuteExchangePlan(ctx, self.domain, self.codomain, shift, p, self.owner, owner_out, self.comm.rank, self.comm.world, adjoint)
+            ok = C.c_int(0)
+            check(lib.xb_dist_plan_pushable(plan.h, C.byref(ok)))
+            if ok.value:   # fused permute + exchange over peer memory: no buffers, no collective call
+                h = C.c_void_p()
+                check(lib.xb_dist_permute_push(ctx.h, plan.h, self.local.h, C.byref(h)))
+                dom, cod = plan.out_legs[:plan.out_rank], plan.out_legs[plan.out_rank:]
+                return ShardedTensor(ctx, self.comm, dom, cod, plan.owner_out, Tensor(ctx, h), layout_structure(ctx, dom, cod))
         plan = self._plan(shift, p, owner_out, adjoint)
         send, recv = plan._buffers
         stream = torch.cuda.ExternalStream(lib.xb_ctx_stream(ctx.h), device=torch.device("cuda", ctx.device))
@@ -244,6 +281,13 @@ class ShardedTensor:
         dom = self.codomain if adj_self else self.domain
         cod = other.domain if adj_other else other.codomain
         st = layout_structure(ctx, dom, cod)
+        if getattr(ctx, "_peer_memory", False) and not adj_self and not adj_other:
+            # row-panel balanced product: heavy sectors are cut into panels computed by other ranks (operands pulled, result panels pushed over NVLink)
+            own = (C.c_int * max(len(st[0]), 1))()
+            h = C.c_void_p()
+            check(ctx.lib.xb_dist_multiply(ctx.h, self.local.h, _ints(self.owner), other.local.h, _ints(other.owner), int(getattr(ctx, "_panel_rows_min", 256)),
+                                           C.byref(h), own, len(st[0])))
+            return ShardedTensor(ctx, self.comm, dom, cod, list(own[:len(st[0])]), Tensor(ctx, h), st)
         owner = [mine[q] if q in mine else theirs.get(q, i % self.comm.world) for i, q in enumerate(st[0])]
         my_q = [q for q, o in zip(st[0], owner) if o == self.comm.rank]
         flat = [x for q in my_q for x in q]

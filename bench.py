@@ -413,18 +413,17 @@ def kernel_sections(xb, device, torch, cpu_d6=False):
 
 def sharded_section(xb, torch, dist, local, world):
     """BASELINE.json configs[4]: the W4 contraction + permute sweep sharded by sector over the ranks.
-    Every rank owns whole sectors (LPT on flops); T*T is purely local, a permute has ONE exchange step (pack kernel -> NCCL
-    alltoallv over NVLink -> gather kernel).  Times are CUDA events on the context stream (which waits for the NCCL stream),
-    max over ranks; bytes / flops are those of the GLOBAL tensor."""
-    from xped_b200.sharded import Comm, ShardedTensor
+    Peer-memory form (csrc/dist.cu): every rank maps every other rank's device arena (CUDA IPC over NVLink / NVSwitch); a sharded permute is ONE
+    launch per rank that transposes the sub-blocks the rank owns straight into the output shard of the destination's owner (no buffers, no
+    collective), T*T is balanced by row panels of the heavy sectors (operands pulled, result panels stored over NVLink).  The pack -> NCCL
+    alltoallv -> gather form of the same permutes is timed beside it.  Times: CUDA events on the context stream, max over ranks; bytes / flops
+    are those of the GLOBAL tensor.  Parity: on a small tensor of the same structure every sharded result is compared with the unsharded one on
+    every rank inside this run (bit-exact permutes, products <= 1e-13)."""
+    import numpy as np
+    from xped_b200.sharded import Comm, ShardedTensor, enable_peer_memory
     ctx = xb.Context([("U1", 0, 0)], device=local)
     comm = Comm()
-    B = u1_basis(ctx, 4, 24)
-    T = ShardedTensor.zeros(ctx, comm, [B, B], [B, B]).setRandom(0)
-    nelem = T.plainSize()
-    mine = sum(T.rows[i] * T.cols[i] for i in T.my_sectors())
-    flops = sum(2.0 * r * c * c for r, c in zip(T.rows, T.cols))
-    my_flops = sum(2.0 * T.rows[i] * T.cols[i] * T.cols[i] for i in T.my_sectors())
+    perms = [(0, (1, 0, 2, 3)), (1, (2, 3, 0, 1)), (-1, (3, 2, 1, 0)), (0, (0, 2, 1, 3))]
 
     def timed(fn, reps):
         fn()                       # warm-up: plans, exchange buffers, NCCL channels
@@ -438,15 +437,75 @@ def sharded_section(xb, torch, dist, local, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- the NCCL form first (before the arena exists)
+    B = u1_basis(ctx, 4, 24)
+    T = ShardedTensor.zeros(ctx, comm, [B, B], [B, B]).setRandom(0)
+    nelem = T.plainSize()
+    flops = sum(2.0 * r * c * c for r, c in zip(T.rows, T.cols))
+    nccl = {"permutes": []}
+    for shift, p in perms:
+        ms = timed(lambda: T.permute(shift, p), 3)
+        nccl["permutes"].append({"p": list(p), "shift": shift, "ms": ms, "GBps_global": 16.0 * nelem / ms / 1e6})
+    ms = timed(lambda: T @ T, 2)
+    nccl["multiply"] = {"op": "T*T, whole sectors per rank (LPT on flops)", "ms": ms, "TFLOPs_global": flops / ms / 1e9}
+    del T
+    # ---- peer-memory form
+    enable_peer_memory(ctx, comm, 12 << 30)
+    parity = {}
+    Bs = u1_basis(ctx, 3, 6)
+    full = ctx.tensor([Bs, Bs], [Bs, Bs]).setRandom(5)
+    Ts = ShardedTensor.zeros(ctx, comm, [Bs, Bs], [Bs, Bs]).setRandom(5)
+    ok = True
+    for shift, p in perms + [(2, (0, 1, 3, 2))]:
+        ok = ok and np.array_equal(Ts.permute(shift, p).gather(), full.permute(shift, p).download())
+    parity["permutes_bit_exact"] = bool(ok)
+    ref = (full @ full).download()
+    worst = 0.0
+    for owner in (None, [0] * len(Ts.sectors)):     # the skewed owner map forces row panels onto the other ranks
+        ctx._panel_rows_min = 16
+        Tp = ShardedTensor.zeros(ctx, comm, [Bs, Bs], [Bs, Bs], owner=owner).setRandom(5)
+        worst = max(worst, float(np.linalg.norm((Tp @ Tp).gather() - ref) / np.linalg.norm(ref)))
+    ctx._panel_rows_min = 256
+    parity["multiply_rel_err"] = worst
+    flag = torch.tensor([0.0 if (ok and worst < 1e-13) else 1.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(flag)
+    parity["all_ranks_ok"] = bool(flag.item() == 0.0)
+    if not parity["all_ranks_ok"]:
+        raise AssertionError(f"sharded parity failed: {parity}")
+    del full, Ts, Tp
+    T = ShardedTensor.zeros(ctx, comm, [B, B], [B, B]).setRandom(0)
+    mine = sum(T.rows[i] * T.cols[i] for i in T.my_sectors())
+    my_flops = sum(2.0 * T.rows[i] * T.cols[i] * T.cols[i] for i in T.my_sectors())
     out = {"tensor": f"W4: U(1) Tensor<2,2>, leg q=-4..4 x 24, {nelem} elements, 17 sectors over {world} ranks (LPT on flops)",
-           "local_fraction_of_elements": mine / nelem, "local_fraction_of_flops": my_flops / flops, "permutes": []}
-    for shift, p in [(0, (1, 0, 2, 3)), (1, (2, 3, 0, 1)), (-1, (3, 2, 1, 0)), (0, (0, 2, 1, 3))]:
+           "form": "peer memory (CUDA IPC arenas over NVLink): fused permute + exchange launch, row-panel balanced product",
+           "local_fraction_of_elements": mine / nelem, "local_fraction_of_flops": my_flops / flops, "permutes": [], "parity": parity}
+    for shift, p in perms:
         ms = timed(lambda: T.permute(shift, p), 3)
         out["permutes"].append({"p": list(p), "shift": shift, "ms": ms, "GBps_global": 16.0 * nelem / ms / 1e6})
     ms = timed(lambda: T @ T, 2)
-    out["multiply"] = {"op": "T*T", "flops": flops, "ms": ms, "TFLOPs_global": flops / ms / 1e9}
+    out["multiply"] = {"op": "T*T, row panels of the heavy sectors spread over the ranks", "flops": flops, "ms": ms, "TFLOPs_global": flops / ms / 1e9}
     ms = timed(lambda: T.contract([-1, -2, 1, 2], T, [1, 2, -3, -4], 2), 2)
-    out["contract"] = {"op": "contract<{-1,-2,1,2},{1,2,-3,-4},2>(T, T): 3 sharded permutes + local product", "ms": ms}
+    out["contract"] = {"op": "contract<{-1,-2,1,2},{1,2,-3,-4},2>(T, T): 3 sharded permutes + sharded product", "ms": ms}
+    out["nccl_form"] = nccl
+    del T
+    # ---- the same operations unsharded on ONE GPU of this run (rank 0; the other ranks wait): the denominators of the scaling figures
+    if comm.rank == 0:
+        ctx1 = xb.Context([("U1", 0, 0)], device=local)
+        B1 = u1_basis(ctx1, 4, 24)
+        T1 = ctx1.tensor([B1, B1], [B1, B1]).setRandom(0)
+        one = {"permutes": []}
+        for shift, p in perms:
+            T1.bench_permute(shift, p, reps=2)
+            ms1, nbytes = T1.bench_permute(shift, p, reps=3)
+            one["permutes"].append({"p": list(p), "shift": shift, "ms": ms1, "GBps": nbytes / ms1 / 1e6})
+        ms1, fl1 = sorted(T1.bench_multiply(T1, reps=2) for _ in range(2))[0]
+        one["multiply"] = {"ms": ms1, "TFLOPs": fl1 / ms1 / 1e9}
+        del T1
+        ctx1.close()
+        out["one_gpu_same_run"] = one
+        out["speedup_vs_one_gpu"] = {"permutes": [a["ms"] / b["ms"] for a, b in zip(one["permutes"], out["permutes"])],
+                                     "multiply": one["multiply"]["ms"] / out["multiply"]["ms"]}
+    dist.barrier()
     ctx.close()
     return out
 
@@ -582,7 +641,7 @@ def run_b200(args):
         launches = int(lt.item())
 
     sharded = None
-    if world > 1 and not args.no_extras:
+    if world > 1 and (not args.no_extras or os.environ.get("XB_BENCH_SHARDED")):
         try:
             sharded = sharded_section(xb, torch, dist, local, world)
         except Exception as e:   # the headline line must survive a failure of the optional section

@@ -154,7 +154,7 @@ def _products(ctx, comm, osym, name):
     return worst
 
 
-def _nccl_worker(rank, world, port, out):
+def _nccl_worker(rank, world, port, out, peer=False):
     import sys
     import torch
     import torch.distributed as dist
@@ -162,7 +162,7 @@ def _nccl_worker(rank, world, port, out):
     for pth in (os.path.dirname(here), os.path.join(os.path.dirname(here), "oracle"), here):
         if pth not in sys.path:
             sys.path.insert(0, pth)
-    from xped_b200.sharded import Comm, ShardedTensor
+    from xped_b200.sharded import Comm, ShardedTensor, enable_peer_memory
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -173,6 +173,9 @@ def _nccl_worker(rank, world, port, out):
             ctx = xb.Context(spec, device=rank)
             osym = xo.Symmetry.from_spec(spec)
             comm = Comm()
+            if peer:   # CUDA IPC arenas: fused permute + exchange launches for the Abelian case, row-panel products; SU(2) plans (fan-in > 1) keep the NCCL form
+                enable_peer_memory(ctx, comm, 1 << 28, name=f"/xb2test_{port}_{name}")
+                ctx._panel_rows_min = 2
             dom, cod = [ctx.basis(e) for e in dom_e], [ctx.basis(e) for e in cod_e]
             ot = xo.Tensor(osym, [obasis(osym, e) for e in dom_e], [obasis(osym, e) for e in cod_e])
             from xped_oracle.rng import uniform_fill
@@ -205,6 +208,24 @@ def test_sharded_tensor_over_nccl_world2():
     out = ctxmp.Queue()
     port = _free_port()
     procs = [ctxmp.Process(target=_nccl_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    assert out.get(timeout=10) < 1e-12
+
+
+def test_sharded_tensor_peer_memory_world2():
+    """the same checks with the peer-memory form of the exchange (csrc/dist.cu): permutes bit-exact / 1e-12 vs the oracle, products incl. row panels"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctxmp = mp.get_context("spawn")
+    out = ctxmp.Queue()
+    port = _free_port()
+    procs = [ctxmp.Process(target=_nccl_worker, args=(r, 2, port, out, True)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

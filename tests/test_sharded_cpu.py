@@ -242,3 +242,49 @@ def test_recoupling_cache_across_multiplicities(name):
                 err = np.linalg.norm(full - ref.data) / max(np.linalg.norm(ref.data), 1e-300)
                 assert err < 1e-13, (name, bump, shift, p, adjoint, err)
     ctx.close()
+
+
+def test_push_plans_exist_exactly_for_fan_in_one():
+    """the direct-write form of the exchange (xb_dist_permute_push) needs every destination sub-block to have one source: Abelian plans qualify, SU(2)
+    plans with recoupling sums do not (they keep the pack / alltoallv / gather form)"""
+    import ctypes as C
+    from xped_b200.sharded import PermuteExchangePlan, PlanningContext, default_owner, layout_structure
+    for name, entries, shift, p, want in [("U1", [(-1, 2), (0, 3), (1, 2)], 1, (2, 0, 3, 1), 1), ("SU2", [(1, 2), (2, 2), (3, 1)], 1, (2, 0, 3, 1), 0),
+                                          ("SU2", [(1, 2), (2, 2), (3, 1)], 0, (1, 0, 2, 3), 1)]:
+        ctx = PlanningContext(SPECS[name])
+        B = ctx.basis(entries)
+        st = layout_structure(ctx, [B, B], [B, B])
+        owner = default_owner(ctx, st[1], st[2], 3)
+        for rank in range(3):
+            plan = PermuteExchangePlan(ctx, [B, B], [B, B], shift, p, owner, None, rank, 3)
+            ok = C.c_int(-1)
+            assert ctx.lib.xb_dist_plan_pushable(plan.h, C.byref(ok)) == 0
+            assert ok.value == want, (name, shift, p)
+        ctx.close()
+
+
+def test_row_panel_assignment_covers_and_balances():
+    """xb_dist_multiply_assignment: every row of every sector exactly once, panels start on multiples of the minimal panel, the heaviest rank within a few
+    percent of the mean even when one sector alone exceeds a rank's share (W4 over 8 ranks: whole-sector LPT reaches 0.54)"""
+    from xped_b200.sharded import PlanningContext, multiply_panel_assignment, owner_lpt
+    ctx = PlanningContext(SPECS["U1"])
+    side = [(9 - abs(q)) * 576 for q in range(-8, 9)]
+    for world in (1, 2, 3, 4, 8):
+        own = owner_lpt(ctx, [float(x) ** 3 for x in side], world)
+        panels = multiply_panel_assignment(ctx, side, side, side, own, world, 256)
+        cover, load = {}, [0.0] * world
+        for s, r, r0, rows in panels:
+            assert 0 <= r < world and rows > 0 and r0 % 256 == 0
+            cover.setdefault(s, []).append((r0, rows))
+            load[r] += 2.0 * rows * side[s] * side[s]
+        for s, m in enumerate(side):
+            pos = 0
+            for r0, rows in sorted(cover[s]):
+                assert r0 == pos
+                pos += rows
+            assert pos == m
+        assert max(load) <= 1.12 * sum(load) / world, (world, load)
+    # a skewed owner map: everything on rank 0 -> the others take panels
+    panels = multiply_panel_assignment(ctx, side, side, side, [0] * len(side), 4, 256)
+    assert {r for _, r, _, _ in panels} == {0, 1, 2, 3}
+    ctx.close()

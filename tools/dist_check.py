@@ -81,6 +81,20 @@ def timing(dim):
             rows.setdefault((shift, p), {})[mode] = (ms, 16.0 * nelem / ms / 1e6)
         ms = timed(lambda: T @ T, 2)
         rows.setdefault("T*T", {})[mode] = (ms, flops / ms / 1e9)
+        if mode == "peer":
+            for mbps in (150000, 300000, 1200000, 10**9):
+                ctx.set_int("dist.pull_mbps", mbps)
+                T @ T; ctx.sync(); dist.barrier()
+                ctx.timer_start()
+                for _ in range(2):
+                    T @ T
+                mine = ctx.timer_stop() / 2
+                t = torch.tensor([mine], dtype=torch.float64, device="cuda")
+                box = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(box, t)
+                per = [round(float(b.item()), 2) for b in box]
+                log(f"T*T pull_mbps {mbps}: per-rank ms {per} -> {flops / max(per) / 1e9:.1f} TFLOP/s")
+            ctx.set_int("dist.pull_mbps", 600000)
         del T
     for k, v in rows.items():
         log(k, {m: (round(a, 3), round(b, 1)) for m, (a, b) in v.items()})

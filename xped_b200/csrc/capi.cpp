@@ -132,6 +132,8 @@ int xb_ctx_set_int(xb_ctx* ctx, const char* key, int64_t value)
             ctx->impl.opt_svd_truncated = value < 0 ? -1 : (value != 0 ? 1 : 0);
         else if(k == "svd.call_tag")
             ctx->impl.svd_call_tag = static_cast<int>(value);
+        else if(k == "dist.pull_mbps")
+            dist_pull_mbps = std::max<int64_t>(value, 1);
         else
             throw std::invalid_argument("xb_ctx_set_int: unknown key '" + k + "'");
     });
@@ -148,6 +150,8 @@ int xb_ctx_get_int(const xb_ctx* ctx, const char* key, int64_t* value)
             *value = ctx->impl.opt_svd_truncated;
         else if(k == "svd.call_tag")
             *value = ctx->impl.svd_call_tag;
+        else if(k == "dist.pull_mbps")
+            *value = dist_pull_mbps;
         else if(k == "svd.truncated_calls")
             *value = ctx->impl.svd_truncated_calls;
         else if(k == "svd.truncated_fallbacks")

@@ -101,6 +101,7 @@ struct DistState
     std::map<int64_t, int64_t> free_list;   // offset -> bytes
     std::map<int64_t, int64_t> used;
     int64_t high_water = 0;
+    cudaStream_t side[DIST_MAX_WORLD] = {};
 };
 
 void dist_shm_create(const char* name, int world)
@@ -206,6 +207,8 @@ void dist_shutdown(Context& ctx)
         for(int q = 0; q < D->world; ++q)
             if(q != D->rank && D->peer[q]) cudaIpcCloseMemHandle(D->peer[q]);
     }
+    for(cudaStream_t st : D->side)
+        if(st) cudaStreamDestroy(st);
     if(D->arena) cudaFree(D->arena);
     if(D->shm) munmap(D->shm, sizeof(DistShm));
     if(D->rank == 0) shm_unlink(D->shm_name.c_str());
@@ -289,6 +292,14 @@ void dist_exchange(Context& ctx, const int64_t mine[DIST_SLOT_WORDS], int64_t al
         for(int w = 0; w < DIST_SLOT_WORDS; ++w) all[q][w] = s->slot[q][k % RING][w];
     }
     D->opseq = k + 1;
+}
+
+cudaStream_t dist_side_stream(Context& ctx, int i)
+{
+    DistState* D = ctx.dist;
+    if(!D || i < 0 || i >= DIST_MAX_WORLD) throw std::invalid_argument("dist_side_stream: bad index");
+    if(!D->side[i]) check_cuda(cudaStreamCreateWithFlags(&D->side[i], cudaStreamNonBlocking), "cudaStreamCreate(side)");
+    return D->side[i];
 }
 
 void dist_barrier(Context& ctx)

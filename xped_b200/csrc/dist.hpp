@@ -3,6 +3,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include <cuda_runtime.h>
+
 namespace xb {
 
 class Context;
@@ -20,6 +22,8 @@ void arena_free(Context& ctx, int64_t off);
 void dist_arena_stats(const Context& ctx, int64_t out[3]);   // arena bytes, bytes in use, high-water mark
 double* dist_peer_ptr(const Context& ctx, int peer, int64_t off);
 void dist_exchange(Context& ctx, const int64_t mine[DIST_SLOT_WORDS], int64_t all[DIST_MAX_WORLD][DIST_SLOT_WORDS]);
-void dist_barrier(Context& ctx);   // stream-ordered barrier over all ranks
+extern int64_t dist_pull_mbps;
+void dist_barrier(Context& ctx);
+cudaStream_t dist_side_stream(Context& ctx, int i);   // one of world - 1 non-blocking side streams (created on first use)   // stream-ordered barrier over all ranks
 
 }   // namespace xb

@@ -44,12 +44,13 @@ Tensor* Context::dist_permute_push(const DistPermutePlan& plan, const Tensor& lo
     dist_exchange(*this, mine, all);
     ProfScope prof(*this, CAT_PERMUTE, static_cast<double>(plan.bytes_local));
     dist_barrier(*this);   // A: every output shard is allocated (and zeroed where needed); what lived there before is no longer in use by its owner
-    for(int k = 0; k < plan.world; ++k) {
-        const int p = (plan.rank + k) % plan.world;   // start with the local part, then round the peers (staggered targets across ranks)
-        const PermutePlan& pp = *plan.push[p];
-        if(pp.n_tiles == 0) continue;
-        double* dst = p == plan.rank ? out->d : dist_peer_ptr(*this, p, all[p][0]);
-        launch_permute(local_in.d, dst, pp, stream);
+    // ONE launch: every tile is transposed in shared memory and leaves for the shard of its destination's owner (this rank's or a peer's, over NVLink)
+    PeerDelta delta;
+    for(int p = 0; p < 8; ++p) delta.d[p] = 0;
+    for(int p = 0; p < plan.world; ++p)
+        if(p != plan.rank) delta.d[p] = dist_peer_ptr(*this, p, all[p][0]) - out->d;
+    if(plan.push[0]->n_tiles > 0) {
+        launch_permute_peers(local_in.d, out->d, *plan.push[0], delta, stream);
         ++launches;
     }
     dist_barrier(*this);   // B: all peers have finished storing into this rank's shard
@@ -57,50 +58,77 @@ Tensor* Context::dist_permute_push(const DistPermutePlan& plan, const Tensor& lo
 }
 
 // ------------------------------------------------------------------------------------------------ row-panel product
+int64_t dist_pull_mbps = 600000;   // modelled rate of pulling operand panels from a peer (MB/s; xb_ctx_set_int "dist.pull_mbps"): weighs transfers against flops
 std::vector<DistPanel> dist_multiply_assignment(const std::vector<int64_t>& m, const std::vector<int64_t>& n, const std::vector<int64_t>& k, const std::vector<int>& owner,
                                                 int world, int panel_rows_min, double imbalance_tol)
 {
-    // deterministic: every rank computes the same list.  Sectors in descending flops; a sector stays whole on its owner while the owner has room
-    // (load <= mean * (1 + tol)); otherwise it is cut into row panels (multiples of `panel_rows_min` rows) that fill the least-loaded ranks up to the mean.
+    // deterministic: every rank computes the same list.  Loads are TIMES (ms): product flops at the grouped-GEMM rate plus, for a panel computed away from
+    // its owner, the pull of the A panel and (once per rank and sector) of B_q at the peer-copy rate.  Sectors in descending flops; a sector stays whole on
+    // its owner while the owner has room (load <= cap); otherwise it is cut into row panels (multiples of `panel_rows_min` rows) that fill the
+    // least-loaded ranks up to the cap; the cap itself is the smallest one the greedy can honour (bisection).
+    const double GEMM_FLOP_PER_MS = 29.0e9, PULL_BYTES_PER_MS = 1.0e3 * static_cast<double>(dist_pull_mbps);
     const int ns = static_cast<int>(m.size());
     std::vector<double> fl(ns);
     double total = 0.0;
     for(int i = 0; i < ns; ++i) {
-        fl[i] = 2.0 * static_cast<double>(m[i]) * static_cast<double>(n[i]) * static_cast<double>(k[i]);
+        fl[i] = 2.0 * static_cast<double>(m[i]) * static_cast<double>(n[i]) * static_cast<double>(k[i]) / GEMM_FLOP_PER_MS;
         total += fl[i];
     }
-    const double mean = total / world, cap = mean * (1.0 + imbalance_tol);
     std::vector<int> order(ns);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return fl[a] > fl[b]; });
-    std::vector<double> load(world, 0.0);
-    std::vector<DistPanel> out;
-    for(int s : order) {
-        if(m[s] == 0 || n[s] == 0) continue;
-        const double per_row = fl[s] / static_cast<double>(m[s]);
-        int64_t r0 = 0;
-        while(r0 < m[s]) {
-            const int64_t left = m[s] - r0;
-            // first choice: the owner (no transfer); else the least-loaded rank
-            int r = owner[s];
-            if(load[r] + per_row * std::min<int64_t>(left, panel_rows_min) > cap) {
-                r = 0;
-                for(int q = 1; q < world; ++q)
-                    if(load[q] < load[r]) r = q;
+    auto greedy = [&](double cap, std::vector<DistPanel>& out) {
+        out.clear();
+        std::vector<double> load(world, 0.0);
+        std::vector<char> has_b(static_cast<size_t>(world) * ns, 0);
+        for(int s : order) {
+            if(m[s] == 0 || n[s] == 0) continue;
+            const double comp_row = fl[s] / static_cast<double>(m[s]);
+            const double pull_row = 8.0 * static_cast<double>(k[s]) / PULL_BYTES_PER_MS, pull_b = 8.0 * static_cast<double>(k[s]) * static_cast<double>(n[s]) / PULL_BYTES_PER_MS;
+            int64_t r0 = 0;
+            while(r0 < m[s]) {
+                const int64_t left = m[s] - r0;
+                int r = owner[s];   // first choice: the owner (no transfer); else the least-loaded rank
+                if(load[r] + comp_row * static_cast<double>(std::min<int64_t>(left, panel_rows_min)) > cap) {
+                    r = 0;
+                    for(int q = 1; q < world; ++q)
+                        if(load[q] < load[r]) r = q;
+                }
+                const bool away = r != owner[s];
+                const double fixed = (away && !has_b[static_cast<size_t>(r) * ns + s]) ? pull_b : 0.0, per_row = comp_row + (away ? pull_row : 0.0);
+                int64_t rows = left;
+                const double room = cap - load[r] - fixed;
+                if(per_row * static_cast<double>(left) > room) {
+                    rows = room > 0.0 ? static_cast<int64_t>(room / per_row) / panel_rows_min * panel_rows_min : 0;
+                    if(rows < panel_rows_min) rows = std::min<int64_t>(left, panel_rows_min);   // everybody is full: overshoot by one minimal panel
+                    if(left - rows < panel_rows_min / 2) rows = left;                           // no sliver at the end
+                }
+                if(away) has_b[static_cast<size_t>(r) * ns + s] = 1;
+                out.push_back({s, r, r0, rows});
+                load[r] += fixed + per_row * static_cast<double>(rows);
+                r0 += rows;
             }
-            int64_t rows = left;
-            const double room = cap - load[r];
-            if(per_row * static_cast<double>(left) > room) {
-                rows = static_cast<int64_t>(room / per_row) / panel_rows_min * panel_rows_min;
-                if(rows < panel_rows_min) rows = std::min<int64_t>(left, panel_rows_min);   // everybody is full: overshoot by one minimal panel
-                if(left - rows < panel_rows_min / 2) rows = left;                           // no sliver at the end
+        }
+        double worst = 0.0;
+        for(double l : load) worst = std::max(worst, l);
+        return worst;
+    };
+    // smallest cap the greedy can honour (a larger one leaves the last ranks short): bisection between the transfer-free mean and twice that
+    std::vector<DistPanel> best, trial;
+    double lo = total / world, hi = 2.0 * lo + 1e-12, best_worst = greedy(hi, best);
+    for(int it = 0; it < 24 && hi - lo > imbalance_tol * 0.25 * lo; ++it) {
+        const double mid = 0.5 * (lo + hi), w = greedy(mid, trial);
+        if(w <= mid * (1.0 + 1e-9)) {
+            hi = mid;
+            if(w <= best_worst) {
+                best_worst = w;
+                best.swap(trial);
             }
-            out.push_back({s, r, r0, rows});
-            load[r] += per_row * static_cast<double>(rows);
-            r0 += rows;
+        } else {
+            lo = mid;
         }
     }
-    return out;
+    return best;
 }
 
 Tensor* Context::dist_multiply(const Tensor& a, const std::vector<int>& owner_a, const Tensor& b, const std::vector<int>& owner_b, int panel_rows_min,
@@ -180,11 +208,13 @@ Tensor* Context::dist_multiply(const Tensor& a, const std::vector<int>& owner_a,
     dist_exchange(*this, mine, all);
     dist_barrier(*this);   // A: operands of every rank are complete, outputs allocated and zeroed
 
-    // ---- stage what this rank computes but does not own, then ONE grouped product over local and staged panels
-    std::vector<GemmItem> items;
+    // ---- what this rank computes but does not own is pulled on a side stream while the panels of its own sectors run; then the staged panels
+    std::vector<GemmItem> items_own, items_staged;
     std::vector<double*> stage;
     std::vector<int> staged_b(no, -1);   // index into `stage` of the copy of B_q
-    double flops_mine = 0.0;
+    cudaStream_t side = nullptr;
+    struct Pull { double* dst; const double* src; int64_t rows, ld, cols; };
+    std::vector<Pull> pulls;
     for(const DistPanel& p : panels) {
         if(p.rank != rank) continue;
         const int o = p.sector, ow = own_o[o];
@@ -196,40 +226,57 @@ Tensor* Context::dist_multiply(const Tensor& a, const std::vector<int>& owner_a,
         g.k = static_cast<int>(k);
         g.alpha = 1.0;
         g.ldc = static_cast<int>(m);
-        flops_mine += 2.0 * p.rows * static_cast<double>(n) * k;
         if(ow == rank) {
             g.a_off = offa[ia[o]] + p.row0;
             g.lda = static_cast<int>(m);
             g.b_off = offb[ib[o]];
             g.ldb = static_cast<int>(k);
             g.c_off = offo[o] + p.row0;
-        } else {
-            double* sa = nullptr;
-            check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&sa), sizeof(double) * static_cast<size_t>(p.rows) * k, stream), "cudaMallocAsync(panel staging)");
-            stage.push_back(sa);
-            const double* pa = dist_peer_ptr(*this, ow, all[ow][0]) + offa[ia[o]] + p.row0;
-            check_cuda(cudaMemcpy2DAsync(sa, sizeof(double) * p.rows, pa, sizeof(double) * m, sizeof(double) * p.rows, static_cast<size_t>(k), cudaMemcpyDeviceToDevice, stream),
-                       "cudaMemcpy2DAsync(A panel from its owner)");
-            if(staged_b[o] < 0) {
-                double* sb = nullptr;
-                check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&sb), sizeof(double) * static_cast<size_t>(k) * n, stream), "cudaMallocAsync(B staging)");
-                staged_b[o] = static_cast<int>(stage.size());
-                stage.push_back(sb);
-                const double* pb = dist_peer_ptr(*this, ow, all[ow][1]) + offb[ib[o]];
-                check_cuda(cudaMemcpyAsync(sb, pb, sizeof(double) * static_cast<size_t>(k) * n, cudaMemcpyDeviceToDevice, stream), "cudaMemcpyAsync(B block from its owner)");
-            }
-            g.a_off = sa - A->d;
-            g.lda = static_cast<int>(p.rows);
-            g.b_off = stage[staged_b[o]] - B->d;
-            g.ldb = static_cast<int>(k);
-            g.c_off = (dist_peer_ptr(*this, ow, all[ow][2]) + offo[o] + p.row0) - out->d;
+            items_own.push_back(g);
+            continue;
         }
-        items.push_back(g);
+        // staging memory comes from the stream-ordered pool of the context stream; the copies are issued on the side stream after a fork event that
+        // follows all allocations, and the memory is released on the context stream after the join
+        double* sa = nullptr;
+        check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&sa), sizeof(double) * static_cast<size_t>(p.rows) * k, stream), "cudaMallocAsync(panel staging)");
+        stage.push_back(sa);
+        const double* pa = dist_peer_ptr(*this, ow, all[ow][0]) + offa[ia[o]] + p.row0;
+        pulls.push_back({sa, pa, p.rows, m, k});
+        if(staged_b[o] < 0) {
+            double* sb = nullptr;
+            check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&sb), sizeof(double) * static_cast<size_t>(k) * n, stream), "cudaMallocAsync(B staging)");
+            staged_b[o] = static_cast<int>(stage.size());
+            stage.push_back(sb);
+            const double* pb = dist_peer_ptr(*this, ow, all[ow][1]) + offb[ib[o]];
+            pulls.push_back({sb, pb, k * n, k * n, 1});
+        }
+        g.a_off = sa - A->d;
+        g.lda = static_cast<int>(p.rows);
+        g.b_off = stage[staged_b[o]] - B->d;
+        g.ldb = static_cast<int>(k);
+        g.c_off = (dist_peer_ptr(*this, ow, all[ow][2]) + offo[o] + p.row0) - out->d;
+        items_staged.push_back(g);
     }
-    run_gemm(A->d, B->d, out->d, items);
+    if(!pulls.empty()) {
+        side = dist_side_stream(*this, 0);
+        cudaEvent_t fork = get_event();
+        check_cuda(cudaEventRecord(fork, stream), "cudaEventRecord(fork)");
+        check_cuda(cudaStreamWaitEvent(side, fork, 0), "cudaStreamWaitEvent(fork)");
+        event_pool.push_back(fork);
+        for(const Pull& c : pulls)   // column-major panel: `cols` runs of `rows` doubles, source pitch `ld`
+            check_cuda(cudaMemcpy2DAsync(c.dst, sizeof(double) * c.rows, c.src, sizeof(double) * c.ld, sizeof(double) * c.rows, static_cast<size_t>(c.cols), cudaMemcpyDeviceToDevice, side),
+                       "cudaMemcpy2DAsync(panel from its owner)");
+    }
+    if(!items_own.empty()) run_gemm(A->d, B->d, out->d, items_own);
+    if(side) {
+        cudaEvent_t join = get_event();
+        check_cuda(cudaEventRecord(join, side), "cudaEventRecord(join)");
+        check_cuda(cudaStreamWaitEvent(stream, join, 0), "cudaStreamWaitEvent(join)");
+        event_pool.push_back(join);
+        run_gemm(A->d, B->d, out->d, items_staged);
+    }
     for(double* s : stage) check_cuda(cudaFreeAsync(s, stream), "cudaFreeAsync(staging)");
     dist_barrier(*this);   // B: every panel of this rank's sectors has arrived; operands may be released
-    (void)flops_mine;
     return guard_out.release();
 }
 

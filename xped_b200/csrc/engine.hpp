@@ -43,6 +43,10 @@ constexpr int PERM_BUF_ELEMS = 3072;    // shared buffer incl. bank-conflict pad
 constexpr int PERM_THREADS = 256;
 constexpr int PERM_STRIP = 8;   // longest per-thread strip
 
+constexpr int PERM_PEER_SHIFT = 56;   // dst_off = (owner rank of the destination shard << 56) | element offset inside that shard
+constexpr long long PERM_OFF_MASK = (1ll << PERM_PEER_SHIFT) - 1;
+struct PeerDelta { long long d[8]; };   // element offset of every rank's destination shard relative to the launch's `dst` pointer
+
 struct PermTask   // one destination sub-block (target tree pair) = sum_k coeff_k * transpose(src_k)
 {
     long long dst_off;
@@ -401,6 +405,9 @@ struct ProfScope
 
 // ---- kernel launchers (kernels.cu) ----
 void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s);
+// pushed permute over peer memory: destination offsets of the plan carry the owner rank of the destination shard in their top byte (PERM_PEER_SHIFT); the
+// element offset of rank p's shard relative to `dst` is delta.d[p] (0 for this rank)
+void launch_permute_peers(const double* src, double* dst, const PermutePlan& plan, const PeerDelta& delta, cudaStream_t s);
 // sources with offset >= split are read from src2 + (offset - split): sharded permute reading [local shard | receive buffer]
 void launch_permute2(const double* src, const double* src2, long long split, double* dst, const PermutePlan& plan, cudaStream_t s);
 // deterministic LPT greedy (largest cost first, ties by index, least-loaded rank, ties lowest rank)

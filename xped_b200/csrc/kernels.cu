@@ -98,7 +98,8 @@ __device__ __forceinline__ void perm_read(const PermTask& T, const int* __restri
 // order) -> barrier -> write phase (destination order) -> barrier.
 __global__ void __launch_bounds__(PERM_THREADS, 4)
 permute_kernel(const double* __restrict__ src, const double* __restrict__ src2, long long split, double* __restrict__ dst,
-               const PermTask* __restrict__ tasks, const PermSrc* __restrict__ srcs, const PermTile* __restrict__ tiles, int n_tiles, int tiles_per_cta)
+               const PermTask* __restrict__ tasks, const PermSrc* __restrict__ srcs, const PermTile* __restrict__ tiles, int n_tiles, int tiles_per_cta,
+               const PeerDelta delta)
 {
     __shared__ PermTask T;
     __shared__ PermSrc S;
@@ -162,7 +163,7 @@ permute_kernel(const double* __restrict__ src, const double* __restrict__ src2, 
         __syncthreads();
 
         // ---- write phase: destination order (lanes along the destination-contiguous leg); every element written once
-        long long dbase = T.dst_off;
+        long long dbase = (T.dst_off & PERM_OFF_MASK) + delta.d[T.dst_off >> PERM_PEER_SHIFT];   // destination shard of this or of a peer rank
         for(int l = 0; l < T.nleg; ++l) dbase += static_cast<long long>(s_base[l]) * T.dstride[l];
         double* __restrict__ dp = dst + dbase;
         const bool zero = T.src_count == 0;
@@ -225,7 +226,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 constexpr int BULK_MAX_TILES_PER_CTA = 32;
 __global__ void __launch_bounds__(BULK_THREADS, 5)
 permute_bulk_kernel(const double* __restrict__ src, double* __restrict__ dst, const BulkTask* __restrict__ tasks, const PermTile* __restrict__ tiles,
-                    const int2* __restrict__ ranges)
+                    const int2* __restrict__ ranges, const PeerDelta delta)
 {
     __shared__ __align__(128) double bufA[BULK_BUF_ELEMS];
     __shared__ __align__(128) double bufB[BULK_BUF_ELEMS];
@@ -316,7 +317,7 @@ permute_bulk_kernel(const double* __restrict__ src, double* __restrict__ dst, co
 
     auto origin = [&](int i, bool is_load) {
         const PermTile& tile = s_tiles[i];
-        long long o = is_load ? T.src_off : T.dst_off;
+        long long o = is_load ? T.src_off : (T.dst_off & PERM_OFF_MASK) + delta.d[T.dst_off >> PERM_PEER_SHIFT];
         const int* __restrict__ gs = is_load ? T.sstride : T.dstride;
         for(int l = 0; l < T.nleg; ++l) o += static_cast<long long>(tile.c[l] * T.w[l]) * gs[l];
         return o;
@@ -389,27 +390,37 @@ permute_bulk_kernel(const double* __restrict__ src, double* __restrict__ dst, co
     asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // all stores complete before the shared memory is released
 }
 
-void launch_permute2(const double* src, const double* src2, long long split, double* dst, const PermutePlan& plan, cudaStream_t s)
+static const PeerDelta NO_PEERS = {{0, 0, 0, 0, 0, 0, 0, 0}};
+
+static void launch_permute2_peers(const double* src, const double* src2, long long split, double* dst, const PermutePlan& plan, const PeerDelta& delta, cudaStream_t s)
 {
     if(plan.n_tiles == 0) return;
     const int tpc = plan.tiles_per_cta < 1 ? 1 : plan.tiles_per_cta;
     const int grid = (plan.n_tiles + tpc - 1) / tpc;
-    permute_kernel<<<grid, PERM_THREADS, 0, s>>>(src, src2, split, dst, plan.d_tasks, plan.d_srcs, plan.d_tiles, plan.n_tiles, tpc);
+    permute_kernel<<<grid, PERM_THREADS, 0, s>>>(src, src2, split, dst, plan.d_tasks, plan.d_srcs, plan.d_tiles, plan.n_tiles, tpc, delta);
     check_cuda(cudaGetLastError(), "permute_kernel launch");
 }
 
-void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s)
+void launch_permute2(const double* src, const double* src2, long long split, double* dst, const PermutePlan& plan, cudaStream_t s)
+{
+    launch_permute2_peers(src, src2, split, dst, plan, NO_PEERS, s);
+}
+
+void launch_permute(const double* src, double* dst, const PermutePlan& plan, cudaStream_t s) { launch_permute_peers(src, dst, plan, NO_PEERS, s); }
+
+void launch_permute_peers(const double* src, double* dst, const PermutePlan& plan, const PeerDelta& delta, cudaStream_t s)
 {
     // bulk-copy form for bandwidth-bound sizes (XB_PERMUTE_BULK=0 / 1 forces never / whenever the plan qualifies)
     const char* bulk_env = std::getenv("XB_PERMUTE_BULK");   // read per call so that tests can toggle it
     const int bulk_mode = bulk_env ? std::atoi(bulk_env) : -1;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+    bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+    for(long long d : delta.d) aligned = aligned && (d & 1) == 0;   // peer shards: 16-byte aligned relative to dst
     if(plan.d_btasks && aligned && bulk_mode != 0 && (bulk_mode == 1 || plan.bytes >= (8ll << 20))) {
-        permute_bulk_kernel<<<plan.n_branges, BULK_THREADS, 0, s>>>(src, dst, plan.d_btasks, plan.d_btiles, plan.d_branges);
+        permute_bulk_kernel<<<plan.n_branges, BULK_THREADS, 0, s>>>(src, dst, plan.d_btasks, plan.d_btiles, plan.d_branges, delta);
         check_cuda(cudaGetLastError(), "permute_bulk_kernel launch");
         return;
     }
-    launch_permute2(src, src, INT64_MAX, dst, plan, s);
+    launch_permute2_peers(src, src, INT64_MAX, dst, plan, delta, s);
 }
 
 // ================================================================================================ elementwise

@@ -392,6 +392,7 @@ struct DstTask
 {
     SubBlock dst;
     std::vector<Contribution> srcs;
+    int peer = 0;   // pushed permutes: owner rank of the shard `dst` addresses (0 otherwise)
 };
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -716,7 +717,7 @@ static bool lower_bulk_task(const PermTask& T, std::vector<BulkTask>& btasks, st
         if(T.src0_stride[j] == 1) ls = j;
     if(ls < 0) return false;
     auto even = [](long long v) { return (v & 1) == 0; };
-    if(!even(T.dst_off) || !even(T.src0_off) || !even(T.dims[0]) || !even(T.dims[ls])) return false;
+    if(!even(T.dst_off & PERM_OFF_MASK) || !even(T.src0_off) || !even(T.dims[0]) || !even(T.dims[ls])) return false;
     for(int j = 0; j < n; ++j) {
         if(j != 0 && !even(T.dstride[j])) return false;
         if(j != ls && !even(T.src0_stride[j])) return false;
@@ -905,7 +906,7 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
         if(n > PERM_MAXLEG) throw std::length_error("permute plan: more than 8 non-fusable legs");
         PermTask T;
         std::memset(&T, 0, sizeof(T));
-        T.dst_off = t.dst.base;
+        T.dst_off = t.dst.base | (static_cast<long long>(t.peer) << PERM_PEER_SHIFT);
         T.nleg = n;
         T.src_begin = static_cast<int>(h_srcs.size());
         T.src_count = static_cast<int>(t.srcs.size());
@@ -1202,6 +1203,7 @@ std::shared_ptr<DistPermutePlan> Context::dist_permute_plan(const LayoutPtr& in,
         std::vector<LayoutPtr> out_shard(world);
         std::vector<std::vector<int>> loc_of(world);
         for(int p = 0; p < world; ++p) out_shard[p] = shard_of(out, P.owner_out, p, loc_of[p]);
+        // ONE launch for all destinations: tasks for the peers first (NVLink-bound: start the wire early), staggered across ranks, the local ones last
         std::vector<std::vector<DstTask>> push_tasks(world);
         std::vector<int64_t> push_elems(world, 0);
         for(const DstTask& g : ts.tasks) {
@@ -1214,15 +1216,21 @@ std::shared_ptr<DistPermutePlan> Context::dist_permute_plan(const LayoutPtr& in,
             DstTask t;
             t.dst = localise(g.dst, out_shard[rd], loc_of[rd]);
             t.srcs.push_back({localise(g.srcs[0].src, P.in_local, loc_in), g.srcs[0].coeff});
+            t.peer = rd;
             push_elems[rd] += t.dst.count();
             push_tasks[rd].push_back(std::move(t));
         }
-        P.push.resize(world);
-        for(int p = 0; p < world; ++p) {
-            P.push[p] = std::make_unique<PermutePlan>();
-            lower_tasks(*this, push_tasks[p], ts.leg_of, ts.N, *P.push[p]);
-            P.push[p]->bytes = 16 * push_elems[p];
+        std::vector<DstTask> all_tasks;
+        int64_t all_elems = 0;
+        for(int k = 1; k <= world; ++k) {
+            const int p = (rank + k) % world;   // ... rank + 1, rank + 2, ..., rank itself last
+            all_elems += push_elems[p];
+            for(DstTask& t : push_tasks[p]) all_tasks.push_back(std::move(t));
         }
+        P.push.resize(1);
+        P.push[0] = std::make_unique<PermutePlan>();
+        lower_tasks(*this, all_tasks, ts.leg_of, ts.N, *P.push[0]);
+        P.push[0]->bytes = 16 * all_elems;
     }
     if(dist_plan_cache_.size() >= 512) dist_plan_cache_.clear();   // plans own device tables; callers hold shared_ptr copies while they run
     dist_plan_cache_.emplace(key, plan);

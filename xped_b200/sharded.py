@@ -228,14 +228,25 @@ class ShardedTensor:
         import torch
         ctx, lib = self.ctx, self.ctx.lib
         if getattr(ctx, "_peer_memory", False):
-            plan = PermuteExchangePlan(ctx, self.domain, self.codomain, shift, p, self.owner, owner_out, self.comm.rank, self.comm.world, adjoint)
-            ok = C.c_int(0)
-            check(lib.xb_dist_plan_pushable(plan.h, C.byref(ok)))
-            if ok.value:   # fused permute + exchange over peer memory: no buffers, no collective call
+            # host-side plan record cached per (bases, permutation, owner maps): the launches of a pushed permute take ~0.1-0.5 ms, python must not add to that
+            key = (tuple(b.h.value for b in self.domain), tuple(b.h.value for b in self.codomain), int(shift), tuple(p), tuple(self.owner),
+                   None if owner_out is None else tuple(owner_out), bool(adjoint))
+            cache = ctx.__dict__.setdefault("_push_plans", {})
+            ent = cache.get(key)
+            if ent is None:
+                plan = PermuteExchangePlan(ctx, self.domain, self.codomain, shift, p, self.owner, owner_out, self.comm.rank, self.comm.world, adjoint)
+                ok = C.c_int(0)
+                check(lib.xb_dist_plan_pushable(plan.h, C.byref(ok)))
+                dom, cod = plan.out_legs[:plan.out_rank], plan.out_legs[plan.out_rank:]
+                ent = (plan, bool(ok.value), dom, cod, layout_structure(ctx, dom, cod), (self.domain, self.codomain))   # (keeps the keyed bases alive)
+                if len(cache) >= 256:
+                    cache.clear()
+                cache[key] = ent
+            plan, pushable, dom, cod, st, _ = ent
+            if pushable:   # fused permute + exchange over peer memory: no buffers, no collective call
                 h = C.c_void_p()
                 check(lib.xb_dist_permute_push(ctx.h, plan.h, self.local.h, C.byref(h)))
-                dom, cod = plan.out_legs[:plan.out_rank], plan.out_legs[plan.out_rank:]
-                return ShardedTensor(ctx, self.comm, dom, cod, plan.owner_out, Tensor(ctx, h), layout_structure(ctx, dom, cod))
+                return ShardedTensor(ctx, self.comm, dom, cod, plan.owner_out, Tensor(ctx, h), st)
         plan = self._plan(shift, p, owner_out, adjoint)
         send, recv = plan._buffers
         stream = torch.cuda.ExternalStream(lib.xb_ctx_stream(ctx.h), device=torch.device("cuda", ctx.device))

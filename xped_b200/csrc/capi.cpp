@@ -775,6 +775,22 @@ int xb_permute_plan_stats(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_bas
     });
 }
 
+int xb_permute_plan_census(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n, int64_t out[4])
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(out, "out");
+        std::vector<BasisPtr> d, c;
+        collect_bases(domain, rank, codomain, corank, d, c);
+        LayoutPtr L = ctx->impl.layout(d, c);
+        auto plan = ctx->impl.permute_plan(L, shift, std::vector<int>(p, p + n), false);
+        out[0] = plan->dst_elems;
+        out[1] = plan->src_reads;
+        out[2] = plan->n_tasks;
+        out[3] = plan->n_srcs;
+    });
+}
+
 int xb_tensor_create_sectors(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, const int* q, int n_sectors,
                              xb_tensor** out)
 {

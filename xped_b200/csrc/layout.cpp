@@ -43,6 +43,8 @@ Context::Context(int dev, const std::vector<Factor>& factors) : sym(std::make_sh
     check_cuda(cudaDeviceGetDefaultMemPool(&pool, device), "cudaDeviceGetDefaultMemPool");
     uint64_t threshold = UINT64_MAX;   // keep freed blocks in the pool: block arenas are recycled every CTM move
     check_cuda(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold), "cudaMemPoolSetAttribute");
+    check_cuda(cudaMalloc(reinterpret_cast<void**>(&gemm_counters), sizeof(int) * GEMM_MAX_COUNTERS), "cudaMalloc(split-K counters)");
+    check_cuda(cudaMemset(gemm_counters, 0, sizeof(int) * GEMM_MAX_COUNTERS), "cudaMemset(split-K counters)");
 }
 
 Context::~Context()
@@ -68,6 +70,7 @@ Context::~Context()
         if(c.fence) cudaEventDestroy(c.fence);
     }
     if(scratch_) cudaFree(scratch_);
+    if(gemm_counters) cudaFree(gemm_counters);
     if(pinned_) cudaFreeHost(pinned_);
     if(stream) cudaStreamDestroy(stream);
 }
@@ -953,6 +956,16 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
             h_tiles.push_back(pt);
         }
         plan->max_fan_in = std::max(plan->max_fan_in, T.src_count);
+        plan->dst_elems += count;
+        plan->src_reads += count * static_cast<int64_t>(T.src_count);
+        {
+            static const bool dump = std::getenv("XB_PLAN_DUMP") != nullptr;
+            if(dump && h_tasks.size() % 97 == 0) {
+                std::fprintf(stderr, "[task %zu] fan-in %d count %lld tile vol %d legs:", h_tasks.size(), T.src_count, static_cast<long long>(count), T.vol);
+                for(int j = 0; j < n; ++j) std::fprintf(stderr, " (d %d w %d ds %d ss %d)", T.dims[j], T.w[j], T.dstride[j], s0[j]);
+                std::fprintf(stderr, "\n");
+            }
+        }
         h_tasks.push_back(T);
         if(bulk_ok) bulk_ok = lower_bulk_task(T, h_btasks, h_btiles);
     }

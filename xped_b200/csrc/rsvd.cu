@@ -550,7 +550,7 @@ constexpr int CHB = 16;
 constexpr int CHOL_THREADS = 512;
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
 rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, const RsvdSec* __restrict__ secs, const int* __restrict__ list, double shift_rel,
-                         double* __restrict__ diag, int* __restrict__ bad)
+                         double* __restrict__ diag, int* __restrict__ bad, int bad_tag)
 {
     extern __shared__ double chol_sh[];
     __shared__ double red[32];
@@ -711,7 +711,7 @@ rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, c
     }
     if(tid == 0) {
         diag[sec] = minpiv;
-        if(anybad) atomicOr(bad, 1);
+        if(anybad) atomicOr(bad, bad_tag);
     }
 }
 
@@ -907,7 +907,7 @@ struct RsvdPlan
            *dNorm = nullptr;
     RsvdSec* d_secs = nullptr;
     int *d_proj = nullptr, *d_direct = nullptr, *d_bad = nullptr;
-    PreparedGemm g_bx, g_bx_all, g_gy, g_ym, g_bty, g_gx2, g_x2m, g_gx, g_xm, g_btw, g_xv;
+    PreparedGemm g_bx, g_bx_all, g_gy, g_ym, g_bty, g_bty_raw, g_gx2, g_x2m, g_gx, g_xm, g_btw, g_xv;
     size_t chol_smem = 0;
     double tol_rel = 0.0, shift_it = 0.0;
     double* dVprev = nullptr;   // Ritz vectors of the previous successful call on this plan (warm start)
@@ -926,7 +926,7 @@ struct RsvdPlan
         if(graph_warm) cudaGraphExecDestroy(graph_warm);
         for(auto& kv : graph_iter)
             if(kv.second) cudaGraphExecDestroy(kv.second);
-        for(PreparedGemm* g : {&g_bx, &g_bx_all, &g_gy, &g_ym, &g_bty, &g_gx2, &g_x2m, &g_gx, &g_xm, &g_btw, &g_xv}) {
+        for(PreparedGemm* g : {&g_bx, &g_bx_all, &g_gy, &g_ym, &g_bty, &g_bty_raw, &g_gx2, &g_x2m, &g_gx, &g_xm, &g_btw, &g_xv}) {
             for(int w = 0; w < 2; ++w)
                 if(g->d_items[w]) cudaFree(g->d_items[w]);
             if(g->d_jobs) cudaFree(g->d_jobs);
@@ -938,7 +938,7 @@ struct RsvdPlan
 
 namespace {
 
-void rsvd_chol(RsvdPlan& P, double shift_rel)
+void rsvd_chol(RsvdPlan& P, double shift_rel, int bad_tag = 1)
 {
     cudaStream_t s = P.ctx->stream;
     static const bool old_form = std::getenv("XB_CHOL_OLD") != nullptr;
@@ -951,7 +951,7 @@ void rsvd_chol(RsvdPlan& P, double shift_rel)
             check_cuda(cudaFuncSetAttribute(rsvd_chol_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, most), "chol smem attr");
             configured = most;
         }
-        rsvd_chol_blocked_kernel<<<P.n_proj, CHOL_THREADS, smem, s>>>(P.dG, P.dM, P.d_secs, P.d_proj, shift_rel, P.dDiag, P.d_bad);
+        rsvd_chol_blocked_kernel<<<P.n_proj, CHOL_THREADS, smem, s>>>(P.dG, P.dM, P.d_secs, P.d_proj, shift_rel, P.dDiag, P.d_bad, bad_tag);
         check_cuda(cudaGetLastError(), "rsvd_chol_blocked_kernel launch");
         ++P.ctx->launches;
         return;
@@ -982,10 +982,10 @@ void rsvd_polish(RsvdPlan& P)
 {   // X <- orthonormal to working precision (two unshifted Cholesky-QR passes)
     Context& c = *P.ctx;
     c.launch_gemm(P.g_gx);
-    rsvd_chol(P, 0.0);
+    rsvd_chol(P, 0.0, 2);
     c.launch_gemm(P.g_xm);
     c.launch_gemm(P.g_gx2);
-    rsvd_chol(P, 0.0);
+    rsvd_chol(P, 0.0, 4);
     c.launch_gemm(P.g_x2m);
 }
 constexpr int WARM_RANDOM_COLS = 16;
@@ -1014,10 +1014,29 @@ void rsvd_start(RsvdPlan& P, bool warm)
     ++c.launches;
     rsvd_polish(P);
 }
-void rsvd_iterate(RsvdPlan& P, int iters)
+void rsvd_iterate(RsvdPlan& P, int iters, bool ordered_basis)
 {   // `iters` subspace iterations X <- orth(B^T orth(B X)), orthonormalise, project: Y = B X
     Context& c = *P.ctx;
+    // One orthonormalisation per iteration: X <- orth(B^T (B X)).  The basis is ordered (warm start = previous Ritz vectors by decreasing value, Cholesky-QR
+    // = Gram-Schmidt in column order), so the iterates stay close to the singular vectors and the Gram matrix of B^T B X is GRADED (diag ~ sigma^4) but nearly
+    // diagonal after scaling -- the regime in which a Cholesky factorisation is accurate column by column.  The shift must stay at round-off level here
+    // (1e-15 of the largest diagonal entry): the pivots of the weakest kept directions are (sigma_keep / sigma_1)^4 ~ 1e-12 of the largest, and a shift above
+    // them spoils the elimination against the leading columns (emulated in numpy on the oracle's CTM matrices: breakdown with the 1e-13 * m shift of the
+    // two-stage iteration, identical residuals to the two-stage iteration with 1e-15 or 0).  The two unshifted passes of rsvd_polish restore orthonormality
+    // before the projection.  Same iteration counts and residuals as with the intermediate orth(B X) (XB_RSVD_TWO_ORTH=1 restores it), 4 instead of 6
+    // products and 1 instead of 2 factorisations per iteration.  A breakdown (exactly rank-deficient input) sets the bad flag: the caller falls back.
+    // A cold start (random X) is NOT ordered: B^T B X is then dominated by the leading direction in every column and its Gram matrix is numerically
+    // rank-deficient -- the first batch of a cold call keeps the intermediate orthonormalisation.
+    static const bool two_orth = std::getenv("XB_RSVD_TWO_ORTH") != nullptr;
     for(int it = 0; it < iters; ++it) {
+        if(!two_orth && ordered_basis && P.K0 > 32) {   // (K <= 32 uses the register-resident factorisation, which does not rescale)
+            c.launch_gemm(P.g_bx);
+            c.launch_gemm(P.g_bty_raw);
+            c.launch_gemm(P.g_gx2);
+            rsvd_chol(P, 1.e-15);
+            c.launch_gemm(P.g_x2m);
+            continue;
+        }
         c.launch_gemm(P.g_bx);
         c.launch_gemm(P.g_gy);
         rsvd_chol(P, P.shift_it);
@@ -1167,6 +1186,7 @@ std::shared_ptr<RsvdPlan> build_rsvd_plan(Context& ctx, const Layout& L, int K0)
     P.g_gy = ctx.prepare_gemm(P.dY, P.dY, P.dG, i_gy);
     P.g_ym = ctx.prepare_gemm(P.dY, P.dM, P.dY2, i_ym);
     P.g_bty = ctx.prepare_gemm(P.dA, P.dY2, P.dX2, i_bty);
+    P.g_bty_raw = ctx.prepare_gemm(P.dA, P.dY, P.dX2, i_bty);   // Z = B^T (B X) without the intermediate orthonormalisation
     P.g_gx2 = ctx.prepare_gemm(P.dX2, P.dX2, P.dG, i_gx2);
     P.g_x2m = ctx.prepare_gemm(P.dX2, P.dM, P.dX, i_x2m);
     P.g_gx = ctx.prepare_gemm(P.dX, P.dX, P.dG, i_gx2);    // same shapes, other buffers (polishing)
@@ -1268,8 +1288,10 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
         next_iters = std::max(1, std::min(next_iters, max_iters - iters_done));
         {
             const int n_it = next_iters;
-            cudaGraphExec_t& slot = P.graph_iter[n_it];
-            run_or_replay(P, &slot, n_it, use_graph, [&]() { rsvd_iterate(P, n_it); });
+            const bool ordered = warm && iters_done == 0;   // (a continuation starts from the Ritz vectors in Jacobi's column order: not ordered)
+            const int key = n_it + (ordered ? 0 : 100000);
+            cudaGraphExec_t& slot = P.graph_iter[key];
+            run_or_replay(P, &slot, key, use_graph, [&]() { rsvd_iterate(P, n_it, ordered); });
         }
         iters_done += next_iters;
         mark(1);

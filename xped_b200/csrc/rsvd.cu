@@ -582,74 +582,87 @@ rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, c
 
     double minpiv = 1.e300;
     bool anybad = false;
-    for(int kb = 0; kb < nblk; ++kb) {
-        const int c0 = kb * CHB, r0 = c0 + CHB, nrows = Kp - r0;
-        if(warp == 0) {
-            // ---- diagonal block: lane r (both half-warps redundantly) owns row r
-            const int r = lane & 15;
-            double d[CHB];
+    // diagonal block at c0 (warp 0): lane r (both half-warps redundantly) owns row r.  `fused`: the block first takes the rank-16 update of the panel that
+    // was just computed (its rows are the first 16 of the panel buffer) -- look-ahead: the next diagonal block is factorised while the other warps apply
+    // the trailing update.
+    auto factor_diag = [&](int c0, bool fused) {
+        const int r = lane & 15;
+        double d[CHB];
 #pragma unroll
-            for(int c = 0; c < CHB; ++c) d[c] = c <= r ? A[(c0 + c) * LD + c0 + r] : 0.0;
+        for(int c = 0; c < CHB; ++c) d[c] = c <= r ? A[(c0 + c) * LD + c0 + r] : 0.0;
+        if(fused) {
+#pragma unroll 4
+            for(int k = 0; k < CHB; ++k) {
+                const double pr = Pb[k * Kp + r];
 #pragma unroll
-            for(int j = 0; j < CHB; ++j) {
-                double djj = __shfl_sync(0xffffffffu, d[j], j);
-                if(!(djj > 0.0) || !isfinite(djj)) {
-                    anybad = true;
-                    djj = gmax * 1.e-30;
-                }
-                if(c0 + j < K) minpiv = fmin(minpiv, djj * gmax_inv);
-                const double rs = rsqrt(djj);
-                if(lane == j) dinv[c0 + j] = rs;
-                const double l = r > j ? d[j] * rs : (r == j ? djj * rs : 0.0);
-                d[j] = l;
-#pragma unroll
-                for(int c = j + 1; c < CHB; ++c) {
-                    const double lc = __shfl_sync(0xffffffffu, l, c);
-                    d[c] = fma(-l, lc, d[c]);
-                }
+                for(int c = 0; c < CHB; ++c) d[c] = fma(-pr, Pb[k * Kp + c], d[c]);   // (entries above the diagonal are never used)
             }
-            __syncwarp();
-            // ---- X = L^-1 of the block by columns: lane c solves L x = e_c (L_ik from its row owner)
-            double x[CHB];
+        }
+#pragma unroll
+        for(int j = 0; j < CHB; ++j) {
+            double djj = __shfl_sync(0xffffffffu, d[j], j);
+            if(!(djj > 0.0) || !isfinite(djj)) {
+                anybad = true;
+                djj = gmax * 1.e-30;
+            }
+            if(c0 + j < K) minpiv = fmin(minpiv, djj * gmax_inv);
+            const double rs = rsqrt(djj);
+            if(lane == j) dinv[c0 + j] = rs;
+            const double l = r > j ? d[j] * rs : (r == j ? djj * rs : 0.0);
+            d[j] = l;
+#pragma unroll
+            for(int c = j + 1; c < CHB; ++c) {
+                const double lc = __shfl_sync(0xffffffffu, l, c);
+                d[c] = fma(-l, lc, d[c]);
+            }
+        }
+        __syncwarp();
+        // ---- X = L^-1 of the block by columns: lane c solves L x = e_c (L_ik from its row owner)
+        double x[CHB];
+#pragma unroll
+        for(int i = 0; i < CHB; ++i) {
+            double acc = (i == r) ? 1.0 : 0.0;
+#pragma unroll
+            for(int k = 0; k < i; ++k) acc = fma(-__shfl_sync(0xffffffffu, d[k], i), x[k], acc);
+            x[i] = acc * dinv[c0 + i];
+        }
+        if(lane < CHB) {
+#pragma unroll
+            for(int c = 0; c < CHB; ++c)
+                if(c <= r) A[(c0 + c) * LD + c0 + r] = d[c];               // L block
 #pragma unroll
             for(int i = 0; i < CHB; ++i) {
-                double acc = (i == r) ? 1.0 : 0.0;
-#pragma unroll
-                for(int k = 0; k < i; ++k) acc = fma(-__shfl_sync(0xffffffffu, d[k], i), x[k], acc);
-                x[i] = acc * dinv[c0 + i];
+                Li[i * (CHB + 1) + r] = x[i];                               // Linv[i][c = r] (zero above the diagonal)
+                if(i > r) A[(c0 + i) * LD + c0 + r] = x[i];                 // M part: position (row c, col i) = X[i][c]
             }
-            if(lane < CHB) {
+        }
+    };
+    if(warp == 0) factor_diag(0, false);
+    __syncthreads();
+    for(int kb = 0; kb + 1 < nblk; ++kb) {
+        const int c0 = kb * CHB, r0 = c0 + CHB, nrows = Kp - r0;
+        // ---- panel: P[i][j] = sum_{c <= j} A[r0 + i][c0 + c] * Linv[j][c]
+        for(int idx = tid; idx < nrows * 4; idx += CHOL_THREADS) {
+            const int jq = idx / nrows, i = idx - jq * nrows;
+            double a[CHB];
 #pragma unroll
-                for(int c = 0; c < CHB; ++c)
-                    if(c <= r) A[(c0 + c) * LD + c0 + r] = d[c];               // L block
+            for(int c = 0; c < CHB; ++c) a[c] = A[(c0 + c) * LD + r0 + i];
 #pragma unroll
-                for(int i = 0; i < CHB; ++i) {
-                    Li[i * (CHB + 1) + r] = x[i];                               // Linv[i][c = r] (zero above the diagonal)
-                    if(i > r) A[(c0 + i) * LD + c0 + r] = x[i];                 // M part: position (row c, col i) = X[i][c]
-                }
+            for(int jj = 0; jj < 4; ++jj) {
+                const int j = jq * 4 + jj;
+                double p = 0.0;
+#pragma unroll
+                for(int c = 0; c < CHB; ++c) p = fma(a[c], Li[j * (CHB + 1) + c], p);   // Linv is lower triangular: entries with c > j are zero
+                Pb[j * Kp + i] = p;
             }
         }
         __syncthreads();
-        if(nrows > 0) {
-            // ---- panel: P[i][j] = sum_{c <= j} A[r0 + i][c0 + c] * Linv[j][c]
-            for(int idx = tid; idx < nrows * 4; idx += CHOL_THREADS) {
-                const int jq = idx / nrows, i = idx - jq * nrows;
-                double a[CHB];
-#pragma unroll
-                for(int c = 0; c < CHB; ++c) a[c] = A[(c0 + c) * LD + r0 + i];
-#pragma unroll
-                for(int jj = 0; jj < 4; ++jj) {
-                    const int j = jq * 4 + jj;
-                    double p = 0.0;
-#pragma unroll
-                    for(int c = 0; c < CHB; ++c) p = fma(a[c], Li[j * (CHB + 1) + c], p);   // Linv is lower triangular: entries with c > j are zero
-                    Pb[j * Kp + i] = p;
-                }
-            }
-            __syncthreads();
-            // ---- trailing update (full square: the matrix stays symmetric) + the panel goes back into the matrix
-            const int q = nrows >> 2;
-            for(int t = tid; t < q * q; t += CHOL_THREADS) {
+        if(warp == 0) {
+            factor_diag(r0, true);   // overwrites Li: the panel above was its last reader
+        } else {
+            // ---- trailing update (full square: the matrix stays symmetric; the next diagonal block belongs to warp 0) + the panel goes back into the matrix
+            const int q = nrows >> 2, t_id = tid - 32, t_n = CHOL_THREADS - 32;
+            for(int t = t_id; t < q * q; t += t_n) {
                 const int tc = t / q, ti = t - tc * q;
                 double acc[4][4];
 #pragma unroll
@@ -671,14 +684,17 @@ rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, c
 #pragma unroll
                 for(int b = 0; b < 4; ++b)
 #pragma unroll
-                    for(int a = 0; a < 4; ++a) A[(r0 + tc + b * q) * LD + r0 + ti + a * q] -= acc[a][b];
+                    for(int a = 0; a < 4; ++a) {
+                        const int gr = ti + a * q, gc = tc + b * q;
+                        if(gr >= CHB || gc >= CHB) A[(r0 + gc) * LD + r0 + gr] -= acc[a][b];
+                    }
             }
-            for(int idx = tid; idx < nrows * CHB; idx += CHOL_THREADS) {
+            for(int idx = t_id; idx < nrows * CHB; idx += t_n) {
                 const int j = idx / nrows, i = idx - j * nrows;
                 A[(c0 + j) * LD + r0 + i] = Pb[j * Kp + i];
             }
-            __syncthreads();
         }
+        __syncthreads();
     }
     // ---- X = L^-1 below the diagonal blocks: column c, rows of block ib:  X[ib][c] = -Linv_ib * sum_{k = 16 jb}^{16 ib - 1} L[ib rows][k] * X[k][c];
     // X[k][c] sits at A[k * LD + c] (upper triangle), Linv_ib[r][k] (k < r) at A[(16 ib + r) * LD + 16 ib + k], its diagonal in dinv
@@ -689,8 +705,16 @@ rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, c
             const int jb = c / CHB;
             for(int ib = jb + 1; ib < nblk; ++ib) {
                 const int row = ib * CHB + r;
-                double sacc = 0.0;
-                for(int k = jb * CHB; k < ib * CHB; ++k) sacc = fma(A[k * LD + row], k == c ? dinv[c] : (k < c ? 0.0 : A[k * LD + c]), sacc);
+                // rows of the diagonal block jb: X[k][c] is dinv[c] at k == c, zero above, stored below; then full blocks, four independent chains
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                for(int k = c; k < (jb + 1) * CHB; ++k) s0 = fma(A[k * LD + row], k == c ? dinv[c] : A[k * LD + c], s0);
+                for(int k = (jb + 1) * CHB; k < ib * CHB; k += 4) {
+                    s0 = fma(A[k * LD + row], A[k * LD + c], s0);
+                    s1 = fma(A[(k + 1) * LD + row], A[(k + 1) * LD + c], s1);
+                    s2 = fma(A[(k + 2) * LD + row], A[(k + 2) * LD + c], s2);
+                    s3 = fma(A[(k + 3) * LD + row], A[(k + 3) * LD + c], s3);
+                }
+                const double sacc = (s0 + s1) + (s2 + s3);
                 double t = 0.0;
 #pragma unroll
                 for(int k = 0; k < CHB; ++k) {

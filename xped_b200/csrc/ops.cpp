@@ -82,6 +82,15 @@ PreparedGemm Context::prepare_gemm(const double* A, const double* B, double* C, 
     // per problem; kept as an option.
     static const bool reduce_kernel = std::getenv("XB_GEMM_SPLITK_INKERNEL") == nullptr;
     int next_counter = 0;
+    // tiles of the whole launch: a launch that fills less than ~two waves (3 CTAs per SM) with LONG contractions leaves SMs idle for a large fraction of its
+    // run time (the 3060 x 160 x 3096 products of the D=6 subspace iteration: 333 CTAs on 148 SMs = 2.25 per SM, 10 TFLOP/s) -- cut K there as well
+    long long launch_tiles = 0;
+    for(const GemmItem& g : problems) {
+        if(g.m <= 0 || g.n <= 0) continue;
+        const int tile_m = g.m > 96 ? 128 : 64;
+        launch_tiles += static_cast<long long>((g.m + tile_m - 1) / tile_m) * ((g.n + GEMM_TILE_N - 1) / GEMM_TILE_N);
+    }
+    static const int wave_split = std::getenv("XB_GEMM_WAVE_SPLIT") ? std::atoi(std::getenv("XB_GEMM_WAVE_SPLIT")) : 6;   // target CTAs per SM (0: off)
     for(GemmItem g : problems) {
         if(g.m <= 0 || g.n <= 0) continue;
         P.flops += 2.0 * g.m * static_cast<double>(g.n) * g.k;
@@ -89,6 +98,8 @@ PreparedGemm Context::prepare_gemm(const double* A, const double* B, double* C, 
         const int ntiles = ((g.m + tile_m - 1) / tile_m) * ((g.n + GEMM_TILE_N - 1) / GEMM_TILE_N);
         int split = 1;
         if(!no_split && !g.acc && g.k >= 256 && ntiles <= 32) split = std::max(1, std::min(8, std::min(g.k / 96, sm_count / ntiles)));
+        if(!no_split && wave_split > 0 && !g.acc && split == 1 && g.k >= 768 && launch_tiles < static_cast<long long>(wave_split) * sm_count)
+            split = std::max(1, std::min(8, std::min(g.k / 256, static_cast<int>((static_cast<long long>(wave_split) * sm_count + launch_tiles - 1) / launch_tiles))));
         if(split > 1) {
             const int kchunk = ((((g.k + split - 1) / split) + 7) / 8) * 8;
             const bool in_kernel = !reduce_kernel && next_counter + ntiles <= GEMM_MAX_COUNTERS;

@@ -180,12 +180,7 @@ struct GemmItem   // one (sector, tile) of a grouped product
     int acc;      // 1: C += alpha * op(A) op(B)   0: C = alpha * op(A) op(B)
     int pad_;
     double alpha;
-    // split-K (nslice > 1): this item is K slice `slice` of a problem; its partial tile goes to scratch (c_off / ldc address the slice), and the LAST slice
-    // CTA of the tile to finish (ticket counter `counter`) sums all slices in slice order -- deterministic -- into c_final / ldc_final
-    long long c_final;
-    int ldc_final, nslice, slice, counter;
 };
-constexpr int GEMM_MAX_COUNTERS = 1 << 16;   // ticket counters of the in-kernel split-K reduction (self-resetting)
 
 // one split-K problem: C[c_off + i + j ldc] = sum_s scratch[s_off + s m n + i + j m]
 struct SplitKJob { long long c_off, s_off; int m, n, ldc, split; };
@@ -323,7 +318,6 @@ public:
     PreparedGemm prepare_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems);
     void launch_gemm(const PreparedGemm& P);
     void free_gemm(PreparedGemm& P);
-    int* gemm_counters = nullptr;   // device, zero-initialised, GEMM_MAX_COUNTERS entries (allocated on first use)
 
     // one Jacobi sweep (flag reset + all rounds) as an instantiated CUDA graph, keyed by layout; valid while the stream-ordered pool
     // hands the same work buffers back (it does in a steady CTM run), re-captured otherwise
@@ -419,7 +413,7 @@ void launch_permute_peers(const double* src, double* dst, const PermutePlan& pla
 void launch_permute2(const double* src, const double* src2, long long split, double* dst, const PermutePlan& plan, cudaStream_t s);
 // deterministic LPT greedy (largest cost first, ties by index, least-loaded rank, ties lowest rank)
 std::vector<int> lpt_owner(const std::vector<double>& cost, int world);
-void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, int tile_m, int* counters, cudaStream_t s);
+void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, int tile_m, cudaStream_t s);
 void launch_splitk_reduce(const double* scratch, double* C, const SplitKJob* d_jobs, int n_jobs, cudaStream_t s);
 void launch_scale_copy(const double* x, double* y, double alpha, int64_t n, cudaStream_t s);
 void launch_axpby(const double* x, const double* y, double* z, double alpha, double beta, int64_t n, cudaStream_t s);

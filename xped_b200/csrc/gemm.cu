@@ -52,9 +52,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 template <int BM>
 __global__ void __launch_bounds__(GEMM_THREADS)
-gemm_grouped_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, const GemmItem* __restrict__ items, int* __restrict__ counters)
+gemm_grouped_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, const GemmItem* __restrict__ items)
 {
-    __shared__ int s_last;
     using cfg = Cfg<BM>;
     constexpr int WM = BM / 2, WN = BN / 2;   // warp tile
     constexpr int TM = WM / 8, TN = WN / 8;   // DMMA tiles per warp
@@ -182,32 +181,9 @@ gemm_grouped_kernel(const double* __restrict__ A, const double* __restrict__ B, 
                     }
             }
         }
-    if(it.nslice > 1) {
-        // split-K: the partial tile is in scratch.  Take a ticket; the CTA that takes the last one sums the slices of this tile in slice order
-        // (independent of the arrival order: bit-reproducible) into the destination and resets the counter for the next launch.
-        __threadfence();
-        __syncthreads();
-        if(tid == 0) s_last = atomicAdd(counters + it.counter, 1) == it.nslice - 1;
-        __syncthreads();
-        if(s_last) {
-            __threadfence();
-            const long long slice_elems = static_cast<long long>(it.m) * it.n;
-            const double* __restrict__ base0 = C + it.c_off - static_cast<long long>(it.slice) * slice_elems;
-            double* __restrict__ Cf = C + it.c_final;
-            const int rows = min(BM, it.m - m0), cols = min(BN, it.n - n0);
-            for(int e = tid; e < rows * cols; e += GEMM_THREADS) {
-                const int c = e / rows, r = e - c * rows;
-                const long long o = (m0 + r) + static_cast<long long>(n0 + c) * it.m;
-                double sum = 0.0;
-                for(int sl = 0; sl < it.nslice; ++sl) sum += __ldcg(base0 + sl * slice_elems + o);
-                Cf[(m0 + r) + static_cast<long long>(n0 + c) * it.ldc_final] = sum;
-            }
-            if(tid == 0) counters[it.counter] = 0;
-        }
-    }
 }
 
-template <int BM> void launch_one(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, int* counters, cudaStream_t s)
+template <int BM> void launch_one(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, cudaStream_t s)
 {
     static bool configured = false;
     if(!configured) {
@@ -215,7 +191,7 @@ template <int BM> void launch_one(const double* A, const double* B, double* C, c
                    "cudaFuncSetAttribute(gemm smem)");
         configured = true;
     }
-    gemm_grouped_kernel<BM><<<n_items, GEMM_THREADS, Cfg<BM>::SMEM_BYTES, s>>>(A, B, C, d_items, counters);
+    gemm_grouped_kernel<BM><<<n_items, GEMM_THREADS, Cfg<BM>::SMEM_BYTES, s>>>(A, B, C, d_items);
     check_cuda(cudaGetLastError(), "gemm_grouped_kernel launch");
 }
 
@@ -242,13 +218,13 @@ void launch_splitk_reduce(const double* scratch, double* C, const SplitKJob* d_j
     check_cuda(cudaGetLastError(), "splitk_reduce_kernel launch");
 }
 
-void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, int tile_m, int* counters, cudaStream_t s)
+void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, int tile_m, cudaStream_t s)
 {
     if(n_items == 0) return;
     if(tile_m == 128)
-        launch_one<128>(A, B, C, d_items, n_items, counters, s);
+        launch_one<128>(A, B, C, d_items, n_items, s);
     else
-        launch_one<64>(A, B, C, d_items, n_items, counters, s);
+        launch_one<64>(A, B, C, d_items, n_items, s);
 }
 
 }   // namespace xb

@@ -43,8 +43,6 @@ Context::Context(int dev, const std::vector<Factor>& factors) : sym(std::make_sh
     check_cuda(cudaDeviceGetDefaultMemPool(&pool, device), "cudaDeviceGetDefaultMemPool");
     uint64_t threshold = UINT64_MAX;   // keep freed blocks in the pool: block arenas are recycled every CTM move
     check_cuda(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold), "cudaMemPoolSetAttribute");
-    check_cuda(cudaMalloc(reinterpret_cast<void**>(&gemm_counters), sizeof(int) * GEMM_MAX_COUNTERS), "cudaMalloc(split-K counters)");
-    check_cuda(cudaMemset(gemm_counters, 0, sizeof(int) * GEMM_MAX_COUNTERS), "cudaMemset(split-K counters)");
 }
 
 Context::~Context()
@@ -70,7 +68,6 @@ Context::~Context()
         if(c.fence) cudaEventDestroy(c.fence);
     }
     if(scratch_) cudaFree(scratch_);
-    if(gemm_counters) cudaFree(gemm_counters);
     if(pinned_) cudaFreeHost(pinned_);
     if(stream) cudaStreamDestroy(stream);
 }

@@ -77,11 +77,9 @@ PreparedGemm Context::prepare_gemm(const double* A, const double* B, double* C, 
     std::vector<SplitKJob> jobs;      // problems with few tiles and a long K: K is cut into slices, the partial products are summed afterwards
     long long scratch_elems = 0;
     static const bool no_split = std::getenv("XB_GEMM_NOSPLIT") != nullptr;
-    // XB_GEMM_SPLITK_INKERNEL=1: the last slice CTA of a tile (ticket counter) sums the slices inside gemm_grouped_kernel instead of the separate reduce
-    // launch.  Measured slower (D=4 CTM step 32.2 vs 26.3 ms): one 128-thread CTA walks 8 slices x 8192 elements at L2 latency, the reduce kernel uses 32 CTAs
-    // per problem; kept as an option.
-    static const bool reduce_kernel = std::getenv("XB_GEMM_SPLITK_INKERNEL") == nullptr;
-    int next_counter = 0;
+    // (measured in round 2 and removed again: summing the slices inside gemm_grouped_kernel by the last slice CTA of a tile (ticket counters) -- 32.2 vs
+    // 26.3 ms per D=4 CTM step, and the extra epilogue raised the 128-row kernel from 168 to 207 registers: 2 instead of 3 CTAs per SM, W4 T*T 23.8 vs 29.1
+    // TFLOP/s)
     // tiles of the whole launch: a launch that fills less than ~two waves (3 CTAs per SM) with LONG contractions leaves SMs idle for a large fraction of its
     // run time (the 3060 x 160 x 3096 products of the D=6 subspace iteration: 333 CTAs on 148 SMs = 2.25 per SM, 10 TFLOP/s) -- cut K there as well
     long long launch_tiles = 0;
@@ -102,8 +100,6 @@ PreparedGemm Context::prepare_gemm(const double* A, const double* B, double* C, 
             split = std::max(1, std::min(8, std::min(g.k / 256, static_cast<int>((static_cast<long long>(wave_split) * sm_count + launch_tiles - 1) / launch_tiles))));
         if(split > 1) {
             const int kchunk = ((((g.k + split - 1) / split) + 7) / 8) * 8;
-            const bool in_kernel = !reduce_kernel && next_counter + ntiles <= GEMM_MAX_COUNTERS;
-            const int nslice = (g.k + kchunk - 1) / kchunk;
             SplitKJob job;
             job.c_off = g.c_off;
             job.s_off = scratch_elems;
@@ -119,27 +115,16 @@ PreparedGemm Context::prepare_gemm(const double* A, const double* B, double* C, 
                 h.c_off = scratch_elems + static_cast<long long>(job.split) * g.m * g.n;   // relative to the scratch buffer; rebased below
                 h.ldc = g.m;
                 h.pad_ = 1;   // marks a scratch destination
-                if(in_kernel) {
-                    h.c_final = g.c_off;
-                    h.ldc_final = g.ldc;
-                    h.nslice = nslice;
-                    h.slice = job.split;
-                }
                 ++job.split;
-                int tile = 0;
                 for(int tn = 0; tn < g.n; tn += GEMM_TILE_N)
                     for(int tm = 0; tm < g.m; tm += tile_m) {
                         h.tm = tm;
                         h.tn = tn;
-                        h.counter = next_counter + tile++;
                         items[which].push_back(h);
                     }
             }
             scratch_elems += static_cast<long long>(job.split) * g.m * g.n;
-            if(in_kernel)
-                next_counter += ntiles;
-            else
-                jobs.push_back(job);
+            jobs.push_back(job);
             continue;
         }
         g.pad_ = 0;
@@ -196,7 +181,7 @@ void Context::launch_gemm(const PreparedGemm& P)
     if(P.launches == 0) return;
     ProfScope prof(*this, CAT_GEMM, P.flops);
     for(int which = 0; which < 2; ++which)
-        if(P.n_items[which] > 0) launch_gemm_grouped(P.A, P.B, P.C, P.d_items[which], P.n_items[which], which == 0 ? 128 : 64, gemm_counters, stream);
+        if(P.n_items[which] > 0) launch_gemm_grouped(P.A, P.B, P.C, P.d_items[which], P.n_items[which], which == 0 ? 128 : 64, stream);
     if(P.n_jobs > 0) launch_splitk_reduce(P.d_scratch, P.C, P.d_jobs, P.n_jobs, stream);
     launches += P.launches;
 }

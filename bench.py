@@ -524,6 +524,16 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- xped_b200 has no CPU fallback (use --impl reference for the CPU oracle arm)")
     torch.cuda.set_device(local)
+    if world > 1 and not os.environ.get("XB_BENCH_NO_PIN"):
+        # one process per GPU, launch-bound steps (~1000 launches in ~21 ms): give every rank its own slice of the host cores so that the launch threads do not
+        # migrate / share a core with another rank's spinning synchronisation
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = len(cpus) // world
+            if per >= 1:
+                os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]))
+        except (AttributeError, OSError):
+            pass
     real_stdout = None
     if world > 1:
         # keep stdout to the ONE JSON line: NCCL prints its version banner to the C-level stdout when the first communicator is

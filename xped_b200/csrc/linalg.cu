@@ -941,7 +941,7 @@ JacobiResult jacobi_all(Context& ctx, const JacobiInput& in, bool shifted, bool 
             pre.push_back(q);
             pre_index.push_back(static_cast<int>(&b - R.blocks.data()));
         }
-        if(!shifted && !no_precond && !pre.empty() && svd_precondition_supported(pre_max_rows)) {
+        if(!shifted && !no_precond && !in.no_precondition && !pre.empty() && svd_precondition_supported(pre_max_rows)) {
             static const bool pre_prof = std::getenv("XB_SVD_PROF") != nullptr;
             double* d_aug = nullptr;
             QrPreBlock* d_pre = nullptr;

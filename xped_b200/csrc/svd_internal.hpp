@@ -36,6 +36,7 @@ struct JacobiInput
     std::vector<long long> off;
     std::vector<int> rows, cols;
     std::string sig;   // key of the cached sweep graphs
+    bool no_precondition = false;   // skip the QR preconditioner (projected blocks of the truncated path: columns already close to the singular directions)
 };
 
 JacobiInput jacobi_input(const Tensor& t);

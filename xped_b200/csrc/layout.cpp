@@ -470,8 +470,17 @@ void choose_tiles(PermTask& T, const int* sstride0, int target)
         nchunk = 1;
         if(T.ntl >= 2) {
             const int wb = T.w[order[1]];
-            strip = 1;
-            while(strip * 2 <= std::min(PERM_STRIP, wb) && (T.vol / wb) * ceil_div(wb, strip * 2) >= PERM_THREADS) strip *= 2;   // power of two: 1, 2, 4, 8
+            // the longest strip <= PERM_STRIP that cuts the leg evenly (extent 3 -> 3, 9 -> 5 + 4, 16 -> 8 + 8), halved while a tile would have fewer
+            // items than threads.  (Round 1 used powers of two: an extent-3 leg -- the SU(2) aux multiplicities -- became strips of 2 + 1, i.e. 1.5 elements
+            // per ~60-instruction index decomposition.)
+            static const bool pow2_strips = std::getenv("XB_PERM_POW2_STRIPS") != nullptr;
+            if(pow2_strips) {
+                strip = 1;
+                while(strip * 2 <= std::min(PERM_STRIP, wb) && (T.vol / wb) * ceil_div(wb, strip * 2) >= PERM_THREADS) strip *= 2;
+            } else {
+                strip = ceil_div(wb, ceil_div(wb, PERM_STRIP));
+                while(strip > 1 && (T.vol / wb) * ceil_div(wb, strip) < PERM_THREADS) strip = ceil_div(strip, 2);
+            }
             nchunk = ceil_div(wb, strip);
         }
         items = T.ntl >= 2 ? (T.vol / T.w[order[1]]) * nchunk : T.vol;

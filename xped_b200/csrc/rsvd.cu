@@ -1251,7 +1251,8 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
     const int nsec = static_cast<int>(L.sector.size());
     constexpr int KMAX = 160;
     if(max_keep + 16 > KMAX || nsec > 4096) return false;
-    const int K0 = static_cast<int>(std::min<int64_t>(KMAX, ((max_keep + 32 + 15) / 16) * 16));
+    static const int oversampling = std::getenv("XB_SVD_TRUNC_OVERSAMPLING") ? std::atoi(std::getenv("XB_SVD_TRUNC_OVERSAMPLING")) : 32;
+    const int K0 = static_cast<int>(std::min<int64_t>(KMAX, ((max_keep + oversampling + 15) / 16) * 16));
     {   // enough of a reduction?
         long long sum_nb = 0, sum_k = 0;
         int n_proj = 0;

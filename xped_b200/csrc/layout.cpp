@@ -478,8 +478,17 @@ void choose_tiles(PermTask& T, const int* sstride0, int target)
                 strip = 1;
                 while(strip * 2 <= std::min(PERM_STRIP, wb) && (T.vol / wb) * ceil_div(wb, strip * 2) >= PERM_THREADS) strip *= 2;
             } else {
-                strip = ceil_div(wb, ceil_div(wb, PERM_STRIP));
-                while(strip > 1 && (T.vol / wb) * ceil_div(wb, strip) < PERM_THREADS) strip = ceil_div(strip, 2);
+                // cost of a phase ~ passes over the thread block x (index decomposition + per-element work of a strip): a tile of 32 x 36 is 256 items of
+                // 5 (one pass), not 288 items of 4 (two passes, the second one with 32 live threads)
+                long long best = -1;
+                for(int c = 1; c <= std::min(PERM_STRIP, wb); ++c) {
+                    const long long its = static_cast<long long>(T.vol / wb) * ceil_div(wb, c);
+                    const long long cost = ((its + PERM_THREADS - 1) / PERM_THREADS) * (60 + 10 * c);
+                    if(best < 0 || cost <= best) {
+                        best = cost;
+                        strip = c;
+                    }
+                }
             }
             nchunk = ceil_div(wb, strip);
         }

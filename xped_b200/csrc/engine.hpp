@@ -318,6 +318,12 @@ public:
     PreparedGemm prepare_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems);
     void launch_gemm(const PreparedGemm& P);
     void free_gemm(PreparedGemm& P);
+    // operator* keeps its prepared tile lists per (operand layouts, adjoint flags): a CTM move repeats the same ~90 products every step, and building, sorting
+    // and uploading the lists per call put ~1.5 ms of copies and allocations on the stream of a 20 ms step.  Offsets are relative to the operand base pointers;
+    // only split-K scratch offsets are relative to the RESULT pointer: an entry with scratch is rebuilt when the pool hands out another result address.
+    struct GemmCacheEntry { PreparedGemm P; const double* c_ptr = nullptr; };
+    std::unordered_map<std::string, GemmCacheEntry> gemm_cache;
+    int64_t gemm_cache_hits = 0, gemm_cache_misses = 0;
 
     // one Jacobi sweep (flag reset + all rounds) as an instantiated CUDA graph, keyed by layout; valid while the stream-ordered pool
     // hands the same work buffers back (it does in a steady CTM run), re-captured otherwise

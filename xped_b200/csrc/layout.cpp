@@ -54,6 +54,8 @@ Context::~Context()
     cudaSetDevice(device);
     if(stream) cudaStreamSynchronize(stream);
     dist_shutdown(*this);
+    for(auto& kv : gemm_cache) free_gemm(kv.second.P);
+    gemm_cache.clear();
     clear_rsvd_plans();
     plan_cache_.clear();
     for(const ProfRec& r : prof_recs) {

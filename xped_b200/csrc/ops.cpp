@@ -248,7 +248,38 @@ Tensor* Context::multiply_sectors(const Tensor& a, bool adj_a, const Tensor& b, 
         g.alpha = 1.0;
         items.push_back(g);
     }
-    run_gemm(a.d, b.d, out->d, items);
+    {
+        static const bool no_cache = std::getenv("XB_GEMM_NOCACHE") != nullptr;
+        const std::string key = LA.sig + "|" + LB.sig + "|" + LO->sig + (adj_a ? "|a" : "|n") + (adj_b ? "a" : "n");
+        auto it = no_cache ? gemm_cache.end() : gemm_cache.find(key);
+        if(it != gemm_cache.end() && it->second.P.d_scratch != nullptr && it->second.c_ptr != out->d) {   // scratch offsets were taken relative to another result
+            free_gemm(it->second.P);
+            gemm_cache.erase(it);
+            it = gemm_cache.end();
+        }
+        if(no_cache) {
+            run_gemm(a.d, b.d, out->d, items);
+        } else {
+            if(it == gemm_cache.end()) {
+                ++gemm_cache_misses;
+                if(gemm_cache.size() >= 512) {
+                    for(auto& kv : gemm_cache) free_gemm(kv.second.P);
+                    gemm_cache.clear();
+                }
+                GemmCacheEntry e;
+                e.P = prepare_gemm(a.d, b.d, out->d, items);
+                e.c_ptr = out->d;
+                it = gemm_cache.emplace(key, e).first;
+            } else {
+                ++gemm_cache_hits;
+            }
+            PreparedGemm& P = it->second.P;
+            P.A = a.d;
+            P.B = b.d;
+            P.C = out->d;
+            launch_gemm(P);
+        }
+    }
     if(taping()) {   // ADTensor.hpp:749-758: adj(left) += adj(res) * right^+, adj(right) += left^+ * adj(res); lazy-adjoint operands get the adjoint of that
         Tensor *ta = tape->keep(a), *tb = tape->keep(b), *tout = tape->keep(*out);
         tape->record([this, ta, tb, tout, adj_a, adj_b](Tape& T) {

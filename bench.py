@@ -311,7 +311,9 @@ def kernel_sections(xb, device, torch, cpu_d6=False):
             ms6 = ctx3.timer_stop()
             prof6 = ctx3.profile_read()
             ctx3.profile(False)
-            steps6.append({"ms": ms6, "device_ms": {k: v[0] for k, v in prof6.items()}, "launch_groups": {k: v[1] for k, v in prof6.items()}})
+            steps6.append({"ms": ms6, "device_ms": {k: v[0] for k, v in prof6.items()}, "launch_groups": {k: v[1] for k, v in prof6.items()},
+                           "permute_GBps": prof6["permute"][2] / max(prof6["permute"][0], 1e-9) / 1e6,      # algorithmic bytes of the step's permutes / their device time
+                           "gemm_TFLOPs": prof6["gemm"][2] / max(prof6["gemm"][0], 1e-9) / 1e9})
         best = min(steps6, key=lambda r: r["ms"])
         out["ctm_d6_chi144"] = {"op": "grow_all() at D=6 (aux {1:3, 2:3}), chi=144, steps 4 and 5 from FROM_A, entirely on the device", "ms_per_step": best["ms"],
                                 "tsvd_ms_per_call": best["device_ms"]["tsvd"] / max(best["launch_groups"]["tsvd"], 1), "steps": steps6,
@@ -689,12 +691,22 @@ def run_b200(args):
                         "on": "W4 (25 permute<shift,p> cases of the 1.30 GB U(1) tensor), algorithmic bytes 8*(N_src+N_dst) per launch",
                         "in_ctm_step": {"launches_per_step": p_cnt / args.steps, "avg_us_per_launch": 1e3 * p_ms / max(p_cnt, 1),
                                         "GBps": p_bytes / max(p_ms, 1e-9) / 1e6, "share_of_step": shares["permute"]}}
+            d6 = extras.get("ctm_d6_chi144", {})
+            if "steps" in d6:
+                b6 = min(d6["steps"], key=lambda r: r["ms"])
+                roofline["in_ctm_step_d6_chi144"] = {"launches_per_step": b6["launch_groups"]["permute"], "ms": b6["device_ms"]["permute"], "GBps": b6["permute_GBps"],
+                                                     "frac": b6["permute_GBps"] / hbm_peak, "share_of_step": b6["device_ms"]["permute"] / b6["ms"],
+                                                     "note": "SU(2) plans: LSU form, recoupling sums read every source element 2.1-2.3 times (DESIGN.md 9.2)"}
             roofline_contract = {"kernel": "gemm_grouped_kernel", "bound": "tensor", "achieved": extras["contract_w4"]["TFLOPs"], "peak": dgemm_peak,
                                  "unit": "TFLOP/s", "frac": extras["contract_w4"]["TFLOPs"] / dgemm_peak, "traffic": traffic.get("gemm_grouped_kernel"),
                                  "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                                  "on": "W4 T*T (1.27e12 flop)",
                                  "in_ctm_step": {"launches_per_step": g_cnt / args.steps, "avg_us_per_launch": 1e3 * g_ms / max(g_cnt, 1),
                                                  "TFLOPs": g_fl / max(g_ms, 1e-9) / 1e9, "share_of_step": shares["gemm"]}}
+            if "steps" in d6:
+                roofline_contract["in_ctm_step_d6_chi144"] = {"launch_groups_per_step": b6["launch_groups"]["gemm"], "ms": b6["device_ms"]["gemm"],
+                                                              "TFLOPs": b6["gemm_TFLOPs"], "frac": b6["gemm_TFLOPs"] / dgemm_peak,
+                                                              "share_of_step": b6["device_ms"]["gemm"] / b6["ms"]}
         else:
             roofline = {"kernel": "permute_kernel", "bound": "hbm", "achieved": p_bytes / max(p_ms, 1e-9) / 1e6, "peak": hbm_peak, "unit": "GB/s",
                         "frac": p_bytes / max(p_ms, 1e-9) / 1e6 / hbm_peak, "traffic": None, "peak_source": peak_src,

@@ -699,15 +699,16 @@ rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, c
     // ---- X = L^-1 below the diagonal blocks: column c, rows of block ib:  X[ib][c] = -Linv_ib * sum_{k = 16 jb}^{16 ib - 1} L[ib rows][k] * X[k][c];
     // X[k][c] sits at A[k * LD + c] (upper triangle), Linv_ib[r][k] (k < r) at A[(16 ib + r) * LD + 16 ib + k], its diagonal in dinv
     {
+        // the two half-warps own the neighbouring columns c (even) and c + 1 of the same 16-block: identical trip counts, so the shuffles and warp
+        // barriers below use the full mask (partial masks cost a MATCH per use)
         const int r = lane & 15, half = lane >> 4;
-        const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
         for(int c = warp * 2 + half; c < Kp; c += CHOL_THREADS / 16) {
             const int jb = c / CHB;
             for(int ib = jb + 1; ib < nblk; ++ib) {
                 const int row = ib * CHB + r;
                 // rows of the diagonal block jb: X[k][c] is dinv[c] at k == c, zero above, stored below; then full blocks, four independent chains
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                for(int k = c; k < (jb + 1) * CHB; ++k) s0 = fma(A[k * LD + row], k == c ? dinv[c] : A[k * LD + c], s0);
+                for(int k = jb * CHB; k < (jb + 1) * CHB; ++k) s0 = fma(A[k * LD + row], k == c ? dinv[c] : (k > c ? A[k * LD + c] : 0.0), s0);
                 for(int k = (jb + 1) * CHB; k < ib * CHB; k += 4) {
                     s0 = fma(A[k * LD + row], A[k * LD + c], s0);
                     s1 = fma(A[(k + 1) * LD + row], A[(k + 1) * LD + c], s1);
@@ -718,12 +719,12 @@ rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, c
                 double t = 0.0;
 #pragma unroll
                 for(int k = 0; k < CHB; ++k) {
-                    const double sk = __shfl_sync(hmask, sacc, (half << 4) | k);
+                    const double sk = __shfl_sync(0xffffffffu, sacc, (half << 4) | k);
                     const double lik = k < r ? A[row * LD + ib * CHB + k] : (k == r ? dinv[row] : 0.0);
                     t = fma(-lik, sk, t);
                 }
                 A[row * LD + c] = t;
-                __syncwarp(hmask);
+                __syncwarp();
             }
         }
     }

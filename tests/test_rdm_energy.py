@@ -78,3 +78,72 @@ def test_gpu_rdm_and_energy_match_the_oracle(name, D, chi):
             o.grow_all()
     finally:
         ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------- known answer: spin-2 AKLT state
+# Site tensor with aux legs = spin 1/2 (D = 2) and a spin-2 physical leg: Hom(1/2 x 1/2, 1/2 x 1/2 x 2) is ONE-dimensional (one sector, q = 3, one tree pair),
+# and its only element is the AKLT map (four virtual spins 1/2 symmetrised into spin 2, singlets on the bonds).  Two neighbouring sites share a singlet of two
+# of their eight virtual spins, so their total spin is at most 3 -- for ANY environment: <P_4> = 0 exactly, the AKLT Hamiltonian H = sum_bonds P_4 has energy 0.
+# A wrong leg pairing in computeRDM_h / computeRDM_v, in the CTM moves that build the environment, or in avg() breaks this.
+def _aklt(osym):
+    aux = obasis(osym, [((2,), 1)])
+    phys = obasis(osym, [((5,), 1)])
+    A = xo.Tensor(osym, [aux, aux], [aux, aux, phys])
+    assert A.plainSize() == 1, "the invariant space is one-dimensional"
+    A.data = np.ones(1)
+    return aux, phys, A
+
+
+def _spin_projector(osym, phys, q_total, data_of=None):
+    P = xo.Tensor(osym, [phys, phys], [phys, phys])
+    secs, rows, cols, offs = P.structure()
+    data = np.zeros(P.plainSize())
+    for q, r, c, o in zip(secs, rows, cols, offs):
+        assert r == 1 and c == 1
+        if q == (q_total,):
+            data[o] = 1.0
+    P.data = data
+    return P
+
+
+def test_oracle_aklt_bond_has_no_spin4_component():
+    osym = xo.Symmetry.from_spec(SPECS["SU2"])
+    aux, phys, A = _aklt(osym)
+    c = OCTM(A, 12)
+    for _ in range(4):
+        c.grow_all()
+    for rho in (c.computeRDM_h(), c.computeRDM_v()):
+        w = {S: oavg(rho, _spin_projector(osym, phys, 2 * S + 1)) for S in range(5)}
+        assert abs(sum(w.values()) - 1.0) < 1e-12                       # the projectors resolve the identity
+        assert all(v > -1e-12 for v in w.values())
+        assert abs(w[4]) < 1e-12, w                                     # E_AKLT = <P_4> = 0
+        assert w[0] > 1e-3 and w[3] > 1e-3                              # (the other sectors are populated)
+
+
+@pytest.mark.gpu
+def test_gpu_aklt_bond_has_no_spin4_component():
+    import xped_b200 as xb
+    ctx = xb.Context(SPECS["SU2"])
+    try:
+        osym = xo.Symmetry.from_spec(SPECS["SU2"])
+        _, ophys, _ = _aklt(osym)
+        a, p = ctx.basis([((2,), 1)]), ctx.basis([((5,), 1)])
+        A = ctx.tensor([a, a], [a, a, p])
+        assert A.plainSize() == 1
+        A.upload(np.ones(1))
+        g = xb.CTM(A, 12)
+        for _ in range(4):
+            g.grow_all()
+        for rho in (g.computeRDM_h(), g.computeRDM_v()):
+            w = {}
+            for S in range(5):
+                oP = _spin_projector(osym, ophys, 2 * S + 1)
+                gP = ctx.tensor([p, p], [p, p])
+                assert gP.structure() == oP.structure()
+                gP.upload(oP.data)
+                w[S] = xb.avg_two_site(rho, gP)
+            assert abs(sum(w.values()) - 1.0) < 1e-12
+            assert abs(w[4]) < 1e-12, w
+            assert w[0] > 1e-3 and w[3] > 1e-3
+    finally:
+        ctx.close()

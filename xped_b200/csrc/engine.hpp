@@ -376,6 +376,16 @@ private:
 };
 
 void check_cuda(cudaError_t e, const char* what);
+// cudaFuncSetAttribute is per DEVICE: true the first time the calling site runs on the current device (one bit per device ordinal in `mask`)
+inline bool first_use_on_current_device(unsigned long long& mask)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    const bool first = (mask & bit) == 0;
+    mask |= bit;
+    return first;
+}
 
 // ---- state interop (io.cpp)
 class Ctm;

@@ -185,11 +185,10 @@ gemm_grouped_kernel(const double* __restrict__ A, const double* __restrict__ B, 
 
 template <int BM> void launch_one(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, cudaStream_t s)
 {
-    static bool configured = false;
-    if(!configured) {
+    static unsigned long long configured = 0;
+    if(first_use_on_current_device(configured)) {
         check_cuda(cudaFuncSetAttribute(gemm_grouped_kernel<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg<BM>::SMEM_BYTES)),
                    "cudaFuncSetAttribute(gemm smem)");
-        configured = true;
     }
     gemm_grouped_kernel<BM><<<n_items, GEMM_THREADS, Cfg<BM>::SMEM_BYTES, s>>>(A, B, C, d_items);
     check_cuda(cudaGetLastError(), "gemm_grouped_kernel launch");

@@ -1144,8 +1144,8 @@ JacobiResult jacobi_all(Context& ctx, const JacobiInput& in, bool shifted, bool 
                                           static_cast<const int*>(d_sweep), round_idx, n_rounds_total), "svd_round_resident_kernel<8> launch");
     };
     {
-        static bool configured = false;
-        if(!configured) {
+        static unsigned long long configured = 0;
+        if(first_use_on_current_device(configured)) {
             const int max_dyn = 200 * 1024;
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<1, 20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<2, 40, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
@@ -1153,7 +1153,6 @@ JacobiResult jacobi_all(Context& ctx, const JacobiInput& in, bool shifted, bool 
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<8, 52, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<16, 28, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn), "svd smem attr");
             check_cuda(cudaFuncSetAttribute(svd_round_resident_kernel<16, 28, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "svd cluster attr");
-            configured = true;
         }
     }
     const int max_sweeps = 150;   // bail-out only

@@ -813,10 +813,9 @@ Selection svd_select(Context& ctx, const double* d_sigma, int n_total, const std
     P.guard = 8;
     P.pad = 0;
     const size_t smem = sizeof(double) * (N + 40) + sizeof(int) * (N + 3 * static_cast<size_t>(nsec) + 8);
-    static bool configured = false;
-    if(!configured) {
+    static unsigned long long configured = 0;
+    if(first_use_on_current_device(configured)) {
         check_cuda(cudaFuncSetAttribute(svd_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024), "svd select smem attr");
-        configured = true;
     }
     svd_select_kernel<<<1, SEL_THREADS, smem, s>>>(d_sigma, d_secs, d_res, d_normpart, P, N, R.d_perm, reinterpret_cast<SelHeader*>(d_out),
                                                   reinterpret_cast<int*>(d_out + sizeof(SelHeader)));
@@ -972,11 +971,10 @@ void rsvd_chol(RsvdPlan& P, double shift_rel, int bad_tag = 1)
     if(P.K0 > 32 && !old_form) {
         const int Kp = (P.K0 + CHB - 1) / CHB * CHB;
         const size_t smem = sizeof(double) * (static_cast<size_t>(Kp) * (Kp + 1) + CHB * Kp + CHB * (CHB + 1) + Kp);
-        static size_t configured = 0;   // NB: per process; the attribute is per device (every device of a process runs the same kernels with the same maximum)
-        if(smem > configured) {
-            const int most = 227 * 1024 - 512;   // the opt-in maximum covers static + dynamic shared memory (256 bytes are static)
+        static unsigned long long configured = 0;
+        if(first_use_on_current_device(configured)) {
+            const int most = 227 * 1024 - 512;   // the opt-in maximum covers static + dynamic shared memory
             check_cuda(cudaFuncSetAttribute(rsvd_chol_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, most), "chol smem attr");
-            configured = most;
         }
         rsvd_chol_blocked_kernel<<<P.n_proj, CHOL_THREADS, smem, s>>>(P.dG, P.dM, P.d_secs, P.d_proj, shift_rel, P.dDiag, P.d_bad, bad_tag);
         check_cuda(cudaGetLastError(), "rsvd_chol_blocked_kernel launch");

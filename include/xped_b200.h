@@ -176,8 +176,8 @@ int xb_layout_structure(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis
 int xb_permute_plan_stats(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n,
                           int64_t out[6]);
 /* census of the same plan: destination elements, source elements read (an element feeding k destination sub-blocks counts k times: SU(2) recoupling
- * sums), destination tasks, source records */
-int xb_permute_plan_census(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n, int64_t out[4]);
+ * sums), destination tasks, source records, tiles of the table-driven form (0: the plan does not have it), bytes of its offset tables */
+int xb_permute_plan_census(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n, int64_t out[6]);
 /* a shard: Tensor(domain, codomain) holding only the listed sectors, in that order, zero-initialised */
 int xb_tensor_create_sectors(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, const int* q, int n_sectors,
                              xb_tensor** out);

@@ -775,7 +775,7 @@ int xb_permute_plan_stats(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_bas
     });
 }
 
-int xb_permute_plan_census(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n, int64_t out[4])
+int xb_permute_plan_census(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n, int64_t out[6])
 {
     return guard([&] {
         need(ctx, "ctx");
@@ -788,6 +788,8 @@ int xb_permute_plan_census(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_ba
         out[1] = plan->src_reads;
         out[2] = plan->n_tasks;
         out[3] = plan->n_srcs;
+        out[4] = plan->n_ltiles;        // > 0: the plan has the table-driven form
+        out[5] = plan->lut_table_bytes;
     });
 }
 

@@ -116,6 +116,26 @@ struct BulkTask
     unsigned magic_wx, magic_wy, magic_nxh, magic_nyh;
 };
 
+// ---- table-driven form of a permute plan (SU(2) recoupling sums, odd extents: everything the bulk form cannot take).  Tiles are full boxes (tile extents
+// divide the leg extents); for every distinct tile shape (extents + strides of the destination and of all sources) the host tabulates, per tile element,
+// the source offset relative to the tile origin for every source, and, in destination order, the destination offset and the staging position.  The kernel
+// does no index arithmetic: a thread reads (table, data), accumulates its <= 8 elements over all sources in registers, stages them once, and the second
+// phase writes them out in destination order.
+constexpr int LUT_TILE_ELEMS = 2048;
+constexpr int LUT_THREADS = 256;
+constexpr int LUT_MAX_SRC = 32;   // sources of one task whose tile origins are staged at once
+struct LutTask
+{
+    long long dst_off;
+    int nleg, vol;            // merged legs (dst order), elements per tile
+    int src_begin, src_count; // PermSrc records (ALL sources, the first one included)
+    int soff_tab;             // int table: source k of tile element e at soff_tab + k * vol + e (e in source-0 order = staging order)
+    int doff_tab;             // int table: destination offset of element e' (destination order)
+    int spos_tab;             // unsigned short table: staging position of element e'
+    int pad_;
+    int w[PERM_MAXLEG], dstride[PERM_MAXLEG];
+};
+
 struct PermutePlan
 {
     LayoutPtr out;
@@ -129,6 +149,14 @@ struct PermutePlan
     PermTile* d_btiles = nullptr;
     int2* d_branges = nullptr;   // per CTA: (first tile, tile count), all tiles of one task
     int n_btiles = 0, n_branges = 0;
+    // table-driven form (nullptr if the plan does not qualify or has the bulk form)
+    LutTask* d_ltasks = nullptr;
+    PermSrc* d_lsrcs = nullptr;
+    PermTile* d_ltiles = nullptr;
+    int* d_lut_int = nullptr;
+    unsigned short* d_lut_pos = nullptr;
+    int n_ltiles = 0, ltiles_per_cta = 1;
+    long long lut_table_bytes = 0;
     bool identity_copy = false;   // permute<0, identity>: plain copy (Tensor.cpp:344)
     int64_t bytes = 0;            // algorithmic bytes: 8*(N_src + N_dst)
     int max_fan_in = 0;

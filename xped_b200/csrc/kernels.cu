@@ -390,6 +390,96 @@ permute_bulk_kernel(const double* __restrict__ src, double* __restrict__ dst, co
     asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // all stores complete before the shared memory is released
 }
 
+// ================================================================================================ permute, table-driven form
+// SU(2) recoupling sums and odd extents (no bulk form): the LSU form spends ~240 thread instructions per destination element on mixed-radix index
+// arithmetic (sub-blocks of ~40 k elements with extents like 4 x 3 x 8 x 3 x 3 x 3).  Here the host tabulates, per distinct tile shape, the offsets of
+// every tile element for every source and for the destination (LutTask, layout.cpp): a thread reads (table entry, source element) pairs, accumulates its
+// <= 8 tile elements over ALL sources in registers, stages them once, and the second phase stores them in destination order.  Three block-wide barriers
+// per tile, no barrier between sources.
+__global__ void __launch_bounds__(LUT_THREADS, 4)
+permute_lut_kernel(const double* __restrict__ src, double* __restrict__ dst, const LutTask* __restrict__ tasks, const PermSrc* __restrict__ srcs,
+                   const PermTile* __restrict__ tiles, int n_tiles, int tiles_per_cta, const int* __restrict__ tab_int, const unsigned short* __restrict__ tab_pos)
+{
+    constexpr int PER_THREAD = LUT_TILE_ELEMS / LUT_THREADS;   // 8
+    __shared__ LutTask T;
+    __shared__ double buf[LUT_TILE_ELEMS + LUT_TILE_ELEMS / 32 + 8];
+    __shared__ long long s_sbase[LUT_MAX_SRC];
+    __shared__ double s_coeff[LUT_MAX_SRC];
+    __shared__ long long s_dbase;
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * tiles_per_cta, t1 = min(n_tiles, t0 + tiles_per_cta);
+    int staged = -1;
+    for(int ti = t0; ti < t1; ++ti) {
+        const PermTile tile = tiles[ti];
+        if(tile.task != staged) {
+            __syncthreads();   // everybody is done with the previous task record
+            const int* g = reinterpret_cast<const int*>(tasks + tile.task);
+            int* sd = reinterpret_cast<int*>(&T);
+            for(int i = tid; i < static_cast<int>(sizeof(LutTask) / sizeof(int)); i += LUT_THREADS) sd[i] = g[i];
+            staged = tile.task;
+            __syncthreads();
+        }
+        const int vol = T.vol, nsrc = T.src_count;
+        double acc[PER_THREAD];
+#pragma unroll
+        for(int j = 0; j < PER_THREAD; ++j) acc[j] = 0.0;
+        for(int k0 = 0; k0 < nsrc; k0 += LUT_MAX_SRC) {
+            const int kn = min(LUT_MAX_SRC, nsrc - k0);
+            if(tid < kn) {   // tile origin inside source k0 + tid
+                const PermSrc* __restrict__ S = srcs + T.src_begin + k0 + tid;
+                long long o = S->off;
+                for(int l = 0; l < T.nleg; ++l) o += static_cast<long long>(tile.c[l] * T.w[l]) * S->sstride[l];
+                s_sbase[tid] = o;
+                s_coeff[tid] = S->coeff;
+            }
+            if(k0 == 0 && tid == LUT_THREADS - 1) {
+                long long o = T.dst_off;
+                for(int l = 0; l < T.nleg; ++l) o += static_cast<long long>(tile.c[l] * T.w[l]) * T.dstride[l];
+                s_dbase = o;
+            }
+            __syncthreads();
+            for(int k = 0; k < kn; ++k) {
+                const double* __restrict__ sp = src + s_sbase[k];
+                const double c = s_coeff[k];
+                const int* __restrict__ tab = tab_int + T.soff_tab + (k0 + k) * vol;
+                double v[PER_THREAD];
+#pragma unroll
+                for(int j = 0; j < PER_THREAD; ++j) {
+                    const int e = tid + j * LUT_THREADS;
+                    v[j] = e < vol ? __ldg(sp + __ldg(tab + e)) : 0.0;
+                }
+#pragma unroll
+                for(int j = 0; j < PER_THREAD; ++j) acc[j] = fma(c, v[j], acc[j]);
+            }
+            if(k0 + LUT_MAX_SRC < nsrc) __syncthreads();   // the origin slots are reused by the next batch of sources
+        }
+        if(nsrc == 0) {
+            if(tid == LUT_THREADS - 1) {
+                long long o = T.dst_off;
+                for(int l = 0; l < T.nleg; ++l) o += static_cast<long long>(tile.c[l] * T.w[l]) * T.dstride[l];
+                s_dbase = o;
+            }
+        }
+#pragma unroll
+        for(int j = 0; j < PER_THREAD; ++j) {
+            const int e = tid + j * LUT_THREADS;
+            if(e < vol) buf[e + (e >> 5)] = acc[j];
+        }
+        __syncthreads();
+        {
+            double* __restrict__ dp = dst + s_dbase;
+            const int* __restrict__ dtab = tab_int + T.doff_tab;
+            const unsigned short* __restrict__ ptab = tab_pos + T.spos_tab;
+#pragma unroll
+            for(int j = 0; j < PER_THREAD; ++j) {
+                const int e = tid + j * LUT_THREADS;
+                if(e < vol) dp[__ldg(dtab + e)] = buf[__ldg(ptab + e)];
+            }
+        }
+        __syncthreads();   // staging buffer and origin slots free for the next tile
+    }
+}
+
 static const PeerDelta NO_PEERS = {{0, 0, 0, 0, 0, 0, 0, 0}};
 
 static void launch_permute2_peers(const double* src, const double* src2, long long split, double* dst, const PermutePlan& plan, const PeerDelta& delta, cudaStream_t s)
@@ -418,6 +508,16 @@ void launch_permute_peers(const double* src, double* dst, const PermutePlan& pla
     if(plan.d_btasks && aligned && bulk_mode != 0 && (bulk_mode == 1 || plan.bytes >= (8ll << 20))) {
         permute_bulk_kernel<<<plan.n_branges, BULK_THREADS, 0, s>>>(src, dst, plan.d_btasks, plan.d_btiles, plan.d_branges, delta);
         check_cuda(cudaGetLastError(), "permute_bulk_kernel launch");
+        return;
+    }
+    // table-driven form (plans with recoupling sums / odd extents, no peers): XB_PERMUTE_LUT=0 / 1 forces never / whenever the plan has it
+    const char* lut_env = std::getenv("XB_PERMUTE_LUT");
+    const int lut_mode = lut_env ? std::atoi(lut_env) : -1;
+    if(plan.d_ltasks && lut_mode != 0 && (lut_mode == 1 || plan.bytes >= (4ll << 20))) {
+        const int tpc = plan.ltiles_per_cta < 1 ? 1 : plan.ltiles_per_cta;
+        const int grid = (plan.n_ltiles + tpc - 1) / tpc;
+        permute_lut_kernel<<<grid, LUT_THREADS, 0, s>>>(src, dst, plan.d_ltasks, plan.d_lsrcs, plan.d_ltiles, plan.n_ltiles, tpc, plan.d_lut_int, plan.d_lut_pos);
+        check_cuda(cudaGetLastError(), "permute_lut_kernel launch");
         return;
     }
     launch_permute2_peers(src, src, INT64_MAX, dst, plan, delta, s);

@@ -250,6 +250,11 @@ PermutePlan::~PermutePlan()
     if(d_srcs) cudaFree(d_srcs);
     if(d_tiles) cudaFree(d_tiles);
     if(d_btasks) cudaFree(d_btasks);
+    if(d_ltasks) cudaFree(d_ltasks);
+    if(d_lsrcs) cudaFree(d_lsrcs);
+    if(d_ltiles) cudaFree(d_ltiles);
+    if(d_lut_int) cudaFree(d_lut_int);
+    if(d_lut_pos) cudaFree(d_lut_pos);
     if(d_btiles) cudaFree(d_btiles);
     if(d_branges) cudaFree(d_branges);
 }
@@ -878,8 +883,187 @@ static bool lower_bulk_task(const PermTask& T, std::vector<BulkTask>& btasks, st
     return true;
 }
 
+// Table-driven lowering of one merged task (see LutTask).  `tabs` dedupes the tables by tile shape.
+struct LutBuild
+{
+    std::vector<LutTask> tasks;
+    std::vector<PermSrc> srcs;
+    std::vector<PermTile> tiles;
+    std::vector<int> tab_int;
+    std::vector<unsigned short> tab_pos;
+    std::unordered_map<std::string, std::array<int, 3>> tabs;   // shape key -> (soff_tab, doff_tab, spos_tab)
+    bool ok = true;
+};
+
+static int lut_staging_pos(int e) { return e + (e >> 5); }   // one padding slot per 32 elements: power-of-two strides of the write phase spread over the banks
+
+// one REGION of a task: a box of the sub-block whose extents are multiples of the tile extents `w` (origin `start`, extents `ext`)
+static void lower_lut_region(const PermTask& T, const PermSrc* src, const int* start, const int* ext, const int* w, LutBuild& B)
+{
+    if(!B.ok) return;
+    const int n = T.nleg;
+    LutTask L;
+    std::memset(&L, 0, sizeof(L));
+    L.dst_off = T.dst_off & PERM_OFF_MASK;
+    L.nleg = n;
+    L.src_begin = static_cast<int>(B.srcs.size());
+    L.src_count = T.src_count;
+    long long vol = 1, ntiles = 1;
+    for(int l = 0; l < n; ++l) {
+        L.w[l] = w[l];
+        L.dstride[l] = T.dstride[l];
+        L.dst_off += static_cast<long long>(start[l]) * T.dstride[l];
+        vol *= w[l];
+        ntiles *= ext[l] / w[l];
+    }
+    if(vol > LUT_TILE_ELEMS || ntiles > (1ll << 24)) {
+        B.ok = false;
+        return;
+    }
+    L.vol = static_cast<int>(vol);
+    for(int k = 0; k < T.src_count; ++k) {
+        PermSrc sk = src[k];
+        for(int l = 0; l < n; ++l) sk.off += static_cast<long long>(start[l]) * sk.sstride[l];
+        B.srcs.push_back(sk);
+    }
+    // source-0 order of the tile legs (staging order); a task without sources is a zero fill: destination order
+    int order[PERM_MAXLEG];
+    std::iota(order, order + n, 0);
+    if(T.src_count > 0) std::stable_sort(order, order + n, [&](int a, int b) { return src[0].sstride[a] < src[0].sstride[b]; });
+    std::string key;
+    key.reserve(64 + 40 * static_cast<size_t>(T.src_count + 1));
+    auto put = [&](int v) { key.append(reinterpret_cast<const char*>(&v), sizeof(int)); };
+    put(n);
+    for(int l = 0; l < n; ++l) {
+        put(L.w[l]);
+        put(L.dstride[l]);
+    }
+    put(T.src_count);
+    for(int k = 0; k < T.src_count; ++k)
+        for(int l = 0; l < n; ++l) put(src[k].sstride[l]);
+    auto hit = B.tabs.find(key);
+    if(hit == B.tabs.end()) {
+        const int V = L.vol;
+        const int soff_tab = static_cast<int>(B.tab_int.size());
+        B.tab_int.resize(B.tab_int.size() + static_cast<size_t>(V) * std::max(T.src_count, 0));
+        std::vector<int> sm_stride(n, 0);   // stride of leg l in the staging enumeration e
+        {
+            int m = 1;
+            for(int j = 0; j < n; ++j) {
+                sm_stride[order[j]] = m;
+                m *= L.w[order[j]];
+            }
+        }
+        int idx[PERM_MAXLEG];
+        for(int e = 0; e < V; ++e) {
+            int r = e;
+            for(int j = 0; j < n; ++j) {
+                idx[order[j]] = r % L.w[order[j]];
+                r /= L.w[order[j]];
+            }
+            for(int k = 0; k < T.src_count; ++k) {
+                long long o = 0;
+                for(int l = 0; l < n; ++l) o += static_cast<long long>(idx[l]) * src[k].sstride[l];
+                if(o > INT32_MAX) {
+                    B.ok = false;
+                    return;
+                }
+                B.tab_int[soff_tab + static_cast<size_t>(k) * V + e] = static_cast<int>(o);
+            }
+        }
+        const int doff_tab = static_cast<int>(B.tab_int.size());
+        B.tab_int.resize(B.tab_int.size() + V);
+        const int spos_tab = static_cast<int>(B.tab_pos.size());
+        B.tab_pos.resize(B.tab_pos.size() + V);
+        for(int e = 0; e < V; ++e) {   // destination order: leg 0 fastest
+            int r = e, se = 0;
+            long long o = 0;
+            for(int l = 0; l < n; ++l) {
+                const int i = r % L.w[l];
+                r /= L.w[l];
+                o += static_cast<long long>(i) * L.dstride[l];
+                se += i * sm_stride[l];
+            }
+            if(o > INT32_MAX) {
+                B.ok = false;
+                return;
+            }
+            B.tab_int[doff_tab + e] = static_cast<int>(o);
+            B.tab_pos[spos_tab + e] = static_cast<unsigned short>(lut_staging_pos(se));
+        }
+        if(B.tab_int.size() > (1ull << 30)) {
+            B.ok = false;
+            return;
+        }
+        hit = B.tabs.emplace(std::move(key), std::array<int, 3>{soff_tab, doff_tab, spos_tab}).first;
+    }
+    L.soff_tab = hit->second[0];
+    L.doff_tab = hit->second[1];
+    L.spos_tab = hit->second[2];
+    const int tid = static_cast<int>(B.tasks.size());
+    int nt[PERM_MAXLEG];
+    for(int l = 0; l < n; ++l) nt[l] = ext[l] / L.w[l];
+    for(long long x = 0; x < ntiles; ++x) {
+        PermTile pt;
+        std::memset(&pt, 0, sizeof(pt));
+        pt.task = tid;
+        long long r = x;
+        for(int l = 0; l < n; ++l) {
+            if(nt[l] > 65535) {
+                B.ok = false;
+                return;
+            }
+            pt.c[l] = static_cast<unsigned short>(r % nt[l]);
+            r /= nt[l];
+        }
+        B.tiles.push_back(pt);
+    }
+    B.tasks.push_back(L);
+}
+
+// A task = the box of its sub-block; along every leg the box is cut into a body of full tiles (extent w, the LSU form's choice) and a remainder (one tile
+// of the remaining extent): up to 2^legs regions of full tiles each, typically one to four (the chi multiplicities of a CTM run -- 73, 54, 17 -- have no
+// useful divisors, so "tile extents that divide the leg" is not an option).
+static void lower_lut_task(const PermTask& T, const PermSrc* src, LutBuild& B)
+{
+    if(!B.ok) return;
+    const int n = T.nleg;
+    int w[PERM_MAXLEG], body[PERM_MAXLEG], rem[PERM_MAXLEG];
+    int nvar = 1;
+    for(int l = 0; l < n; ++l) {
+        w[l] = std::max(1, std::min(T.w[l], T.dims[l]));
+        body[l] = T.dims[l] / w[l] * w[l];
+        rem[l] = T.dims[l] - body[l];
+        if(rem[l] > 0) nvar *= 2;
+    }
+    if(nvar > 64) {
+        B.ok = false;
+        return;
+    }
+    for(int mask = 0; mask < (1 << n); ++mask) {   // bit l: the remainder part of leg l
+        int start[PERM_MAXLEG], ext[PERM_MAXLEG], tw[PERM_MAXLEG];
+        bool valid = true;
+        for(int l = 0; l < n && valid; ++l) {
+            if(mask >> l & 1) {
+                if(rem[l] == 0) valid = false;
+                start[l] = body[l];
+                ext[l] = rem[l];
+                tw[l] = rem[l];
+            } else {
+                if(body[l] == 0) valid = false;
+                start[l] = 0;
+                ext[l] = body[l];
+                tw[l] = w[l];
+            }
+        }
+        if(valid) lower_lut_region(T, src, start, ext, tw, B);
+    }
+}
+
 static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const std::vector<int>& leg_of, int N, PermutePlan& planref)
 {
+    LutBuild lut;
+    bool any_peer = false;
     PermutePlan* plan = &planref;
     const int sm_count = ctx.sm_count;
     std::vector<PermTask> h_tasks;
@@ -985,6 +1169,8 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
         }
         h_tasks.push_back(T);
         if(bulk_ok) bulk_ok = lower_bulk_task(T, h_btasks, h_btiles);
+        if(t.peer != 0) any_peer = true;
+        lower_lut_task(T, h_srcs.data() + T.src_begin, lut);
     }
     plan->n_tasks = static_cast<int>(h_tasks.size());
     plan->n_srcs = static_cast<int>(h_srcs.size());
@@ -992,6 +1178,17 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
     // consecutive tiles (mostly of the same task) per CTA: amortises the task staging, keeps >= 16 CTAs per SM in the grid
     plan->tiles_per_cta = std::max(1, std::min(8, plan->n_tiles / (sm_count * 16)));
     if(bulk_ok && !h_btiles.empty()) plan->n_btiles = static_cast<int>(h_btiles.size());   // also in planning-only contexts (host-logic tests)
+    {   // table-driven form: for plans without the bulk form whose tables stay small next to the tensor (pushed permutes keep the other two forms)
+        const long long table_bytes = static_cast<long long>(lut.tab_int.size()) * 4 + static_cast<long long>(lut.tab_pos.size()) * 2;
+        static const bool no_lut = std::getenv("XB_PERMUTE_LUT") != nullptr && std::atoi(std::getenv("XB_PERMUTE_LUT")) == 0;
+        long long lut_bytes_ref = 0;   // (plan->bytes is set by the caller after lowering: use the element count of the tiles)
+        for(const PermTile& pt : lut.tiles) lut_bytes_ref += 16ll * lut.tasks[pt.task].vol;
+        if(!no_lut && lut.ok && !any_peer && !(bulk_ok && !h_btiles.empty()) && !lut.tiles.empty() && table_bytes <= std::max<long long>(lut_bytes_ref / 2, 1 << 20)) {
+            plan->n_ltiles = static_cast<int>(lut.tiles.size());
+            plan->ltiles_per_cta = std::max(1, std::min(8, plan->n_ltiles / (sm_count * 16)));
+            plan->lut_table_bytes = table_bytes;
+        }
+    }
     if(ctx.planning_only()) return;
     if(plan->n_tasks) {
         check_cuda(cudaMalloc(&plan->d_tasks, h_tasks.size() * sizeof(PermTask)), "cudaMalloc plan tasks");
@@ -1021,6 +1218,18 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
     if(plan->n_srcs) {
         check_cuda(cudaMalloc(&plan->d_srcs, h_srcs.size() * sizeof(PermSrc)), "cudaMalloc plan sources");
         check_cuda(cudaMemcpy(plan->d_srcs, h_srcs.data(), h_srcs.size() * sizeof(PermSrc), cudaMemcpyHostToDevice), "upload plan sources");
+    }
+    if(plan->n_ltiles > 0) {
+        auto up = [&](auto** d, const auto& v, const char* what) {
+            using E = typename std::decay<decltype(v)>::type::value_type;
+            check_cuda(cudaMalloc(reinterpret_cast<void**>(d), std::max<size_t>(v.size(), 1) * sizeof(E)), what);
+            if(!v.empty()) check_cuda(cudaMemcpy(*d, v.data(), v.size() * sizeof(E), cudaMemcpyHostToDevice), what);
+        };
+        up(&plan->d_ltasks, lut.tasks, "upload table-driven tasks");
+        up(&plan->d_lsrcs, lut.srcs, "upload table-driven sources");
+        up(&plan->d_ltiles, lut.tiles, "upload table-driven tiles");
+        up(&plan->d_lut_int, lut.tab_int, "upload offset tables");
+        up(&plan->d_lut_pos, lut.tab_pos, "upload staging tables");
     }
 }
 

@@ -123,18 +123,17 @@ struct BulkTask
 // phase writes them out in destination order.
 constexpr int LUT_TILE_ELEMS = 2048;
 constexpr int LUT_THREADS = 256;
-constexpr int LUT_MAX_SRC = 32;   // sources of one task whose tile origins are staged at once
 struct LutTask
 {
-    long long dst_off;
-    int nleg, vol;            // merged legs (dst order), elements per tile
-    int src_begin, src_count; // PermSrc records (ALL sources, the first one included)
+    int vol, src_count;       // elements per tile, fan-in
     int soff_tab;             // int table: source k of tile element e at soff_tab + k * vol + e (e in source-0 order = staging order)
     int doff_tab;             // int table: destination offset of element e' (destination order)
     int spos_tab;             // unsigned short table: staging position of element e'
+    int first_tile;           // index of the task's first tile
+    int tsrc_begin;           // LutTileSrc records of the task's tiles: tsrc_begin + (tile - first_tile) * src_count + k
     int pad_;
-    int w[PERM_MAXLEG], dstride[PERM_MAXLEG];
 };
+struct LutTileSrc { long long off; double coeff; };   // origin of one tile inside one source, and that source's recoupling coefficient
 
 struct PermutePlan
 {
@@ -151,8 +150,9 @@ struct PermutePlan
     int n_btiles = 0, n_branges = 0;
     // table-driven form (nullptr if the plan does not qualify or has the bulk form)
     LutTask* d_ltasks = nullptr;
-    PermSrc* d_lsrcs = nullptr;
-    PermTile* d_ltiles = nullptr;
+    LutTileSrc* d_ltsrc = nullptr;      // per (tile, source)
+    int* d_ltile_task = nullptr;        // per tile
+    long long* d_ltile_dst = nullptr;   // per tile: origin in the destination
     int* d_lut_int = nullptr;
     unsigned short* d_lut_pos = nullptr;
     int n_ltiles = 0, ltiles_per_cta = 1;

@@ -397,86 +397,74 @@ permute_bulk_kernel(const double* __restrict__ src, double* __restrict__ dst, co
 // <= 8 tile elements over ALL sources in registers, stages them once, and the second phase stores them in destination order.  Three block-wide barriers
 // per tile, no barrier between sources.
 __global__ void __launch_bounds__(LUT_THREADS, 4)
-permute_lut_kernel(const double* __restrict__ src, double* __restrict__ dst, const LutTask* __restrict__ tasks, const PermSrc* __restrict__ srcs,
-                   const PermTile* __restrict__ tiles, int n_tiles, int tiles_per_cta, const int* __restrict__ tab_int, const unsigned short* __restrict__ tab_pos)
+permute_lut_kernel(const double* __restrict__ src, double* __restrict__ dst, const LutTask* __restrict__ tasks, const LutTileSrc* __restrict__ tsrc,
+                   const int* __restrict__ tile_task, const long long* __restrict__ tile_dst, int n_tiles, int tiles_per_cta, const int* __restrict__ tab_int,
+                   const unsigned short* __restrict__ tab_pos)
 {
     constexpr int PER_THREAD = LUT_TILE_ELEMS / LUT_THREADS;   // 8
-    __shared__ LutTask T;
-    __shared__ double buf[LUT_TILE_ELEMS + LUT_TILE_ELEMS / 32 + 8];
-    __shared__ long long s_sbase[LUT_MAX_SRC];
-    __shared__ double s_coeff[LUT_MAX_SRC];
-    __shared__ long long s_dbase;
+    constexpr int BUF = LUT_TILE_ELEMS + LUT_TILE_ELEMS / 32 + 8;
+    __shared__ double buf[2][BUF];   // two staging buffers: ONE block-wide barrier per tile
     const int tid = threadIdx.x;
     const int t0 = blockIdx.x * tiles_per_cta, t1 = min(n_tiles, t0 + tiles_per_cta);
-    int staged = -1;
     for(int ti = t0; ti < t1; ++ti) {
-        const PermTile tile = tiles[ti];
-        if(tile.task != staged) {
-            __syncthreads();   // everybody is done with the previous task record
-            const int* g = reinterpret_cast<const int*>(tasks + tile.task);
-            int* sd = reinterpret_cast<int*>(&T);
-            for(int i = tid; i < static_cast<int>(sizeof(LutTask) / sizeof(int)); i += LUT_THREADS) sd[i] = g[i];
-            staged = tile.task;
-            __syncthreads();
-        }
-        const int vol = T.vol, nsrc = T.src_count;
+        // task record, tile origins and coefficients are uniform across the CTA: broadcast loads, no staging
+        const LutTask* __restrict__ T = tasks + __ldg(tile_task + ti);
+        const int vol = __ldg(&T->vol), nsrc = __ldg(&T->src_count);
+        const LutTileSrc* __restrict__ ts = tsrc + __ldg(&T->tsrc_begin) + (ti - __ldg(&T->first_tile)) * nsrc;
+        const int* __restrict__ tab = tab_int + __ldg(&T->soff_tab);
         double acc[PER_THREAD];
+        int o_cur[PER_THREAD];
 #pragma unroll
-        for(int j = 0; j < PER_THREAD; ++j) acc[j] = 0.0;
-        for(int k0 = 0; k0 < nsrc; k0 += LUT_MAX_SRC) {
-            const int kn = min(LUT_MAX_SRC, nsrc - k0);
-            if(tid < kn) {   // tile origin inside source k0 + tid
-                const PermSrc* __restrict__ S = srcs + T.src_begin + k0 + tid;
-                long long o = S->off;
-                for(int l = 0; l < T.nleg; ++l) o += static_cast<long long>(tile.c[l] * T.w[l]) * S->sstride[l];
-                s_sbase[tid] = o;
-                s_coeff[tid] = S->coeff;
-            }
-            if(k0 == 0 && tid == LUT_THREADS - 1) {
-                long long o = T.dst_off;
-                for(int l = 0; l < T.nleg; ++l) o += static_cast<long long>(tile.c[l] * T.w[l]) * T.dstride[l];
-                s_dbase = o;
-            }
-            __syncthreads();
-            for(int k = 0; k < kn; ++k) {
-                const double* __restrict__ sp = src + s_sbase[k];
-                const double c = s_coeff[k];
-                const int* __restrict__ tab = tab_int + T.soff_tab + (k0 + k) * vol;
-                double v[PER_THREAD];
-#pragma unroll
-                for(int j = 0; j < PER_THREAD; ++j) {
-                    const int e = tid + j * LUT_THREADS;
-                    v[j] = e < vol ? __ldg(sp + __ldg(tab + e)) : 0.0;
-                }
-#pragma unroll
-                for(int j = 0; j < PER_THREAD; ++j) acc[j] = fma(c, v[j], acc[j]);
-            }
-            if(k0 + LUT_MAX_SRC < nsrc) __syncthreads();   // the origin slots are reused by the next batch of sources
+        for(int j = 0; j < PER_THREAD; ++j) {
+            acc[j] = 0.0;
+            const int e = tid + j * LUT_THREADS;
+            o_cur[j] = (nsrc > 0 && e < vol) ? __ldg(tab + e) : 0;
         }
-        if(nsrc == 0) {
-            if(tid == LUT_THREADS - 1) {
-                long long o = T.dst_off;
-                for(int l = 0; l < T.nleg; ++l) o += static_cast<long long>(tile.c[l] * T.w[l]) * T.dstride[l];
-                s_dbase = o;
+        for(int k = 0; k < nsrc; ++k) {
+            const double* __restrict__ sp = src + __ldg(&ts[k].off);
+            const double c = __ldg(&ts[k].coeff);
+            double v[PER_THREAD];
+            int o_nxt[PER_THREAD];
+#pragma unroll
+            for(int j = 0; j < PER_THREAD; ++j) {
+                const int e = tid + j * LUT_THREADS;
+                v[j] = e < vol ? __ldg(sp + o_cur[j]) : 0.0;
             }
+#pragma unroll
+            for(int j = 0; j < PER_THREAD; ++j) {   // offsets of the next source are in flight together with this source's data
+                const int e = tid + j * LUT_THREADS;
+                o_nxt[j] = (k + 1 < nsrc && e < vol) ? __ldg(tab + (k + 1) * vol + e) : 0;
+            }
+#pragma unroll
+            for(int j = 0; j < PER_THREAD; ++j) {
+                acc[j] = fma(c, v[j], acc[j]);
+                o_cur[j] = o_nxt[j];
+            }
+        }
+        double* __restrict__ sb = buf[ti & 1];
+        const int* __restrict__ dtab = tab_int + __ldg(&T->doff_tab);
+        const unsigned short* __restrict__ ptab = tab_pos + __ldg(&T->spos_tab);
+        int d_off[PER_THREAD];
+        int d_pos[PER_THREAD];
+#pragma unroll
+        for(int j = 0; j < PER_THREAD; ++j) {   // tables of the write phase: issued before the barrier
+            const int e = tid + j * LUT_THREADS;
+            d_off[j] = e < vol ? __ldg(dtab + e) : 0;
+            d_pos[j] = e < vol ? static_cast<int>(__ldg(ptab + e)) : 0;
         }
 #pragma unroll
         for(int j = 0; j < PER_THREAD; ++j) {
             const int e = tid + j * LUT_THREADS;
-            if(e < vol) buf[e + (e >> 5)] = acc[j];
+            if(e < vol) sb[e + (e >> 5)] = acc[j];
         }
         __syncthreads();
-        {
-            double* __restrict__ dp = dst + s_dbase;
-            const int* __restrict__ dtab = tab_int + T.doff_tab;
-            const unsigned short* __restrict__ ptab = tab_pos + T.spos_tab;
+        double* __restrict__ dp = dst + __ldg(tile_dst + ti);
 #pragma unroll
-            for(int j = 0; j < PER_THREAD; ++j) {
-                const int e = tid + j * LUT_THREADS;
-                if(e < vol) dp[__ldg(dtab + e)] = buf[__ldg(ptab + e)];
-            }
+        for(int j = 0; j < PER_THREAD; ++j) {
+            const int e = tid + j * LUT_THREADS;
+            if(e < vol) dp[d_off[j]] = sb[d_pos[j]];
         }
-        __syncthreads();   // staging buffer and origin slots free for the next tile
+        // no second barrier: the next tile stages into the other buffer, and a thread reaches the tile after that only through the next barrier
     }
 }
 
@@ -516,7 +504,8 @@ void launch_permute_peers(const double* src, double* dst, const PermutePlan& pla
     if(plan.d_ltasks && lut_mode != 0 && (lut_mode == 1 || plan.bytes >= (4ll << 20))) {
         const int tpc = plan.ltiles_per_cta < 1 ? 1 : plan.ltiles_per_cta;
         const int grid = (plan.n_ltiles + tpc - 1) / tpc;
-        permute_lut_kernel<<<grid, LUT_THREADS, 0, s>>>(src, dst, plan.d_ltasks, plan.d_lsrcs, plan.d_ltiles, plan.n_ltiles, tpc, plan.d_lut_int, plan.d_lut_pos);
+        permute_lut_kernel<<<grid, LUT_THREADS, 0, s>>>(src, dst, plan.d_ltasks, plan.d_ltsrc, plan.d_ltile_task, plan.d_ltile_dst, plan.n_ltiles, tpc, plan.d_lut_int,
+                                                        plan.d_lut_pos);
         check_cuda(cudaGetLastError(), "permute_lut_kernel launch");
         return;
     }

@@ -251,8 +251,9 @@ PermutePlan::~PermutePlan()
     if(d_tiles) cudaFree(d_tiles);
     if(d_btasks) cudaFree(d_btasks);
     if(d_ltasks) cudaFree(d_ltasks);
-    if(d_lsrcs) cudaFree(d_lsrcs);
-    if(d_ltiles) cudaFree(d_ltiles);
+    if(d_ltsrc) cudaFree(d_ltsrc);
+    if(d_ltile_task) cudaFree(d_ltile_task);
+    if(d_ltile_dst) cudaFree(d_ltile_dst);
     if(d_lut_int) cudaFree(d_lut_int);
     if(d_lut_pos) cudaFree(d_lut_pos);
     if(d_btiles) cudaFree(d_btiles);
@@ -887,8 +888,9 @@ static bool lower_bulk_task(const PermTask& T, std::vector<BulkTask>& btasks, st
 struct LutBuild
 {
     std::vector<LutTask> tasks;
-    std::vector<PermSrc> srcs;
-    std::vector<PermTile> tiles;
+    std::vector<LutTileSrc> tsrc;
+    std::vector<int> tile_task;
+    std::vector<long long> tile_dst;
     std::vector<int> tab_int;
     std::vector<unsigned short> tab_pos;
     std::unordered_map<std::string, std::array<int, 3>> tabs;   // shape key -> (soff_tab, doff_tab, spos_tab)
@@ -902,17 +904,16 @@ static void lower_lut_region(const PermTask& T, const PermSrc* src, const int* s
 {
     if(!B.ok) return;
     const int n = T.nleg;
-    LutTask L;
-    std::memset(&L, 0, sizeof(L));
-    L.dst_off = T.dst_off & PERM_OFF_MASK;
-    L.nleg = n;
-    L.src_begin = static_cast<int>(B.srcs.size());
-    L.src_count = T.src_count;
+    struct { int w[PERM_MAXLEG], dstride[PERM_MAXLEG]; int vol; } L;
+    LutTask LT;
+    std::memset(&LT, 0, sizeof(LT));
+    LT.src_count = T.src_count;
+    long long region_dst = T.dst_off & PERM_OFF_MASK;
     long long vol = 1, ntiles = 1;
     for(int l = 0; l < n; ++l) {
         L.w[l] = w[l];
         L.dstride[l] = T.dstride[l];
-        L.dst_off += static_cast<long long>(start[l]) * T.dstride[l];
+        region_dst += static_cast<long long>(start[l]) * T.dstride[l];
         vol *= w[l];
         ntiles *= ext[l] / w[l];
     }
@@ -921,10 +922,11 @@ static void lower_lut_region(const PermTask& T, const PermSrc* src, const int* s
         return;
     }
     L.vol = static_cast<int>(vol);
+    LT.vol = L.vol;
+    std::vector<long long> region_src(T.src_count);
     for(int k = 0; k < T.src_count; ++k) {
-        PermSrc sk = src[k];
-        for(int l = 0; l < n; ++l) sk.off += static_cast<long long>(start[l]) * sk.sstride[l];
-        B.srcs.push_back(sk);
+        region_src[k] = src[k].off;
+        for(int l = 0; l < n; ++l) region_src[k] += static_cast<long long>(start[l]) * src[k].sstride[l];
     }
     // source-0 order of the tile legs (staging order); a task without sources is a zero fill: destination order
     int order[PERM_MAXLEG];
@@ -997,28 +999,32 @@ static void lower_lut_region(const PermTask& T, const PermSrc* src, const int* s
         }
         hit = B.tabs.emplace(std::move(key), std::array<int, 3>{soff_tab, doff_tab, spos_tab}).first;
     }
-    L.soff_tab = hit->second[0];
-    L.doff_tab = hit->second[1];
-    L.spos_tab = hit->second[2];
+    LT.soff_tab = hit->second[0];
+    LT.doff_tab = hit->second[1];
+    LT.spos_tab = hit->second[2];
+    LT.first_tile = static_cast<int>(B.tile_task.size());
+    LT.tsrc_begin = static_cast<int>(B.tsrc.size());
     const int tid = static_cast<int>(B.tasks.size());
     int nt[PERM_MAXLEG];
     for(int l = 0; l < n; ++l) nt[l] = ext[l] / L.w[l];
-    for(long long x = 0; x < ntiles; ++x) {
-        PermTile pt;
-        std::memset(&pt, 0, sizeof(pt));
-        pt.task = tid;
-        long long r = x;
+    for(long long x = 0; x < ntiles; ++x) {   // tile origins inside the destination and inside every source: no index arithmetic left for the device
+        long long r = x, od = region_dst;
+        std::vector<long long> os(region_src);
         for(int l = 0; l < n; ++l) {
-            if(nt[l] > 65535) {
-                B.ok = false;
-                return;
-            }
-            pt.c[l] = static_cast<unsigned short>(r % nt[l]);
+            const long long c = (r % nt[l]) * L.w[l];
             r /= nt[l];
+            od += c * L.dstride[l];
+            for(int k = 0; k < T.src_count; ++k) os[k] += c * src[k].sstride[l];
         }
-        B.tiles.push_back(pt);
+        B.tile_task.push_back(tid);
+        B.tile_dst.push_back(od);
+        for(int k = 0; k < T.src_count; ++k) B.tsrc.push_back({os[k], src[k].coeff});
     }
-    B.tasks.push_back(L);
+    if(B.tsrc.size() > (1ull << 30) || B.tile_task.size() > (1ull << 30)) {
+        B.ok = false;
+        return;
+    }
+    B.tasks.push_back(LT);
 }
 
 // A task = the box of its sub-block; along every leg the box is cut into a body of full tiles (extent w, the LSU form's choice) and a remainder (one tile
@@ -1182,11 +1188,12 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
         const long long table_bytes = static_cast<long long>(lut.tab_int.size()) * 4 + static_cast<long long>(lut.tab_pos.size()) * 2;
         static const bool no_lut = std::getenv("XB_PERMUTE_LUT") != nullptr && std::atoi(std::getenv("XB_PERMUTE_LUT")) == 0;
         long long lut_bytes_ref = 0;   // (plan->bytes is set by the caller after lowering: use the element count of the tiles)
-        for(const PermTile& pt : lut.tiles) lut_bytes_ref += 16ll * lut.tasks[pt.task].vol;
-        if(!no_lut && lut.ok && !any_peer && !(bulk_ok && !h_btiles.empty()) && !lut.tiles.empty() && table_bytes <= std::max<long long>(lut_bytes_ref / 2, 1 << 20)) {
-            plan->n_ltiles = static_cast<int>(lut.tiles.size());
+        for(int t : lut.tile_task) lut_bytes_ref += 16ll * lut.tasks[t].vol;
+        const long long table_bytes_all = table_bytes + static_cast<long long>(lut.tsrc.size()) * 16 + static_cast<long long>(lut.tile_task.size()) * 12;
+        if(!no_lut && lut.ok && !any_peer && !(bulk_ok && !h_btiles.empty()) && !lut.tile_task.empty() && table_bytes_all <= std::max<long long>(lut_bytes_ref / 2, 1 << 20)) {
+            plan->n_ltiles = static_cast<int>(lut.tile_task.size());
             plan->ltiles_per_cta = std::max(1, std::min(8, plan->n_ltiles / (sm_count * 16)));
-            plan->lut_table_bytes = table_bytes;
+            plan->lut_table_bytes = table_bytes_all;
         }
     }
     if(ctx.planning_only()) return;
@@ -1226,8 +1233,9 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
             if(!v.empty()) check_cuda(cudaMemcpy(*d, v.data(), v.size() * sizeof(E), cudaMemcpyHostToDevice), what);
         };
         up(&plan->d_ltasks, lut.tasks, "upload table-driven tasks");
-        up(&plan->d_lsrcs, lut.srcs, "upload table-driven sources");
-        up(&plan->d_ltiles, lut.tiles, "upload table-driven tiles");
+        up(&plan->d_ltsrc, lut.tsrc, "upload table-driven tile origins");
+        up(&plan->d_ltile_task, lut.tile_task, "upload table-driven tiles");
+        up(&plan->d_ltile_dst, lut.tile_dst, "upload table-driven tile destinations");
         up(&plan->d_lut_int, lut.tab_int, "upload offset tables");
         up(&plan->d_lut_pos, lut.tab_pos, "upload staging tables");
     }

@@ -498,10 +498,10 @@ void launch_permute_peers(const double* src, double* dst, const PermutePlan& pla
         check_cuda(cudaGetLastError(), "permute_bulk_kernel launch");
         return;
     }
-    // table-driven form (plans with recoupling sums / odd extents, no peers): XB_PERMUTE_LUT=0 / 1 forces never / whenever the plan has it
+    // table-driven form (plans with recoupling sums / odd extents, no peers): XB_PERMUTE_LUT=0 switches it off
     const char* lut_env = std::getenv("XB_PERMUTE_LUT");
     const int lut_mode = lut_env ? std::atoi(lut_env) : -1;
-    if(plan.d_ltasks && lut_mode != 0 && (lut_mode == 1 || plan.bytes >= (4ll << 20))) {
+    if(plan.d_ltasks && lut_mode != 0) {   // (no size threshold: also ahead of the LSU form on the launch-bound tensors of a D=4 CTM step, 1.12 vs 1.24 ms)
         const int tpc = plan.ltiles_per_cta < 1 ? 1 : plan.ltiles_per_cta;
         const int grid = (plan.n_ltiles + tpc - 1) / tpc;
         permute_lut_kernel<<<grid, LUT_THREADS, 0, s>>>(src, dst, plan.d_ltasks, plan.d_ltsrc, plan.d_ltile_task, plan.d_ltile_dst, plan.n_ltiles, tpc, plan.d_lut_int,

@@ -1079,7 +1079,23 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
     std::vector<PermTile> h_btiles;
     bool bulk_ok = true;
     h_tasks.reserve(tasks.size());
-    for(const DstTask& t : tasks) {
+    // Plans with recoupling sums read every source sub-block from several tasks: process the tasks in the order of their first source (instead of the
+    // storage order of the destination) so that the re-reads of a source are close in time and hit the L2 (the W3 corner is larger than the L2).
+    std::vector<int> task_order(tasks.size());
+    std::iota(task_order.begin(), task_order.end(), 0);
+    {
+        bool sums = false;
+        for(const DstTask& t : tasks)
+            if(t.srcs.size() > 1) sums = true;
+        static const bool no_sort = std::getenv("XB_PLAN_NOSORT") != nullptr;
+        if(sums && !no_sort)
+            std::stable_sort(task_order.begin(), task_order.end(), [&](int a, int b) {
+                const long long oa = tasks[a].srcs.empty() ? -1 : tasks[a].srcs[0].src.base, ob = tasks[b].srcs.empty() ? -1 : tasks[b].srcs[0].src.base;
+                return oa < ob;
+            });
+    }
+    for(int task_index : task_order) {
+        const DstTask& t = tasks[task_index];
         if(t.dst.nlegs != N) throw std::logic_error("permute plan: leg count mismatch");
         // legs in dst order with their per-source strides; drop extent-1 legs
         int n = 0;

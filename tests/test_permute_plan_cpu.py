@@ -47,3 +47,29 @@ def test_su2_plans_sum_over_recoupled_trees():
     s = permute_plan_stats(ctx, [B, B], [B, B], 1, (2, 0, 3, 1))
     assert s["max_fan_in"] > 1 and s["bulk_tiles"] == 0          # recoupling sums: LSU form with fan-in
     ctx.close()
+
+
+def test_su2_plans_get_the_table_driven_form():
+    """plans with recoupling sums (no bulk form) carry the table-driven form: full tiles + remainder regions cover every destination element once, the
+    tables stay small next to the tensor; Abelian plans with the bulk form do not build it"""
+    import ctypes as C
+    from xped_b200.sharded import _handles, _ints
+    from xped_b200.capi import check
+
+    def census(ctx, dom, cod, shift, p):
+        out = (C.c_int64 * 6)()
+        check(ctx.lib.xb_permute_plan_census(ctx.h, _handles(dom), len(dom), _handles(cod), len(cod), shift, _ints(p), len(p), out))
+        return dict(dst=out[0], reads=out[1], tasks=out[2], srcs=out[3], lut_tiles=out[4], lut_bytes=out[5])
+    ctx = _ctx("SU2")
+    a, e = ctx.basis([(1, 3), (2, 3)]), ctx.basis([(1, 17), (2, 31), (3, 37), (4, 29), (5, 18), (6, 9), (7, 3)])   # multiplicities without useful divisors
+    for shift, p in [(-1, (0, 2, 3, 5, 1, 4)), (1, (0, 3, 5, 1, 2, 4)), (0, (1, 0, 2, 4, 3, 5))]:
+        c = census(ctx, [e, a, a], [e, a, a], shift, p)
+        assert c["lut_tiles"] > 0
+        assert c["dst"] / c["lut_tiles"] > 1000          # tiles stay near the 2048-element budget in spite of the odd extents
+        assert c["lut_bytes"] < 0.1 * 8 * c["dst"]       # deduplicated tables
+    ctx.close()
+    ctx = _ctx("U1")
+    B = ctx.basis([(q, 8) for q in range(-2, 3)])
+    c = census(ctx, [B, B], [B, B], 0, (1, 0, 2, 3))
+    assert c["lut_tiles"] == 0                           # bulk form available
+    ctx.close()

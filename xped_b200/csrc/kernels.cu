@@ -6,7 +6,8 @@
 //                      HBM-bound: every source element is read once, every destination element written once.
 //                      Bulk form: tiles move through shared memory with the TMA engine's 1-D cp.async.bulk (one
 //                      operation per contiguous run; needs 16-byte aligned runs of even length, fan-in 1);
-//                      LSU form for everything else (SU(2) fan-in > 1, odd run lengths, small tensors, sharded gather).
+//                      table-driven form (permute_lut_kernel) for SU(2) recoupling sums / odd run lengths: all index arithmetic tabulated at plan time;
+//                      LSU form for what is left (sharded pack / gather, plans whose tables would be large next to the tensor).
 //                      Tensor maps (cp.async.bulk.tensor) are not used: sub-block origins and leading dimensions are
 //                      arbitrary multiples of 8 bytes and change with every buffer.
 //  (gemm.cu)           gemm_grouped_kernel: ragged per-sector C_q += op(A_q) * op(B_q) (src/Core/TensorBase.cpp:262-279) on

@@ -157,6 +157,8 @@ struct PermutePlan
     unsigned short* d_lut_pos = nullptr;
     int n_ltiles = 0, ltiles_per_cta = 1;
     long long lut_table_bytes = 0;
+    int uses = 0;              // cache hits (the table-driven form is built when a plan is used for the second time: ~30-50 ms of host work per plan)
+    bool lut_tried = false;
     bool identity_copy = false;   // permute<0, identity>: plain copy (Tensor.cpp:344)
     int64_t bytes = 0;            // algorithmic bytes: 8*(N_src + N_dst)
     int max_fan_in = 0;

@@ -1007,18 +1007,26 @@ static void lower_lut_region(const PermTask& T, const PermSrc* src, const int* s
     const int tid = static_cast<int>(B.tasks.size());
     int nt[PERM_MAXLEG];
     for(int l = 0; l < n; ++l) nt[l] = ext[l] / L.w[l];
-    for(long long x = 0; x < ntiles; ++x) {   // tile origins inside the destination and inside every source: no index arithmetic left for the device
-        long long r = x, od = region_dst;
-        std::vector<long long> os(region_src);
-        for(int l = 0; l < n; ++l) {
-            const long long c = (r % nt[l]) * L.w[l];
-            r /= nt[l];
-            od += c * L.dstride[l];
-            for(int k = 0; k < T.src_count; ++k) os[k] += c * src[k].sstride[l];
+    // tile origins inside the destination and inside every source: no index arithmetic left for the device
+    B.tile_task.insert(B.tile_task.end(), static_cast<size_t>(ntiles), tid);
+    const size_t d0 = B.tile_dst.size(), s0 = B.tsrc.size();
+    B.tile_dst.resize(d0 + static_cast<size_t>(ntiles));
+    B.tsrc.resize(s0 + static_cast<size_t>(ntiles) * T.src_count);
+    int c[PERM_MAXLEG] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for(long long x = 0; x < ntiles; ++x) {   // odometer over the tile coordinates
+        long long od = region_dst;
+        for(int l = 0; l < n; ++l) od += static_cast<long long>(c[l]) * L.w[l] * L.dstride[l];
+        B.tile_dst[d0 + x] = od;
+        LutTileSrc* ts = B.tsrc.data() + s0 + static_cast<size_t>(x) * T.src_count;
+        for(int k = 0; k < T.src_count; ++k) {
+            long long os = region_src[k];
+            for(int l = 0; l < n; ++l) os += static_cast<long long>(c[l]) * L.w[l] * src[k].sstride[l];
+            ts[k] = {os, src[k].coeff};
         }
-        B.tile_task.push_back(tid);
-        B.tile_dst.push_back(od);
-        for(int k = 0; k < T.src_count; ++k) B.tsrc.push_back({os[k], src[k].coeff});
+        for(int l = 0; l < n; ++l) {
+            if(++c[l] < nt[l]) break;
+            c[l] = 0;
+        }
     }
     if(B.tsrc.size() > (1ull << 30) || B.tile_task.size() > (1ull << 30)) {
         B.ok = false;
@@ -1066,9 +1074,10 @@ static void lower_lut_task(const PermTask& T, const PermSrc* src, LutBuild& B)
     }
 }
 
-static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const std::vector<int>& leg_of, int N, PermutePlan& planref)
+static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const std::vector<int>& leg_of, int N, PermutePlan& planref, bool want_lut = false)
 {
     LutBuild lut;
+    lut.ok = want_lut;
     bool any_peer = false;
     PermutePlan* plan = &planref;
     const int sm_count = ctx.sm_count;
@@ -1539,6 +1548,23 @@ std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shif
     auto hit = plan_cache_.find(key);
     if(hit != plan_cache_.end()) {
         ++plan_hits;
+        PermutePlan& P = *hit->second;
+        if(!P.lut_tried && !P.identity_copy && !P.d_btasks && ++P.uses >= 1) {
+            // second use of the plan: worth the table-driven form (built into a scratch plan, its tables move over)
+            P.lut_tried = true;
+            TaskSet ts2 = build_tasks(*this, in, shift, pi, adjoint_plan);
+            PermutePlan tmp;
+            lower_tasks(*this, ts2.tasks, ts2.leg_of, ts2.N, tmp, true);
+            std::swap(P.d_ltasks, tmp.d_ltasks);
+            std::swap(P.d_ltsrc, tmp.d_ltsrc);
+            std::swap(P.d_ltile_task, tmp.d_ltile_task);
+            std::swap(P.d_ltile_dst, tmp.d_ltile_dst);
+            std::swap(P.d_lut_int, tmp.d_lut_int);
+            std::swap(P.d_lut_pos, tmp.d_lut_pos);
+            P.n_ltiles = tmp.n_ltiles;
+            P.ltiles_per_cta = tmp.ltiles_per_cta;
+            P.lut_table_bytes = tmp.lut_table_bytes;
+        }
         return hit->second;
     }
     ++plan_misses;
@@ -1554,7 +1580,8 @@ std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shif
     } else {
         plan->out = ts.out;
         plan->bytes = 8 * (in->size + ts.out->size);
-        lower_tasks(*this, ts.tasks, ts.leg_of, ts.N, *plan);
+        lower_tasks(*this, ts.tasks, ts.leg_of, ts.N, *plan, planning_only());   // (planning-only contexts: host statistics of all forms at once)
+        plan->lut_tried = planning_only();
     }
     // bound the cache: a CTM run whose chi bases still change from step to step creates ~200 new plans (a few MB of device tables each)
     // per step; plans in use stay alive through their shared_ptr

@@ -76,6 +76,40 @@ def test_permute_bulk_path(ctxs, name, dim, monkeypatch):
             assert np.array_equal(gp.download(), op.data), f"{name} bulk permute p={p} shift={shift}"
 
 
+@pytest.mark.parametrize("name", ["SU2", "U1", "fU1", "fU1xSU2", "Z3"])
+def test_permute_table_driven_form(ctxs, name):
+    """The table-driven form (permute_lut_kernel: recoupling sums, odd extents) is built when a plan is used for the second time: every permutation runs
+    three times -- LSU form first, then twice the table-driven form -- and all three results are compared with the oracle; (2,2) tensors with odd
+    multiplicities (all 24 x 3 shifts), CTM-shaped (3,3) and (4,3) tensors, permute_adj, and the forms against each other."""
+    ctx, osym = ctxs(name)
+    rng = np.random.default_rng(31)
+    B, C = rand_entries(SPECS[name], 9, rng), rand_entries(SPECS[name], 7, rng)
+    g, o = pair(ctx, osym, [B, C], [B, C], 13)
+    for shift in (-1, 0, 2):
+        for p in itertools.permutations(range(4)):
+            op = o.permute(shift, p)
+            first = g.permute(shift, p)
+            for rep in range(2):
+                again = g.permute(shift, p)
+                assert_same(again, op, TOL, f"{name} permute<{shift},{p}> repeat {rep}")
+                assert np.abs(again.download() - first.download()).max() <= 1e-13 * max(np.abs(op.data).max(), 1.0)
+    chi, aux = rand_entries(SPECS[name], 11, rng, 3), rand_entries(SPECS[name], 5, rng, 2)
+    g6, o6 = pair(ctx, osym, [chi, aux, aux], [chi, aux, aux], 14)
+    for shift, p in [(-1, (0, 2, 3, 5, 1, 4)), (1, (0, 3, 5, 1, 2, 4)), (0, (1, 0, 2, 4, 3, 5)), (-3, (5, 4, 3, 2, 1, 0))]:
+        op = o6.permute(shift, p)
+        for rep in range(3):
+            assert_same(g6.permute(shift, p), op, TOL, f"{name} (3,3) permute<{shift},{p}> use {rep}")
+        oa = o6.permute_adj(shift, p)
+        for rep in range(3):
+            assert_same(g6.permute_adj(shift, p), oa, TOL, f"{name} (3,3) permute_adj<{shift},{p}> use {rep}")
+    phys = rand_entries(SPECS[name], 2, rng, 1)
+    g7, o7 = pair(ctx, osym, [chi, aux, aux, aux], [aux, aux, phys], 15)
+    for shift, p in [(0, (0, 2, 4, 5, 1, 3, 6)), (1, (0, 3, 5, 1, 2, 4, 6))]:
+        op = o7.permute(shift, p)
+        for rep in range(3):
+            assert_same(g7.permute(shift, p), op, TOL, f"{name} (4,3) permute<{shift},{p}> use {rep}")
+
+
 @pytest.mark.parametrize("name", ["SU2", "U1", "fU1xSU2"])
 def test_permute_ctm_shaped(ctxs, name):
     """The (3,3)<->(4,2)/(1,5)-style regroupings contractCorner issues, incl. 6- and 7-leg tensors."""

@@ -1037,7 +1037,10 @@ void rsvd_start(RsvdPlan& P, bool warm)
     rsvd_norm2_kernel<<<dim3(NORM_PARTS, P.nsec), 256, 0, s>>>(P.dA, P.d_secs, P.dNorm);
     check_cuda(cudaGetLastError(), "rsvd_norm2_kernel launch");
     ++c.launches;
-    rsvd_polish(P);
+    // a warm start (orthonormal Ritz vectors + random columns at the end) goes straight into X <- orth(B^T B X), which needs a well-conditioned, ordered basis,
+    // not an orthonormal one; the two Cholesky-QR passes (8 launches) are only spent on a cold start
+    static const bool two_orth = std::getenv("XB_RSVD_TWO_ORTH") != nullptr, always_polish = std::getenv("XB_RSVD_START_POLISH") != nullptr;
+    if(!warm || two_orth || always_polish || P.K0 <= 32) rsvd_polish(P);
 }
 void rsvd_iterate(RsvdPlan& P, int iters, bool ordered_basis)
 {   // `iters` subspace iterations X <- orth(B^T orth(B X)), orthonormalise, project: Y = B X

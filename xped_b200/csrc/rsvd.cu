@@ -736,7 +736,8 @@ rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, c
     }
     if(tid == 0) {
         diag[sec] = minpiv;
-        if(anybad) atomicOr(bad, bad_tag);
+if(anybad) atomicOr(bad, bad_tag);
+        if(bad_tag == 16 && minpiv < 0.25) atomicOr(bad, 8);   // single-pass polish on a basis too far from orthonormal
     }
 }
 
@@ -1003,12 +1004,18 @@ void rsvd_chol(RsvdPlan& P, double shift_rel, int bad_tag = 1)
     check_cuda(cudaGetLastError(), "rsvd_chol_kernel launch");
     ++P.ctx->launches;
 }
-void rsvd_polish(RsvdPlan& P)
-{   // X <- orthonormal to working precision (two unshifted Cholesky-QR passes)
+void rsvd_polish(RsvdPlan& P, bool single_pass = false)
+{   // X <- orthonormal to working precision: two unshifted Cholesky-QR passes, or ONE when X comes out of an iteration (its orthonormality error is then
+    // 1e-6 .. 3e-2 on CTM matrices, one pass leaves 1e-15 -- numpy emulation; the factorisation flags a smallest pivot below 1/4 of the largest diagonal
+    // entry, i.e. a basis too far from orthonormal for one pass, as a failed call: bad bit 8)
     Context& c = *P.ctx;
     c.launch_gemm(P.g_gx);
-    rsvd_chol(P, 0.0, 2);
+    rsvd_chol(P, 0.0, single_pass ? 16 : 2);
     c.launch_gemm(P.g_xm);
+    if(single_pass) {
+        check_cuda(cudaMemcpyAsync(P.dX, P.dX2, sizeof(double) * P.xo, cudaMemcpyDeviceToDevice, c.stream), "rsvd basis copy");
+        return;
+    }
     c.launch_gemm(P.g_gx2);
     rsvd_chol(P, 0.0, 4);
     c.launch_gemm(P.g_x2m);
@@ -1056,6 +1063,7 @@ void rsvd_iterate(RsvdPlan& P, int iters, bool ordered_basis)
     // A cold start (random X) is NOT ordered: B^T B X is then dominated by the leading direction in every column and its Gram matrix is numerically
     // rank-deficient -- the first batch of a cold call keeps the intermediate orthonormalisation.
     static const bool two_orth = std::getenv("XB_RSVD_TWO_ORTH") != nullptr;
+    bool single_orth_path = false;
     for(int it = 0; it < iters; ++it) {
         if(!two_orth && ordered_basis && P.K0 > 32) {   // (K <= 32 uses the register-resident factorisation, which does not rescale)
             c.launch_gemm(P.g_bx);
@@ -1063,6 +1071,7 @@ void rsvd_iterate(RsvdPlan& P, int iters, bool ordered_basis)
             c.launch_gemm(P.g_gx2);
             rsvd_chol(P, 1.e-15);
             c.launch_gemm(P.g_x2m);
+            single_orth_path = true;
             continue;
         }
         c.launch_gemm(P.g_bx);
@@ -1074,7 +1083,8 @@ void rsvd_iterate(RsvdPlan& P, int iters, bool ordered_basis)
         rsvd_chol(P, P.shift_it);
         c.launch_gemm(P.g_x2m);
     }
-    rsvd_polish(P);
+    static const bool two_pass_polish = std::getenv("XB_RSVD_POLISH2") != nullptr;
+    rsvd_polish(P, single_orth_path && !two_pass_polish);
     c.launch_gemm(P.g_bx_all);
 }
 

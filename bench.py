@@ -637,8 +637,9 @@ def run_b200(args):
                 stot = (q[0] - 1) / 2.0
                 data[o] = 0.5 * (stot * (stot + 1.0) - 1.5)
             H.upload(data)
-            ctm.computeRDM_h()   # plan build
-            ctm.computeRDM_v()
+            for _ in range(2):   # plan build; the second use of a plan builds its table-driven permute form (host work)
+                ctm.computeRDM_h()
+                ctm.computeRDM_v()
             ctx.sync()
             ctx.timer_start()
             rho_h, rho_v = ctm.computeRDM_h(), ctm.computeRDM_v()

@@ -1397,10 +1397,20 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
         // next call from this call site: when one projection sufficed, try fewer iterations (the warm start may need far fewer than a cold one; the
         // residual floor hides how many were spare); when it did not, remember what was needed and hold that for a while
         if(checks == 1) {
-            if(P.hold > 0)
+            if(P.hold > 0) {
                 --P.hold;
-            else
-                P.iters_hint = std::max(2, std::min(iters_done - 1, static_cast<int>(std::ceil(0.6 * iters_done))));
+            } else {
+                // a failed probe costs a whole extra projection (Jacobi + check): only go down while the observed residual, scaled back by the measured
+                // convergence factor per iteration (rate^2), predicts that fewer iterations still meet the tolerance with a factor 4 to spare
+                const double per_it = std::min(0.98, std::max(1.e-4, sel.hdr.rate * sel.hdr.rate));
+                int spare = 0;
+                double predicted = std::max(sel.hdr.max_res, 1.e-300);
+                while(spare < iters_done - 2 && predicted / per_it < 0.25 * P.tol_rel) {
+                    predicted /= per_it;
+                    ++spare;
+                }
+                P.iters_hint = std::max(2, iters_done - std::min(spare, std::max(1, iters_done / 3)));
+            }
         } else {
             P.iters_hint = iters_done;
             P.hold = 6;

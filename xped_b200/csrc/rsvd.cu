@@ -1062,8 +1062,13 @@ void rsvd_iterate(RsvdPlan& P, int iters, bool ordered_basis)
     // products and 1 instead of 2 factorisations per iteration.  A breakdown (exactly rank-deficient input) sets the bad flag: the caller falls back.
     // A cold start (random X) is NOT ordered: B^T B X is then dominated by the leading direction in every column and its Gram matrix is numerically
     // rank-deficient -- the first batch of a cold call keeps the intermediate orthonormalisation.
+    // iters < 0: only the tail (orthonormalisation + projection) after -iters - 1 ... see the caller: the iterations and the tail are separate CUDA graphs, so
+    // that a changing iteration count does not need a new graph (an instantiation costs 40-60 ms)
     static const bool two_orth = std::getenv("XB_RSVD_TWO_ORTH") != nullptr;
-    bool single_orth_path = false;
+    bool single_orth_path = !two_orth && ordered_basis && P.K0 > 32;
+    const bool tail_only = iters < 0, no_tail = iters >= 1000;
+    if(no_tail) iters -= 1000;
+    if(tail_only) iters = 0;
     for(int it = 0; it < iters; ++it) {
         if(!two_orth && ordered_basis && P.K0 > 32) {   // (K <= 32 uses the register-resident factorisation, which does not rescale)
             c.launch_gemm(P.g_bx);
@@ -1083,6 +1088,7 @@ void rsvd_iterate(RsvdPlan& P, int iters, bool ordered_basis)
         rsvd_chol(P, P.shift_it);
         c.launch_gemm(P.g_x2m);
     }
+    if(no_tail) return;
     static const bool two_pass_polish = std::getenv("XB_RSVD_POLISH2") != nullptr;
     rsvd_polish(P, single_orth_path && !two_pass_polish);
     c.launch_gemm(P.g_bx_all);
@@ -1329,9 +1335,14 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
         {
             const int n_it = next_iters;
             const bool ordered = warm && iters_done == 0;   // (a continuation starts from the Ritz vectors in Jacobi's column order: not ordered)
-            const int key = n_it + (ordered ? 0 : 100000);
-            cudaGraphExec_t& slot = P.graph_iter[key];
-            run_or_replay(P, &slot, key, use_graph, [&]() { rsvd_iterate(P, n_it, ordered); });
+            // ONE graph of a single iteration, replayed n_it times, and one graph of the tail (orthonormalisation + projection)
+            const int key_it = ordered ? 1 : 2, key_tail = ordered ? 3 : 4;
+            for(int i = 0; i < n_it; ++i) {
+                cudaGraphExec_t& slot = P.graph_iter[key_it];
+                run_or_replay(P, &slot, key_it, use_graph, [&]() { rsvd_iterate(P, 1001, ordered); });
+            }
+            cudaGraphExec_t& slot = P.graph_iter[key_tail];
+            run_or_replay(P, &slot, key_tail, use_graph, [&]() { rsvd_iterate(P, -1, ordered); });
         }
         iters_done += next_iters;
         mark(1);

@@ -1168,6 +1168,7 @@ int xb_tsvd(xb_ctx* ctx, const xb_tensor* t, int64_t max_keep, double eps_svd, i
             double* trunc_weight, double* entropy)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(t, "tensor");
         SvdResult r = ctx->impl.tsvd(*t->t, max_keep, eps_svd, preserve_multiplets != 0);
         *U = wrap(ctx, r.U);
@@ -1182,6 +1183,7 @@ int xb_tsvd_backward(xb_ctx* ctx, const xb_tensor* A, const xb_tensor* U, const 
                      const xb_tensor* dS, const xb_tensor* dVdag, xb_tensor** dA)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(A, "A");
         need(U, "U");
         need(S, "S");
@@ -1245,6 +1247,7 @@ int xb_mps_left_sweep_step(xb_ctx* ctx, const xb_tensor* A_loc, const xb_tensor*
                            xb_tensor** A_nb_new, double* trunc_weight, double* entropy)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(A_loc, "A_loc");
         Tensor *a = nullptr, *b = nullptr;
         ctx->impl.mps_left_sweep_step(*A_loc->t, A_prev ? A_prev->t.get() : nullptr, max_nsv, eps_svd, &a, &b, trunc_weight, entropy);
@@ -1257,6 +1260,7 @@ int xb_mps_right_sweep_step(xb_ctx* ctx, const xb_tensor* A_loc, const xb_tensor
                             xb_tensor** A_nb_new, double* trunc_weight, double* entropy)
 {
     return guard([&] {
+        need(ctx, "ctx");
         need(A_loc, "A_loc");
         Tensor *a = nullptr, *b = nullptr;
         ctx->impl.mps_right_sweep_step(*A_loc->t, A_next ? A_next->t.get() : nullptr, max_nsv, eps_svd, &a, &b, trunc_weight, entropy);

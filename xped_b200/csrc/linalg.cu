@@ -769,7 +769,14 @@ __global__ void svd_gather_kernel(const double* __restrict__ W, const double* __
     }
 }
 
-__global__ void svd_sweep_bump_kernel(int* sweep) { *sweep += 1; }
+// start of a sweep: flag[0] = "a rotation was applied" of the previous sweep (reset here), flag[1] = number of sweeps after which the iteration was first found
+// converged (-1: not yet).  Sweeps enqueued behind the converged one skip all their pairs (clean > last_mod), so the host can enqueue several without reading back.
+__global__ void svd_sweep_bump_kernel(int* sweep, int* flag)
+{
+    if(flag[0] == 0 && flag[1] < 0) flag[1] = *sweep;
+    flag[0] = 0;
+    *sweep += 1;
+}
 
 // Round-robin schedule over `nb` column blocks: rounds x pairs; a bye (odd nb / nb == 1) becomes a single-block task.
 void schedule(int block, int nb, int gbase, std::vector<std::vector<SvdTask>>& rounds)
@@ -1062,7 +1069,7 @@ JacobiResult jacobi_all(Context& ctx, const JacobiInput& in, bool shifted, bool 
             check_cuda(cudaFreeAsync(d_pre, s), "svd precondition free");
         }
     }
-    int* h_flag = static_cast<int*>(ctx.pinned(sizeof(int)));
+    int* h_flag = static_cast<int*>(ctx.pinned(2 * sizeof(int)));
     unsigned long long* d_tprof = nullptr;
     static const bool svd_prof = std::getenv("XB_SVD_PROF") != nullptr;
     if(svd_prof) {
@@ -1177,8 +1184,7 @@ JacobiResult jacobi_all(Context& ctx, const JacobiInput& in, bool shifted, bool 
             bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             if(ok) {
                 try {
-                    check_cuda(cudaMemsetAsync(d_flag, 0, sizeof(int), s), "svd flag reset");
-                    svd_sweep_bump_kernel<<<1, 1, 0, s>>>(d_sweep);
+                    svd_sweep_bump_kernel<<<1, 1, 0, s>>>(d_sweep, d_flag);
                     for(size_t r = 0; r + 1 < round_begin.size(); ++r) {
                         const int cnt = round_begin[r + 1] - round_begin[r];
                         if(cnt > 0) launch_round(d_tasks + round_begin[r], cnt, static_cast<int>(r));
@@ -1202,25 +1208,42 @@ JacobiResult jacobi_all(Context& ctx, const JacobiInput& in, bool shifted, bool 
         }
         if(g.exec) sg = &g;
     }
-    for(R.sweeps = 0; R.sweeps < max_sweeps; ++R.sweeps) {
-        if(sg) {
-            check_cuda(cudaGraphLaunch(sg->exec, s), "svd sweep graph launch");
-            ctx.launches += sg->rounds;
-        } else {
-        check_cuda(cudaMemsetAsync(d_flag, 0, sizeof(int), s), "svd flag reset");
-        svd_sweep_bump_kernel<<<1, 1, 0, s>>>(d_sweep);
-        for(size_t r = 0; r + 1 < round_begin.size(); ++r) {
-            const int cnt = round_begin[r + 1] - round_begin[r];
-            if(cnt == 0) continue;
-            launch_round(d_tasks + round_begin[r], cnt, static_cast<int>(r));
-            ++ctx.launches;
+    // Sweeps are enqueued in batches and the convergence record is read back once per batch: a sweep behind the converged one costs its (empty) launches
+    // only, a read-back costs a host round trip with the device idle (~35 us against ~80 us of a D=4 sweep).  First batch = the caller's expectation.
+    check_cuda(cudaMemsetAsync(d_flag, 0xff, 2 * sizeof(int), s), "svd flag init");   // flag[0] != 0: "rotated", flag[1] = -1: not converged
+    const bool batched = rounds_per_sweep <= 16;
+    int enqueued = 0, batch = batched ? std::max(1, std::min(in.sweeps_hint > 0 ? in.sweeps_hint : 2, max_sweeps)) : 1;
+    bool converged = false;
+    while(!converged && enqueued < max_sweeps) {
+        batch = std::min(batch, max_sweeps - enqueued);
+        for(int b = 0; b < batch; ++b) {
+            if(sg) {
+                check_cuda(cudaGraphLaunch(sg->exec, s), "svd sweep graph launch");
+                ctx.launches += sg->rounds;
+            } else {
+                svd_sweep_bump_kernel<<<1, 1, 0, s>>>(d_sweep, d_flag);
+                for(size_t r = 0; r + 1 < round_begin.size(); ++r) {
+                    const int cnt = round_begin[r + 1] - round_begin[r];
+                    if(cnt == 0) continue;
+                    launch_round(d_tasks + round_begin[r], cnt, static_cast<int>(r));
+                    ++ctx.launches;
+                }
+            }
         }
-        }
+        enqueued += batch;
         check_cuda(cudaGetLastError(), "svd_round_kernel launch");
-        check_cuda(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s), "svd flag readback");
+        check_cuda(cudaMemcpyAsync(h_flag, d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, s), "svd flag readback");
         check_cuda(cudaStreamSynchronize(s), "svd sweep sync");
-        if(*h_flag == 0) break;
+        if(h_flag[1] >= 0) {   // found converged inside the batch: after h_flag[1] sweeps
+            R.sweeps = h_flag[1] - 1;
+            converged = true;
+        } else if(h_flag[0] == 0) {   // the last sweep of the batch applied no rotation
+            R.sweeps = enqueued - 1;
+            converged = true;
+        }
+        batch = batched ? 2 : 1;
     }
+    if(!converged) R.sweeps = max_sweeps;
     if(R.sweeps >= max_sweeps) {
         cudaFreeAsync(d_meta, s);
         cudaFreeAsync(R.d_W, s);

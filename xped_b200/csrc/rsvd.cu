@@ -946,6 +946,7 @@ struct RsvdPlan
     JacobiInput jin;
     std::string jin_sig_base;
     bool jacobi_precondition = false;   // see the Rayleigh-Ritz step
+    int jacobi_sweeps = 0;               // sweeps of the previous projected Jacobi solve from this call site (batch size of the next one)
     std::vector<SelSector> sel_secs;
     ~RsvdPlan()
     {
@@ -1302,10 +1303,12 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
     const bool use_graph = !no_graph && P.uses >= 2;   // a layout seen once (chi bases still moving) is not worth an instantiation
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float t_iter = 0.f, t_jac = 0.f, t_chk = 0.f;
+    double host_ms[6] = {0, 0, 0, 0, 0, 0};   // host clock at the marks (verbose only): where the call spends wall time outside the device phases
     auto mark = [&](int k) {
         if(!verbose) return;
         if(!ev[k]) ev[k] = get_event();
         cudaEventRecord(ev[k], s);
+        host_ms[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     };
     auto lap = [&](int a, int b, float& acc) {
         if(!verbose) return;
@@ -1352,7 +1355,9 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
         // took more than 16 switches the preconditioner back on for its later calls.
         P.jin.no_precondition = !P.jacobi_precondition;
         P.jin.sig = P.jin_sig_base + (P.jin.no_precondition ? "#np" : "");
+        P.jin.sweeps_hint = P.jacobi_sweeps;   // sweeps the previous call from this call site needed
         J = jacobi_all(*this, P.jin, false, false);
+        P.jacobi_sweeps = J.sweeps + 1;
         if(P.jin.no_precondition && J.sweeps + 1 > 16) P.jacobi_precondition = true;
         mark(2);
         bool layout_ok = true;
@@ -1383,6 +1388,8 @@ bool Context::tsvd_truncated(const Tensor& t, int64_t max_keep, double eps_svd, 
                          "iterate %.3f jacobi %.3f check %.3f graph %d warm %d\n",
                          K0, nsec, P.n_proj, iters_done, sel.hdr.verdict, sel.hdr.max_res, P.tol_rel, sel.hdr.rate, sel.hdr.nkeep,
                          sel.hdr.smax > 0 ? sel.hdr.cut / sel.hdr.smax : 0.0, J.sweeps + 1, h_bad, t_iter, t_jac, t_chk, use_graph ? 1 : 0, warm ? 1 : 0);
+            std::fprintf(stderr, "[rsvd] host clock at marks (ms since entry): start %.3f iterate-enqueued %.3f jacobi-done %.3f check-done %.3f\n", host_ms[0], host_ms[1],
+                         host_ms[2], host_ms[3]);
             t_iter = t_jac = t_chk = 0.f;
         }
         if(sel.hdr.verdict == 0 && !h_bad) {

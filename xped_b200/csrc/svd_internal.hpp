@@ -36,6 +36,7 @@ struct JacobiInput
     std::vector<long long> off;
     std::vector<int> rows, cols;
     std::string sig;   // key of the cached sweep graphs
+    int sweeps_hint = 0;            // expected number of sweeps (0: unknown): size of the first batch enqueued without a convergence read-back
     bool no_precondition = false;   // skip the QR preconditioner (projected blocks of the truncated path: columns already close to the singular directions)
 };
 

@@ -17,7 +17,8 @@ for step in range(STEPS):
     ctm.grow_all()
     ms = ctx.timer_stop()
     prof = ctx.profile_read(); ctx.profile(False)
-    print(f"step {step}: {ms:.2f} ms; prof {dict((k, (round(v[0], 2), v[1])) for k, v in prof.items())}", flush=True)
+    print(f"step {step}: {ms:.2f} ms; prof {dict((k, (round(v[0], 2), v[1])) for k, v in prof.items())}; truncated calls / fallbacks / iterations so far "
+          f"{ctx.get_int('svd.truncated_calls')} / {ctx.get_int('svd.truncated_fallbacks')} / {ctx.get_int('svd.truncated_iterations')}", flush=True)
 # gauge-invariant fingerprint of the environment: singular values of C1 and T1 (per sector)
 Q = ctm.contractCorner(0)
 Q4 = ctm.contractCorner(3)

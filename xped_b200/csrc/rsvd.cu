@@ -550,10 +550,20 @@ constexpr int CHB = 16;
 constexpr int CHOL_THREADS = 512;
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
 rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, const RsvdSec* __restrict__ secs, const int* __restrict__ list, double shift_rel,
-                         double* __restrict__ diag, int* __restrict__ bad, int bad_tag)
+                         double* __restrict__ diag, int* __restrict__ bad, int bad_tag, unsigned long long* __restrict__ tprof)
 {
     extern __shared__ double chol_sh[];
     __shared__ double red[32];
+    // optional phase timing (XB_CHOL_PROF=1): lane 0 of warp 0 / warp 1 of CTA 0 accumulate clock64() deltas per phase
+    const bool prof = tprof != nullptr && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32);
+    long long tp = prof ? clock64() : 0;
+    auto lap = [&](int slot) {
+        if(prof) {
+            const long long now = clock64();
+            atomicAdd(tprof + slot, static_cast<unsigned long long>(now - tp));
+            tp = now;
+        }
+    };
     const int sec = list[blockIdx.x];
     const RsvdSec s = secs[sec];
     const int K = s.K, Kp = (K + CHB - 1) / CHB * CHB, LD = Kp + 1, nblk = Kp / CHB;
@@ -579,6 +589,7 @@ rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, c
     const double shift = shift_rel * gmax, gmax_inv = 1.0 / gmax;
     for(int i = tid; i < K; i += CHOL_THREADS) A[i * LD + i] += shift;
     __syncthreads();
+    lap(threadIdx.x == 0 ? 0 : 8);   // load
 
     double minpiv = 1.e300;
     bool anybad = false;
@@ -638,7 +649,9 @@ rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, c
         }
     };
     if(warp == 0) factor_diag(0, false);
+    lap(threadIdx.x == 0 ? 1 : 9);   // first diagonal block (warp 1: waits)
     __syncthreads();
+    lap(threadIdx.x == 0 ? 2 : 10);
     for(int kb = 0; kb + 1 < nblk; ++kb) {
         const int c0 = kb * CHB, r0 = c0 + CHB, nrows = Kp - r0;
         // ---- panel: P[i][j] = sum_{c <= j} A[r0 + i][c0 + c] * Linv[j][c]
@@ -656,9 +669,12 @@ rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, c
                 Pb[j * Kp + i] = p;
             }
         }
+        lap(threadIdx.x == 0 ? 3 : 11);   // panel
         __syncthreads();
+        lap(threadIdx.x == 0 ? 2 : 10);   // barrier wait
         if(warp == 0) {
             factor_diag(r0, true);   // overwrites Li: the panel above was its last reader
+            lap(4);   // diagonal block
         } else {
             // ---- trailing update (full square: the matrix stays symmetric; the next diagonal block belongs to warp 0) + the panel goes back into the matrix
             const int q = nrows >> 2, t_id = tid - 32, t_n = CHOL_THREADS - 32;
@@ -693,47 +709,75 @@ rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, c
                 const int j = idx / nrows, i = idx - j * nrows;
                 A[(c0 + j) * LD + r0 + i] = Pb[j * Kp + i];
             }
+            lap(12);   // trailing update
         }
         __syncthreads();
+        lap(threadIdx.x == 0 ? 2 : 10);
     }
-    // ---- X = L^-1 below the diagonal blocks: column c, rows of block ib:  X[ib][c] = -Linv_ib * sum_{k = 16 jb}^{16 ib - 1} L[ib rows][k] * X[k][c];
-    // X[k][c] sits at A[k * LD + c] (upper triangle), Linv_ib[r][k] (k < r) at A[(16 ib + r) * LD + 16 ib + k], its diagonal in dinv
+    // ---- X = L^-1 below the diagonal blocks, one block ROW per step, all threads:  X[ib][c] = -Linv_ib * S,  S[r][c] = sum_{k = c}^{16 ib - 1} L[16 ib + r][k] X[k][c].
+    // X[k][c] sits at A[k * LD + c] (upper triangle), Linv_ib[r][k] (k < r) at A[(16 ib + r) * LD + 16 ib + k]; the diagonal of A takes X's diagonal (1 / L_jj) first,
+    // so that neither sum has a special case.  Thread = (row r of the block, columns c = group + 32 m): plain dot products on four chains, S goes through the panel
+    // buffer, two barriers per block row.  (The column-by-column form with one half-warp per column walked 16-step dependent chains per 16 x 16 block and took
+    // 50 k of the kernel's 127 k cycles at K = 96.)
+    for(int i = tid; i < Kp; i += CHOL_THREADS) A[i * LD + i] = dinv[i];
+    __syncthreads();
     {
-        // the two half-warps own the neighbouring columns c (even) and c + 1 of the same 16-block: identical trip counts, so the shuffles and warp
-        // barriers below use the full mask (partial masks cost a MATCH per use)
-        const int r = lane & 15, half = lane >> 4;
-        for(int c = warp * 2 + half; c < Kp; c += CHOL_THREADS / 16) {
-            const int jb = c / CHB;
-            for(int ib = jb + 1; ib < nblk; ++ib) {
-                const int row = ib * CHB + r;
-                // rows of the diagonal block jb: X[k][c] is dinv[c] at k == c, zero above, stored below; then full blocks, four independent chains
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                for(int k = jb * CHB; k < (jb + 1) * CHB; ++k) s0 = fma(A[k * LD + row], k == c ? dinv[c] : (k > c ? A[k * LD + c] : 0.0), s0);
-                for(int k = (jb + 1) * CHB; k < ib * CHB; k += 4) {
-                    s0 = fma(A[k * LD + row], A[k * LD + c], s0);
-                    s1 = fma(A[(k + 1) * LD + row], A[(k + 1) * LD + c], s1);
-                    s2 = fma(A[(k + 2) * LD + row], A[(k + 2) * LD + c], s2);
-                    s3 = fma(A[(k + 3) * LD + row], A[(k + 3) * LD + c], s3);
-                }
-                const double sacc = (s0 + s1) + (s2 + s3);
-                double t = 0.0;
+        constexpr int MC = 5;   // Kp <= 160 columns / 32 groups
+        const int r = tid & 15, grp = tid >> 4;
+        for(int ib = 1; ib < nblk; ++ib) {
+            const int row = ib * CHB + r, ncol = ib * CHB;
+            const double* __restrict__ Lr = A + row;
 #pragma unroll
-                for(int k = 0; k < CHB; ++k) {
-                    const double sk = __shfl_sync(0xffffffffu, sacc, (half << 4) | k);
-                    const double lik = k < r ? A[row * LD + ib * CHB + k] : (k == r ? dinv[row] : 0.0);
-                    t = fma(-lik, sk, t);
+            for(int m = 0; m < MC; ++m) {
+                const int c = grp + 32 * m;
+                if(c < ncol) {
+                    const double* __restrict__ Xc = A + c;
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    int k = c;
+                    for(; k + 3 < ncol; k += 4) {
+                        s0 = fma(Lr[k * LD], Xc[k * LD], s0);
+                        s1 = fma(Lr[(k + 1) * LD], Xc[(k + 1) * LD], s1);
+                        s2 = fma(Lr[(k + 2) * LD], Xc[(k + 2) * LD], s2);
+                        s3 = fma(Lr[(k + 3) * LD], Xc[(k + 3) * LD], s3);
+                    }
+                    for(; k < ncol; ++k) s0 = fma(Lr[k * LD], Xc[k * LD], s0);
+                    Pb[r * Kp + c] = (s0 + s1) + (s2 + s3);
                 }
-                A[row * LD + c] = t;
-                __syncwarp();
             }
+            __syncthreads();
+            {
+                double acc[MC];
+#pragma unroll
+                for(int m = 0; m < MC; ++m) acc[m] = 0.0;
+                const double* __restrict__ Li_r = A + row * LD + ib * CHB;   // Linv_ib[r][k], k <= r
+#pragma unroll 4
+                for(int k = 0; k < CHB; ++k) {
+                    const double li = k <= r ? -Li_r[k] : 0.0;
+#pragma unroll
+                    for(int m = 0; m < MC; ++m) {
+                        const int c = grp + 32 * m;
+                        if(c < ncol) acc[m] = fma(li, Pb[k * Kp + c], acc[m]);
+                    }
+                }
+#pragma unroll
+                for(int m = 0; m < MC; ++m) {
+                    const int c = grp + 32 * m;
+                    if(c < ncol) A[row * LD + c] = acc[m];
+                }
+            }
+            __syncthreads();
         }
     }
+    lap(threadIdx.x == 0 ? 5 : 13);   // substitution
     __syncthreads();
+    lap(threadIdx.x == 0 ? 2 : 10);
     double* __restrict__ m_out = M + s.g_off;
     for(int e = tid; e < K * K; e += CHOL_THREADS) {
         const int c = e / K, rr = e - c * K;   // M(rr, c) = X(c, rr)
         m_out[e] = rr < c ? A[c * LD + rr] : (rr == c ? dinv[c] : 0.0);
     }
+    lap(threadIdx.x == 0 ? 6 : 14);   // store
+    if(prof && threadIdx.x == 0) atomicAdd(tprof + 7, 1ull);
     if(tid == 0) {
         diag[sec] = minpiv;
 if(anybad) atomicOr(bad, bad_tag);
@@ -978,7 +1022,25 @@ void rsvd_chol(RsvdPlan& P, double shift_rel, int bad_tag = 1)
             const int most = 227 * 1024 - 512;   // the opt-in maximum covers static + dynamic shared memory
             check_cuda(cudaFuncSetAttribute(rsvd_chol_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, most), "chol smem attr");
         }
-        rsvd_chol_blocked_kernel<<<P.n_proj, CHOL_THREADS, smem, s>>>(P.dG, P.dM, P.d_secs, P.d_proj, shift_rel, P.dDiag, P.d_bad, bad_tag);
+        static unsigned long long* d_tprof = nullptr;
+        static const bool chol_prof = std::getenv("XB_CHOL_PROF") != nullptr;
+        if(chol_prof && !d_tprof) {
+            cudaMalloc(reinterpret_cast<void**>(&d_tprof), 16 * sizeof(unsigned long long));
+            cudaMemset(d_tprof, 0, 16 * sizeof(unsigned long long));
+        }
+        rsvd_chol_blocked_kernel<<<P.n_proj, CHOL_THREADS, smem, s>>>(P.dG, P.dM, P.d_secs, P.d_proj, shift_rel, P.dDiag, P.d_bad, bad_tag, d_tprof);
+        if(chol_prof) {
+            static int calls = 0;
+            if(++calls % 100 == 0) {
+                cudaStreamSynchronize(s);
+                unsigned long long h[16];
+                cudaMemcpy(h, d_tprof, sizeof(h), cudaMemcpyDeviceToHost);
+                const double n = static_cast<double>(h[7] ? h[7] : 1);
+                std::fprintf(stderr, "[chol prof] K0 %d, %.0f launches | warp 0 cycles/launch: load %.0f diag0 %.0f barrier %.0f panel %.0f diag %.0f subst %.0f store %.0f | warp 1: load %.0f "
+                                     "wait-diag0 %.0f barrier %.0f panel %.0f trailing %.0f subst %.0f store %.0f\n",
+                             P.K0, n, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n, h[12] / n, h[13] / n, h[14] / n);
+            }
+        }
         check_cuda(cudaGetLastError(), "rsvd_chol_blocked_kernel launch");
         ++P.ctx->launches;
         return;

@@ -11,7 +11,13 @@ aux = {4: [(1, 2), (2, 2)], 6: [(1, 3), (2, 3)], 3: [(1, 1), (2, 1)], 2: [(1, 1)
 a, phys = ctx.basis(aux), ctx.basis([(2, 1)])
 A = ctx.tensor([a, a], [a, a, phys]).setRandom(0)
 ctm = xb.CTM(A, CHI)
+_cuda = None
+if os.environ.get("XB_CHECK_NCU_LAST"):   # ncu --profile-from-start off: capture the last step only
+    import ctypes
+    _cuda = ctypes.CDLL("libcuda.so.1")
 for step in range(STEPS):
+    if _cuda is not None and step == STEPS - 1:
+        ctx.sync(); _cuda.cuProfilerStart()
     ctx.sync(); ctx.profile(True); ctx.profile_read()
     ctx.timer_start()
     ctm.grow_all()
@@ -19,6 +25,8 @@ for step in range(STEPS):
     prof = ctx.profile_read(); ctx.profile(False)
     print(f"step {step}: {ms:.2f} ms; prof {dict((k, (round(v[0], 2), v[1])) for k, v in prof.items())}; truncated calls / fallbacks / iterations so far "
           f"{ctx.get_int('svd.truncated_calls')} / {ctx.get_int('svd.truncated_fallbacks')} / {ctx.get_int('svd.truncated_iterations')}", flush=True)
+    if _cuda is not None and step == STEPS - 1:
+        ctx.sync(); _cuda.cuProfilerStop()
 # gauge-invariant fingerprint of the environment: singular values of C1 and T1 (per sector)
 Q = ctm.contractCorner(0)
 Q4 = ctm.contractCorner(3)

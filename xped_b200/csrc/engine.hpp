@@ -223,7 +223,7 @@ struct PreparedGemm
     GemmItem* d_items[2] = {nullptr, nullptr};
     int n_items[2] = {0, 0};
     SplitKJob* d_jobs = nullptr;
-    int n_jobs = 0;
+    int n_jobs = 0, max_job_elems = 0;   // split-K problems and the element count of the largest one (grid of the reduce launch)
     double* d_scratch = nullptr;
     int launches = 0;
     double flops = 0.0;
@@ -460,7 +460,7 @@ void launch_permute2(const double* src, const double* src2, long long split, dou
 // deterministic LPT greedy (largest cost first, ties by index, least-loaded rank, ties lowest rank)
 std::vector<int> lpt_owner(const std::vector<double>& cost, int world);
 void launch_gemm_grouped(const double* A, const double* B, double* C, const GemmItem* d_items, int n_items, int tile_m, cudaStream_t s);
-void launch_splitk_reduce(const double* scratch, double* C, const SplitKJob* d_jobs, int n_jobs, cudaStream_t s);
+void launch_splitk_reduce(const double* scratch, double* C, const SplitKJob* d_jobs, int n_jobs, int max_job_elems, cudaStream_t s);
 void launch_scale_copy(const double* x, double* y, double alpha, int64_t n, cudaStream_t s);
 void launch_axpby(const double* x, const double* y, double* z, double alpha, double beta, int64_t n, cudaStream_t s);
 void launch_absmax(const double* x, int64_t n, double* d_out, cudaStream_t s);

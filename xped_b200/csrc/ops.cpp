@@ -171,6 +171,7 @@ PreparedGemm Context::prepare_gemm(const double* A, const double* B, double* C, 
         check_cuda(cudaMallocAsync(reinterpret_cast<void**>(&P.d_jobs), jobs.size() * sizeof(SplitKJob), stream), "cudaMallocAsync split-K jobs");
         upload_async(P.d_jobs, jobs.data(), jobs.size() * sizeof(SplitKJob));
         P.n_jobs = static_cast<int>(jobs.size());
+        for(const SplitKJob& j : jobs) P.max_job_elems = std::max(P.max_job_elems, j.m * j.n);
         ++P.launches;
     }
     return P;
@@ -182,7 +183,7 @@ void Context::launch_gemm(const PreparedGemm& P)
     ProfScope prof(*this, CAT_GEMM, P.flops);
     for(int which = 0; which < 2; ++which)
         if(P.n_items[which] > 0) launch_gemm_grouped(P.A, P.B, P.C, P.d_items[which], P.n_items[which], which == 0 ? 128 : 64, stream);
-    if(P.n_jobs > 0) launch_splitk_reduce(P.d_scratch, P.C, P.d_jobs, P.n_jobs, stream);
+    if(P.n_jobs > 0) launch_splitk_reduce(P.d_scratch, P.C, P.d_jobs, P.n_jobs, P.max_job_elems, stream);
     launches += P.launches;
 }
 

@@ -82,17 +82,33 @@ PreparedGemm Context::prepare_gemm(const double* A, const double* B, double* C, 
     // TFLOP/s)
     // tiles of the whole launch: a launch that fills less than ~two waves (3 CTAs per SM) with LONG contractions leaves SMs idle for a large fraction of its
     // run time (the 3060 x 160 x 3096 products of the D=6 subspace iteration: 333 CTAs on 148 SMs = 2.25 per SM, 10 TFLOP/s) -- cut K there as well
+    // Small launches (the products of a D=4 subspace iteration: 136 CTAs of 128 x 64 tiles, ONE CTA = four warps per SM: tensor pipe 31 % busy, the warps wait on
+    // their own DMMA chains, 32 us for 0.15 GFLOP) use 64-row tiles for every problem: twice the CTAs, two CTAs per SM.
+    static const bool no_small64 = std::getenv("XB_GEMM_SMALL64") != nullptr && std::atoi(std::getenv("XB_GEMM_SMALL64")) == 0;
+    bool force64 = false;
+    if(!no_small64) {
+        long long ctas = 0;
+        for(const GemmItem& g : problems) {
+            if(g.m <= 0 || g.n <= 0) continue;
+            const int tile_m = g.m > 96 ? 128 : 64;
+            const long long ntiles = static_cast<long long>((g.m + tile_m - 1) / tile_m) * ((g.n + GEMM_TILE_N - 1) / GEMM_TILE_N);
+            long long split = 1;
+            if(!no_split && !g.acc && g.k >= 256 && ntiles <= 32) split = std::max<long long>(1, std::min<long long>(8, std::min<long long>(g.k / 96, sm_count / ntiles)));
+            ctas += ntiles * split;
+        }
+        force64 = ctas < 2ll * sm_count;
+    }
     long long launch_tiles = 0;
     for(const GemmItem& g : problems) {
         if(g.m <= 0 || g.n <= 0) continue;
-        const int tile_m = g.m > 96 ? 128 : 64;
+        const int tile_m = (g.m > 96 && !force64) ? 128 : 64;
         launch_tiles += static_cast<long long>((g.m + tile_m - 1) / tile_m) * ((g.n + GEMM_TILE_N - 1) / GEMM_TILE_N);
     }
     static const int wave_split = std::getenv("XB_GEMM_WAVE_SPLIT") ? std::atoi(std::getenv("XB_GEMM_WAVE_SPLIT")) : 6;   // target CTAs per SM (0: off)
     for(GemmItem g : problems) {
         if(g.m <= 0 || g.n <= 0) continue;
         P.flops += 2.0 * g.m * static_cast<double>(g.n) * g.k;
-        const int which = g.m > 96 ? 0 : 1, tile_m = which == 0 ? 128 : 64;
+        const int which = (g.m > 96 && !force64) ? 0 : 1, tile_m = which == 0 ? 128 : 64;
         const int ntiles = ((g.m + tile_m - 1) / tile_m) * ((g.n + GEMM_TILE_N - 1) / GEMM_TILE_N);
         int split = 1;
         if(!no_split && !g.acc && g.k >= 256 && ntiles <= 32) split = std::max(1, std::min(8, std::min(g.k / 96, sm_count / ntiles)));

@@ -37,7 +37,7 @@ namespace {
 constexpr int SEL_THREADS = 1024;
 constexpr int SEL_MAX = 16384;   // capacity of the shared-memory sort
 constexpr int SEL_COL_BITS = 14;
-constexpr int NORM_PARTS = 32;
+constexpr int NORM_PARTS = 128;   // (32 parts: 272 us for the 155 MB matrix of a D=6 chi=144 call, one load in flight per thread)
 
 struct SelSector
 {
@@ -378,8 +378,19 @@ __global__ void rsvd_norm2_kernel(const double* __restrict__ A, const RsvdSec* _
     const long long cnt = static_cast<long long>(s.m) * s.n;
     const long long chunk = (cnt + gridDim.x - 1) / gridDim.x;
     const long long e0 = chunk * blockIdx.x, e1 = e0 + chunk < cnt ? e0 + chunk : cnt;
-    double v = 0.0;
-    for(long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) v = fma(A[s.a_off + e], A[s.a_off + e], v);
+    double v = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;   // four chains: four loads in flight per thread (fixed order => deterministic)
+    long long e = e0 + threadIdx.x;
+    const long long bd = blockDim.x;
+    const double* __restrict__ a = A + s.a_off;
+    for(; e + 3 * bd < e1; e += 4 * bd) {
+        const double x0 = a[e], x1 = a[e + bd], x2 = a[e + 2 * bd], x3 = a[e + 3 * bd];
+        v = fma(x0, x0, v);
+        v1 = fma(x1, x1, v1);
+        v2 = fma(x2, x2, v2);
+        v3 = fma(x3, x3, v3);
+    }
+    for(; e < e1; e += bd) v = fma(a[e], a[e], v);
+    v = (v + v1) + (v2 + v3);
     for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
     __syncthreads();
@@ -574,11 +585,23 @@ rsvd_chol_blocked_kernel(const double* __restrict__ G, double* __restrict__ M, c
     double* __restrict__ dinv = Li + CHB * (CHB + 1);   // 1 / L_jj
     const double* __restrict__ g = G + s.g_off;
     double gmax = 0.0;
-    for(int e = tid; e < Kp * Kp; e += CHOL_THREADS) {
-        const int c = e / Kp, i = e - c * Kp;
-        const double v = (i < K && c < K) ? g[i + c * K] : (i == c ? 1.0 : 0.0);   // identity padding: decoupled
-        A[c * LD + i] = v;
-        if(i == c && i < K) gmax = fmax(gmax, v);
+    for(int e0 = tid; e0 < Kp * Kp; e0 += 4 * CHOL_THREADS) {   // four loads in flight per thread (one per iteration: 9 k of the kernel's 127 k cycles at K = 96)
+        double v[4];
+        int cc[4], ii[4];
+#pragma unroll
+        for(int u = 0; u < 4; ++u) {
+            const int e = e0 + u * CHOL_THREADS;
+            cc[u] = e / Kp;
+            ii[u] = e - cc[u] * Kp;
+            v[u] = (e < Kp * Kp && ii[u] < K && cc[u] < K) ? g[ii[u] + cc[u] * K] : (ii[u] == cc[u] ? 1.0 : 0.0);   // identity padding: decoupled
+        }
+#pragma unroll
+        for(int u = 0; u < 4; ++u) {
+            if(e0 + u * CHOL_THREADS < Kp * Kp) {
+                A[cc[u] * LD + ii[u]] = v[u];
+                if(ii[u] == cc[u] && ii[u] < K) gmax = fmax(gmax, v[u]);
+            }
+        }
     }
     for(int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
     if(lane == 0) red[warp] = gmax;

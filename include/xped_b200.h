@@ -178,6 +178,12 @@ int xb_permute_plan_stats(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_bas
 /* census of the same plan: destination elements, source elements read (an element feeding k destination sub-blocks counts k times: SU(2) recoupling
  * sums), destination tasks, source records, tiles of the table-driven form (0: the plan does not have it), bytes of its offset tables */
 int xb_permute_plan_census(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n, int64_t out[6]);
+/* TEST SUPPORT, planning-only contexts only (no GPU; the tensors of such a context own no data, so no product path can reach this): applies the HOST tables
+ * of the plan of permute<shift,p> (adjoint != 0: permute_adj) to host arrays the way the kernels address them -- form 0: tile list of the LSU form, form 1:
+ * table-driven form -- with every offset bounds-checked and every destination element written exactly once.  `src` / `dst` are the `m_data` images of the
+ * input / output tensor.  The CPU tests compare the result with the oracle's Tensor::permute (src/Core/Tensor.cpp:83-214). */
+int xb_permute_plan_emulate(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n, int adjoint,
+                            int form, const double* src, int64_t n_src, double* dst, int64_t n_dst);
 /* a shard: Tensor(domain, codomain) holding only the listed sectors, in that order, zero-initialised */
 int xb_tensor_create_sectors(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, const int* q, int n_sectors,
                              xb_tensor** out);

@@ -1,0 +1,108 @@
+"""The permute plan builder checked WITHOUT a GPU: a planning-only context keeps the host copies of a plan's tables, `xb_permute_plan_emulate` walks them over
+host arrays the way the kernels address device memory (form 0: tile list of the LSU form, form 1: table-driven form; every offset bounds-checked, every
+destination element written exactly once), and the result is compared with the oracle's Tensor::permute (src/Core/Tensor.cpp:83-214, 258-333).
+What this covers: recoupling coefficients, sub-block offsets and strides of every source, tile origins / clipping, the offset / staging tables of the
+table-driven form and its cut of a sub-block into full tiles + remainder regions.  What it does not cover: the kernels themselves (tests/test_gpu_parity.py)."""
+import itertools
+
+import numpy as np
+import pytest
+
+import xped_oracle as xo
+from xped_oracle.rng import uniform_fill
+from helpers import SPECS, obasis, rand_entries
+from xped_b200.sharded import PlanningContext, layout_structure, permute_plan_emulate, permute_plan_stats
+
+TOL = 1e-13
+
+
+def oracle_tensor(osym, dom, cod, seed):
+    t = xo.Tensor(osym, [obasis(osym, e) for e in dom], [obasis(osym, e) for e in cod])
+    t.data = uniform_fill(seed, t.plainSize())
+    return t
+
+
+def check(ctx, osym, dom, cod, shift, p, seed, forms=(0, 1), adjoint=False, rank_after=None):
+    o = oracle_tensor(osym, dom, cod, seed)
+    ref = o.permute_adj(shift, p) if adjoint else o.permute(shift, p)
+    gdom, gcod = [ctx.basis(e) for e in dom], [ctx.basis(e) for e in cod]
+    stats = permute_plan_stats(ctx, gdom, gcod, shift, p) if not adjoint else None
+    scale = max(float(np.abs(ref.data).max()), 1.0)
+    for form in forms:
+        try:
+            out = permute_plan_emulate(ctx, gdom, gcod, shift, p, o.data, ref.plainSize(), form, adjoint)
+        except Exception as e:   # plans with the bulk form (even Abelian runs) carry no table-driven form
+            if form == 1 and "no table-driven form" in str(e):
+                continue
+            raise
+        assert not np.isnan(out).any()
+        err = float(np.abs(out - ref.data).max())
+        assert err <= TOL * scale, f"form {form} permute<{shift},{p}> adjoint={adjoint}: max abs error {err:.3e}"
+        if stats is not None and stats["max_fan_in"] <= 1 and not stats["identity"]:
+            # fan-in 1: one product per element (coefficient x value) on both sides -- bit-exact for coefficients +-1 (bosonic / fermionic Abelian)
+            if all(kind != "SU2" for kind, _, _ in ctx.spec):
+                assert np.array_equal(out, ref.data), f"form {form} permute<{shift},{p}>: Abelian plan is not bit-exact"
+
+
+@pytest.fixture(params=list(SPECS))
+def world(request):
+    name = request.param
+    ctx = PlanningContext(SPECS[name])
+    ctx.spec = SPECS[name]
+    yield name, ctx, xo.Symmetry.from_spec(SPECS[name])
+    ctx.close()
+
+
+def test_all_24_permutations_of_a_2_2_tensor(world):
+    """tests/tensor_tests.hpp:2-48 shape: Tensor<2,2> with odd multiplicities, all 24 permutations x shifts -2..2, both forms of the plan"""
+    name, ctx, osym = world
+    rng = np.random.default_rng(5)
+    B, C = rand_entries(SPECS[name], 8, rng), rand_entries(SPECS[name], 7, rng)
+    for shift in (-2, -1, 0, 1, 2):
+        for p in itertools.permutations(range(4)):
+            check(ctx, osym, [B, C], [B, C], shift, p, 3)
+
+
+def test_ctm_shaped_plans(world):
+    """corner-shaped (3,3) tensors and the (4,3) intermediate of a CTM move: the plans a CTM step actually builds (SU(2): recoupling sums with fan-in > 1),
+    extents without useful divisors so that the table-driven form needs its remainder regions"""
+    name, ctx, osym = world
+    rng = np.random.default_rng(17)
+    chi, aux = rand_entries(SPECS[name], 13, rng, 3), rand_entries(SPECS[name], 5, rng, 2)
+    for shift, p in [(-1, (0, 2, 3, 5, 1, 4)), (1, (0, 3, 5, 1, 2, 4)), (0, (1, 0, 2, 4, 3, 5)), (-3, (5, 4, 3, 2, 1, 0)), (2, (3, 1, 5, 0, 2, 4))]:
+        check(ctx, osym, [chi, aux, aux], [chi, aux, aux], shift, p, 14)
+    for shift, p in [(0, (0, 2, 1, 3, 5, 4, 6)), (-2, (6, 0, 5, 1, 4, 2, 3)), (1, (1, 0, 3, 2, 4, 6, 5))]:
+        check(ctx, osym, [chi, aux, aux, aux], [chi, aux, aux], shift, p, 15)
+
+
+def test_permute_adj_plans(world):
+    """the adjoint plans of the reverse pass (Tensor::permute_adj, src/Core/Tensor.cpp:258-333)"""
+    name, ctx, osym = world
+    rng = np.random.default_rng(23)
+    B, C = rand_entries(SPECS[name], 7, rng), rand_entries(SPECS[name], 6, rng)
+    for shift, p in [(1, (2, 0, 3, 1)), (-1, (0, 2, 3, 1)), (0, (1, 0, 3, 2)), (2, (3, 2, 1, 0))]:
+        check(ctx, osym, [B, C], [C, B], shift, p, 29, adjoint=True)
+
+
+def test_large_tiles_and_many_tiles():
+    """an SU(2) tensor large enough that sub-blocks span several 2048-element tiles per region (body of full tiles + remainders along two legs)"""
+    ctx = PlanningContext(SPECS["SU2"])
+    ctx.spec = SPECS["SU2"]
+    osym = xo.Symmetry.SU2()
+    e, a = [((1,), 7), ((2,), 13), ((3,), 9)], [((1,), 3), ((2,), 2)]
+    for shift, p in [(-1, (0, 2, 3, 5, 1, 4)), (1, (0, 3, 5, 1, 2, 4)), (0, (1, 0, 2, 4, 3, 5))]:
+        check(ctx, osym, [e, a, a], [e, a, a], shift, p, 41)
+    ctx.close()
+
+
+def test_emulation_is_refused_by_nothing_but_planning_contexts():
+    """the entry point is test support: it needs the host tables that only a planning-only context keeps"""
+    ctx = PlanningContext(SPECS["U1"])
+    B = ctx.basis([((q,), 3) for q in (-1, 0, 1)])
+    st = layout_structure(ctx, [B, B], [B, B])
+    n = sum(r * c for r, c in zip(st[1], st[2]))
+    with pytest.raises(Exception):
+        permute_plan_emulate(ctx, [B, B], [B, B], 0, (1, 0, 2, 3), np.zeros(n + 1), n, 0)   # wrong array size
+    with pytest.raises(Exception):
+        permute_plan_emulate(ctx, [B, B], [B, B], 0, (1, 0, 2, 3), np.zeros(n), n, 7)       # unknown form
+    ctx.close()

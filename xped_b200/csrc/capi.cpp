@@ -793,6 +793,23 @@ int xb_permute_plan_census(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_ba
     });
 }
 
+int xb_permute_plan_emulate(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n, int adjoint,
+                            int form, const double* src, int64_t n_src, double* dst, int64_t n_dst)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(src, "src");
+        need(dst, "dst");
+        if(!ctx->impl.planning_only()) throw std::invalid_argument("xb_permute_plan_emulate: test support of planning-only contexts (the device path is xb_permute)");
+        std::vector<BasisPtr> d, c;
+        collect_bases(domain, rank, codomain, corank, d, c);
+        LayoutPtr L = ctx->impl.layout(d, c);
+        auto plan = ctx->impl.permute_plan(L, shift, std::vector<int>(p, p + n), adjoint != 0);
+        if(n_src != L->size || n_dst != plan->out->size) throw std::invalid_argument("xb_permute_plan_emulate: array sizes do not match the tensors");
+        ctx->impl.emulate_permute_plan(*plan, form, src, n_src, dst, n_dst);
+    });
+}
+
 int xb_tensor_create_sectors(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, const int* q, int n_sectors,
                              xb_tensor** out)
 {

@@ -135,9 +135,25 @@ struct LutTask
 };
 struct LutTileSrc { long long off; double coeff; };   // origin of one tile inside one source, and that source's recoupling coefficient
 
+// Host copies of a plan's tables.  Kept only in planning-only contexts (no GPU), where the CPU tests walk them element by element the way the kernels do
+// (Context::emulate_permute_plan): the plan builder is the most intricate host logic of the path and can be checked against the oracle without a device.
+struct PlanHostTables
+{
+    std::vector<PermTask> tasks;
+    std::vector<PermSrc> srcs;
+    std::vector<PermTile> tiles;
+    std::vector<LutTask> ltasks;
+    std::vector<LutTileSrc> ltsrc;
+    std::vector<int> ltile_task;
+    std::vector<long long> ltile_dst;
+    std::vector<int> lut_int;
+    std::vector<unsigned short> lut_pos;
+};
+
 struct PermutePlan
 {
     LayoutPtr out;
+    std::shared_ptr<PlanHostTables> host;   // planning-only contexts
     int n_tasks = 0, n_srcs = 0, n_tiles = 0;
     int tiles_per_cta = 1;
     PermTask* d_tasks = nullptr;
@@ -285,6 +301,8 @@ public:
     LayoutPtr layout(const std::vector<BasisPtr>& dom, const std::vector<BasisPtr>& cod);
     LayoutPtr layout_custom(const std::vector<BasisPtr>& dom, const std::vector<BasisPtr>& cod, const std::vector<Q>& sectors);
     std::shared_ptr<PermutePlan> permute_plan(const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan);
+    // test support: applies the HOST tables of a plan of a planning-only context to host arrays (form 0: tile list of the LSU form, 1: table-driven form)
+    void emulate_permute_plan(const PermutePlan& plan, int form, const double* src, int64_t n_src, double* dst, int64_t n_dst) const;
     // sector-sharded permute: exchange plan of rank `rank` for the global tensor layout `in` (cached)
     std::shared_ptr<DistPermutePlan> dist_permute_plan(const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan,
                                                        const std::vector<int>& owner_in, const std::vector<int>& owner_out, int rank, int world);

@@ -6,6 +6,8 @@
 // into a gather plan (each destination sub-block = sum_k coeff_k * transpose(src_k)), tiled, uploaded and
 // cached; the data then moves in one kernel launch (kernels.cu: permute_kernel).
 #include <algorithm>
+#include <cmath>
+#include <limits>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -1221,7 +1223,22 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
             plan->lut_table_bytes = table_bytes_all;
         }
     }
-    if(ctx.planning_only()) return;
+    if(ctx.planning_only()) {   // no device: keep the tables for the host walk of the CPU tests
+        auto H = std::make_shared<PlanHostTables>();
+        H->tasks = h_tasks;
+        H->srcs = h_srcs;
+        H->tiles = h_tiles;
+        if(plan->n_ltiles > 0) {
+            H->ltasks = lut.tasks;
+            H->ltsrc = lut.tsrc;
+            H->ltile_task = lut.tile_task;
+            H->ltile_dst = lut.tile_dst;
+            H->lut_int = lut.tab_int;
+            H->lut_pos = lut.tab_pos;
+        }
+        plan->host = H;
+        return;
+    }
     if(plan->n_tasks) {
         check_cuda(cudaMalloc(&plan->d_tasks, h_tasks.size() * sizeof(PermTask)), "cudaMalloc plan tasks");
         check_cuda(cudaMemcpy(plan->d_tasks, h_tasks.data(), h_tasks.size() * sizeof(PermTask), cudaMemcpyHostToDevice), "upload plan tasks");
@@ -1539,6 +1556,80 @@ void Context::dist_remote(const DistPermutePlan& plan, const Tensor& local_in, c
     ProfScope prof(*this, CAT_PERMUTE, 0.0);
     launch_permute2(local_in.d, d_recv, plan.split, local_out.d, plan.remote, stream);
     ++launches;
+}
+
+// Walks the host tables of a plan exactly as the kernels address them: form 0 = tile list of the LSU form (permute_kernel: tile origin from the tile coordinates,
+// tile clipped at the sub-block, every source of the task), form 1 = table-driven form (permute_lut_kernel: offsets of every tile element in every source,
+// staging position and destination offset in destination order).  Every index is bounds-checked and every destination element has to be written exactly once.
+void Context::emulate_permute_plan(const PermutePlan& plan, int form, const double* src, int64_t n_src, double* dst, int64_t n_dst) const
+{
+    if(plan.identity_copy) {
+        if(n_src != n_dst) throw std::invalid_argument("emulate_permute_plan: identity plan with different sizes");
+        std::copy(src, src + n_src, dst);
+        return;
+    }
+    if(!plan.host) throw std::invalid_argument("emulate_permute_plan: the plan has no host tables (planning-only contexts keep them)");
+    const PlanHostTables& H = *plan.host;
+    std::vector<unsigned char> written(static_cast<size_t>(n_dst), 0);
+    auto put = [&](long long o, double v) {
+        if(o < 0 || o >= n_dst) throw std::runtime_error("emulate_permute_plan: destination offset out of range");
+        if(written[static_cast<size_t>(o)]++) throw std::runtime_error("emulate_permute_plan: destination element written twice");
+        dst[o] = v;
+    };
+    auto get = [&](long long o) {
+        if(o < 0 || o >= n_src) throw std::runtime_error("emulate_permute_plan: source offset out of range");
+        return src[o];
+    };
+    if(form == 0) {
+        for(const PermTile& tile : H.tiles) {
+            const PermTask& T = H.tasks.at(static_cast<size_t>(tile.task));
+            const int n = T.nleg;
+            int origin[PERM_MAXLEG], ext[PERM_MAXLEG], idx[PERM_MAXLEG];
+            long long count = 1;
+            for(int l = 0; l < n; ++l) {
+                origin[l] = static_cast<int>(tile.c[l]) * T.w[l];
+                ext[l] = std::min(T.w[l], T.dims[l] - origin[l]);
+                if(ext[l] <= 0) throw std::runtime_error("emulate_permute_plan: empty tile");
+                idx[l] = 0;
+                count *= ext[l];
+            }
+            for(long long e = 0; e < count; ++e) {
+                long long od = T.dst_off & PERM_OFF_MASK;
+                for(int l = 0; l < n; ++l) od += static_cast<long long>(origin[l] + idx[l]) * T.dstride[l];
+                double acc = 0.0;
+                for(int k = 0; k < T.src_count; ++k) {
+                    const PermSrc& S = H.srcs.at(static_cast<size_t>(T.src_begin + k));
+                    long long os = S.off;
+                    for(int l = 0; l < n; ++l) os += static_cast<long long>(origin[l] + idx[l]) * S.sstride[l];
+                    acc = std::fma(S.coeff, get(os), acc);
+                }
+                put(od, acc);
+                for(int l = 0; l < n; ++l) {
+                    if(++idx[l] < ext[l]) break;
+                    idx[l] = 0;
+                }
+            }
+        }
+    } else if(form == 1) {
+        if(H.ltile_task.empty()) throw std::invalid_argument("emulate_permute_plan: the plan has no table-driven form");
+        std::vector<double> staged(LUT_TILE_ELEMS + LUT_TILE_ELEMS / 32 + 8);
+        for(size_t ti = 0; ti < H.ltile_task.size(); ++ti) {
+            const LutTask& T = H.ltasks.at(static_cast<size_t>(H.ltile_task[ti]));
+            const LutTileSrc* ts = H.ltsrc.data() + T.tsrc_begin + (static_cast<long long>(ti) - T.first_tile) * T.src_count;
+            if(T.vol > LUT_TILE_ELEMS) throw std::runtime_error("emulate_permute_plan: tile larger than the tile budget");
+            std::fill(staged.begin(), staged.end(), std::numeric_limits<double>::quiet_NaN());
+            for(int e = 0; e < T.vol; ++e) {   // read phase: element e in the order of the first source, accumulated over the sources in order
+                double acc = 0.0;
+                for(int k = 0; k < T.src_count; ++k) acc = std::fma(ts[k].coeff, get(ts[k].off + H.lut_int.at(static_cast<size_t>(T.soff_tab) + static_cast<size_t>(k) * T.vol + e)), acc);
+                staged.at(static_cast<size_t>(e + (e >> 5))) = acc;
+            }
+            for(int e = 0; e < T.vol; ++e)   // write phase: destination order
+                put(H.ltile_dst[ti] + H.lut_int.at(static_cast<size_t>(T.doff_tab) + e), staged.at(H.lut_pos.at(static_cast<size_t>(T.spos_tab) + e)));
+        }
+    } else
+        throw std::invalid_argument("emulate_permute_plan: form must be 0 (tile list) or 1 (table-driven)");
+    for(int64_t o = 0; o < n_dst; ++o)
+        if(!written[static_cast<size_t>(o)]) throw std::runtime_error("emulate_permute_plan: destination element " + std::to_string(o) + " never written");
 }
 
 std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan)

@@ -379,3 +379,14 @@ def permute_plan_stats(ctx, domain, codomain, shift, p):
     out = (C.c_int64 * 6)()
     check(ctx.lib.xb_permute_plan_stats(ctx.h, _handles(domain), len(domain), _handles(codomain), len(codomain), int(shift), _ints(p), len(p), out))
     return dict(tasks=out[0], tiles=out[1], max_fan_in=out[2], identity=bool(out[3]), bulk_tiles=out[4], bytes=out[5])
+
+
+def permute_plan_emulate(ctx, domain, codomain, shift, p, src, n_dst, form, adjoint=False):
+    """TEST SUPPORT (planning-only contexts): walks the host tables of the permute plan over the `m_data` image `src` like the kernels do
+    (form 0: tile list of the LSU form, 1: table-driven form) and returns the `m_data` image of the result"""
+    src = np.ascontiguousarray(src, dtype=np.float64)
+    dst = np.full(int(n_dst), np.nan)
+    DP = C.POINTER(C.c_double)
+    check(ctx.lib.xb_permute_plan_emulate(ctx.h, _handles(domain), len(domain), _handles(codomain), len(codomain), int(shift), _ints(p), len(p), int(bool(adjoint)),
+                                          int(form), src.ctypes.data_as(DP), src.size, dst.ctypes.data_as(DP), dst.size))
+    return dst

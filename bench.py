@@ -718,7 +718,7 @@ def run_b200(args):
                 b6 = min(d6["steps"], key=lambda r: r["ms"])
                 roofline["in_ctm_step_d6_chi144"] = {"launches_per_step": b6["launch_groups"]["permute"], "ms": b6["device_ms"]["permute"], "GBps": b6["permute_GBps"],
                                                      "frac": b6["permute_GBps"] / hbm_peak, "share_of_step": b6["device_ms"]["permute"] / b6["ms"],
-                                                     "note": "SU(2) plans: LSU form, recoupling sums read every source element 2.1-2.3 times (DESIGN.md 9.2)"}
+                                                     "note": "SU(2) plans: table-driven form (permute_lut_kernel), recoupling sums read every source element 2.1-2.3 times (DESIGN.md 9.2)"}
             roofline_contract = {"kernel": "gemm_grouped_kernel", "bound": "tensor", "achieved": extras["contract_w4"]["TFLOPs"], "peak": dgemm_peak,
                                  "unit": "TFLOP/s", "frac": extras["contract_w4"]["TFLOPs"] / dgemm_peak, "traffic": traffic.get("gemm_grouped_kernel"),
                                  "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)",

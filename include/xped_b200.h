@@ -184,6 +184,13 @@ int xb_permute_plan_census(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_ba
  * input / output tensor.  The CPU tests compare the result with the oracle's Tensor::permute (src/Core/Tensor.cpp:83-214). */
 int xb_permute_plan_emulate(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n, int adjoint,
                             int form, const double* src, int64_t n_src, double* dst, int64_t n_dst);
+/* TEST SUPPORT, planning-only contexts only: the host lists of op(A) * op(B) (tile items of both kernel variants, split-K jobs, scratch slices; built for a
+ * device with `sm_count` SMs, <= 0: the context's default of 148) applied to host arrays the way gemm_grouped_kernel / splitk_reduce_kernel address device
+ * memory, bounds-checked and write-once-checked.  counts = {128-row tile items, 64-row tile items, split-K jobs, scratch elements}.  The CPU tests compare the
+ * result with per-sector products of the oracle (TensorBase::operator*, src/Core/TensorBase.cpp:243-288). */
+int xb_multiply_plan_emulate(xb_ctx* ctx, xb_basis* const* a_domain, int a_rank, xb_basis* const* a_codomain, int a_corank, int adj_a, xb_basis* const* b_domain,
+                             int b_rank, xb_basis* const* b_codomain, int b_corank, int adj_b, int sm_count, const double* a, int64_t n_a, const double* b, int64_t n_b,
+                             double* c, int64_t n_c, int64_t counts[4]);
 /* a shard: Tensor(domain, codomain) holding only the listed sectors, in that order, zero-initialised */
 int xb_tensor_create_sectors(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, const int* q, int n_sectors,
                              xb_tensor** out);

@@ -810,6 +810,34 @@ int xb_permute_plan_emulate(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_b
     });
 }
 
+int xb_multiply_plan_emulate(xb_ctx* ctx, xb_basis* const* a_domain, int a_rank, xb_basis* const* a_codomain, int a_corank, int adj_a, xb_basis* const* b_domain,
+                             int b_rank, xb_basis* const* b_codomain, int b_corank, int adj_b, int sm_count, const double* a, int64_t n_a, const double* b, int64_t n_b,
+                             double* c, int64_t n_c, int64_t counts[4])
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(a, "a");
+        need(b, "b");
+        need(c, "c");
+        if(!ctx->impl.planning_only()) throw std::invalid_argument("xb_multiply_plan_emulate: test support of planning-only contexts (the device path is xb_multiply)");
+        std::vector<BasisPtr> ad, ac, bd, bc;
+        collect_bases(a_domain, a_rank, a_codomain, a_corank, ad, ac);
+        collect_bases(b_domain, b_rank, b_codomain, b_corank, bd, bc);
+        LayoutPtr LA = ctx->impl.layout(ad, ac), LB = ctx->impl.layout(bd, bc);
+        LayoutPtr LO = ctx->impl.layout(adj_a ? ac : ad, adj_b ? bd : bc);
+        if(n_a != LA->size || n_b != LB->size || n_c != LO->size) throw std::invalid_argument("xb_multiply_plan_emulate: array sizes do not match the tensors");
+        const GemmLists G = build_gemm_lists(multiply_problems(*LA, adj_a != 0, *LB, adj_b != 0, *LO), sm_count > 0 ? sm_count : ctx->impl.sm_count);
+        std::fill(c, c + n_c, 0.0);   // Tout.setZero(): sectors missing in an operand stay zero blocks
+        emulate_gemm_lists(G, a, n_a, b, n_b, c, n_c);
+        if(counts) {
+            counts[0] = static_cast<int64_t>(G.items[0].size());
+            counts[1] = static_cast<int64_t>(G.items[1].size());
+            counts[2] = static_cast<int64_t>(G.jobs.size());
+            counts[3] = G.scratch_elems;
+        }
+    });
+}
+
 int xb_tensor_create_sectors(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, const int* q, int n_sectors,
                              xb_tensor** out)
 {

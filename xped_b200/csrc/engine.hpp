@@ -231,6 +231,18 @@ struct GemmItem   // one (sector, tile) of a grouped product
 // one split-K problem: C[c_off + i + j ldc] = sum_s scratch[s_off + s m n + i + j m]
 struct SplitKJob { long long c_off, s_off; int m, n, ldc, split; };
 
+// host lists of a grouped product (ops.cpp: build_gemm_lists)
+struct GemmLists
+{
+    std::vector<GemmItem> items[2];   // [0]: 128 x 64 tiles, [1]: 64 x 64 tiles
+    std::vector<SplitKJob> jobs;
+    long long scratch_elems = 0;
+    double flops = 0.0;
+};
+GemmLists build_gemm_lists(const std::vector<GemmItem>& problems, int sm_count);
+void emulate_gemm_lists(const GemmLists& G, const double* A, int64_t n_a, const double* B, int64_t n_b, double* C, int64_t n_c);   // test support
+std::vector<GemmItem> multiply_problems(const Layout& LA, bool adj_a, const Layout& LB, bool adj_b, const Layout& LO);
+
 // a grouped product whose tile lists are already on the device: launched any number of times (iterative solvers, graph capture)
 struct PreparedGemm
 {

@@ -1,5 +1,6 @@
 // Whole-tensor operations of the B200 backend (the methods of Xped::Tensor that sit on the hot path).
 #include <algorithm>
+#include <limits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -67,15 +68,15 @@ Tensor* Context::copy(const Tensor& t)
 }
 
 // ------------------------------------------------------------------------------------------------ grouped GEMM launcher
-PreparedGemm Context::prepare_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems)
+// Host part of prepare_gemm: tile lists of the two kernel variants, split-K jobs and the size of their scratch buffer.  A pure function of the problem list and
+// the SM count -- no device involved, so that the CPU tests can walk the lists element by element (Context::emulate_gemm).  Scratch destinations are marked
+// pad_ = 1 with c_off relative to the scratch buffer; prepare_gemm rebases them onto the allocation.
+GemmLists build_gemm_lists(const std::vector<GemmItem>& problems, int sm_count)
 {
-    PreparedGemm P;
-    P.A = A;
-    P.B = B;
-    P.C = C;
-    std::vector<GemmItem> items[2];   // [0]: 128 x 64 tiles (sectors with m > 96), [1]: 64 x 64 tiles
-    std::vector<SplitKJob> jobs;      // problems with few tiles and a long K: K is cut into slices, the partial products are summed afterwards
-    long long scratch_elems = 0;
+    GemmLists G;
+    std::vector<GemmItem>(&items)[2] = G.items;   // [0]: 128 x 64 tiles (sectors with m > 96), [1]: 64 x 64 tiles
+    std::vector<SplitKJob>& jobs = G.jobs;        // problems with few tiles and a long K: K is cut into slices, the partial products are summed afterwards
+    long long& scratch_elems = G.scratch_elems;
     static const bool no_split = std::getenv("XB_GEMM_NOSPLIT") != nullptr;
     // (measured in round 2 and removed again: summing the slices inside gemm_grouped_kernel by the last slice CTA of a tile (ticket counters) -- 32.2 vs
     // 26.3 ms per D=4 CTM step, and the extra epilogue raised the 128-row kernel from 168 to 207 registers: 2 instead of 3 CTAs per SM, W4 T*T 23.8 vs 29.1
@@ -107,7 +108,7 @@ PreparedGemm Context::prepare_gemm(const double* A, const double* B, double* C, 
     static const int wave_split = std::getenv("XB_GEMM_WAVE_SPLIT") ? std::atoi(std::getenv("XB_GEMM_WAVE_SPLIT")) : 6;   // target CTAs per SM (0: off)
     for(GemmItem g : problems) {
         if(g.m <= 0 || g.n <= 0) continue;
-        P.flops += 2.0 * g.m * static_cast<double>(g.n) * g.k;
+        G.flops += 2.0 * g.m * static_cast<double>(g.n) * g.k;
         const int which = (g.m > 96 && !force64) ? 0 : 1, tile_m = which == 0 ? 128 : 64;
         const int ntiles = ((g.m + tile_m - 1) / tile_m) * ((g.n + GEMM_TILE_N - 1) / GEMM_TILE_N);
         int split = 1;
@@ -151,6 +152,20 @@ PreparedGemm Context::prepare_gemm(const double* A, const double* B, double* C, 
                 items[which].push_back(g);
             }
     }
+    return G;
+}
+
+PreparedGemm Context::prepare_gemm(const double* A, const double* B, double* C, const std::vector<GemmItem>& problems)
+{
+    PreparedGemm P;
+    P.A = A;
+    P.B = B;
+    P.C = C;
+    GemmLists G = build_gemm_lists(problems, sm_count);
+    std::vector<GemmItem>(&items)[2] = G.items;
+    std::vector<SplitKJob>& jobs = G.jobs;
+    const long long scratch_elems = G.scratch_elems;
+    P.flops = G.flops;
     if(items[0].empty() && items[1].empty()) return P;
     static const bool gemm_log = std::getenv("XB_GEMM_LOG") != nullptr;
     if(gemm_log) {
@@ -222,6 +237,91 @@ void Context::run_gemm(const double* A, const double* B, double* C, const std::v
 // ------------------------------------------------------------------------------------------------ operator*
 // TensorBase::operator* (src/Core/TensorBase.cpp:243-288). Operands may be lazy adjoints (AdjointOp.hpp:26-69):
 // the block is then read transposed, domain/codomain swap roles, the sector list stays the operand's.
+// Test support (planning-only contexts): walks the host lists of a grouped product the way gemm_grouped_kernel / splitk_reduce_kernel address device memory --
+// every (problem, tile) item computes its clipped tile of alpha * op(A) op(B) over its K range into C or into its slice of the scratch buffer, the split-K jobs
+// sum their slices in slice order -- with every offset bounds-checked and every element of a non-accumulating destination written exactly once.
+void emulate_gemm_lists(const GemmLists& G, const double* A, int64_t n_a, const double* B, int64_t n_b, double* C, int64_t n_c)
+{
+    std::vector<double> scratch(static_cast<size_t>(std::max<long long>(G.scratch_elems, 0)), std::numeric_limits<double>::quiet_NaN());
+    std::vector<unsigned char> written_c(static_cast<size_t>(n_c), 0), written_s(scratch.size(), 0);
+    auto at = [](const double* p, int64_t n, long long o, const char* what) {
+        if(o < 0 || o >= n) throw std::runtime_error(std::string("emulate_gemm_lists: ") + what + " offset out of range");
+        return p[o];
+    };
+    for(int which = 0; which < 2; ++which) {
+        const int tile_m = which == 0 ? 128 : 64;
+        for(const GemmItem& it : G.items[which]) {
+            if(it.tm % tile_m != 0 || it.tn % GEMM_TILE_N != 0 || it.tm >= it.m || it.tn >= it.n) throw std::runtime_error("emulate_gemm_lists: bad tile origin");
+            const int i1 = std::min(it.m, it.tm + tile_m), j1 = std::min(it.n, it.tn + GEMM_TILE_N);
+            for(int j = it.tn; j < j1; ++j)
+                for(int i = it.tm; i < i1; ++i) {
+                    double acc = 0.0;
+                    for(int kk = 0; kk < it.k; ++kk) {
+                        const double a = at(A, n_a, it.a_off + (it.ta ? kk + static_cast<long long>(i) * it.lda : i + static_cast<long long>(kk) * it.lda), "A");
+                        const double b = at(B, n_b, it.b_off + (it.tb ? j + static_cast<long long>(kk) * it.ldb : kk + static_cast<long long>(j) * it.ldb), "B");
+                        acc = std::fma(a, b, acc);
+                    }
+                    const long long o = it.c_off + i + static_cast<long long>(j) * it.ldc;
+                    if(it.pad_) {   // a K slice: scratch destination
+                        if(o < 0 || o >= static_cast<long long>(scratch.size())) throw std::runtime_error("emulate_gemm_lists: scratch offset out of range");
+                        if(written_s[static_cast<size_t>(o)]++) throw std::runtime_error("emulate_gemm_lists: scratch element written twice");
+                        scratch[static_cast<size_t>(o)] = it.alpha * acc;
+                    } else {
+                        if(o < 0 || o >= n_c) throw std::runtime_error("emulate_gemm_lists: C offset out of range");
+                        if(!it.acc && written_c[static_cast<size_t>(o)]++) throw std::runtime_error("emulate_gemm_lists: C element written twice");
+                        C[o] = it.acc ? C[o] + it.alpha * acc : it.alpha * acc;
+                    }
+                }
+        }
+    }
+    for(const SplitKJob& j : G.jobs) {
+        const long long cnt = static_cast<long long>(j.m) * j.n;
+        for(long long e = 0; e < cnt; ++e) {
+            double sum = 0.0;
+            for(int sl = 0; sl < j.split; ++sl) {
+                const long long o = j.s_off + sl * cnt + e;
+                if(o < 0 || o >= static_cast<long long>(scratch.size()) || !written_s[static_cast<size_t>(o)]) throw std::runtime_error("emulate_gemm_lists: slice element missing");
+                sum += scratch[static_cast<size_t>(o)];
+            }
+            const long long col = e / j.m, o = j.c_off + (e - col * j.m) + col * j.ldc;
+            if(o < 0 || o >= n_c) throw std::runtime_error("emulate_gemm_lists: job destination out of range");
+            if(written_c[static_cast<size_t>(o)]++) throw std::runtime_error("emulate_gemm_lists: C element written twice");
+            C[o] = sum;
+        }
+    }
+}
+
+// the per-sector problems of operator* (src/Core/TensorBase.cpp:262-279): host metadata only
+std::vector<GemmItem> multiply_problems(const Layout& LA, bool adj_a, const Layout& LB, bool adj_b, const Layout& LO)
+{
+    std::vector<GemmItem> items;
+    for(size_t i = 0; i < LA.sector.size(); ++i) {
+        const int j = LB.find(LA.sector[i]);
+        if(j < 0) continue;
+        const int o = LO.find(LA.sector[i]);
+        if(o < 0) continue;
+        GemmItem g;
+        std::memset(&g, 0, sizeof(g));
+        g.a_off = LA.off[i];
+        g.b_off = LB.off[j];
+        g.c_off = LO.off[o];
+        g.lda = static_cast<int>(LA.rows[i]);
+        g.ldb = static_cast<int>(LB.rows[j]);
+        g.ldc = static_cast<int>(LO.rows[o]);
+        g.ta = adj_a;
+        g.tb = adj_b;
+        g.m = static_cast<int>(adj_a ? LA.cols[i] : LA.rows[i]);
+        g.k = static_cast<int>(adj_a ? LA.rows[i] : LA.cols[i]);
+        const int kb = static_cast<int>(adj_b ? LB.cols[j] : LB.rows[j]);
+        g.n = static_cast<int>(adj_b ? LB.rows[j] : LB.cols[j]);
+        if(kb != g.k || g.m != LO.rows[o] || g.n != LO.cols[o]) throw std::logic_error("operator*: block shape mismatch");
+        if(g.m == 0 || g.n == 0) continue;
+        g.alpha = 1.0;
+        items.push_back(g);
+    }
+    return items;
+}
+
 Tensor* Context::multiply(const Tensor& a, bool adj_a, const Tensor& b, bool adj_b) { return multiply_sectors(a, adj_a, b, adj_b, nullptr); }
 
 // `out_sectors` (sector-sharded operands): the result holds exactly these sectors in this order (the ones this
@@ -251,31 +351,7 @@ Tensor* Context::multiply_sectors(const Tensor& a, bool adj_a, const Tensor& b, 
     }
     auto* out = new Tensor(this, LO, covered != LO->sector.size());
 
-    std::vector<GemmItem> items;
-    for(size_t i = 0; i < LA.sector.size(); ++i) {
-        const int j = LB.find(LA.sector[i]);
-        if(j < 0) continue;
-        const int o = LO->find(LA.sector[i]);
-        if(o < 0) continue;
-        GemmItem g;
-        std::memset(&g, 0, sizeof(g));
-        g.a_off = LA.off[i];
-        g.b_off = LB.off[j];
-        g.c_off = LO->off[o];
-        g.lda = static_cast<int>(LA.rows[i]);
-        g.ldb = static_cast<int>(LB.rows[j]);
-        g.ldc = static_cast<int>(LO->rows[o]);
-        g.ta = adj_a;
-        g.tb = adj_b;
-        g.m = static_cast<int>(adj_a ? LA.cols[i] : LA.rows[i]);
-        g.k = static_cast<int>(adj_a ? LA.rows[i] : LA.cols[i]);
-        const int kb = static_cast<int>(adj_b ? LB.cols[j] : LB.rows[j]);
-        g.n = static_cast<int>(adj_b ? LB.rows[j] : LB.cols[j]);
-        if(kb != g.k || g.m != LO->rows[o] || g.n != LO->cols[o]) throw std::logic_error("operator*: block shape mismatch");
-        if(g.m == 0 || g.n == 0) continue;
-        g.alpha = 1.0;
-        items.push_back(g);
-    }
+    std::vector<GemmItem> items = multiply_problems(LA, adj_a, LB, adj_b, *LO);
     {
         static const bool no_cache = std::getenv("XB_GEMM_NOCACHE") != nullptr;
         const std::string key = LA.sig + "|" + LB.sig + "|" + LO->sig + (adj_a ? "|a" : "|n") + (adj_b ? "a" : "n");

@@ -390,3 +390,16 @@ def permute_plan_emulate(ctx, domain, codomain, shift, p, src, n_dst, form, adjo
     check(ctx.lib.xb_permute_plan_emulate(ctx.h, _handles(domain), len(domain), _handles(codomain), len(codomain), int(shift), _ints(p), len(p), int(bool(adjoint)),
                                           int(form), src.ctypes.data_as(DP), src.size, dst.ctypes.data_as(DP), dst.size))
     return dst
+
+
+def multiply_plan_emulate(ctx, a_dom, a_cod, adj_a, b_dom, b_cod, adj_b, a_data, b_data, n_c, sm_count=0):
+    """TEST SUPPORT (planning-only contexts): applies the host lists of op(A) * op(B) (tile items, split-K jobs) to the `m_data` images of the operands like
+    the grouped GEMM kernels do; returns (m_data image of the product, dict of list sizes)"""
+    a_data, b_data = np.ascontiguousarray(a_data, dtype=np.float64), np.ascontiguousarray(b_data, dtype=np.float64)
+    c = np.full(int(n_c), np.nan)
+    DP = C.POINTER(C.c_double)
+    counts = (C.c_int64 * 4)()
+    check(ctx.lib.xb_multiply_plan_emulate(ctx.h, _handles(a_dom), len(a_dom), _handles(a_cod), len(a_cod), int(bool(adj_a)), _handles(b_dom), len(b_dom),
+                                           _handles(b_cod), len(b_cod), int(bool(adj_b)), int(sm_count), a_data.ctypes.data_as(DP), a_data.size,
+                                           b_data.ctypes.data_as(DP), b_data.size, c.ctypes.data_as(DP), c.size, counts))
+    return c, dict(tiles128=counts[0], tiles64=counts[1], jobs=counts[2], scratch=counts[3])

@@ -69,7 +69,7 @@ Tensor* Context::copy(const Tensor& t)
 
 // ------------------------------------------------------------------------------------------------ grouped GEMM launcher
 // Host part of prepare_gemm: tile lists of the two kernel variants, split-K jobs and the size of their scratch buffer.  A pure function of the problem list and
-// the SM count -- no device involved, so that the CPU tests can walk the lists element by element (Context::emulate_gemm).  Scratch destinations are marked
+// the SM count -- no device involved, so that the CPU tests can walk the lists element by element (emulate_gemm_lists).  Scratch destinations are marked
 // pad_ = 1 with c_off relative to the scratch buffer; prepare_gemm rebases them onto the allocation.
 GemmLists build_gemm_lists(const std::vector<GemmItem>& problems, int sm_count)
 {

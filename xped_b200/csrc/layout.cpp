@@ -958,42 +958,55 @@ static void lower_lut_region(const PermTask& T, const PermSrc* src, const int* s
                 m *= L.w[order[j]];
             }
         }
-        int idx[PERM_MAXLEG];
-        for(int e = 0; e < V; ++e) {
-            int r = e;
-            for(int j = 0; j < n; ++j) {
-                idx[order[j]] = r % L.w[order[j]];
-                r /= L.w[order[j]];
-            }
-            for(int k = 0; k < T.src_count; ++k) {
-                long long o = 0;
-                for(int l = 0; l < n; ++l) o += static_cast<long long>(idx[l]) * src[k].sstride[l];
-                if(o > INT32_MAX) {
-                    B.ok = false;
-                    return;
+        // both tables are filled by an odometer over the tile legs (offsets advance by the leg's stride and fall back on a carry): no division per element
+        {
+            int idx[PERM_MAXLEG] = {0, 0, 0, 0, 0, 0, 0, 0};
+            std::vector<long long> cur(static_cast<size_t>(std::max(T.src_count, 0)), 0);
+            for(int e = 0; e < V; ++e) {   // staging order: legs by increasing stride of the first source
+                for(int k = 0; k < T.src_count; ++k) {
+                    if(cur[k] > INT32_MAX) {
+                        B.ok = false;
+                        return;
+                    }
+                    B.tab_int[soff_tab + static_cast<size_t>(k) * V + e] = static_cast<int>(cur[k]);
                 }
-                B.tab_int[soff_tab + static_cast<size_t>(k) * V + e] = static_cast<int>(o);
+                for(int j = 0; j < n; ++j) {
+                    const int l = order[j];
+                    if(++idx[l] < L.w[l]) {
+                        for(int k = 0; k < T.src_count; ++k) cur[k] += src[k].sstride[l];
+                        break;
+                    }
+                    idx[l] = 0;
+                    for(int k = 0; k < T.src_count; ++k) cur[k] -= static_cast<long long>(L.w[l] - 1) * src[k].sstride[l];
+                }
             }
         }
         const int doff_tab = static_cast<int>(B.tab_int.size());
         B.tab_int.resize(B.tab_int.size() + V);
         const int spos_tab = static_cast<int>(B.tab_pos.size());
         B.tab_pos.resize(B.tab_pos.size() + V);
-        for(int e = 0; e < V; ++e) {   // destination order: leg 0 fastest
-            int r = e, se = 0;
+        {
+            int idx[PERM_MAXLEG] = {0, 0, 0, 0, 0, 0, 0, 0};
             long long o = 0;
-            for(int l = 0; l < n; ++l) {
-                const int i = r % L.w[l];
-                r /= L.w[l];
-                o += static_cast<long long>(i) * L.dstride[l];
-                se += i * sm_stride[l];
+            int se = 0;
+            for(int e = 0; e < V; ++e) {   // destination order: leg 0 fastest
+                if(o > INT32_MAX) {
+                    B.ok = false;
+                    return;
+                }
+                B.tab_int[doff_tab + e] = static_cast<int>(o);
+                B.tab_pos[spos_tab + e] = static_cast<unsigned short>(lut_staging_pos(se));
+                for(int l = 0; l < n; ++l) {
+                    if(++idx[l] < L.w[l]) {
+                        o += L.dstride[l];
+                        se += sm_stride[l];
+                        break;
+                    }
+                    idx[l] = 0;
+                    o -= static_cast<long long>(L.w[l] - 1) * L.dstride[l];
+                    se -= (L.w[l] - 1) * sm_stride[l];
+                }
             }
-            if(o > INT32_MAX) {
-                B.ok = false;
-                return;
-            }
-            B.tab_int[doff_tab + e] = static_cast<int>(o);
-            B.tab_pos[spos_tab + e] = static_cast<unsigned short>(lut_staging_pos(se));
         }
         if(B.tab_int.size() > (1ull << 30)) {
             B.ok = false;

@@ -106,3 +106,20 @@ def test_emulation_is_refused_by_nothing_but_planning_contexts():
     with pytest.raises(Exception):
         permute_plan_emulate(ctx, [B, B], [B, B], 0, (1, 0, 2, 3), np.zeros(n), n, 7)       # unknown form
     ctx.close()
+
+
+def test_w3_corner_plans_both_forms_agree_at_full_size():
+    """configs[3] shape: the SU(2) D=6 chi=144 corner Q(3,3) (19.3 M elements, 442 sub-blocks, recoupling sums with fan-in up to 5).  The tile list of the LSU
+    form and the tables of the table-driven form (11.5 k tiles, ~10 MB of tables, full tiles + remainder regions) are walked over the same random data: both
+    visit every destination element exactly once, stay inside the arrays, and -- accumulating over the sources in the same order -- agree bit for bit."""
+    ctx = PlanningContext(SPECS["SU2"])
+    a, e = ctx.basis([((1,), 3), ((2,), 3)]), ctx.basis([((1,), 16), ((2,), 32), ((3,), 36), ((4,), 30), ((5,), 18), ((6,), 8), ((7,), 4)])
+    st = layout_structure(ctx, [e, a, a], [e, a, a])
+    n = int(sum(r * c for r, c in zip(st[1], st[2])))
+    assert n == 19327896
+    src = uniform_fill(9, n)
+    for shift, p in [(-1, (0, 2, 3, 5, 1, 4)), (1, (0, 3, 5, 1, 2, 4)), (0, (1, 0, 2, 4, 3, 5))]:
+        lsu = permute_plan_emulate(ctx, [e, a, a], [e, a, a], shift, p, src, n, 0)
+        lut = permute_plan_emulate(ctx, [e, a, a], [e, a, a], shift, p, src, n, 1)
+        assert not np.isnan(lsu).any() and np.array_equal(lsu, lut), (shift, p)
+    ctx.close()

@@ -191,6 +191,12 @@ int xb_permute_plan_emulate(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_b
 int xb_multiply_plan_emulate(xb_ctx* ctx, xb_basis* const* a_domain, int a_rank, xb_basis* const* a_codomain, int a_corank, int adj_a, xb_basis* const* b_domain,
                              int b_rank, xb_basis* const* b_codomain, int b_corank, int adj_b, int sm_count, const double* a, int64_t n_a, const double* b, int64_t n_b,
                              double* c, int64_t n_c, int64_t counts[4]);
+/* TEST SUPPORT, planning-only contexts only: contract<labels_a, labels_b, res_rank> (include/Xped/Core/Tensor.hpp:328-351) the way the device path lowers it --
+ * get_permutations (Util/Constfct.hpp:55-109), two operand permutes, the grouped product, the permute of the result -- with every plan / list walked on the
+ * host (table_form != 0: the table-driven form of the permute plans where a plan has it, else their tile lists). */
+int xb_contract_plan_emulate(xb_ctx* ctx, xb_basis* const* a_domain, int a_rank, xb_basis* const* a_codomain, int a_corank, const int* labels_a,
+                             xb_basis* const* b_domain, int b_rank, xb_basis* const* b_codomain, int b_corank, const int* labels_b, int res_rank, int table_form,
+                             const double* a, int64_t n_a, const double* b, int64_t n_b, double* c, int64_t n_c);
 /* a shard: Tensor(domain, codomain) holding only the listed sectors, in that order, zero-initialised */
 int xb_tensor_create_sectors(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, const int* q, int n_sectors,
                              xb_tensor** out);

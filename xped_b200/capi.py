@@ -135,6 +135,7 @@ SIGNATURES = {
     "xb_permute_plan_stats": (C.c_int, [P, PP, C.c_int, PP, C.c_int, C.c_int, IP, C.c_int, LP]),
     "xb_permute_plan_census": (C.c_int, [P, PP, C.c_int, PP, C.c_int, C.c_int, IP, C.c_int, LP]),
     "xb_multiply_plan_emulate": (C.c_int, [P, PP, C.c_int, PP, C.c_int, C.c_int, PP, C.c_int, PP, C.c_int, C.c_int, C.c_int, DP, C.c_int64, DP, C.c_int64, DP, C.c_int64, LP]),
+    "xb_contract_plan_emulate": (C.c_int, [P, PP, C.c_int, PP, C.c_int, IP, PP, C.c_int, PP, C.c_int, IP, C.c_int, C.c_int, DP, C.c_int64, DP, C.c_int64, DP, C.c_int64]),
     "xb_permute_plan_emulate": (C.c_int, [P, PP, C.c_int, PP, C.c_int, C.c_int, IP, C.c_int, C.c_int, C.c_int, DP, C.c_int64, DP, C.c_int64]),
     "xb_ctm_rdm": (C.c_int, [P, C.c_int, PP]),
     "xb_avg_two_site": (C.c_int, [P, P, P, DP]),

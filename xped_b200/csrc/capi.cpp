@@ -2,6 +2,7 @@
 #include "../../include/xped_b200.h"
 
 #include <algorithm>
+#include <limits>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -835,6 +836,45 @@ int xb_multiply_plan_emulate(xb_ctx* ctx, xb_basis* const* a_domain, int a_rank,
             counts[2] = static_cast<int64_t>(G.jobs.size());
             counts[3] = G.scratch_elems;
         }
+    });
+}
+
+int xb_contract_plan_emulate(xb_ctx* ctx, xb_basis* const* a_domain, int a_rank, xb_basis* const* a_codomain, int a_corank, const int* labels_a,
+                             xb_basis* const* b_domain, int b_rank, xb_basis* const* b_codomain, int b_corank, const int* labels_b, int res_rank, int table_form,
+                             const double* a, int64_t n_a, const double* b, int64_t n_b, double* c, int64_t n_c)
+{
+    return guard([&] {
+        need(ctx, "ctx");
+        need(a, "a");
+        need(b, "b");
+        need(c, "c");
+        Context& C = ctx->impl;
+        if(!C.planning_only()) throw std::invalid_argument("xb_contract_plan_emulate: test support of planning-only contexts (the device path is xb_contract)");
+        std::vector<BasisPtr> ad, ac, bd, bc;
+        collect_bases(a_domain, a_rank, a_codomain, a_corank, ad, ac);
+        collect_bases(b_domain, b_rank, b_codomain, b_corank, bd, bc);
+        LayoutPtr LA = C.layout(ad, ac), LB = C.layout(bd, bc);
+        if(n_a != LA->size || n_b != LB->size) throw std::invalid_argument("xb_contract_plan_emulate: operand sizes do not match the tensors");
+        const ContractPerms cp = contract_permutations(a_rank, a_corank, std::vector<int>(labels_a, labels_a + a_rank + a_corank), b_rank, b_corank,
+                                                       std::vector<int>(labels_b, labels_b + b_rank + b_corank), res_rank);
+        auto walk = [&](const LayoutPtr& L, int shift, const std::vector<int>& p, const double* src, int64_t n_src, LayoutPtr& out_layout) {
+            auto plan = C.permute_plan(L, shift, p, false);
+            out_layout = plan->out;
+            std::vector<double> dst(static_cast<size_t>(plan->out->size), std::numeric_limits<double>::quiet_NaN());
+            const bool has_tables = plan->host && !plan->host->ltile_task.empty();
+            C.emulate_permute_plan(*plan, (table_form != 0 && has_tables) ? 1 : 0, src, n_src, dst.data(), static_cast<int64_t>(dst.size()));
+            return dst;
+        };
+        LayoutPtr L1, L2, L3;
+        const std::vector<double> ap = walk(LA, cp.shift1, cp.p1, a, n_a, L1);
+        const std::vector<double> bp = walk(LB, cp.shift2, cp.p2, b, n_b, L2);
+        LayoutPtr LO = C.layout(L1->dom, L2->cod);
+        std::vector<double> prod(static_cast<size_t>(LO->size), 0.0);
+        emulate_gemm_lists(build_gemm_lists(multiply_problems(*L1, false, *L2, false, *LO), C.sm_count), ap.data(), static_cast<int64_t>(ap.size()), bp.data(),
+                           static_cast<int64_t>(bp.size()), prod.data(), static_cast<int64_t>(prod.size()));
+        const std::vector<double> res = walk(LO, cp.shiftres, cp.pres, prod.data(), static_cast<int64_t>(prod.size()), L3);
+        if(n_c != static_cast<int64_t>(res.size())) throw std::invalid_argument("xb_contract_plan_emulate: result size does not match the contraction");
+        std::copy(res.begin(), res.end(), c);
     });
 }
 

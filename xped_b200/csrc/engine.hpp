@@ -240,6 +240,8 @@ struct GemmLists
     double flops = 0.0;
 };
 GemmLists build_gemm_lists(const std::vector<GemmItem>& problems, int sm_count);
+struct ContractPerms { std::vector<int> p1, p2, pres; int shift1 = 0, shift2 = 0, shiftres = 0; };
+ContractPerms contract_permutations(int rank_a, int corank_a, const std::vector<int>& l1, int rank_b, int corank_b, const std::vector<int>& l2, int res_rank);
 void emulate_gemm_lists(const GemmLists& G, const double* A, int64_t n_a, const double* B, int64_t n_b, double* C, int64_t n_c);   // test support
 std::vector<GemmItem> multiply_problems(const Layout& LA, bool adj_a, const Layout& LB, bool adj_b, const Layout& LO);
 

@@ -399,11 +399,13 @@ Tensor* Context::multiply_sectors(const Tensor& a, bool adj_a, const Tensor& b, 
 
 // ------------------------------------------------------------------------------------------------ contract
 // Tensor::contract (include/Xped/Core/Tensor.hpp:328-351) with get_permutations (Util/Constfct.hpp:55-109).
-Tensor* Context::contract(const Tensor& a, const std::vector<int>& l1, const Tensor& b, const std::vector<int>& l2, int res_rank)
+// get_permutations (include/Xped/Util/Constfct.hpp:55-109) for contract<a1, a2, ResRank>: the leg permutations / shifts that turn the contraction into
+// permute(a) * permute(b) followed by a permute of the product.  Host metadata only.
+ContractPerms contract_permutations(int rank_a, int corank_a, const std::vector<int>& l1, int rank_b, int corank_b, const std::vector<int>& l2, int res_rank)
 {
+    ContractPerms cp;
     const int r1 = static_cast<int>(l1.size()), r2 = static_cast<int>(l2.size());
-    if(r1 != a.layout->rank() + a.layout->corank() || r2 != b.layout->rank() + b.layout->corank())
-        throw std::invalid_argument("contract: label array length != number of legs");
+    if(r1 != rank_a + corank_a || r2 != rank_b + corank_b) throw std::invalid_argument("contract: label array length != number of legs");
     const int max1 = std::max(0, r1 ? *std::max_element(l1.begin(), l1.end()) : 0);
     const int max2 = std::max(0, r2 ? *std::max_element(l2.begin(), l2.end()) : 0);
     if(max1 != max2) throw std::invalid_argument("contract: contracted labels do not match");
@@ -412,7 +414,8 @@ Tensor* Context::contract(const Tensor& a, const std::vector<int>& l1, const Ten
         if(it == v.end()) throw std::invalid_argument("contract: missing contraction label");
         return static_cast<int>(it - v.begin());
     };
-    std::vector<int> p1, p2, con1;
+    std::vector<int>&p1 = cp.p1, &p2 = cp.p2, &pres = cp.pres;
+    std::vector<int> con1;
     for(int k = 1; k <= max2; ++k) p2.push_back(pos(l2, k));
     for(int i = 0; i < r2; ++i)
         if(std::find(p2.begin(), p2.begin() + max2, i) == p2.begin() + max2) p2.push_back(i);
@@ -425,12 +428,20 @@ Tensor* Context::contract(const Tensor& a, const std::vector<int>& l1, const Ten
         if(x < 0) open.push_back(x);
     for(int x : l2)
         if(x < 0) open.push_back(x);
-    std::vector<int> pres(open.size());
+    pres.resize(open.size());
     std::iota(pres.begin(), pres.end(), 0);
     std::sort(pres.begin(), pres.end(), [&](int i, int j) { return open[i] > open[j]; });
-    const int shift1 = a.layout->rank() - r1 + max1;
-    const int shift2 = b.layout->rank() - max2;
-    const int shiftres = r1 - max1 - res_rank;
+    cp.shift1 = rank_a - r1 + max1;
+    cp.shift2 = rank_b - max2;
+    cp.shiftres = r1 - max1 - res_rank;
+    return cp;
+}
+
+Tensor* Context::contract(const Tensor& a, const std::vector<int>& l1, const Tensor& b, const std::vector<int>& l2, int res_rank)
+{
+    const ContractPerms cp = contract_permutations(a.layout->rank(), a.layout->corank(), l1, b.layout->rank(), b.layout->corank(), l2, res_rank);
+    const std::vector<int>&p1 = cp.p1, &p2 = cp.p2, &pres = cp.pres;
+    const int shift1 = cp.shift1, shift2 = cp.shift2, shiftres = cp.shiftres;
 
     std::unique_ptr<Tensor> ap(permute(a, shift1, p1));
     std::unique_ptr<Tensor> bp(permute(b, shift2, p2));

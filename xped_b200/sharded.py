@@ -403,3 +403,15 @@ def multiply_plan_emulate(ctx, a_dom, a_cod, adj_a, b_dom, b_cod, adj_b, a_data,
                                            _handles(b_cod), len(b_cod), int(bool(adj_b)), int(sm_count), a_data.ctypes.data_as(DP), a_data.size,
                                            b_data.ctypes.data_as(DP), b_data.size, c.ctypes.data_as(DP), c.size, counts))
     return c, dict(tiles128=counts[0], tiles64=counts[1], jobs=counts[2], scratch=counts[3])
+
+
+def contract_plan_emulate(ctx, a_dom, a_cod, labels_a, b_dom, b_cod, labels_b, res_rank, a_data, b_data, n_c, table_form=True):
+    """TEST SUPPORT (planning-only contexts): contract<labels_a, labels_b, res_rank> lowered like the device path (two operand permutes, grouped product,
+    permute of the result), every plan / list walked on the host; returns the `m_data` image of the result"""
+    a_data, b_data = np.ascontiguousarray(a_data, dtype=np.float64), np.ascontiguousarray(b_data, dtype=np.float64)
+    c = np.full(int(n_c), np.nan)
+    DP = C.POINTER(C.c_double)
+    check(ctx.lib.xb_contract_plan_emulate(ctx.h, _handles(a_dom), len(a_dom), _handles(a_cod), len(a_cod), _ints(labels_a), _handles(b_dom), len(b_dom),
+                                           _handles(b_cod), len(b_cod), _ints(labels_b), int(res_rank), int(bool(table_form)), a_data.ctypes.data_as(DP), a_data.size,
+                                           b_data.ctypes.data_as(DP), b_data.size, c.ctypes.data_as(DP), c.size))
+    return c

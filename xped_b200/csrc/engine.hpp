@@ -395,6 +395,7 @@ public:
     // statistics for bench / gpu_launches
     int64_t launches = 0;
     int64_t plan_hits = 0, plan_misses = 0;
+    int64_t host_table_bytes = 0;   // planning-only contexts: bytes of the host copies kept with the cached plans (bounded: 1 GB, then plans go without)
 
     // ---- live per-category device timing (bench.py roofline): CUDA event pairs on `stream` around each
     // launch group while profiling is enabled; prof_read() synchronises, sums and resets.

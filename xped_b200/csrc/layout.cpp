@@ -1236,7 +1236,13 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
             plan->lut_table_bytes = table_bytes_all;
         }
     }
-    if(ctx.planning_only()) {   // no device: keep the tables for the host walk of the CPU tests
+    if(ctx.planning_only()) {   // no device: keep the tables for the host walk of the CPU tests (bounded; plans beyond the bound simply have none)
+        const int64_t bytes = static_cast<int64_t>(h_tasks.size() * sizeof(PermTask) + h_srcs.size() * sizeof(PermSrc) + h_tiles.size() * sizeof(PermTile)) +
+                              (plan->n_ltiles > 0 ? static_cast<int64_t>(lut.tasks.size() * sizeof(LutTask) + lut.tsrc.size() * sizeof(LutTileSrc) + lut.tile_task.size() * 12 +
+                                                                         lut.tab_int.size() * 4 + lut.tab_pos.size() * 2)
+                                                  : 0);
+        if(ctx.host_table_bytes + bytes > (1ll << 30)) return;
+        ctx.host_table_bytes += bytes;
         auto H = std::make_shared<PlanHostTables>();
         H->tasks = h_tasks;
         H->srcs = h_srcs;
@@ -1694,7 +1700,10 @@ std::shared_ptr<PermutePlan> Context::permute_plan(const LayoutPtr& in, int shif
         std::fprintf(stderr, "[plan prof] tasks %d tiles %d: build_tasks %.2f ms, lower_tasks %.2f ms\n", plan->n_tasks, plan->n_tiles,
                      std::chrono::duration<double, std::milli>(tp1 - tp0).count(), std::chrono::duration<double, std::milli>(tp2 - tp1).count());
     }
-    if(plan_cache_.size() >= 4096) plan_cache_.clear();
+    if(plan_cache_.size() >= 4096) {
+        plan_cache_.clear();
+        host_table_bytes = 0;
+    }
     plan_cache_.emplace(key, plan);
     return plan;
 }

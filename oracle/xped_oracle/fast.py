@@ -55,7 +55,7 @@ def _basis_sig(b):
 
 
 def _sig(t: Tensor):
-    return (id(t.sym), tuple(_basis_sig(b) for b in t.uncoupled_domain), tuple(_basis_sig(b) for b in t.uncoupled_codomain), tuple(tuple(q) for q in t.sector))
+    return (t.sym.name(), tuple(_basis_sig(b) for b in t.uncoupled_domain), tuple(_basis_sig(b) for b in t.uncoupled_codomain), tuple(tuple(q) for q in t.sector))
 
 
 def _strides(rows, dt, ct):

@@ -20,7 +20,7 @@ import numpy as np
 from .basis import FusionTree, Qbasis, build_FusionTree, treepair_permute
 from .symmetry import Symmetry
 
-_PERMUTE_CACHE = {}   # (sym id, shift, pi, t1, t2) -> {(t1', t2'): coeff}; cf. XPED_CACHE_PERMUTE_OUTPUT (treepair.cpp:170-176)
+_PERMUTE_CACHE = {}   # (symmetry name, shift, pi, t1, t2) -> {(t1', t2'): coeff}; cf. XPED_CACHE_PERMUTE_OUTPUT (treepair.cpp:170-176)
 
 
 def get_permutations(a1, rank1, a2, rank2, rankres):
@@ -176,7 +176,7 @@ class Tensor:
         return [pick(i, True) for i in range(newR)], [pick(i, False) for i in range(newR, n)]
 
     def _pairs(self, shift, pi, dt, ct):
-        key = (id(self.sym), shift, tuple(pi), dt, ct, dt.IS_DUAL, ct.IS_DUAL)
+        key = (self.sym.name(), shift, tuple(pi), dt, ct, dt.IS_DUAL, ct.IS_DUAL)   # (the symmetry by CONTENT: the id of a collected Symmetry object is reused)
         v = _PERMUTE_CACHE.get(key)
         if v is None:
             v = treepair_permute(self.sym, shift, dt, ct, pi)

@@ -180,7 +180,7 @@ int xb_permute_plan_stats(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_bas
 int xb_permute_plan_census(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n, int64_t out[6]);
 /* TEST SUPPORT, planning-only contexts only (no GPU; the tensors of such a context own no data, so no product path can reach this): applies the HOST tables
  * of the plan of permute<shift,p> (adjoint != 0: permute_adj) to host arrays the way the kernels address them -- form 0: tile list of the LSU form, form 1:
- * table-driven form -- with every offset bounds-checked and every destination element written exactly once.  `src` / `dst` are the `m_data` images of the
+ * table-driven form, form 2: cp.async.bulk form (every bulk operation and the transposing pass; alignment and mbarrier byte counts checked) -- with every offset bounds-checked and every destination element written exactly once.  `src` / `dst` are the `m_data` images of the
  * input / output tensor.  The CPU tests compare the result with the oracle's Tensor::permute (src/Core/Tensor.cpp:83-214). */
 int xb_permute_plan_emulate(xb_ctx* ctx, xb_basis* const* domain, int rank, xb_basis* const* codomain, int corank, int shift, const int* p, int n, int adjoint,
                             int form, const double* src, int64_t n_src, double* dst, int64_t n_dst);

@@ -123,3 +123,54 @@ def test_w3_corner_plans_both_forms_agree_at_full_size():
         lut = permute_plan_emulate(ctx, [e, a, a], [e, a, a], shift, p, src, n, 1)
         assert not np.isnan(lsu).any() and np.array_equal(lsu, lut), (shift, p)
     ctx.close()
+
+
+@pytest.mark.parametrize("name,dim", [("U1", 4), ("U1", 8), ("U1", 12), ("Z3", 10), ("U0", 8), ("U0", 48), ("fU1", 8)])
+def test_bulk_form_all_24_permutations(name, dim):
+    """the cp.async.bulk form (the kernel behind the headline HBM roofline): every bulk operation of every tile is replayed on the host -- source runs into the
+    staging buffer, transposing pass, destination runs out of it -- with the hardware's demands on a bulk copy checked (16-byte aligned addresses and sizes,
+    inside the staging buffer) and the byte count announced to the mbarrier compared with what the loads deliver.  Bit-exact against the oracle for bosonic
+    symmetries; fermionic plans carry -1 coefficients through the transposing pass."""
+    ctx, osym = PlanningContext(SPECS[name]), xo.Symmetry.from_spec(SPECS[name])
+    ctx.spec = SPECS[name]
+    if name in ("U1", "fU1"):
+        B = [((q,), dim) for q in range(-2, 3)]
+    elif name == "Z3":
+        B = [((q,), dim) for q in range(3)]
+    else:
+        B = [((), dim)]
+    o = oracle_tensor(osym, [B, B], [B, B], 81)
+    gB = ctx.basis(B)
+    used = 0
+    for p in itertools.permutations(range(4)):
+        for shift in (0, 1, -1, 2, -2):
+            st = permute_plan_stats(ctx, [gB, gB], [gB, gB], shift, p)
+            if st["identity"] or st["bulk_tiles"] == 0:
+                continue
+            ref = o.permute(shift, p)
+            out = permute_plan_emulate(ctx, [gB, gB], [gB, gB], shift, p, o.data, ref.plainSize(), 2)
+            assert np.array_equal(out, ref.data), f"{name} dim {dim} bulk permute<{shift},{p}>"
+            used += 1
+    assert used > (0 if dim < 8 else 60), used   # runs shorter than 8 doubles are not worth a bulk operation: dim 4 has few or no bulk plans
+    ctx.close()
+
+
+def test_bulk_form_w4_shaped_tensor():
+    """configs[4] at a reduced size: U(1) Tensor<2,2>, leg q = -4..4 x 8 (17 sectors, 2.0 M elements), the five permutes x three shifts of the W4 bench set"""
+    ctx, osym = PlanningContext(SPECS["U1"]), xo.Symmetry.U1()
+    B = [((q,), 8) for q in range(-4, 5)]
+    o = oracle_tensor(osym, [B, B], [B, B], 7)
+    from xped_oracle import fast
+    fast.install()
+    try:
+        gB = ctx.basis(B)
+        for p in [(1, 0, 2, 3), (0, 1, 3, 2), (2, 3, 0, 1), (0, 2, 1, 3), (3, 2, 1, 0)]:
+            for shift in (0, 1, -2):
+                st = permute_plan_stats(ctx, [gB, gB], [gB, gB], shift, p)
+                assert st["bulk_tiles"] > 0
+                ref = o.permute(shift, p)
+                out = permute_plan_emulate(ctx, [gB, gB], [gB, gB], shift, p, o.data, ref.plainSize(), 2)
+                assert np.array_equal(out, ref.data), (p, shift)
+    finally:
+        fast.uninstall()
+    ctx.close()

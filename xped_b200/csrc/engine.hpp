@@ -142,6 +142,8 @@ struct PlanHostTables
     std::vector<PermTask> tasks;
     std::vector<PermSrc> srcs;
     std::vector<PermTile> tiles;
+    std::vector<BulkTask> btasks;   // bulk form (empty if the plan does not qualify)
+    std::vector<PermTile> btiles;
     std::vector<LutTask> ltasks;
     std::vector<LutTileSrc> ltsrc;
     std::vector<int> ltile_task;
@@ -315,7 +317,7 @@ public:
     LayoutPtr layout(const std::vector<BasisPtr>& dom, const std::vector<BasisPtr>& cod);
     LayoutPtr layout_custom(const std::vector<BasisPtr>& dom, const std::vector<BasisPtr>& cod, const std::vector<Q>& sectors);
     std::shared_ptr<PermutePlan> permute_plan(const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan);
-    // test support: applies the HOST tables of a plan of a planning-only context to host arrays (form 0: tile list of the LSU form, 1: table-driven form)
+    // test support: applies the HOST tables of a plan of a planning-only context to host arrays (form 0: tile list of the LSU form, 1: table-driven form, 2: cp.async.bulk form)
     void emulate_permute_plan(const PermutePlan& plan, int form, const double* src, int64_t n_src, double* dst, int64_t n_dst) const;
     // sector-sharded permute: exchange plan of rank `rank` for the global tensor layout `in` (cached)
     std::shared_ptr<DistPermutePlan> dist_permute_plan(const LayoutPtr& in, int shift, const std::vector<int>& pi, bool adjoint_plan,

@@ -1247,6 +1247,10 @@ static void lower_tasks(Context& ctx, const std::vector<DstTask>& tasks, const s
         H->tasks = h_tasks;
         H->srcs = h_srcs;
         H->tiles = h_tiles;
+        if(bulk_ok && !h_btiles.empty()) {
+            H->btasks = h_btasks;
+            H->btiles = h_btiles;
+        }
         if(plan->n_ltiles > 0) {
             H->ltasks = lut.tasks;
             H->ltsrc = lut.tsrc;
@@ -1645,8 +1649,110 @@ void Context::emulate_permute_plan(const PermutePlan& plan, int form, const doub
             for(int e = 0; e < T.vol; ++e)   // write phase: destination order
                 put(H.ltile_dst[ti] + H.lut_int.at(static_cast<size_t>(T.doff_tab) + e), staged.at(H.lut_pos.at(static_cast<size_t>(T.spos_tab) + e)));
         }
+    } else if(form == 2) {
+        // cp.async.bulk form: every bulk operation of permute_bulk_kernel (one per leader run: source runs into the staging buffer, destination runs out of it) and
+        // its transposing pass in shared memory, with what the hardware demands of a bulk copy checked on the way -- 16-byte aligned global and shared addresses,
+        // byte counts that are multiples of 16, operations inside the staging buffer -- and the byte count the CTA announces to its mbarrier (expect_tx) compared with
+        // what the loads deliver (a mismatch is a hang on the device).
+        if(H.btiles.empty()) throw std::invalid_argument("emulate_permute_plan: the plan has no bulk form");
+        struct Run { long long rel; int smem; unsigned bytes; };
+        auto prep = [](const BulkTask& T, bool copy, bool is_load, int r) {   // permute_bulk_kernel: prep (divisions instead of magic numbers)
+            Run R{0, 0, 0u};
+            const int nrun = copy ? T.nz : T.nz * (is_load ? T.wx : T.wy);
+            if(r >= nrun) return R;
+            const int group = is_load ? T.mrg_load : T.mrg_store;
+            const int* gs = is_load ? T.sstride : T.dstride;
+            int z = r, count = 1, group_index = r, zc_in_group = 0;
+            bool leader = true;
+            if(!copy) {
+                if(is_load && T.nzc > 1) {
+                    const int t = r / T.nzc;
+                    zc_in_group = r - t * T.nzc;
+                    const int zr = t / T.wx, x = t - zr * T.wx;
+                    group_index = t;
+                    z = zr * T.nzc + zc_in_group;
+                    R.rel += static_cast<long long>(x) * gs[0];
+                    leader = zc_in_group == 0;
+                    count = T.nzc;
+                } else {
+                    const int wi = is_load ? T.wx : T.wy;
+                    z = r / wi;
+                    const int inner = r - z * wi;
+                    R.rel += static_cast<long long>(inner) * gs[is_load ? 0 : T.ls];
+                    if(group > 1) {
+                        leader = inner == 0;
+                        count = group;
+                    }
+                }
+            }
+            for(int i = 0; i < T.nzleg; ++i) {
+                const int l = T.zleg[i];
+                const int q = z / T.w[l], c = z - q * T.w[l];
+                z = q;
+                R.rel += static_cast<long long>(c) * gs[l];
+                if(copy && i == 0 && group > 1) {
+                    leader = c == 0;
+                    count = group;
+                }
+            }
+            if(leader) R.bytes = static_cast<unsigned>((is_load ? (copy ? T.wx : T.wy) : T.wx) * count) * 8u;
+            R.smem = (!copy && is_load) ? group_index * T.gp + zc_in_group * T.wy : r * (is_load ? T.rs_s : T.rs_d);
+            return R;
+        };
+        const double nan = std::numeric_limits<double>::quiet_NaN();
+        std::vector<double> S(BULK_BUF_ELEMS), D(BULK_BUF_ELEMS);
+        for(const PermTile& tile : H.btiles) {
+            const BulkTask& T = H.btasks.at(static_cast<size_t>(tile.task));
+            const bool copy = T.ls == 0;
+            long long os = T.src_off, od = T.dst_off & PERM_OFF_MASK, tile_elems = 1;
+            for(int l = 0; l < T.nleg; ++l) {
+                if(T.dims[l] % T.w[l] != 0) throw std::runtime_error("emulate_permute_plan: bulk tile extent does not divide the leg");
+                os += static_cast<long long>(tile.c[l]) * T.w[l] * T.sstride[l];
+                od += static_cast<long long>(tile.c[l]) * T.w[l] * T.dstride[l];
+                tile_elems *= T.w[l];
+            }
+            std::fill(S.begin(), S.end(), nan);
+            std::fill(D.begin(), D.end(), nan);
+            const int nload = copy ? T.nz : T.nz * T.wx, nstore = copy ? T.nz : T.nz * T.wy;
+            if(nload > 2 * BULK_THREADS || nstore > 2 * BULK_THREADS) throw std::runtime_error("emulate_permute_plan: more runs than two per thread");
+            long long loaded = 0;
+            for(int r = 0; r < nload; ++r) {
+                const Run R = prep(T, copy, true, r);
+                if(!R.bytes) continue;
+                const long long g = os + R.rel;
+                if((g & 1) || (R.smem & 1) || (R.bytes & 15u)) throw std::runtime_error("emulate_permute_plan: bulk load not 16-byte aligned");
+                const int cnt = static_cast<int>(R.bytes / 8);
+                if(R.smem < 0 || R.smem + cnt > BULK_BUF_ELEMS) throw std::runtime_error("emulate_permute_plan: bulk load outside the staging buffer");
+                for(int i = 0; i < cnt; ++i) S[static_cast<size_t>(R.smem + i)] = get(g + i);
+                loaded += cnt;
+            }
+            if(loaded != tile_elems) throw std::runtime_error("emulate_permute_plan: loads deliver " + std::to_string(loaded) + " elements, the barrier expects " + std::to_string(tile_elems));
+            const std::vector<double>* out = &S;
+            if(!copy) {   // transposing pass: D[(z wy + y) rs_d + x] = coeff * S[(z_rest wx + x) gp + zc wy + y]
+                for(int z = 0; z < T.nz; ++z) {
+                    const int zr = z / T.nzc, zc = z - zr * T.nzc;
+                    for(int x = 0; x < T.wx; ++x)
+                        for(int y = 0; y < T.wy; ++y) {
+                            const int si = (zr * T.wx + x) * T.gp + zc * T.wy + y, di = (z * T.wy + y) * T.rs_d + x;
+                            if(si < 0 || si >= BULK_BUF_ELEMS || di < 0 || di >= BULK_BUF_ELEMS) throw std::runtime_error("emulate_permute_plan: transposing pass outside the staging buffers");
+                            D[static_cast<size_t>(di)] = T.coeff * S[static_cast<size_t>(si)];
+                        }
+                }
+                out = &D;
+            } else if(T.coeff != 1.0)
+                throw std::runtime_error("emulate_permute_plan: copy mode with a coefficient");
+            for(int r = 0; r < nstore; ++r) {
+                const Run R = prep(T, copy, false, r);
+                if(!R.bytes) continue;
+                const long long g = od + R.rel;
+                if((g & 1) || (R.smem & 1) || (R.bytes & 15u)) throw std::runtime_error("emulate_permute_plan: bulk store not 16-byte aligned");
+                const int cnt = static_cast<int>(R.bytes / 8);
+                if(R.smem < 0 || R.smem + cnt > BULK_BUF_ELEMS) throw std::runtime_error("emulate_permute_plan: bulk store outside the staging buffer");
+                for(int i = 0; i < cnt; ++i) put(g + i, (*out)[static_cast<size_t>(R.smem + i)]);
+            }
+        }
     } else
-        throw std::invalid_argument("emulate_permute_plan: form must be 0 (tile list) or 1 (table-driven)");
+        throw std::invalid_argument("emulate_permute_plan: form must be 0 (tile list), 1 (table-driven) or 2 (bulk)");
     for(int64_t o = 0; o < n_dst; ++o)
         if(!written[static_cast<size_t>(o)]) throw std::runtime_error("emulate_permute_plan: destination element " + std::to_string(o) + " never written");
 }

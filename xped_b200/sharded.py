@@ -383,7 +383,7 @@ def permute_plan_stats(ctx, domain, codomain, shift, p):
 
 def permute_plan_emulate(ctx, domain, codomain, shift, p, src, n_dst, form, adjoint=False):
     """TEST SUPPORT (planning-only contexts): walks the host tables of the permute plan over the `m_data` image `src` like the kernels do
-    (form 0: tile list of the LSU form, 1: table-driven form) and returns the `m_data` image of the result"""
+    (form 0: tile list of the LSU form, 1: table-driven form, 2: cp.async.bulk form) and returns the `m_data` image of the result"""
     src = np.ascontiguousarray(src, dtype=np.float64)
     dst = np.full(int(n_dst), np.nan)
     DP = C.POINTER(C.c_double)

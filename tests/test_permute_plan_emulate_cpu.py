@@ -155,10 +155,12 @@ def test_bulk_form_all_24_permutations(name, dim):
     ctx.close()
 
 
-def test_bulk_form_w4_shaped_tensor():
-    """configs[4] at a reduced size: U(1) Tensor<2,2>, leg q = -4..4 x 8 (17 sectors, 2.0 M elements), the five permutes x three shifts of the W4 bench set"""
+@pytest.mark.parametrize("qmax,dim", [(4, 8), (1, 24)])
+def test_bulk_form_w4_shaped_tensor(qmax, dim):
+    """configs[4] at reduced sizes: U(1) Tensor<2,2>, leg q = -4..4 x 8 (17 sectors, 2.0 M elements) and q = -1..1 x 24 (the W4 multiplicity: the tile extents
+    the 1.30 GB tensor gets), the five permutes x three shifts of the W4 bench set"""
     ctx, osym = PlanningContext(SPECS["U1"]), xo.Symmetry.U1()
-    B = [((q,), 8) for q in range(-4, 5)]
+    B = [((q,), dim) for q in range(-qmax, qmax + 1)]
     o = oracle_tensor(osym, [B, B], [B, B], 7)
     from xped_oracle import fast
     fast.install()
